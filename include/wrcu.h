@@ -1,0 +1,252 @@
+/* wrcu.h — C ABI of the B200-native WebRender frame-draw backend.
+ *
+ * This is the drop-in boundary for ONE path of servo/webrender: the render
+ * thread's `Renderer::draw_frame` (webrender/src/renderer/mod.rs:4525) and the
+ * device calls it makes — `draw_instanced_batch` (mod.rs:2022), target binds,
+ * clears, clip-mask batches and the final tile composite.  In the reference
+ * those calls go through `Device` to the `gleam::gl::Gl` trait object
+ * (renderer/init.rs:292-297); with the software rasteriser the trait is
+ * implemented by 99 `extern "C"` symbols (swgl/src/swgl_fns.rs:23-320 →
+ * swgl/src/gl.cc:1080-2851).  This header is the "thin FFI" version of that
+ * seam (SURVEY.md §8b option 2): every entry point names the reference call
+ * sequence it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *  - Every function returns WRCU_OK (0) or a negative wrcu_status; nothing
+ *    throws or aborts across the ABI.  Like GL (gl.cc:1126-1134) the context
+ *    also keeps a sticky error readable with wrcu_get_error().
+ *  - The host owns every array it passes in; the backend copies what it needs
+ *    before the call returns (the reference copies at glBufferData time,
+ *    device/gl.rs:3552-3600).
+ *  - Work is queued on a CUDA stream; wrcu_read_pixels / wrcu_finish
+ *    synchronise (the SWGL equivalents are synchronous, gl.cc:2802).
+ *  - One context per host thread, like `MakeCurrent` (gl.cc:2808).
+ *  - Colour targets are "RGBA8" with B,G,R,A byte order in memory exactly as
+ *    SWGL stores them (swgl/src/texture.h:85-90); alpha targets are R8.
+ */
+#ifndef WRCU_H
+#define WRCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WRCU_ABI_VERSION 1
+
+typedef struct wrcu_ctx wrcu_ctx;
+typedef uint32_t wrcu_tex; /* 0 = none; like a GLuint texture name */
+
+typedef enum wrcu_status {
+  WRCU_OK = 0,
+  WRCU_ERR_INVALID = -1,      /* bad argument / unknown handle            */
+  WRCU_ERR_OOM = -2,          /* GL_OUT_OF_MEMORY (gl.cc:1134)            */
+  WRCU_ERR_CUDA = -3,         /* a CUDA runtime call failed               */
+  WRCU_ERR_UNSUPPORTED = -4,  /* valid in the reference, not built here   */
+  WRCU_ERR_NO_DEVICE = -5     /* no usable CUDA device (never falls back) */
+} wrcu_status;
+
+/* Texture formats (gl.cc:216-260 bytes_for_internal_format). */
+typedef enum wrcu_format {
+  WRCU_FMT_RGBA8 = 1,   /* 4 B/px, BGRA in memory                         */
+  WRCU_FMT_R8 = 2,      /* 1 B/px                                         */
+  WRCU_FMT_RGBAF32 = 3, /* 16 B/texel (data textures, GPU cache)          */
+  WRCU_FMT_RGBAI32 = 4, /* 16 B/texel                                     */
+  WRCU_FMT_DEPTH24 = 5  /* 4 B/px, 24-bit depth (rasterize.h:37)          */
+} wrcu_format;
+
+typedef enum wrcu_filter { WRCU_NEAREST = 0, WRCU_LINEAR = 1 } wrcu_filter;
+
+/* Batch kinds = the reference's shader programs (SURVEY.md §2.3, Appendix C;
+ * BatchKind in webrender/src/batch.rs:60-86, shader table renderer/shade.rs). */
+typedef enum wrcu_kind {
+  WRCU_KIND_QUAD_TEXTURED = 1,         /* ps_quad_textured                 */
+  WRCU_KIND_QUAD_MASK = 2,             /* ps_quad_mask [FAST_PATH]         */
+  WRCU_KIND_BRUSH_SOLID = 3,           /* brush_solid                      */
+  WRCU_KIND_BRUSH_IMAGE = 4,           /* brush_image                      */
+  WRCU_KIND_BRUSH_LINEAR_GRADIENT = 5, /* brush_linear_gradient            */
+  WRCU_KIND_BRUSH_BLEND = 6,           /* brush_blend                      */
+  WRCU_KIND_BRUSH_MIX_BLEND = 7,       /* brush_mix_blend                  */
+  WRCU_KIND_BRUSH_OPACITY = 8,         /* brush_opacity                    */
+  WRCU_KIND_TEXT_RUN = 9,              /* ps_text_run                      */
+  WRCU_KIND_CLIP_RECTANGLE = 10,       /* cs_clip_rectangle [FAST_PATH]    */
+  WRCU_KIND_CLIP_BOX_SHADOW = 11,      /* cs_clip_box_shadow               */
+  WRCU_KIND_COMPOSITE = 12,            /* composite [FAST_PATH]            */
+  WRCU_KIND_CLEAR = 13,                /* ps_clear                         */
+  WRCU_KIND_BLUR = 14,                 /* cs_blur      */
+  WRCU_KIND_SCALE = 15                 /* cs_scale                         */
+} wrcu_kind;
+
+/* Shader feature bits (webrender_build/src/shader_features.rs:64-247). */
+enum {
+  WRCU_FEAT_ALPHA_PASS = 1u << 0,
+  WRCU_FEAT_FAST_PATH = 1u << 1,
+  WRCU_FEAT_ANTIALIASING = 1u << 2,
+  WRCU_FEAT_REPETITION = 1u << 3,
+  WRCU_FEAT_DUAL_SOURCE_BLENDING = 1u << 4,
+  WRCU_FEAT_ADVANCED_BLEND = 1u << 5,
+  WRCU_FEAT_GLYPH_TRANSFORM = 1u << 6,
+  WRCU_FEAT_TEXTURE_2D = 1u << 7
+};
+
+/* Blend keys: exactly the set the reference's blend stage implements
+ * (FOR_EACH_BLEND_KEY, swgl/src/gl.cc:617-649), i.e. what the Device blend
+ * setters reduce to (device/gl.rs:3901-4017 → gl.cc:1240-1335).  Blending
+ * disabled = WRCU_BLEND_NONE. */
+typedef enum wrcu_blend {
+  WRCU_BLEND_NONE = 0,              /* ONE, ZERO / blending off            */
+  WRCU_BLEND_ALPHA = 1,             /* SRC_ALPHA,1-SRC_ALPHA,ONE,1-SRC_ALPHA */
+  WRCU_BLEND_PREMULTIPLIED_ALPHA = 2,   /* ONE, 1-SRC_ALPHA                */
+  WRCU_BLEND_SUBPIXEL_PASS0 = 3,        /* ZERO, 1-SRC_COLOR               */
+  WRCU_BLEND_SUBPIXEL_PASS0_KEEP_A = 4, /* ZERO,1-SRC_COLOR,ZERO,ONE       */
+  WRCU_BLEND_PREMULTIPLIED_DEST_OUT = 5, /* ZERO, 1-SRC_ALPHA              */
+  WRCU_BLEND_MULTIPLY = 6,              /* ZERO, SRC_COLOR (clip masks)    */
+  WRCU_BLEND_PLUS_LIGHTER = 7,          /* ONE, ONE                        */
+  WRCU_BLEND_ADD_KEEP_ALPHA_OVER = 8,   /* ONE,ONE,ONE,1-SRC_ALPHA         */
+  WRCU_BLEND_DST_ALPHA_ADD = 9,         /* 1-DST_ALPHA,ONE,ZERO,ONE        */
+  WRCU_BLEND_CONSTANT_COLOR = 10,       /* CONSTANT_COLOR, 1-SRC_COLOR     */
+  WRCU_BLEND_SUBPIXEL_DUAL_SOURCE = 11, /* ONE, 1-SRC1_COLOR               */
+  WRCU_BLEND_MIN = 12,
+  WRCU_BLEND_MAX = 13,
+  /* KHR_blend_equation_advanced (MixBlendMode → device/gl.rs:3996-4017) */
+  WRCU_BLEND_ADV_MULTIPLY = 14,
+  WRCU_BLEND_ADV_SCREEN = 15,
+  WRCU_BLEND_ADV_OVERLAY = 16,
+  WRCU_BLEND_ADV_DARKEN = 17,
+  WRCU_BLEND_ADV_LIGHTEN = 18,
+  WRCU_BLEND_ADV_COLOR_DODGE = 19,
+  WRCU_BLEND_ADV_COLOR_BURN = 20,
+  WRCU_BLEND_ADV_HARD_LIGHT = 21,
+  WRCU_BLEND_ADV_SOFT_LIGHT = 22,
+  WRCU_BLEND_ADV_DIFFERENCE = 23,
+  WRCU_BLEND_ADV_EXCLUSION = 24,
+  WRCU_BLEND_ADV_HUE = 25,
+  WRCU_BLEND_ADV_SATURATION = 26,
+  WRCU_BLEND_ADV_COLOR = 27,
+  WRCU_BLEND_ADV_LUMINOSITY = 28,
+  WRCU_BLEND__COUNT
+} wrcu_blend;
+
+typedef enum wrcu_depth {
+  WRCU_DEPTH_OFF = 0,          /* depth test disabled                      */
+  WRCU_DEPTH_TEST = 1,         /* LEQUAL test, no write (alpha pass)       */
+  WRCU_DEPTH_TEST_WRITE = 2    /* LEQUAL test + write (opaque pass)        */
+} wrcu_depth;
+
+/* Per-frame data tables = the 1024-texel-wide data textures the reference
+ * uploads in bind_frame_data / prepare_gpu_cache (renderer/mod.rs:4418,
+ * 1536; renderer/vertex.rs:984-1038).  Counts are in 16-byte texels ("vec4
+ * blocks"); addresses inside instance data index these arrays linearly
+ * (address -> (a % 1024, a / 1024) in the reference, res/gpu_cache.glsl:16). */
+typedef struct wrcu_frame_tables {
+  const float* prim_headers_f;   size_t prim_headers_f_texels;  /* 2/prim  */
+  const int32_t* prim_headers_i; size_t prim_headers_i_texels;  /* 2/prim  */
+  const float* transforms;       size_t transforms_texels;      /* 8/xform */
+  const float* render_tasks;     size_t render_tasks_texels;    /* 2/task  */
+  const float* gpu_cache;        size_t gpu_cache_texels;
+  const float* gpu_buffer_f;     size_t gpu_buffer_f_texels;
+  const int32_t* gpu_buffer_i;   size_t gpu_buffer_i_texels;
+} wrcu_frame_tables;
+
+/* State a draw depends on (SURVEY.md §8b last row): what the reference holds
+ * in GL state — bound textures (renderer/mod.rs:369-386), blend, depth,
+ * scissor — passed explicitly. */
+typedef struct wrcu_draw_state {
+  int32_t blend;        /* wrcu_blend                                      */
+  int32_t depth;        /* wrcu_depth                                      */
+  wrcu_tex color[3];    /* sColor0..2                                      */
+  wrcu_tex clip_mask;   /* sClipMask (BatchTextures.clip_mask)             */
+  int32_t scissor_enabled;
+  int32_t scissor[4];   /* x, y, w, h — device pixels, GL SetScissor       */
+  float blend_color[4]; /* glBlendColor, for WRCU_BLEND_CONSTANT_COLOR     */
+} wrcu_draw_state;
+
+/* ---- context ----------------------------------------------------------- */
+/* CreateContext/MakeCurrent (gl.cc:2806-2818).  device_ordinal = CUDA device. */
+int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out);
+void wrcu_ctx_destroy(wrcu_ctx* ctx);                 /* DestroyContext     */
+int wrcu_get_error(wrcu_ctx* ctx);                    /* GetError, sticky   */
+const char* wrcu_last_error_string(wrcu_ctx* ctx);
+const char* wrcu_get_string(int what);                /* GetString: 0=renderer
+        returns "Software WebRender" so the host keeps is_software behaviour
+        (gl.cc:1214, device/gl.rs:1645) ; 1=backend description              */
+int wrcu_abi_version(void);
+int wrcu_finish(wrcu_ctx* ctx);                       /* Finish (gl.cc:2802) */
+
+/* ---- textures / render targets ------------------------------------------ */
+/* GenTextures + TexStorage2D (gl.cc:1755, 1863). */
+int wrcu_texture_create(wrcu_ctx* ctx, int format, int width, int height,
+                        wrcu_tex* out);
+/* SetTextureParameter MAG/MIN filter (gl.cc:1838). */
+int wrcu_texture_set_filter(wrcu_ctx* ctx, wrcu_tex tex, int filter);
+/* TexSubImage2D (gl.cc:1794): rows are `src_stride` bytes apart. */
+int wrcu_texture_upload(wrcu_ctx* ctx, wrcu_tex tex, int x, int y, int w, int h,
+                        const void* data, size_t src_stride);
+int wrcu_texture_destroy(wrcu_ctx* ctx, wrcu_tex tex);   /* DeleteTexture   */
+/* ReadPixels (gl.cc:2562): synchronises. */
+int wrcu_read_pixels(wrcu_ctx* ctx, wrcu_tex tex, int x, int y, int w, int h,
+                     void* out, size_t dst_stride);
+
+/* ---- frame --------------------------------------------------------------- */
+/* bind_frame_data + gpu_buffer textures + prepare_gpu_cache
+ * (renderer/mod.rs:4418, 4551-4558, 1536). */
+int wrcu_frame_begin(wrcu_ctx* ctx, const wrcu_frame_tables* tables);
+int wrcu_frame_end(wrcu_ctx* ctx);   /* end_frame / gl.flush (mod.rs:4820) */
+
+/* ---- target binding, clears ---------------------------------------------- */
+/* bind_draw_target + uTransform + viewport (device/gl.rs:2130-2180,
+ * renderer/mod.rs:4705-4712).  `projection` is the column-major 4x4 ortho
+ * matrix the reference passes as uTransform; viewport is x,y,w,h.
+ * depth = 0 → no depth attachment. */
+int wrcu_target_bind(wrcu_ctx* ctx, wrcu_tex color, wrcu_tex depth,
+                     const float projection[16], const int32_t viewport[4]);
+/* clear_target (device/gl.rs:3779-3830 → gl.cc:2498 Clear).  rect NULL =
+ * whole target; color NULL = leave colour; depth NULL = leave depth. */
+int wrcu_clear(wrcu_ctx* ctx, const int32_t rect[4], const float color[4],
+               const float* depth);
+
+/* ---- draws ---------------------------------------------------------------- */
+/* draw_instanced_batch (renderer/mod.rs:2022-2065) =
+ *   bind_textures + update_vao_instances (glBufferData) +
+ *   glDrawElementsInstanced(TRIANGLES, 6, u16, 0, n) (gl.cc:2702).
+ * `instances` is the tightly packed #[repr(C)] instance array for `kind`
+ * (webrender/src/gpu_types.rs); `instance_stride` its
+ * element size in bytes.  Instances are drawn in order. */
+int wrcu_draw_batch(wrcu_ctx* ctx, int kind, uint32_t features,
+                    const wrcu_draw_state* state, const void* instances,
+                    size_t instance_stride, int n_instances);
+
+/* Program-key lookup: maps the reference's program name string
+ * "<shader>[ FEAT,FEAT]" (swgl/build.rs:13-31, gl.cc:1431) to kind+features.
+ * Returns WRCU_ERR_UNSUPPORTED for programs outside the hot path. */
+int wrcu_program_from_name(const char* key, int* kind, uint32_t* features);
+
+/* ---- statistics ------------------------------------------------------------ */
+typedef struct wrcu_stats {
+  uint64_t kernel_launches;   /* kernels of THIS library launched so far   */
+  uint64_t draw_calls;        /* wrcu_draw_batch calls                      */
+  uint64_t instances;         /* instances submitted                        */
+  uint64_t h2d_bytes;         /* host→device bytes copied                   */
+  uint64_t d2h_bytes;         /* device→host bytes copied                   */
+} wrcu_stats;
+int wrcu_get_stats(wrcu_ctx* ctx, wrcu_stats* out);
+int wrcu_reset_stats(wrcu_ctx* ctx);
+
+/* Device-side timing of the draws issued between begin/end, CUDA events on
+ * the context's stream (the reference's GpuTimer, device/query_gl.rs:20-31). */
+int wrcu_timer_begin(wrcu_ctx* ctx);
+int wrcu_timer_end(wrcu_ctx* ctx, float* elapsed_ms); /* synchronises */
+
+/* Raw device pointer + pitch of a texture (GetColorBuffer, gl.cc:2317): valid
+ * until the texture is destroyed.  Used by the multi-GPU tile gather. */
+int wrcu_texture_device_ptr(wrcu_ctx* ctx, wrcu_tex tex, void** dptr,
+                            size_t* pitch_bytes);
+/* The CUDA stream (cudaStream_t) the context queues work on. */
+int wrcu_stream(wrcu_ctx* ctx, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WRCU_H */

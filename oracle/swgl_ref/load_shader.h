@@ -1,0 +1,11 @@
+// TEST INFRASTRUCTURE — stands in for the `load_shader.h` that swgl/build.rs:19-31
+// generates: maps a program key ("name feat,feat") to its loader.
+#pragma once
+#include "wr_common.h"
+#include "ps_quad.h"
+#include "ps_quad_textured.h"
+
+ProgramLoader load_shader(const char* name) {
+  if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
+  return nullptr;
+}

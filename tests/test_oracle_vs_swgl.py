@@ -1,0 +1,34 @@
+"""Pins the C oracle (oracle/wr_oracle.c) against the UNMODIFIED reference
+rasteriser (oracle/_ref/libswgl_ref.so, built from /root/reference/swgl/src/gl.cc):
+same frames through both, byte-for-byte.  Skipped where the reference build is
+absent (it needs /root/reference at build time)."""
+import numpy as np
+import pytest
+
+from oracle.backends import OracleDevice, SwglDevice, have_swgl
+from webrender_b200 import abi, scenes
+
+from common import assert_same, render
+
+pytestmark = pytest.mark.skipif(not have_swgl(), reason="oracle/_ref not built (needs /root/reference)")
+
+BLENDS = [abi.BLEND_PREMULTIPLIED_ALPHA, abi.BLEND_ALPHA, abi.BLEND_PREMULTIPLIED_DEST_OUT, abi.BLEND_MULTIPLY,
+          abi.BLEND_PLUS_LIGHTER, abi.BLEND_SUBPIXEL_PASS0, abi.BLEND_NONE]
+
+
+@pytest.mark.parametrize("blend", BLENDS)
+@pytest.mark.parametrize("random_rects", [False, True])
+def test_alpha_rects(blend, random_rects):
+    f = scenes.alpha_rects_frame(333, 141, 41, random_rects=random_rects, seed=5, blend=blend,
+                                 color=(0.25, 0.125, 0.05, 0.3))
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), f"blend={blend}")
+
+
+@pytest.mark.parametrize("blend", list(range(abi.BLEND_ADV_MULTIPLY, abi.BLEND_ADV_LUMINOSITY + 1)) +
+                         [abi.BLEND_MIN, abi.BLEND_MAX, abi.BLEND_ADD_KEEP_ALPHA_OVER, abi.BLEND_DST_ALPHA_ADD,
+                          abi.BLEND_SUBPIXEL_PASS0_KEEP_A])
+def test_blend_keys_random_layers(blend):
+    """Every blend key of the reference's blend stage over random premultiplied layers."""
+    f = scenes.alpha_rects_frame(160, 64, 24, random_rects=True, seed=100 + blend, blend=blend,
+                                 color=None, clear_color=(0.4, 0.7, 0.2, 0.8))
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), f"blend={blend}")

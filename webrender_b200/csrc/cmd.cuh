@@ -1,0 +1,53 @@
+// cmd.cuh — DrawCmd records: the output of the per-instance "setup" kernels
+// (the reference's vertex stage + draw_quad set-up, swgl/src/rasterize.h:
+// 1549-1632) and the input of the tile raster kernels.
+//
+// A command is split into a 32-byte HOT part that every tile CTA streams
+// through shared memory (coverage rect, flags, z, packed colour) and a COLD
+// part that only the CTAs actually covered by the instance read from L2
+// (AA ramps, clip-mask placement, interpolation frame, sampler parameters).
+#pragma once
+#include <stdint.h>
+
+enum : uint32_t {
+  CMD_MASK = 1u << 1,       // SWGL_CLIP_FLAG_MASK   (blend.h:345)
+  CMD_AA = 1u << 2,         // SWGL_CLIP_FLAG_AA
+  CMD_TEXTURED = 1u << 3,   // fragment samples sColor0
+  CMD_OUT_RRRR = 1u << 4,   // QF_IS_MASK: output_color.rrrr
+  CMD_FULL_ROW_BODY = 1u << 5,
+};
+
+struct __align__(16) CmdHot {
+  short x0, y0, x1, y1;  // half-open pixel rect; empty rect == skipped instance
+  uint32_t flags;
+  uint32_t z;            // 24-bit depth of the quad (rasterize.h:1587-1594)
+  uint16_t col[4];       // B,G,R,A 16-bit lanes (round_pixel of v_color)
+  short aa_left_end;     // leftAA.end   (rasterize.h:546)
+  short aa_right_start;  // rightAA.start
+  uint32_t cold;         // index of the CmdCold record
+};
+static_assert(sizeof(CmdHot) == 32, "CmdHot must be 32 bytes");
+
+struct __align__(16) CmdCold {
+  // AA coverage ramps: dist = start + x*slope per edge (rasterize.h:511-519)
+  float aa_l0, aa_ls, aa_r0, aa_rs;
+  // clip mask: texel for fb pixel (x,y) = mask[(y-cmy)*pitch + (x-cmx)]
+  const uint8_t* mask_ptr;
+  int mask_pitch;
+  short cmx, cmy;
+  // Interpolation frame of the (screen-axis-aligned) quad: left/right edge x,
+  // top y, 1/height, and interpolants at the four edge end points.
+  float xl, xr, yt, yscale;
+  float i_lt[4], i_lb[4], i_rt[4], i_rb[4];
+  // kind-specific
+  float f[8];   // e.g. uv sample bounds
+  int32_t i[4];
+};
+
+// Per-batch info written by the setup kernel.
+struct BatchInfo {
+  int bx0, by0, bx1, by1;  // bounding box of all commands
+  int unsupported;         // instances the setup kernel had to reject
+  int simple;              // 1 while every command is a plain solid quad (no mask/AA/texture, lanes<=255)
+  int pad[2];
+};

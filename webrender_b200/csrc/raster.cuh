@@ -1,0 +1,359 @@
+// raster.cuh — tile-resident raster kernels.
+//
+// The reference draws a batch instance by instance: for each instance every
+// row, every span, every 4-pixel chunk is read-modify-written in the
+// framebuffer (swgl/src/rasterize.h:783-1054, blend.h:416).  On a GPU that
+// shape would serialise on memory: N overlapping instances = N passes over
+// the same bytes.  Here the loop nest is inverted: one CTA owns a 128x8-pixel
+// tile of the render target, keeps its pixels in registers (4 pixels/thread),
+// streams the batch's command list through shared memory IN BATCH ORDER (order
+// matters for blending), applies fragment + blend stage per pixel, and writes
+// the tile once.  DRAM sees each target byte at most once in and once out per
+// batch, however many layers the batch stacks.
+//
+// Thread mapping: 256 threads = 8 warps; warp w owns tile row w (128 px =
+// 512 B contiguous for RGBA8 → one fully coalesced 16-byte vector access per
+// lane); lane l owns pixels [4l, 4l+4).
+#pragma once
+#include "blend.cuh"
+#include "cmd.cuh"
+#include "sample.cuh"
+#include "wrcu_internal.h"
+
+struct RasterArgs {
+  TargetDev tgt;
+  const CmdHot* hot;
+  const CmdCold* cold;
+  const BatchInfo* info;
+  int n;
+  int blend;        // wrcu_blend
+  int depth_mode;   // wrcu_depth
+  Px blend_color;   // glBlendColor in lane order
+  TexView color0;   // sColor0
+  int fast_eligible;  // host-side part of the solid-premult fast-path test
+};
+
+#define CHUNK_CMDS 256
+
+// AA weight of pixel x for the current command (DO_AA, blend.h:433-445, with
+// the span set-up of aa_span, rasterize.h:546-557).  Chunks of 4 start at the
+// span start c.x0.
+__device__ __forceinline__ int wr_aa_weight(const CmdHot& c, const CmdCold& k, int x) {
+  int j = (x - c.x0) & 3;
+  int xc = x - j;
+  int opaque = max((int)c.aa_right_start - (int)c.aa_left_end - 3, 0);
+  int off = xc - c.aa_left_end;
+  if (off >= 0 && off < opaque) return 256;
+  float offs = (float)(c.aa_left_end + j);
+  float left = __fadd_rn(k.aa_l0, __fmul_rn(offs, k.aa_ls));
+  float right = __fadd_rn(k.aa_r0, __fmul_rn(offs, k.aa_rs));
+  float fo = (float)off;
+  float dist = wr_clamp(wr_min(__fadd_rn(left, __fmul_rn(k.aa_ls, fo)),
+                               __fadd_rn(right, __fmul_rn(k.aa_rs, fo))),
+                        0.0f, 256.0f);
+  return wr_round_pixel(dist, 1.0f);
+}
+
+// Interpolants of a screen-axis-aligned quad at pixel (x,y): closed form of the
+// reference's edge walk (Edge ctor + nextRow, rasterize.h:850-889) and span
+// set-up (rasterize.h:1003-1017): lane j of chunk k of the span that starts at
+// sx0.  Exact whenever the reference's running sums are exact (integer or
+// half-integer 1:1 mappings); within 1 ulp otherwise.
+template <int N>
+__device__ __forceinline__ void wr_interp(const CmdCold& k, int sx0, int x, int y, float* out) {
+  float yc = (float)y + 0.5f;
+  float dy = __fsub_rn(yc, k.yt);
+  float stepScale = __fdiv_rn(1.0f, __fsub_rn(k.xr, k.xl));
+  if (!isfinite(stepScale)) stepScale = 0.0f;
+  int rel = x - sx0;
+  int j = rel & 3;
+  float kf = (float)(rel >> 2);
+  float x0f = __fsub_rn(__fadd_rn((float)sx0, 0.5f), k.xl);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float li = __fadd_rn(k.i_lt[i], __fmul_rn(dy, __fmul_rn(__fsub_rn(k.i_lb[i], k.i_lt[i]), k.yscale)));
+    float ri = __fadd_rn(k.i_rt[i], __fmul_rn(dy, __fmul_rn(__fsub_rn(k.i_rb[i], k.i_rt[i]), k.yscale)));
+    float step = __fmul_rn(__fsub_rn(ri, li), stepScale);
+    float o = __fadd_rn(li, __fmul_rn(step, x0f));
+    // chunk advance: interp_step * chunks (glsl-to-cxx step_interp_inputs)
+    float v = __fadd_rn(o, __fmul_rn(__fmul_rn(step, 4.0f), kf));
+    // lanes accumulate sequentially (init_interp, glsl.h:3083-3088)
+    for (int s = 0; s < j; s++) v = __fadd_rn(v, step);
+    out[i] = v;
+  }
+}
+
+// ---- fragment stage: ps_quad_textured -------------------------------------------
+// Source colour (16-bit lanes) of pixel (x,y) for a quad command.  `body` tells
+// whether the pixel belongs to the part of the span the reference draws with
+// swgl_drawSpanRGBA8 (first len&~3 pixels) or to the tail that runs the
+// fragment shader (ps_quad_textured.glsl:39-64).
+__device__ __forceinline__ Px wr_quad_source(const RasterArgs& a, const CmdHot& c, int x, int y,
+                                             bool rgba_target) {
+  Px col{c.col[0], c.col[1], c.col[2], c.col[3]};
+  const int len = c.x1 - c.x0;
+  if (!(c.flags & CMD_TEXTURED)) {
+    // swgl_drawSpanRGBA8 commits v_color for the span body even for mask quads;
+    // only the fragment-shader tail applies .rrrr (ps_quad_textured.glsl:52-64,
+    // ps_quad.glsl:411-413).  R8 targets have no span shader: always fragment.
+    if (c.flags & CMD_OUT_RRRR) {
+      int body_len0 = (rgba_target && len >= 4) ? (len & ~3) : 0;
+      if ((x - c.x0) >= body_len0) col.b = col.g = col.a = col.r;
+    }
+    return col;
+  }
+  const CmdCold& k = a.cold[c.cold];
+  const TexView& t = a.color0;
+  int body_len = (rgba_target && len >= 4 && !(c.flags & CMD_OUT_RRRR) &&
+                  t.fmt == WRCU_FMT_RGBA8) ? (len & ~3) : 0;
+  bool body = (x - c.x0) < body_len;
+  float uv[2];
+  wr_interp<2>(k, c.x0, x, y, uv);
+  bool linear = t.filter == WRCU_LINEAR;
+  Px s;
+  if (body) {
+    // swgl_commitTextureLinearColorRGBA8 (swgl_ext.h:589-612)
+    // needsTextureLinear uses lanes 0,1 of the span start chunk
+    float uv0[2], uv1[2];
+    wr_interp<2>(k, c.x0, c.x0, y, uv0);
+    wr_interp<2>(k, c.x0, c.x0 + 1, y, uv1);
+    // The span path does not consult the sampler's filter mode, only
+    // needsTextureLinear (swgl_ext.h:554-612).
+    int filter = 0;  // LINEAR_FILTER_NEAREST
+    if (t.w >= 2) {
+      if (uv0[1] != uv1[1]) {
+        filter = 1;
+      } else {
+        float px0 = __fmul_rn(uv0[0], (float)t.w), px1 = __fmul_rn(uv1[0], (float)t.w);
+        float py0 = __fmul_rn(uv0[1], (float)t.h);
+        int sp = (body_len & ~127) + 128;
+        int scaled = (int)roundf(__fmul_rn(__fsub_rn(px1, px0), (float)sp));
+        if (scaled != sp) filter = 1;
+        else if ((((int)__fadd_rn(__fmul_rn(px0, 4.0f), 0.5f)) & 3) != 2 ||
+                 (((int)__fadd_rn(__fmul_rn(py0, 4.0f), 0.5f)) & 3) != 2) filter = 3;
+      }
+    }
+    if (filter != 0) {
+      // quantised uv accumulator: qu_j + k*ustep (LINEAR_QUANTIZE_UV, swgl_ext.h:160-169)
+      int rel = x - c.x0, j = rel & 3;
+      float kf = (float)(rel >> 2);
+      float uvj[2];
+      wr_interp<2>(k, c.x0, c.x0 + j, y, uvj);
+      float qu0 = wr_linear_quantize(uv0[0], t.w), qu1 = wr_linear_quantize(uv1[0], t.w);
+      float qv0 = wr_linear_quantize(uv0[1], t.h), qv1 = wr_linear_quantize(uv1[1], t.h);
+      float ustep = __fmul_rn(4.0f, __fsub_rn(qu1, qu0));
+      float vstep = __fmul_rn(4.0f, __fsub_rn(qv1, qv0));
+      float qu = __fadd_rn(wr_linear_quantize(uvj[0], t.w), __fmul_rn(ustep, kf));
+      float qv = __fadd_rn(wr_linear_quantize(uvj[1], t.h), __fmul_rn(vstep, kf));
+      float minu = wr_max(wr_linear_quantize(k.f[0], t.w), 0.0f);
+      float minv = wr_max(wr_linear_quantize(k.f[1], t.h), 0.0f);
+      float maxu = wr_max(wr_linear_quantize(k.f[2], t.w), minu);
+      float maxv = wr_max(wr_linear_quantize(k.f[3], t.h), minv);
+      s = wr_texture_linear_rgba8(t, (int)wr_clamp(qu, minu, maxu), (int)wr_clamp(qv, minv, maxv));
+    } else {
+      // blendTextureNearestFast (swgl_ext.h:476-541)
+      int ix = (int)__fmul_rn(uv0[0], (float)t.w), iy = (int)__fmul_rn(uv0[1], (float)t.h);
+      int minUx = (int)__fmul_rn(k.f[0], (float)t.w), minUy = (int)__fmul_rn(k.f[1], (float)t.h);
+      int maxUx = (int)__fmul_rn(k.f[2], (float)t.w), maxUy = (int)__fmul_rn(k.f[3], (float)t.h);
+      int ry = wr_clamp_coord(min(max(iy, minUy), maxUy), t.h);
+      int minX = min(max(minUx, 0), t.w - 1);
+      int maxX = min(max(maxUx, minX), t.w - 1);
+      int sx = min(max(ix + (x - c.x0), minX), maxX);
+      s = px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)ry * t.pitch) + sx));
+    }
+    return px_apply_color(s, col);
+  }
+  // fragment path: fs_sample_color0 + texture() (sample_color0.glsl:25-31,
+  // texture.h:948-975), float multiply by v_color, then round_pixel.
+  float cu = wr_clamp(uv[0], k.f[0], k.f[2]);
+  float cv = wr_clamp(uv[1], k.f[1], k.f[3]);
+  float tex[4];
+  if (linear) {
+    Px p = wr_texture_linear_rgba8(t, (int)wr_linear_quantize(cu, t.w), (int)wr_linear_quantize(cv, t.h));
+    tex[0] = __fmul_rn((float)p.r, 1.0f / 255.0f);
+    tex[1] = __fmul_rn((float)p.g, 1.0f / 255.0f);
+    tex[2] = __fmul_rn((float)p.b, 1.0f / 255.0f);
+    tex[3] = __fmul_rn((float)p.a, 1.0f / 255.0f);
+  } else {
+    int tx = wr_clamp_coord((int)__fmul_rn(cu, (float)t.w), t.w);
+    int ty = wr_clamp_coord((int)__fmul_rn(cv, (float)t.h), t.h);
+    uint32_t p = __ldg((const uint32_t*)(t.ptr + (size_t)ty * t.pitch) + tx);
+    tex[0] = __fmul_rn((float)((p >> 16) & 0xFF), 1.0f / 255.0f);
+    tex[1] = __fmul_rn((float)((p >> 8) & 0xFF), 1.0f / 255.0f);
+    tex[2] = __fmul_rn((float)(p & 0xFF), 1.0f / 255.0f);
+    tex[3] = __fmul_rn((float)(p >> 24), 1.0f / 255.0f);
+  }
+  // textured quads force v_color = 1 (ps_quad_textured.glsl:27)
+  Px o;
+  if (c.flags & CMD_OUT_RRRR) {
+    int r = wr_round_pixel(tex[0], 255.0f) & 0xFFFF;
+    o = Px{r, r, r, r};
+  } else {
+    o.r = wr_round_pixel(tex[0], 255.0f) & 0xFFFF;
+    o.g = wr_round_pixel(tex[1], 255.0f) & 0xFFFF;
+    o.b = wr_round_pixel(tex[2], 255.0f) & 0xFFFF;
+    o.a = wr_round_pixel(tex[3], 255.0f) & 0xFFFF;
+  }
+  return o;
+}
+
+// ---- the generic tile kernel (any quad command, any blend key) -------------------
+template <int FMT>
+__global__ void __launch_bounds__(WRCU_THREADS)
+wr_raster_quads(RasterArgs a) {
+  __shared__ CmdHot sh[CHUNK_CMDS];
+  const int tx0 = blockIdx.x * WRCU_TILE_W, ty0 = blockIdx.y * WRCU_TILE_H;
+  const BatchInfo bi = *a.info;
+  if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
+  // whole-CTA early out: tile outside the batch's bounding box
+  if (tx0 >= bi.bx1 || tx0 + WRCU_TILE_W <= bi.bx0 || ty0 >= bi.by1 || ty0 + WRCU_TILE_H <= bi.by0)
+    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = tx0 + lane * 4, y = ty0 + warp;
+  const bool row_ok = y < a.tgt.h;
+  uint32_t px[4] = {0, 0, 0, 0};
+  uint32_t zb[4] = {0, 0, 0, 0};
+  bool loaded = false, dirty = false, zdirty = false;
+  uint8_t* rowp = a.tgt.color + (size_t)y * a.tgt.color_pitch;
+  uint32_t* zrow = a.tgt.depth ? (uint32_t*)((uint8_t*)a.tgt.depth + (size_t)y * a.tgt.depth_pitch) : nullptr;
+  const bool use_depth = a.depth_mode != WRCU_DEPTH_OFF && zrow != nullptr;
+
+  for (int base = 0; base < a.n; base += CHUNK_CMDS) {
+    __syncthreads();
+    int m = min(CHUNK_CMDS, a.n - base);
+    if (threadIdx.x < m) sh[threadIdx.x] = a.hot[base + threadIdx.x];
+    __syncthreads();
+    for (int i = 0; i < m; i++) {
+      const CmdHot c = sh[i];
+      if (!row_ok || y < c.y0 || y >= c.y1) continue;          // warp-uniform
+      if (c.x1 <= tx0 || c.x0 >= tx0 + WRCU_TILE_W) continue;  // CTA-uniform
+      if (!loaded) {
+        // lazy tile load: first command that touches this row
+        loaded = true;
+        if (FMT == WRCU_FMT_RGBA8) {
+          uint4 v = *(const uint4*)(rowp + (size_t)x * 4);
+          px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+        } else {
+          uint32_t v = *(const uint32_t*)(rowp + x);
+          px[0] = v & 0xFF; px[1] = (v >> 8) & 0xFF; px[2] = (v >> 16) & 0xFF; px[3] = v >> 24;
+        }
+        if (use_depth) {
+          uint4 v = *(const uint4*)(zrow + x);
+          zb[0] = v.x; zb[1] = v.y; zb[2] = v.z; zb[3] = v.w;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        int xx = x + p;
+        if (xx < c.x0 || xx >= c.x1) continue;
+        if (use_depth) {
+          if (!(c.z <= zb[p])) continue;  // GL_LEQUAL
+          if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) { zb[p] = c.z; zdirty = true; }
+        }
+        Px src = wr_quad_source(a, c, xx, y, FMT == WRCU_FMT_RGBA8);
+        if (a.blend != WRCU_BLEND_NONE) {
+          if (c.flags & (CMD_AA | CMD_MASK)) {
+            const CmdCold& k = a.cold[c.cold];
+            if (c.flags & CMD_AA) {
+              int aa = wr_aa_weight(c, k, xx);
+              if (FMT == WRCU_FMT_RGBA8) src = px_scale256(src, aa);
+              else src.r = wr_muldiv256(src.r, aa);
+            }
+            if (c.flags & CMD_MASK) {
+              int mk = __ldg(k.mask_ptr + (size_t)(y - k.cmy) * k.mask_pitch + (xx - k.cmx));
+              if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
+              else src.r = wr_muldiv255(src.r, mk);
+            }
+          }
+          if (FMT == WRCU_FMT_RGBA8) px[p] = px_pack(wr_blend_rgba8(a.blend, src, px_unpack(px[p]), a.blend_color));
+          else px[p] = wr_pack16(wr_blend_r8(a.blend, src.r, (int)px[p]));
+        } else {
+          if (FMT == WRCU_FMT_RGBA8) px[p] = px_pack(src);
+          else px[p] = wr_pack16(src.r);
+        }
+        dirty = true;
+      }
+    }
+  }
+  if (dirty) {
+    if (FMT == WRCU_FMT_RGBA8) {
+      *(uint4*)(rowp + (size_t)x * 4) = make_uint4(px[0], px[1], px[2], px[3]);
+    } else {
+      *(uint32_t*)(rowp + x) = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+    }
+  }
+  if (zdirty) *(uint4*)(zrow + x) = make_uint4(zb[0], zb[1], zb[2], zb[3]);
+}
+
+// ---- specialised hot kernel: solid quads, premultiplied-alpha over, no depth,
+// no mask/AA (config B, the alpha-blend brush pass).  Pixels stay unpacked as
+// (rb, ga) lane pairs across the whole command list; per pixel-layer the work
+// is 2 x (IMAD, PRMT, IADD, VMIN).  Commands whose colour lanes exceed 255 or
+// that carry mask/AA flags are not routed here (the host checks the batch).
+__global__ void __launch_bounds__(WRCU_THREADS)
+wr_raster_solid_premult(RasterArgs a) {
+  __shared__ CmdHot sh[CHUNK_CMDS];
+  const int tx0 = blockIdx.x * WRCU_TILE_W, ty0 = blockIdx.y * WRCU_TILE_H;
+  const BatchInfo bi = *a.info;
+  if (!bi.simple) return;  // mixed batch → wr_raster_quads
+  if (tx0 >= bi.bx1 || tx0 + WRCU_TILE_W <= bi.bx0 || ty0 >= bi.by1 || ty0 + WRCU_TILE_H <= bi.by0)
+    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = tx0 + lane * 4, y = ty0 + warp;
+  const bool row_ok = y < a.tgt.h;
+  uint8_t* rowp = a.tgt.color + (size_t)y * a.tgt.color_pitch + (size_t)x * 4;
+  uint32_t rb[4], ga[4];
+  bool dirty = false;
+  {
+    uint4 v = row_ok ? *(const uint4*)rowp : make_uint4(0, 0, 0, 0);
+    uint32_t pv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      rb[p] = pv[p] & 0x00FF00FFu;
+      ga[p] = (pv[p] >> 8) & 0x00FF00FFu;
+    }
+  }
+  for (int base = 0; base < a.n; base += CHUNK_CMDS) {
+    __syncthreads();
+    int m = min(CHUNK_CMDS, a.n - base);
+    if (threadIdx.x < m) sh[threadIdx.x] = a.hot[base + threadIdx.x];
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < m; i++) {
+      const uint4 h0 = *(const uint4*)&sh[i];         // rect, flags, z
+      const uint2 h1 = *(const uint2*)&sh[i].col[0];  // colour lanes
+      int cx0 = (short)(h0.x & 0xFFFF), cy0 = (short)(h0.x >> 16);
+      int cx1 = (short)(h0.y & 0xFFFF), cy1 = (short)(h0.y >> 16);
+      if (y < cy0 || y >= cy1) continue;
+      // h1.x = B | G<<16, h1.y = R | A<<16  → pairs (B,R) and (G,A)
+      uint32_t srb = __byte_perm(h1.x, h1.y, 0x5410);  // B | R<<16
+      uint32_t sga = __byte_perm(h1.x, h1.y, 0x7632);  // G | A<<16
+      uint32_t cc = 255u - (h1.y >> 16);
+      if (cx0 <= x && cx1 >= x + 4) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          rb[p] = wr_premult_over_pair(rb[p], srb, cc);
+          ga[p] = wr_premult_over_pair(ga[p], sga, cc);
+        }
+        dirty = true;
+      } else if (cx1 > x && cx0 < x + 4) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          if (x + p >= cx0 && x + p < cx1) {
+            rb[p] = wr_premult_over_pair(rb[p], srb, cc);
+            ga[p] = wr_premult_over_pair(ga[p], sga, cc);
+          }
+        }
+        dirty = true;
+      }
+    }
+  }
+  if (dirty && row_ok) {
+    uint4 v;
+    v.x = rb[0] | (ga[0] << 8);
+    v.y = rb[1] | (ga[1] << 8);
+    v.z = rb[2] | (ga[2] << 8);
+    v.w = rb[3] | (ga[3] << 8);
+    *(uint4*)rowp = v;
+  }
+}

@@ -1,0 +1,245 @@
+// setup_common.cuh — pieces of the reference's vertex stage shared by all
+// kinds: data-table fetches (webrender/res/gpu_cache.glsl, gpu_buffer.glsl,
+// render_task.glsl, transform.glsl) and draw_quad's screen-space set-up for
+// screen-axis-aligned quads (swgl/src/rasterize.h:1549-1632, 783-941).
+//
+// Compiled with -fmad=false: every float expression below is evaluated as
+// written, in IEEE fp32, in the same order as the GLSL / glsl.h source, so
+// device rects and interpolants match the g++ build of SWGL bit for bit.
+#pragma once
+#include "blend.cuh"
+#include "cmd.cuh"
+#include "wrcu_internal.h"
+
+struct SetupArgs {
+  FrameTablesDev tabs;
+  TargetDev tgt;
+  const uint8_t* instances;
+  int stride;
+  int n;
+  CmdHot* hot;
+  CmdCold* cold;
+  BatchInfo* info;
+  int* err_counter;
+  int blend_enabled;
+  TexView color0;
+  TexView clip_mask;
+};
+
+__device__ __forceinline__ float4 wr_fetch(const float4* t, int n, int addr) {
+  if (n <= 0) return make_float4(0, 0, 0, 0);
+  addr = min(max(addr, 0), n - 1);
+  return __ldg(t + addr);
+}
+__device__ __forceinline__ int4 wr_fetchi(const int4* t, int n, int addr) {
+  if (n <= 0) return make_int4(0, 0, 0, 0);
+  addr = min(max(addr, 0), n - 1);
+  return __ldg(t + addr);
+}
+
+struct DevTransform {
+  float m[16], inv_m[16];
+  bool is_axis_aligned;
+};
+
+__device__ inline DevTransform wr_fetch_transform(const FrameTablesDev& t, int id) {
+  DevTransform r;
+  r.is_axis_aligned = (id >> 23) == 0;
+  int index = id & 0x007fffff;
+  for (int i = 0; i < 4; i++) {
+    float4 a = wr_fetch(t.transforms, t.n_transforms, index * 8 + i);
+    float4 b = wr_fetch(t.transforms, t.n_transforms, index * 8 + 4 + i);
+    r.m[4 * i + 0] = a.x; r.m[4 * i + 1] = a.y; r.m[4 * i + 2] = a.z; r.m[4 * i + 3] = a.w;
+    r.inv_m[4 * i + 0] = b.x; r.inv_m[4 * i + 1] = b.y; r.inv_m[4 * i + 2] = b.z; r.inv_m[4 * i + 3] = b.w;
+  }
+  return r;
+}
+
+// mat4 * vec4 with glsl.h's evaluation order (glsl.h:2581-2588)
+__device__ __forceinline__ float4 wr_mat_mul(const float* m, float4 v) {
+  float4 u;
+  u.x = m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * v.w;
+  u.y = m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * v.w;
+  u.z = m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * v.w;
+  u.w = m[3] * v.x + m[7] * v.y + m[11] * v.z + m[15] * v.w;
+  return u;
+}
+
+struct DevPictureTask {
+  float tx0, ty0, tx1, ty1;  // task_rect
+  float device_pixel_scale;
+  float ox, oy;  // content_origin
+};
+__device__ inline DevPictureTask wr_fetch_picture_task(const FrameTablesDev& t, int address) {
+  float4 a = wr_fetch(t.render_tasks, t.n_render_tasks, address * 2);
+  float4 b = wr_fetch(t.render_tasks, t.n_render_tasks, address * 2 + 1);
+  return DevPictureTask{a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+}
+
+__device__ __forceinline__ int wr_round_i(float v) { return (int)floorf(v + 0.5f); }
+
+// Output of a kind's vertex stage for one instance.
+struct QuadOut {
+  float4 pos[4];        // gl_Position per lane (lanes = unit quad corners 0,1,3,2)
+  float interp[4][4];   // up to 4 interpolated floats per lane
+  int n_interp;
+  uint32_t flags;       // CMD_* set by the vertex stage
+  int aa_edge_mask;     // swgl_antiAlias edges (lane-index bits)
+  // swgl_clipMask(offset, bb_origin, bb_size)
+  int cm_off[2], cm_bb[4];
+  uint16_t col[4];
+};
+
+// draw_quad + the parts of draw_quad_spans that are per-instance constants for
+// a quad whose screen edges are vertical/horizontal.  Writes hot/cold; returns
+// false (and writes an empty command) when the instance draws nothing.
+// Sets *unsupported when the quad needs the general edge walker (rotation or
+// perspective), which this backend does not rasterise yet.
+__device__ inline bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupported) {
+  CmdHot h;
+  h.x0 = h.y0 = h.x1 = h.y1 = 0;
+  h.flags = 0;
+  h.z = 0;
+  h.col[0] = q.col[0]; h.col[1] = q.col[1]; h.col[2] = q.col[2]; h.col[3] = q.col[3];
+  h.aa_left_end = h.aa_right_start = 0;
+  h.cold = idx;
+  CmdCold k;
+  memset(&k, 0, sizeof k);
+  bool ok = false;
+  do {
+    if (q.pos[1].w != q.pos[0].w || q.pos[2].w != q.pos[0].w || q.pos[3].w != q.pos[0].w) {
+      *unsupported = 1;  // draw_perspective
+      break;
+    }
+    float w = 1.0f / q.pos[0].w;
+    if (!isfinite(w)) w = 0.0f;
+    float px[4], py[4];
+    for (int i = 0; i < 4; i++) {
+      px[i] = (q.pos[i].x * w + 1) * 0.5f * (float)a.tgt.vp[2] + (float)a.tgt.vp[0];
+      py[i] = (q.pos[i].y * w + 1) * 0.5f * (float)a.tgt.vp[3] + (float)a.tgt.vp[1];
+    }
+    uint32_t flags = a.blend_enabled ? q.flags : (q.flags & ~(CMD_MASK | CMD_AA));
+    float cx0 = (float)a.tgt.cx0, cy0 = (float)a.tgt.cy0, cx1 = (float)a.tgt.cx1, cy1 = (float)a.tgt.cy1;
+    if (flags & CMD_MASK) {
+      int mx0 = max(q.cm_bb[0], 0), my0 = max(q.cm_bb[1], 0);
+      int mx1 = min(q.cm_bb[0] + q.cm_bb[2], a.clip_mask.w);
+      int my1 = min(q.cm_bb[1] + q.cm_bb[3], a.clip_mask.h);
+      int cmx = q.cm_off[0] + a.tgt.vp[0], cmy = q.cm_off[1] + a.tgt.vp[1];
+      mx0 += cmx; mx1 += cmx; my0 += cmy; my1 += cmy;
+      cx0 = wr_max(cx0, (float)mx0); cy0 = wr_max(cy0, (float)my0);
+      cx1 = wr_min(cx1, (float)mx1); cy1 = wr_min(cy1, (float)my1);
+      k.mask_ptr = a.clip_mask.ptr;
+      k.mask_pitch = a.clip_mask.pitch;
+      k.cmx = (short)cmx;
+      k.cmy = (short)cmy;
+    }
+    int sides = 0;
+    for (int i = 0; i < 4; i++) {
+      sides |= px[i] < cx1 ? (px[i] > cx0 ? 1 | 2 : 1) : 2;
+      sides |= py[i] < cy1 ? (py[i] > cy0 ? 4 | 8 : 4) : 8;
+    }
+    if (sides != 0xF) break;
+    float screenZ = (q.pos[0].z * w + 1) * 0.5f;
+    if (screenZ < 0 || screenZ > 1) break;
+    h.z = (uint32_t)(16777215.0f * screenZ);
+
+    // vertex selection, rasterize.h:796-846
+    int top = py[3] < py[2] ? (py[0] < py[1] ? (py[0] < py[3] ? 0 : 3) : (py[1] < py[3] ? 1 : 3))
+                            : (py[0] < py[1] ? (py[0] < py[2] ? 0 : 2) : (py[1] < py[2] ? 1 : 2));
+    int next = (top + 1) & 3, prev = (top + 3) & 3;
+    int l0i, l1i, r0i, r1i;
+    if (py[top] == py[next]) {
+      l0i = next; l1i = (next + 1) & 3; r0i = top; r1i = prev;
+    } else if (py[top] == py[prev]) {
+      l0i = top; l1i = next; r0i = prev; r1i = (prev + 3) & 3;
+    } else {
+      l0i = r0i = top; l1i = next; r1i = prev;
+    }
+    // axis-aligned requirement: both descending edges vertical, same y extent
+    if (px[l0i] != px[l1i] || px[r0i] != px[r1i] || py[l0i] != py[r0i] || py[l1i] != py[r1i]) {
+      *unsupported = 1;
+      break;
+    }
+    float perp = (px[l1i] - px[l0i]) * (py[r1i] - py[r0i]) - (py[l1i] - py[l0i]) * (px[r1i] - px[r0i]);
+    bool flipped = px[l0i] > px[r0i] || (px[l0i] == px[r0i] && perp > 0.0f);
+    int Lt = flipped ? r0i : l0i, Lb = flipped ? r1i : l1i;   // final left edge: top/bottom lanes
+    int Rt = flipped ? l0i : r0i, Rb = flipped ? l1i : r1i;
+    int left_edge_index = flipped ? r0i : l1i;   // Edge(...,edgeIndex): left=l1i, right=r0i
+    int right_edge_index = flipped ? l1i : r0i;
+    float yt = py[l0i], yb = py[l1i];
+    float xl = px[Lt], xr = px[Rt];
+    bool aa = (flags & CMD_AA) != 0;
+    float aaRound = aa ? 0.0f : 0.5f;
+    float ystart = floorf(wr_max(wr_min(yt, cy1), cy0) + aaRound) + 0.5f;
+    // Edge ctor: x = p0.x + (y - p0.y) * xSlope with xSlope == 0 * yScale
+    float yScale = 1.0f / wr_max(yb - yt, 1.0f / 256);
+    float slopeL = (px[Lb] - px[Lt]) * yScale, slopeR = (px[Rb] - px[Rt]) * yScale;
+    float lx = xl + (ystart - yt) * slopeL, rx = xr + (ystart - yt) * slopeR;
+    // rows: centre y drawn while y <= min(yb, cy1)
+    float ylim = wr_min(yb, cy1);
+    int r0 = (int)(ystart - 0.5f);
+    int r1 = (int)floorf(ylim - 0.5f) + 1;
+    while ((float)r1 + 0.5f <= ylim) r1++;
+    while (r1 > r0 && (float)(r1 - 1) + 0.5f > ylim) r1--;
+    if (r1 <= r0) break;
+    // clipSpan = clipRect.x_range().clip(x_range(l0,l1).merge(x_range(r0,r1)))
+    float cs0 = wr_clamp(wr_min(xl, xr), cx0, cx1), cs1 = wr_clamp(wr_max(xl, xr), cx0, cx1);
+    int sx0, sx1;
+    if (!aa) {
+      sx0 = wr_round_i(wr_clamp(lx, cs0, cs1));
+      sx1 = wr_round_i(wr_clamp(rx, cs0, cs1));
+    } else {
+      int la0, la1, ra0, ra1;
+      bool lmask = (q.aa_edge_mask >> left_edge_index) & 1;
+      bool rmask = (q.aa_edge_mask >> right_edge_index) & 1;
+      if (lmask) {
+        float rad = 0.5f * fabsf(slopeL);
+        la0 = (int)floorf(wr_clamp(lx - rad, cs0, cs1));
+        la1 = (int)ceilf(wr_clamp(lx + rad, cs0, cs1));
+        float dx = (-1.0f * 256.0f) * (1.0f / sqrtf(1.0f + slopeL * slopeL));
+        k.aa_l0 = 128.0f + dx * (lx - 0.5f);
+        k.aa_ls = -dx;
+      } else {
+        la0 = la1 = wr_round_i(wr_clamp(lx, cs0, cs1));
+        k.aa_l0 = 256.0f;
+        k.aa_ls = 0.0f;
+      }
+      if (rmask) {
+        float rad = 0.5f * fabsf(slopeR);
+        ra0 = (int)floorf(wr_clamp(rx - rad, cs0, cs1));
+        ra1 = (int)ceilf(wr_clamp(rx + rad, cs0, cs1));
+        float dx = (1.0f * 256.0f) * (1.0f / sqrtf(1.0f + slopeR * slopeR));
+        k.aa_r0 = 128.0f + dx * (rx - 0.5f);
+        k.aa_rs = -dx;
+      } else {
+        ra0 = ra1 = wr_round_i(wr_clamp(rx, cs0, cs1));
+        k.aa_r0 = 256.0f;
+        k.aa_rs = 0.0f;
+      }
+      h.aa_left_end = (short)la1;
+      h.aa_right_start = (short)ra0;
+      sx0 = la0;
+      sx1 = ra1;
+    }
+    if (sx1 <= sx0) break;
+    h.x0 = (short)sx0; h.x1 = (short)sx1; h.y0 = (short)r0; h.y1 = (short)r1;
+    h.flags = flags;
+    k.xl = lx; k.xr = rx; k.yt = yt; k.yscale = yScale;
+    for (int i = 0; i < 4; i++) {
+      k.i_lt[i] = q.interp[Lt][i]; k.i_lb[i] = q.interp[Lb][i];
+      k.i_rt[i] = q.interp[Rt][i]; k.i_rb[i] = q.interp[Rb][i];
+    }
+    ok = true;
+  } while (0);
+  a.hot[idx] = h;
+  if (ok) {
+    bool simple = !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&
+                  h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255;
+    if (!simple) a.info->simple = 0;
+    atomicMin(&a.info->bx0, (int)h.x0); atomicMin(&a.info->by0, (int)h.y0);
+    atomicMax(&a.info->bx1, (int)h.x1); atomicMax(&a.info->by1, (int)h.y1);
+  }
+  // cold record is written by the caller after it fills the kind-specific part
+  a.cold[idx] = k;
+  return ok;
+}

@@ -1,0 +1,155 @@
+// setup_quad.cuh — vertex stage of the ps_quad_* programs
+// (webrender/res/ps_quad.glsl:239-389 quad_primive_info/write_vertex/main,
+//  ps_quad_textured.glsl:15-36 pattern_vertex, sample_color0.glsl:12-21),
+// SWGL branches (SWGL_ANTIALIAS: edge AA is requested from the rasteriser via
+// swgl_antiAlias instead of AA varyings).  One thread per instance.
+#pragma once
+#include "setup_common.cuh"
+
+#define WR_QF_IS_OPAQUE 1
+#define WR_QF_APPLY_DEVICE_CLIP 2
+#define WR_QF_IGNORE_DEVICE_SCALE 4
+#define WR_QF_USE_AA_SEGMENTS 8
+#define WR_QF_IS_MASK 16
+#define WR_AA_PIXEL_RADIUS 2.0f
+
+struct QuadPrimInfo {
+  float2 local_pos[4];  // PrimitiveInfo.local_pos (after pattern scale/offset), per lane
+  float seg_rect[4], seg_uv_rect[4];
+  float prim_bounds[4], prim_clip[4];
+  float color[4];
+  int edge_flags, quad_flags;
+  int pattern_input[2];
+};
+
+__device__ inline void wr_quad_primitive_info(const SetupArgs& a, int4 aData, QuadOut& q,
+                                              QuadPrimInfo& pi) {
+  const FrameTablesDev& T = a.tabs;
+  int prim_address_i = aData.x, prim_address_f = aData.y;
+  int quad_flags = (aData.z >> 24) & 0xff, edge_flags = (aData.z >> 16) & 0xff;
+  int part_index = (aData.z >> 8) & 0xff, segment_index = aData.z & 0xff;
+  int picture_task_address = aData.w;
+  int4 header = wr_fetchi(T.gpu_buffer_i, T.n_gpu_buffer_i, prim_address_i);
+  int transform_id = header.x, z_id = header.y;
+  pi.pattern_input[0] = header.z;
+  pi.pattern_input[1] = header.w;
+  DevTransform transform = wr_fetch_transform(T, transform_id);
+  DevPictureTask task = wr_fetch_picture_task(T, picture_task_address);
+  float4 t0 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f);
+  float4 t1 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f + 1);
+  float4 t2 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f + 2);
+  float4 so = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f + 3);
+  float4 t4 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f + 4);
+  float z = (float)z_id;
+  float4 seg_rect, seg_uv;
+  if (segment_index == 0xff) {
+    seg_rect = t0;
+    seg_uv = t2;
+  } else {
+    seg_rect = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f + 5 + segment_index * 2);
+    seg_uv = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, prim_address_f + 5 + segment_index * 2 + 1);
+  }
+  float c0x = wr_max(seg_rect.x, t1.x), c0y = wr_max(seg_rect.y, t1.y);
+  float c1x = wr_min(seg_rect.z, t1.z), c1y = wr_min(seg_rect.w, t1.w);
+  c1x = wr_max(c0x, c1x);
+  c1y = wr_max(c0y, c1y);
+  int aa_mask = 0;
+  switch (part_index) {
+    case 1: c1x = c0x + WR_AA_PIXEL_RADIUS; aa_mask = 1; break;
+    case 2:
+      c0x = c0x + WR_AA_PIXEL_RADIUS; c1x = c1x - WR_AA_PIXEL_RADIUS;
+      c1y = c0y + WR_AA_PIXEL_RADIUS; aa_mask = 2; break;
+    case 3: c0x = c1x - WR_AA_PIXEL_RADIUS; aa_mask = 4; break;
+    case 4:
+      c0x = c0x + WR_AA_PIXEL_RADIUS; c1x = c1x - WR_AA_PIXEL_RADIUS;
+      c0y = c1y - WR_AA_PIXEL_RADIUS; aa_mask = 8; break;
+    case 0:
+      c0x += (edge_flags & 1) ? WR_AA_PIXEL_RADIUS : 0.0f;
+      c1x -= (edge_flags & 4) ? WR_AA_PIXEL_RADIUS : 0.0f;
+      c0y += (edge_flags & 2) ? WR_AA_PIXEL_RADIUS : 0.0f;
+      c1y -= (edge_flags & 8) ? WR_AA_PIXEL_RADIUS : 0.0f;
+      break;
+    default: aa_mask = edge_flags; break;
+  }
+  q.aa_edge_mask = aa_mask;
+  q.flags = aa_mask ? CMD_AA : 0;
+  float dps = task.device_pixel_scale;
+  if (quad_flags & WR_QF_IGNORE_DEVICE_SCALE) dps = 1.0f;
+  float fox = -task.ox + task.tx0, foy = -task.oy + task.ty0;
+  const float ax[4] = {0.0f, 1.0f, 1.0f, 0.0f}, ay[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+  for (int i = 0; i < 4; i++) {
+    float lpx = (c1x - c0x) * ax[i] + c0x, lpy = (c1y - c0y) * ay[i] + c0y;
+    float4 world = wr_mat_mul(transform.m, make_float4(lpx, lpy, 0.0f, 1.0f));
+    float dpx = world.x * dps, dpy = world.y * dps;
+    float vix = lpx, viy = lpy;
+    if (quad_flags & WR_QF_APPLY_DEVICE_CLIP) {
+      float d1x = task.ox + task.tx1 - task.tx0, d1y = task.oy + task.ty1 - task.ty0;
+      dpx = wr_clamp(dpx, task.ox, d1x);
+      dpy = wr_clamp(dpy, task.oy, d1y);
+      float4 r = wr_mat_mul(transform.inv_m, make_float4(dpx / dps, dpy / dps, 0.0f, 1.0f));
+      vix = r.x;
+      viy = r.y;
+    }
+    q.pos[i] = wr_mat_mul(a.tgt.proj, make_float4(dpx + fox * world.w, dpy + foy * world.w,
+                                                  z * world.w, world.w));
+    pi.local_pos[i] = make_float2(vix * so.x + so.z, viy * so.y + so.w);
+  }
+  pi.color[0] = t4.x; pi.color[1] = t4.y; pi.color[2] = t4.z; pi.color[3] = t4.w;
+  pi.seg_rect[0] = seg_rect.x * so.x + so.z; pi.seg_rect[1] = seg_rect.y * so.y + so.w;
+  pi.seg_rect[2] = seg_rect.z * so.x + so.z; pi.seg_rect[3] = seg_rect.w * so.y + so.w;
+  pi.seg_uv_rect[0] = seg_uv.x; pi.seg_uv_rect[1] = seg_uv.y;
+  pi.seg_uv_rect[2] = seg_uv.z; pi.seg_uv_rect[3] = seg_uv.w;
+  pi.prim_bounds[0] = t0.x * so.x + so.z; pi.prim_bounds[1] = t0.y * so.y + so.w;
+  pi.prim_bounds[2] = t0.z * so.x + so.z; pi.prim_bounds[3] = t0.w * so.y + so.w;
+  pi.prim_clip[0] = t1.x * so.x + so.z; pi.prim_clip[1] = t1.y * so.y + so.w;
+  pi.prim_clip[2] = t1.z * so.x + so.z; pi.prim_clip[3] = t1.w * so.y + so.w;
+  pi.edge_flags = edge_flags;
+  pi.quad_flags = quad_flags;
+}
+
+__global__ void wr_setup_quad_textured(SetupArgs a) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n) return;
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  QuadOut q;
+  QuadPrimInfo pi;
+  memset(&q, 0, sizeof q);
+  wr_quad_primitive_info(a, aData, q, pi);
+  float col[4] = {pi.color[0], pi.color[1], pi.color[2], pi.color[3]};
+  float bounds[4] = {0, 0, 0, 0};
+  q.n_interp = 0;
+  if (pi.quad_flags & WR_QF_IS_MASK) q.flags |= CMD_OUT_RRRR;
+  if (pi.seg_uv_rect[0] != pi.seg_uv_rect[2] || pi.seg_uv_rect[1] != pi.seg_uv_rect[3]) {
+    q.flags |= CMD_TEXTURED;
+    col[0] = col[1] = col[2] = col[3] = 1.0f;
+    float tw = (float)a.color0.w, th = (float)a.color0.h;
+    for (int i = 0; i < 4; i++) {
+      float fx = (pi.local_pos[i].x - pi.seg_rect[0]) / (pi.seg_rect[2] - pi.seg_rect[0]);
+      float fy = (pi.local_pos[i].y - pi.seg_rect[1]) / (pi.seg_rect[3] - pi.seg_rect[1]);
+      float ux = (pi.seg_uv_rect[2] - pi.seg_uv_rect[0]) * fx + pi.seg_uv_rect[0];
+      float uy = (pi.seg_uv_rect[3] - pi.seg_uv_rect[1]) * fy + pi.seg_uv_rect[1];
+      q.interp[i][0] = ux / tw;
+      q.interp[i][1] = uy / th;
+    }
+    q.n_interp = 2;
+    bounds[0] = (pi.seg_uv_rect[0] + 0.5f) / tw;
+    bounds[1] = (pi.seg_uv_rect[1] + 0.5f) / th;
+    bounds[2] = (pi.seg_uv_rect[2] - 0.5f) / tw;
+    bounds[3] = (pi.seg_uv_rect[3] - 0.5f) / th;
+  }
+  // pack_span / packColor: round_pixel then 16-bit lanes (B,G,R,A order)
+  q.col[0] = (uint16_t)wr_round_pixel(col[2], 255.0f);
+  q.col[1] = (uint16_t)wr_round_pixel(col[1], 255.0f);
+  q.col[2] = (uint16_t)wr_round_pixel(col[0], 255.0f);
+  q.col[3] = (uint16_t)wr_round_pixel(col[3], 255.0f);
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    k->f[0] = bounds[0]; k->f[1] = bounds[1]; k->f[2] = bounds[2]; k->f[3] = bounds[3];
+  }
+  if (unsupported) {
+    atomicAdd(&a.info->unsupported, 1);
+    atomicAdd(a.err_counter, 1);
+  }
+}

@@ -1,0 +1,598 @@
+// wrcu_api.cu — the C ABI of include/wrcu.h: context, textures, per-frame
+// tables, target binding, clears and the draw dispatch.  Host side of the
+// B200 backend; every pixel is produced by the CUDA kernels in raster.cuh /
+// setup_*.cuh.  There is no CPU rasterisation path in this library.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "raster.cuh"
+#include "setup_quad.cuh"
+#include "wrcu_internal.h"
+
+int wrcu_fail(wrcu_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+    if (!c->sticky_error) c->sticky_error = code;
+  }
+  return code;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int fmt_bpp(int fmt) {
+  switch (fmt) {
+    case WRCU_FMT_RGBA8: return 4;
+    case WRCU_FMT_R8: return 1;
+    case WRCU_FMT_RGBAF32: return 16;
+    case WRCU_FMT_RGBAI32: return 16;
+    case WRCU_FMT_DEPTH24: return 4;
+  }
+  return 0;
+}
+
+// ---- small kernels ---------------------------------------------------------------
+__global__ void wr_init_batch_info(BatchInfo* info) {
+  info->bx0 = 0x7fffffff; info->by0 = 0x7fffffff;
+  info->bx1 = -0x7fffffff; info->by1 = -0x7fffffff;
+  info->unsupported = 0;
+  info->simple = 1;
+}
+
+// Clear (swgl/src/gl.cc:2498-2518 → clear_buffer): fills a rect of a 4-byte or
+// 1-byte target.  Rows are written as 16-byte vectors where alignment allows.
+__global__ void wr_clear_u32(uint8_t* base, int pitch, int x0, int y0, int x1, int y1, uint32_t v) {
+  int y = y0 + blockIdx.y;
+  if (y >= y1) return;
+  uint32_t* row = (uint32_t*)(base + (size_t)y * pitch);
+  // vector body on 4-pixel boundaries
+  int xa = (x0 + 3) & ~3, xb = x1 & ~3;
+  if (xa >= xb) {
+    for (int x = x0 + blockIdx.x * blockDim.x + threadIdx.x; x < x1; x += gridDim.x * blockDim.x) row[x] = v;
+    return;
+  }
+  uint4 vv = make_uint4(v, v, v, v);
+  for (int x = xa + 4 * (blockIdx.x * blockDim.x + threadIdx.x); x < xb; x += 4 * gridDim.x * blockDim.x)
+    *(uint4*)(row + x) = vv;
+  if (blockIdx.x == 0) {
+    for (int x = x0 + threadIdx.x; x < xa; x += blockDim.x) row[x] = v;
+    for (int x = xb + threadIdx.x; x < x1; x += blockDim.x) row[x] = v;
+  }
+}
+__global__ void wr_clear_u8(uint8_t* base, int pitch, int x0, int y0, int x1, int y1, uint8_t v) {
+  int y = y0 + blockIdx.y;
+  if (y >= y1) return;
+  uint8_t* row = base + (size_t)y * pitch;
+  for (int x = x0 + blockIdx.x * blockDim.x + threadIdx.x; x < x1; x += gridDim.x * blockDim.x) row[x] = v;
+}
+
+// ---- context -----------------------------------------------------------------------
+extern "C" int wrcu_abi_version(void) { return WRCU_ABI_VERSION; }
+
+extern "C" const char* wrcu_get_string(int what) {
+  switch (what) {
+    case 0: return "Software WebRender";  // keeps is_software host behaviour (gl.cc:1214)
+    case 1: return "wrcu: B200 (sm_100a) tile-resident CUDA rasteriser";
+    default: return "";
+  }
+}
+
+static int arena_init(wrcu_ctx* c, Arena* a, size_t cap) {
+  a->cap = cap;
+  a->used = 0;
+  WRCU_CUDA(c, cudaMallocHost((void**)&a->host, cap));
+  WRCU_CUDA(c, cudaMalloc((void**)&a->dev, cap));
+  WRCU_CUDA(c, cudaEventCreateWithFlags(&a->done, cudaEventDisableTiming));
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
+  if (!out) return WRCU_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_ordinal < 0 || device_ordinal >= n)
+    return WRCU_ERR_NO_DEVICE;  // fail loudly: there is no CPU path
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) return WRCU_ERR_NO_DEVICE;
+  wrcu_ctx* c = new wrcu_ctx();
+  c->device = device_ordinal;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return WRCU_ERR_CUDA;
+  }
+  int rc;
+  if ((rc = arena_init(c, &c->arena[0], 64u << 20)) != WRCU_OK ||
+      (rc = arena_init(c, &c->arena[1], 64u << 20)) != WRCU_OK) {
+    delete c;
+    return rc;
+  }
+  cudaEventCreate(&c->t0);
+  cudaEventCreate(&c->t1);
+  if (cudaMalloc((void**)&c->batch_info, sizeof(BatchInfo)) != cudaSuccess ||
+      cudaMalloc((void**)&c->dev_err, sizeof(int)) != cudaSuccess) {
+    delete c;
+    return WRCU_ERR_OOM;
+  }
+  cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
+  *out = c;
+  return WRCU_OK;
+}
+
+extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < wrcu_ctx::MAX_TEX; i++)
+    if (c->tex[i].live) cudaFree(c->tex[i].dptr);
+  for (int i = 0; i < 2; i++) {
+    if (c->arena[i].host) cudaFreeHost(c->arena[i].host);
+    if (c->arena[i].dev) cudaFree(c->arena[i].dev);
+    if (c->arena[i].done) cudaEventDestroy(c->arena[i].done);
+  }
+  if (c->cmd_hot) cudaFree(c->cmd_hot);
+  if (c->cmd_cold) cudaFree(c->cmd_cold);
+  if (c->batch_info) cudaFree(c->batch_info);
+  if (c->dev_err) cudaFree(c->dev_err);
+  if (c->t0) cudaEventDestroy(c->t0);
+  if (c->t1) cudaEventDestroy(c->t1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int wrcu_get_error(wrcu_ctx* c) {
+  int e = c->sticky_error;
+  c->sticky_error = 0;
+  return e;
+}
+extern "C" const char* wrcu_last_error_string(wrcu_ctx* c) { return c ? c->err : "no context"; }
+
+static int sync_and_check(wrcu_ctx* c);
+extern "C" int wrcu_finish(wrcu_ctx* c) {
+  cudaSetDevice(c->device);
+  return sync_and_check(c);
+}
+
+extern "C" int wrcu_stream(wrcu_ctx* c, void** stream) {
+  *stream = (void*)c->stream;
+  return WRCU_OK;
+}
+
+// ---- arena ---------------------------------------------------------------------------
+// Stage `bytes` of host data for the device: copy into the pinned arena (so the
+// caller may free its buffer on return) and queue the H2D copy on the stream.
+static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
+  Arena* a = &c->arena[c->cur_arena];
+  size_t off = align_up(a->used, 256);
+  if (off + bytes > a->cap) {
+    // grow: finish outstanding work, then reallocate this arena larger
+    WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+    size_t ncap = align_up((off + bytes) * 2, 1u << 20);
+    uint8_t *nh = nullptr, *nd = nullptr;
+    WRCU_CUDA(c, cudaMallocHost((void**)&nh, ncap));
+    WRCU_CUDA(c, cudaMalloc((void**)&nd, ncap));
+    // earlier stagings of this frame are still referenced by queued kernels →
+    // they have completed (we synchronised), but tables may be used by later
+    // draws: keep contents by copying.
+    memcpy(nh, a->host, a->used);
+    WRCU_CUDA(c, cudaMemcpy(nd, a->dev, a->used, cudaMemcpyDeviceToDevice));
+    // rebase table pointers
+    ptrdiff_t delta = nd - a->dev;
+#define REBASE(p) if (p) p = (decltype(p))((uint8_t*)(p) + delta)
+    REBASE(c->tables.prim_headers_f); REBASE(c->tables.prim_headers_i);
+    REBASE(c->tables.transforms); REBASE(c->tables.render_tasks);
+    REBASE(c->tables.gpu_cache); REBASE(c->tables.gpu_buffer_f); REBASE(c->tables.gpu_buffer_i);
+#undef REBASE
+    cudaFreeHost(a->host);
+    cudaFree(a->dev);
+    a->host = nh;
+    a->dev = nd;
+    a->cap = ncap;
+  }
+  memcpy(a->host + off, src, bytes);
+  WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, bytes, cudaMemcpyHostToDevice, c->stream));
+  a->used = off + bytes;
+  c->stats.h2d_bytes += bytes;
+  *dev_out = a->dev + off;
+  return WRCU_OK;
+}
+
+// ---- textures ----------------------------------------------------------------------
+extern "C" int wrcu_texture_create(wrcu_ctx* c, int format, int w, int h, wrcu_tex* out) {
+  int bpp = fmt_bpp(format);
+  if (!bpp || w <= 0 || h <= 0 || w > 32768 || h > 32768 || !out)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "texture_create: bad arguments");
+  cudaSetDevice(c->device);
+  for (int i = 1; i < wrcu_ctx::MAX_TEX; i++) {
+    if (!c->tex[i].live) {
+      WrTexture& t = c->tex[i];
+      t.fmt = format; t.w = w; t.h = h; t.bpp = bpp; t.filter = WRCU_LINEAR;
+      // pitch covers whole raster tiles so tile-wide vector accesses stay inside
+      // the allocation; rows padded to tile height likewise.
+      t.pitch = align_up((size_t)align_up(w, WRCU_TILE_W) * bpp, 256);
+      size_t rows = align_up(h, WRCU_TILE_H);
+      WRCU_CUDA(c, cudaMalloc((void**)&t.dptr, t.pitch * rows));
+      WRCU_CUDA(c, cudaMemsetAsync(t.dptr, 0, t.pitch * rows, c->stream));
+      t.live = true;
+      *out = (wrcu_tex)i;
+      return WRCU_OK;
+    }
+  }
+  return wrcu_fail(c, WRCU_ERR_OOM, "texture_create: out of texture handles");
+}
+
+static WrTexture* get_tex(wrcu_ctx* c, wrcu_tex id) {
+  return (id > 0 && id < wrcu_ctx::MAX_TEX && c->tex[id].live) ? &c->tex[id] : nullptr;
+}
+
+extern "C" int wrcu_texture_set_filter(wrcu_ctx* c, wrcu_tex id, int filter) {
+  WrTexture* t = get_tex(c, id);
+  if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_set_filter: bad handle");
+  t->filter = filter;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_texture_upload(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, int h,
+                                   const void* data, size_t src_stride) {
+  WrTexture* t = get_tex(c, id);
+  if (!t || !data || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "texture_upload: bad arguments");
+  cudaSetDevice(c->device);
+  size_t row = (size_t)w * t->bpp;
+  // pack rows tightly into the pinned arena, then one strided async copy
+  Arena* a = &c->arena[c->cur_arena];
+  size_t need = row * h;
+  void* dsrc = nullptr;
+  if (src_stride == row) {
+    int rc = stage(c, data, need, &dsrc);
+    if (rc) return rc;
+  } else {
+    // stage row by row (host memcpy), single device copy
+    uint8_t* tmp = (uint8_t*)malloc(need);
+    if (!tmp) return wrcu_fail(c, WRCU_ERR_OOM, "texture_upload: host oom");
+    for (int r = 0; r < h; r++) memcpy(tmp + r * row, (const uint8_t*)data + (size_t)r * src_stride, row);
+    int rc = stage(c, tmp, need, &dsrc);
+    free(tmp);
+    if (rc) return rc;
+  }
+  (void)a;
+  WRCU_CUDA(c, cudaMemcpy2DAsync(t->dptr + (size_t)y * t->pitch + (size_t)x * t->bpp, t->pitch, dsrc, row,
+                                 row, h, cudaMemcpyDeviceToDevice, c->stream));
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_texture_destroy(wrcu_ctx* c, wrcu_tex id) {
+  WrTexture* t = get_tex(c, id);
+  if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_destroy: bad handle");
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(t->dptr);
+  *t = WrTexture();
+  if (c->color_tex == id) c->color_tex = 0;
+  if (c->depth_tex == id) c->depth_tex = 0;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_texture_device_ptr(wrcu_ctx* c, wrcu_tex id, void** dptr, size_t* pitch) {
+  WrTexture* t = get_tex(c, id);
+  if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_device_ptr: bad handle");
+  *dptr = t->dptr;
+  *pitch = t->pitch;
+  return WRCU_OK;
+}
+
+// Synchronise and surface instances the setup kernels could not rasterise
+// (rotated / perspective quads): reported once, as WRCU_ERR_UNSUPPORTED.
+static int sync_and_check(wrcu_ctx* c) {
+  int n = 0;
+  WRCU_CUDA(c, cudaMemcpyAsync(&n, c->dev_err, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+  WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n) {
+    cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED,
+                     "%d instance(s) need the general edge walker (rotation/perspective), not rasterised", n);
+  }
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_read_pixels(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, int h, void* out,
+                                size_t dst_stride) {
+  WrTexture* t = get_tex(c, id);
+  if (!t || !out || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "read_pixels: bad arguments");
+  cudaSetDevice(c->device);
+  size_t row = (size_t)w * t->bpp;
+  WRCU_CUDA(c, cudaMemcpy2DAsync(out, dst_stride, t->dptr + (size_t)y * t->pitch + (size_t)x * t->bpp,
+                                 t->pitch, row, h, cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += row * h;
+  return sync_and_check(c);
+}
+
+// ---- frame ---------------------------------------------------------------------------
+extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
+  if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null tables");
+  cudaSetDevice(c->device);
+  // switch arena; wait until the frame that last used it has drained
+  c->cur_arena ^= 1;
+  Arena* a = &c->arena[c->cur_arena];
+  if (a->in_flight) {
+    WRCU_CUDA(c, cudaEventSynchronize(a->done));
+    a->in_flight = false;
+  }
+  a->used = 0;
+  int rc;
+  void* p;
+#define TAB(field, count, T)                                                     \
+  c->tables.field = nullptr;                                                     \
+  c->tables.n_##field = (int)t->count;                                           \
+  if (t->count) {                                                                \
+    if (!t->field) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null " #field); \
+    if ((rc = stage(c, t->field, t->count * 16, &p)) != WRCU_OK) return rc;      \
+    c->tables.field = (const T*)p;                                               \
+  }
+  TAB(prim_headers_f, prim_headers_f_texels, float4)
+  TAB(prim_headers_i, prim_headers_i_texels, int4)
+  TAB(transforms, transforms_texels, float4)
+  TAB(render_tasks, render_tasks_texels, float4)
+  TAB(gpu_cache, gpu_cache_texels, float4)
+  TAB(gpu_buffer_f, gpu_buffer_f_texels, float4)
+  TAB(gpu_buffer_i, gpu_buffer_i_texels, int4)
+#undef TAB
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_frame_end(wrcu_ctx* c) {
+  cudaSetDevice(c->device);
+  Arena* a = &c->arena[c->cur_arena];
+  WRCU_CUDA(c, cudaEventRecord(a->done, c->stream));
+  a->in_flight = true;
+  return WRCU_OK;
+}
+
+// ---- targets -------------------------------------------------------------------------
+extern "C" int wrcu_target_bind(wrcu_ctx* c, wrcu_tex color, wrcu_tex depth, const float projection[16],
+                                const int32_t viewport[4]) {
+  WrTexture* t = get_tex(c, color);
+  if (!t || (t->fmt != WRCU_FMT_RGBA8 && t->fmt != WRCU_FMT_R8) || !projection || !viewport)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "target_bind: bad colour target");
+  if (depth) {
+    WrTexture* d = get_tex(c, depth);
+    if (!d || d->fmt != WRCU_FMT_DEPTH24 || d->w != t->w || d->h != t->h)
+      return wrcu_fail(c, WRCU_ERR_INVALID, "target_bind: bad depth target");
+  }
+  c->color_tex = color;
+  c->depth_tex = depth;
+  memcpy(c->proj, projection, sizeof c->proj);
+  memcpy(c->vp, viewport, sizeof c->vp);
+  return WRCU_OK;
+}
+
+static inline int host_round_pixel(float v) { return (int)(v * 255.0f + 0.5f); }
+
+extern "C" int wrcu_clear(wrcu_ctx* c, const int32_t rect[4], const float color[4], const float* depth) {
+  WrTexture* t = get_tex(c, c->color_tex);
+  if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "clear: no target bound");
+  cudaSetDevice(c->device);
+  int x0 = 0, y0 = 0, x1 = t->w, y1 = t->h;
+  if (rect) {
+    x0 = rect[0] > 0 ? rect[0] : 0;
+    y0 = rect[1] > 0 ? rect[1] : 0;
+    x1 = rect[0] + rect[2] < t->w ? rect[0] + rect[2] : t->w;
+    y1 = rect[1] + rect[3] < t->h ? rect[1] + rect[3] : t->h;
+  }
+  if (x1 <= x0 || y1 <= y0) return WRCU_OK;
+  dim3 grid((unsigned)((x1 - x0 + 1023) / 1024), (unsigned)(y1 - y0));
+  if (grid.x > 8) grid.x = 8;
+  if (color) {
+    // ClearTexSubImage: round_pixel, truncating U8 convert, BGRA swizzle (gl.cc:2426-2481)
+    uint32_t r = host_round_pixel(color[0]) & 0xFF, g = host_round_pixel(color[1]) & 0xFF;
+    uint32_t b = host_round_pixel(color[2]) & 0xFF, a = host_round_pixel(color[3]) & 0xFF;
+    if (t->fmt == WRCU_FMT_RGBA8)
+      wr_clear_u32<<<grid, 256, 0, c->stream>>>(t->dptr, (int)t->pitch, x0, y0, x1, y1,
+                                               b | (g << 8) | (r << 16) | (a << 24));
+    else
+      wr_clear_u8<<<grid, 256, 0, c->stream>>>(t->dptr, (int)t->pitch, x0, y0, x1, y1, (uint8_t)r);
+    c->stats.kernel_launches++;
+  }
+  if (depth && c->depth_tex) {
+    WrTexture* d = get_tex(c, c->depth_tex);
+    uint32_t z = (uint32_t)((double)*depth * 0xFFFFFF);  // gl.cc:2391
+    wr_clear_u32<<<grid, 256, 0, c->stream>>>(d->dptr, (int)d->pitch, x0, y0, x1, y1, z);
+    c->stats.kernel_launches++;
+  }
+  WRCU_CUDA(c, cudaGetLastError());
+  return WRCU_OK;
+}
+
+// ---- draws ---------------------------------------------------------------------------
+static TexView tex_view(wrcu_ctx* c, wrcu_tex id) {
+  TexView v;
+  memset(&v, 0, sizeof v);
+  WrTexture* t = get_tex(c, id);
+  if (!t) {
+    v.w = v.h = 1;  // null sampler (gl.cc:894-905); ptr stays null → callers check
+    return v;
+  }
+  v.ptr = t->dptr;
+  v.w = t->w;
+  v.h = t->h;
+  v.pitch = (int)t->pitch;
+  v.filter = t->w >= 2 ? t->filter : WRCU_NEAREST;  // init_filter, gl.cc:870-877
+  v.fmt = t->fmt;
+  return v;
+}
+
+static int ensure_cmd_capacity(wrcu_ctx* c, size_t n) {
+  if (n <= c->cmd_cap) return WRCU_OK;
+  WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->cmd_hot) cudaFree(c->cmd_hot);
+  if (c->cmd_cold) cudaFree(c->cmd_cold);
+  c->cmd_hot = c->cmd_cold = nullptr;
+  size_t cap = align_up(n * 2, 1024);
+  WRCU_CUDA(c, cudaMalloc(&c->cmd_hot, cap * sizeof(CmdHot)));
+  WRCU_CUDA(c, cudaMalloc(&c->cmd_cold, cap * sizeof(CmdCold)));
+  c->cmd_cap = cap;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const wrcu_draw_state* st,
+                               const void* instances, size_t stride, int n) {
+  (void)features;
+  if (!st || !instances || n < 0 || stride == 0)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: bad arguments");
+  if (n == 0) return WRCU_OK;
+  WrTexture* tgt = get_tex(c, c->color_tex);
+  if (!tgt) return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: no target bound");
+  if (st->blend < 0 || st->blend >= WRCU_BLEND__COUNT)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: bad blend key");
+  if (st->blend == WRCU_BLEND_SUBPIXEL_DUAL_SOURCE && kind != WRCU_KIND_TEXT_RUN)
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "dual-source blending outside text runs");
+  cudaSetDevice(c->device);
+  c->stats.draw_calls++;
+  c->stats.instances += (uint64_t)n;
+
+  int rc;
+  void* dinst = nullptr;
+  if ((rc = stage(c, instances, stride * (size_t)n, &dinst)) != WRCU_OK) return rc;
+  if ((rc = ensure_cmd_capacity(c, (size_t)n)) != WRCU_OK) return rc;
+
+  TargetDev T;
+  memset(&T, 0, sizeof T);
+  T.color = tgt->dptr;
+  T.color_pitch = (int)tgt->pitch;
+  T.fmt = tgt->fmt;
+  T.w = tgt->w;
+  T.h = tgt->h;
+  WrTexture* dep = (st->depth != WRCU_DEPTH_OFF) ? get_tex(c, c->depth_tex) : nullptr;
+  T.depth = dep ? (uint32_t*)dep->dptr : nullptr;
+  T.depth_pitch = dep ? (int)dep->pitch : 0;
+  memcpy(T.proj, c->proj, sizeof T.proj);
+  memcpy(T.vp, c->vp, sizeof T.vp);
+  T.cx0 = 0; T.cy0 = 0; T.cx1 = tgt->w; T.cy1 = tgt->h;
+  if (st->scissor_enabled) {
+    T.cx0 = max(T.cx0, st->scissor[0]);
+    T.cy0 = max(T.cy0, st->scissor[1]);
+    T.cx1 = min(T.cx1, st->scissor[0] + st->scissor[2]);
+    T.cy1 = min(T.cy1, st->scissor[1] + st->scissor[3]);
+  }
+
+  SetupArgs sa;
+  memset(&sa, 0, sizeof sa);
+  sa.tabs = c->tables;
+  sa.tgt = T;
+  sa.instances = (const uint8_t*)dinst;
+  sa.stride = (int)stride;
+  sa.n = n;
+  sa.hot = (CmdHot*)c->cmd_hot;
+  sa.cold = (CmdCold*)c->cmd_cold;
+  sa.info = (BatchInfo*)c->batch_info;
+  sa.err_counter = c->dev_err;
+  sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
+  sa.color0 = tex_view(c, st->color[0]);
+  sa.clip_mask = tex_view(c, st->clip_mask);
+
+  wr_init_batch_info<<<1, 1, 0, c->stream>>>((BatchInfo*)c->batch_info);
+  c->stats.kernel_launches++;
+  int sblocks = (n + 127) / 128;
+  switch (kind) {
+    case WRCU_KIND_QUAD_TEXTURED:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "quad instance stride < 16");
+      wr_setup_quad_textured<<<sblocks, 128, 0, c->stream>>>(sa);
+      break;
+    default:
+      return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);
+  }
+  c->stats.kernel_launches++;
+
+  RasterArgs ra;
+  memset(&ra, 0, sizeof ra);
+  ra.tgt = T;
+  ra.hot = (const CmdHot*)c->cmd_hot;
+  ra.cold = (const CmdCold*)c->cmd_cold;
+  ra.info = (const BatchInfo*)c->batch_info;
+  ra.n = n;
+  ra.blend = st->blend;
+  ra.depth_mode = T.depth ? st->depth : WRCU_DEPTH_OFF;
+  ra.blend_color = Px{host_round_pixel(st->blend_color[2]) & 0xFFFF, host_round_pixel(st->blend_color[1]) & 0xFFFF,
+                      host_round_pixel(st->blend_color[0]) & 0xFFFF, host_round_pixel(st->blend_color[3]) & 0xFFFF};
+  ra.color0 = sa.color0;
+  dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
+  if (grid.x == 0 || grid.y == 0) return WRCU_OK;
+  // Device-side dispatch: the setup kernel decides whether the whole batch is
+  // plain solid quads; the specialised and the generic kernel each return at
+  // once when it is not their turn (the host never has to wait for the flag).
+  bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
+                 ra.depth_mode == WRCU_DEPTH_OFF;
+  ra.fast_eligible = fast_ok ? 1 : 0;
+  if (fast_ok) {
+    wr_raster_solid_premult<<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
+    c->stats.kernel_launches++;
+  }
+  if (T.fmt == WRCU_FMT_RGBA8)
+    wr_raster_quads<WRCU_FMT_RGBA8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
+  else
+    wr_raster_quads<WRCU_FMT_R8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
+  c->stats.kernel_launches++;
+  WRCU_CUDA(c, cudaGetLastError());
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* features) {
+  if (!key || !kind || !features) return WRCU_ERR_INVALID;
+  static const struct { const char* name; int kind; } names[] = {
+      {"ps_quad_textured", WRCU_KIND_QUAD_TEXTURED}, {"ps_quad_mask", WRCU_KIND_QUAD_MASK},
+      {"brush_solid", WRCU_KIND_BRUSH_SOLID}, {"brush_image", WRCU_KIND_BRUSH_IMAGE},
+      {"brush_linear_gradient", WRCU_KIND_BRUSH_LINEAR_GRADIENT}, {"brush_blend", WRCU_KIND_BRUSH_BLEND},
+      {"brush_mix_blend", WRCU_KIND_BRUSH_MIX_BLEND}, {"brush_opacity", WRCU_KIND_BRUSH_OPACITY},
+      {"ps_text_run", WRCU_KIND_TEXT_RUN}, {"cs_clip_rectangle", WRCU_KIND_CLIP_RECTANGLE},
+      {"cs_clip_box_shadow", WRCU_KIND_CLIP_BOX_SHADOW}, {"composite", WRCU_KIND_COMPOSITE},
+      {"ps_clear", WRCU_KIND_CLEAR}, {"cs_blur", WRCU_KIND_BLUR}, {"cs_scale", WRCU_KIND_SCALE}};
+  static const struct { const char* name; uint32_t bit; } feats[] = {
+      {"ALPHA_PASS", WRCU_FEAT_ALPHA_PASS}, {"FAST_PATH", WRCU_FEAT_FAST_PATH},
+      {"ANTIALIASING", WRCU_FEAT_ANTIALIASING}, {"REPETITION", WRCU_FEAT_REPETITION},
+      {"DUAL_SOURCE_BLENDING", WRCU_FEAT_DUAL_SOURCE_BLENDING}, {"ADVANCED_BLEND", WRCU_FEAT_ADVANCED_BLEND},
+      {"GLYPH_TRANSFORM", WRCU_FEAT_GLYPH_TRANSFORM}, {"TEXTURE_2D", WRCU_FEAT_TEXTURE_2D}};
+  const char* sp = strchr(key, ' ');
+  size_t nlen = sp ? (size_t)(sp - key) : strlen(key);
+  *kind = 0;
+  for (auto& e : names)
+    if (strlen(e.name) == nlen && !strncmp(e.name, key, nlen)) *kind = e.kind;
+  if (!*kind) return WRCU_ERR_UNSUPPORTED;
+  *features = 0;
+  const char* p = sp ? sp + 1 : nullptr;
+  while (p && *p) {
+    const char* comma = strchr(p, ',');
+    size_t flen = comma ? (size_t)(comma - p) : strlen(p);
+    bool found = false;
+    for (auto& f : feats)
+      if (strlen(f.name) == flen && !strncmp(f.name, p, flen)) {
+        *features |= f.bit;
+        found = true;
+      }
+    if (!found) return WRCU_ERR_UNSUPPORTED;  // TEXTURE_RECT, YUV, DEBUG_OVERDRAW, ...
+    p = comma ? comma + 1 : nullptr;
+  }
+  return WRCU_OK;
+}
+
+// ---- stats / timing ---------------------------------------------------------------------
+extern "C" int wrcu_get_stats(wrcu_ctx* c, wrcu_stats* out) {
+  *out = c->stats;
+  return WRCU_OK;
+}
+extern "C" int wrcu_reset_stats(wrcu_ctx* c) {
+  memset(&c->stats, 0, sizeof c->stats);
+  return WRCU_OK;
+}
+extern "C" int wrcu_timer_begin(wrcu_ctx* c) {
+  WRCU_CUDA(c, cudaEventRecord(c->t0, c->stream));
+  return WRCU_OK;
+}
+extern "C" int wrcu_timer_end(wrcu_ctx* c, float* ms) {
+  WRCU_CUDA(c, cudaEventRecord(c->t1, c->stream));
+  WRCU_CUDA(c, cudaEventSynchronize(c->t1));
+  WRCU_CUDA(c, cudaEventElapsedTime(ms, c->t0, c->t1));
+  return WRCU_OK;
+}

@@ -1,0 +1,114 @@
+// wrcu_internal.h — private definitions of the B200 frame-draw backend.
+//
+// Layout of the implementation (all sm_100a CUDA, no CPU fallback):
+//   wrcu_api.cu      C ABI (include/wrcu.h): context, textures, frame tables,
+//                    target binding, clears, draw dispatch.
+//   cmd.cuh          DrawCmd records produced by the per-kind "setup" kernels
+//                    (= the reference's vertex stage, one thread per instance).
+//   blend.cuh        The blend stage (bit-identical integer math to
+//                    swgl/src/blend.h) as device functions.
+//   raster.cuh       Tile-resident raster kernels: one CTA owns a 128x8-pixel
+//                    framebuffer tile, keeps it in registers, walks the batch's
+//                    commands IN ORDER, blends, and writes the tile once.
+//   setup_*.cuh      Vertex stages per BatchKind.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/wrcu.h"
+
+#define WRCU_TILE_W 128
+#define WRCU_TILE_H 8
+#define WRCU_THREADS 256
+
+struct WrTexture {
+  int fmt = 0, w = 0, h = 0, bpp = 0, filter = WRCU_LINEAR;
+  size_t pitch = 0;
+  uint8_t* dptr = nullptr;
+  bool live = false;
+};
+
+// Device-side view of a texture (passed by value to kernels).
+struct TexView {
+  const uint8_t* ptr;
+  int w, h;
+  int pitch;   // bytes
+  int filter;  // WRCU_NEAREST / WRCU_LINEAR (already demoted if w < 2)
+  int fmt;
+};
+
+// Device pointers to the per-frame data tables (16-byte texels).
+struct FrameTablesDev {
+  const float4* prim_headers_f; int n_prim_headers_f;
+  const int4* prim_headers_i;   int n_prim_headers_i;
+  const float4* transforms;     int n_transforms;
+  const float4* render_tasks;   int n_render_tasks;
+  const float4* gpu_cache;      int n_gpu_cache;
+  const float4* gpu_buffer_f;   int n_gpu_buffer_f;
+  const int4* gpu_buffer_i;     int n_gpu_buffer_i;
+};
+
+// Bound render target + the state draw_quad depends on
+// (swgl/src/rasterize.h:1549-1632).
+struct TargetDev {
+  uint8_t* color;
+  int color_pitch;
+  int fmt;  // WRCU_FMT_RGBA8 | WRCU_FMT_R8
+  int w, h;
+  uint32_t* depth;  // nullptr when no depth test for this draw
+  int depth_pitch;
+  float proj[16];
+  int vp[4];
+  // scissor ∩ target bounds, as ints
+  int cx0, cy0, cx1, cy1;
+};
+
+// Bump arena: pinned host staging + device mirror, double-buffered per frame.
+struct Arena {
+  uint8_t* host = nullptr;
+  uint8_t* dev = nullptr;
+  size_t cap = 0, used = 0;
+  cudaEvent_t done = nullptr;  // recorded at frame end
+  bool in_flight = false;
+};
+
+struct wrcu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sticky_error = 0;
+  char err[512] = {0};
+  static const int MAX_TEX = 8192;
+  WrTexture tex[MAX_TEX];
+  FrameTablesDev tables = {};
+  // target
+  wrcu_tex color_tex = 0, depth_tex = 0;
+  float proj[16] = {0};
+  int vp[4] = {0, 0, 0, 0};
+  // arenas
+  Arena arena[2];
+  int cur_arena = 0;
+  // scratch for commands
+  void* cmd_hot = nullptr;
+  void* cmd_cold = nullptr;
+  int* batch_info = nullptr;  // bbox etc.
+  int* dev_err = nullptr;     // count of instances rejected by setup kernels (sticky until read)
+  size_t cmd_cap = 0;
+  // stats / timing
+  wrcu_stats stats = {};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  int sm_count = 148;
+};
+
+int wrcu_fail(wrcu_ctx* c, int code, const char* fmt, ...);
+
+#define WRCU_CUDA(c, call)                                                     \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess)                                                     \
+      return wrcu_fail((c), e_ == cudaErrorMemoryAllocation ? WRCU_ERR_OOM     \
+                                                            : WRCU_ERR_CUDA,   \
+                       "%s failed: %s", #call, cudaGetErrorString(e_));        \
+  } while (0)

@@ -1,0 +1,182 @@
+"""ctypes binding of libwrcu.so (include/wrcu.h): the product device.
+
+Fails loudly when the CUDA library or a CUDA device is missing — there is no
+CPU path in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwrcu.so")
+
+
+class WrcuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"wrcu error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise WrcuError(abi.ERR_NO_DEVICE,
+                        f"{path} not built — run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    lib.wrcu_last_error_string.restype = C.c_char_p
+    lib.wrcu_get_string.restype = C.c_char_p
+    return lib
+
+
+def bind_prefixed(lib, prefix):
+    """Give `lib`'s `<prefix>_*` device entry points the shared argtypes."""
+    def f(name):
+        return getattr(lib, prefix + name)
+    vp, i32, u32, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_size_t
+    f("texture_create").argtypes = [vp, i32, i32, i32, C.POINTER(u32)]
+    f("texture_set_filter").argtypes = [vp, u32, i32]
+    f("texture_upload").argtypes = [vp, u32, i32, i32, i32, i32, vp, sz]
+    f("texture_destroy").argtypes = [vp, u32]
+    f("read_pixels").argtypes = [vp, u32, i32, i32, i32, i32, vp, sz]
+    f("frame_begin").argtypes = [vp, C.POINTER(abi.FrameTables)]
+    f("frame_end").argtypes = [vp]
+    f("target_bind").argtypes = [vp, u32, u32, C.POINTER(C.c_float), C.POINTER(i32)]
+    f("clear").argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    f("draw_batch").argtypes = [vp, i32, u32, C.POINTER(abi.DrawState), vp, sz, i32]
+    f("last_error_string").argtypes = [vp]
+    f("last_error_string").restype = C.c_char_p
+
+
+class DeviceBase:
+    """Shared marshalling for any library exporting the wrcu device calls under
+    a prefix (`wrcu_` for the CUDA backend)."""
+    prefix = "wrcu_"
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WrcuError(rc, self._f("last_error_string")(self.ctx).decode())
+
+    def texture_create(self, fmt, w, h):
+        out = C.c_uint32(0)
+        self._check(self._f("texture_create")(self.ctx, fmt, w, h, C.byref(out)))
+        return out.value
+
+    def texture_set_filter(self, tex, filt):
+        self._check(self._f("texture_set_filter")(self.ctx, tex, filt))
+
+    def texture_upload(self, tex, x, y, w, h, data):
+        data = np.ascontiguousarray(data)
+        rows = data.view(np.uint8).reshape(h, -1)
+        self._check(self._f("texture_upload")(self.ctx, tex, x, y, w, h, rows.ctypes.data, rows.strides[0]))
+
+    def texture_destroy(self, tex):
+        self._check(self._f("texture_destroy")(self.ctx, tex))
+
+    def read_pixels(self, tex, x, y, w, h, bpp):
+        out = np.empty((h, w * bpp), dtype=np.uint8)
+        self._check(self._f("read_pixels")(self.ctx, tex, x, y, w, h, out.ctypes.data, out.strides[0]))
+        return out
+
+    def frame_begin(self, tables):
+        t = abi.FrameTables()
+        self._keep = []
+        for name in ("prim_headers_f", "prim_headers_i", "transforms", "render_tasks", "gpu_cache",
+                     "gpu_buffer_f", "gpu_buffer_i"):
+            arr = np.ascontiguousarray(tables[name])
+            self._keep.append(arr)
+            setattr(t, name, arr.ctypes.data if arr.size else None)
+            setattr(t, name + "_texels", arr.size // 4)
+        self._check(self._f("frame_begin")(self.ctx, C.byref(t)))
+
+    def frame_end(self):
+        self._check(self._f("frame_end")(self.ctx))
+
+    def target_bind(self, color, depth, projection, viewport):
+        proj = (C.c_float * 16)(*[float(v) for v in projection])
+        vp = (C.c_int32 * 4)(*viewport)
+        self._check(self._f("target_bind")(self.ctx, color, depth, proj, vp))
+
+    def clear(self, rect, color, depth):
+        r = (C.c_int32 * 4)(*rect) if rect is not None else None
+        col = (C.c_float * 4)(*color) if color is not None else None
+        d = C.byref(C.c_float(depth)) if depth is not None else None
+        self._check(self._f("clear")(self.ctx, r, col, C.cast(d, C.POINTER(C.c_float)) if d is not None else None))
+
+    def draw_batch(self, kind, features, blend, depth, colors, clip_mask, scissor, blend_color, inst):
+        st = abi.DrawState()
+        st.blend, st.depth = blend, depth
+        for i in range(3):
+            st.color[i] = colors[i]
+        st.clip_mask = clip_mask
+        st.scissor_enabled = 1 if scissor is not None else 0
+        if scissor is not None:
+            for i in range(4):
+                st.scissor[i] = scissor[i]
+        for i in range(4):
+            st.blend_color[i] = blend_color[i]
+        inst = np.ascontiguousarray(inst)
+        n, stride = inst.shape
+        self._check(self._f("draw_batch")(self.ctx, kind, features, C.byref(st), inst.ctypes.data, stride, n))
+
+
+class CudaDevice(DeviceBase):
+    """wrcu context on one B200 (one per process / GPU)."""
+    prefix = "wrcu_"
+
+    def __init__(self, device_ordinal=0, lib_path=LIB_PATH):
+        self.lib = load_library(lib_path)
+        bind_prefixed(self.lib, "wrcu_")
+        self.lib.wrcu_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        self.lib.wrcu_ctx_destroy.argtypes = [C.c_void_p]
+        self.lib.wrcu_finish.argtypes = [C.c_void_p]
+        self.lib.wrcu_get_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
+        self.lib.wrcu_reset_stats.argtypes = [C.c_void_p]
+        self.lib.wrcu_timer_begin.argtypes = [C.c_void_p]
+        self.lib.wrcu_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        self.lib.wrcu_texture_device_ptr.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p),
+                                                     C.POINTER(C.c_size_t)]
+        self.lib.wrcu_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        ctx = C.c_void_p()
+        rc = self.lib.wrcu_ctx_create(device_ordinal, C.byref(ctx))
+        if rc != 0:
+            raise WrcuError(rc, "wrcu_ctx_create failed: no usable CUDA device (this backend has no CPU path)")
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.wrcu_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def finish(self):
+        self._check(self.lib.wrcu_finish(self.ctx))
+
+    def stats(self):
+        s = abi.Stats()
+        self.lib.wrcu_get_stats(self.ctx, C.byref(s))
+        return {k: getattr(s, k) for k, _ in abi.Stats._fields_}
+
+    def reset_stats(self):
+        self.lib.wrcu_reset_stats(self.ctx)
+
+    def timer_begin(self):
+        self._check(self.lib.wrcu_timer_begin(self.ctx))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        self._check(self.lib.wrcu_timer_end(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def texture_device_ptr(self, tex):
+        p, pitch = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.wrcu_texture_device_ptr(self.ctx, tex, C.byref(p), C.byref(pitch)))
+        return p.value, pitch.value
+
+    def stream(self):
+        s = C.c_void_p()
+        self.lib.wrcu_stream(self.ctx, C.byref(s))
+        return s.value

@@ -1,0 +1,153 @@
+"""Binary layouts of the batch inputs the frame-draw path consumes.
+
+Host-side encoders for the `#[repr(C)]` records of webrender/src/gpu_types.rs
+and the per-frame data tables.  These are what the
+reference's frame builder (CPU, out of scope) hands to `Renderer::draw_frame`;
+tests and benchmarks use them to synthesise frames.
+"""
+import numpy as np
+
+# QuadFlags, webrender/src/command_buffer.rs:76 / ps_quad.glsl:62-66
+QF_IS_OPAQUE = 1
+QF_APPLY_DEVICE_CLIP = 2
+QF_IGNORE_DEVICE_SCALE = 4
+QF_USE_AA_SEGMENTS = 8
+QF_IS_MASK = 16
+
+EDGE_AA_LEFT, EDGE_AA_TOP, EDGE_AA_RIGHT, EDGE_AA_BOTTOM = 1, 2, 4, 8
+PART_CENTER, PART_LEFT, PART_TOP, PART_RIGHT, PART_BOTTOM, PART_ALL = range(6)
+INVALID_SEGMENT_INDEX = 0xFF
+
+CLIP_TASK_EMPTY = 0x7FFFFFFF  # render_task.glsl:75
+
+IDENTITY = np.eye(4, dtype=np.float32)
+
+
+def ortho(width, height, near=-float(1 << 22), far=float((1 << 22) - 1)):
+    """Transform3D::ortho(0, w, 0, h, near, far) as the reference passes it to
+    uTransform (renderer/mod.rs:4705-4712, device/gl.rs:2040-2046); returned
+    column-major, 16 floats (euclid: m11..m44 row-vector convention == GL
+    column-major upload)."""
+    left, right, bottom, top = np.float32(0), np.float32(width), np.float32(0), np.float32(height)
+    near, far = np.float32(near), np.float32(far)
+    tx = -((right + left) / (right - left))
+    ty = -((top + bottom) / (top - bottom))
+    tz = -((far + near) / (far - near))
+    m = np.zeros(16, dtype=np.float32)
+    m[0] = np.float32(2) / (right - left)
+    m[5] = np.float32(2) / (top - bottom)
+    m[10] = np.float32(-2) / (far - near)
+    m[12], m[13], m[14], m[15] = tx, ty, tz, 1
+    return m
+
+
+def scale_offset_transform(sx=1.0, sy=1.0, tx=0.0, ty=0.0):
+    m = np.eye(4, dtype=np.float32)
+    m[0, 0], m[1, 1], m[0, 3], m[1, 3] = sx, sy, tx, ty
+    return m
+
+
+class FrameTables:
+    """The per-frame data tables (`Frame.prim_headers`, `transform_palette`,
+    `render_tasks`, gpu cache, `gpu_buffer_f/i`; frame_builder.rs:1129-1180).
+    All tables are arrays of 16-byte texels."""
+
+    def __init__(self):
+        self.prim_headers_f = []   # 2 texels / prim
+        self.prim_headers_i = []   # 2 texels / prim
+        self.transforms = []       # 8 texels / transform
+        self.render_tasks = []     # 2 texels / task
+        self.gpu_cache = []
+        self.gpu_buffer_f = []
+        self.gpu_buffer_i = []
+        self.add_transform(IDENTITY)  # TransformPaletteId::IDENTITY == 0
+
+    # -- transform palette (gpu_types.rs:736-768, transform.glsl:22-46) -----
+    def add_transform(self, m, inv=None, axis_aligned=True):
+        """m: 4x4 matrix in math (row, col) convention; stored column-major."""
+        m = np.asarray(m, dtype=np.float32).reshape(4, 4)
+        if inv is None:
+            inv = np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+        idx = len(self.transforms) // 8
+        for mat in (m, inv):
+            for col in range(4):
+                self.transforms.append(mat[:, col].astype(np.float32).copy())
+        return idx | (0 if axis_aligned else (1 << 23))
+
+    # -- render tasks (render_task.rs:723-836, render_task.glsl) ------------
+    def add_render_task(self, rect, device_pixel_scale=1.0, content_origin=(0.0, 0.0)):
+        addr = len(self.render_tasks) // 2
+        self.render_tasks.append(np.array(rect, dtype=np.float32))
+        self.render_tasks.append(np.array([device_pixel_scale, content_origin[0], content_origin[1], 0.0],
+                                          dtype=np.float32))
+        return addr
+
+    def push_gpu_cache(self, blocks):
+        addr = len(self.gpu_cache)
+        for b in blocks:
+            self.gpu_cache.append(np.asarray(b, dtype=np.float32).reshape(4))
+        return addr
+
+    def push_gpu_buffer_f(self, blocks):
+        addr = len(self.gpu_buffer_f)
+        for b in blocks:
+            self.gpu_buffer_f.append(np.asarray(b, dtype=np.float32).reshape(4))
+        return addr
+
+    def push_gpu_buffer_i(self, block):
+        addr = len(self.gpu_buffer_i)
+        self.gpu_buffer_i.append(np.asarray(block, dtype=np.int32).reshape(4))
+        return addr
+
+    # -- prim headers (gpu_types.rs:476-493, prim_shared.glsl:77-96) --------
+    def add_prim_header(self, local_rect, local_clip_rect, z, specific_prim_address, transform_id,
+                        render_task_address, user_data=(0, 0, 0, 0)):
+        idx = len(self.prim_headers_f) // 2
+        self.prim_headers_f.append(np.array(local_rect, dtype=np.float32))
+        self.prim_headers_f.append(np.array(local_clip_rect, dtype=np.float32))
+        self.prim_headers_i.append(np.array([z, specific_prim_address, transform_id, render_task_address],
+                                            dtype=np.int32))
+        self.prim_headers_i.append(np.array(user_data, dtype=np.int64).astype(np.int32))
+        return idx
+
+    # -- quads (quad.rs:941-1001, ps_quad.glsl:96-145) -------------------------
+    def add_quad_prim(self, bounds, clip, color, uv_rect=(0, 0, 0, 0), scale_offset=(1, 1, 0, 0),
+                      segments=()):
+        """write_prim_blocks: 5 blocks + 2 per segment (rect, uv rect)."""
+        blocks = [bounds, clip, uv_rect, scale_offset, color]
+        for rect, uv in segments:
+            blocks += [rect, uv]
+        return self.push_gpu_buffer_f(blocks)
+
+    def add_quad_header(self, transform_id, z_id, pattern_input=(0, 0)):
+        return self.push_gpu_buffer_i([transform_id, z_id, pattern_input[0], pattern_input[1]])
+
+    def arrays(self):
+        def f(lst):
+            return (np.ascontiguousarray(np.stack(lst).astype(np.float32)) if lst
+                    else np.zeros((0, 4), np.float32))
+
+        def i(lst):
+            return (np.ascontiguousarray(np.stack(lst).astype(np.int32)) if lst
+                    else np.zeros((0, 4), np.int32))
+        return {
+            "prim_headers_f": f(self.prim_headers_f), "prim_headers_i": i(self.prim_headers_i),
+            "transforms": f(self.transforms), "render_tasks": f(self.render_tasks),
+            "gpu_cache": f(self.gpu_cache), "gpu_buffer_f": f(self.gpu_buffer_f),
+            "gpu_buffer_i": i(self.gpu_buffer_i),
+        }
+
+
+def quad_instance(prim_address_i, prim_address_f, quad_flags, edge_flags, part_index, segment_index,
+                  render_task_address):
+    """QuadInstance → PrimitiveInstanceData (gpu_types.rs:554-587)."""
+    z = ((quad_flags & 0xFF) << 24) | ((edge_flags & 0xFF) << 16) | ((part_index & 0xFF) << 8) | (segment_index & 0xFF)
+    return np.array([prim_address_i, prim_address_f, z, render_task_address], dtype=np.int64).astype(np.int32)
+
+
+def brush_instance(prim_header_index, clip_task_address, segment_index, edge_flags, brush_flags,
+                   resource_address):
+    """BrushInstance → PrimitiveInstanceData (gpu_types.rs:681-703)."""
+    z = (segment_index & 0xFFFF) | ((brush_flags & 0xFFF) << 16) | ((edge_flags & 0xF) << 28)
+    return np.array([prim_header_index, clip_task_address, z, resource_address],
+                    dtype=np.int64).astype(np.int32)
