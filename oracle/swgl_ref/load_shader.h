@@ -4,8 +4,12 @@
 #include "wr_common.h"
 #include "ps_quad.h"
 #include "ps_quad_textured.h"
+#include "brush.h"
+#include "brush_solid.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
+  if (!strcmp(name, "brush_solid")) return brush_solid_program::loader;
+  if (!strcmp(name, "brush_solid ALPHA_PASS")) return brush_solid_ALPHA_PASS_program::loader;
   return nullptr;
 }

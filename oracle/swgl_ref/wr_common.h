@@ -275,12 +275,12 @@ struct WrCommon {
     self->bind_textures();                                                     \
   }                                                                            \
   void init_vertex_abi() {                                                     \
-    set_uniform_1i_func = &set_uniform_1i;                                     \
-    set_uniform_4fv_func = &set_uniform_4fv;                                   \
-    set_uniform_matrix4fv_func = &set_uniform_matrix4fv;                       \
-    init_batch_func = &init_batch;                                             \
-    load_attribs_func = &load_attribs;                                         \
-    run_primitive_func = &run;                                                 \
+    this->set_uniform_1i_func = &set_uniform_1i;                                     \
+    this->set_uniform_4fv_func = &set_uniform_4fv;                                   \
+    this->set_uniform_matrix4fv_func = &set_uniform_matrix4fv;                       \
+    this->init_batch_func = &init_batch;                                             \
+    this->load_attribs_func = &Self::load_attribs;                                         \
+    this->run_primitive_func = &run;                                                 \
   }
 
 // Boilerplate for the fragment side (lib.rs:3563-3636).
@@ -295,12 +295,12 @@ struct WrCommon {
     self->step_interp_inputs(steps);                                           \
   }                                                                            \
   void init_fragment_abi() {                                                   \
-    init_span_func = &read_interp_inputs;                                      \
-    run_func = &run;                                                           \
-    skip_func = &skip;                                                         \
-    init_span_w_func = &read_interp_inputs;                                    \
-    run_w_func = &run;                                                         \
-    skip_w_func = &skip;                                                       \
+    this->init_span_func = &read_interp_inputs;                                      \
+    this->run_func = &run;                                                           \
+    this->skip_func = &skip;                                                         \
+    this->init_span_w_func = &read_interp_inputs;                                    \
+    this->run_w_func = &run;                                                         \
+    this->skip_w_func = &skip;                                                       \
   }
 
 // Boilerplate for the program class (lib.rs:224-241).

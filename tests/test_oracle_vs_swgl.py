@@ -32,3 +32,12 @@ def test_blend_keys_random_layers(blend):
     f = scenes.alpha_rects_frame(160, 64, 24, random_rects=True, seed=100 + blend, blend=blend,
                                  color=None, clear_color=(0.4, 0.7, 0.2, 0.8))
     assert_same(render(SwglDevice, f), render(OracleDevice, f), f"blend={blend}")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["plain", "fractional", "force_aa", "aa_fractional", "scaled"])
+def test_brush_solid_opaque_alpha_masks(seed, variant):
+    f = scenes.brush_solid_frame(333, 207, seed=seed, fractional="fractional" in variant,
+                                 force_aa="aa" in variant,
+                                 device_pixel_scale=1.5 if variant == "scaled" else 1.0)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -14,7 +14,7 @@ enum : uint32_t {
   CMD_AA = 1u << 2,         // SWGL_CLIP_FLAG_AA
   CMD_TEXTURED = 1u << 3,   // fragment samples sColor0
   CMD_OUT_RRRR = 1u << 4,   // QF_IS_MASK: output_color.rrrr
-  CMD_FULL_ROW_BODY = 1u << 5,
+  CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
 };
 
 struct __align__(16) CmdHot {

@@ -254,13 +254,24 @@ wr_raster_quads(RasterArgs a) {
         if (a.blend != WRCU_BLEND_NONE) {
           if (c.flags & (CMD_AA | CMD_MASK)) {
             const CmdCold& k = a.cold[c.cold];
+            // Order of the two source modifiers: the blend stage applies AA then
+            // the clip mask (blend.h:447-461); commit_masked_solid_span
+            // (swgl_ext.h:10-24) — whole chunks of solid spans — folds the mask
+            // into the colour first.
+            int len = c.x1 - c.x0;
+            bool mask_first = (c.flags & CMD_SPAN_SOLID) && (xx - c.x0) < (len >= 4 ? (len & ~3) : 0);
+            int mk = 255;
+            if (c.flags & CMD_MASK) mk = __ldg(k.mask_ptr + (size_t)(y - k.cmy) * k.mask_pitch + (xx - k.cmx));
+            if ((c.flags & CMD_MASK) && mask_first) {
+              if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
+              else src.r = wr_muldiv255(src.r, mk);
+            }
             if (c.flags & CMD_AA) {
               int aa = wr_aa_weight(c, k, xx);
               if (FMT == WRCU_FMT_RGBA8) src = px_scale256(src, aa);
               else src.r = wr_muldiv256(src.r, aa);
             }
-            if (c.flags & CMD_MASK) {
-              int mk = __ldg(k.mask_ptr + (size_t)(y - k.cmy) * k.mask_pitch + (xx - k.cmx));
+            if ((c.flags & CMD_MASK) && !mask_first) {
               if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
               else src.r = wr_muldiv255(src.r, mk);
             }

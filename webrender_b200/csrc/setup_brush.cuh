@@ -1,0 +1,152 @@
+// setup_brush.cuh — vertex stage of the brush_* programs
+// (webrender/res/brush.glsl:95-222 brush_shader_main_vs/main,
+//  prim_shared.glsl:44-200 decode/fetch_prim_header/write_vertex/
+//  clip_and_init_antialiasing/write_clip), SWGL branches: clip masks and edge
+// AA are handed to the rasteriser (swgl_clipMask / swgl_antiAlias).
+#pragma once
+#include "setup_common.cuh"
+
+#define WR_BRUSH_FLAG_FORCE_AA 1024
+
+struct DevPrimHeader {
+  float lr[4], lcr[4];  // local_rect, local_clip_rect (x0,y0,x1,y1)
+  float z;
+  int specific_prim_address, transform_id, picture_task_address;
+  int user_data[4];
+};
+
+__device__ inline DevPrimHeader wr_fetch_prim_header(const FrameTablesDev& T, int index) {
+  DevPrimHeader ph;
+  float4 f0 = wr_fetch(T.prim_headers_f, T.n_prim_headers_f, index * 2);
+  float4 f1 = wr_fetch(T.prim_headers_f, T.n_prim_headers_f, index * 2 + 1);
+  int4 i0 = wr_fetchi(T.prim_headers_i, T.n_prim_headers_i, index * 2);
+  int4 i1 = wr_fetchi(T.prim_headers_i, T.n_prim_headers_i, index * 2 + 1);
+  ph.lr[0] = f0.x; ph.lr[1] = f0.y; ph.lr[2] = f0.z; ph.lr[3] = f0.w;
+  ph.lcr[0] = f1.x; ph.lcr[1] = f1.y; ph.lcr[2] = f1.z; ph.lcr[3] = f1.w;
+  ph.z = (float)i0.x;
+  ph.specific_prim_address = i0.y;
+  ph.transform_id = i0.z;
+  ph.picture_task_address = i0.w;
+  ph.user_data[0] = i1.x; ph.user_data[1] = i1.y; ph.user_data[2] = i1.z; ph.user_data[3] = i1.w;
+  return ph;
+}
+
+struct BrushVS {
+  float2 local_pos[4];
+  float4 world_pos[4];
+  DevPrimHeader ph;
+  float segment_rect[4];
+  float4 segment_data;
+  int brush_flags, edge_flags, resource_address;
+  DevTransform transform;
+  DevPictureTask task;
+};
+
+// write_clip → swgl_clipMask (prim_shared.glsl:183-190, swgl_ext.h:1867-1877)
+__device__ inline void wr_write_clip(const FrameTablesDev& T, int clip_address, const DevPictureTask& task,
+                                     QuadOut& q) {
+  if (clip_address >= 0x7FFFFFFF) return;  // CLIP_TASK_EMPTY → zero rect → ignored
+  float4 a = wr_fetch(T.render_tasks, T.n_render_tasks, clip_address * 2);
+  float4 b = wr_fetch(T.render_tasks, T.n_render_tasks, clip_address * 2 + 1);
+  float sx = a.z - a.x, sy = a.w - a.y;
+  if (sx != 0.0f || sy != 0.0f) {
+    q.flags |= CMD_MASK;
+    float ox = (task.tx0 - task.ox) - (a.x - b.y);
+    float oy = (task.ty0 - task.oy) - (a.y - b.z);
+    q.cm_off[0] = (int)ox;
+    q.cm_off[1] = (int)oy;
+    q.cm_bb[0] = (int)a.x;
+    q.cm_bb[1] = (int)a.y;
+    q.cm_bb[2] = (int)sx;
+    q.cm_bb[3] = (int)sy;
+  }
+}
+
+__device__ inline void wr_brush_vertex(const SetupArgs& a, int4 aData, int vecs_per_specific_brush,
+                                       QuadOut& q, BrushVS& o) {
+  const FrameTablesDev& T = a.tabs;
+  int prim_header_address = aData.x, clip_address = aData.y;
+  int segment_index = aData.z & 0xffff, flags = aData.z >> 16;
+  o.resource_address = aData.w & 0xffffff;
+  o.ph = wr_fetch_prim_header(T, prim_header_address);
+  o.transform = wr_fetch_transform(T, o.ph.transform_id);
+  o.task = wr_fetch_picture_task(T, o.ph.picture_task_address);
+  int edge_flags = (flags >> 12) & 0xf;
+  int brush_flags = flags & 0xfff;
+  o.edge_flags = edge_flags;
+  o.brush_flags = brush_flags;
+  float seg[4];
+  if (segment_index == 0xffff) {
+    seg[0] = o.ph.lr[0]; seg[1] = o.ph.lr[1]; seg[2] = o.ph.lr[2]; seg[3] = o.ph.lr[3];
+    o.segment_data = make_float4(0, 0, 0, 0);
+  } else {
+    int sa = o.ph.specific_prim_address + vecs_per_specific_brush + segment_index * 2;
+    float4 s0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, sa);
+    o.segment_data = wr_fetch(T.gpu_cache, T.n_gpu_cache, sa + 1);
+    seg[0] = s0.x + o.ph.lr[0]; seg[1] = s0.y + o.ph.lr[1];
+    seg[2] = s0.z + o.ph.lr[0]; seg[3] = s0.w + o.ph.lr[1];
+  }
+  for (int i = 0; i < 4; i++) o.segment_rect[i] = seg[i];
+  float adj[4] = {seg[0], seg[1], seg[2], seg[3]};
+  bool antialiased = !o.transform.is_axis_aligned || (brush_flags & WR_BRUSH_FLAG_FORCE_AA) != 0;
+  q.flags = 0;
+  q.aa_edge_mask = 0;
+  if (antialiased) {
+    const float* cr = o.ph.lcr;
+    int m = edge_flags | (cr[0] > adj[0] ? 1 : 0) | (cr[1] > adj[1] ? 2 : 0) | (cr[2] < adj[2] ? 4 : 0) |
+            (cr[3] < adj[3] ? 8 : 0);
+    q.aa_edge_mask = m;
+    if (m) q.flags |= CMD_AA;
+    adj[0] = wr_clamp(adj[0], cr[0], cr[2]); adj[1] = wr_clamp(adj[1], cr[1], cr[3]);
+    adj[2] = wr_clamp(adj[2], cr[0], cr[2]); adj[3] = wr_clamp(adj[3], cr[1], cr[3]);
+    o.ph.lcr[0] = o.ph.lcr[1] = -1.0e16f;
+    o.ph.lcr[2] = o.ph.lcr[3] = 1.0e16f;
+  }
+  float fox = -o.task.ox + o.task.tx0, foy = -o.task.oy + o.task.ty0;
+  const float ax[4] = {0.0f, 1.0f, 1.0f, 0.0f}, ay[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+  for (int i = 0; i < 4; i++) {
+    float lpx = (adj[2] - adj[0]) * ax[i] + adj[0], lpy = (adj[3] - adj[1]) * ay[i] + adj[1];
+    lpx = wr_clamp(lpx, o.ph.lcr[0], o.ph.lcr[2]);
+    lpy = wr_clamp(lpy, o.ph.lcr[1], o.ph.lcr[3]);
+    float4 world = wr_mat_mul(o.transform.m, make_float4(lpx, lpy, 0.0f, 1.0f));
+    float dpx = world.x * o.task.device_pixel_scale, dpy = world.y * o.task.device_pixel_scale;
+    q.pos[i] = wr_mat_mul(a.tgt.proj, make_float4(dpx + fox * world.w, dpy + foy * world.w,
+                                                  o.ph.z * world.w, world.w));
+    o.local_pos[i] = make_float2(lpx, lpy);
+    o.world_pos[i] = world;
+  }
+  wr_write_clip(T, clip_address, o.task, q);
+}
+
+__device__ __forceinline__ void wr_pack_color(QuadOut& q, const float* col) {
+  q.col[0] = (uint16_t)wr_round_pixel(col[2], 255.0f);
+  q.col[1] = (uint16_t)wr_round_pixel(col[1], 255.0f);
+  q.col[2] = (uint16_t)wr_round_pixel(col[0], 255.0f);
+  q.col[3] = (uint16_t)wr_round_pixel(col[3], 255.0f);
+}
+
+__device__ __forceinline__ void wr_finish_setup(const SetupArgs& a, int unsupported) {
+  if (unsupported) {
+    atomicAdd(&a.info->unsupported, 1);
+    atomicAdd(a.err_counter, 1);
+  }
+}
+
+// brush_solid (brush_solid.glsl:22-38): colour = gpu_cache[prim] * opacity
+__global__ void wr_setup_brush_solid(SetupArgs a) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n) return;
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  QuadOut q;
+  BrushVS vs;
+  memset(&q, 0, sizeof q);
+  wr_brush_vertex(a, aData, 1, q, vs);
+  float4 c = wr_fetch(a.tabs.gpu_cache, a.tabs.n_gpu_cache, vs.ph.specific_prim_address);
+  float opacity = (float)vs.ph.user_data[0] / 65535.0f;
+  float col[4] = {c.x * opacity, c.y * opacity, c.z * opacity, c.w * opacity};
+  wr_pack_color(q, col);
+  q.flags |= CMD_SPAN_SOLID;  // swgl_drawSpanRGBA8/R8 both commit solid spans
+  int unsupported = 0;
+  wr_emit_quad(a, idx, q, &unsupported);
+  wr_finish_setup(a, unsupported);
+}

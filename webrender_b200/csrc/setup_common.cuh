@@ -118,8 +118,12 @@ __device__ inline bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& 
       px[i] = (q.pos[i].x * w + 1) * 0.5f * (float)a.tgt.vp[2] + (float)a.tgt.vp[0];
       py[i] = (q.pos[i].y * w + 1) * 0.5f * (float)a.tgt.vp[3] + (float)a.tgt.vp[1];
     }
-    uint32_t flags = a.blend_enabled ? q.flags : (q.flags & ~(CMD_MASK | CMD_AA));
+    uint32_t flags = a.blend_enabled ? q.flags : (q.flags & ~(CMD_MASK | CMD_AA | CMD_SPAN_SOLID));
     float cx0 = (float)a.tgt.cx0, cy0 = (float)a.tgt.cy0, cx1 = (float)a.tgt.cx1, cy1 = (float)a.tgt.cy1;
+    if ((flags & CMD_MASK) && a.clip_mask.ptr == nullptr) {
+      *unsupported = 1;  // clip task referenced but no sClipMask bound
+      break;
+    }
     if (flags & CMD_MASK) {
       int mx0 = max(q.cm_bb[0], 0), my0 = max(q.cm_bb[1], 0);
       int mx1 = min(q.cm_bb[0] + q.cm_bb[2], a.clip_mask.w);
@@ -233,7 +237,7 @@ __device__ inline bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& 
   } while (0);
   a.hot[idx] = h;
   if (ok) {
-    bool simple = !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&
+    bool simple = !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&  // CMD_SPAN_SOLID is fine
                   h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255;
     if (!simple) a.info->simple = 0;
     atomicMin(&a.info->bx0, (int)h.x0); atomicMin(&a.info->by0, (int)h.y0);

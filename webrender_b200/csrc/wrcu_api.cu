@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "raster.cuh"
+#include "setup_brush.cuh"
 #include "setup_quad.cuh"
 #include "wrcu_internal.h"
 
@@ -500,6 +501,10 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_QUAD_TEXTURED:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "quad instance stride < 16");
       wr_setup_quad_textured<<<sblocks, 128, 0, c->stream>>>(sa);
+      break;
+    case WRCU_KIND_BRUSH_SOLID:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      wr_setup_brush_solid<<<sblocks, 128, 0, c->stream>>>(sa);
       break;
     default:
       return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);

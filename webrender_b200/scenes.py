@@ -60,3 +60,80 @@ def pixel_layers_of_quad_batch(frame: Frame):
         total += max(0, int(np.floor(x1 + 0.5)) - int(np.floor(x0 + 0.5))) * \
             max(0, int(np.floor(y1 + 0.5)) - int(np.floor(y0 + 0.5)))
     return total
+
+
+def _rand_rect(rng, width, height, min_size=8, max_size=None, integer=True):
+    max_size = max_size or max(width, height)
+    w = rng.randint(min_size, max(min_size + 1, min(max_size, width)))
+    h = rng.randint(min_size, max(min_size + 1, min(max_size, height)))
+    x0 = rng.randint(-w // 4, max(1, width - w // 2))
+    y0 = rng.randint(-h // 4, max(1, height - h // 2))
+    if integer:
+        return (float(x0), float(y0), float(x0 + w), float(y0 + h))
+    fx, fy = rng.uniform(0, 1, 2)
+    return (float(np.float32(x0 + fx)), float(np.float32(y0 + fy)),
+            float(np.float32(x0 + w + fy)), float(np.float32(y0 + h + fx)))
+
+
+def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, with_masks=True,
+                      fractional=False, force_aa=False, device_pixel_scale=1.0):
+    """Brush(Solid) batches the way draw_alpha_batch_container issues them
+    (renderer/mod.rs:2804-2969): an opaque batch front-to-back with depth
+    LEQUAL + write, then an alpha batch with premultiplied blending, depth test
+    only, and per-instance clip masks sampled from an R8 alpha target."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
+    mw, mh = 256, 256
+    mask = rng.randint(0, 256, size=(mh, mw)).astype(np.uint8)
+    mask[rng.randint(0, mh, 40)[:, None], :] = 255
+    mask[:, rng.randint(0, mw, 40)] = 0
+    z = 1
+    opaque, alpha = [], []
+
+    def add(rect, clip_rect, color, opacity, clip_task, flags=0, edge=0):
+        nonlocal z
+        addr = t.push_gpu_cache([color])
+        hdr = t.add_prim_header(rect, clip_rect, z, addr, 0, pic, (int(opacity * 65535), 0, 0, 0))
+        z += 1
+        return brush_instance(hdr, clip_task, 0xFFFF, edge, flags, 0)
+
+    s = 1.0 / device_pixel_scale
+    for _ in range(n_opaque):
+        r = _rand_rect(rng, width, height, 16, integer=not fractional)
+        r = tuple(v * s for v in r)
+        c = tuple(float(v) for v in rng.uniform(0, 1, 3)) + (1.0,)
+        opaque.append(add(r, (-1e9, -1e9, 1e9, 1e9), c, 1.0, CLIP_TASK_EMPTY))
+    for i in range(n_alpha):
+        r = _rand_rect(rng, width, height, 16, integer=not fractional)
+        a = rng.uniform(0.1, 1.0)
+        c = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (float(a),)
+        clip_task = CLIP_TASK_EMPTY
+        if with_masks and i % 2 == 0:
+            # mask region: device rect (sx,sy,w,h) stored in the mask texture at (mx,my)
+            w_ = int(min(r[2] - r[0], 120))
+            h_ = int(min(r[3] - r[1], 100))
+            sx, sy = int(np.floor(r[0])) + rng.randint(0, 8), int(np.floor(r[1])) + rng.randint(0, 8)
+            mx, my = rng.randint(0, mw - w_), rng.randint(0, mh - h_)
+            clip_task = t.add_render_task((float(mx), float(my), float(mx + w_), float(my + h_)), 1.0,
+                                          (float(sx), float(sy)))
+        clip = (-1e9, -1e9, 1e9, 1e9)
+        if i % 3 == 0:
+            clip = (r[0] + 3.0, r[1] + 2.0, r[2] - 5.0, r[3] - 1.0)
+        r = tuple(v * s for v in r)
+        clip = tuple(v * s for v in clip)
+        flags = 1024 if force_aa else 0
+        edge = (i % 16) if force_aa else 0
+        alpha.append(add(r, clip, c, rng.uniform(0.3, 1.0), clip_task, flags, edge))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "depth": TextureDesc(abi.FMT_DEPTH24, width, height),
+                "mask": TextureDesc(abi.FMT_R8, mw, mh, mask)}
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0), depth=1.0)]
+    if opaque:
+        ops.append(Batch(abi.KIND_BRUSH_SOLID, np.stack(opaque[::-1]), blend=abi.BLEND_NONE,
+                         depth=abi.DEPTH_TEST_WRITE))
+    if alpha:
+        ops.append(Batch(abi.KIND_BRUSH_SOLID, np.stack(alpha), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                         depth=abi.DEPTH_TEST, features=abi.FEAT_ALPHA_PASS, clip_mask="mask"))
+    return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
