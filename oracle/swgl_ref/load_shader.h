@@ -6,10 +6,13 @@
 #include "ps_quad_textured.h"
 #include "brush.h"
 #include "brush_solid.h"
+#include "cs_clip_rectangle.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
   if (!strcmp(name, "brush_solid")) return brush_solid_program::loader;
   if (!strcmp(name, "brush_solid ALPHA_PASS")) return brush_solid_ALPHA_PASS_program::loader;
+  if (!strcmp(name, "cs_clip_rectangle")) return cs_clip_rectangle_program::loader;
+  if (!strcmp(name, "cs_clip_rectangle FAST_PATH")) return cs_clip_rectangle_FAST_PATH_program::loader;
   return nullptr;
 }

@@ -88,3 +88,16 @@ def test_brush_solid_aa_with_occluders_within_1lsb(seed):
     a, b = render(CudaDevice, f, ["target"])["target"], render(OracleDevice, f, ["target"])["target"]
     assert max_abs_diff(a, b) <= 1
     assert (a != b).sum() < a.size * 1e-3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled"])
+def test_clip_rectangle_masks_bit_exact(seed, variant):
+    """cs_clip_rectangle (fast + general, Clip/ClipOut, overwrite + multiply): R8 masks bit-exact."""
+    f = scenes.clip_mask_frame(seed=seed, fractional=variant != "integer", scale=1.25 if variant == "scaled" else 1.0)
+    assert_same(render(CudaDevice, f), render(OracleDevice, f), variant)
+
+
+def test_clip_rectangle_large():
+    f = scenes.clip_mask_frame(2048, 1024, n_clips=40, seed=9, fractional=True)
+    assert_same(render(CudaDevice, f), render(OracleDevice, f))

@@ -41,3 +41,12 @@ def test_brush_solid_opaque_alpha_masks(seed, variant):
                                  force_aa="aa" in variant,
                                  device_pixel_scale=1.5 if variant == "scaled" else 1.0)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled"])
+def test_clip_rectangle_masks(seed, variant):
+    """cs_clip_rectangle fast + general paths, Clip/ClipOut, primary (overwrite) and
+    secondary (multiply) — bit-exact R8 masks."""
+    f = scenes.clip_mask_frame(seed=seed, fractional=variant != "integer", scale=1.25 if variant == "scaled" else 1.0)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), variant)

@@ -14,6 +14,7 @@ enum : uint32_t {
   CMD_AA = 1u << 2,         // SWGL_CLIP_FLAG_AA
   CMD_TEXTURED = 1u << 3,   // fragment samples sColor0
   CMD_OUT_RRRR = 1u << 4,   // QF_IS_MASK: output_color.rrrr
+  CMD_CONST_COLOR = 1u << 6, // fragment output is the constant colour in CmdHot.col
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
 };
 
@@ -42,6 +43,7 @@ struct __align__(16) CmdCold {
   // kind-specific
   float f[8];   // e.g. uv sample bounds
   int32_t i[4];
+  float g[36];  // large kind-specific block (rounded-rect clip geometry, ...)
 };
 
 // Per-batch info written by the setup kernel.

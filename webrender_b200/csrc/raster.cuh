@@ -197,10 +197,23 @@ __device__ __forceinline__ Px wr_quad_source(const RasterArgs& a, const CmdHot& 
   return o;
 }
 
-// ---- the generic tile kernel (any quad command, any blend key) -------------------
-template <int FMT>
+// Shader policy for quad / solid-brush commands.
+struct QuadShader {
+  struct Row {};
+  __device__ static __forceinline__ void row_setup(const RasterArgs&, const CmdHot&, int, bool, Row&) {}
+  __device__ static __forceinline__ Px source(const RasterArgs& a, const CmdHot& c, const Row&, int x, int y,
+                                              bool rgba) {
+    return wr_quad_source(a, c, x, y, rgba);
+  }
+};
+
+// ---- the generic tile kernel (any command kind via the shader policy S, any
+// blend key).  S::row_setup computes per-(command,row) constants once per warp
+// (all 32 lanes of a warp share the row, so the work is warp-uniform);
+// S::source returns the fragment stage's output for one pixel as 16-bit lanes.
+template <class S, int FMT>
 __global__ void __launch_bounds__(WRCU_THREADS)
-wr_raster_quads(RasterArgs a) {
+wr_raster(RasterArgs a) {
   __shared__ CmdHot sh[CHUNK_CMDS];
   const int tx0 = blockIdx.x * WRCU_TILE_W, ty0 = blockIdx.y * WRCU_TILE_H;
   const BatchInfo bi = *a.info;
@@ -242,6 +255,8 @@ wr_raster_quads(RasterArgs a) {
           zb[0] = v.x; zb[1] = v.y; zb[2] = v.z; zb[3] = v.w;
         }
       }
+      typename S::Row row;
+      S::row_setup(a, c, y, FMT == WRCU_FMT_RGBA8, row);
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         int xx = x + p;
@@ -250,7 +265,7 @@ wr_raster_quads(RasterArgs a) {
           if (!(c.z <= zb[p])) continue;  // GL_LEQUAL
           if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) { zb[p] = c.z; zdirty = true; }
         }
-        Px src = wr_quad_source(a, c, xx, y, FMT == WRCU_FMT_RGBA8);
+        Px src = S::source(a, c, row, xx, y, FMT == WRCU_FMT_RGBA8);
         if (a.blend != WRCU_BLEND_NONE) {
           if (c.flags & (CMD_AA | CMD_MASK)) {
             const CmdCold& k = a.cold[c.cold];

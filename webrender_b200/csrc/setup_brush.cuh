@@ -145,7 +145,7 @@ __global__ void wr_setup_brush_solid(SetupArgs a) {
   float opacity = (float)vs.ph.user_data[0] / 65535.0f;
   float col[4] = {c.x * opacity, c.y * opacity, c.z * opacity, c.w * opacity};
   wr_pack_color(q, col);
-  q.flags |= CMD_SPAN_SOLID;  // swgl_drawSpanRGBA8/R8 both commit solid spans
+  q.flags |= CMD_SPAN_SOLID | CMD_CONST_COLOR;  // swgl_drawSpanRGBA8/R8 both commit solid spans
   int unsupported = 0;
   wr_emit_quad(a, idx, q, &unsupported);
   wr_finish_setup(a, unsupported);

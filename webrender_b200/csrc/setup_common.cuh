@@ -22,6 +22,7 @@ struct SetupArgs {
   BatchInfo* info;
   int* err_counter;
   int blend_enabled;
+  uint32_t features;
   TexView color0;
   TexView clip_mask;
 };
@@ -237,7 +238,7 @@ __device__ inline bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& 
   } while (0);
   a.hot[idx] = h;
   if (ok) {
-    bool simple = !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&  // CMD_SPAN_SOLID is fine
+    bool simple = (h.flags & CMD_CONST_COLOR) && !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&
                   h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255;
     if (!simple) a.info->simple = 0;
     atomicMin(&a.info->bx0, (int)h.x0); atomicMin(&a.info->by0, (int)h.y0);

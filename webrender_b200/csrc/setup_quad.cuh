@@ -144,6 +144,7 @@ __global__ void wr_setup_quad_textured(SetupArgs a) {
   q.col[3] = (uint16_t)wr_round_pixel(col[3], 255.0f);
   // swgl_drawSpanRGBA8 → swgl_commitSolidRGBA8 for untextured quads on RGBA8 targets
   if (!(q.flags & CMD_TEXTURED) && a.tgt.fmt == WRCU_FMT_RGBA8) q.flags |= CMD_SPAN_SOLID;
+  if (!(q.flags & CMD_TEXTURED)) q.flags |= CMD_CONST_COLOR;
   int unsupported = 0;
   bool ok = wr_emit_quad(a, idx, q, &unsupported);
   if (ok) {

@@ -6,7 +6,9 @@
 #include <stdlib.h>
 
 #include "raster.cuh"
+#include "shader_clip_rect.cuh"
 #include "setup_brush.cuh"
+#include "setup_clip.cuh"
 #include "setup_quad.cuh"
 #include "wrcu_internal.h"
 
@@ -440,7 +442,6 @@ static int ensure_cmd_capacity(wrcu_ctx* c, size_t n) {
 
 extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const wrcu_draw_state* st,
                                const void* instances, size_t stride, int n) {
-  (void)features;
   if (!st || !instances || n < 0 || stride == 0)
     return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: bad arguments");
   if (n == 0) return WRCU_OK;
@@ -506,6 +507,11 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       wr_setup_brush_solid<<<sblocks, 128, 0, c->stream>>>(sa);
       break;
+    case WRCU_KIND_CLIP_RECTANGLE:
+      if (stride < 200) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceRect stride < 200");
+      sa.features = features;
+      wr_setup_clip_rectangle<<<sblocks, 128, 0, c->stream>>>(sa);
+      break;
     default:
       return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);
   }
@@ -535,10 +541,18 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     wr_raster_solid_premult<<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
     c->stats.kernel_launches++;
   }
-  if (T.fmt == WRCU_FMT_RGBA8)
-    wr_raster_quads<WRCU_FMT_RGBA8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
-  else
-    wr_raster_quads<WRCU_FMT_R8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
+#define LAUNCH_RASTER(S)                                                         \
+  do {                                                                           \
+    if (T.fmt == WRCU_FMT_RGBA8)                                                 \
+      wr_raster<S, WRCU_FMT_RGBA8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);    \
+    else                                                                         \
+      wr_raster<S, WRCU_FMT_R8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);       \
+  } while (0)
+  switch (kind) {
+    case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
+    default: LAUNCH_RASTER(QuadShader); break;
+  }
+#undef LAUNCH_RASTER
   c->stats.kernel_launches++;
   WRCU_CUDA(c, cudaGetLastError());
   return WRCU_OK;

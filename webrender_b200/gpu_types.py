@@ -151,3 +151,30 @@ def brush_instance(prim_header_index, clip_task_address, segment_index, edge_fla
     z = (segment_index & 0xFFFF) | ((brush_flags & 0xFFF) << 16) | ((edge_flags & 0xF) << 28)
     return np.array([prim_header_index, clip_task_address, z, resource_address],
                     dtype=np.int64).astype(np.int32)
+
+
+def clip_rect_instance(sub_rect, task_origin, screen_origin, device_pixel_scale, clip_transform_id,
+                       prim_transform_id, local_pos, local_rect, mode, radii):
+    """ClipMaskInstanceRect, 200 bytes (gpu_types.rs:208-225, prim_store/mod.rs:774-813).
+    radii = ((tl_rx, tl_ry), (tr_rx, tr_ry), (bl_rx, bl_ry), (br_rx, br_ry))."""
+    x0, y0, x1, y1 = local_rect
+    (tl, tr, bl, br) = radii
+    corner_rects = [
+        (x0, y0, x0 + tl[0], y0 + tl[1]),
+        (x1 - tr[0], y0, x1, y0 + tr[1]),
+        (x0, y1 - bl[1], x0 + bl[0], y1),
+        (x1 - br[0], y1 - br[1], x1, y1),
+    ]
+    buf = np.zeros(50, dtype=np.float32)
+    buf[0:4] = sub_rect
+    buf[4:6] = task_origin
+    buf[6:8] = screen_origin
+    buf[8] = device_pixel_scale
+    buf[9:11] = np.array([clip_transform_id, prim_transform_id], dtype=np.int32).view(np.float32)
+    buf[11:13] = local_pos
+    buf[13:17] = local_rect
+    buf[17] = mode
+    for i, (rect, r) in enumerate(zip(corner_rects, (tl, tr, bl, br))):
+        buf[18 + 8 * i: 22 + 8 * i] = rect
+        buf[22 + 8 * i: 26 + 8 * i] = (r[0], r[1], 0.0, 0.0)
+    return buf.view(np.uint8).copy()

@@ -137,3 +137,49 @@ def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, wi
         ops.append(Batch(abi.KIND_BRUSH_SOLID, np.stack(alpha), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
                          depth=abi.DEPTH_TEST, features=abi.FEAT_ALPHA_PASS, clip_mask="mask"))
     return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
+
+
+def clip_mask_frame(width=512, height=384, n_clips=10, seed=1, fractional=False, scale=1.0):
+    """An alpha (R8) target filled the way draw_alpha_target does it
+    (renderer/mod.rs:3754-3929): clear to one, primary rounded-rect clips with
+    blending off, then secondary clips multiplied in (ZERO, SRC_COLOR).  Mixes
+    the FAST_PATH (uniform radius) and general (per-corner elliptical radii)
+    programs and both clip modes."""
+    from .gpu_types import clip_rect_instance
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    xf = t.add_transform(scale_matrix(scale)) if scale != 1.0 else 0
+    fast, slow, fast2, slow2 = [], [], [], []
+    for i in range(n_clips):
+        # mask task region inside the R8 target
+        w, h = int(rng.randint(24, 200)), int(rng.randint(24, 160))
+        tx, ty = int(rng.randint(0, width - w)), int(rng.randint(0, height - h))
+        sx, sy = int(rng.randint(0, 500)), int(rng.randint(0, 500))
+        # the clip rect in local space roughly covering the task's screen rect
+        off = rng.uniform(-6, 6, 4) if fractional else rng.randint(-6, 7, 4).astype(np.float64)
+        rect = ((sx + off[0]) / scale, (sy + off[1]) / scale, (sx + w + off[2]) / scale, (sy + h + off[3]) / scale)
+        rw, rh = rect[2] - rect[0], rect[3] - rect[1]
+        mode = float(i % 3 == 2)
+        uniform = i % 2 == 0
+        if uniform:
+            r = float(rng.uniform(2, min(rw, rh) / 2)) if fractional else float(rng.randint(2, max(3, int(min(rw, rh) / 2))))
+            radii = ((r, r),) * 4
+        else:
+            radii = tuple((float(rng.uniform(1, rw / 2)), float(rng.uniform(1, rh / 2))) for _ in range(4))
+        inst = clip_rect_instance((0.0, 0.0, float(w), float(h)), (float(tx), float(ty)), (float(sx), float(sy)),
+                                  scale, xf, xf, (rect[0], rect[1]), rect, mode, radii)
+        primary = i < n_clips * 2 // 3
+        (fast if uniform else slow).append(inst) if primary else (fast2 if uniform else slow2).append(inst)
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0))]
+    for lst, feat, blend in ((slow, 0, abi.BLEND_NONE), (fast, abi.FEAT_FAST_PATH, abi.BLEND_NONE),
+                             (slow2, 0, abi.BLEND_MULTIPLY), (fast2, abi.FEAT_FAST_PATH, abi.BLEND_MULTIPLY)):
+        if lst:
+            ops.append(Batch(abi.KIND_CLIP_RECTANGLE, np.stack(lst), blend=blend, features=feat))
+    textures = {"mask": TextureDesc(abi.FMT_R8, width, height)}
+    return Frame(t.arrays(), textures, [[Target("mask", ops=ops)]])
+
+
+def scale_matrix(s):
+    m = np.eye(4, dtype=np.float32)
+    m[0, 0] = m[1, 1] = s
+    return m
