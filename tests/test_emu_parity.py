@@ -1,0 +1,31 @@
+"""CPU tier: the CUDA sources' per-instance / per-pixel device functions,
+executed on the host (tests/emu.py), against the oracle.  This is a development
+aid for a box without a GPU; the parity tests proper are test_cuda_parity.py."""
+import pytest
+
+from oracle.backends import OracleDevice
+from webrender_b200 import abi, scenes
+
+from common import assert_same, render
+from emu import EmuDevice
+
+
+@pytest.mark.parametrize("blend", [abi.BLEND_PREMULTIPLIED_ALPHA, abi.BLEND_ALPHA, abi.BLEND_ADV_SOFT_LIGHT,
+                                   abi.BLEND_ADV_HUE, abi.BLEND_NONE])
+def test_quads(blend):
+    f = scenes.alpha_rects_frame(257, 91, 23, random_rects=True, seed=blend, blend=blend, color=None)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f))
+
+
+@pytest.mark.parametrize("variant", ["plain", "fractional", "scaled"])
+def test_brush_solid(variant):
+    f = scenes.brush_solid_frame(333, 207, seed=2, fractional=variant == "fractional",
+                                 device_pixel_scale=1.5 if variant == "scaled" else 1.0)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled"])
+def test_clip_rectangle(seed, variant):
+    f = scenes.clip_mask_frame(seed=seed, fractional=variant != "integer", scale=1.25 if variant == "scaled" else 1.0)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f), variant)

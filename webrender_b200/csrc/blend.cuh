@@ -11,7 +11,7 @@
 //  * a generic per-lane path for every other key (advanced blend modes etc.).
 #pragma once
 #include <stdint.h>
-#include "../../include/wrcu.h"
+#include "wrcu_internal.h"
 
 struct Px {  // 16-bit lanes held in ints, memory order B,G,R,A
   int b, g, r, a;
@@ -19,67 +19,67 @@ struct Px {  // 16-bit lanes held in ints, memory order B,G,R,A
 
 // 16-bit lanes: products wrap mod 2^16 before the logical shift, as in the
 // reference's uint16_t vectors.
-__device__ __forceinline__ int wr_muldiv255(int x, int y) { return ((x * y + x) & 0xFFFF) >> 8; }
-__device__ __forceinline__ int wr_muldiv256(int x, int y) { return ((x * y) & 0xFFFF) >> 8; }
+WRD int wr_muldiv255(int x, int y) { return ((x * y + x) & 0xFFFF) >> 8; }
+WRD int wr_muldiv256(int x, int y) { return ((x * y) & 0xFFFF) >> 8; }
 // 16-bit lane wrap + signed-saturating pack (texture.h:13-21)
-__device__ __forceinline__ uint32_t wr_pack16(int v) {
+WRD uint32_t wr_pack16(int v) {
   uint32_t u = (uint32_t)v & 0xFFFFu;
   return (u & 0x8000u) ? 0u : (u > 255u ? 255u : u);
 }
-__device__ __forceinline__ int wr_addlow(int x, int y) {  // blend.h:202-205
+WRD int wr_addlow(int x, int y) {  // blend.h:202-205
   return (((x & 0xFF) + (y & 0xFF)) & 0xFF) |
          (((((x >> 8) & 0xFF) + ((y >> 8) & 0xFF)) & 0xFF) << 8);
 }
-__device__ __forceinline__ Px px_unpack(uint32_t p) {
+WRD Px px_unpack(uint32_t p) {
   return Px{(int)(p & 0xFF), (int)((p >> 8) & 0xFF), (int)((p >> 16) & 0xFF), (int)(p >> 24)};
 }
-__device__ __forceinline__ uint32_t px_pack(Px v) {
+WRD uint32_t px_pack(Px v) {
   return wr_pack16(v.b) | (wr_pack16(v.g) << 8) | (wr_pack16(v.r) << 16) | (wr_pack16(v.a) << 24);
 }
-__device__ __forceinline__ Px px_scale256(Px s, int aa) {
+WRD Px px_scale256(Px s, int aa) {
   return Px{wr_muldiv256(s.b, aa), wr_muldiv256(s.g, aa), wr_muldiv256(s.r, aa), wr_muldiv256(s.a, aa)};
 }
-__device__ __forceinline__ Px px_scale255(Px s, int m) {
+WRD Px px_scale255(Px s, int m) {
   return Px{wr_muldiv255(s.b, m), wr_muldiv255(s.g, m), wr_muldiv255(s.r, m), wr_muldiv255(s.a, m)};
 }
 // applyColor(src, color) = muldiv255(color, src)  (blend.h:156-163)
-__device__ __forceinline__ Px px_apply_color(Px src, Px color) {
+WRD Px px_apply_color(Px src, Px color) {
   return Px{wr_muldiv255(color.b, src.b), wr_muldiv255(color.g, src.g),
             wr_muldiv255(color.r, src.r), wr_muldiv255(color.a, src.a)};
 }
 
-__device__ __forceinline__ int wr_round_pixel(float v, float scale) {
+WRD int wr_round_pixel(float v, float scale) {
   // roundfast for the non-SSE build: int(v*scale + 0.5f) (glsl.h:732-737)
   return (int)(__fadd_rn(__fmul_rn(v, scale), 0.5f));
 }
-__device__ __forceinline__ float wr_recip_or(float v, float f) {
+WRD float wr_recip_or(float v, float f) {
   return v != 0.0f ? __fdiv_rn(1.0f, v) : f;
 }
-__device__ __forceinline__ float wr_min(float a, float b) { return a < b ? a : b; }
-__device__ __forceinline__ float wr_max(float a, float b) { return a > b ? a : b; }
-__device__ __forceinline__ float wr_clamp(float a, float lo, float hi) {
+WRD float wr_min(float a, float b) { return a < b ? a : b; }
+WRD float wr_max(float a, float b) { return a > b ? a : b; }
+WRD float wr_clamp(float a, float lo, float hi) {
   return wr_min(wr_max(a, lo), hi);
 }
 
 // ---- HSL helpers (blend.h:312-343) -------------------------------------------
-__device__ __forceinline__ float wr_lum(const float* v) {
+WRD float wr_lum(const float* v) {
   return __fadd_rn(__fadd_rn(__fmul_rn(v[0], 0.30f), __fmul_rn(v[1], 0.59f)), __fmul_rn(v[2], 0.11f));
 }
-__device__ __forceinline__ float wr_min3(const float* v) { return wr_min(wr_min(v[0], v[1]), v[2]); }
-__device__ __forceinline__ float wr_max3(const float* v) { return wr_max(wr_max(v[0], v[1]), v[2]); }
-__device__ inline void wr_clip_color(float* out, const float* v, float lum, float alpha) {
+WRD float wr_min3(const float* v) { return wr_min(wr_min(v[0], v[1]), v[2]); }
+WRD float wr_max3(const float* v) { return wr_max(wr_max(v[0], v[1]), v[2]); }
+WRD void wr_clip_color(float* out, const float* v, float lum, float alpha) {
   float mincol = wr_max(-wr_min3(v), lum);
   float maxcol = wr_max(wr_max3(v), __fsub_rn(alpha, lum));
   float k = __fmul_rn(__fmul_rn(lum, __fsub_rn(alpha, lum)),
                       wr_recip_or(__fmul_rn(mincol, maxcol), 0.0f));
   for (int i = 0; i < 3; i++) out[i] = __fadd_rn(lum, __fmul_rn(v[i], k));
 }
-__device__ inline void wr_set_lum(float* out, const float* base, const float* ref, float alpha) {
+WRD void wr_set_lum(float* out, const float* base, const float* ref, float alpha) {
   float lb = wr_lum(base);
   float t[3] = {__fsub_rn(base[0], lb), __fsub_rn(base[1], lb), __fsub_rn(base[2], lb)};
   wr_clip_color(out, t, wr_lum(ref), alpha);
 }
-__device__ inline void wr_set_lum_sat(float* out, const float* base, const float* sref,
+WRD void wr_set_lum_sat(float* out, const float* base, const float* sref,
                                       const float* lref, float alpha) {
   float mb = wr_min3(base);
   float diff[3] = {__fsub_rn(base[0], mb), __fsub_rn(base[1], mb), __fsub_rn(base[2], mb)};
@@ -103,7 +103,7 @@ __device__ inline void wr_set_lum_sat(float* out, const float* base, const float
 
 // Generic blend of one RGBA8 pixel (all keys), blend.h:462-700.  `kc` is
 // ctx->blendcolor in B,G,R,A lane order.
-__device__ inline Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
+WRD Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
   Px o = src;
   switch (key) {
     case WRCU_BLEND_NONE:
@@ -294,7 +294,7 @@ __device__ inline Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
 }
 
 // R8 blend stage (blend.h:703-735)
-__device__ __forceinline__ int wr_blend_r8(int key, int src, int dst) {
+WRD int wr_blend_r8(int key, int src, int dst) {
   switch (key) {
     case WRCU_BLEND_MULTIPLY: return wr_muldiv255(src, dst) & 0xFFFF;
     case WRCU_BLEND_PLUS_LIGHTER: return (src + dst) & 0xFFFF;
@@ -308,7 +308,7 @@ __device__ __forceinline__ int wr_blend_r8(int key, int src, int dst) {
 // With c = 255 - sa:  dst - ((dst*(sa+1))>>8) == (dst*c + 255) >> 8   (exact:
 // dst - floor(t/256) = ceil((256*dst - t)/256) with t = dst*(sa+1)), so one
 // multiply-add per lane pair.  Requires 0 <= sa <= 255.
-__device__ __forceinline__ uint32_t wr_premult_over_pair(uint32_t dst_pair, uint32_t src_pair,
+WRD uint32_t wr_premult_over_pair(uint32_t dst_pair, uint32_t src_pair,
                                                          uint32_t c /*255-sa*/) {
   uint32_t t = dst_pair * c + 0x00FF00FFu;     // each lane <= 255*255+255 < 65536
   uint32_t m = __byte_perm(t, 0, 0x4341);      // (t >> 8) & 0x00FF00FF

@@ -8,6 +8,7 @@
 // (AA ramps, clip-mask placement, interpolation frame, sampler parameters).
 #pragma once
 #include <stdint.h>
+#include "wrcu_internal.h"
 
 enum : uint32_t {
   CMD_MASK = 1u << 1,       // SWGL_CLIP_FLAG_MASK   (blend.h:345)
@@ -43,7 +44,7 @@ struct __align__(16) CmdCold {
   // kind-specific
   float f[8];   // e.g. uv sample bounds
   int32_t i[4];
-  float g[36];  // large kind-specific block (rounded-rect clip geometry, ...)
+  float g[40];  // large kind-specific block (rounded-rect clip geometry, ...)
 };
 
 // Per-batch info written by the setup kernel.

@@ -38,7 +38,7 @@ struct RasterArgs {
 // AA weight of pixel x for the current command (DO_AA, blend.h:433-445, with
 // the span set-up of aa_span, rasterize.h:546-557).  Chunks of 4 start at the
 // span start c.x0.
-__device__ __forceinline__ int wr_aa_weight(const CmdHot& c, const CmdCold& k, int x) {
+WRD int wr_aa_weight(const CmdHot& c, const CmdCold& k, int x) {
   int j = (x - c.x0) & 3;
   int xc = x - j;
   int opaque = max((int)c.aa_right_start - (int)c.aa_left_end - 3, 0);
@@ -54,31 +54,48 @@ __device__ __forceinline__ int wr_aa_weight(const CmdHot& c, const CmdCold& k, i
   return wr_round_pixel(dist, 1.0f);
 }
 
-// Interpolants of a screen-axis-aligned quad at pixel (x,y): closed form of the
-// reference's edge walk (Edge ctor + nextRow, rasterize.h:850-889) and span
-// set-up (rasterize.h:1003-1017): lane j of chunk k of the span that starts at
-// sx0.  Exact whenever the reference's running sums are exact (integer or
-// half-integer 1:1 mappings); within 1 ulp otherwise.
+// Interpolants of a screen-axis-aligned quad.  The reference walks the left and
+// right edges row by row, adding the per-row slope each time (Edge::nextRow,
+// rasterize.h:880-884), then derives the span's start value and per-pixel step
+// (rasterize.h:1003-1017).  wr_row_interp reproduces that running sum exactly:
+// it starts from the Edge constructor's value at the first row and adds the
+// slope (y - y0) times — warp-uniform work, once per (command,row).
 template <int N>
-__device__ __forceinline__ void wr_interp(const CmdCold& k, int sx0, int x, int y, float* out) {
-  float yc = (float)y + 0.5f;
-  float dy = __fsub_rn(yc, k.yt);
+WRD void wr_row_interp(const CmdCold& k, const CmdHot& c, int y, float* o, float* step) {
+  float y0c = (float)c.y0 + 0.5f;
+  float dy = __fsub_rn(y0c, k.yt);
   float stepScale = __fdiv_rn(1.0f, __fsub_rn(k.xr, k.xl));
   if (!isfinite(stepScale)) stepScale = 0.0f;
-  int rel = x - sx0;
-  int j = rel & 3;
-  float kf = (float)(rel >> 2);
-  float x0f = __fsub_rn(__fadd_rn((float)sx0, 0.5f), k.xl);
+  float x0f = __fsub_rn(__fadd_rn((float)c.x0, 0.5f), k.xl);
+  int rows = y - c.y0;
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    float li = __fadd_rn(k.i_lt[i], __fmul_rn(dy, __fmul_rn(__fsub_rn(k.i_lb[i], k.i_lt[i]), k.yscale)));
-    float ri = __fadd_rn(k.i_rt[i], __fmul_rn(dy, __fmul_rn(__fsub_rn(k.i_rb[i], k.i_rt[i]), k.yscale)));
-    float step = __fmul_rn(__fsub_rn(ri, li), stepScale);
-    float o = __fadd_rn(li, __fmul_rn(step, x0f));
-    // chunk advance: interp_step * chunks (glsl-to-cxx step_interp_inputs)
-    float v = __fadd_rn(o, __fmul_rn(__fmul_rn(step, 4.0f), kf));
-    // lanes accumulate sequentially (init_interp, glsl.h:3083-3088)
-    for (int s = 0; s < j; s++) v = __fadd_rn(v, step);
+    float sl = __fmul_rn(__fsub_rn(k.i_lb[i], k.i_lt[i]), k.yscale);
+    float sr = __fmul_rn(__fsub_rn(k.i_rb[i], k.i_rt[i]), k.yscale);
+    float li = __fadd_rn(k.i_lt[i], __fmul_rn(dy, sl));
+    float ri = __fadd_rn(k.i_rt[i], __fmul_rn(dy, sr));
+    for (int r = 0; r < rows; r++) {
+      li = __fadd_rn(li, sl);
+      ri = __fadd_rn(ri, sr);
+    }
+    float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
+    step[i] = st;
+    o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
+  }
+}
+
+// Value of interpolant lanes at pixel x of the span: lane j of chunk k.  Chunk
+// advance is closed-form (o + (4*step)*k, exact for the 1:1 mappings that
+// dominate); the lane offset accumulates sequentially as init_interp does
+// (glsl.h:3083-3088).
+template <int N>
+WRD void wr_interp_at(const float* o, const float* step, int rel, float* out) {
+  int j = rel & 3;
+  float kf = (float)(rel >> 2);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float v = __fadd_rn(o[i], __fmul_rn(__fmul_rn(step[i], 4.0f), kf));
+    for (int s = 0; s < j; s++) v = __fadd_rn(v, step[i]);
     out[i] = v;
   }
 }
@@ -88,8 +105,8 @@ __device__ __forceinline__ void wr_interp(const CmdCold& k, int sx0, int x, int 
 // whether the pixel belongs to the part of the span the reference draws with
 // swgl_drawSpanRGBA8 (first len&~3 pixels) or to the tail that runs the
 // fragment shader (ps_quad_textured.glsl:39-64).
-__device__ __forceinline__ Px wr_quad_source(const RasterArgs& a, const CmdHot& c, int x, int y,
-                                             bool rgba_target) {
+WRD Px wr_quad_source(const RasterArgs& a, const CmdHot& c, const float* ro, const float* rstep, int x, int y,
+                  bool rgba_target) {
   Px col{c.col[0], c.col[1], c.col[2], c.col[3]};
   const int len = c.x1 - c.x0;
   if (!(c.flags & CMD_TEXTURED)) {
@@ -108,15 +125,15 @@ __device__ __forceinline__ Px wr_quad_source(const RasterArgs& a, const CmdHot& 
                   t.fmt == WRCU_FMT_RGBA8) ? (len & ~3) : 0;
   bool body = (x - c.x0) < body_len;
   float uv[2];
-  wr_interp<2>(k, c.x0, x, y, uv);
+  wr_interp_at<2>(ro, rstep, x - c.x0, uv);
   bool linear = t.filter == WRCU_LINEAR;
   Px s;
   if (body) {
     // swgl_commitTextureLinearColorRGBA8 (swgl_ext.h:589-612)
     // needsTextureLinear uses lanes 0,1 of the span start chunk
     float uv0[2], uv1[2];
-    wr_interp<2>(k, c.x0, c.x0, y, uv0);
-    wr_interp<2>(k, c.x0, c.x0 + 1, y, uv1);
+    wr_interp_at<2>(ro, rstep, 0, uv0);
+    wr_interp_at<2>(ro, rstep, 1, uv1);
     // The span path does not consult the sampler's filter mode, only
     // needsTextureLinear (swgl_ext.h:554-612).
     int filter = 0;  // LINEAR_FILTER_NEAREST
@@ -138,7 +155,7 @@ __device__ __forceinline__ Px wr_quad_source(const RasterArgs& a, const CmdHot& 
       int rel = x - c.x0, j = rel & 3;
       float kf = (float)(rel >> 2);
       float uvj[2];
-      wr_interp<2>(k, c.x0, c.x0 + j, y, uvj);
+      wr_interp_at<2>(ro, rstep, j, uvj);
       float qu0 = wr_linear_quantize(uv0[0], t.w), qu1 = wr_linear_quantize(uv1[0], t.w);
       float qv0 = wr_linear_quantize(uv0[1], t.h), qv1 = wr_linear_quantize(uv1[1], t.h);
       float ustep = __fmul_rn(4.0f, __fsub_rn(qu1, qu0));
@@ -199,14 +216,106 @@ __device__ __forceinline__ Px wr_quad_source(const RasterArgs& a, const CmdHot& 
 
 // Shader policy for quad / solid-brush commands.
 struct QuadShader {
-  struct Row {};
-  __device__ static __forceinline__ void row_setup(const RasterArgs&, const CmdHot&, int, bool, Row&) {}
-  __device__ static __forceinline__ Px source(const RasterArgs& a, const CmdHot& c, const Row&, int x, int y,
-                                              bool rgba) {
-    return wr_quad_source(a, c, x, y, rgba);
+  struct Row {
+    float o[2], step[2];
+  };
+  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, bool, Row& r) {
+    if (c.flags & CMD_TEXTURED) wr_row_interp<2>(a.cold[c.cold], c, y, r.o, r.step);
+  }
+  WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int y, bool rgba) {
+    return wr_quad_source(a, c, r.o, r.step, x, y, rgba);
   }
 };
 
+// One pixel of one command through depth test, fragment stage, AA/mask
+// modifiers and the blend stage.  Shared by the tile kernel and (tests only) the
+// host emulation.  px = packed destination pixel (RGBA8) or value (R8).
+template <class S, int FMT>
+WRD void wr_shade_pixel(const RasterArgs& a, const CmdHot& c, const typename S::Row& row, int xx, int y,
+                        bool use_depth, uint32_t& px, uint32_t& zb, bool& dirty, bool& zdirty) {
+  if (use_depth) {
+    if (!(c.z <= zb)) return;  // GL_LEQUAL
+    if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) { zb = c.z; zdirty = true; }
+  }
+  Px src = S::source(a, c, row, xx, y, FMT == WRCU_FMT_RGBA8);
+  if (a.blend != WRCU_BLEND_NONE) {
+    if (c.flags & (CMD_AA | CMD_MASK)) {
+      const CmdCold& k = a.cold[c.cold];
+      // Order of the two source modifiers: the blend stage applies AA then the
+      // clip mask (blend.h:447-461); commit_masked_solid_span (swgl_ext.h:10-24)
+      // — whole chunks of solid spans — folds the mask into the colour first.
+      int len = c.x1 - c.x0;
+      bool mask_first = (c.flags & CMD_SPAN_SOLID) && (xx - c.x0) < (len >= 4 ? (len & ~3) : 0);
+      int mk = 255;
+      if (c.flags & CMD_MASK) mk = __ldg(k.mask_ptr + (size_t)(y - k.cmy) * k.mask_pitch + (xx - k.cmx));
+      if ((c.flags & CMD_MASK) && mask_first) {
+        if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
+        else src.r = wr_muldiv255(src.r, mk);
+      }
+      if (c.flags & CMD_AA) {
+        int aa = wr_aa_weight(c, k, xx);
+        if (FMT == WRCU_FMT_RGBA8) src = px_scale256(src, aa);
+        else src.r = wr_muldiv256(src.r, aa);
+      }
+      if ((c.flags & CMD_MASK) && !mask_first) {
+        if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
+        else src.r = wr_muldiv255(src.r, mk);
+      }
+    }
+    if (FMT == WRCU_FMT_RGBA8) px = px_pack(wr_blend_rgba8(a.blend, src, px_unpack(px), a.blend_color));
+    else px = wr_pack16(wr_blend_r8(a.blend, src.r, (int)px));
+  } else {
+    if (FMT == WRCU_FMT_RGBA8) px = px_pack(src);
+    else px = wr_pack16(src.r);
+  }
+  dirty = true;
+}
+
+#ifdef WRCU_HOSTEMU
+// tests only: the same per-pixel code, pixel by pixel, commands in batch order
+template <class S, int FMT>
+static void wr_raster(const RasterArgs& a) {
+  const BatchInfo bi = *a.info;
+  if (a.fast_eligible && bi.simple) return;
+  for (int y = 0; y < a.tgt.h; y++) {
+    uint8_t* rowp = a.tgt.color + (size_t)y * a.tgt.color_pitch;
+    uint32_t* zrow = a.tgt.depth ? (uint32_t*)((uint8_t*)a.tgt.depth + (size_t)y * a.tgt.depth_pitch) : nullptr;
+    const bool use_depth = a.depth_mode != WRCU_DEPTH_OFF && zrow != nullptr;
+    for (int i = 0; i < a.n; i++) {
+      const CmdHot c = a.hot[i];
+      if (y < c.y0 || y >= c.y1) continue;
+      typename S::Row row;
+      S::row_setup(a, c, y, FMT == WRCU_FMT_RGBA8, row);
+      for (int xx = c.x0; xx < c.x1; xx++) {
+        uint32_t px = FMT == WRCU_FMT_RGBA8 ? ((uint32_t*)rowp)[xx] : rowp[xx];
+        uint32_t zb = use_depth ? zrow[xx] : 0;
+        bool dirty = false, zdirty = false;
+        wr_shade_pixel<S, FMT>(a, c, row, xx, y, use_depth, px, zb, dirty, zdirty);
+        if (dirty) { if (FMT == WRCU_FMT_RGBA8) ((uint32_t*)rowp)[xx] = px; else rowp[xx] = (uint8_t)px; }
+        if (zdirty) zrow[xx] = zb;
+      }
+    }
+  }
+}
+static void wr_raster_solid_premult(const RasterArgs& a) {
+  const BatchInfo bi = *a.info;
+  if (!bi.simple) return;
+  for (int i = 0; i < a.n; i++) {
+    const CmdHot c = a.hot[i];
+    uint32_t srb = (uint32_t)c.col[0] | ((uint32_t)c.col[2] << 16), sga = (uint32_t)c.col[1] | ((uint32_t)c.col[3] << 16);
+    uint32_t cc = 255u - c.col[3];
+    for (int y = c.y0; y < c.y1; y++) {
+      uint32_t* rowp = (uint32_t*)(a.tgt.color + (size_t)y * a.tgt.color_pitch);
+      for (int x = c.x0; x < c.x1; x++) {
+        uint32_t p = rowp[x];
+        uint32_t rb = wr_premult_over_pair(p & 0x00FF00FFu, srb, cc);
+        uint32_t ga = wr_premult_over_pair((p >> 8) & 0x00FF00FFu, sga, cc);
+        rowp[x] = rb | (ga << 8);
+      }
+    }
+  }
+}
+#else
 // ---- the generic tile kernel (any command kind via the shader policy S, any
 // blend key).  S::row_setup computes per-(command,row) constants once per warp
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
@@ -261,43 +370,7 @@ wr_raster(RasterArgs a) {
       for (int p = 0; p < 4; p++) {
         int xx = x + p;
         if (xx < c.x0 || xx >= c.x1) continue;
-        if (use_depth) {
-          if (!(c.z <= zb[p])) continue;  // GL_LEQUAL
-          if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) { zb[p] = c.z; zdirty = true; }
-        }
-        Px src = S::source(a, c, row, xx, y, FMT == WRCU_FMT_RGBA8);
-        if (a.blend != WRCU_BLEND_NONE) {
-          if (c.flags & (CMD_AA | CMD_MASK)) {
-            const CmdCold& k = a.cold[c.cold];
-            // Order of the two source modifiers: the blend stage applies AA then
-            // the clip mask (blend.h:447-461); commit_masked_solid_span
-            // (swgl_ext.h:10-24) — whole chunks of solid spans — folds the mask
-            // into the colour first.
-            int len = c.x1 - c.x0;
-            bool mask_first = (c.flags & CMD_SPAN_SOLID) && (xx - c.x0) < (len >= 4 ? (len & ~3) : 0);
-            int mk = 255;
-            if (c.flags & CMD_MASK) mk = __ldg(k.mask_ptr + (size_t)(y - k.cmy) * k.mask_pitch + (xx - k.cmx));
-            if ((c.flags & CMD_MASK) && mask_first) {
-              if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
-              else src.r = wr_muldiv255(src.r, mk);
-            }
-            if (c.flags & CMD_AA) {
-              int aa = wr_aa_weight(c, k, xx);
-              if (FMT == WRCU_FMT_RGBA8) src = px_scale256(src, aa);
-              else src.r = wr_muldiv256(src.r, aa);
-            }
-            if ((c.flags & CMD_MASK) && !mask_first) {
-              if (FMT == WRCU_FMT_RGBA8) src = px_scale255(src, mk);
-              else src.r = wr_muldiv255(src.r, mk);
-            }
-          }
-          if (FMT == WRCU_FMT_RGBA8) px[p] = px_pack(wr_blend_rgba8(a.blend, src, px_unpack(px[p]), a.blend_color));
-          else px[p] = wr_pack16(wr_blend_r8(a.blend, src.r, (int)px[p]));
-        } else {
-          if (FMT == WRCU_FMT_RGBA8) px[p] = px_pack(src);
-          else px[p] = wr_pack16(src.r);
-        }
-        dirty = true;
+        wr_shade_pixel<S, FMT>(a, c, row, xx, y, use_depth, px[p], zb[p], dirty, zdirty);
       }
     }
   }
@@ -383,3 +456,4 @@ wr_raster_solid_premult(RasterArgs a) {
     *(uint4*)rowp = v;
   }
 }
+#endif  // !WRCU_HOSTEMU

@@ -6,18 +6,18 @@
 #include "blend.cuh"
 #include "wrcu_internal.h"
 
-__device__ __forceinline__ int wr_clamp_coord(int coord, int limit) {  // texture.h:73-75
+WRD int wr_clamp_coord(int coord, int limit) {  // texture.h:73-75
   return min(max(coord, 0), limit - 1);
 }
 
-__device__ __forceinline__ int wr_lerp7(int a, int b, int f) {
+WRD int wr_lerp7(int a, int b, int f) {
   // a + (((b - a) * f) >> 7) in int16 lanes (texture.h:493-497)
   return (int)(short)(a + (int)(short)(((int)(short)((b - a) * f)) >> 7));
 }
 
 // textureLinearUnpackedRGBA8 for one lane (texture.h:1027-1075): (ix,iy) is the
 // coordinate quantised to 1/128 texel (linearQuantize, texture.h:427-431).
-__device__ __forceinline__ Px wr_texture_linear_rgba8(const TexView& t, int ix, int iy) {
+WRD Px wr_texture_linear_rgba8(const TexView& t, int ix, int iy) {
   int x = ix >> 7, y = iy >> 7;
   int cx = wr_clamp_coord(x, t.w - 1);
   int cy = wr_clamp_coord(y, t.h);
@@ -41,7 +41,7 @@ __device__ __forceinline__ Px wr_texture_linear_rgba8(const TexView& t, int ix, 
 }
 
 // textureLinearUnpackedR8 for one lane (texture.h:542-574)
-__device__ __forceinline__ int wr_texture_linear_r8(const TexView& t, int ix, int iy) {
+WRD int wr_texture_linear_r8(const TexView& t, int ix, int iy) {
   int x = ix >> 7, y = iy >> 7;
   int cx = wr_clamp_coord(x, t.w - 1);
   int cy = wr_clamp_coord(y, t.h);
@@ -57,6 +57,6 @@ __device__ __forceinline__ int wr_texture_linear_r8(const TexView& t, int ix, in
 }
 
 // linearQuantize(P, 128, sampler) for one axis: (uv * size) * 128 + (0.5 - 64)
-__device__ __forceinline__ float wr_linear_quantize(float uv, int size) {
+WRD float wr_linear_quantize(float uv, int size) {
   return __fadd_rn(__fmul_rn(__fmul_rn(uv, (float)size), 128.0f), 0.5f - 0.5f * 128.0f);
 }

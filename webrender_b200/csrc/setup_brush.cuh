@@ -15,7 +15,7 @@ struct DevPrimHeader {
   int user_data[4];
 };
 
-__device__ inline DevPrimHeader wr_fetch_prim_header(const FrameTablesDev& T, int index) {
+WRD DevPrimHeader wr_fetch_prim_header(const FrameTablesDev& T, int index) {
   DevPrimHeader ph;
   float4 f0 = wr_fetch(T.prim_headers_f, T.n_prim_headers_f, index * 2);
   float4 f1 = wr_fetch(T.prim_headers_f, T.n_prim_headers_f, index * 2 + 1);
@@ -43,7 +43,7 @@ struct BrushVS {
 };
 
 // write_clip → swgl_clipMask (prim_shared.glsl:183-190, swgl_ext.h:1867-1877)
-__device__ inline void wr_write_clip(const FrameTablesDev& T, int clip_address, const DevPictureTask& task,
+WRD void wr_write_clip(const FrameTablesDev& T, int clip_address, const DevPictureTask& task,
                                      QuadOut& q) {
   if (clip_address >= 0x7FFFFFFF) return;  // CLIP_TASK_EMPTY → zero rect → ignored
   float4 a = wr_fetch(T.render_tasks, T.n_render_tasks, clip_address * 2);
@@ -62,7 +62,7 @@ __device__ inline void wr_write_clip(const FrameTablesDev& T, int clip_address, 
   }
 }
 
-__device__ inline void wr_brush_vertex(const SetupArgs& a, int4 aData, int vecs_per_specific_brush,
+WRD void wr_brush_vertex(const SetupArgs& a, int4 aData, int vecs_per_specific_brush,
                                        QuadOut& q, BrushVS& o) {
   const FrameTablesDev& T = a.tabs;
   int prim_header_address = aData.x, clip_address = aData.y;
@@ -118,14 +118,14 @@ __device__ inline void wr_brush_vertex(const SetupArgs& a, int4 aData, int vecs_
   wr_write_clip(T, clip_address, o.task, q);
 }
 
-__device__ __forceinline__ void wr_pack_color(QuadOut& q, const float* col) {
+WRD void wr_pack_color(QuadOut& q, const float* col) {
   q.col[0] = (uint16_t)wr_round_pixel(col[2], 255.0f);
   q.col[1] = (uint16_t)wr_round_pixel(col[1], 255.0f);
   q.col[2] = (uint16_t)wr_round_pixel(col[0], 255.0f);
   q.col[3] = (uint16_t)wr_round_pixel(col[3], 255.0f);
 }
 
-__device__ __forceinline__ void wr_finish_setup(const SetupArgs& a, int unsupported) {
+WRD void wr_finish_setup(const SetupArgs& a, int unsupported) {
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);
     atomicAdd(a.err_counter, 1);
@@ -133,9 +133,7 @@ __device__ __forceinline__ void wr_finish_setup(const SetupArgs& a, int unsuppor
 }
 
 // brush_solid (brush_solid.glsl:22-38): colour = gpu_cache[prim] * opacity
-__global__ void wr_setup_brush_solid(SetupArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.n) return;
+WRD void wr_setup_brush_solid_one(const SetupArgs& a, int idx) {
   int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
   QuadOut q;
   BrushVS vs;
@@ -150,3 +148,4 @@ __global__ void wr_setup_brush_solid(SetupArgs a) {
   wr_emit_quad(a, idx, q, &unsupported);
   wr_finish_setup(a, unsupported);
 }
+WR_SETUP_KERNEL(wr_setup_brush_solid)

@@ -5,7 +5,7 @@
 #include "setup_common.cuh"
 #include "shader_clip_rect.cuh"
 
-__device__ inline float4 wr_get_node_pos(float px, float py, const DevTransform& t) {
+WRD float4 wr_get_node_pos(float px, float py, const DevTransform& t) {
   float4 ah = wr_mat_mul(t.m, make_float4(0.0f, 0.0f, 0.0f, 1.0f));
   float ax = ah.x / ah.w, ay = ah.y / ah.w, az = ah.z / ah.w;
   float nx = t.inv_m[0] * 0.0f + t.inv_m[1] * 0.0f + t.inv_m[2] * 1.0f;
@@ -23,7 +23,7 @@ __device__ inline float4 wr_get_node_pos(float px, float py, const DevTransform&
 }
 
 // common: ClipMaskInstanceCommon at the start of every clip instance
-__device__ inline void wr_clip_tile_vertex(const SetupArgs& a, const float* f, QuadOut& q, float4 local_out[4]) {
+WRD void wr_clip_tile_vertex(const SetupArgs& a, const float* f, QuadOut& q, float4 local_out[4]) {
   const int* ids = (const int*)(f + 9);
   DevTransform clip_transform = wr_fetch_transform(a.tabs, ids[0]);
   DevTransform prim_transform = wr_fetch_transform(a.tabs, ids[1]);
@@ -43,14 +43,12 @@ __device__ inline void wr_clip_tile_vertex(const SetupArgs& a, const float* f, Q
   }
 }
 
-__device__ __forceinline__ void wr_inverse_radii_squared(const float* r, float* out) {
+WRD void wr_inverse_radii_squared(const float* r, float* out) {
   out[0] = 1.0f / wr_max(r[0] * r[0], 1.0e-6f);
   out[1] = 1.0f / wr_max(r[1] * r[1], 1.0e-6f);
 }
 
-__global__ void wr_setup_clip_rectangle(SetupArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.n) return;
+WRD void wr_setup_clip_rectangle_one(const SetupArgs& a, int idx) {
   const float* f = (const float*)(a.instances + (size_t)idx * a.stride);
   bool fast = (a.features & WRCU_FEAT_FAST_PATH) != 0;
   QuadOut q;
@@ -63,8 +61,8 @@ __global__ void wr_setup_clip_rectangle(SetupArgs a) {
   const float* corner[4] = {f + 18, f + 26, f + 34, f + 42};  // TL, TR, BL, BR
   float diffx = clx - lr[0], diffy = cly - lr[1];
   lr[0] = clx; lr[1] = cly; lr[2] += diffx; lr[3] += diffy;
-  float g[36];
-  for (int i = 0; i < 36; i++) g[i] = 0.0f;
+  float g[40];
+  for (int i = 0; i < 40; i++) g[i] = 0.0f;
   g[CR_MODE] = mode;
   g[CR_FAST] = fast ? 1.0f : 0.0f;
   g[CR_BOUNDS] = lr[0]; g[CR_BOUNDS + 1] = lr[1]; g[CR_BOUNDS + 2] = lr[2]; g[CR_BOUNDS + 3] = lr[3];
@@ -100,10 +98,11 @@ __global__ void wr_setup_clip_rectangle(SetupArgs a) {
   bool ok = wr_emit_quad(a, idx, q, &unsupported);
   if (ok) {
     CmdCold* k = &a.cold[idx];
-    for (int i = 0; i < 36; i++) k->g[i] = g[i];
+    for (int i = 0; i < 40; i++) k->g[i] = g[i];
   }
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);
     atomicAdd(a.err_counter, 1);
   }
 }
+WR_SETUP_KERNEL(wr_setup_clip_rectangle)

@@ -27,12 +27,25 @@ struct SetupArgs {
   TexView clip_mask;
 };
 
-__device__ __forceinline__ float4 wr_fetch(const float4* t, int n, int addr) {
+// A setup kernel = one thread per instance running <name>_one.  Under the host
+// emulation (tests only) the same function is called in a plain loop.
+#ifdef WRCU_HOSTEMU
+#define WR_SETUP_KERNEL(name) \
+  static void name(const SetupArgs& a) { for (int i = 0; i < a.n; i++) name##_one(a, i); }
+#else
+#define WR_SETUP_KERNEL(name)                              \
+  __global__ void name(SetupArgs a) {                      \
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;       \
+    if (idx < a.n) name##_one(a, idx);                     \
+  }
+#endif
+
+WRD float4 wr_fetch(const float4* t, int n, int addr) {
   if (n <= 0) return make_float4(0, 0, 0, 0);
   addr = min(max(addr, 0), n - 1);
   return __ldg(t + addr);
 }
-__device__ __forceinline__ int4 wr_fetchi(const int4* t, int n, int addr) {
+WRD int4 wr_fetchi(const int4* t, int n, int addr) {
   if (n <= 0) return make_int4(0, 0, 0, 0);
   addr = min(max(addr, 0), n - 1);
   return __ldg(t + addr);
@@ -43,7 +56,7 @@ struct DevTransform {
   bool is_axis_aligned;
 };
 
-__device__ inline DevTransform wr_fetch_transform(const FrameTablesDev& t, int id) {
+WRD DevTransform wr_fetch_transform(const FrameTablesDev& t, int id) {
   DevTransform r;
   r.is_axis_aligned = (id >> 23) == 0;
   int index = id & 0x007fffff;
@@ -57,7 +70,7 @@ __device__ inline DevTransform wr_fetch_transform(const FrameTablesDev& t, int i
 }
 
 // mat4 * vec4 with glsl.h's evaluation order (glsl.h:2581-2588)
-__device__ __forceinline__ float4 wr_mat_mul(const float* m, float4 v) {
+WRD float4 wr_mat_mul(const float* m, float4 v) {
   float4 u;
   u.x = m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * v.w;
   u.y = m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * v.w;
@@ -71,13 +84,13 @@ struct DevPictureTask {
   float device_pixel_scale;
   float ox, oy;  // content_origin
 };
-__device__ inline DevPictureTask wr_fetch_picture_task(const FrameTablesDev& t, int address) {
+WRD DevPictureTask wr_fetch_picture_task(const FrameTablesDev& t, int address) {
   float4 a = wr_fetch(t.render_tasks, t.n_render_tasks, address * 2);
   float4 b = wr_fetch(t.render_tasks, t.n_render_tasks, address * 2 + 1);
   return DevPictureTask{a.x, a.y, a.z, a.w, b.x, b.y, b.z};
 }
 
-__device__ __forceinline__ int wr_round_i(float v) { return (int)floorf(v + 0.5f); }
+WRD int wr_round_i(float v) { return (int)floorf(v + 0.5f); }
 
 // Output of a kind's vertex stage for one instance.
 struct QuadOut {
@@ -96,7 +109,7 @@ struct QuadOut {
 // false (and writes an empty command) when the instance draws nothing.
 // Sets *unsupported when the quad needs the general edge walker (rotation or
 // perspective), which this backend does not rasterise yet.
-__device__ inline bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupported) {
+WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupported) {
   CmdHot h;
   h.x0 = h.y0 = h.x1 = h.y1 = 0;
   h.flags = 0;

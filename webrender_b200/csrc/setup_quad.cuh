@@ -22,7 +22,7 @@ struct QuadPrimInfo {
   int pattern_input[2];
 };
 
-__device__ inline void wr_quad_primitive_info(const SetupArgs& a, int4 aData, QuadOut& q,
+WRD void wr_quad_primitive_info(const SetupArgs& a, int4 aData, QuadOut& q,
                                               QuadPrimInfo& pi) {
   const FrameTablesDev& T = a.tabs;
   int prim_address_i = aData.x, prim_address_f = aData.y;
@@ -107,9 +107,7 @@ __device__ inline void wr_quad_primitive_info(const SetupArgs& a, int4 aData, Qu
   pi.quad_flags = quad_flags;
 }
 
-__global__ void wr_setup_quad_textured(SetupArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.n) return;
+WRD void wr_setup_quad_textured_one(const SetupArgs& a, int idx) {
   int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
   QuadOut q;
   QuadPrimInfo pi;
@@ -156,3 +154,4 @@ __global__ void wr_setup_quad_textured(SetupArgs a) {
     atomicAdd(a.err_counter, 1);
   }
 }
+WR_SETUP_KERNEL(wr_setup_quad_textured)

@@ -23,25 +23,25 @@
 #define CR_CORNER 9
 #define CR_PLANE 25
 
-__device__ __forceinline__ float cr_distance_aa(float aa_range, float sd) {
+WRD float cr_distance_aa(float aa_range, float sd) {
   return wr_clamp(0.5f - sd * aa_range, 0.0f, 1.0f);
 }
-__device__ __forceinline__ float cr_mix(float x, float y, float a) { return (y - x) * a + x; }
-__device__ __forceinline__ float cr_sd_rounded_box(float px, float py, const float* p) {
+WRD float cr_mix(float x, float y, float a) { return (y - x) * a + x; }
+WRD float cr_sd_rounded_box(float px, float py, const float* p) {
   float dx = fabsf(px) - p[0], dy = fabsf(py) - p[1];
   float mx = wr_max(dx, 0.0f), my = wr_max(dy, 0.0f);
   return (sqrtf(mx * mx + my * my) + wr_min(wr_max(dx, dy), 0.0f)) - p[2];
 }
-__device__ __forceinline__ float cr_ellipse_approx(float px, float py, float irx, float iry, float scale) {
+WRD float cr_ellipse_approx(float px, float py, float irx, float iry, float scale) {
   float prx = px * irx, pry = py * iry;
   float g = (px * prx + py * pry) - scale;
   float gx = (1.0f + scale) * prx, gy = (1.0f + scale) * pry;
   return g * (1.0f / sqrtf(gx * gx + gy * gy));
 }
-__device__ __forceinline__ float cr_sd_rect(float px, float py, const float* b) {
+WRD float cr_sd_rect(float px, float py, const float* b) {
   return wr_max(wr_max(b[0] - px, px - b[2]), wr_max(b[1] - py, py - b[3]));
 }
-__device__ inline float cr_distance_to_rounded_rect(const float* g, float px, float py) {
+WRD float cr_distance_to_rounded_rect(const float* g, float px, float py) {
   const float* cr = g + CR_CORNER;
   const float* pl = g + CR_PLANE;
   float c0 = 1.0e-6f, c1 = 1.0e-6f, c2 = 1.0f, c3 = 1.0f;
@@ -64,25 +64,11 @@ struct ClipRectShader {
     float sp[3], ep[3], sc[4], ec[4];  // start/end plane and corner
   };
 
-  __device__ static inline void row_setup(const RasterArgs& a, const CmdHot& c, int y, bool rgba, Row& r) {
+  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
     r.g = k.g;
-    // interpolants at the span start: closed form of the edge walk
-    {
-      float yc = (float)y + 0.5f;
-      float dy = yc - k.yt;
-      float stepScale = 1.0f / (k.xr - k.xl);
-      if (!isfinite(stepScale)) stepScale = 0.0f;
-      float x0f = ((float)c.x0 + 0.5f) - k.xl;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float li = k.i_lt[i] + dy * ((k.i_lb[i] - k.i_lt[i]) * k.yscale);
-        float ri = k.i_rt[i] + dy * ((k.i_rb[i] - k.i_rt[i]) * k.yscale);
-        float st = (ri - li) * stepScale;
-        r.step[i] = st;
-        r.L0[i] = li + st * x0f;
-      }
-    }
+    // interpolants at the span start (exact running sums of the edge walk)
+    wr_row_interp<4>(k, c, y, r.L0, r.step);
     int len = c.x1 - c.x0;
     r.body_len = (!rgba && len >= 4) ? (len & ~3) : 0;
     r.span_ok = false;
@@ -183,7 +169,7 @@ struct ClipRectShader {
     r.end_corner_on = !fast && r.ep[0] < 1.0e5f;
   }
 
-  __device__ static inline Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int y, bool rgba) {
+  WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int y, bool rgba) {
     (void)a; (void)y;
     const float* g = r.g;
     float mode = g[CR_MODE];

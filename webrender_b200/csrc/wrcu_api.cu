@@ -36,8 +36,17 @@ static int fmt_bpp(int fmt) {
   return 0;
 }
 
+// ---- launch helpers: real kernel launches, or (tests only) host loops -------------
+#ifdef WRCU_HOSTEMU
+#define WR_LAUNCH(kernel, grid, block, stream, ...) kernel(__VA_ARGS__)
+#define WR_GLOBAL static
+#else
+#define WR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define WR_GLOBAL __global__
+#endif
+
 // ---- small kernels ---------------------------------------------------------------
-__global__ void wr_init_batch_info(BatchInfo* info) {
+WR_GLOBAL void wr_init_batch_info(BatchInfo* info) {
   info->bx0 = 0x7fffffff; info->by0 = 0x7fffffff;
   info->bx1 = -0x7fffffff; info->by1 = -0x7fffffff;
   info->unsupported = 0;
@@ -46,6 +55,14 @@ __global__ void wr_init_batch_info(BatchInfo* info) {
 
 // Clear (swgl/src/gl.cc:2498-2518 → clear_buffer): fills a rect of a 4-byte or
 // 1-byte target.  Rows are written as 16-byte vectors where alignment allows.
+#ifdef WRCU_HOSTEMU
+static void wr_clear_u32(uint8_t* base, int pitch, int x0, int y0, int x1, int y1, uint32_t v) {
+  for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++) ((uint32_t*)(base + (size_t)y * pitch))[x] = v;
+}
+static void wr_clear_u8(uint8_t* base, int pitch, int x0, int y0, int x1, int y1, uint8_t v) {
+  for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++) (base + (size_t)y * pitch)[x] = v;
+}
+#else
 __global__ void wr_clear_u32(uint8_t* base, int pitch, int x0, int y0, int x1, int y1, uint32_t v) {
   int y = y0 + blockIdx.y;
   if (y >= y1) return;
@@ -70,6 +87,8 @@ __global__ void wr_clear_u8(uint8_t* base, int pitch, int x0, int y0, int x1, in
   uint8_t* row = base + (size_t)y * pitch;
   for (int x = x0 + blockIdx.x * blockDim.x + threadIdx.x; x < x1; x += gridDim.x * blockDim.x) row[x] = v;
 }
+
+#endif
 
 // ---- context -----------------------------------------------------------------------
 extern "C" int wrcu_abi_version(void) { return WRCU_ABI_VERSION; }
@@ -393,16 +412,16 @@ extern "C" int wrcu_clear(wrcu_ctx* c, const int32_t rect[4], const float color[
     uint32_t r = host_round_pixel(color[0]) & 0xFF, g = host_round_pixel(color[1]) & 0xFF;
     uint32_t b = host_round_pixel(color[2]) & 0xFF, a = host_round_pixel(color[3]) & 0xFF;
     if (t->fmt == WRCU_FMT_RGBA8)
-      wr_clear_u32<<<grid, 256, 0, c->stream>>>(t->dptr, (int)t->pitch, x0, y0, x1, y1,
+      WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, t->dptr, (int)t->pitch, x0, y0, x1, y1,
                                                b | (g << 8) | (r << 16) | (a << 24));
     else
-      wr_clear_u8<<<grid, 256, 0, c->stream>>>(t->dptr, (int)t->pitch, x0, y0, x1, y1, (uint8_t)r);
+      WR_LAUNCH(wr_clear_u8, grid, 256, c->stream, t->dptr, (int)t->pitch, x0, y0, x1, y1, (uint8_t)r);
     c->stats.kernel_launches++;
   }
   if (depth && c->depth_tex) {
     WrTexture* d = get_tex(c, c->depth_tex);
     uint32_t z = (uint32_t)((double)*depth * 0xFFFFFF);  // gl.cc:2391
-    wr_clear_u32<<<grid, 256, 0, c->stream>>>(d->dptr, (int)d->pitch, x0, y0, x1, y1, z);
+    WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, d->dptr, (int)d->pitch, x0, y0, x1, y1, z);
     c->stats.kernel_launches++;
   }
   WRCU_CUDA(c, cudaGetLastError());
@@ -495,22 +514,22 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.color0 = tex_view(c, st->color[0]);
   sa.clip_mask = tex_view(c, st->clip_mask);
 
-  wr_init_batch_info<<<1, 1, 0, c->stream>>>((BatchInfo*)c->batch_info);
+  WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info);
   c->stats.kernel_launches++;
   int sblocks = (n + 127) / 128;
   switch (kind) {
     case WRCU_KIND_QUAD_TEXTURED:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "quad instance stride < 16");
-      wr_setup_quad_textured<<<sblocks, 128, 0, c->stream>>>(sa);
+      WR_LAUNCH(wr_setup_quad_textured, sblocks, 128, c->stream, sa);
       break;
     case WRCU_KIND_BRUSH_SOLID:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
-      wr_setup_brush_solid<<<sblocks, 128, 0, c->stream>>>(sa);
+      WR_LAUNCH(wr_setup_brush_solid, sblocks, 128, c->stream, sa);
       break;
     case WRCU_KIND_CLIP_RECTANGLE:
       if (stride < 200) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceRect stride < 200");
       sa.features = features;
-      wr_setup_clip_rectangle<<<sblocks, 128, 0, c->stream>>>(sa);
+      WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
     default:
       return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);
@@ -538,15 +557,17 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
                  ra.depth_mode == WRCU_DEPTH_OFF;
   ra.fast_eligible = fast_ok ? 1 : 0;
   if (fast_ok) {
-    wr_raster_solid_premult<<<grid, WRCU_THREADS, 0, c->stream>>>(ra);
+    WR_LAUNCH(wr_raster_solid_premult, grid, WRCU_THREADS, c->stream, ra);
     c->stats.kernel_launches++;
   }
 #define LAUNCH_RASTER(S)                                                         \
   do {                                                                           \
+    auto k_rgba = wr_raster<S, WRCU_FMT_RGBA8>;                                   \
+    auto k_r8 = wr_raster<S, WRCU_FMT_R8>;                                        \
     if (T.fmt == WRCU_FMT_RGBA8)                                                 \
-      wr_raster<S, WRCU_FMT_RGBA8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);    \
+      WR_LAUNCH(k_rgba, grid, WRCU_THREADS, c->stream, ra);                      \
     else                                                                         \
-      wr_raster<S, WRCU_FMT_R8><<<grid, WRCU_THREADS, 0, c->stream>>>(ra);       \
+      WR_LAUNCH(k_r8, grid, WRCU_THREADS, c->stream, ra);                        \
   } while (0)
   switch (kind) {
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;

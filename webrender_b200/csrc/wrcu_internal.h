@@ -13,7 +13,15 @@
 //   setup_*.cuh      Vertex stages per BatchKind.
 #pragma once
 
+#ifdef WRCU_HOSTEMU
+#include "hostemu_shim.h"  // tests only: g++ build of the device functions (symbols wremu_*)
+#define WRD static inline
+#define WRD_MEMBER static inline
+#else
 #include <cuda_runtime.h>
+#define WRD __device__ __forceinline__
+#define WRD_MEMBER __device__ static __forceinline__
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
