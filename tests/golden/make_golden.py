@@ -1,0 +1,50 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference rasteriser
+(oracle/_ref/libswgl_ref.so built from /root/reference/swgl/src/gl.cc).
+
+Run here (needs /root/reference at build time):  python tests/golden/make_golden.py
+Each case stores the scene-builder call (name + kwargs) and the reference's output
+bytes; tests rebuild the frame from the call and compare oracle / CUDA output to
+the stored bytes.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CASES = [
+    ("alpha_rects_premult", "alpha_rects_frame", dict(width=301, height=157, n_rects=37, random_rects=True, seed=3)),
+    ("alpha_rects_full_cover", "alpha_rects_frame", dict(width=256, height=64, n_rects=100)),
+    ("alpha_rects_softlight", "alpha_rects_frame", dict(width=160, height=64, n_rects=24, random_rects=True, seed=122,
+                                                         blend=22, color=None, clear_color=(0.4, 0.7, 0.2, 0.8))),
+    ("alpha_rects_hue", "alpha_rects_frame", dict(width=160, height=64, n_rects=24, random_rects=True, seed=125,
+                                                   blend=25, color=None, clear_color=(0.4, 0.7, 0.2, 0.8))),
+    ("brush_solid_masks_depth", "brush_solid_frame", dict(width=333, height=207, seed=1)),
+    ("brush_solid_aa_fractional", "brush_solid_frame", dict(width=333, height=207, seed=2, fractional=True, force_aa=True)),
+    ("clip_rect_integer", "clip_mask_frame", dict(seed=1)),
+    ("clip_rect_fractional", "clip_mask_frame", dict(seed=2, fractional=True)),
+    ("clip_rect_scaled", "clip_mask_frame", dict(seed=3, fractional=True, scale=1.25)),
+]
+
+
+def main():
+    from common import render
+    from oracle.backends import SwglDevice
+    from webrender_b200 import scenes
+    index = {}
+    for name, builder, kwargs in CASES:
+        frame = getattr(scenes, builder)(**kwargs)
+        out = render(SwglDevice, frame)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(out)}
+        print(name, {k: v.shape for k, v in out.items()})
+    json.dump(index, open(os.path.join(HERE, "index.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
