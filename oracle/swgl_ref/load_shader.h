@@ -7,6 +7,7 @@
 #include "brush.h"
 #include "brush_solid.h"
 #include "cs_clip_rectangle.h"
+#include "ps_quad_mask.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -14,5 +15,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "brush_solid ALPHA_PASS")) return brush_solid_ALPHA_PASS_program::loader;
   if (!strcmp(name, "cs_clip_rectangle")) return cs_clip_rectangle_program::loader;
   if (!strcmp(name, "cs_clip_rectangle FAST_PATH")) return cs_clip_rectangle_FAST_PATH_program::loader;
+  if (!strcmp(name, "ps_quad_mask")) return ps_quad_mask_program::loader;
+  if (!strcmp(name, "ps_quad_mask FAST_PATH")) return ps_quad_mask_FAST_PATH_program::loader;
   return nullptr;
 }

@@ -101,3 +101,13 @@ def test_clip_rectangle_masks_bit_exact(seed, variant):
 def test_clip_rectangle_large():
     f = scenes.clip_mask_frame(2048, 1024, n_clips=40, seed=9, fractional=True)
     assert_same(render(CudaDevice, f), render(OracleDevice, f))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled", "nearest"])
+def test_rounded_rects_indirect(seed, variant):
+    """Config A flavour: quad → off-screen, ps_quad_mask multiply, textured composite."""
+    f = scenes.rounded_rects_frame(seed=seed, fractional=variant in ("fractional", "scaled"),
+                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0,
+                                   filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(CudaDevice, f), render(OracleDevice, f), variant)

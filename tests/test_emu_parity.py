@@ -29,3 +29,12 @@ def test_brush_solid(variant):
 def test_clip_rectangle(seed, variant):
     f = scenes.clip_mask_frame(seed=seed, fractional=variant != "integer", scale=1.25 if variant == "scaled" else 1.0)
     assert_same(render(EmuDevice, f), render(OracleDevice, f), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled", "nearest"])
+def test_rounded_rects_indirect(seed, variant):
+    f = scenes.rounded_rects_frame(seed=seed, fractional=variant in ("fractional", "scaled"),
+                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0,
+                                   filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f), variant)

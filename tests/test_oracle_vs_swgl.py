@@ -50,3 +50,14 @@ def test_clip_rectangle_masks(seed, variant):
     secondary (multiply) — bit-exact R8 masks."""
     f = scenes.clip_mask_frame(seed=seed, fractional=variant != "integer", scale=1.25 if variant == "scaled" else 1.0)
     assert_same(render(SwglDevice, f), render(OracleDevice, f), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled", "nearest"])
+def test_rounded_rects_indirect(seed, variant):
+    """Config A flavour: off-screen quad + ps_quad_mask (fast/slow) multiply, then a
+    textured composite quad sampling the off-screen task."""
+    f = scenes.rounded_rects_frame(seed=seed, fractional=variant in ("fractional", "scaled"),
+                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0,
+                                   filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), variant)

@@ -85,17 +85,54 @@ WRD void wr_row_interp(const CmdCold& k, const CmdHot& c, int y, float* o, float
 }
 
 // Value of interpolant lanes at pixel x of the span: lane j of chunk k.  Chunk
-// advance is closed-form (o + (4*step)*k, exact for the 1:1 mappings that
-// dominate); the lane offset accumulates sequentially as init_interp does
-// (glsl.h:3083-3088).
+// offset accumulates sequentially as init_interp does (glsl.h:3083-3088), then
+// the chunk advance is one multiply-add (step_interp_inputs(drawn) after a
+// span body; exact for the 1:1 mappings that dominate).
 template <int N>
 WRD void wr_interp_at(const float* o, const float* step, int rel, float* out) {
   int j = rel & 3;
   float kf = (float)(rel >> 2);
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    float v = __fadd_rn(o[i], __fmul_rn(__fmul_rn(step[i], 4.0f), kf));
-    for (int s = 0; s < j; s++) v = __fadd_rn(v, step[i]);
+    float v = o[i];
+    for (int s = 0; s < j; s++) v = __fadd_rn(v, step[i]);         // init_interp lanes first,
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(step[i], 4.0f), kf));     // then interp_step * chunks
+    out[i] = v;
+  }
+}
+
+// Fragment-path interpolants: the reference advances varyings once per 4-pixel
+// chunk (v += interp_step, glsl-to-cxx step_interp_inputs), a running sum.
+// wr_chunk_base walks that sum to the first chunk a tile touches (warp-uniform,
+// once per command/row/tile); wr_chunk_lane finishes the walk for one pixel
+// (at most 32 more additions inside a 128-pixel tile).
+template <int N>
+WRD int wr_chunk_base(const float* o, const float* step, const CmdHot& c, int tx0, float (*base)[N]) {
+  int kb = max(0, (max(tx0, (int)c.x0) - (int)c.x0) >> 2);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float is = __fmul_rn(step[i], 4.0f);
+    float v = o[i];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      // init_interp: lane j of chunk 0 = lane j-1 + step (glsl.h:3083-3088);
+      // every later chunk adds interp_step to each lane
+      float l = v;
+      for (int s = 0; s < kb; s++) l = __fadd_rn(l, is);
+      base[j][i] = l;
+      v = __fadd_rn(v, step[i]);
+    }
+  }
+  return kb;
+}
+// lane j (0..3) of chunk k >= kb, given the lanes of chunk kb in base
+template <int N>
+WRD void wr_chunk_lane(const float (*base)[N], const float* step, int kb, int k, int j, float* out) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float is = __fmul_rn(step[i], 4.0f);
+    float v = base[j][i];
+    for (int s = kb; s < k; s++) v = __fadd_rn(v, is);
     out[i] = v;
   }
 }
@@ -219,7 +256,7 @@ struct QuadShader {
   struct Row {
     float o[2], step[2];
   };
-  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, bool, Row& r) {
+  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int, bool, Row& r) {
     if (c.flags & CMD_TEXTURED) wr_row_interp<2>(a.cold[c.cold], c, y, r.o, r.step);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int y, bool rgba) {
@@ -285,14 +322,16 @@ static void wr_raster(const RasterArgs& a) {
       const CmdHot c = a.hot[i];
       if (y < c.y0 || y >= c.y1) continue;
       typename S::Row row;
-      S::row_setup(a, c, y, FMT == WRCU_FMT_RGBA8, row);
-      for (int xx = c.x0; xx < c.x1; xx++) {
+      for (int tx0 = (c.x0 / WRCU_TILE_W) * WRCU_TILE_W; tx0 < c.x1; tx0 += WRCU_TILE_W) {
+      S::row_setup(a, c, y, tx0, FMT == WRCU_FMT_RGBA8, row);
+      for (int xx = max((int)c.x0, tx0); xx < min((int)c.x1, tx0 + WRCU_TILE_W); xx++) {
         uint32_t px = FMT == WRCU_FMT_RGBA8 ? ((uint32_t*)rowp)[xx] : rowp[xx];
         uint32_t zb = use_depth ? zrow[xx] : 0;
         bool dirty = false, zdirty = false;
         wr_shade_pixel<S, FMT>(a, c, row, xx, y, use_depth, px, zb, dirty, zdirty);
         if (dirty) { if (FMT == WRCU_FMT_RGBA8) ((uint32_t*)rowp)[xx] = px; else rowp[xx] = (uint8_t)px; }
         if (zdirty) zrow[xx] = zb;
+      }
       }
     }
   }
@@ -365,7 +404,7 @@ wr_raster(RasterArgs a) {
         }
       }
       typename S::Row row;
-      S::row_setup(a, c, y, FMT == WRCU_FMT_RGBA8, row);
+      S::row_setup(a, c, y, tx0, FMT == WRCU_FMT_RGBA8, row);
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         int xx = x + p;

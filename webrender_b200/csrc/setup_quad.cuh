@@ -5,6 +5,7 @@
 // swgl_antiAlias instead of AA varyings).  One thread per instance.
 #pragma once
 #include "setup_common.cuh"
+#include "setup_clip.cuh"
 
 #define WR_QF_IS_OPAQUE 1
 #define WR_QF_APPLY_DEVICE_CLIP 2
@@ -155,3 +156,73 @@ WRD void wr_setup_quad_textured_one(const SetupArgs& a, int idx) {
   }
 }
 WR_SETUP_KERNEL(wr_setup_quad_textured)
+
+// ps_quad_mask (ps_quad_mask.glsl:66-137): MaskInstance = quad instance +
+// aClipData [clip_transform_id, clip_address, clip_space, _].
+WRD void wr_setup_quad_mask_one(const SetupArgs& a, int idx) {
+  const int* inst = (const int*)(a.instances + (size_t)idx * a.stride);
+  int4 aData = make_int4(inst[0], inst[1], inst[2], inst[3]);
+  int clip_transform_id = inst[4], index = inst[5], space = inst[6];
+  bool fast = (a.features & WRCU_FEAT_FAST_PATH) != 0;
+  QuadOut q;
+  QuadPrimInfo pi;
+  memset(&q, 0, sizeof q);
+  wr_quad_primitive_info(a, aData, q, pi);
+  const FrameTablesDev& T = a.tabs;
+  float4 t0 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, index);
+  float4 t1 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, index + 1);
+  float4 t2 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, index + 2);
+  float4 t3 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, index + 3);
+  float lr[4] = {t0.x, t0.y, t0.z, t0.w};
+  DevTransform ct = wr_fetch_transform(T, clip_transform_id);
+  for (int k = 0; k < 4; k++) {
+    float4 p = wr_mat_mul(ct.m, make_float4(pi.local_pos[k].x, pi.local_pos[k].y, 0.0f, 1.0f));
+    q.interp[k][0] = p.x; q.interp[k][1] = p.y; q.interp[k][2] = p.z; q.interp[k][3] = p.w;
+  }
+  q.n_interp = 4;
+  float g[40];
+  for (int i = 0; i < 40; i++) g[i] = 0.0f;
+  g[CR_FAST] = fast ? 1.0f : 0.0f;
+  if (fast) {
+    g[CR_MODE] = t2.x;
+    float hx = 0.5f * (lr[2] - lr[0]), hy = 0.5f * (lr[3] - lr[1]);
+    float radius = t1.x;
+    for (int k = 0; k < 4; k++) {
+      q.interp[k][0] -= (hx + lr[0]) * q.interp[k][3];
+      q.interp[k][1] -= (hy + lr[1]) * q.interp[k][3];
+    }
+    g[CR_PARAMS] = hx - radius; g[CR_PARAMS + 1] = hy - radius; g[CR_PARAMS + 2] = radius;
+  } else {
+    g[CR_MODE] = t3.x;
+    if (space == 0) {
+      g[CR_BOUNDS] = lr[0]; g[CR_BOUNDS + 1] = lr[1]; g[CR_BOUNDS + 2] = lr[2]; g[CR_BOUNDS + 3] = lr[3];
+    } else {
+      g[CR_BOUNDS] = wr_max(lr[0], pi.prim_clip[0]); g[CR_BOUNDS + 1] = wr_max(lr[1], pi.prim_clip[1]);
+      g[CR_BOUNDS + 2] = wr_min(lr[2], pi.prim_clip[2]); g[CR_BOUNDS + 3] = wr_min(lr[3], pi.prim_clip[3]);
+    }
+    float r_tl[2] = {t1.x, t1.y}, r_tr[2] = {t1.z, t1.w}, r_bl[2] = {t2.x, t2.y}, r_br[2] = {t2.z, t2.w};
+    float* cr = g + CR_CORNER;
+    cr[0] = lr[0] + r_tl[0]; cr[1] = lr[1] + r_tl[1]; wr_inverse_radii_squared(r_tl, cr + 2);
+    cr[4] = lr[2] - r_tr[0]; cr[5] = lr[1] + r_tr[1]; wr_inverse_radii_squared(r_tr, cr + 6);
+    cr[8] = lr[2] - r_br[0]; cr[9] = lr[3] - r_br[1]; wr_inverse_radii_squared(r_br, cr + 10);
+    cr[12] = lr[0] + r_bl[0]; cr[13] = lr[3] - r_bl[1]; wr_inverse_radii_squared(r_bl, cr + 14);
+    float* pl = g + CR_PLANE;
+    float n_tl[2] = {-r_tl[1], -r_tl[0]}, n_tr[2] = {r_tr[1], -r_tr[0]};
+    float n_br[2] = {r_br[1], r_br[0]}, n_bl[2] = {-r_bl[1], r_bl[0]};
+    pl[0] = n_tl[0]; pl[1] = n_tl[1]; pl[2] = n_tl[0] * lr[0] + n_tl[1] * (lr[1] + r_tl[1]);
+    pl[3] = n_tr[0]; pl[4] = n_tr[1]; pl[5] = n_tr[0] * (lr[2] - r_tr[0]) + n_tr[1] * lr[1];
+    pl[6] = n_br[0]; pl[7] = n_br[1]; pl[8] = n_br[0] * lr[2] + n_br[1] * (lr[3] - r_br[1]);
+    pl[9] = n_bl[0]; pl[10] = n_bl[1]; pl[11] = n_bl[0] * (lr[0] + r_bl[0]) + n_bl[1] * lr[3];
+  }
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    for (int i = 0; i < 40; i++) k->g[i] = g[i];
+  }
+  if (unsupported) {
+    atomicAdd(&a.info->unsupported, 1);
+    atomicAdd(a.err_counter, 1);
+  }
+}
+WR_SETUP_KERNEL(wr_setup_quad_mask)

@@ -64,7 +64,7 @@ struct ClipRectShader {
     float sp[3], ep[3], sc[4], ec[4];  // start/end plane and corner
   };
 
-  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, bool rgba, Row& r) {
+  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
     r.g = k.g;
     // interpolants at the span start (exact running sums of the edge walk)

@@ -7,6 +7,7 @@
 
 #include "raster.cuh"
 #include "shader_clip_rect.cuh"
+#include "shader_quad_mask.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -526,6 +527,11 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       WR_LAUNCH(wr_setup_brush_solid, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_QUAD_MASK:
+      if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "MaskInstance stride < 32");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_quad_mask, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_CLIP_RECTANGLE:
       if (stride < 200) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceRect stride < 200");
       sa.features = features;
@@ -571,6 +577,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   } while (0)
   switch (kind) {
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
+    case WRCU_KIND_QUAD_MASK: LAUNCH_RASTER(QuadMaskShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

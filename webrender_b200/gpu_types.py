@@ -178,3 +178,10 @@ def clip_rect_instance(sub_rect, task_origin, screen_origin, device_pixel_scale,
         buf[18 + 8 * i: 22 + 8 * i] = rect
         buf[22 + 8 * i: 26 + 8 * i] = (r[0], r[1], 0.0, 0.0)
     return buf.view(np.uint8).copy()
+
+
+def mask_instance(prim_instance, clip_transform_id, clip_address, clip_space=0):
+    """MaskInstance, 32 bytes (gpu_types.rs:614-624; vertex.rs:632-650): the quad
+    instance followed by aClipData = [clip_transform_id, clip_address, clip_space, 0]."""
+    return np.concatenate([np.asarray(prim_instance, dtype=np.int32),
+                           np.array([clip_transform_id, clip_address, clip_space, 0], dtype=np.int32)])

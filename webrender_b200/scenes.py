@@ -183,3 +183,69 @@ def scale_matrix(s):
     m = np.eye(4, dtype=np.float32)
     m[0, 0] = m[1, 1] = s
     return m
+
+
+def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=False, device_pixel_scale=1.0,
+                        filter=abi.LINEAR):
+    """Config A flavour (wrench/reftests/aa/rounded-rects.yaml): solid rects with
+    rounded-rect clips drawn the Indirect way (quad.rs:722-792, 239-264):
+      pass 0, off-screen colour target: each rect as an untextured Quad with
+        blending off (handle_prims, mod.rs:2199), then its clip multiplied in with
+        ps_quad_mask (FAST_PATH for a uniform radius) (handle_clips, mod.rs:2278);
+      pass 1, picture-cache tile: one textured Quad per rect sampling the
+        off-screen task, premultiplied-alpha blended."""
+    from .gpu_types import mask_instance, QF_IS_MASK
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    sw, sh = 512, 512
+    tile_task = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
+    prims, masks_fast, masks_slow, composites = [], [], [], []
+    cursor_x, cursor_y, row_h = 0, 0, 0
+    s = device_pixel_scale
+    for i in range(n_rects):
+        w, h = int(rng.randint(40, 220)), int(rng.randint(30, 160))
+        if cursor_x + w > sw:
+            cursor_x, cursor_y, row_h = 0, cursor_y + row_h, 0
+        tx, ty = cursor_x, cursor_y
+        cursor_x += w
+        row_h = max(row_h, h)
+        # device-space rect of the primitive, local = device / scale
+        dx, dy = int(rng.randint(0, width - w)), int(rng.randint(0, height - h))
+        fo = rng.uniform(0, 1, 2) if fractional else (0.0, 0.0)
+        rect = ((dx + fo[0]) / s, (dy + fo[1]) / s, (dx + w - fo[1]) / s, (dy + h - fo[0]) / s)
+        task = t.add_render_task((float(tx), float(ty), float(tx + w), float(ty + h)), s, (float(dx), float(dy)))
+        a = rng.uniform(0.3, 1.0)
+        color = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (float(a),)
+        prim_f = t.add_quad_prim(rect, rect, color)
+        prim_i = t.add_quad_header(0, i + 1)
+        qi = quad_instance(prim_i, prim_f, QF_APPLY_DEVICE_CLIP, 0, PART_ALL, INVALID_SEGMENT_INDEX, task)
+        prims.append(qi)
+        rw, rh = rect[2] - rect[0], rect[3] - rect[1]
+        uniform = i % 2 == 0
+        mode = float(i % 5 == 4)
+        if uniform:
+            r = float(rng.uniform(2, min(rw, rh) / 2)) if fractional else float(rng.randint(2, max(3, int(min(rw, rh) / 2))))
+            clip_addr = t.push_gpu_buffer_f([rect, (r, r, r, r), (mode, 0, 0, 0)])
+        else:
+            rad = [float(rng.uniform(1, rw / 2)) if k % 2 == 0 else float(rng.uniform(1, rh / 2)) for k in range(8)]
+            clip_addr = t.push_gpu_buffer_f([rect, rad[0:4], rad[4:8], (mode, 0, 0, 0)])
+        mprim_f = t.add_quad_prim(rect, rect, (1.0, 1.0, 1.0, 1.0))
+        mqi = quad_instance(prim_i, mprim_f, QF_APPLY_DEVICE_CLIP | QF_IS_MASK, 0, PART_ALL, INVALID_SEGMENT_INDEX, task)
+        (masks_fast if uniform else masks_slow).append(mask_instance(mqi, 0, clip_addr, 0))
+        # composite: textured quad, uv rect = the task rect in the off-screen surface
+        cprim_f = t.add_quad_prim(rect, rect, (1.0, 1.0, 1.0, 1.0),
+                                  uv_rect=(float(tx), float(ty), float(tx + w), float(ty + h)))
+        cprim_i = t.add_quad_header(0, 100 + i)
+        composites.append(quad_instance(cprim_i, cprim_f, QF_APPLY_DEVICE_CLIP, 0, PART_ALL, INVALID_SEGMENT_INDEX,
+                                        tile_task))
+    textures = {"surface": TextureDesc(abi.FMT_RGBA8, sw, sh, filter=filter),
+                "target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    p0 = [Clear(color=(0.0, 0.0, 0.0, 0.0)), Batch(abi.KIND_QUAD_TEXTURED, np.stack(prims), blend=abi.BLEND_NONE)]
+    if masks_fast:
+        p0.append(Batch(abi.KIND_QUAD_MASK, np.stack(masks_fast), blend=abi.BLEND_MULTIPLY, features=abi.FEAT_FAST_PATH))
+    if masks_slow:
+        p0.append(Batch(abi.KIND_QUAD_MASK, np.stack(masks_slow), blend=abi.BLEND_MULTIPLY))
+    p1 = [Clear(color=(1.0, 1.0, 1.0, 1.0)),
+          Batch(abi.KIND_QUAD_TEXTURED, np.stack(composites), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                color=("surface", "", ""))]
+    return Frame(t.arrays(), textures, [[Target("surface", ops=p0)], [Target("target", ops=p1)]])
