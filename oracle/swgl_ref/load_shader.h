@@ -8,6 +8,7 @@
 #include "brush_solid.h"
 #include "cs_clip_rectangle.h"
 #include "ps_quad_mask.h"
+#include "brush_image.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -17,5 +18,9 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "cs_clip_rectangle FAST_PATH")) return cs_clip_rectangle_FAST_PATH_program::loader;
   if (!strcmp(name, "ps_quad_mask")) return ps_quad_mask_program::loader;
   if (!strcmp(name, "ps_quad_mask FAST_PATH")) return ps_quad_mask_FAST_PATH_program::loader;
+  if (!strcmp(name, "brush_image TEXTURE_2D")) return brush_image_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "brush_image ALPHA_PASS,TEXTURE_2D")) return brush_image_ALPHA_PASS_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "brush_image ADVANCED_BLEND,ALPHA_PASS,TEXTURE_2D"))
+    return brush_image_ADVANCED_BLEND_ALPHA_PASS_TEXTURE_2D_program::loader;
   return nullptr;
 }

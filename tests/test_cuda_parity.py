@@ -111,3 +111,31 @@ def test_rounded_rects_indirect(seed, variant):
                                    device_pixel_scale=1.5 if variant == "scaled" else 1.0,
                                    filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
     assert_same(render(CudaDevice, f), render(OracleDevice, f), variant)
+
+
+IMAGE_VARIANTS = ["linear", "nearest", "linear_1to1", "nearest_1to1", "linear_fractional"]
+
+
+def _image_frame(seed, variant, n_opaque):
+    return scenes.image_frame(seed=seed, n_opaque=n_opaque, filter=abi.NEAREST if "nearest" in variant else abi.LINEAR,
+                              one_to_one="1to1" in variant, fractional="fractional" in variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", IMAGE_VARIANTS)
+def test_brush_image_unoccluded_exact(seed, variant):
+    f = _image_frame(seed, variant, 0)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", IMAGE_VARIANTS)
+def test_brush_image_occluded(seed, variant):
+    """Opaque occluders split spans into depth runs; see DESIGN.md §4.4."""
+    f = _image_frame(seed, variant, 8)
+    a = render(CudaDevice, f, ["target"])["target"]
+    b = render(OracleDevice, f, ["target"])["target"]
+    if "1to1" in variant:
+        assert (a == b).all()
+    else:
+        assert max_abs_diff(a, b) <= 2 and (a != b).mean() < 1e-3

@@ -61,3 +61,11 @@ def test_rounded_rects_indirect(seed, variant):
                                    device_pixel_scale=1.5 if variant == "scaled" else 1.0,
                                    filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
     assert_same(render(SwglDevice, f), render(OracleDevice, f), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["linear", "nearest", "linear_1to1", "nearest_1to1", "linear_fractional"])
+def test_brush_image(seed, variant):
+    f = scenes.image_frame(seed=seed, filter=abi.NEAREST if "nearest" in variant else abi.LINEAR,
+                           one_to_one="1to1" in variant, fractional="fractional" in variant)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -13,6 +13,10 @@
 #include <stdint.h>
 #include "wrcu_internal.h"
 
+// internal blend keys set per command by blend overrides (not part of the ABI)
+#define WRCU_BLEND__DROP_SHADOW 100
+#define WRCU_BLEND__SUBPIXEL_TEXT 101
+
 struct Px {  // 16-bit lanes held in ints, memory order B,G,R,A
   int b, g, r, a;
 };
@@ -286,6 +290,15 @@ WRD Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
       o.g = wr_round_pixel(out[1], 1.0f) & 0xFFFF;
       o.b = wr_round_pixel(out[2], 1.0f) & 0xFFFF;
       o.a = wr_round_pixel(out[3], 1.0f) & 0xFFFF;
+      return o;
+    }
+    case WRCU_BLEND__DROP_SHADOW: {  // SWGL_BLEND_DROP_SHADOW, blend.h:680-686
+      Px color{wr_muldiv255(kc.b, src.a), wr_muldiv255(kc.g, src.a), wr_muldiv255(kc.r, src.a), wr_muldiv255(kc.a, src.a)};
+      int ca = color.a;
+      o.b = (color.b + dst.b - wr_muldiv255(dst.b, ca)) & 0xFFFF;
+      o.g = (color.g + dst.g - wr_muldiv255(dst.g, ca)) & 0xFFFF;
+      o.r = (color.r + dst.r - wr_muldiv255(dst.r, ca)) & 0xFFFF;
+      o.a = (color.a + dst.a - wr_muldiv255(dst.a, ca)) & 0xFFFF;
       return o;
     }
     default:

@@ -18,6 +18,7 @@
 #include "blend.cuh"
 #include "cmd.cuh"
 #include "sample.cuh"
+#include "texspan.cuh"
 #include "wrcu_internal.h"
 
 struct RasterArgs {
@@ -138,129 +139,64 @@ WRD void wr_chunk_lane(const float (*base)[N], const float* step, int kb, int k,
 }
 
 // ---- fragment stage: ps_quad_textured -------------------------------------------
-// Source colour (16-bit lanes) of pixel (x,y) for a quad command.  `body` tells
-// whether the pixel belongs to the part of the span the reference draws with
-// swgl_drawSpanRGBA8 (first len&~3 pixels) or to the tail that runs the
-// fragment shader (ps_quad_textured.glsl:39-64).
-WRD Px wr_quad_source(const RasterArgs& a, const CmdHot& c, const float* ro, const float* rstep, int x, int y,
-                  bool rgba_target) {
-  Px col{c.col[0], c.col[1], c.col[2], c.col[3]};
-  const int len = c.x1 - c.x0;
-  if (!(c.flags & CMD_TEXTURED)) {
-    // swgl_drawSpanRGBA8 commits v_color for the span body even for mask quads;
-    // only the fragment-shader tail applies .rrrr (ps_quad_textured.glsl:52-64,
-    // ps_quad.glsl:411-413).  R8 targets have no span shader: always fragment.
-    if (c.flags & CMD_OUT_RRRR) {
-      int body_len0 = (rgba_target && len >= 4) ? (len & ~3) : 0;
-      if ((x - c.x0) >= body_len0) col.b = col.g = col.a = col.r;
-    }
-    return col;
-  }
-  const CmdCold& k = a.cold[c.cold];
-  const TexView& t = a.color0;
-  int body_len = (rgba_target && len >= 4 && !(c.flags & CMD_OUT_RRRR) &&
-                  t.fmt == WRCU_FMT_RGBA8) ? (len & ~3) : 0;
-  bool body = (x - c.x0) < body_len;
-  float uv[2];
-  wr_interp_at<2>(ro, rstep, x - c.x0, uv);
-  bool linear = t.filter == WRCU_LINEAR;
-  Px s;
-  if (body) {
-    // swgl_commitTextureLinearColorRGBA8 (swgl_ext.h:589-612)
-    // needsTextureLinear uses lanes 0,1 of the span start chunk
-    float uv0[2], uv1[2];
-    wr_interp_at<2>(ro, rstep, 0, uv0);
-    wr_interp_at<2>(ro, rstep, 1, uv1);
-    // The span path does not consult the sampler's filter mode, only
-    // needsTextureLinear (swgl_ext.h:554-612).
-    int filter = 0;  // LINEAR_FILTER_NEAREST
-    if (t.w >= 2) {
-      if (uv0[1] != uv1[1]) {
-        filter = 1;
-      } else {
-        float px0 = __fmul_rn(uv0[0], (float)t.w), px1 = __fmul_rn(uv1[0], (float)t.w);
-        float py0 = __fmul_rn(uv0[1], (float)t.h);
-        int sp = (body_len & ~127) + 128;
-        int scaled = (int)roundf(__fmul_rn(__fsub_rn(px1, px0), (float)sp));
-        if (scaled != sp) filter = 1;
-        else if ((((int)__fadd_rn(__fmul_rn(px0, 4.0f), 0.5f)) & 3) != 2 ||
-                 (((int)__fadd_rn(__fmul_rn(py0, 4.0f), 0.5f)) & 3) != 2) filter = 3;
-      }
-    }
-    if (filter != 0) {
-      // quantised uv accumulator: qu_j + k*ustep (LINEAR_QUANTIZE_UV, swgl_ext.h:160-169)
-      int rel = x - c.x0, j = rel & 3;
-      float kf = (float)(rel >> 2);
-      float uvj[2];
-      wr_interp_at<2>(ro, rstep, j, uvj);
-      float qu0 = wr_linear_quantize(uv0[0], t.w), qu1 = wr_linear_quantize(uv1[0], t.w);
-      float qv0 = wr_linear_quantize(uv0[1], t.h), qv1 = wr_linear_quantize(uv1[1], t.h);
-      float ustep = __fmul_rn(4.0f, __fsub_rn(qu1, qu0));
-      float vstep = __fmul_rn(4.0f, __fsub_rn(qv1, qv0));
-      float qu = __fadd_rn(wr_linear_quantize(uvj[0], t.w), __fmul_rn(ustep, kf));
-      float qv = __fadd_rn(wr_linear_quantize(uvj[1], t.h), __fmul_rn(vstep, kf));
-      float minu = wr_max(wr_linear_quantize(k.f[0], t.w), 0.0f);
-      float minv = wr_max(wr_linear_quantize(k.f[1], t.h), 0.0f);
-      float maxu = wr_max(wr_linear_quantize(k.f[2], t.w), minu);
-      float maxv = wr_max(wr_linear_quantize(k.f[3], t.h), minv);
-      s = wr_texture_linear_rgba8(t, (int)wr_clamp(qu, minu, maxu), (int)wr_clamp(qv, minv, maxv));
-    } else {
-      // blendTextureNearestFast (swgl_ext.h:476-541)
-      int ix = (int)__fmul_rn(uv0[0], (float)t.w), iy = (int)__fmul_rn(uv0[1], (float)t.h);
-      int minUx = (int)__fmul_rn(k.f[0], (float)t.w), minUy = (int)__fmul_rn(k.f[1], (float)t.h);
-      int maxUx = (int)__fmul_rn(k.f[2], (float)t.w), maxUy = (int)__fmul_rn(k.f[3], (float)t.h);
-      int ry = wr_clamp_coord(min(max(iy, minUy), maxUy), t.h);
-      int minX = min(max(minUx, 0), t.w - 1);
-      int maxX = min(max(maxUx, minX), t.w - 1);
-      int sx = min(max(ix + (x - c.x0), minX), maxX);
-      s = px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)ry * t.pitch) + sx));
-    }
-    return px_apply_color(s, col);
-  }
-  // fragment path: fs_sample_color0 + texture() (sample_color0.glsl:25-31,
-  // texture.h:948-975), float multiply by v_color, then round_pixel.
-  float cu = wr_clamp(uv[0], k.f[0], k.f[2]);
-  float cv = wr_clamp(uv[1], k.f[1], k.f[3]);
-  float tex[4];
-  if (linear) {
-    Px p = wr_texture_linear_rgba8(t, (int)wr_linear_quantize(cu, t.w), (int)wr_linear_quantize(cv, t.h));
-    tex[0] = __fmul_rn((float)p.r, 1.0f / 255.0f);
-    tex[1] = __fmul_rn((float)p.g, 1.0f / 255.0f);
-    tex[2] = __fmul_rn((float)p.b, 1.0f / 255.0f);
-    tex[3] = __fmul_rn((float)p.a, 1.0f / 255.0f);
-  } else {
-    int tx = wr_clamp_coord((int)__fmul_rn(cu, (float)t.w), t.w);
-    int ty = wr_clamp_coord((int)__fmul_rn(cv, (float)t.h), t.h);
-    uint32_t p = __ldg((const uint32_t*)(t.ptr + (size_t)ty * t.pitch) + tx);
-    tex[0] = __fmul_rn((float)((p >> 16) & 0xFF), 1.0f / 255.0f);
-    tex[1] = __fmul_rn((float)((p >> 8) & 0xFF), 1.0f / 255.0f);
-    tex[2] = __fmul_rn((float)(p & 0xFF), 1.0f / 255.0f);
-    tex[3] = __fmul_rn((float)(p >> 24), 1.0f / 255.0f);
-  }
-  // textured quads force v_color = 1 (ps_quad_textured.glsl:27)
-  Px o;
-  if (c.flags & CMD_OUT_RRRR) {
-    int r = wr_round_pixel(tex[0], 255.0f) & 0xFFFF;
-    o = Px{r, r, r, r};
-  } else {
-    o.r = wr_round_pixel(tex[0], 255.0f) & 0xFFFF;
-    o.g = wr_round_pixel(tex[1], 255.0f) & 0xFFFF;
-    o.b = wr_round_pixel(tex[2], 255.0f) & 0xFFFF;
-    o.a = wr_round_pixel(tex[3], 255.0f) & 0xFFFF;
-  }
-  return o;
-}
-
-// Shader policy for quad / solid-brush commands.
+// (webrender/res/ps_quad_textured.glsl:39-64, ps_quad.glsl:406-417).  The first
+// len&~3 pixels of a span are drawn by swgl_drawSpanRGBA8 (solid commit or
+// swgl_commitTextureLinearColorRGBA8), the rest by the fragment shader.
 struct QuadShader {
   struct Row {
     float o[2], step[2];
+    TexRow tr;
   };
-  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int, bool, Row& r) {
-    if (c.flags & CMD_TEXTURED) wr_row_interp<2>(a.cold[c.cold], c, y, r.o, r.step);
+  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool rgba, Row& r) {
+    r.tr.mode = TEX_NONE;
+    r.tr.body_len = 0;
+    if (!(c.flags & CMD_TEXTURED)) return;
+    const CmdCold& k = a.cold[c.cold];
+    wr_row_interp<2>(k, c, y, r.o, r.step);
+    int len = c.x1 - c.x0;
+    int body_len = (rgba && len >= 4 && !(c.flags & CMD_OUT_RRRR)) ? (len & ~3) : 0;
+    float u[4], v[4];
+    for (int j = 0; j < 4; j++) {
+      float uv[2];
+      wr_interp_at<2>(r.o, r.step, j, uv);
+      u[j] = uv[0];
+      v[j] = uv[1];
+    }
+    wr_tex_row_setup(a.color0, k.f, false, body_len, u, v, max(tx0, (int)c.x0) - (int)c.x0, r.tr);
   }
-  WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int y, bool rgba) {
-    return wr_quad_source(a, c, r.o, r.step, x, y, rgba);
+  WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool rgba) {
+    Px col{c.col[0], c.col[1], c.col[2], c.col[3]};
+    const int len = c.x1 - c.x0;
+    int rel = x - c.x0;
+    if (!(c.flags & CMD_TEXTURED)) {
+      // swgl_drawSpanRGBA8 commits v_color for the span body even for mask quads;
+      // only the fragment-shader tail applies .rrrr.  R8 targets have no span
+      // shader: always the fragment path.
+      if (c.flags & CMD_OUT_RRRR) {
+        int body_len0 = (rgba && len >= 4) ? (len & ~3) : 0;
+        if (rel >= body_len0) col.b = col.g = col.a = col.r;
+      }
+      return col;
+    }
+    const TexView& t = a.color0;
+    if (rel < r.tr.body_len) return px_apply_color(wr_tex_body(t, r.tr, rel), col);
+    // fragment path: fs_sample_color0 (sample_color0.glsl:25-31), v_color == 1
+    const CmdCold& k = a.cold[c.cold];
+    float uv[2];
+    wr_interp_at<2>(r.o, r.step, rel, uv);
+    float tex[4];
+    wr_tex_fragment(t, wr_clamp(uv[0], k.f[0], k.f[2]), wr_clamp(uv[1], k.f[1], k.f[3]), tex);
+    Px o;
+    if (c.flags & CMD_OUT_RRRR) {
+      int rr = wr_round_pixel(tex[0], 255.0f) & 0xFFFF;
+      o = Px{rr, rr, rr, rr};
+    } else {
+      o.r = wr_round_pixel(tex[0], 255.0f) & 0xFFFF;
+      o.g = wr_round_pixel(tex[1], 255.0f) & 0xFFFF;
+      o.b = wr_round_pixel(tex[2], 255.0f) & 0xFFFF;
+      o.a = wr_round_pixel(tex[3], 255.0f) & 0xFFFF;
+    }
+    return o;
   }
 };
 
@@ -299,7 +235,16 @@ WRD void wr_shade_pixel(const RasterArgs& a, const CmdHot& c, const typename S::
         else src.r = wr_muldiv255(src.r, mk);
       }
     }
-    if (FMT == WRCU_FMT_RGBA8) px = px_pack(wr_blend_rgba8(a.blend, src, px_unpack(px), a.blend_color));
+    if (FMT == WRCU_FMT_RGBA8) {
+      int key = a.blend;
+      Px kc = a.blend_color;
+      if (c.flags & CMD_DROP_SHADOW) {  // SWGL_CLIP_FLAG_BLEND_OVERRIDE (rasterize.h:410-413)
+        const CmdCold& k = a.cold[c.cold];
+        key = WRCU_BLEND__DROP_SHADOW;
+        kc = Px{k.i[0] & 0xFFFF, (k.i[0] >> 16) & 0xFFFF, k.i[1] & 0xFFFF, (k.i[1] >> 16) & 0xFFFF};
+      }
+      px = px_pack(wr_blend_rgba8(key, src, px_unpack(px), kc));
+    }
     else px = wr_pack16(wr_blend_r8(a.blend, src.r, (int)px));
   } else {
     if (FMT == WRCU_FMT_RGBA8) px = px_pack(src);

@@ -149,3 +149,108 @@ WRD void wr_setup_brush_solid_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_brush_solid)
+
+// brush_image (brush_image.glsl:57-283, without WR_FEATURE_REPETITION)
+WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  bool alpha_pass = (a.features & WRCU_FEAT_ALPHA_PASS) != 0;
+  QuadOut q;
+  BrushVS vs;
+  memset(&q, 0, sizeof q);
+  wr_brush_vertex(a, aData, 3, q, vs);
+  const FrameTablesDev& T = a.tabs;
+  float4 d0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.ph.specific_prim_address);
+  float4 d2 = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.ph.specific_prim_address + 2);
+  float image_color[4] = {d0.x, d0.y, d0.z, d0.w};
+  float stretch[2] = {d2.x, d2.y};
+  float tw = (float)a.color0.w, th = (float)a.color0.h;
+  float4 r0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.resource_address);
+  float uv0[2] = {r0.x, r0.y}, uv1[2] = {r0.z, r0.w};
+  float lr[4] = {vs.ph.lr[0], vs.ph.lr[1], vs.ph.lr[2], vs.ph.lr[3]};
+  if (stretch[0] < 0.0f) { stretch[0] = lr[2] - lr[0]; stretch[1] = lr[3] - lr[1]; }
+  if (vs.brush_flags & 2) {  // SEGMENT_RELATIVE
+    for (int i = 0; i < 4; i++) lr[i] = vs.segment_rect[i];
+    stretch[0] = lr[2] - lr[0]; stretch[1] = lr[3] - lr[1];
+    if (vs.brush_flags & 512) {  // TEXEL_RECT
+      float usx = r0.z - r0.x, usy = r0.w - r0.y;
+      uv0[0] = r0.x + vs.segment_data.x * usx; uv0[1] = r0.y + vs.segment_data.y * usy;
+      uv1[0] = r0.x + vs.segment_data.z * usx; uv1[1] = r0.y + vs.segment_data.w * usy;
+    }
+  }
+  float perspective = (vs.brush_flags & 1) ? 1.0f : 0.0f;
+  if (vs.brush_flags & 2048) { uv0[0] *= tw; uv0[1] *= th; uv1[0] *= tw; uv1[1] *= th; }
+  float minu[2] = {wr_min(uv0[0], uv1[0]), wr_min(uv0[1], uv1[1])};
+  float maxu[2] = {wr_max(uv0[0], uv1[0]), wr_max(uv0[1], uv1[1])};
+  float fcold[8], gcold[8];
+  fcold[0] = (minu[0] + 0.5f) / tw; fcold[1] = (minu[1] + 0.5f) / th;
+  fcold[2] = (maxu[0] - 0.5f) / tw; fcold[3] = (maxu[1] - 0.5f) / th;
+  int color_mode = vs.ph.user_data[0] & 0xffff, blend_mode = vs.ph.user_data[0] >> 16;
+  int raster_space = vs.ph.user_data[1];
+  float repeat[2] = {(lr[2] - lr[0]) / stretch[0], (lr[3] - lr[1]) / stretch[1]};
+  for (int k = 0; k < 4; k++) {
+    float fx = (vs.local_pos[k].x - lr[0]) / (lr[2] - lr[0]);
+    float fy = (vs.local_pos[k].y - lr[1]) / (lr[3] - lr[1]);
+    if (raster_space == 1) {  // get_image_quad_uv
+      float4 tl = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.resource_address + 2);
+      float4 tr = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.resource_address + 3);
+      float4 bl = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.resource_address + 4);
+      float4 br = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.resource_address + 5);
+      float Xx = (tr.x - tl.x) * fx + tl.x, Xy = (tr.y - tl.y) * fx + tl.y, Xw = (tr.w - tl.w) * fx + tl.w;
+      float Yx = (br.x - bl.x) * fx + bl.x, Yy = (br.y - bl.y) * fx + bl.y, Yw = (br.w - bl.w) * fx + bl.w;
+      float Zx = (Yx - Xx) * fy + Xx, Zy = (Yy - Xy) * fy + Xy, Zw = (Yw - Xw) * fy + Xw;
+      fx = Zx / Zw;
+      fy = Zy / Zw;
+    }
+    float ux = ((uv1[0] - uv0[0]) * fx + uv0[0]) - minu[0];
+    float uy = ((uv1[1] - uv0[1]) * fy + uv0[1]) - minu[1];
+    ux *= repeat[0]; uy *= repeat[1];
+    ux /= tw; uy /= th;
+    if (perspective == 0.0f) { ux *= vs.world_pos[k].w; uy *= vs.world_pos[k].w; }
+    q.interp[k][0] = ux;
+    q.interp[k][1] = uy;
+  }
+  q.n_interp = 2;
+  fcold[4] = minu[0] / tw; fcold[5] = minu[1] / th;
+  fcold[6] = perspective;
+  float fw = 1.0f / q.pos[0].w;
+  if (!isfinite(fw)) fw = 0.0f;
+  fcold[7] = fw;
+  float vcolor[4] = {1.0f, 1.0f, 1.0f, 1.0f}, swz[2] = {1.0f, 0.0f};
+  bool drop_shadow = false;
+  uint16_t shadow[4] = {0, 0, 0, 0};
+  if (alpha_pass) {
+    float opacity = (float)vs.ph.user_data[2] / 65535.0f;
+    if (blend_mode == 0) image_color[3] *= opacity;
+    else for (int i = 0; i < 4; i++) image_color[i] *= opacity;
+    switch (color_mode) {
+      case 0: case 2:
+        drop_shadow = a.blend_enabled != 0;  // swgl_blendDropShadow needs blending on
+        shadow[0] = (uint16_t)wr_round_pixel(image_color[2], 255.0f); shadow[1] = (uint16_t)wr_round_pixel(image_color[1], 255.0f);
+        shadow[2] = (uint16_t)wr_round_pixel(image_color[0], 255.0f); shadow[3] = (uint16_t)wr_round_pixel(image_color[3], 255.0f);
+        break;
+      case 4: for (int i = 0; i < 4; i++) vcolor[i] = image_color[i]; break;
+      case 3: for (int i = 0; i < 4; i++) vcolor[i] = image_color[3]; break;
+      case 1: swz[0] = image_color[3]; swz[1] = 0.0f; for (int i = 0; i < 4; i++) vcolor[i] = image_color[i]; break;
+      case 5: swz[0] = -image_color[3]; swz[1] = image_color[3]; for (int i = 0; i < 4; i++) vcolor[i] = image_color[i]; break;
+      default: swz[0] = swz[1] = 0.0f; break;
+    }
+  }
+  for (int i = 0; i < 4; i++) gcold[i] = vcolor[i];
+  gcold[4] = swz[0]; gcold[5] = swz[1];
+  gcold[6] = alpha_pass ? 1.0f : 0.0f;
+  // swgl_drawSpanRGBA8 bails for non-(1,0) swizzles in the alpha pass
+  gcold[7] = (!alpha_pass || (swz[0] == 1.0f && swz[1] == 0.0f)) ? 1.0f : 0.0f;
+  wr_pack_color(q, vcolor);
+  q.flags |= CMD_TEXTURED;
+  if (drop_shadow) q.flags |= CMD_DROP_SHADOW;
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    for (int i = 0; i < 8; i++) { k->f[i] = fcold[i]; k->g[i] = gcold[i]; }
+    k->i[0] = (int)shadow[0] | ((int)shadow[1] << 16);
+    k->i[1] = (int)shadow[2] | ((int)shadow[3] << 16);
+  }
+  wr_finish_setup(a, unsupported);
+}
+WR_SETUP_KERNEL(wr_setup_brush_image)

@@ -1,0 +1,251 @@
+// texspan.cuh — textured span sampling shared by the quad, image-brush and
+// composite shaders: the reference's swgl_commitTexture* family
+// (swgl/src/swgl_ext.h:385-612, 775-947) restated per pixel.
+//
+// SWGL draws the first len&~3 pixels of a span with a span shader that picks a
+// filter from the uv step (needsTextureLinear / needsNearestFallback) and then
+// runs blendTextureLinearDispatch: a clamped prefix through the fallback
+// bilinear filter, an interior run through a specialised filter (FAST: 1 texel
+// per pixel with constant fractions; DOWNSCALE: 2 texels per pixel; UPSCALE),
+// and the remainder through the fallback again.  TexRow holds that partition,
+// computed once per (command,row) per warp; wr_tex_body evaluates one pixel.
+// The remaining len&3 pixels run the fragment shader (texture(): wr_tex_fragment).
+//
+// Exactness: inside FALLBACK / UPSCALE / nearest-fallback runs the reference
+// accumulates the (quantised) uv chunk by chunk.  wr_tex_row_setup walks that
+// running sum up to the first chunk the tile touches (warp-uniform, once per
+// command/row/tile) and wr_tex_body finishes it per pixel (<= 32 additions in
+// a 128-pixel tile), so every run is reproduced bit for bit.
+#pragma once
+#include "blend.cuh"
+#include "sample.cuh"
+
+enum { TEX_NONE = 0, TEX_LINEAR = 1, TEX_NEAREST_FAST = 2, TEX_NEAREST_FALLBACK = 3 };
+enum { LF_NEAREST = 0, LF_FALLBACK = 1, LF_UPSCALE = 2, LF_FAST = 3, LF_DOWNSCALE = 4 };
+
+struct TexRow {
+  int mode, body_len;
+  float u[4], v[4];  // uv lanes of chunk 0 of the span body
+  // linear
+  int filter, before, inside;
+  float qu[4], qv[4], ustep, vstep, minu, minv, maxu, maxv;
+  int fcx, fcy, fnext, ffx, ffy;  // FAST/DOWNSCALE: clamped start texel, next-row flag, fractions
+  int uiy0;                       // UPSCALE: lane 0's clamped quantised y
+  // nearest
+  int nix, nry, nminx, nmaxx;     // fast
+  int nsolid;                     // fallback: single-texel span
+  // running-sum bases: x lanes of the first chunk >= the tile start inside each
+  // of the three dispatch segments (prefix fallback / interior / remainder)
+  int kb[3];
+  float bu[3][4], bv[4];
+};
+
+// needsTextureLinear (swgl_ext.h:554-587); u0,u1,v0,v1 = lanes 0,1
+WRD int wr_needs_texture_linear(const TexView& t, float u0, float u1, float v0, float v1, int span) {
+  if (t.w < 2) return LF_NEAREST;
+  if (v0 != v1) return LF_FALLBACK;
+  float px0 = u0 * (float)t.w, px1 = u1 * (float)t.w, py0 = v0 * (float)t.h;
+  int sp = (span & ~127) + 128;
+  int scaled = (int)roundf((px1 - px0) * (float)sp);
+  int scale = scaled != sp ? (scaled == sp * 2 ? 2 : 1) : 0;
+  if (scale) return (px0 < px1 && px1 - px0 <= 1) ? LF_UPSCALE : (scale == 2 ? LF_DOWNSCALE : LF_FALLBACK);
+  if ((((int)(px0 * 4.0f + 0.5f)) & 3) != 2 || (((int)(py0 * 4.0f + 0.5f)) & 3) != 2) return LF_FAST;
+  return LF_NEAREST;
+}
+
+// Set up the span-body partition.  `use_sampler_filter`: swgl_commitTexture
+// (image brush, composite) picks linear vs nearest from the sampler's filter;
+// swgl_commitTextureLinear (quads) always takes the linear decision tree.
+WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
+  for (int j = 0; j < 4; j++) {
+    float v = start[j];
+    for (int s = 0; s < kb; s++) v = v + step;
+    out[j] = v;
+  }
+}
+
+WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sampler_filter, int body_len,
+                          const float* u, const float* v, int tile_rel, TexRow& r) {
+  r.body_len = body_len;
+  r.mode = TEX_NONE;
+  if (body_len == 0 || t.fmt != WRCU_FMT_RGBA8) {
+    r.body_len = 0;
+    return;
+  }
+  for (int j = 0; j < 4; j++) { r.u[j] = u[j]; r.v[j] = v[j]; }
+  bool linear = !use_sampler_filter || t.filter == WRCU_LINEAR;
+  int filter = LF_NEAREST;
+  if (linear) {
+    filter = wr_needs_texture_linear(t, u[0], u[1], v[0], v[1], body_len);
+  } else {
+    // needsNearestFallback (swgl_ext.h:860-863)
+    float p0x = u[0] * (float)t.w, p1x = u[1] * (float)t.w, p0y = v[0] * (float)t.h, p1y = v[1] * (float)t.h;
+    int sp = (body_len & ~127) + 128;
+    int scaled = (int)roundf((p1x - p0x) * (float)sp);
+    if ((p1y - p0y) * (float)body_len >= 0.5f || scaled != sp) {
+      r.mode = TEX_NEAREST_FALLBACK;
+      float ustep = 4.0f * (p1x - p0x), vstep = 4.0f * (p1y - p0y);
+      r.ustep = ustep; r.vstep = vstep;
+      r.minu = bounds[0] * (float)t.w; r.minv = bounds[1] * (float)t.h;
+      r.maxu = bounds[2] * (float)t.w; r.maxv = bounds[3] * (float)t.h;
+      r.nsolid = ((int)r.minu >= (int)r.maxu || fabsf(ustep) * (float)body_len * 1.0f < 0.5f) &&
+                 ((int)r.minv >= (int)r.maxv || fabsf(vstep) * (float)body_len * 1.0f < 0.5f);
+      for (int j = 0; j < 4; j++) { r.qu[j] = u[j] * (float)t.w; r.qv[j] = v[j] * (float)t.h; }
+      r.kb[2] = r.nsolid ? 0 : max(0, tile_rel >> 2);
+      wr_tex_seq_base(r.qu, ustep, r.kb[2], r.bu[2]);
+      wr_tex_seq_base(r.qv, vstep, r.kb[2], r.bv);
+      return;
+    }
+  }
+  if (filter == LF_NEAREST) {
+    // blendTextureNearestFast (swgl_ext.h:476-541)
+    r.mode = TEX_NEAREST_FAST;
+    r.nix = (int)(u[0] * (float)t.w);
+    int iy = (int)(v[0] * (float)t.h);
+    int minUx = (int)(bounds[0] * (float)t.w), minUy = (int)(bounds[1] * (float)t.h);
+    int maxUx = (int)(bounds[2] * (float)t.w), maxUy = (int)(bounds[3] * (float)t.h);
+    r.nry = wr_clamp_coord(min(max(iy, minUy), maxUy), t.h);
+    r.nminx = min(max(minUx, 0), t.w - 1);
+    r.nmaxx = min(max(maxUx, r.nminx), t.w - 1);
+    return;
+  }
+  r.mode = TEX_LINEAR;
+  r.filter = filter;
+  for (int j = 0; j < 4; j++) {
+    r.qu[j] = wr_linear_quantize(u[j], t.w);
+    r.qv[j] = wr_linear_quantize(v[j], t.h);
+  }
+  r.ustep = 4.0f * (r.qu[1] - r.qu[0]);
+  r.vstep = 4.0f * (r.qv[1] - r.qv[0]);
+  r.minu = wr_max(wr_linear_quantize(bounds[0], t.w), 0.0f);
+  r.minv = wr_max(wr_linear_quantize(bounds[1], t.h), 0.0f);
+  r.maxu = wr_max(wr_linear_quantize(bounds[2], t.w), r.minu);
+  r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
+  r.before = 0;
+  r.inside = 0;
+  if (filter != LF_FALLBACK) {
+    // blendTextureLinearDispatch (swgl_ext.h:385-448)
+    float q0 = r.qu[0];
+    float beforeDist = wr_max(0.0f, r.minu) - q0;
+    if (beforeDist > 0) {
+      r.before = min(max((int)ceilf(beforeDist / r.ustep) * 4, 0), body_len);
+      q0 = q0 + (float)(r.before / 4) * r.ustep;
+    }
+    float insideDist = wr_min(r.maxu, (float)((t.w - 4) * 128)) - q0;
+    if (r.ustep > 0.0f && insideDist >= r.ustep) {
+      int inside = body_len - r.before;
+      if (filter == LF_DOWNSCALE) inside = min(((int)(insideDist * (0.5f / 128.0f))) & ~3, inside);
+      else if (filter == LF_UPSCALE) inside = min((int)(insideDist / r.ustep) * 4, inside);
+      else inside = min(((int)(insideDist * (1.0f / 128.0f))) & ~3, inside);
+      r.inside = max(inside, 0);
+    }
+    if (r.inside > 0) {
+      int ix0 = (int)wr_clamp(q0, r.minu, r.maxu), iy0 = (int)wr_clamp(r.qv[0], r.minv, r.maxv);
+      r.uiy0 = iy0;
+      int tx = ix0 >> 7, ty = iy0 >> 7;
+      r.fcx = wr_clamp_coord(tx, t.w - 1);
+      r.fcy = wr_clamp_coord(ty, t.h);
+      r.fnext = (ty >= 0 && ty < t.h - 1) ? 1 : 0;
+      int overread = tx > t.w - 2 ? -1 : 0;
+      r.ffx = (int)(short)((((ix0 & (tx >= 0 ? -1 : 0)) | overread) & 0x7F) - overread);
+      r.ffy = iy0 & 0x7F;
+    }
+  }
+  // running-sum bases per segment
+  {
+    float start[4];
+    for (int j = 0; j < 4; j++) start[j] = r.qu[j];
+    r.kb[0] = max(0, tile_rel >> 2);
+    if (r.before > 0) wr_tex_seq_base(start, r.ustep, min(r.kb[0], r.before >> 2), r.bu[0]);
+    if (r.before > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.before / 4) * r.ustep;
+    r.kb[1] = max(0, (tile_rel - r.before) >> 2);
+    if (r.inside > 0 && r.filter == LF_UPSCALE) wr_tex_seq_base(start, r.ustep, min(r.kb[1], r.inside >> 2), r.bu[1]);
+    if (r.inside > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.inside / 4) * r.ustep;
+    r.kb[2] = max(0, (tile_rel - r.before - r.inside) >> 2);
+    wr_tex_seq_base(start, r.ustep, r.kb[2], r.bu[2]);
+    wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
+    r.kb[0] = min(r.kb[0], r.before >> 2);
+    r.kb[1] = min(r.kb[1], r.inside >> 2);
+  }
+}
+
+// Source texel (before colour modulation) of body pixel `rel` (0-based in the span).
+WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
+  if (r.mode == TEX_NEAREST_FAST) {
+    int sx = min(max(r.nix + rel, r.nminx), r.nmaxx);
+    return px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)r.nry * t.pitch) + sx));
+  }
+  int j = rel & 3;
+  if (r.mode == TEX_NEAREST_FALLBACK) {
+    float su = r.bu[2][j], sv = r.bv[j];
+    if (!r.nsolid) for (int s = r.kb[2]; s < (rel >> 2); s++) { su = su + r.ustep; sv = sv + r.vstep; }
+    int ix = (int)wr_clamp(su, r.minu, r.maxu), iy = (int)wr_clamp(sv, r.minv, r.maxv);
+    int cx = wr_clamp_coord(ix, t.w), cy = wr_clamp_coord(iy, t.h);
+    return px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)cy * t.pitch) + cx));
+  }
+  // TEX_LINEAR
+  if (rel < r.before || rel >= r.before + r.inside) {
+    // fallback filter (swgl_ext.h:172-184): uv += uv_step per chunk
+    float qu, qv;
+    if (rel < r.before) {
+      qu = r.bu[0][j];
+      for (int s = r.kb[0]; s < (rel >> 2); s++) qu = qu + r.ustep;
+      qv = r.qv[j];  // prefix exists only for constant-y filters
+    } else {
+      int p = rel - r.before - r.inside;
+      qu = r.bu[2][j];
+      qv = r.bv[j];
+      for (int s = r.kb[2]; s < (p >> 2); s++) { qu = qu + r.ustep; qv = qv + r.vstep; }
+    }
+    return wr_texture_linear_rgba8(t, (int)wr_clamp(qu, r.minu, r.maxu), (int)wr_clamp(qv, r.minv, r.maxv));
+  }
+  int p = rel - r.before;
+  if (r.filter == LF_UPSCALE) {
+    float qu = r.bu[1][j];
+    for (int s = r.kb[1]; s < (p >> 2); s++) qu = qu + r.ustep;
+    int ix = (p < 4) ? (int)wr_clamp(qu, r.minu, r.maxu) : (int)qu;
+    return wr_texture_linear_rgba8(t, ix, r.uiy0);
+  }
+  // FAST / DOWNSCALE (swgl_ext.h:284-371): integer texel stepping, constant fractions
+  int mul = r.filter == LF_DOWNSCALE ? 2 : 1;
+  const uint8_t* row0 = t.ptr + (size_t)r.fcy * t.pitch + (size_t)(r.fcx + p * mul) * 4;
+  const uint8_t* row1 = row0 + (r.fnext ? t.pitch : 0);
+  uint2 a = make_uint2(__ldg((const uint32_t*)row0), __ldg((const uint32_t*)row0 + 1));
+  uint2 b = make_uint2(__ldg((const uint32_t*)row1), __ldg((const uint32_t*)row1 + 1));
+  int vv[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int a0 = (a.x >> (8 * k)) & 0xFF, a1 = (b.x >> (8 * k)) & 0xFF;
+    int b0 = (a.y >> (8 * k)) & 0xFF, b1 = (b.y >> (8 * k)) & 0xFF;
+    int l = wr_lerp7(a0, a1, r.ffy);
+    int rr = wr_lerp7(b0, b1, r.ffy);
+    vv[k] = wr_lerp7(l, rr, r.ffx) & 0xFFFF;
+  }
+  return Px{vv[0], vv[1], vv[2], vv[3]};
+}
+
+// texture(sampler2D, vec2) → float RGBA (texture.h:948-975), uv already clamped
+WRD void wr_tex_fragment(const TexView& t, float cu, float cv, float* out) {
+  if (t.fmt == WRCU_FMT_R8) {
+    int rr;
+    if (t.filter == WRCU_LINEAR) {
+      rr = wr_texture_linear_r8(t, (int)wr_linear_quantize(cu, t.w), (int)wr_linear_quantize(cv, t.h));
+    } else {
+      int x = wr_clamp_coord((int)(cu * (float)t.w), t.w), y = wr_clamp_coord((int)(cv * (float)t.h), t.h);
+      rr = __ldg(t.ptr + (size_t)y * t.pitch + x);
+    }
+    out[0] = (float)rr * (1.0f / 255.0f);
+    out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;
+    return;
+  }
+  if (t.filter == WRCU_LINEAR) {
+    Px p = wr_texture_linear_rgba8(t, (int)wr_linear_quantize(cu, t.w), (int)wr_linear_quantize(cv, t.h));
+    out[0] = (float)p.r * (1.0f / 255.0f); out[1] = (float)p.g * (1.0f / 255.0f);
+    out[2] = (float)p.b * (1.0f / 255.0f); out[3] = (float)p.a * (1.0f / 255.0f);
+  } else {
+    int x = wr_clamp_coord((int)(cu * (float)t.w), t.w), y = wr_clamp_coord((int)(cv * (float)t.h), t.h);
+    uint32_t p = __ldg((const uint32_t*)(t.ptr + (size_t)y * t.pitch) + x);
+    out[0] = (float)((p >> 16) & 0xFF) * (1.0f / 255.0f); out[1] = (float)((p >> 8) & 0xFF) * (1.0f / 255.0f);
+    out[2] = (float)(p & 0xFF) * (1.0f / 255.0f); out[3] = (float)(p >> 24) * (1.0f / 255.0f);
+  }
+}

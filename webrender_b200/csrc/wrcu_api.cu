@@ -8,6 +8,7 @@
 #include "raster.cuh"
 #include "shader_clip_rect.cuh"
 #include "shader_quad_mask.cuh"
+#include "shader_image.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -527,6 +528,14 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       WR_LAUNCH(wr_setup_brush_solid, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_BRUSH_IMAGE:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (features & (WRCU_FEAT_REPETITION | WRCU_FEAT_DUAL_SOURCE_BLENDING))
+        return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "brush_image REPETITION / DUAL_SOURCE_BLENDING variants not built yet");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_image without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_brush_image, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_QUAD_MASK:
       if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "MaskInstance stride < 32");
       sa.features = features;
@@ -578,6 +587,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   switch (kind) {
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
     case WRCU_KIND_QUAD_MASK: LAUNCH_RASTER(QuadMaskShader); break;
+    case WRCU_KIND_BRUSH_IMAGE: LAUNCH_RASTER(ImageShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

@@ -249,3 +249,72 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
           Batch(abi.KIND_QUAD_TEXTURED, np.stack(composites), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
                 color=("surface", "", ""))]
     return Frame(t.arrays(), textures, [[Target("surface", ops=p0)], [Target("target", ops=p1)]])
+
+
+def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=abi.LINEAR, one_to_one=False,
+                fractional=False):
+    """Brush(Image) batches: an opaque batch (depth write, blending off) and an
+    alpha batch (premultiplied over, depth test) sampling one RGBA8 atlas, with
+    colour modes Image / ColorBitmap / Alpha(drop-shadow override), 1:1 and
+    scaled mappings, plus segment-relative texel-rect (nine-patch style) instances."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    aw, ah = 256, 192
+    atlas = rng.randint(0, 256, size=(ah, aw, 4)).astype(np.uint8)
+    # premultiply so colours are valid
+    a = atlas[..., 3:4].astype(np.uint16)
+    atlas[..., :3] = (atlas[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)
+    z = 1
+    opaque, alpha = [], []
+
+    def add(rect, uv, color, color_mode, opacity, flags=0, segment=None, stretch=(-1.0, -1.0)):
+        nonlocal z
+        blocks = [color, (0.0, 0.0, 0.0, 0.0), (stretch[0], stretch[1], 0.0, 0.0)]
+        seg_index = 0xFFFF
+        if segment is not None:
+            blocks += [segment[0], segment[1]]
+            seg_index = 0
+        addr = t.push_gpu_cache(blocks)
+        res = t.push_gpu_cache([uv, (0.0, 0.0, 0.0, 0.0)])
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic,
+                                (color_mode | (1 << 16), 0, int(opacity * 65535), 0))
+        z += 1
+        return brush_instance(hdr, CLIP_TASK_EMPTY, seg_index, 0, flags, res)
+
+    def rand_uv(w, h):
+        if one_to_one:
+            uw, uh = int(w), int(h)
+        else:
+            uw, uh = int(rng.randint(4, 120)), int(rng.randint(4, 100))
+        uw, uh = min(uw, aw - 1), min(uh, ah - 1)
+        u0, v0 = int(rng.randint(0, aw - uw)), int(rng.randint(0, ah - uh))
+        return (float(u0), float(v0), float(u0 + uw), float(v0 + uh))
+
+    for _ in range(n_opaque):
+        r = _rand_rect(rng, width, height, 16, 200, integer=not fractional)
+        opaque.append(add(r, rand_uv(r[2] - r[0], r[3] - r[1]), (1.0, 1.0, 1.0, 1.0), 4, 1.0))
+    for i in range(n_alpha):
+        r = _rand_rect(rng, width, height, 16, 200, integer=not fractional)
+        mode = [4, 4, 3, 0, 4][i % 5]
+        col = (1.0, 1.0, 1.0, 1.0) if i % 4 == 0 else tuple(float(v) for v in rng.uniform(0.2, 1.0, 4))
+        if i % 7 == 6:
+            # segment-relative texel rect: the middle ninth of the uv rect on the middle of the prim
+            rw, rh = r[2] - r[0], r[3] - r[1]
+            seg = ((float(int(rw / 4)), float(int(rh / 4)), float(int(rw * 3 / 4)), float(int(rh * 3 / 4))),
+                   (0.25, 0.25, 0.75, 0.75))
+            alpha.append(add(r, rand_uv(rw, rh), col, mode, rng.uniform(0.4, 1.0), flags=2 | 512, segment=seg))
+        else:
+            alpha.append(add(r, rand_uv(r[2] - r[0], r[3] - r[1]), col, mode, rng.uniform(0.4, 1.0)))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "depth": TextureDesc(abi.FMT_DEPTH24, width, height),
+                "atlas": TextureDesc(abi.FMT_RGBA8, aw, ah, atlas.reshape(ah, aw * 4), filter=filter)}
+    ops = [Clear(color=(0.2, 0.3, 0.4, 1.0), depth=1.0)]
+    if opaque:
+        ops.append(Batch(abi.KIND_BRUSH_IMAGE, np.stack(opaque[::-1]), blend=abi.BLEND_NONE, depth=abi.DEPTH_TEST_WRITE,
+                         features=abi.FEAT_TEXTURE_2D, color=("atlas", "", "")))
+    if alpha:
+        ops.append(Batch(abi.KIND_BRUSH_IMAGE, np.stack(alpha), blend=abi.BLEND_PREMULTIPLIED_ALPHA, depth=abi.DEPTH_TEST,
+                         features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("atlas", "", "")))
+    return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
