@@ -9,6 +9,7 @@
 #include "cs_clip_rectangle.h"
 #include "ps_quad_mask.h"
 #include "brush_image.h"
+#include "ps_text_run.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -22,5 +23,8 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "brush_image ALPHA_PASS,TEXTURE_2D")) return brush_image_ALPHA_PASS_TEXTURE_2D_program::loader;
   if (!strcmp(name, "brush_image ADVANCED_BLEND,ALPHA_PASS,TEXTURE_2D"))
     return brush_image_ADVANCED_BLEND_ALPHA_PASS_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "ps_text_run ALPHA_PASS,TEXTURE_2D")) return ps_text_run_ALPHA_PASS_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "ps_text_run ALPHA_PASS,DUAL_SOURCE_BLENDING,TEXTURE_2D"))
+    return ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_TEXTURE_2D_program::loader;
   return nullptr;
 }

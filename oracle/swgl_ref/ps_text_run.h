@@ -1,0 +1,158 @@
+// TEST INFRASTRUCTURE — hand-instantiated SWGL programs
+//   "ps_text_run ALPHA_PASS,TEXTURE_2D" and
+//   "ps_text_run ALPHA_PASS,DUAL_SOURCE_BLENDING,TEXTURE_2D"
+// (webrender/res/ps_text_run.glsl without WR_FEATURE_GLYPH_TRANSFORM).
+// DUAL: 1 for the DUAL_SOURCE_BLENDING variant (under SWGL_BLEND only the
+// swizzle line and the span commit differ).
+#pragma once
+
+template <int DUAL>
+struct ps_text_run_vert_t : PrimVertBase {
+  typedef ps_text_run_vert_t Self;
+  vec4_scalar v_color;
+  vec3_scalar v_mask_swizzle;
+  vec4_scalar v_uv_bounds;
+  vec2 v_uv;
+  struct InterpOutputs {
+    vec2_scalar v_uv;
+  };
+  ps_text_run_vert_t() {
+    sampler_mask |= WR_S_Color0;
+    init_vertex_abi();
+  }
+
+  // ps_text_run.glsl:98-264
+  void main() {
+    Instance instance = decode_instance_attributes();
+    PrimitiveHeader ph = fetch_prim_header(instance.prim_header_address);
+    Transform transform = fetch_transform(ph.transform_id);
+    ClipArea clip_area = fetch_clip_area(instance.clip_address);
+    PictureTask task = fetch_picture_task(ph.picture_task_address);
+    int glyph_index = instance.segment_index;
+    int subpx_dir = (instance.flags >> 8) & 0xff;
+    int color_mode = instance.flags & 0xff;
+    vec4_scalar text_color = fetch_from_gpu_cache_1(ph.specific_prim_address);
+    vec2_scalar text_offset = ph.local_rect.p1;
+    // fetch_glyph
+    int glyph_address = ph.specific_prim_address + 1 + int(uint32_t(glyph_index) / 2U);
+    vec4_scalar data = fetch_from_gpu_cache_1(glyph_address);
+    vec2_scalar glyph_offset = (uint32_t(glyph_index) % 2U == 1U) ? data.sel(Z, W) : data.sel(X, Y);
+    glyph_offset += ph.local_rect.p0;
+    // fetch_glyph_resource
+    vec4_scalar res_uv_rect = fetch_gpu_cache(instance.resource_address, 0);
+    vec4_scalar res1 = fetch_gpu_cache(instance.resource_address, 1);
+    vec2_scalar res_offset = res1.sel(X, Y);
+    float res_scale = res1.z;
+    vec2_scalar snap_bias;
+    switch (subpx_dir) {
+      case 1: snap_bias = vec2_scalar(0.125f, 0.5f); break;
+      case 2: snap_bias = vec2_scalar(0.5f, 0.125f); break;
+      case 3: snap_bias = vec2_scalar(0.125f); break;
+      default: snap_bias = vec2_scalar(0.5f); break;
+    }
+    float raster_scale = float(ph.user_data.x) / 65535.0f;
+    float glyph_raster_scale = raster_scale * task.device_pixel_scale;
+    float glyph_scale_inv = res_scale / glyph_raster_scale;
+    vec2_scalar raster_glyph_offset = floor(glyph_offset * glyph_raster_scale + snap_bias) / res_scale;
+    vec2_scalar glyph_origin = glyph_scale_inv * (res_offset + raster_glyph_offset) + text_offset;
+    RectWithEndpoint glyph_rect = RectWithEndpoint{
+        glyph_origin, glyph_origin + glyph_scale_inv * (res_uv_rect.sel(Z, W) - res_uv_rect.sel(X, Y))};
+    vec2 local_pos = mix(glyph_rect.p0, glyph_rect.p1, aPosition);
+    VertexInfo vi = write_vertex(local_pos, ph.local_clip_rect, ph.z, transform, task);
+    vec2 f = (vi.local_pos - vec2(glyph_rect.p0)) / vec2(glyph_rect.p1 - glyph_rect.p0);
+    write_clip(clip_area, task);
+    switch (color_mode) {
+      case 0:  // COLOR_MODE_ALPHA
+        v_mask_swizzle = vec3_scalar(0.0f, 1.0f, 1.0f);
+        v_color = text_color;
+        break;
+      case 2:  // COLOR_MODE_BITMAP_SHADOW
+        swgl_blendDropShadow(text_color);
+        v_mask_swizzle = vec3_scalar(1.0f, 0.0f, 0.0f);
+        v_color = vec4_scalar(1.0f);
+        break;
+      case 3:  // COLOR_MODE_COLOR_BITMAP
+        v_mask_swizzle = vec3_scalar(1.0f, 0.0f, 0.0f);
+        v_color = vec4_scalar(text_color.w);
+        break;
+      case 1:  // COLOR_MODE_SUBPX_DUAL_SOURCE
+        swgl_blendSubpixelText(text_color);
+        v_mask_swizzle = vec3_scalar(1.0f, 0.0f, 0.0f);
+        v_color = vec4_scalar(1.0f);
+        break;
+      default:
+        v_mask_swizzle = vec3_scalar(0.0f, 0.0f, 0.0f);
+        v_color = vec4_scalar(1.0f);
+    }
+    vec2_scalar texture_size = make_vec2(textureSize(sColor0, 0));
+    vec2_scalar st0 = res_uv_rect.sel(X, Y) / texture_size;
+    vec2_scalar st1 = res_uv_rect.sel(Z, W) / texture_size;
+    v_uv = mix(st0, st1, f);
+    v_uv_bounds = (res_uv_rect + vec4_scalar(0.5f, 0.5f, -0.5f, -0.5f)) / texture_size.sel(X, Y, X, Y);
+  }
+  ALWAYS_INLINE void store_interp_outputs(char* dest_ptr, size_t stride) {
+    for (int n = 0; n < 4; n++) {
+      auto* dest = reinterpret_cast<InterpOutputs*>(dest_ptr);
+      dest->v_uv = get_nth(v_uv, n);
+      dest_ptr += stride;
+    }
+  }
+  WR_VERTEX_ABI(ps_text_run)
+};
+
+template <int DUAL>
+struct ps_text_run_frag_t : FragmentShaderImpl, ps_text_run_vert_t<DUAL> {
+  typedef ps_text_run_frag_t Self;
+  typedef typename ps_text_run_vert_t<DUAL>::InterpOutputs InterpInputs;
+  typedef typename ps_text_run_vert_t<DUAL>::InterpOutputs InterpOutputs;
+  vec2 v_uv;
+  InterpInputs interp_step;
+  static void read_interp_inputs(FragmentShaderImpl* impl, const void* init_, const void* step_) {
+    Self* self = (Self*)impl;
+    const InterpInputs* init = (const InterpInputs*)init_;
+    const InterpInputs* step = (const InterpInputs*)step_;
+    self->v_uv = init_interp(init->v_uv, step->v_uv);
+    self->interp_step.v_uv = step->v_uv * 4.0f;
+  }
+  ALWAYS_INLINE void step_interp_inputs(int steps = 4) {
+    float chunks = steps * 0.25f;
+    v_uv += interp_step.v_uv * chunks;
+  }
+  // ps_text_run.glsl:278-317
+  void main() {
+    vec2 tc = clamp(v_uv, vec2(this->v_uv_bounds.sel(X, Y)), vec2(this->v_uv_bounds.sel(Z, W)));
+    vec4 mask = texture(this->sColor0, tc);
+    if (this->v_mask_swizzle.z != 0.0f) mask = mask.sel(X, X, X, X);
+    if (!DUAL) {
+      vec3 rgb = mask.sel(X, Y, Z) * Float(this->v_mask_swizzle.x) + mask.sel(W, W, W) * Float(this->v_mask_swizzle.y);
+      mask.x = rgb.x; mask.y = rgb.y; mask.z = rgb.z;
+    }
+    vec4 color = vec4(this->v_color) * mask;
+    color *= Float(1.0f);  // do_clip()
+    this->gl_FragColor = color;
+  }
+  // ps_text_run.glsl:321-337
+  void swgl_drawSpanRGBA8() {
+    if (this->v_mask_swizzle.x != 0.0f && this->v_mask_swizzle.x != 1.0f) return;
+    if (DUAL) {
+      swgl_commitTextureLinearRGBA8(this->sColor0, v_uv, this->v_uv_bounds);
+    } else if (swgl_isTextureR8(this->sColor0)) {
+      swgl_commitTextureLinearColorR8ToRGBA8(this->sColor0, v_uv, this->v_uv_bounds, this->v_color);
+    } else {
+      swgl_commitTextureLinearColorRGBA8(this->sColor0, v_uv, this->v_uv_bounds, this->v_color);
+    }
+  }
+  static int draw_span_RGBA8(FragmentShaderImpl* impl) {
+    Self* self = (Self*)impl;
+    DISPATCH_DRAW_SPAN(self, RGBA8);
+  }
+  WR_FRAGMENT_ABI()
+  ps_text_run_frag_t() {
+    this->init_fragment_abi();
+    this->draw_span_RGBA8_func = &draw_span_RGBA8;
+  }
+};
+typedef ps_text_run_frag_t<0> ps_text_run_ALPHA_PASS_TEXTURE_2D_frag;
+typedef ps_text_run_frag_t<1> ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_TEXTURE_2D_frag;
+WR_PROGRAM(ps_text_run_ALPHA_PASS_TEXTURE_2D, "ps_text_run ALPHA_PASS,TEXTURE_2D")
+WR_PROGRAM(ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_TEXTURE_2D, "ps_text_run ALPHA_PASS,DUAL_SOURCE_BLENDING,TEXTURE_2D")

@@ -139,3 +139,33 @@ def test_brush_image_occluded(seed, variant):
         assert (a == b).all()
     else:
         assert max_abs_diff(a, b) <= 2 and (a != b).mean() < 1e-3
+
+
+TEXT_VARIANTS = ["r8_alpha", "r8_fractional", "r8_scaled", "rgba_modes", "r8_shadow_masks"]
+
+
+def _text_frame(seed, variant, **extra):
+    kw = dict(seed=seed, width=480, height=270, n_runs=8, glyphs_per_run=20)
+    if variant == "r8_fractional":
+        kw.update(fractional=True)
+    elif variant == "r8_scaled":
+        kw.update(device_pixel_scale=1.5, fractional=True)
+    elif variant == "rgba_modes":
+        kw.update(atlas="rgba8", color_modes=(3, 1, 2))
+    elif variant == "r8_shadow_masks":
+        kw.update(color_modes=(0, 2), with_masks=True)
+    kw.update(extra)
+    return scenes.text_frame(**kw)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", TEXT_VARIANTS)
+def test_text_run(seed, variant):
+    f = _text_frame(seed, variant)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+def test_text_run_config_c_size():
+    """Config C flavour at full size: ~6000 glyphs on a 3840x2160 target, 2048^2 R8 atlas."""
+    f = scenes.text_frame(width=3840, height=2160, n_runs=68, glyphs_per_run=89, seed=2, atlas_size=2048)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

@@ -69,3 +69,19 @@ def test_brush_image(seed, variant):
     f = scenes.image_frame(seed=seed, filter=abi.NEAREST if "nearest" in variant else abi.LINEAR,
                            one_to_one="1to1" in variant, fractional="fractional" in variant)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["r8_alpha", "r8_fractional", "r8_scaled", "rgba_modes", "r8_shadow_masks"])
+def test_text_run(seed, variant):
+    kw = dict(seed=seed, width=480, height=270, n_runs=8, glyphs_per_run=20)
+    if variant == "r8_fractional":
+        kw.update(fractional=True)
+    elif variant == "r8_scaled":
+        kw.update(device_pixel_scale=1.5, fractional=True)
+    elif variant == "rgba_modes":
+        kw.update(atlas="rgba8", color_modes=(3, 1, 2))
+    elif variant == "r8_shadow_masks":
+        kw.update(color_modes=(0, 2), with_masks=True)
+    f = scenes.text_frame(**kw)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -301,6 +301,14 @@ WRD Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
       o.a = (color.a + dst.a - wr_muldiv255(dst.a, ca)) & 0xFFFF;
       return o;
     }
+    case WRCU_BLEND__SUBPIXEL_TEXT: {  // SWGL_BLEND_SUBPIXEL_TEXT, blend.h:688-692
+      int ka = kc.a;
+      o.b = (wr_muldiv255(kc.b, src.b) + dst.b - wr_muldiv255(dst.b, wr_muldiv255(ka, src.b))) & 0xFFFF;
+      o.g = (wr_muldiv255(kc.g, src.g) + dst.g - wr_muldiv255(dst.g, wr_muldiv255(ka, src.g))) & 0xFFFF;
+      o.r = (wr_muldiv255(kc.r, src.r) + dst.r - wr_muldiv255(dst.r, wr_muldiv255(ka, src.r))) & 0xFFFF;
+      o.a = (wr_muldiv255(kc.a, src.a) + dst.a - wr_muldiv255(dst.a, wr_muldiv255(ka, src.a))) & 0xFFFF;
+      return o;
+    }
     default:
       return src;
   }

@@ -15,6 +15,7 @@ enum : uint32_t {
   CMD_AA = 1u << 2,         // SWGL_CLIP_FLAG_AA
   CMD_TEXTURED = 1u << 3,   // fragment samples sColor0
   CMD_OUT_RRRR = 1u << 4,   // QF_IS_MASK: output_color.rrrr
+  CMD_SUBPIXEL_TEXT = 1u << 8, // swgl_blendSubpixelText override
   CMD_DROP_SHADOW = 1u << 7, // swgl_blendDropShadow override; colour in CmdCold.i[0..1]
   CMD_CONST_COLOR = 1u << 6, // fragment output is the constant colour in CmdHot.col
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)

@@ -238,9 +238,9 @@ WRD void wr_shade_pixel(const RasterArgs& a, const CmdHot& c, const typename S::
     if (FMT == WRCU_FMT_RGBA8) {
       int key = a.blend;
       Px kc = a.blend_color;
-      if (c.flags & CMD_DROP_SHADOW) {  // SWGL_CLIP_FLAG_BLEND_OVERRIDE (rasterize.h:410-413)
+      if (c.flags & (CMD_DROP_SHADOW | CMD_SUBPIXEL_TEXT)) {  // SWGL_CLIP_FLAG_BLEND_OVERRIDE (rasterize.h:410-413)
         const CmdCold& k = a.cold[c.cold];
-        key = WRCU_BLEND__DROP_SHADOW;
+        key = (c.flags & CMD_DROP_SHADOW) ? WRCU_BLEND__DROP_SHADOW : WRCU_BLEND__SUBPIXEL_TEXT;
         kc = Px{k.i[0] & 0xFFFF, (k.i[0] >> 16) & 0xFFFF, k.i[1] & 0xFFFF, (k.i[1] >> 16) & 0xFFFF};
       }
       px = px_pack(wr_blend_rgba8(key, src, px_unpack(px), kc));

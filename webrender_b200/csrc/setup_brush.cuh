@@ -254,3 +254,89 @@ WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_brush_image)
+
+// ps_text_run main (ps_text_run.glsl:98-264), no GLYPH_TRANSFORM
+WRD void wr_setup_text_run_one(const SetupArgs& a, int idx) {
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  const FrameTablesDev& T = a.tabs;
+  int prim_header_address = aData.x, clip_address = aData.y;
+  int glyph_index = aData.z & 0xffff, flags = aData.z >> 16;
+  int resource_address = aData.w & 0xffffff;
+  int subpx_dir = (flags >> 8) & 0xff, color_mode = flags & 0xff;
+  QuadOut q;
+  memset(&q, 0, sizeof q);
+  DevPrimHeader ph = wr_fetch_prim_header(T, prim_header_address);
+  DevTransform transform = wr_fetch_transform(T, ph.transform_id);
+  DevPictureTask task = wr_fetch_picture_task(T, ph.picture_task_address);
+  float4 text_color = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.specific_prim_address);
+  float tox = ph.lr[2], toy = ph.lr[3];  // text_offset = local_rect.p1
+  float4 gd = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.specific_prim_address + 1 + (int)((unsigned)glyph_index / 2U));
+  float gox = ((unsigned)glyph_index % 2U == 1U) ? gd.z : gd.x;
+  float goy = ((unsigned)glyph_index % 2U == 1U) ? gd.w : gd.y;
+  gox += ph.lr[0];
+  goy += ph.lr[1];
+  float4 r0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, resource_address);
+  float4 r1 = wr_fetch(T.gpu_cache, T.n_gpu_cache, resource_address + 1);
+  float res_scale = r1.z;
+  float snx = 0.5f, sny = 0.5f;
+  if (subpx_dir == 1) snx = 0.125f;
+  else if (subpx_dir == 2) sny = 0.125f;
+  else if (subpx_dir == 3) snx = sny = 0.125f;
+  float raster_scale = (float)ph.user_data[0] / 65535.0f;
+  float grs = raster_scale * task.device_pixel_scale;
+  float gsi = res_scale / grs;
+  float rgx = floorf(gox * grs + snx) / res_scale, rgy = floorf(goy * grs + sny) / res_scale;
+  float ox = gsi * (r1.x + rgx) + tox, oy = gsi * (r1.y + rgy) + toy;
+  float gr[4] = {ox, oy, ox + gsi * (r0.z - r0.x), oy + gsi * (r0.w - r0.y)};
+  float fox = -task.ox + task.tx0, foy = -task.oy + task.ty0;
+  float tw = (float)a.color0.w, th = (float)a.color0.h;
+  float st0x = r0.x / tw, st0y = r0.y / th, st1x = r0.z / tw, st1y = r0.w / th;
+  const float ax[4] = {0.0f, 1.0f, 1.0f, 0.0f}, ay[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+  for (int k = 0; k < 4; k++) {
+    float lpx = (gr[2] - gr[0]) * ax[k] + gr[0], lpy = (gr[3] - gr[1]) * ay[k] + gr[1];
+    lpx = wr_clamp(lpx, ph.lcr[0], ph.lcr[2]);
+    lpy = wr_clamp(lpy, ph.lcr[1], ph.lcr[3]);
+    float4 world = wr_mat_mul(transform.m, make_float4(lpx, lpy, 0.0f, 1.0f));
+    float dpx = world.x * task.device_pixel_scale, dpy = world.y * task.device_pixel_scale;
+    q.pos[k] = wr_mat_mul(a.tgt.proj, make_float4(dpx + fox * world.w, dpy + foy * world.w, ph.z * world.w, world.w));
+    float fx = (lpx - gr[0]) / (gr[2] - gr[0]), fy = (lpy - gr[1]) / (gr[3] - gr[1]);
+    q.interp[k][0] = (st1x - st0x) * fx + st0x;
+    q.interp[k][1] = (st1y - st0y) * fy + st0y;
+  }
+  q.n_interp = 2;
+  q.flags = CMD_TEXTURED;
+  wr_write_clip(T, clip_address, task, q);
+  bool dual = (a.features & WRCU_FEAT_DUAL_SOURCE_BLENDING) != 0;
+  float vcolor[4] = {1.0f, 1.0f, 1.0f, 1.0f}, swz[3] = {0.0f, 0.0f, 0.0f};
+  uint16_t bc[4] = {0, 0, 0, 0};
+  float tc[4] = {text_color.x, text_color.y, text_color.z, text_color.w};
+  switch (color_mode) {
+    case 0: swz[1] = 1.0f; swz[2] = 1.0f; for (int i = 0; i < 4; i++) vcolor[i] = tc[i]; break;
+    case 2:
+    case 1:
+      if (a.blend_enabled) q.flags |= (color_mode == 2 ? CMD_DROP_SHADOW : CMD_SUBPIXEL_TEXT);
+      bc[0] = (uint16_t)wr_round_pixel(tc[2], 255.0f); bc[1] = (uint16_t)wr_round_pixel(tc[1], 255.0f);
+      bc[2] = (uint16_t)wr_round_pixel(tc[0], 255.0f); bc[3] = (uint16_t)wr_round_pixel(tc[3], 255.0f);
+      swz[0] = 1.0f;
+      break;
+    case 3: swz[0] = 1.0f; for (int i = 0; i < 4; i++) vcolor[i] = tc[3]; break;
+    default: break;
+  }
+  float packc[4] = {vcolor[0], vcolor[1], vcolor[2], vcolor[3]};
+  if (dual) packc[0] = packc[1] = packc[2] = packc[3] = 1.0f;  // span commit without colour
+  wr_pack_color(q, packc);
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    k->f[0] = (r0.x + 0.5f) / tw; k->f[1] = (r0.y + 0.5f) / th;
+    k->f[2] = (r0.z + -0.5f) / tw; k->f[3] = (r0.w + -0.5f) / th;
+    for (int i = 0; i < 4; i++) k->g[i] = vcolor[i];
+    k->g[4] = swz[0]; k->g[5] = swz[1]; k->g[6] = swz[2];
+    k->g[7] = dual ? 1.0f : 0.0f;
+    k->i[0] = (int)bc[0] | ((int)bc[1] << 16);
+    k->i[1] = (int)bc[2] | ((int)bc[3] << 16);
+  }
+  wr_finish_setup(a, unsupported);
+}
+WR_SETUP_KERNEL(wr_setup_text_run)

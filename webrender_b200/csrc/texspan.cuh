@@ -20,7 +20,7 @@
 #include "blend.cuh"
 #include "sample.cuh"
 
-enum { TEX_NONE = 0, TEX_LINEAR = 1, TEX_NEAREST_FAST = 2, TEX_NEAREST_FALLBACK = 3 };
+enum { TEX_NONE = 0, TEX_LINEAR = 1, TEX_NEAREST_FAST = 2, TEX_NEAREST_FALLBACK = 3, TEX_LINEAR_R8 = 4 };
 enum { LF_NEAREST = 0, LF_FALLBACK = 1, LF_UPSCALE = 2, LF_FAST = 3, LF_DOWNSCALE = 4 };
 
 struct TexRow {
@@ -169,6 +169,31 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
   }
 }
 
+// blendTextureLinearR8 (swgl_ext.h:634-650): R8 atlas through the fallback
+// bilinear filter, expanded to four lanes (glyph blit into an RGBA8 target).
+WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len, const float* u, const float* v,
+                             int tile_rel, TexRow& r) {
+  r.mode = TEX_NONE;
+  r.body_len = 0;
+  if (body_len == 0 || t.fmt != WRCU_FMT_R8 || t.w < 2) return;
+  r.mode = TEX_LINEAR_R8;
+  r.body_len = body_len;
+  r.before = r.inside = 0;
+  for (int j = 0; j < 4; j++) {
+    r.qu[j] = wr_linear_quantize(u[j], t.w);
+    r.qv[j] = wr_linear_quantize(v[j], t.h);
+  }
+  r.ustep = 4.0f * (r.qu[1] - r.qu[0]);
+  r.vstep = 4.0f * (r.qv[1] - r.qv[0]);
+  r.minu = wr_max(wr_linear_quantize(bounds[0], t.w), 0.0f);
+  r.minv = wr_max(wr_linear_quantize(bounds[1], t.h), 0.0f);
+  r.maxu = wr_max(wr_linear_quantize(bounds[2], t.w), r.minu);
+  r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
+  r.kb[2] = max(0, tile_rel >> 2);
+  wr_tex_seq_base(r.qu, r.ustep, r.kb[2], r.bu[2]);
+  wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
+}
+
 // Source texel (before colour modulation) of body pixel `rel` (0-based in the span).
 WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
   if (r.mode == TEX_NEAREST_FAST) {
@@ -176,6 +201,12 @@ WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
     return px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)r.nry * t.pitch) + sx));
   }
   int j = rel & 3;
+  if (r.mode == TEX_LINEAR_R8) {
+    float qu = r.bu[2][j], qv = r.bv[j];
+    for (int s = r.kb[2]; s < (rel >> 2); s++) { qu = qu + r.ustep; qv = qv + r.vstep; }
+    int rr = wr_texture_linear_r8(t, (int)wr_clamp(qu, r.minu, r.maxu), (int)wr_clamp(qv, r.minv, r.maxv));
+    return Px{rr, rr, rr, rr};
+  }
   if (r.mode == TEX_NEAREST_FALLBACK) {
     float su = r.bu[2][j], sv = r.bv[j];
     if (!r.nsolid) for (int s = r.kb[2]; s < (rel >> 2); s++) { su = su + r.ustep; sv = sv + r.vstep; }

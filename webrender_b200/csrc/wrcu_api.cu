@@ -9,6 +9,7 @@
 #include "shader_clip_rect.cuh"
 #include "shader_quad_mask.cuh"
 #include "shader_image.cuh"
+#include "shader_text.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -470,8 +471,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   if (!tgt) return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: no target bound");
   if (st->blend < 0 || st->blend >= WRCU_BLEND__COUNT)
     return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: bad blend key");
-  if (st->blend == WRCU_BLEND_SUBPIXEL_DUAL_SOURCE && kind != WRCU_KIND_TEXT_RUN)
-    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "dual-source blending outside text runs");
+  if (st->blend == WRCU_BLEND_SUBPIXEL_DUAL_SOURCE)
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "GL dual-source blending: SWGL hosts use the subpixel-text blend override instead");
   cudaSetDevice(c->device);
   c->stats.draw_calls++;
   c->stats.instances += (uint64_t)n;
@@ -536,6 +537,14 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_brush_image, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_TEXT_RUN:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (features & WRCU_FEAT_GLYPH_TRANSFORM)
+        return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "ps_text_run GLYPH_TRANSFORM variant not built yet");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "ps_text_run without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_text_run, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_QUAD_MASK:
       if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "MaskInstance stride < 32");
       sa.features = features;
@@ -588,6 +597,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
     case WRCU_KIND_QUAD_MASK: LAUNCH_RASTER(QuadMaskShader); break;
     case WRCU_KIND_BRUSH_IMAGE: LAUNCH_RASTER(ImageShader); break;
+    case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

@@ -185,3 +185,9 @@ def mask_instance(prim_instance, clip_transform_id, clip_address, clip_space=0):
     instance followed by aClipData = [clip_transform_id, clip_address, clip_space, 0]."""
     return np.concatenate([np.asarray(prim_instance, dtype=np.int32),
                            np.array([clip_transform_id, clip_address, clip_space, 0], dtype=np.int32)])
+
+
+def glyph_instance(prim_header_index, clip_task_address, subpx_dir, color_mode, glyph_index, uv_rect_address):
+    """GlyphInstance::build → PrimitiveInstanceData (gpu_types.rs:511-528)."""
+    z = ((subpx_dir & 0xFF) << 24) | ((color_mode & 0xFF) << 16) | (glyph_index & 0xFFFF)
+    return np.array([prim_header_index, clip_task_address, z, uv_rect_address], dtype=np.int64).astype(np.int32)

@@ -318,3 +318,86 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
         ops.append(Batch(abi.KIND_BRUSH_IMAGE, np.stack(alpha), blend=abi.BLEND_PREMULTIPLIED_ALPHA, depth=abi.DEPTH_TEST,
                          features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("atlas", "", "")))
     return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
+
+
+def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atlas_size=512, atlas="r8",
+               device_pixel_scale=1.0, fractional=False, color_modes=(0,), with_masks=False):
+    """Config C flavour (wrench/benchmarks/text-rendering.yaml): text runs as
+    TextRun(Alpha) glyph instances blitting from a glyph atlas.  The atlas is
+    synthetic (seeded coverage cells, w,h in [4,16]) — glyph rasterisation is
+    FreeType's job upstream and out of scope; the blit is what is under test."""
+    from .gpu_types import glyph_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
+    # atlas: grid of 16x16 cells each holding one glyph of random size
+    cells = atlas_size // 16
+    bpp = 1 if atlas == "r8" else 4
+    tex = np.zeros((atlas_size, atlas_size, bpp), dtype=np.uint8)
+    glyph_res = []
+    for gy in range(cells):
+        for gx in range(cells):
+            gw, gh = int(rng.randint(4, 17)), int(rng.randint(4, 17))
+            cov = rng.randint(0, 256, size=(gh, gw, bpp)).astype(np.uint8)
+            if bpp == 4:
+                a = cov[..., 3:4].astype(np.uint16)
+                cov[..., :3] = (cov[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)
+            tex[gy * 16: gy * 16 + gh, gx * 16: gx * 16 + gw] = cov
+            glyph_res.append((gx * 16, gy * 16, gw, gh))
+    res_addr = {}
+    inst_by_mode = {}
+    z = 1
+    mask = None
+    mw = mh = 256
+    if with_masks:
+        mask = rng.randint(0, 256, size=(mh, mw)).astype(np.uint8)
+    for r in range(n_runs):
+        color_mode = color_modes[r % len(color_modes)]
+        a = rng.uniform(0.5, 1.0)
+        color = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (float(a),)
+        base_x, base_y = float(rng.randint(0, width - 100)), float(rng.randint(16, height - 16))
+        if fractional:
+            base_x += float(rng.uniform(0, 1)); base_y += float(rng.uniform(0, 1))
+        offsets = []
+        pen = 0.0
+        gids = []
+        for g in range(glyphs_per_run):
+            gid = int(rng.randint(0, len(glyph_res)))
+            gids.append(gid)
+            offsets.append((pen + (float(rng.uniform(0, 1)) if fractional else 0.0), 0.0))
+            pen += glyph_res[gid][2] + 1.0
+        blocks = [color]
+        for k in range(0, len(offsets), 2):
+            o0 = offsets[k]
+            o1 = offsets[k + 1] if k + 1 < len(offsets) else (0.0, 0.0)
+            blocks.append((o0[0], o0[1], o1[0], o1[1]))
+        addr = t.push_gpu_cache(blocks)
+        s = 1.0 / device_pixel_scale
+        # local_rect.p0 = run origin (added to glyph offsets), local_rect.p1 = text_offset (batch.rs:1109-1340)
+        hdr = t.add_prim_header((base_x * s, base_y * s, 0.0, 0.0), (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic,
+                                (65535, 0, 0, 0))
+        z += 1
+        clip_task = CLIP_TASK_EMPTY
+        if with_masks and r % 2 == 0:
+            mx, my = int(rng.randint(0, mw - 200)), int(rng.randint(0, mh - 40))
+            clip_task = t.add_render_task((float(mx), float(my), float(mx + 200), float(my + 40)), 1.0,
+                                          (float(int(base_x)), float(int(base_y) - 12)))
+        for g, gid in enumerate(gids):
+            if gid not in res_addr:
+                gx, gy, gw, gh = glyph_res[gid]
+                # GlyphResource: uv_rect (px), offset.xy, scale (ps_text_run.glsl:56-65)
+                res_addr[gid] = t.push_gpu_cache([(float(gx), float(gy), float(gx + gw), float(gy + gh)),
+                                                  (0.0, float(-gh), 1.0, 0.0)])
+            inst_by_mode.setdefault(color_mode, []).append(
+                glyph_instance(hdr, clip_task, 0, color_mode, g, res_addr[gid]))
+    fmt = abi.FMT_R8 if atlas == "r8" else abi.FMT_RGBA8
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "atlas": TextureDesc(fmt, atlas_size, atlas_size, tex.reshape(atlas_size, atlas_size * bpp))}
+    if mask is not None:
+        textures["mask"] = TextureDesc(abi.FMT_R8, mw, mh, mask)
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0))]
+    for mode, lst in sorted(inst_by_mode.items()):
+        ops.append(Batch(abi.KIND_TEXT_RUN, np.stack(lst), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                         features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("atlas", "", ""),
+                         clip_mask="mask" if mask is not None else ""))
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
