@@ -10,6 +10,7 @@
 #include "ps_quad_mask.h"
 #include "brush_image.h"
 #include "ps_text_run.h"
+#include "brush_linear_gradient.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -26,5 +27,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_text_run ALPHA_PASS,TEXTURE_2D")) return ps_text_run_ALPHA_PASS_TEXTURE_2D_program::loader;
   if (!strcmp(name, "ps_text_run ALPHA_PASS,DUAL_SOURCE_BLENDING,TEXTURE_2D"))
     return ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "brush_linear_gradient")) return brush_linear_gradient_program::loader;
+  if (!strcmp(name, "brush_linear_gradient ALPHA_PASS")) return brush_linear_gradient_ALPHA_PASS_program::loader;
   return nullptr;
 }

@@ -85,3 +85,14 @@ def test_text_run(seed, variant):
         kw.update(color_modes=(0, 2), with_masks=True)
     f = scenes.text_frame(**kw)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["opaque", "alpha", "fractional", "repeat", "full_frame"])
+def test_linear_gradient(seed, variant):
+    """brush_linear_gradient incl. the span shader's merged-run 16-bit colour
+    stepping (swgl_commitLinearGradientRGBA8) — the oracle restates it exactly."""
+    f = scenes.gradient_frame(seed=seed, fractional=variant == "fractional", repeat=variant == "repeat",
+                              full_frame=variant == "full_frame",
+                              blend=abi.BLEND_PREMULTIPLIED_ALPHA if variant == "alpha" else abi.BLEND_NONE)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), variant)

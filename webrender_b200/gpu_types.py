@@ -191,3 +191,49 @@ def glyph_instance(prim_header_index, clip_task_address, subpx_dir, color_mode, 
     """GlyphInstance::build → PrimitiveInstanceData (gpu_types.rs:511-528)."""
     z = ((subpx_dir & 0xFF) << 24) | ((color_mode & 0xFF) << 16) | (glyph_index & 0xFFFF)
     return np.array([prim_header_index, clip_task_address, z, uv_rect_address], dtype=np.int64).astype(np.int32)
+
+
+def build_gradient_table(stops):
+    """GradientGpuBlockBuilder::build (prim_store/gradient/mod.rs:166-340), forward
+    order: 130 entries of (start_color, step), first/last = clamp entries.
+    stops = [(offset, (r, g, b, a) premultiplied)], first offset 0, last 1.
+    Returns a (260, 4) float32 array."""
+    f32 = np.float32
+    N = 130
+    start = np.ones((N, 4), dtype=f32)
+    step_arr = np.zeros((N, 4), dtype=f32)
+
+    def fill(i0, i1, c0, c1, prev_step):
+        inv = f32(1.0) / f32(i1 - i0)
+        step = ((c1 - c0) * inv).astype(f32)
+        if np.array_equal(step, prev_step):
+            a = step[3]
+            bits = np.uint32(1) if a == 0.0 else np.float32(a).view(np.uint32) + np.uint32(1)
+            step = step.copy()
+            step[3] = np.uint32(bits).view(np.float32)
+        cur = c0.copy()
+        for idx in range(i0, i1):
+            start[idx] = cur
+            cur = (cur + step).astype(f32)
+            step_arr[idx] = step
+        return step
+
+    def get_index(off):
+        return int(np.floor(f32(min(max(off, 0.0), 1.0)) * f32(128) + f32(1) + f32(0.5)))
+
+    cur_color = np.array(stops[0][1], dtype=f32)
+    prev = cur_color
+    prev = fill(0, 1, cur_color, cur_color, prev)
+    cur_idx = 1
+    for off, col in stops[1:]:
+        nc = np.array(col, dtype=f32)
+        ni = get_index(off)
+        if ni > cur_idx:
+            prev = fill(cur_idx, ni, cur_color, nc, prev)
+            cur_idx = ni
+        cur_color = nc
+    fill(129, 130, cur_color, cur_color, prev)
+    out = np.zeros((260, 4), dtype=f32)
+    out[0::2] = start
+    out[1::2] = step_arr
+    return out

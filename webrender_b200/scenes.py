@@ -401,3 +401,47 @@ def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atla
                          features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("atlas", "", ""),
                          clip_mask="mask" if mask is not None else ""))
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, full_frame=False, repeat=False,
+                   blend=abi.BLEND_NONE):
+    """Config D flavour (wrench/benchmarks/aligned-gradient.yaml / unaligned-gradient.yaml):
+    Brush(LinearGradient) instances; under is_software non-tiled linear gradients
+    stay uncached brushes (scene_building.rs:3392-3396).  Each has its own
+    130-entry two-colour LUT in gpu_buffer_f."""
+    from .gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    inst = []
+    for i in range(n_grad):
+        if full_frame:
+            r = (0.0, 0.0, float(width), float(height))
+            start, end = (0.0, -2000.0), (float(i % 2), 4000.0)   # aligned / unaligned-gradient.yaml
+            stops = [(0.0, (1.0, 0.0, 0.0, 1.0)), (1.0, (0.0, 1.0, 0.0, 1.0))]
+        else:
+            r = _rand_rect(rng, width, height, 24, 400, integer=not fractional)
+            start = (float(rng.uniform(-20, 60)), float(rng.uniform(-20, 60)))
+            end = (float(rng.uniform(80, 300)), float(rng.uniform(-50, 200)))
+            ns = int(rng.randint(2, 5))
+            offs = [0.0] + sorted(float(v) for v in rng.uniform(0.05, 0.95, ns - 2)) + [1.0]
+            stops = []
+            for o in offs:
+                a = float(rng.uniform(0.3, 1.0)) if blend != abi.BLEND_NONE else 1.0
+                stops.append((o, tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (a,)))
+        # keep the 260-texel table inside one 1024-texel row (swgl_validateGradient)
+        pad = (-len(t.gpu_buffer_f)) % 1024
+        if (len(t.gpu_buffer_f) % 1024) + 260 > 1024:
+            t.push_gpu_buffer_f([(0, 0, 0, 0)] * pad)
+        lut = t.push_gpu_buffer_f(list(build_gradient_table(stops)))
+        rw, rh = r[2] - r[0], r[3] - r[1]
+        stretch = (rw, rh) if not repeat else (rw / 2.5, rh / 1.5)
+        addr = t.push_gpu_cache([(start[0], start[1], end[0], end[1]),
+                                 (1.0 if (repeat and i % 2) else 0.0, stretch[0], stretch[1], 0.0)])
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, addr, 0, pic, (lut, 0, 0, 0))
+        inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    feats = abi.FEAT_ALPHA_PASS if blend != abi.BLEND_NONE else 0
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0)),
+           Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, np.stack(inst), blend=blend, features=feats)]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
