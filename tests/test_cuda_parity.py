@@ -169,3 +169,21 @@ def test_text_run_config_c_size():
     """Config C flavour at full size: ~6000 glyphs on a 3840x2160 target, 2048^2 R8 atlas."""
     f = scenes.text_frame(width=3840, height=2160, n_runs=68, glyphs_per_run=89, seed=2, atlas_size=2048)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+GRADIENT_VARIANTS = ["opaque", "alpha", "fractional", "repeat", "full_frame"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", GRADIENT_VARIANTS)
+def test_linear_gradient(seed, variant):
+    f = scenes.gradient_frame(seed=seed, fractional=variant == "fractional", repeat=variant == "repeat",
+                              full_frame=variant == "full_frame",
+                              blend=abi.BLEND_PREMULTIPLIED_ALPHA if variant == "alpha" else abi.BLEND_NONE)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+def test_linear_gradient_config_d_size():
+    """Config D: full-frame two-stop gradients at 3840x2160 (aligned + unaligned)."""
+    f = scenes.gradient_frame(width=3840, height=2160, n_grad=4, full_frame=True)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

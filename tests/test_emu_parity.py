@@ -94,3 +94,19 @@ def _text_frame(seed, variant, **extra):
 def test_text_run(seed, variant):
     f = _text_frame(seed, variant)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+GRADIENT_VARIANTS = ["opaque", "alpha", "fractional", "repeat", "full_frame"]
+
+
+def _gradient_frame(seed, variant):
+    return scenes.gradient_frame(seed=seed, fractional=variant == "fractional", repeat=variant == "repeat",
+                                 full_frame=variant == "full_frame",
+                                 blend=abi.BLEND_PREMULTIPLIED_ALPHA if variant == "alpha" else abi.BLEND_NONE)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", GRADIENT_VARIANTS)
+def test_linear_gradient(seed, variant):
+    f = _gradient_frame(seed, variant)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -32,6 +32,8 @@ struct RasterArgs {
   Px blend_color;   // glBlendColor in lane order
   TexView color0;   // sColor0
   int fast_eligible;  // host-side part of the solid-premult fast-path test
+  const float4* gbuf_f;  // gpu_buffer_f (gradient LUTs)
+  int n_gbuf_f;
 };
 
 #define CHUNK_CMDS 256

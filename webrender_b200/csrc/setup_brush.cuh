@@ -340,3 +340,68 @@ WRD void wr_setup_text_run_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_text_run)
+
+// brush_linear_gradient (brush_linear_gradient.glsl:18-70, gradient_shared.glsl:20-60)
+WRD void wr_setup_brush_linear_gradient_one(const SetupArgs& a, int idx) {
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  QuadOut q;
+  BrushVS vs;
+  memset(&q, 0, sizeof q);
+  wr_brush_vertex(a, aData, 2, q, vs);
+  const FrameTablesDev& T = a.tabs;
+  float4 g0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.ph.specific_prim_address);
+  float4 g1 = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.ph.specific_prim_address + 1);
+  int extend_mode = (int)g1.x;
+  float stretch[2] = {g1.y, g1.z};
+  const float* lr = vs.ph.lr;
+  const float* sr = vs.segment_rect;
+  for (int k = 0; k < 4; k++) {
+    float vx, vy;
+    if (vs.brush_flags & 2) {  // SEGMENT_RELATIVE
+      vx = (vs.local_pos[k].x - sr[0]) / (sr[2] - sr[0]);
+      vy = (vs.local_pos[k].y - sr[1]) / (sr[3] - sr[1]);
+      vx = vx * (vs.segment_data.z - vs.segment_data.x) + vs.segment_data.x;
+      vy = vy * (vs.segment_data.w - vs.segment_data.y) + vs.segment_data.y;
+      vx = vx * (lr[2] - lr[0]);
+      vy = vy * (lr[3] - lr[1]);
+    } else {
+      vx = vs.local_pos[k].x - lr[0];
+      vy = vs.local_pos[k].y - lr[1];
+    }
+    q.interp[k][0] = vx / stretch[0];
+    q.interp[k][1] = vy / stretch[1];
+  }
+  q.n_interp = 2;
+  float dirx = g0.z - g0.x, diry = g0.w - g0.y;
+  float dd = dirx * dirx + diry * diry;
+  float sdx = dirx / dd, sdy = diry / dd;
+  int address = vs.ph.user_data[0];
+  // swgl_validateGradient (swgl_ext.h:1336-1348): 130 entries x 2 texels inside one row
+  int ax = (int)((uint32_t)address % 1024U);
+  bool valid = address >= 0 && ax + 260 <= 1024 && address + 260 <= T.n_gpu_buffer_f;
+  uint32_t merge[5] = {0, 0, 0, 0, 0};
+  if (valid) {
+    float4 prev = __ldg(T.gpu_buffer_f + address + 1);
+    for (int e = 0; e < 129; e++) {
+      float4 nx = __ldg(T.gpu_buffer_f + address + 2 * (e + 1) + 1);
+      if (prev.x == nx.x && prev.y == nx.y && prev.z == nx.z && prev.w == nx.w) merge[e >> 5] |= 1u << (e & 31);
+      prev = nx;
+    }
+  }
+  float white[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+  wr_pack_color(q, white);
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    k->f[2] = g0.x * sdx + g0.y * sdy;
+    k->f[0] = sdx * stretch[0];
+    k->f[1] = sdy * stretch[1];
+    k->f[3] = (float)(extend_mode == 1);
+    k->i[0] = address;
+    k->i[1] = valid ? 1 : 0;
+    for (int i = 0; i < 5; i++) k->g[i] = __uint_as_float(merge[i]);
+  }
+  wr_finish_setup(a, unsupported);
+}
+WR_SETUP_KERNEL(wr_setup_brush_linear_gradient)

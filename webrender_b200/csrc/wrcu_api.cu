@@ -10,6 +10,7 @@
 #include "shader_quad_mask.cuh"
 #include "shader_image.cuh"
 #include "shader_text.cuh"
+#include "shader_gradient.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -537,6 +538,11 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_brush_image, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_BRUSH_LINEAR_GRADIENT:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_brush_linear_gradient, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_TEXT_RUN:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (features & WRCU_FEAT_GLYPH_TRANSFORM)
@@ -572,6 +578,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   ra.blend_color = Px{host_round_pixel(st->blend_color[2]) & 0xFFFF, host_round_pixel(st->blend_color[1]) & 0xFFFF,
                       host_round_pixel(st->blend_color[0]) & 0xFFFF, host_round_pixel(st->blend_color[3]) & 0xFFFF};
   ra.color0 = sa.color0;
+  ra.gbuf_f = c->tables.gpu_buffer_f;
+  ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
   if (grid.x == 0 || grid.y == 0) return WRCU_OK;
   // Device-side dispatch: the setup kernel decides whether the whole batch is
@@ -598,6 +606,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_QUAD_MASK: LAUNCH_RASTER(QuadMaskShader); break;
     case WRCU_KIND_BRUSH_IMAGE: LAUNCH_RASTER(ImageShader); break;
     case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
+    case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER
