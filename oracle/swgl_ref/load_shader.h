@@ -11,6 +11,7 @@
 #include "brush_image.h"
 #include "ps_text_run.h"
 #include "brush_linear_gradient.h"
+#include "cs_clip_box_shadow.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -29,5 +30,6 @@ ProgramLoader load_shader(const char* name) {
     return ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_TEXTURE_2D_program::loader;
   if (!strcmp(name, "brush_linear_gradient")) return brush_linear_gradient_program::loader;
   if (!strcmp(name, "brush_linear_gradient ALPHA_PASS")) return brush_linear_gradient_ALPHA_PASS_program::loader;
+  if (!strcmp(name, "cs_clip_box_shadow TEXTURE_2D")) return cs_clip_box_shadow_TEXTURE_2D_program::loader;
   return nullptr;
 }

@@ -96,3 +96,23 @@ def test_linear_gradient(seed, variant):
                               full_frame=variant == "full_frame",
                               blend=abi.BLEND_PREMULTIPLIED_ALPHA if variant == "alpha" else abi.BLEND_NONE)
     assert_same(render(SwglDevice, f), render(OracleDevice, f), variant)
+
+
+BOX_SHADOW_VARIANTS = ["integer", "fractional", "scaled", "nearest"]
+
+
+def _box_shadow_frame(seed, variant):
+    f = scenes.box_shadow_frame(seed=seed, fractional=variant in ("fractional", "scaled"),
+                                scale=1.5 if variant == "scaled" else 1.0)
+    if variant == "nearest":
+        f.textures["shadow"].filter = abi.NEAREST
+    return f
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", BOX_SHADOW_VARIANTS)
+def test_clip_box_shadow(seed, variant):
+    """cs_clip_box_shadow: nine-patch / simple stretch of a blurred R8 mask, both
+    clip modes, span shader with solid, per-fragment and texture-span sections."""
+    f = _box_shadow_frame(seed, variant)
+    assert_same(render(SwglDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]), variant)

@@ -237,3 +237,24 @@ def build_gradient_table(stops):
     out[0::2] = start
     out[1::2] = step_arr
     return out
+
+
+def box_shadow_instance(sub_rect, task_origin, screen_origin, device_pixel_scale, clip_transform_id,
+                        prim_transform_id, resource_address, src_rect_size, clip_mode, stretch_mode, dest_rect):
+    """ClipMaskInstanceBoxShadow, 84 bytes (gpu_types.rs:226-247; vertex.rs:446-500).
+    resource_address = gpu-cache texel index of the shadow mask's uv rect (sent as
+    u16 x, u16 y); stretch_mode = (x, y) with 0 = Stretch, 1 = Simple."""
+    buf = np.zeros(21, dtype=np.float32)
+    buf[0:4] = sub_rect
+    buf[4:6] = task_origin
+    buf[6:8] = screen_origin
+    buf[8] = device_pixel_scale
+    ints = buf.view(np.int32)
+    ints[9] = clip_transform_id
+    ints[10] = prim_transform_id
+    buf.view(np.uint16)[22:24] = (resource_address % 1024, resource_address // 1024)
+    buf[12:14] = src_rect_size
+    ints[14] = clip_mode
+    ints[15:17] = stretch_mode
+    buf[17:21] = dest_rect
+    return buf.view(np.uint8).copy()

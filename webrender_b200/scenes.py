@@ -445,3 +445,62 @@ def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, fu
     ops = [Clear(color=(1.0, 1.0, 1.0, 1.0)),
            Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, np.stack(inst), blend=blend, features=feats)]
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def shadow_mask_texture(size=256, seed=5):
+    """A seeded stand-in for the blurred box-shadow masks cs_blur produces
+    (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float64)
+    img = np.zeros((size, size))
+    for _ in range(6):
+        cx, cy = rng.uniform(0, size, 2)
+        sx, sy = rng.uniform(size / 10, size / 3, 2)
+        img += np.exp(-(((xx - cx) / sx) ** 2 + ((yy - cy) / sy) ** 2))
+    img = img / img.max() * 255.0 + rng.uniform(-6, 6, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def box_shadow_frame(width=512, height=384, n_clips=8, seed=1, fractional=False, scale=1.0, atlas=256,
+                     full_size=None):
+    """Box-shadow clip masks the way draw_alpha_target issues them
+    (renderer/mod.rs:3754-3929, batch.rs:3816-3838): a cs_clip_box_shadow batch
+    with blending off for first clips, then one multiplied in.  Each instance
+    nine-patches (Stretch) or scales (Simple) a blurred R8 mask into its task
+    rect; every other one is ClipOut."""
+    from .gpu_types import box_shadow_instance
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    xf = t.add_transform(scale_matrix(scale)) if scale != 1.0 else 0
+    prim, sec = [], []
+    for i in range(n_clips):
+        if full_size:
+            w, h = full_size
+            tx = ty = 0
+        else:
+            w, h = int(rng.randint(48, 240)), int(rng.randint(40, 200))
+            tx, ty = int(rng.randint(0, width - w)), int(rng.randint(0, height - h))
+        sx, sy = int(rng.randint(0, 400)), int(rng.randint(0, 400))
+        # shadow mask cell inside the atlas
+        cw, ch = int(rng.randint(24, 96)), int(rng.randint(24, 96))
+        cx, cy = int(rng.randint(0, atlas - cw)), int(rng.randint(0, atlas - ch))
+        res = t.push_gpu_cache([(float(cx), float(cy), float(cx + cw), float(cy + ch)), (0.0, 0.0, 0.0, 0.0)])
+        # destination rect in local space: a bit inside / outside the task rect
+        off = rng.uniform(-10, 30, 4) if fractional else rng.randint(-10, 31, 4).astype(np.float64)
+        dest = ((sx + off[0]) / scale, (sy + off[1]) / scale, (sx + w - off[2]) / scale, (sy + h - off[3]) / scale)
+        stretch = (int(rng.randint(0, 2)), int(rng.randint(0, 2)))
+        src_size = (float(cw) / scale, float(ch) / scale)
+        if fractional:
+            src_size = (src_size[0] * float(rng.uniform(0.8, 1.3)), src_size[1] * float(rng.uniform(0.8, 1.3)))
+        inst = box_shadow_instance((0.0, 0.0, float(w), float(h)), (float(tx), float(ty)), (float(sx), float(sy)),
+                                   scale, xf, xf, res, src_size, i % 2, stretch, dest)
+        (prim if i < max(1, n_clips * 2 // 3) else sec).append(inst)
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0))]
+    for lst, blend in ((prim, abi.BLEND_NONE), (sec, abi.BLEND_MULTIPLY)):
+        if lst:
+            ops.append(Batch(abi.KIND_CLIP_BOX_SHADOW, np.stack(lst), blend=blend, features=abi.FEAT_TEXTURE_2D,
+                             color=("shadow", "", "")))
+    textures = {"mask": TextureDesc(abi.FMT_R8, width, height),
+                "shadow": TextureDesc(abi.FMT_R8, atlas, atlas, data=shadow_mask_texture(atlas, seed + 10),
+                                      filter=abi.LINEAR)}
+    return Frame(t.arrays(), textures, [[Target("mask", ops=ops)]])
