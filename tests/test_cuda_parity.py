@@ -187,3 +187,22 @@ def test_linear_gradient_config_d_size():
     """Config D: full-frame two-stop gradients at 3840x2160 (aligned + unaligned)."""
     f = scenes.gradient_frame(width=3840, height=2160, n_grad=4, full_frame=True)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+BOX_SHADOW_VARIANTS = ["integer", "fractional", "scaled", "nearest"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", BOX_SHADOW_VARIANTS)
+def test_clip_box_shadow(seed, variant):
+    f = scenes.box_shadow_frame(seed=seed, fractional=variant in ("fractional", "scaled"),
+                                scale=1.5 if variant == "scaled" else 1.0)
+    if variant == "nearest":
+        f.textures["shadow"].filter = abi.NEAREST
+    assert_same(render(CudaDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]), variant)
+
+
+def test_clip_box_shadow_config_d_size():
+    """Config D: one 1024x1024 box-shadow mask instance (large-boxshadow-ellipse style)."""
+    f = scenes.box_shadow_frame(width=1024, height=1024, n_clips=1, full_size=(1024, 1024), seed=7)
+    assert_same(render(CudaDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]))

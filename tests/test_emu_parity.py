@@ -110,3 +110,21 @@ def _gradient_frame(seed, variant):
 def test_linear_gradient(seed, variant):
     f = _gradient_frame(seed, variant)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+BOX_SHADOW_VARIANTS = ["integer", "fractional", "scaled", "nearest"]
+
+
+def _box_shadow_frame(seed, variant):
+    f = scenes.box_shadow_frame(seed=seed, fractional=variant in ("fractional", "scaled"),
+                                scale=1.5 if variant == "scaled" else 1.0)
+    if variant == "nearest":
+        f.textures["shadow"].filter = abi.NEAREST
+    return f
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", BOX_SHADOW_VARIANTS)
+def test_clip_box_shadow(seed, variant):
+    f = _box_shadow_frame(seed, variant)
+    assert_same(render(EmuDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]), variant)

@@ -32,6 +32,8 @@ struct __align__(16) CmdHot {
 };
 static_assert(sizeof(CmdHot) == 32, "CmdHot must be 32 bytes");
 
+#define WR_NI 6  // interpolated floats per vertex (cs_clip_box_shadow: vLocalPos + vUv)
+
 struct __align__(16) CmdCold {
   // AA coverage ramps: dist = start + x*slope per edge (rasterize.h:511-519)
   float aa_l0, aa_ls, aa_r0, aa_rs;
@@ -42,7 +44,7 @@ struct __align__(16) CmdCold {
   // Interpolation frame of the (screen-axis-aligned) quad: left/right edge x,
   // top y, 1/height, and interpolants at the four edge end points.
   float xl, xr, yt, yscale;
-  float i_lt[4], i_lb[4], i_rt[4], i_rb[4];
+  float i_lt[WR_NI], i_lb[WR_NI], i_rt[WR_NI], i_rb[WR_NI];
   // kind-specific
   float f[8];   // e.g. uv sample bounds
   int32_t i[4];

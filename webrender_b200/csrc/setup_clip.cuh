@@ -106,3 +106,49 @@ WRD void wr_setup_clip_rectangle_one(const SetupArgs& a, int idx) {
   }
 }
 WR_SETUP_KERNEL(wr_setup_clip_rectangle)
+
+// cs_clip_box_shadow vertex stage (cs_clip_box_shadow.glsl:59-124)
+WRD void wr_setup_clip_box_shadow_one(const SetupArgs& a, int idx) {
+  const float* f = (const float*)(a.instances + (size_t)idx * a.stride);
+  const int* iv = (const int*)f;
+  const uint16_t* ra = (const uint16_t*)(f + 11);
+  QuadOut q;
+  memset(&q, 0, sizeof q);
+  float4 lp[4];
+  wr_clip_tile_vertex(a, f, q, lp);
+  float src_w = f[12], src_h = f[13];
+  int clip_mode = iv[14], smx = iv[15], smy = iv[16];
+  float dest[4] = {f[17], f[18], f[19], f[20]};
+  // fetch_image_source_direct: the address is a texel (x, y) of the gpu cache
+  float4 res0 = wr_fetch(a.tabs.gpu_cache, a.tabs.n_gpu_cache, (int)ra[1] * 1024 + (int)ra[0]);
+  float tw = (float)a.color0.w, th = (float)a.color0.h;
+  float dsx = dest[2] - dest[0], dsy = dest[3] - dest[1];
+  for (int k = 0; k < 4; k++) {
+    float lpx = lp[k].x / lp[k].w, lpy = lp[k].y / lp[k].w;
+    float ux = (smx == 0) ? (lpx - dest[0]) / src_w : (lpx - dest[0]) / dsx;
+    float uy = (smy == 0) ? (lpy - dest[1]) / src_h : (lpy - dest[1]) / dsy;
+    q.interp[k][0] = lp[k].x; q.interp[k][1] = lp[k].y; q.interp[k][2] = lp[k].z; q.interp[k][3] = lp[k].w;
+    q.interp[k][4] = ux * lp[k].w;
+    q.interp[k][5] = uy * lp[k].w;
+  }
+  q.n_interp = 6;
+  float edge[4];
+  if (smx == 0) { edge[0] = 0.5f; edge[2] = (dsx / src_w) - 0.5f; } else { edge[0] = 1.0f; edge[2] = 1.0f; }
+  if (smy == 0) { edge[1] = 0.5f; edge[3] = (dsy / src_h) - 0.5f; } else { edge[1] = 1.0f; edge[3] = 1.0f; }
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    for (int i = 0; i < 4; i++) k->f[i] = edge[i];
+    k->f[4] = (res0.x + 0.5f) / tw; k->f[5] = (res0.y + 0.5f) / th;
+    k->f[6] = (res0.z - 0.5f) / tw; k->f[7] = (res0.w - 0.5f) / th;
+    k->g[0] = res0.x / tw; k->g[1] = res0.y / th; k->g[2] = res0.z / tw; k->g[3] = res0.w / th;
+    for (int i = 0; i < 4; i++) k->g[4 + i] = dest[i];
+    k->g[8] = (float)clip_mode;
+  }
+  if (unsupported) {
+    atomicAdd(&a.info->unsupported, 1);
+    atomicAdd(a.err_counter, 1);
+  }
+}
+WR_SETUP_KERNEL(wr_setup_clip_box_shadow)

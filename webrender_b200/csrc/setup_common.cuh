@@ -95,7 +95,7 @@ WRD int wr_round_i(float v) { return (int)floorf(v + 0.5f); }
 // Output of a kind's vertex stage for one instance.
 struct QuadOut {
   float4 pos[4];        // gl_Position per lane (lanes = unit quad corners 0,1,3,2)
-  float interp[4][4];   // up to 4 interpolated floats per lane
+  float interp[4][WR_NI];  // up to WR_NI interpolated floats per lane
   int n_interp;
   uint32_t flags;       // CMD_* set by the vertex stage
   int aa_edge_mask;     // swgl_antiAlias edges (lane-index bits)
@@ -243,7 +243,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     h.x0 = (short)sx0; h.x1 = (short)sx1; h.y0 = (short)r0; h.y1 = (short)r1;
     h.flags = flags;
     k.xl = lx; k.xr = rx; k.yt = yt; k.yscale = yScale;
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < WR_NI; i++) {
       k.i_lt[i] = q.interp[Lt][i]; k.i_lb[i] = q.interp[Lb][i];
       k.i_rt[i] = q.interp[Rt][i]; k.i_rb[i] = q.interp[Rb][i];
     }

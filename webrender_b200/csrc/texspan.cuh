@@ -40,6 +40,18 @@ struct TexRow {
   float bu[3][4], bv[4];
 };
 
+// Texel access by texture format.  R8 texels travel in Px.r (the lane the R8
+// blend stage reads); matchTextureFormat (swgl_ext.h:143-156) guarantees the
+// span paths only ever see source format == target format.
+WRD Px wr_tex_linear_any(const TexView& t, int ix, int iy) {
+  if (t.fmt == WRCU_FMT_RGBA8) return wr_texture_linear_rgba8(t, ix, iy);
+  return Px{0, 0, wr_texture_linear_r8(t, ix, iy), 0};
+}
+WRD Px wr_tex_load_any(const TexView& t, int cy, int cx) {
+  if (t.fmt == WRCU_FMT_RGBA8) return px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)cy * t.pitch) + cx));
+  return Px{0, 0, (int)__ldg(t.ptr + (size_t)cy * t.pitch + cx), 0};
+}
+
 // needsTextureLinear (swgl_ext.h:554-587); u0,u1,v0,v1 = lanes 0,1
 WRD int wr_needs_texture_linear(const TexView& t, float u0, float u1, float v0, float v1, int span) {
   if (t.w < 2) return LF_NEAREST;
@@ -65,10 +77,11 @@ WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
 }
 
 WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sampler_filter, int body_len,
-                          const float* u, const float* v, int tile_rel, TexRow& r) {
+                          const float* u, const float* v, int tile_rel, TexRow& r,
+                          int target_fmt = WRCU_FMT_RGBA8) {
   r.body_len = body_len;
   r.mode = TEX_NONE;
-  if (body_len == 0 || t.fmt != WRCU_FMT_RGBA8) {
+  if (body_len == 0 || t.fmt != target_fmt) {
     r.body_len = 0;
     return;
   }
@@ -198,7 +211,7 @@ WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len
 WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
   if (r.mode == TEX_NEAREST_FAST) {
     int sx = min(max(r.nix + rel, r.nminx), r.nmaxx);
-    return px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)r.nry * t.pitch) + sx));
+    return wr_tex_load_any(t, r.nry, sx);
   }
   int j = rel & 3;
   if (r.mode == TEX_LINEAR_R8) {
@@ -212,7 +225,7 @@ WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
     if (!r.nsolid) for (int s = r.kb[2]; s < (rel >> 2); s++) { su = su + r.ustep; sv = sv + r.vstep; }
     int ix = (int)wr_clamp(su, r.minu, r.maxu), iy = (int)wr_clamp(sv, r.minv, r.maxv);
     int cx = wr_clamp_coord(ix, t.w), cy = wr_clamp_coord(iy, t.h);
-    return px_unpack(__ldg((const uint32_t*)(t.ptr + (size_t)cy * t.pitch) + cx));
+    return wr_tex_load_any(t, cy, cx);
   }
   // TEX_LINEAR
   if (rel < r.before || rel >= r.before + r.inside) {
@@ -228,17 +241,24 @@ WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
       qv = r.bv[j];
       for (int s = r.kb[2]; s < (p >> 2); s++) { qu = qu + r.ustep; qv = qv + r.vstep; }
     }
-    return wr_texture_linear_rgba8(t, (int)wr_clamp(qu, r.minu, r.maxu), (int)wr_clamp(qv, r.minv, r.maxv));
+    return wr_tex_linear_any(t, (int)wr_clamp(qu, r.minu, r.maxu), (int)wr_clamp(qv, r.minv, r.maxv));
   }
   int p = rel - r.before;
   if (r.filter == LF_UPSCALE) {
     float qu = r.bu[1][j];
     for (int s = r.kb[1]; s < (p >> 2); s++) qu = qu + r.ustep;
     int ix = (p < 4) ? (int)wr_clamp(qu, r.minu, r.maxu) : (int)qu;
-    return wr_texture_linear_rgba8(t, ix, r.uiy0);
+    return wr_tex_linear_any(t, ix, r.uiy0);
   }
   // FAST / DOWNSCALE (swgl_ext.h:284-371): integer texel stepping, constant fractions
   int mul = r.filter == LF_DOWNSCALE ? 2 : 1;
+  if (t.fmt == WRCU_FMT_R8) {
+    const uint8_t* r0 = t.ptr + (size_t)r.fcy * t.pitch + (size_t)(r.fcx + p * mul);
+    const uint8_t* r1 = r0 + (r.fnext ? t.pitch : 0);
+    int l = wr_lerp7(__ldg(r0), __ldg(r1), r.ffy);
+    int rr = wr_lerp7(__ldg(r0 + 1), __ldg(r1 + 1), r.ffy);
+    return Px{0, 0, wr_lerp7(l, rr, r.ffx) & 0xFFFF, 0};
+  }
   const uint8_t* row0 = t.ptr + (size_t)r.fcy * t.pitch + (size_t)(r.fcx + p * mul) * 4;
   const uint8_t* row1 = row0 + (r.fnext ? t.pitch : 0);
   uint2 a = make_uint2(__ldg((const uint32_t*)row0), __ldg((const uint32_t*)row0 + 1));

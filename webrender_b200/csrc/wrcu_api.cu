@@ -11,6 +11,7 @@
 #include "shader_image.cuh"
 #include "shader_text.cuh"
 #include "shader_gradient.cuh"
+#include "shader_box_shadow.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -561,6 +562,13 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_CLIP_BOX_SHADOW:
+      if (stride < 84) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceBoxShadow stride < 84");
+      if (!sa.color0.ptr || sa.color0.fmt != WRCU_FMT_R8)
+        return wrcu_fail(c, WRCU_ERR_INVALID, "cs_clip_box_shadow needs an R8 shadow mask in sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_clip_box_shadow, sblocks, 128, c->stream, sa);
+      break;
     default:
       return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);
   }
@@ -607,6 +615,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_BRUSH_IMAGE: LAUNCH_RASTER(ImageShader); break;
     case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
+    case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER
