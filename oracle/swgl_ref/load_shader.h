@@ -12,6 +12,7 @@
 #include "ps_text_run.h"
 #include "brush_linear_gradient.h"
 #include "cs_clip_box_shadow.h"
+#include "composite.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -31,5 +32,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "brush_linear_gradient")) return brush_linear_gradient_program::loader;
   if (!strcmp(name, "brush_linear_gradient ALPHA_PASS")) return brush_linear_gradient_ALPHA_PASS_program::loader;
   if (!strcmp(name, "cs_clip_box_shadow TEXTURE_2D")) return cs_clip_box_shadow_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "composite TEXTURE_2D")) return composite_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "composite FAST_PATH,TEXTURE_2D")) return composite_FAST_PATH_TEXTURE_2D_program::loader;
   return nullptr;
 }

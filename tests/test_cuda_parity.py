@@ -206,3 +206,19 @@ def test_clip_box_shadow_config_d_size():
     """Config D: one 1024x1024 box-shadow mask instance (large-boxshadow-ellipse style)."""
     f = scenes.box_shadow_frame(width=1024, height=1024, n_clips=1, full_size=(1024, 1024), seed=7)
     assert_same(render(CudaDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]))
+
+
+COMPOSITE_VARIANTS = ["tiles", "fractional", "external", "external_fractional"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", COMPOSITE_VARIANTS)
+def test_composite(seed, variant):
+    f = scenes.composite_frame(seed=seed, external="external" in variant, fractional="fractional" in variant)
+    assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)
+
+
+def test_composite_4k():
+    """Row 15 at full size: 4x5 picture-cache tiles of 1024x512 into a 3840x2160 framebuffer."""
+    f = scenes.composite_frame(width=3840, height=2160, tile_w=1024, tile_h=512, seed=4)
+    assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]))

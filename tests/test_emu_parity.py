@@ -128,3 +128,13 @@ def _box_shadow_frame(seed, variant):
 def test_clip_box_shadow(seed, variant):
     f = _box_shadow_frame(seed, variant)
     assert_same(render(EmuDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]), variant)
+
+
+COMPOSITE_VARIANTS = ["tiles", "fractional", "external", "external_fractional"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", COMPOSITE_VARIANTS)
+def test_composite(seed, variant):
+    f = scenes.composite_frame(seed=seed, external="external" in variant, fractional="fractional" in variant)
+    assert_same(render(EmuDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)

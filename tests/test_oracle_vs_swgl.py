@@ -116,3 +116,20 @@ def test_clip_box_shadow(seed, variant):
     clip modes, span shader with solid, per-fragment and texture-span sections."""
     f = _box_shadow_frame(seed, variant)
     assert_same(render(SwglDevice, f, ["mask"]), render(OracleDevice, f, ["mask"]), variant)
+
+
+COMPOSITE_VARIANTS = ["tiles", "fractional", "external", "external_fractional"]
+
+
+def _composite_frame(seed, variant):
+    return scenes.composite_frame(seed=seed, external="external" in variant, fractional="fractional" in variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", COMPOSITE_VARIANTS)
+def test_composite(seed, variant):
+    """composite_simple: opaque FAST_PATH tile copies, clear tile (dest-out), alpha
+    and solid-colour tiles, external RGB surfaces with unnormalised uv rects,
+    linear filtering, colour modulation and flips."""
+    f = _composite_frame(seed, variant)
+    assert_same(render(SwglDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)

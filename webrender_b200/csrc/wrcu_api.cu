@@ -12,6 +12,7 @@
 #include "shader_text.cuh"
 #include "shader_gradient.cuh"
 #include "shader_box_shadow.cuh"
+#include "shader_composite.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -562,6 +563,12 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_COMPOSITE:
+      if (stride < 120) return wrcu_fail(c, WRCU_ERR_INVALID, "CompositeInstance stride < 120");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "composite without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_composite, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_CLIP_BOX_SHADOW:
       if (stride < 84) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceBoxShadow stride < 84");
       if (!sa.color0.ptr || sa.color0.fmt != WRCU_FMT_R8)
@@ -616,6 +623,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
+    case WRCU_KIND_COMPOSITE: LAUNCH_RASTER(CompositeShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

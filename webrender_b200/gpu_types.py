@@ -258,3 +258,19 @@ def box_shadow_instance(sub_rect, task_origin, screen_origin, device_pixel_scale
     ints[15:17] = stretch_mode
     buf[17:21] = dest_rect
     return buf.view(np.uint8).copy()
+
+
+def composite_instance(rect, clip_rect, color=(1.0, 1.0, 1.0, 1.0), uv_rect=(0.0, 0.0, 1.0, 1.0), normalized=True,
+                       flip=(False, False)):
+    """CompositeInstance, 120 bytes (gpu_types.rs:288-356; vertex.rs desc::COMPOSITE):
+    rect, clip_rect, premultiplied colour, params [_, uv_type, 0, 0], 3 uv rects, flip."""
+    buf = np.zeros(30, dtype=np.float32)
+    buf[0:4] = rect
+    buf[4:8] = clip_rect
+    buf[8:12] = color
+    buf[13] = 0.0 if normalized else 1.0   # UV_TYPE_NORMALIZED = 0, UV_TYPE_UNNORMALIZED = 1
+    buf[16:20] = uv_rect
+    buf[20:24] = uv_rect
+    buf[24:28] = uv_rect
+    buf[28:30] = (float(flip[0]), float(flip[1]))
+    return buf.view(np.uint8).copy()

@@ -504,3 +504,86 @@ def box_shadow_frame(width=512, height=384, n_clips=8, seed=1, fractional=False,
                 "shadow": TextureDesc(abi.FMT_R8, atlas, atlas, data=shadow_mask_texture(atlas, seed + 10),
                                       filter=abi.LINEAR)}
     return Frame(t.arrays(), textures, [[Target("mask", ops=ops)]])
+
+
+def tile_texture(w, h, seed, opaque=True):
+    """Seeded picture-cache tile content: smooth colour ramps plus noise, BGRA
+    premultiplied."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.zeros((h, w, 4))
+    ph = rng.uniform(0, 6.28, 6)
+    for ch in range(3):
+        img[..., ch] = 0.5 + 0.5 * np.sin(xx / (17.0 + 9 * ch) + ph[ch]) * np.cos(yy / (23.0 - 5 * ch) + ph[3 + ch])
+    img[..., :3] += rng.uniform(-0.08, 0.08, (h, w, 3))
+    a = np.ones((h, w)) if opaque else np.clip(0.5 + 0.5 * np.sin(xx / 31.0 + yy / 19.0), 0, 1)
+    img = np.clip(img, 0, 1)
+    img[..., :3] *= a[..., None]
+    img[..., 3] = a
+    return np.clip(np.rint(img * 255.0), 0, 255).astype(np.uint8).reshape(h, w * 4)
+
+
+def composite_frame(width=640, height=384, tile_w=256, tile_h=128, seed=1, external=False, fractional=False):
+    """composite_simple / draw_tile_list (renderer/mod.rs:3340-3484, 3126-3334):
+    the framebuffer is cleared, opaque picture-cache tiles are copied front to
+    back with blending off (FAST_PATH program: whole-texture uv, white), clear
+    tiles punch holes with premultiplied dest-out, alpha tiles and solid-colour
+    tiles (1x1 dummy texture) go over back to front.  `external` adds RGB
+    external surfaces: unnormalised uv sub-rects, linear filter, scaling, flips."""
+    from .gpu_types import composite_instance
+    rng = np.random.RandomState(seed)
+    textures = {"fb": TextureDesc(abi.FMT_RGBA8, width, height),
+                "dummy": TextureDesc(abi.FMT_RGBA8, 1, 1, data=np.full((1, 4), 255, dtype=np.uint8),
+                                     filter=abi.NEAREST)}
+    ops = [Clear(color=(0.0, 0.0, 0.0, 0.0))]
+    cols, rows = (width + tile_w - 1) // tile_w, (height + tile_h - 1) // tile_h
+    jit = (lambda: float(rng.uniform(-0.4, 0.4))) if fractional else (lambda: 0.0)
+    ti = 0
+    alpha_ops = []
+    for ry in range(rows):
+        for cx in range(cols):
+            name = "tile%d" % ti
+            opaque = (ti % 3) != 2
+            textures[name] = TextureDesc(abi.FMT_RGBA8, tile_w, tile_h, data=tile_texture(tile_w, tile_h, seed * 100 + ti, opaque),
+                                         filter=abi.NEAREST)
+            x0, y0 = cx * tile_w + jit(), ry * tile_h + jit()
+            rect = (x0, y0, x0 + tile_w, y0 + tile_h)
+            clip = (max(rect[0], 0.0) + (float(rng.randint(0, 40)) if ti % 4 == 1 else 0.0), max(rect[1], 0.0),
+                    min(rect[2], float(width)), min(rect[3], float(height)) - (float(rng.randint(0, 30)) if ti % 5 == 2 else 0.0))
+            inst = composite_instance(rect, clip)
+            b = Batch(abi.KIND_COMPOSITE, inst[None, :], blend=abi.BLEND_NONE if opaque else abi.BLEND_PREMULTIPLIED_ALPHA,
+                      features=abi.FEAT_FAST_PATH | abi.FEAT_TEXTURE_2D, color=(name, "", ""))
+            (ops if opaque else alpha_ops).append(b)
+            ti += 1
+    # a clear tile (dest-out with black through the dummy texture) and solid colour tiles
+    r = _rand_rect(rng, width, height, 40, 200, integer=not fractional)
+    ops.append(Batch(abi.KIND_COMPOSITE, composite_instance(r, r, (0.0, 0.0, 0.0, 1.0))[None, :],
+                     blend=abi.BLEND_PREMULTIPLIED_DEST_OUT, features=abi.FEAT_TEXTURE_2D, color=("dummy", "", "")))
+    ops += alpha_ops
+    solid = []
+    for i in range(3):
+        r = _rand_rect(rng, width, height, 30, 220, integer=not fractional)
+        a = float(rng.uniform(0.3, 1.0))
+        col = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (a,)
+        solid.append(composite_instance(r, r, col))
+    ops.append(Batch(abi.KIND_COMPOSITE, np.stack(solid), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                     features=abi.FEAT_TEXTURE_2D, color=("dummy", "", "")))
+    if external:
+        textures["ext"] = TextureDesc(abi.FMT_RGBA8, 320, 200, data=tile_texture(320, 200, seed + 77, False),
+                                      filter=abi.LINEAR)
+        ext = []
+        for i in range(4):
+            r = _rand_rect(rng, width, height, 60, 300, integer=not fractional)
+            ux, uy = float(rng.randint(0, 100)), float(rng.randint(0, 60))
+            if i == 0:
+                uw, uh = r[2] - r[0], r[3] - r[1]          # 1:1
+                uw, uh = min(uw, 320 - ux), min(uh, 200 - uy)
+                r = (r[0], r[1], r[0] + uw, r[1] + uh)
+            else:
+                uw, uh = float(rng.randint(40, 200)), float(rng.randint(30, 130))
+            clip = (r[0] + 3.0, r[1] + 2.0, r[2] - 5.0, r[3] - 1.0)
+            ext.append(composite_instance(r, clip, (1.0, 1.0, 1.0, 1.0) if i % 2 == 0 else (0.5, 0.5, 0.5, 0.5),
+                                          (ux, uy, ux + uw, uy + uh), normalized=False, flip=(i == 2, i == 3)))
+        ops.append(Batch(abi.KIND_COMPOSITE, np.stack(ext), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                         features=abi.FEAT_TEXTURE_2D, color=("ext", "", "")))
+    return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
