@@ -222,3 +222,21 @@ def test_composite_4k():
     """Row 15 at full size: 4x5 picture-cache tiles of 1024x512 into a 3840x2160 framebuffer."""
     f = scenes.composite_frame(width=3840, height=2160, tile_w=1024, tile_h=512, seed=4)
     assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]))
+
+
+OPACITY_VARIANTS = ["scaled", "fractional", "one_to_one", "nearest"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", OPACITY_VARIANTS)
+def test_brush_opacity(seed, variant):
+    f = scenes.opacity_frame(seed=seed, fractional=variant == "fractional", one_to_one=variant == "one_to_one",
+                             filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("r8", [False, True])
+def test_ps_clear(seed, r8):
+    f = scenes.clear_frame(seed=seed, r8=r8)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

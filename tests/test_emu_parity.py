@@ -138,3 +138,21 @@ COMPOSITE_VARIANTS = ["tiles", "fractional", "external", "external_fractional"]
 def test_composite(seed, variant):
     f = scenes.composite_frame(seed=seed, external="external" in variant, fractional="fractional" in variant)
     assert_same(render(EmuDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)
+
+
+OPACITY_VARIANTS = ["scaled", "fractional", "one_to_one", "nearest"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", OPACITY_VARIANTS)
+def test_brush_opacity(seed, variant):
+    f = scenes.opacity_frame(seed=seed, fractional=variant == "fractional", one_to_one=variant == "one_to_one",
+                             filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("r8", [False, True])
+def test_ps_clear(seed, r8):
+    f = scenes.clear_frame(seed=seed, r8=r8)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

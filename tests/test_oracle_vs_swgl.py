@@ -133,3 +133,25 @@ def test_composite(seed, variant):
     linear filtering, colour modulation and flips."""
     f = _composite_frame(seed, variant)
     assert_same(render(SwglDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)
+
+
+OPACITY_VARIANTS = ["scaled", "fractional", "one_to_one", "nearest"]
+
+
+def _opacity_frame(seed, variant):
+    return scenes.opacity_frame(seed=seed, fractional=variant == "fractional", one_to_one=variant == "one_to_one",
+                                filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", OPACITY_VARIANTS)
+def test_brush_opacity(seed, variant):
+    f = _opacity_frame(seed, variant)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("r8", [False, True])
+def test_ps_clear(seed, r8):
+    f = scenes.clear_frame(seed=seed, r8=r8)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

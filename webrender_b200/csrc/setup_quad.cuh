@@ -226,3 +226,27 @@ WRD void wr_setup_quad_mask_one(const SetupArgs& a, int idx) {
   }
 }
 WR_SETUP_KERNEL(wr_setup_quad_mask)
+
+// ps_clear (ps_clear.glsl:13-18): quad-based clear, depth forced to the far plane
+WRD void wr_setup_clear_one(const SetupArgs& a, int idx) {
+  const float* f = (const float*)(a.instances + (size_t)idx * a.stride);
+  QuadOut q;
+  memset(&q, 0, sizeof q);
+  const float ax[4] = {0.0f, 1.0f, 1.0f, 0.0f}, ay[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+  for (int k = 0; k < 4; k++) {
+    float px = (f[2] - f[0]) * ax[k] + f[0], py = (f[3] - f[1]) * ay[k] + f[1];
+    q.pos[k] = wr_mat_mul(a.tgt.proj, make_float4(px, py, 0.0f, 1.0f));
+    q.pos[k].z = q.pos[k].w;
+  }
+  q.n_interp = 0;
+  q.col[0] = (uint16_t)wr_round_pixel(f[6], 255.0f); q.col[1] = (uint16_t)wr_round_pixel(f[5], 255.0f);
+  q.col[2] = (uint16_t)wr_round_pixel(f[4], 255.0f); q.col[3] = (uint16_t)wr_round_pixel(f[7], 255.0f);
+  q.flags = CMD_CONST_COLOR;
+  int unsupported = 0;
+  wr_emit_quad(a, idx, q, &unsupported);
+  if (unsupported) {
+    atomicAdd(&a.info->unsupported, 1);
+    atomicAdd(a.err_counter, 1);
+  }
+}
+WR_SETUP_KERNEL(wr_setup_clear)

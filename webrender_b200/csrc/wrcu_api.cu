@@ -13,6 +13,7 @@
 #include "shader_gradient.cuh"
 #include "shader_box_shadow.cuh"
 #include "shader_composite.cuh"
+#include "shader_opacity.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -563,6 +564,16 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_CLEAR:
+      if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "ClearInstance stride < 32");
+      WR_LAUNCH(wr_setup_clear, sblocks, 128, c->stream, sa);
+      break;
+    case WRCU_KIND_BRUSH_OPACITY:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_opacity without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_brush_opacity, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_COMPOSITE:
       if (stride < 120) return wrcu_fail(c, WRCU_ERR_INVALID, "CompositeInstance stride < 120");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "composite without sColor0");
@@ -624,6 +635,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
     case WRCU_KIND_COMPOSITE: LAUNCH_RASTER(CompositeShader); break;
+    case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

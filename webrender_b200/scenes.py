@@ -587,3 +587,84 @@ def composite_frame(width=640, height=384, tile_w=256, tile_h=128, seed=1, exter
         ops.append(Batch(abi.KIND_COMPOSITE, np.stack(ext), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
                          features=abi.FEAT_TEXTURE_2D, color=("ext", "", "")))
     return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
+
+
+def _picture_source(t, rng, aw, ah, w, h, one_to_one):
+    """gpu-cache entry of an off-screen picture's uv rect the way
+    RenderTaskCache/resolve_location publishes it: uv rect, user data, and the
+    four homogeneous corner coordinates get_image_quad_uv reads
+    (gpu_cache.glsl:103-135)."""
+    if one_to_one:
+        uw, uh = int(w), int(h)
+    else:
+        uw, uh = int(rng.randint(16, 160)), int(rng.randint(16, 120))
+    uw, uh = min(uw, aw - 1), min(uh, ah - 1)
+    u0, v0 = int(rng.randint(0, aw - uw)), int(rng.randint(0, ah - uh))
+    return t.push_gpu_cache([(float(u0), float(v0), float(u0 + uw), float(v0 + uh)), (0.0, 0.0, 0.0, 0.0),
+                             (0.0, 0.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)])
+
+
+def opacity_frame(width=640, height=360, n_prims=14, seed=1, fractional=False, one_to_one=False, filter=abi.LINEAR):
+    """Brush(Opacity) batch (batch.rs:1671-1712): pictures with a filter:
+    opacity() drawn from their off-screen surface, premultiplied-alpha blended;
+    prim user data = [uv_rect_address, amount * 65536, 0, 0]."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    aw, ah = 320, 200
+    inst = []
+    for i in range(n_prims):
+        r = _rand_rect(rng, width, height, 24, 220, integer=not fractional)
+        src = _picture_source(t, rng, aw, ah, r[2] - r[0], r[3] - r[1], one_to_one)
+        spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
+        amount = 1.0 if i % 5 == 0 else float(rng.uniform(0.05, 1.0))
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (src, int(amount * 65536.0), 0, 0))
+        inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "surface": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 31, opaque=False), filter=filter)}
+    ops = [Clear(color=(0.9, 0.9, 0.9, 1.0)),
+           Batch(abi.KIND_BRUSH_OPACITY, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                 features=abi.FEAT_ALPHA_PASS, color=("surface", "", ""))]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def clear_frame(width=512, height=320, seed=1, r8=False):
+    """Quad-based clears (ps_clear; renderer/mod.rs:2714-2744, 3795-3833,
+    3971-3994): rects cleared by ClearInstance quads with depth forced to the
+    far plane (so a depth-writing clear also resets depth), between batches of
+    opaque depth-tested solid brushes."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+
+    def solids(n, z0):
+        out = []
+        for i in range(n):
+            r = _rand_rect(rng, width, height, 30, 260)
+            addr = t.push_gpu_cache([tuple(float(v) for v in rng.uniform(0, 1, 3)) + (1.0,)])
+            hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), z0 + i, addr, 0, pic, (65535, 0, 0, 0))
+            out.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+        return np.stack(out[::-1])
+
+    def clears(n, colors):
+        out = np.zeros((n, 8), dtype=np.float32)
+        for i in range(n):
+            out[i, 0:4] = _rand_rect(rng, width, height, 40, 220)
+            out[i, 4:8] = colors[i % len(colors)]
+        return out
+
+    if r8:
+        textures = {"target": TextureDesc(abi.FMT_R8, width, height)}
+        ops = [Clear(color=(0.5, 0.5, 0.5, 0.5)),
+               Batch(abi.KIND_CLEAR, clears(6, [(0.0, 0.0, 0.0, 0.0), (1.0, 1.0, 1.0, 1.0)]))]
+        return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "depth": TextureDesc(abi.FMT_DEPTH24, width, height)}
+    ops = [Clear(color=(0.1, 0.2, 0.3, 1.0), depth=1.0),
+           Batch(abi.KIND_BRUSH_SOLID, solids(8, 10), depth=abi.DEPTH_TEST_WRITE),
+           Batch(abi.KIND_CLEAR, clears(3, [(0.0, 0.0, 0.0, 0.0), (0.25, 0.5, 0.75, 1.0)]), depth=abi.DEPTH_TEST_WRITE),
+           Batch(abi.KIND_BRUSH_SOLID, solids(8, 1), depth=abi.DEPTH_TEST_WRITE),
+           Batch(abi.KIND_CLEAR, clears(2, [(1.0, 1.0, 1.0, 1.0)]))]
+    return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
