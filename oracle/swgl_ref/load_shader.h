@@ -15,6 +15,7 @@
 #include "composite.h"
 #include "brush_opacity.h"
 #include "ps_clear.h"
+#include "brush_blend.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -40,5 +41,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "brush_opacity ALPHA_PASS")) return brush_opacity_ALPHA_PASS_program::loader;
   if (!strcmp(name, "brush_opacity ALPHA_PASS,ANTIALIASING")) return brush_opacity_ALPHA_PASS_ANTIALIASING_program::loader;
   if (!strcmp(name, "ps_clear")) return ps_clear_program::loader;
+  if (!strcmp(name, "brush_blend")) return brush_blend_program::loader;
+  if (!strcmp(name, "brush_blend ALPHA_PASS")) return brush_blend_ALPHA_PASS_program::loader;
   return nullptr;
 }

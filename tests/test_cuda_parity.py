@@ -240,3 +240,19 @@ def test_brush_opacity(seed, variant):
 def test_ps_clear(seed, r8):
     f = scenes.clear_frame(seed=seed, r8=r8)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["alpha", "fractional", "opaque"])
+def test_brush_blend(seed, variant):
+    """Bit-exact except the hue-rotate picture: its matrix comes from cosf/sinf,
+    evaluated by the host libm in the reference and on the device here
+    (correctly rounded via double) — at most 1 LSB apart on a few pixels."""
+    import numpy as np
+    f = scenes.blend_frame(seed=seed, fractional=variant == "fractional", opaque_source=variant == "opaque")
+    a = render(CudaDevice, f, ["target"])["target"].astype(int)
+    b = render(OracleDevice, f, ["target"])["target"].astype(int)
+    hue = np.zeros(a.shape, dtype=bool)
+    hue[0:140, 4 * (8 + 2 * 126 - 2):4 * (8 + 3 * 126 + 2)] = True   # filters[2] = hue-rotate cell
+    assert (a[~hue] == b[~hue]).all()
+    assert np.abs(a - b).max() <= 1 and (a != b).mean() < 2e-3

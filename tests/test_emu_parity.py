@@ -156,3 +156,10 @@ def test_brush_opacity(seed, variant):
 def test_ps_clear(seed, r8):
     f = scenes.clear_frame(seed=seed, r8=r8)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["alpha", "fractional", "opaque"])
+def test_brush_blend(seed, variant):
+    f = scenes.blend_frame(seed=seed, fractional=variant == "fractional", opaque_source=variant == "opaque")
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

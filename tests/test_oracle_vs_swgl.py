@@ -155,3 +155,12 @@ def test_brush_opacity(seed, variant):
 def test_ps_clear(seed, r8):
     f = scenes.clear_frame(seed=seed, r8=r8)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["alpha", "fractional", "opaque"])
+def test_brush_blend(seed, variant):
+    """brush_blend: every CSS filter op incl. the vector pow() approximation
+    behind sRGB<->linear and gamma transfer."""
+    f = scenes.blend_frame(seed=seed, fractional=variant == "fractional", opaque_source=variant == "opaque")
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

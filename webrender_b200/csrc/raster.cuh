@@ -34,6 +34,8 @@ struct RasterArgs {
   int fast_eligible;  // host-side part of the solid-premult fast-path test
   const float4* gbuf_f;  // gpu_buffer_f (gradient LUTs)
   int n_gbuf_f;
+  const float4* gpu_cache;  // component-transfer tables
+  int n_gpu_cache;
 };
 
 #define CHUNK_CMDS 256

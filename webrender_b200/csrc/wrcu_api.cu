@@ -14,6 +14,7 @@
 #include "shader_box_shadow.cuh"
 #include "shader_composite.cuh"
 #include "shader_opacity.cuh"
+#include "shader_blend.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -564,6 +565,12 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_BRUSH_BLEND:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_blend without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_brush_blend, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_CLEAR:
       if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "ClearInstance stride < 32");
       WR_LAUNCH(wr_setup_clear, sblocks, 128, c->stream, sa);
@@ -606,6 +613,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   ra.color0 = sa.color0;
   ra.gbuf_f = c->tables.gpu_buffer_f;
   ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
+  ra.gpu_cache = c->tables.gpu_cache;
+  ra.n_gpu_cache = c->tables.n_gpu_cache;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
   if (grid.x == 0 || grid.y == 0) return WRCU_OK;
   // Device-side dispatch: the setup kernel decides whether the whole batch is
@@ -636,6 +645,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
     case WRCU_KIND_COMPOSITE: LAUNCH_RASTER(CompositeShader); break;
     case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
+    case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

@@ -668,3 +668,64 @@ def clear_frame(width=512, height=320, seed=1, r8=False):
            Batch(abi.KIND_BRUSH_SOLID, solids(8, 1), depth=abi.DEPTH_TEST_WRITE),
            Batch(abi.KIND_CLEAR, clears(2, [(1.0, 1.0, 1.0, 1.0)]))]
     return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
+
+
+# Filter::as_int (internal_types.rs) / blend.glsl:13-24
+(FILTER_CONTRAST, FILTER_GRAYSCALE, FILTER_HUE_ROTATE, FILTER_INVERT, FILTER_SATURATE, FILTER_SEPIA,
+ FILTER_BRIGHTNESS, FILTER_COLOR_MATRIX, FILTER_SRGB_TO_LINEAR, FILTER_LINEAR_TO_SRGB, FILTER_FLOOD,
+ FILTER_COMPONENT_TRANSFER) = range(12)
+
+
+def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=False):
+    """Brush(Blend) batch (batch.rs:1715-1890): one picture per CSS filter op —
+    contrast, grayscale, hue-rotate, invert, saturate, sepia, brightness, colour
+    matrix, sRGB<->linear, flood and a component transfer (table / discrete /
+    linear / gamma) — each reading its off-screen surface through sColor0."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    aw, ah = 320, 200
+    inst = []
+    filters = [(FILTER_CONTRAST, 1.6), (FILTER_GRAYSCALE, 0.7), (FILTER_HUE_ROTATE, 110.0), (FILTER_INVERT, 0.85),
+               (FILTER_SATURATE, 2.2), (FILTER_SEPIA, 0.6), (FILTER_BRIGHTNESS, 1.4), (FILTER_COLOR_MATRIX, None),
+               (FILTER_SRGB_TO_LINEAR, None), (FILTER_LINEAR_TO_SRGB, None), (FILTER_FLOOD, None),
+               (FILTER_COMPONENT_TRANSFER, None), (FILTER_CONTRAST, 0.4), (FILTER_BRIGHTNESS, 0.5)]
+    for i, (op, amount) in enumerate(filters):
+        col, row = i % 5, i // 5
+        x0, y0 = 8 + col * 126 + (float(rng.uniform(0, 1)) if fractional else 0.0), 8 + row * 130 + (float(rng.uniform(0, 1)) if fractional else 0.0)
+        r = (x0, y0, x0 + 118.0, y0 + 122.0)
+        src = _picture_source(t, rng, aw, ah, 118, 122, i % 2 == 0)
+        mode = op
+        if op in (FILTER_CONTRAST, FILTER_GRAYSCALE, FILTER_INVERT, FILTER_SATURATE, FILTER_SEPIA, FILTER_BRIGHTNESS):
+            user = int(amount * 65536.0)
+        elif op == FILTER_HUE_ROTATE:
+            user = int(0.01745329251 * amount * 65536.0)
+        elif op == FILTER_COLOR_MATRIX:
+            m = rng.uniform(-0.3, 0.9, (4, 4)).astype(np.float32)
+            user = t.push_gpu_cache([tuple(float(v) for v in m[k]) for k in range(4)] +
+                                    [tuple(float(v) for v in rng.uniform(-0.1, 0.2, 4))])
+        elif op == FILTER_FLOOD:
+            user = t.push_gpu_cache([(0.2, 0.6, 0.4, 0.7)])
+        elif op == FILTER_COMPONENT_TRANSFER:
+            # r: table (256 values = 64 blocks), g: discrete, b: linear, a: gamma
+            table = np.clip(np.linspace(0, 1, 256) ** 0.5 + rng.uniform(-0.02, 0.02, 256), -0.1, 1.1).astype(np.float32)
+            disc = (np.floor(np.linspace(0, 0.999, 256) * 5) / 4).astype(np.float32)
+            blocks = [tuple(float(v) for v in table[4 * k: 4 * k + 4]) for k in range(64)]
+            blocks += [tuple(float(v) for v in disc[4 * k: 4 * k + 4]) for k in range(64)]
+            blocks += [(0.8, 0.1, 0.0, 0.0), (0.9, 1.7, 0.05, 0.0)]
+            user = t.push_gpu_cache(blocks)
+            mode = op | (1 << 28) | (2 << 24) | (3 << 20) | (4 << 16)
+        else:
+            user = 0
+        spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (src, mode, user, 0))
+        inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "surface": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 51, opaque=opaque_source),
+                                       filter=abi.LINEAR)}
+    blend = abi.BLEND_NONE if opaque_source else abi.BLEND_PREMULTIPLIED_ALPHA
+    ops = [Clear(color=(0.8, 0.85, 0.9, 1.0)),
+           Batch(abi.KIND_BRUSH_BLEND, np.stack(inst), blend=blend,
+                 features=0 if opaque_source else abi.FEAT_ALPHA_PASS, color=("surface", "", ""))]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
