@@ -16,6 +16,7 @@
 #include "brush_opacity.h"
 #include "ps_clear.h"
 #include "brush_blend.h"
+#include "brush_mix_blend.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -43,5 +44,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_clear")) return ps_clear_program::loader;
   if (!strcmp(name, "brush_blend")) return brush_blend_program::loader;
   if (!strcmp(name, "brush_blend ALPHA_PASS")) return brush_blend_ALPHA_PASS_program::loader;
+  if (!strcmp(name, "brush_mix_blend")) return brush_mix_blend_program::loader;
+  if (!strcmp(name, "brush_mix_blend ALPHA_PASS")) return brush_mix_blend_ALPHA_PASS_program::loader;
   return nullptr;
 }

@@ -256,3 +256,10 @@ def test_brush_blend(seed, variant):
     hue[0:140, 4 * (8 + 2 * 126 - 2):4 * (8 + 3 * 126 + 2)] = True   # filters[2] = hue-rotate cell
     assert (a[~hue] == b[~hue]).all()
     assert np.abs(a - b).max() <= 1 and (a != b).mean() < 2e-3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional"])
+def test_brush_mix_blend(seed, variant):
+    f = scenes.mix_blend_frame(seed=seed, fractional=variant == "fractional")
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -163,3 +163,10 @@ def test_ps_clear(seed, r8):
 def test_brush_blend(seed, variant):
     f = scenes.blend_frame(seed=seed, fractional=variant == "fractional", opaque_source=variant == "opaque")
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional"])
+def test_brush_mix_blend(seed, variant):
+    f = scenes.mix_blend_frame(seed=seed, fractional=variant == "fractional")
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

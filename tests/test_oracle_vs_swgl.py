@@ -164,3 +164,10 @@ def test_brush_blend(seed, variant):
     behind sRGB<->linear and gamma transfer."""
     f = scenes.blend_frame(seed=seed, fractional=variant == "fractional", opaque_source=variant == "opaque")
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional"])
+def test_brush_mix_blend(seed, variant):
+    f = scenes.mix_blend_frame(seed=seed, fractional=variant == "fractional")
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -31,6 +31,7 @@ struct RasterArgs {
   int depth_mode;   // wrcu_depth
   Px blend_color;   // glBlendColor in lane order
   TexView color0;   // sColor0
+  TexView color1;   // sColor1 (brush_mix_blend source)
   int fast_eligible;  // host-side part of the solid-premult fast-path test
   const float4* gbuf_f;  // gpu_buffer_f (gradient LUTs)
   int n_gbuf_f;

@@ -24,6 +24,7 @@ struct SetupArgs {
   int blend_enabled;
   uint32_t features;
   TexView color0;
+  TexView color1;
   TexView clip_mask;
 };
 

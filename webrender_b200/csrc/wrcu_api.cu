@@ -15,6 +15,7 @@
 #include "shader_composite.cuh"
 #include "shader_opacity.cuh"
 #include "shader_blend.cuh"
+#include "shader_mix_blend.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -520,6 +521,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.err_counter = c->dev_err;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
   sa.color0 = tex_view(c, st->color[0]);
+  sa.color1 = tex_view(c, st->color[1]);
   sa.clip_mask = tex_view(c, st->clip_mask);
 
   WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info);
@@ -564,6 +566,13 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       if (stride < 200) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceRect stride < 200");
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
+      break;
+    case WRCU_KIND_BRUSH_MIX_BLEND:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (!sa.color0.ptr || !sa.color1.ptr)
+        return wrcu_fail(c, WRCU_ERR_INVALID, "brush_mix_blend needs sColor0 (backdrop) and sColor1 (source)");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_brush_mix_blend, sblocks, 128, c->stream, sa);
       break;
     case WRCU_KIND_BRUSH_BLEND:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
@@ -611,6 +620,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   ra.blend_color = Px{host_round_pixel(st->blend_color[2]) & 0xFFFF, host_round_pixel(st->blend_color[1]) & 0xFFFF,
                       host_round_pixel(st->blend_color[0]) & 0xFFFF, host_round_pixel(st->blend_color[3]) & 0xFFFF};
   ra.color0 = sa.color0;
+  ra.color1 = sa.color1;
   ra.gbuf_f = c->tables.gpu_buffer_f;
   ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
   ra.gpu_cache = c->tables.gpu_cache;
@@ -646,6 +656,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_COMPOSITE: LAUNCH_RASTER(CompositeShader); break;
     case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
     case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
+    case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER(MixBlendShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

@@ -729,3 +729,38 @@ def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=F
            Batch(abi.KIND_BRUSH_BLEND, np.stack(inst), blend=blend,
                  features=0 if opaque_source else abi.FEAT_ALPHA_PASS, color=("surface", "", ""))]
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
+    """Brush(MixBlend) batch (batch.rs:1931-2001): one picture per non-separable /
+    separable mix-blend-mode handled in the shader (multiply, overlay, darken,
+    lighten, colour-dodge, colour-burn, hard-light, soft-light, difference, hue,
+    saturation, colour, luminosity): sColor0 = backdrop readback, sColor1 = the
+    picture's own surface; user data = [mode, backdrop uv, source uv, 0]."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    aw, ah = 320, 200
+    inst = []
+    modes = [1, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 14, 15, 9, 6]
+    for i, mode in enumerate(modes):
+        col, row = i % 5, i // 5
+        jx = float(rng.uniform(0, 1)) if fractional else 0.0
+        jy = float(rng.uniform(0, 1)) if fractional else 0.0
+        x0, y0 = 8 + col * 126 + jx, 8 + row * 130 + jy
+        r = (x0, y0, x0 + 118.0, y0 + 122.0)
+        back = _picture_source(t, rng, aw, ah, 118, 122, True)
+        src = _picture_source(t, rng, aw, ah, 118, 122, i % 3 != 2)
+        spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (mode, back, src, 0))
+        inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "backdrop": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 61, opaque=seed % 2 == 0),
+                                        filter=abi.LINEAR),
+                "surface": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 62, opaque=False),
+                                       filter=abi.LINEAR)}
+    ops = [Clear(color=(0.8, 0.85, 0.9, 1.0)),
+           Batch(abi.KIND_BRUSH_MIX_BLEND, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                 features=abi.FEAT_ALPHA_PASS, color=("backdrop", "surface", ""))]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
