@@ -166,6 +166,40 @@ def cpu_baseline_sample():
                       f"includes table upload + clear; SWGL built with g++ -O2 (generic, non-SSE-intrinsic paths)"}
 
 
+def run_config_e(dev, rank, world, steps, barrier):
+    """One 8192x4096 frame = 64 picture-cache tiles of 1024x512 (config-B' rect
+    list cut per tile), tiles round-robin over the ranks, one NCCL gather to
+    rank 0, composite there.  Strong scaling of a single frame; wall time per
+    frame is the max over ranks between barriers."""
+    import zlib
+    import torch
+    import torch.distributed as dist
+    from webrender_b200 import multi_gpu
+    scene = multi_gpu.tiled_alpha_scene()
+    sr = multi_gpu.ShardedRenderer(dev, scene, rank, world)
+    for _ in range(2):
+        sr.render()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sr.render()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        crc = zlib.crc32(sr.read_framebuffer().tobytes())
+        single = multi_gpu.ShardedRenderer(dev, scene, 0, 1)
+        single.render()
+        crc1 = zlib.crc32(single.read_framebuffer().tobytes())
+        ms = float(dt[0]) / steps * 1e3
+        out = {"workload": "config E: 8192x4096 frame, 64 tiles of 1024x512, 1000 seeded alpha rects cut per tile",
+               "ms_per_frame": ms, "fps": 1e3 / ms, "Mpix_s": scene.pixel_layers / (ms * 1e-3) / 1e6,
+               "tiles_per_rank": sr.per_rank, "exchange": "torch.distributed gather over NCCL, device memory",
+               "framebuffer_crc32": crc, "matches_single_gpu": bool(crc == crc1)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -270,6 +304,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
 
+    # ---- config E, informational: ONE 8K frame whose 64 tiles are
+    # sharded over the ranks, gathered to rank 0 over NCCL and composited there ----
+    config_e = None
+    if world > 1:
+        try:
+            config_e = run_config_e(dev, rank, world, max(3, args.steps // 4), barrier)
+        except Exception as e:  # keep the headline line even if the extra fails
+            config_e = {"error": repr(e)[:200]}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         ms_per_step = total_ms / args.steps
@@ -294,6 +337,8 @@ def main():
                          "note": "algorithmic bytes = 8 B per pixel-layer (SURVEY.md §8d); the tile-resident kernel "
                                  "keeps layers on chip, so DRAM traffic is ~2 x 33 MB per launch and achieved may exceed peak"},
         }
+        if config_e is not None:
+            line["config_e"] = config_e
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))
