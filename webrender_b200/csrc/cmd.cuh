@@ -56,5 +56,6 @@ struct BatchInfo {
   int bx0, by0, bx1, by1;  // bounding box of all commands
   int unsupported;         // instances the setup kernel had to reject
   int simple;              // 1 while every command is a plain solid quad (no mask/AA/texture, lanes<=255)
-  int pad[2];
+  int premul_valid;        // 1 while every command's colour lanes are <= its alpha lane
+  int pad[1];
 };

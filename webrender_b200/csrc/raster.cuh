@@ -313,6 +313,7 @@ template <class S, int FMT>
 __global__ void __launch_bounds__(WRCU_THREADS)
 wr_raster(RasterArgs a) {
   __shared__ CmdHot sh[CHUNK_CMDS];
+  __shared__ int wsum[WRCU_THREADS / 32];
   const int tx0 = blockIdx.x * WRCU_TILE_W, ty0 = blockIdx.y * WRCU_TILE_H;
   const BatchInfo bi = *a.info;
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
@@ -330,14 +331,33 @@ wr_raster(RasterArgs a) {
   const bool use_depth = a.depth_mode != WRCU_DEPTH_OFF && zrow != nullptr;
 
   for (int base = 0; base < a.n; base += CHUNK_CMDS) {
+    // Binning: each thread tests one command of the chunk against this tile; the
+    // survivors' indices are compacted in batch order (ballot + prefix sum), so
+    // the pixel loop only visits commands that touch the tile.
+    const int m = min(CHUNK_CMDS, a.n - base);
+    int keep = 0;
+    CmdHot mine;
+    if ((int)threadIdx.x < m) {
+      mine = a.hot[base + threadIdx.x];
+      keep = mine.x1 > tx0 && mine.x0 < tx0 + WRCU_TILE_W && mine.y1 > ty0 && mine.y0 < ty0 + WRCU_TILE_H &&
+             mine.x1 > mine.x0;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    __syncthreads();  // previous chunk fully consumed
+    if (lane == 0) wsum[warp] = __popc(bal);
     __syncthreads();
-    int m = min(CHUNK_CMDS, a.n - base);
-    if (threadIdx.x < m) sh[threadIdx.x] = a.hot[base + threadIdx.x];
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < WRCU_THREADS / 32; w++) {
+      const int v = wsum[w];
+      if (w < warp) off += v;
+      total += v;
+    }
+    if (keep) sh[off + __popc(bal & ((1u << lane) - 1u))] = mine;
     __syncthreads();
-    for (int i = 0; i < m; i++) {
+    for (int i = 0; i < total; i++) {
       const CmdHot c = sh[i];
       if (!row_ok || y < c.y0 || y >= c.y1) continue;          // warp-uniform
-      if (c.x1 <= tx0 || c.x0 >= tx0 + WRCU_TILE_W) continue;  // CTA-uniform
       if (!loaded) {
         // lazy tile load: first command that touches this row
         loaded = true;
@@ -374,75 +394,157 @@ wr_raster(RasterArgs a) {
 }
 
 // ---- specialised hot kernel: solid quads, premultiplied-alpha over, no depth,
-// no mask/AA (config B, the alpha-blend brush pass).  Pixels stay unpacked as
-// (rb, ga) lane pairs across the whole command list; per pixel-layer the work
-// is 2 x (IMAD, PRMT, IADD, VMIN).  Commands whose colour lanes exceed 255 or
-// that carry mask/AA flags are not routed here (the host checks the batch).
-__global__ void __launch_bounds__(WRCU_THREADS)
-wr_raster_solid_premult(RasterArgs a) {
-  __shared__ CmdHot sh[CHUNK_CMDS];
-  const int tx0 = blockIdx.x * WRCU_TILE_W, ty0 = blockIdx.y * WRCU_TILE_H;
-  const BatchInfo bi = *a.info;
-  if (!bi.simple) return;  // mixed batch → wr_raster_quads
-  if (tx0 >= bi.bx1 || tx0 + WRCU_TILE_W <= bi.bx0 || ty0 >= bi.by1 || ty0 + WRCU_TILE_H <= bi.by0)
-    return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x = tx0 + lane * 4, y = ty0 + warp;
-  const bool row_ok = y < a.tgt.h;
-  uint8_t* rowp = a.tgt.color + (size_t)y * a.tgt.color_pitch + (size_t)x * 4;
-  uint32_t rb[4], ga[4];
-  bool dirty = false;
-  {
-    uint4 v = row_ok ? *(const uint4*)rowp : make_uint4(0, 0, 0, 0);
-    uint32_t pv[4] = {v.x, v.y, v.z, v.w};
+// no mask/AA (config B, the alpha-blend brush pass).
+//
+// Work decomposition.  A CTA of 128 threads owns a 128x8 tile; warp w holds rows
+// w and w+4, lane l pixels [4l, 4l+4) of both: 8 pixels per thread, kept
+// unpacked as (B,R) / (G,A) 16-bit lane pairs for the whole command list.
+// CTAs are persistent and stride over the tiles of the batch's bounding box;
+// the host sizes the grid so the tile count divides evenly over the resident
+// CTAs (see wr_fast_grid).
+//
+// Per chunk of 128 commands the CTA first CLASSIFIES cooperatively — one
+// command per thread against the tile: no overlap (dropped), full cover, or
+// partial — and compacts the survivors in batch order into shared memory
+// (ballot + prefix sum), together with the per-command blend constants.  The
+// pixel loop then runs over survivors only; for a full-cover command it is
+// branch-free.
+//
+// Arithmetic per 16-bit lane, c = 255 - src.a (blend.h:473-474, muldiv255):
+//   dst' = dst + src - ((dst*src.a + dst) >> 8)  ==  ((dst*c + 255) >> 8) + src
+// (exact: dst - floor(t/256) = ceil((256 dst - t)/256), t = dst*(src.a+1)).
+// When every source lane <= src.a (a valid premultiplied colour) the sum cannot
+// exceed 255, so `+ src` folds into the multiply-add's addend and the
+// saturating pack disappears:   dst' = (dst*c + (255 + 256*src)) >> 8,
+// i.e. one IMAD + one PRMT per lane pair = 4 instructions per pixel-layer.
+// Batches with over-range colours (src > src.a) take the saturating variant.
+#define FAST_THREADS 128
+#define FAST_CHUNK 128
+
+WRD uint32_t wr_over_folded(uint32_t dst_pair, uint32_t c, uint32_t k) {
+  return __byte_perm(dst_pair * c + k, 0, 0x4341);  // (t >> 8) & 0x00FF00FF
+}
+
+template <bool VALID>
+WRD void wr_fast_blend8(uint32_t* rb, uint32_t* ga, uint32_t c, uint32_t krb, uint32_t kga) {
+  if (VALID) {
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      rb[p] = pv[p] & 0x00FF00FFu;
-      ga[p] = (pv[p] >> 8) & 0x00FF00FFu;
+    for (int p = 0; p < 8; p++) {
+      rb[p] = wr_over_folded(rb[p], c, krb);
+      ga[p] = wr_over_folded(ga[p], c, kga);
+    }
+  } else {
+    const uint32_t srb = (krb - 0x00FF00FFu) >> 8, sga = (kga - 0x00FF00FFu) >> 8;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+      rb[p] = wr_premult_over_pair(rb[p], srb, c);
+      ga[p] = wr_premult_over_pair(ga[p], sga, c);
     }
   }
-  for (int base = 0; base < a.n; base += CHUNK_CMDS) {
+}
+
+template <bool VALID>
+WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb, int* wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = tx0 + lane * 4;
+  const int y0 = ty0 + warp, y1 = ty0 + warp + 4;
+  uint8_t* p0 = a.tgt.color + (size_t)y0 * a.tgt.color_pitch + (size_t)x * 4;
+  uint8_t* p1 = a.tgt.color + (size_t)y1 * a.tgt.color_pitch + (size_t)x * 4;
+  uint32_t rb[8], ga[8];
+  bool loaded = false, dirty = false;
+  for (int base = 0; base < a.n; base += FAST_CHUNK) {
+    // ---- classify + compact (one command per thread) ----
+    int keep = 0;
+    uint4 A = make_uint4(0, 0, 0, 0);
+    int4 B = make_int4(0, 0, 0, 0);
+    if (base + (int)threadIdx.x < a.n) {
+      const CmdHot c = a.hot[base + threadIdx.x];
+      keep = c.x1 > tx0 && c.x0 < tx0 + WRCU_TILE_W && c.y1 > ty0 && c.y0 < ty0 + WRCU_TILE_H && c.x1 > c.x0;
+      const uint32_t full = c.x0 <= tx0 && c.x1 >= tx0 + WRCU_TILE_W && c.y0 <= ty0 && c.y1 >= ty0 + WRCU_TILE_H;
+      const uint32_t srb = (uint32_t)c.col[0] | ((uint32_t)c.col[2] << 16);  // B | R<<16
+      const uint32_t sga = (uint32_t)c.col[1] | ((uint32_t)c.col[3] << 16);  // G | A<<16
+      A = make_uint4(255u - c.col[3], 0x00FF00FFu + (srb << 8), 0x00FF00FFu + (sga << 8), full);
+      B = make_int4(c.x0, c.x1, c.y0, c.y1);
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    __syncthreads();  // previous chunk's readers are done with fa/fb/wsum
+    if (lane == 0) wsum[warp] = __popc(bal);
     __syncthreads();
-    int m = min(CHUNK_CMDS, a.n - base);
-    if (threadIdx.x < m) sh[threadIdx.x] = a.hot[base + threadIdx.x];
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FAST_THREADS / 32; w++) {
+      const int v = wsum[w];
+      if (w < warp) off += v;
+      total += v;
+    }
+    if (keep) {
+      const int slot = off + __popc(bal & ((1u << lane) - 1u));
+      fa[slot] = A;
+      fb[slot] = B;
+    }
     __syncthreads();
+    if (total == 0) continue;
+    if (!loaded) {
+      loaded = true;  // lazy tile load: first chunk with a command on this tile
+      const uint4 v0 = *(const uint4*)p0, v1 = *(const uint4*)p1;
+      const uint32_t pv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        rb[p] = pv[p] & 0x00FF00FFu;
+        ga[p] = (pv[p] >> 8) & 0x00FF00FFu;
+      }
+    }
+    // ---- blend the survivors in batch order ----
 #pragma unroll 2
-    for (int i = 0; i < m; i++) {
-      const uint4 h0 = *(const uint4*)&sh[i];         // rect, flags, z
-      const uint2 h1 = *(const uint2*)&sh[i].col[0];  // colour lanes
-      int cx0 = (short)(h0.x & 0xFFFF), cy0 = (short)(h0.x >> 16);
-      int cx1 = (short)(h0.y & 0xFFFF), cy1 = (short)(h0.y >> 16);
-      if (y < cy0 || y >= cy1) continue;
-      // h1.x = B | G<<16, h1.y = R | A<<16  → pairs (B,R) and (G,A)
-      uint32_t srb = __byte_perm(h1.x, h1.y, 0x5410);  // B | R<<16
-      uint32_t sga = __byte_perm(h1.x, h1.y, 0x7632);  // G | A<<16
-      uint32_t cc = 255u - (h1.y >> 16);
-      if (cx0 <= x && cx1 >= x + 4) {
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-          rb[p] = wr_premult_over_pair(rb[p], srb, cc);
-          ga[p] = wr_premult_over_pair(ga[p], sga, cc);
-        }
+    for (int i = 0; i < total; i++) {
+      const uint4 k = fa[i];
+      if (k.w) {
+        wr_fast_blend8<VALID>(rb, ga, k.x, k.y, k.z);
         dirty = true;
-      } else if (cx1 > x && cx0 < x + 4) {
+      } else {
+        const int4 r = fb[i];
+        const uint32_t srb = (k.y - 0x00FF00FFu) >> 8, sga = (k.z - 0x00FF00FFu) >> 8;
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-          if (x + p >= cx0 && x + p < cx1) {
-            rb[p] = wr_premult_over_pair(rb[p], srb, cc);
-            ga[p] = wr_premult_over_pair(ga[p], sga, cc);
+        for (int row = 0; row < 2; row++) {
+          const int yy = row ? y1 : y0;
+          if (yy < r.z || yy >= r.w || r.y <= x || r.x >= x + 4) continue;
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            if (x + p >= r.x && x + p < r.y) {
+              rb[4 * row + p] = wr_premult_over_pair(rb[4 * row + p], srb, k.x);
+              ga[4 * row + p] = wr_premult_over_pair(ga[4 * row + p], sga, k.x);
+            }
           }
+          dirty = true;
         }
-        dirty = true;
       }
     }
   }
-  if (dirty && row_ok) {
-    uint4 v;
-    v.x = rb[0] | (ga[0] << 8);
-    v.y = rb[1] | (ga[1] << 8);
-    v.z = rb[2] | (ga[2] << 8);
-    v.w = rb[3] | (ga[3] << 8);
-    *(uint4*)rowp = v;
+  if (dirty) {
+    // rows past the target height exist in the allocation (textures are padded to
+    // whole tiles), so both rows can be stored unconditionally
+    *(uint4*)p0 = make_uint4(rb[0] | (ga[0] << 8), rb[1] | (ga[1] << 8), rb[2] | (ga[2] << 8), rb[3] | (ga[3] << 8));
+    *(uint4*)p1 = make_uint4(rb[4] | (ga[4] << 8), rb[5] | (ga[5] << 8), rb[6] | (ga[6] << 8), rb[7] | (ga[7] << 8));
+  }
+}
+
+__global__ void __launch_bounds__(FAST_THREADS)
+wr_raster_solid_premult(RasterArgs a) {
+  __shared__ uint4 fa[FAST_CHUNK];
+  __shared__ int4 fb[FAST_CHUNK];
+  __shared__ int wsum[FAST_THREADS / 32];
+  const BatchInfo bi = *a.info;
+  if (!bi.simple) return;  // mixed batch → generic kernel
+  // tiles of the batch's bounding box (clamped to the target)
+  const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
+  const int bx1 = (min(bi.bx1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
+  const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
+  const int nx = bx1 - bx0, n_tiles = nx * (by1 - by0);
+  if (nx <= 0 || n_tiles <= 0) return;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tx0 = (bx0 + t % nx) * WRCU_TILE_W, ty0 = (by0 + t / nx) * WRCU_TILE_H;
+    if (bi.premul_valid) wr_fast_tile<true>(a, tx0, ty0, fa, fb, wsum);
+    else wr_fast_tile<false>(a, tx0, ty0, fa, fb, wsum);
   }
 }
 #endif  // !WRCU_HOSTEMU

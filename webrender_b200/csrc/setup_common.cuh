@@ -255,6 +255,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     bool simple = (h.flags & CMD_CONST_COLOR) && !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&
                   h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255;
     if (!simple) a.info->simple = 0;
+    if (!(h.col[0] <= h.col[3] && h.col[1] <= h.col[3] && h.col[2] <= h.col[3])) a.info->premul_valid = 0;
     atomicMin(&a.info->bx0, (int)h.x0); atomicMin(&a.info->by0, (int)h.y0);
     atomicMax(&a.info->bx1, (int)h.x1); atomicMax(&a.info->by1, (int)h.y1);
   }

@@ -60,6 +60,7 @@ WR_GLOBAL void wr_init_batch_info(BatchInfo* info) {
   info->bx1 = -0x7fffffff; info->by1 = -0x7fffffff;
   info->unsupported = 0;
   info->simple = 1;
+  info->premul_valid = 1;
 }
 
 // Clear (swgl/src/gl.cc:2498-2518 → clear_buffer): fills a rect of a 4-byte or
@@ -634,7 +635,31 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
                  ra.depth_mode == WRCU_DEPTH_OFF;
   ra.fast_eligible = fast_ok ? 1 : 0;
   if (fast_ok) {
-    WR_LAUNCH(wr_raster_solid_premult, grid, WRCU_THREADS, c->stream, ra);
+#ifdef WRCU_HOSTEMU
+    wr_raster_solid_premult(ra);
+#else
+    // persistent CTAs: size the grid so the tile count splits evenly over the
+    // CTAs resident at once (a partial last wave would idle most of the chip)
+    if (c->fast_ctas_per_sm == 0) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wr_raster_solid_premult, FAST_THREADS, 0) != cudaSuccess || nb < 1)
+        nb = 8;
+      c->fast_ctas_per_sm = nb;
+    }
+    const int n_tiles = (int)(grid.x * grid.y);
+    const int sms = c->sm_count > 0 ? c->sm_count : 148;
+    int best_grid = n_tiles;
+    if (n_tiles > sms * c->fast_ctas_per_sm) {
+      double best_eff = 0.0;
+      for (int k = c->fast_ctas_per_sm; k >= max(1, c->fast_ctas_per_sm / 2); k--) {
+        const int slots = sms * k;
+        const int rounds = (n_tiles + slots - 1) / slots;
+        const double eff = (double)n_tiles / ((double)rounds * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_grid = slots; }
+      }
+    }
+    wr_raster_solid_premult<<<best_grid, FAST_THREADS, 0, c->stream>>>(ra);
+#endif
     c->stats.kernel_launches++;
   }
 #define LAUNCH_RASTER(S)                                                         \

@@ -108,6 +108,7 @@ struct wrcu_ctx {
   wrcu_stats stats = {};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int sm_count = 148;
+  int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
 };
 
 int wrcu_fail(wrcu_ctx* c, int code, const char* fmt, ...);
