@@ -246,6 +246,21 @@ int wrcu_texture_device_ptr(wrcu_ctx* ctx, wrcu_tex tex, void** dptr,
 /* The CUDA stream (cudaStream_t) the context queues work on. */
 int wrcu_stream(wrcu_ctx* ctx, void** stream);
 
+/* ---- asynchronous readback (the reference's PBO path) ----------------------- */
+/* Page-locked host memory for uploads/readbacks: create_pbo_with_size /
+ * map_pbo_for_readback (device/gl.rs:3146, 3241).  Buffers from here make
+ * wrcu_texture_upload / wrcu_read_pixels[_async] run at full PCIe rate. */
+int wrcu_host_alloc(wrcu_ctx* ctx, size_t bytes, void** out);
+int wrcu_host_free(wrcu_ctx* ctx, void* ptr);
+/* read_pixels_into_pbo (device/gl.rs:3190): queue a readback of `tex` behind
+ * the draws issued so far and return at once; the copy runs on a second stream,
+ * so it overlaps the following draws (which must target another texture — a
+ * later wrcu_target_bind of `tex` waits for the copy).  `*fence` identifies the
+ * copy; `out` is valid after wrcu_fence_wait(fence) or wrcu_finish. */
+int wrcu_read_pixels_async(wrcu_ctx* ctx, wrcu_tex tex, int x, int y, int w,
+                           int h, void* out, size_t dst_stride, uint64_t* fence);
+int wrcu_fence_wait(wrcu_ctx* ctx, uint64_t fence);
+
 #ifdef __cplusplus
 }
 #endif

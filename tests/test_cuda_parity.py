@@ -263,3 +263,24 @@ def test_brush_blend(seed, variant):
 def test_brush_mix_blend(seed, variant):
     f = scenes.mix_blend_frame(seed=seed, fractional=variant == "fractional")
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+def test_async_readback_matches_sync():
+    """wrcu_read_pixels_async into page-locked memory + fence == wrcu_read_pixels."""
+    import numpy as np
+    from webrender_b200.frame import draw_frame
+    f = scenes.alpha_rects_frame(640, 360, 40, random_rects=True, seed=5, color=None)
+    dev = CudaDevice(0)
+    try:
+        h = draw_frame(dev, f)
+        want = dev.read_pixels(h["target"], 0, 0, 640, 360, 4)
+        buf = dev.host_alloc((360, 640 * 4))
+        buf[:] = 0
+        fence = dev.read_pixels_async(h["target"], 0, 0, 640, 360, buf)
+        # drawing to the same texture again must wait for the copy
+        draw_frame(dev, f, h)
+        dev.fence_wait(fence)
+        assert (buf == want).all()
+        dev.finish()
+    finally:
+        dev.close()

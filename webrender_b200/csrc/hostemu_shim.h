@@ -75,6 +75,7 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = n
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)calloc(n + 64, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }

@@ -170,6 +170,12 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->dev_err) cudaFree(c->dev_err);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->ready_ev);
+    for (int i = 0; i < wrcu_ctx::N_FENCES; i++) cudaEventDestroy(c->fence_ev[i]);
+  }
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -184,7 +190,9 @@ extern "C" const char* wrcu_last_error_string(wrcu_ctx* c) { return c ? c->err :
 static int sync_and_check(wrcu_ctx* c);
 extern "C" int wrcu_finish(wrcu_ctx* c) {
   cudaSetDevice(c->device);
-  return sync_and_check(c);
+  int rc = sync_and_check(c);
+  if (c->copy_stream) WRCU_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  return rc;
 }
 
 extern "C" int wrcu_stream(wrcu_ctx* c, void** stream) {
@@ -342,6 +350,63 @@ extern "C" int wrcu_read_pixels(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, i
   return sync_and_check(c);
 }
 
+// ---- asynchronous readback ---------------------------------------------------------------
+extern "C" int wrcu_host_alloc(wrcu_ctx* c, size_t bytes, void** out) {
+  if (!out || bytes == 0) return wrcu_fail(c, WRCU_ERR_INVALID, "host_alloc: bad arguments");
+  cudaSetDevice(c->device);
+  WRCU_CUDA(c, cudaMallocHost(out, bytes));
+  return WRCU_OK;
+}
+extern "C" int wrcu_host_free(wrcu_ctx* c, void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+  (void)c;
+  return WRCU_OK;
+}
+
+static int wait_fence(wrcu_ctx* c, uint64_t fence, bool on_stream) {
+  if (fence == 0) return WRCU_OK;
+  int slot = (int)(fence % wrcu_ctx::N_FENCES);
+  if (c->fence_id[slot] != fence) return WRCU_OK;  // slot recycled: that copy completed long ago
+  if (on_stream) WRCU_CUDA(c, cudaStreamWaitEvent(c->stream, c->fence_ev[slot], 0));
+  else WRCU_CUDA(c, cudaEventSynchronize(c->fence_ev[slot]));
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_read_pixels_async(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, int h, void* out,
+                                      size_t dst_stride, uint64_t* fence) {
+  WrTexture* t = get_tex(c, id);
+  if (!t || !out || !fence || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "read_pixels_async: bad arguments");
+  cudaSetDevice(c->device);
+  if (!c->copy_stream) {
+    WRCU_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    WRCU_CUDA(c, cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
+    for (int i = 0; i < wrcu_ctx::N_FENCES; i++)
+      WRCU_CUDA(c, cudaEventCreateWithFlags(&c->fence_ev[i], cudaEventDisableTiming));
+  }
+  uint64_t id64 = c->next_fence++;
+  int slot = (int)(id64 % wrcu_ctx::N_FENCES);
+  if (c->fence_id[slot]) WRCU_CUDA(c, cudaEventSynchronize(c->fence_ev[slot]));  // ring wrapped: oldest copy must be done
+  size_t row = (size_t)w * t->bpp;
+  WRCU_CUDA(c, cudaEventRecord(c->ready_ev, c->stream));
+  WRCU_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ready_ev, 0));
+  WRCU_CUDA(c, cudaMemcpy2DAsync(out, dst_stride, t->dptr + (size_t)y * t->pitch + (size_t)x * t->bpp, t->pitch, row, h,
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+  WRCU_CUDA(c, cudaEventRecord(c->fence_ev[slot], c->copy_stream));
+  c->fence_id[slot] = id64;
+  t->pending_read = id64;
+  c->stats.d2h_bytes += row * h;
+  *fence = id64;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_fence_wait(wrcu_ctx* c, uint64_t fence) {
+  cudaSetDevice(c->device);
+  int rc = wait_fence(c, fence, false);
+  if (rc != WRCU_OK) return rc;
+  return WRCU_OK;
+}
+
 // ---- frame ---------------------------------------------------------------------------
 extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null tables");
@@ -393,6 +458,12 @@ extern "C" int wrcu_target_bind(wrcu_ctx* c, wrcu_tex color, wrcu_tex depth, con
     WrTexture* d = get_tex(c, depth);
     if (!d || d->fmt != WRCU_FMT_DEPTH24 || d->w != t->w || d->h != t->h)
       return wrcu_fail(c, WRCU_ERR_INVALID, "target_bind: bad depth target");
+  }
+  if (t->pending_read) {  // an async readback of this texture must finish before it is drawn to again
+    cudaSetDevice(c->device);
+    int rc = wait_fence(c, t->pending_read, true);
+    if (rc != WRCU_OK) return rc;
+    t->pending_read = 0;
   }
   c->color_tex = color;
   c->depth_tex = depth;

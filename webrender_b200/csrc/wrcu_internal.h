@@ -37,6 +37,7 @@ struct WrTexture {
   size_t pitch = 0;
   uint8_t* dptr = nullptr;
   bool live = false;
+  uint64_t pending_read = 0;  // fence of an in-flight async readback of this texture
 };
 
 // Device-side view of a texture (passed by value to kernels).
@@ -108,6 +109,13 @@ struct wrcu_ctx {
   wrcu_stats stats = {};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int sm_count = 148;
+  // asynchronous readback: second stream + a ring of fences
+  static const int N_FENCES = 8;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ready_ev = nullptr;
+  cudaEvent_t fence_ev[N_FENCES] = {};
+  uint64_t fence_id[N_FENCES] = {};
+  uint64_t next_fence = 1;
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
 };
 

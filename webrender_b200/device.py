@@ -141,6 +141,11 @@ class CudaDevice(DeviceBase):
         self.lib.wrcu_texture_device_ptr.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p),
                                                      C.POINTER(C.c_size_t)]
         self.lib.wrcu_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        self.lib.wrcu_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        self.lib.wrcu_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.wrcu_read_pixels_async.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
+                                                    C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+        self.lib.wrcu_fence_wait.argtypes = [C.c_void_p, C.c_uint64]
         ctx = C.c_void_p()
         rc = self.lib.wrcu_ctx_create(device_ordinal, C.byref(ctx))
         if rc != 0:
@@ -149,6 +154,9 @@ class CudaDevice(DeviceBase):
 
     def close(self):
         if getattr(self, "ctx", None):
+            for p in getattr(self, "_pinned", []):
+                self.lib.wrcu_host_free(self.ctx, p)
+            self._pinned = []
             self.lib.wrcu_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -175,6 +183,27 @@ class CudaDevice(DeviceBase):
         p, pitch = C.c_void_p(), C.c_size_t()
         self._check(self.lib.wrcu_texture_device_ptr(self.ctx, tex, C.byref(p), C.byref(pitch)))
         return p.value, pitch.value
+
+    def host_alloc(self, shape, dtype=np.uint8):
+        """Page-locked host array (the PBO analogue) owned by the context."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.wrcu_host_alloc(self.ctx, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p.value)
+        return arr
+
+    def read_pixels_async(self, tex, x, y, w, h, out):
+        """Queue a readback into a (pinned) host array; returns a fence."""
+        f = C.c_uint64(0)
+        self._check(self.lib.wrcu_read_pixels_async(self.ctx, tex, x, y, w, h, out.ctypes.data, out.strides[0],
+                                                    C.byref(f)))
+        return f.value
+
+    def fence_wait(self, fence):
+        self._check(self.lib.wrcu_fence_wait(self.ctx, fence))
 
     def stream(self):
         s = C.c_void_p()
