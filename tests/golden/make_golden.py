@@ -29,6 +29,17 @@ CASES = [
     ("clip_rect_integer", "clip_mask_frame", dict(seed=1)),
     ("clip_rect_fractional", "clip_mask_frame", dict(seed=2, fractional=True)),
     ("clip_rect_scaled", "clip_mask_frame", dict(seed=3, fractional=True, scale=1.25)),
+    # config A: wrench/reftests/aa/rounded-rects.yaml (also checked against the reference's own PNG,
+    # tests/test_golden.py::test_config_a_against_reference_png)
+    ("config_a_rounded_rects", "config_a_frame", dict()),
+    ("image_scaled", "image_frame", dict(seed=2, fractional=True)),
+    ("text_run_fractional", "text_frame", dict(seed=3, width=480, height=270, n_runs=8, glyphs_per_run=20, fractional=True)),
+    ("linear_gradient_alpha", "gradient_frame", dict(seed=2, blend=2)),
+    ("box_shadow_fractional", "box_shadow_frame", dict(seed=2, fractional=True)),
+    ("composite_external", "composite_frame", dict(seed=2, external=True)),
+    ("brush_opacity_scaled", "opacity_frame", dict(seed=2)),
+    ("brush_blend_filters", "blend_frame", dict(seed=1)),
+    ("brush_mix_blend_modes", "mix_blend_frame", dict(seed=2)),
 ]
 
 

@@ -186,7 +186,7 @@ def scale_matrix(s):
 
 
 def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=False, device_pixel_scale=1.0,
-                        filter=abi.LINEAR):
+                        filter=abi.LINEAR, spec=None, surface=(512, 512)):
     """Config A flavour (wrench/reftests/aa/rounded-rects.yaml): solid rects with
     rounded-rect clips drawn the Indirect way (quad.rs:722-792, 239-264):
       pass 0, off-screen colour target: each rect as an untextured Quad with
@@ -197,25 +197,36 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
     from .gpu_types import mask_instance, QF_IS_MASK
     rng = np.random.RandomState(seed)
     t = FrameTables()
-    sw, sh = 512, 512
+    sw, sh = surface
     tile_task = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
     prims, masks_fast, masks_slow, composites = [], [], [], []
     cursor_x, cursor_y, row_h = 0, 0, 0
     s = device_pixel_scale
+    if spec is not None:
+        n_rects = len(spec)
     for i in range(n_rects):
-        w, h = int(rng.randint(40, 220)), int(rng.randint(30, 160))
+        if spec is not None:
+            (sx0, sy0, sx1, sy1), scolor, sradii = spec[i]
+            w, h = int(sx1 - sx0), int(sy1 - sy0)
+        else:
+            w, h = int(rng.randint(40, 220)), int(rng.randint(30, 160))
         if cursor_x + w > sw:
             cursor_x, cursor_y, row_h = 0, cursor_y + row_h, 0
         tx, ty = cursor_x, cursor_y
         cursor_x += w
         row_h = max(row_h, h)
         # device-space rect of the primitive, local = device / scale
-        dx, dy = int(rng.randint(0, width - w)), int(rng.randint(0, height - h))
-        fo = rng.uniform(0, 1, 2) if fractional else (0.0, 0.0)
-        rect = ((dx + fo[0]) / s, (dy + fo[1]) / s, (dx + w - fo[1]) / s, (dy + h - fo[0]) / s)
+        if spec is not None:
+            dx, dy = int(sx0), int(sy0)
+            rect = (float(sx0), float(sy0), float(sx1), float(sy1))
+            color = scolor
+        else:
+            dx, dy = int(rng.randint(0, width - w)), int(rng.randint(0, height - h))
+            fo = rng.uniform(0, 1, 2) if fractional else (0.0, 0.0)
+            rect = ((dx + fo[0]) / s, (dy + fo[1]) / s, (dx + w - fo[1]) / s, (dy + h - fo[0]) / s)
+            a = rng.uniform(0.3, 1.0)
+            color = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (float(a),)
         task = t.add_render_task((float(tx), float(ty), float(tx + w), float(ty + h)), s, (float(dx), float(dy)))
-        a = rng.uniform(0.3, 1.0)
-        color = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (float(a),)
         prim_f = t.add_quad_prim(rect, rect, color)
         prim_i = t.add_quad_header(0, i + 1)
         qi = quad_instance(prim_i, prim_f, QF_APPLY_DEVICE_CLIP, 0, PART_ALL, INVALID_SEGMENT_INDEX, task)
@@ -223,7 +234,17 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
         rw, rh = rect[2] - rect[0], rect[3] - rect[1]
         uniform = i % 2 == 0
         mode = float(i % 5 == 4)
-        if uniform:
+        if spec is not None:
+            mode = 0.0
+            uniform = not isinstance(sradii, (list, tuple))
+        if spec is not None and uniform:
+            r = float(sradii)
+            clip_addr = t.push_gpu_buffer_f([rect, (r, r, r, r), (mode, 0, 0, 0)])
+        elif spec is not None:
+            (tl, tr, bl, br) = sradii   # radii_top = (tl, tr), radii_bottom = (bl, br): ps_quad_mask.glsl:55-60
+            clip_addr = t.push_gpu_buffer_f([rect, (tl[0], tl[1], tr[0], tr[1]), (bl[0], bl[1], br[0], br[1]),
+                                             (mode, 0, 0, 0)])
+        elif uniform:
             r = float(rng.uniform(2, min(rw, rh) / 2)) if fractional else float(rng.randint(2, max(3, int(min(rw, rh) / 2))))
             clip_addr = t.push_gpu_buffer_f([rect, (r, r, r, r), (mode, 0, 0, 0)])
         else:
@@ -764,3 +785,14 @@ def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
            Batch(abi.KIND_BRUSH_MIX_BLEND, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
                  features=abi.FEAT_ALPHA_PASS, color=("backdrop", "surface", ""))]
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def config_a_frame():
+    """Config A: wrench/reftests/aa/rounded-rects.yaml — three solid rects under
+    rounded-rect clips (uniform radius 8; per-corner circular 16/32/48/64;
+    per-corner elliptical), white background, drawn the Indirect way (see
+    rounded_rects_frame) at the size of its reference image (1036x604)."""
+    spec = [((50, 50, 250, 250), (1.0, 0.0, 0.0, 1.0), 8.0),
+            ((270, 50, 470, 250), (0.0, 1.0, 0.0, 1.0), ((16.0, 16.0), (32.0, 32.0), (48.0, 48.0), (64.0, 64.0))),
+            ((490, 50, 990, 550), (0.0, 0.0, 1.0, 1.0), ((32.0, 16.0), (40.0, 24.0), (48.0, 64.0), (52.0, 80.0)))]
+    return rounded_rects_frame(width=1036, height=604, spec=spec, surface=(1024, 512))
