@@ -284,3 +284,30 @@ def test_async_readback_matches_sync():
         dev.finish()
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5, 90.0, 45.0, 180.0, 3.0])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_rotated_brush_solid(rot, seed):
+    """Non-axis-aligned quads through the edge-walk path (CMD_GENERAL)."""
+    f = scenes.brush_solid_frame(seed=seed, rotate=rot, fractional=True, with_masks=seed == 2)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), f"rot {rot}")
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5, 90.0])
+@pytest.mark.parametrize("kind", ["image", "gradient_alpha", "gradient_opaque"])
+def test_rotated_textured(rot, kind):
+    if kind == "image":
+        f = scenes.image_frame(seed=2, rotate=rot, fractional=True, n_opaque=0)
+    elif kind == "gradient_alpha":
+        f = scenes.gradient_frame(seed=2, rotate=rot, fractional=True, blend=abi.BLEND_PREMULTIPLIED_ALPHA)
+    else:
+        f = scenes.gradient_frame(seed=2, rotate=rot)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)
+
+
+def test_rotated_full_size():
+    """A 4K frame of rotated brushes (rows up to 2160: long edge walks)."""
+    f = scenes.brush_solid_frame(width=3840, height=2160, seed=3, rotate=23.0, fractional=True, with_masks=False,
+                                 n_opaque=6, n_alpha=20)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

@@ -170,3 +170,24 @@ def test_brush_blend(seed, variant):
 def test_brush_mix_blend(seed, variant):
     f = scenes.mix_blend_frame(seed=seed, fractional=variant == "fractional")
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5, 90.0, 45.0, 180.0, 3.0])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_rotated_brush_solid(rot, seed):
+    f = scenes.brush_solid_frame(seed=seed, rotate=rot, fractional=True, with_masks=seed == 2)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), f"rot {rot}")
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5, 90.0])
+@pytest.mark.parametrize("kind", ["image", "gradient_alpha", "gradient_opaque"])
+def test_rotated_textured(rot, kind):
+    """Rotated image / gradient brushes: per-row spans from the edge walk, uv rows
+    that change along the span (fallback bilinear filter), AA on all edges."""
+    if kind == "image":
+        f = scenes.image_frame(seed=2, rotate=rot, fractional=True, n_opaque=0)
+    elif kind == "gradient_alpha":
+        f = scenes.gradient_frame(seed=2, rotate=rot, fractional=True, blend=abi.BLEND_PREMULTIPLIED_ALPHA)
+    else:
+        f = scenes.gradient_frame(seed=2, rotate=rot)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)

@@ -171,3 +171,26 @@ def test_brush_blend(seed, variant):
 def test_brush_mix_blend(seed, variant):
     f = scenes.mix_blend_frame(seed=seed, fractional=variant == "fractional")
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5, 90.0, 45.0, 180.0, 3.0])
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("masks", [False, True])
+def test_rotated_brush_solid(rot, seed, masks):
+    """Non-axis-aligned quads: the full edge walk of draw_quad_spans (edge
+    switches at vertices, AA on every edge in the alpha pass, none in the opaque
+    pass), depth and clip masks."""
+    f = scenes.brush_solid_frame(seed=seed, rotate=rot, fractional=True, with_masks=masks)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), f"rot {rot}")
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5, 90.0])
+@pytest.mark.parametrize("kind", ["image", "image_occluded", "gradient_alpha", "gradient_opaque"])
+def test_rotated_textured(rot, kind):
+    if kind.startswith("image"):
+        f = scenes.image_frame(seed=2, rotate=rot, fractional=True, n_opaque=0 if kind == "image" else 8)
+    elif kind == "gradient_alpha":
+        f = scenes.gradient_frame(seed=2, rotate=rot, fractional=True, blend=abi.BLEND_PREMULTIPLIED_ALPHA)
+    else:
+        f = scenes.gradient_frame(seed=2, rotate=rot)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)

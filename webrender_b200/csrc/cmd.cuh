@@ -18,6 +18,7 @@ enum : uint32_t {
   CMD_SUBPIXEL_TEXT = 1u << 8, // swgl_blendSubpixelText override
   CMD_DROP_SHADOW = 1u << 7, // swgl_blendDropShadow override; colour in CmdCold.i[0..1]
   CMD_CONST_COLOR = 1u << 6, // fragment output is the constant colour in CmdHot.col
+  CMD_GENERAL = 1u << 9,    // screen edges not axis-aligned: per-row spans from the edge walk (GenQuad)
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
 };
 
@@ -49,6 +50,22 @@ struct __align__(16) CmdCold {
   float f[8];   // e.g. uv sample bounds
   int32_t i[4];
   float g[40];  // large kind-specific block (rounded-rect clip geometry, ...)
+  // CMD_GENERAL: the quad's screen vertices (interpolants per vertex are then in
+  // i_lt, i_lb, i_rt, i_rb = vertices 0..3), its clip rect, and the edge walk of
+  // draw_quad_spans (rasterize.h:783-1054) recorded as events: from row `row`
+  // on, the l-chain edge is l0->l1 (initialised at row lrow) and the r-chain edge
+  // r0->r1 (initialised at row rrow).
+  float gpx[4], gpy[4];
+  float gclip[4];
+  struct { short row, lrow, rrow; uint8_t l0, l1, r0, r1; } gev[6];
+  int gn_ev, gflipped, gaa_mask, gpad;
+};
+
+// Per-(command,row) state of a general quad, computed by wr_general_row.
+struct GenRow {
+  float lx, rx;                      // left.x / right.x at this row
+  float aa_l0, aa_ls, aa_r0, aa_rs;  // AA ramps of this row
+  int lv0, lv1, lrow, rv0, rv1, rrow;  // (final) left/right edge: vertices and init row
 };
 
 // Per-batch info written by the setup kernel.

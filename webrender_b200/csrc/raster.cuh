@@ -37,6 +37,7 @@ struct RasterArgs {
   int n_gbuf_f;
   const float4* gpu_cache;  // component-transfer tables
   int n_gpu_cache;
+  const GenRow* gen;  // per-thread row state of the current CMD_GENERAL command
 };
 
 #define CHUNK_CMDS 256
@@ -44,18 +45,21 @@ struct RasterArgs {
 // AA weight of pixel x for the current command (DO_AA, blend.h:433-445, with
 // the span set-up of aa_span, rasterize.h:546-557).  Chunks of 4 start at the
 // span start c.x0.
-WRD int wr_aa_weight(const CmdHot& c, const CmdCold& k, int x) {
+WRD int wr_aa_weight(const RasterArgs& a, const CmdHot& c, const CmdCold& k, int x) {
   int j = (x - c.x0) & 3;
   int xc = x - j;
   int opaque = max((int)c.aa_right_start - (int)c.aa_left_end - 3, 0);
   int off = xc - c.aa_left_end;
   if (off >= 0 && off < opaque) return 256;
+  const bool gen = (c.flags & CMD_GENERAL) != 0;
+  const float l0 = gen ? a.gen->aa_l0 : k.aa_l0, ls = gen ? a.gen->aa_ls : k.aa_ls;
+  const float r0 = gen ? a.gen->aa_r0 : k.aa_r0, rs = gen ? a.gen->aa_rs : k.aa_rs;
   float offs = (float)(c.aa_left_end + j);
-  float left = __fadd_rn(k.aa_l0, __fmul_rn(offs, k.aa_ls));
-  float right = __fadd_rn(k.aa_r0, __fmul_rn(offs, k.aa_rs));
+  float left = __fadd_rn(l0, __fmul_rn(offs, ls));
+  float right = __fadd_rn(r0, __fmul_rn(offs, rs));
   float fo = (float)off;
-  float dist = wr_clamp(wr_min(__fadd_rn(left, __fmul_rn(k.aa_ls, fo)),
-                               __fadd_rn(right, __fmul_rn(k.aa_rs, fo))),
+  float dist = wr_clamp(wr_min(__fadd_rn(left, __fmul_rn(ls, fo)),
+                               __fadd_rn(right, __fmul_rn(rs, fo))),
                         0.0f, 256.0f);
   return wr_round_pixel(dist, 1.0f);
 }
@@ -66,8 +70,117 @@ WRD int wr_aa_weight(const CmdHot& c, const CmdCold& k, int x) {
 // (rasterize.h:1003-1017).  wr_row_interp reproduces that running sum exactly:
 // it starts from the Edge constructor's value at the first row and adds the
 // slope (y - y0) times — warp-uniform work, once per (command,row).
+// One edge of the walk at row y: Edge(y_init, p0, p1, interp0, interp1) followed by
+// (y - init row) nextRow() steps (rasterize.h:851-884).
+WRD void wr_gen_edge_x(const CmdCold& k, int v0, int v1, int init_row, int y, float* x, float* slope) {
+  float ys = (float)init_row + 0.5f;
+  float yScale = 1.0f / wr_max(k.gpy[v1] - k.gpy[v0], 1.0f / 256);
+  float xs = (k.gpx[v1] - k.gpx[v0]) * yScale;
+  float xx = k.gpx[v0] + (ys - k.gpy[v0]) * xs;
+  for (int r = init_row; r < y; r++) xx = xx + xs;
+  *x = xx;
+  *slope = xs;
+}
+WRD const float* wr_gen_vertex_interp(const CmdCold& k, int v) {
+  return v == 0 ? k.i_lt : v == 1 ? k.i_lb : v == 2 ? k.i_rt : k.i_rb;
+}
+
+// aa_span + the edge state of draw_quad_spans for row y of a general quad.
+// Fills g and the row's span in `out` (a copy of the hot record); false = empty.
+WRD bool wr_general_row(const CmdCold& k, const CmdHot& c, int y, GenRow& g, CmdHot& out) {
+  int e = 0;
+  for (int i = 1; i < k.gn_ev; i++)
+    if (k.gev[i].row <= y) e = i;
+  const int l0 = k.gev[e].l0, l1 = k.gev[e].l1, r0 = k.gev[e].r0, r1 = k.gev[e].r1;
+  float lcx, lcs, rcx, rcs;  // l-chain / r-chain edge x and slope
+  wr_gen_edge_x(k, l0, l1, k.gev[e].lrow, y, &lcx, &lcs);
+  wr_gen_edge_x(k, r0, r1, k.gev[e].rrow, y, &rcx, &rcs);
+  // edgeMask: Edge(.., edgeIndex = l1i) for the l-chain, r0i for the r-chain
+  int lcm = (k.gaa_mask >> l1) & 1, rcm = (k.gaa_mask >> r0) & 1;
+  float leftx, lefts, rightx, rights;
+  int lmask, rmask;
+  if (k.gflipped) {
+    leftx = rcx; lefts = rcs; lmask = rcm; rightx = lcx; rights = lcs; rmask = lcm;
+    g.lv0 = r0; g.lv1 = r1; g.lrow = k.gev[e].rrow; g.rv0 = l0; g.rv1 = l1; g.rrow = k.gev[e].lrow;
+  } else {
+    leftx = lcx; lefts = lcs; lmask = lcm; rightx = rcx; rights = rcs; rmask = rcm;
+    g.lv0 = l0; g.lv1 = l1; g.lrow = k.gev[e].lrow; g.rv0 = r0; g.rv1 = r1; g.rrow = k.gev[e].rrow;
+  }
+  g.lx = leftx;
+  g.rx = rightx;
+  const float cx0 = k.gclip[0], cx1 = k.gclip[2];
+  float cs0 = wr_clamp(wr_min(wr_min(k.gpx[l0], k.gpx[l1]), wr_min(k.gpx[r0], k.gpx[r1])), cx0, cx1);
+  float cs1 = wr_clamp(wr_max(wr_max(k.gpx[l0], k.gpx[l1]), wr_max(k.gpx[r0], k.gpx[r1])), cx0, cx1);
+  int sx0, sx1;
+  out = c;
+  if (!(c.flags & CMD_AA)) {
+    sx0 = (int)floorf(wr_clamp(leftx, cs0, cs1) + 0.5f);
+    sx1 = (int)floorf(wr_clamp(rightx, cs0, cs1) + 0.5f);
+  } else {
+    int la0, la1, ra0, ra1;
+    if (lmask) {
+      float rad = 0.5f * fabsf(lefts);
+      la0 = (int)floorf(wr_clamp(leftx - rad, cs0, cs1));
+      la1 = (int)ceilf(wr_clamp(leftx + rad, cs0, cs1));
+      float dx = (-1.0f * 256.0f) * (1.0f / sqrtf(1.0f + lefts * lefts));
+      g.aa_l0 = 128.0f + dx * (leftx - 0.5f);
+      g.aa_ls = -dx;
+    } else {
+      la0 = la1 = (int)floorf(wr_clamp(leftx, cs0, cs1) + 0.5f);
+      g.aa_l0 = 256.0f;
+      g.aa_ls = 0.0f;
+    }
+    if (rmask) {
+      float rad = 0.5f * fabsf(rights);
+      ra0 = (int)floorf(wr_clamp(rightx - rad, cs0, cs1));
+      ra1 = (int)ceilf(wr_clamp(rightx + rad, cs0, cs1));
+      float dx = (1.0f * 256.0f) * (1.0f / sqrtf(1.0f + rights * rights));
+      g.aa_r0 = 128.0f + dx * (rightx - 0.5f);
+      g.aa_rs = -dx;
+    } else {
+      ra0 = ra1 = (int)floorf(wr_clamp(rightx, cs0, cs1) + 0.5f);
+      g.aa_r0 = 256.0f;
+      g.aa_rs = 0.0f;
+    }
+    out.aa_left_end = (short)la1;
+    out.aa_right_start = (short)ra0;
+    sx0 = la0;
+    sx1 = ra1;
+  }
+  out.x0 = (short)sx0;
+  out.x1 = (short)sx1;
+  return sx1 > sx0;
+}
+
 template <int N>
-WRD void wr_row_interp(const CmdCold& k, const CmdHot& c, int y, float* o, float* step) {
+WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step) {
+  if (c.flags & CMD_GENERAL) {
+    // left.interp / right.interp of the walk at this row, then the span's start
+    // value and per-pixel step (rasterize.h:1003-1017)
+    const GenRow& g = *a.gen;
+    float stepScale = __fdiv_rn(1.0f, __fsub_rn(g.rx, g.lx));
+    if (!isfinite(stepScale)) stepScale = 0.0f;
+    float x0f = __fsub_rn(__fadd_rn((float)c.x0, 0.5f), g.lx);
+    const float* l0i = wr_gen_vertex_interp(k, g.lv0);
+    const float* l1i = wr_gen_vertex_interp(k, g.lv1);
+    const float* r0i = wr_gen_vertex_interp(k, g.rv0);
+    const float* r1i = wr_gen_vertex_interp(k, g.rv1);
+    float lys = (float)g.lrow + 0.5f, rys = (float)g.rrow + 0.5f;
+    float lsc = 1.0f / wr_max(k.gpy[g.lv1] - k.gpy[g.lv0], 1.0f / 256);
+    float rsc = 1.0f / wr_max(k.gpy[g.rv1] - k.gpy[g.rv0], 1.0f / 256);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float sl = (l1i[i] - l0i[i]) * lsc, sr = (r1i[i] - r0i[i]) * rsc;
+      float li = l0i[i] + (lys - k.gpy[g.lv0]) * sl;
+      float ri = r0i[i] + (rys - k.gpy[g.rv0]) * sr;
+      for (int r = g.lrow; r < y; r++) li = li + sl;
+      for (int r = g.rrow; r < y; r++) ri = ri + sr;
+      float st = (ri - li) * stepScale;
+      step[i] = st;
+      o[i] = li + st * x0f;
+    }
+    return;
+  }
   float y0c = (float)c.y0 + 0.5f;
   float dy = __fsub_rn(y0c, k.yt);
   float stepScale = __fdiv_rn(1.0f, __fsub_rn(k.xr, k.xl));
@@ -157,7 +270,7 @@ struct QuadShader {
     r.tr.body_len = 0;
     if (!(c.flags & CMD_TEXTURED)) return;
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     int len = c.x1 - c.x0;
     int body_len = (rgba && len >= 4 && !(c.flags & CMD_OUT_RRRR)) ? (len & ~3) : 0;
     float u[4], v[4];
@@ -231,7 +344,7 @@ WRD void wr_shade_pixel(const RasterArgs& a, const CmdHot& c, const typename S::
         else src.r = wr_muldiv255(src.r, mk);
       }
       if (c.flags & CMD_AA) {
-        int aa = wr_aa_weight(c, k, xx);
+        int aa = wr_aa_weight(a, c, k, xx);
         if (FMT == WRCU_FMT_RGBA8) src = px_scale256(src, aa);
         else src.r = wr_muldiv256(src.r, aa);
       }
@@ -269,8 +382,16 @@ static void wr_raster(const RasterArgs& a) {
     uint32_t* zrow = a.tgt.depth ? (uint32_t*)((uint8_t*)a.tgt.depth + (size_t)y * a.tgt.depth_pitch) : nullptr;
     const bool use_depth = a.depth_mode != WRCU_DEPTH_OFF && zrow != nullptr;
     for (int i = 0; i < a.n; i++) {
-      const CmdHot c = a.hot[i];
+      CmdHot c = a.hot[i];
       if (y < c.y0 || y >= c.y1) continue;
+      GenRow g;
+      RasterArgs ar = a;
+      ar.gen = &g;
+      if (c.flags & CMD_GENERAL) {
+        const CmdHot c0 = c;
+        if (!wr_general_row(a.cold[c0.cold], c0, y, g, c)) continue;
+      }
+      const RasterArgs& a = ar;  // shadows: the shaders see the row state
       typename S::Row row;
       for (int tx0 = (c.x0 / WRCU_TILE_W) * WRCU_TILE_W; tx0 < c.x1; tx0 += WRCU_TILE_W) {
       S::row_setup(a, c, y, tx0, FMT == WRCU_FMT_RGBA8, row);
@@ -323,6 +444,8 @@ wr_raster(RasterArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
+  GenRow grow;
+  a.gen = &grow;
   uint32_t px[4] = {0, 0, 0, 0};
   uint32_t zb[4] = {0, 0, 0, 0};
   bool loaded = false, dirty = false, zdirty = false;
@@ -356,8 +479,14 @@ wr_raster(RasterArgs a) {
     if (keep) sh[off + __popc(bal & ((1u << lane) - 1u))] = mine;
     __syncthreads();
     for (int i = 0; i < total; i++) {
-      const CmdHot c = sh[i];
+      CmdHot c = sh[i];
       if (!row_ok || y < c.y0 || y >= c.y1) continue;          // warp-uniform
+      if (c.flags & CMD_GENERAL) {
+        // rotated quad: this row's span comes from the edge walk (warp-uniform)
+        const CmdHot c0 = c;
+        if (!wr_general_row(a.cold[c0.cold], c0, y, grow, c)) continue;
+        if (c.x1 <= tx0 || c.x0 >= tx0 + WRCU_TILE_W) continue;
+      }
       if (!loaded) {
         // lazy tile load: first command that touches this row
         loaded = true;
@@ -467,15 +596,17 @@ WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb
       B = make_int4(c.x0, c.x1, c.y0, c.y1);
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    const unsigned balp = __ballot_sync(0xFFFFFFFFu, keep && !A.w);  // partial-cover survivors
     __syncthreads();  // previous chunk's readers are done with fa/fb/wsum
-    if (lane == 0) wsum[warp] = __popc(bal);
+    if (lane == 0) wsum[warp] = __popc(bal) | (__popc(balp) << 16);
     __syncthreads();
-    int off = 0, total = 0;
+    int off = 0, total = 0, partial = 0;
 #pragma unroll
     for (int w = 0; w < FAST_THREADS / 32; w++) {
       const int v = wsum[w];
-      if (w < warp) off += v;
-      total += v;
+      if (w < warp) off += v & 0xFFFF;
+      total += v & 0xFFFF;
+      partial += v >> 16;
     }
     if (keep) {
       const int slot = off + __popc(bal & ((1u << lane) - 1u));
@@ -495,6 +626,16 @@ WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb
       }
     }
     // ---- blend the survivors in batch order ----
+    if (partial == 0) {
+      // every survivor covers the whole tile: no per-command branch at all
+#pragma unroll 4
+      for (int i = 0; i < total; i++) {
+        const uint4 k = fa[i];
+        wr_fast_blend8<VALID>(rb, ga, k.x, k.y, k.z);
+      }
+      dirty = true;
+      continue;
+    }
 #pragma unroll 2
     for (int i = 0; i < total; i++) {
       const uint4 k = fa[i];

@@ -174,9 +174,77 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     } else {
       l0i = r0i = top; l1i = next; r1i = prev;
     }
-    // axis-aligned requirement: both descending edges vertical, same y extent
+    // Screen-axis-aligned quads (both descending edges vertical, same y extent) get
+    // a constant span; anything else keeps the full edge walk of draw_quad_spans.
     if (px[l0i] != px[l1i] || px[r0i] != px[r1i] || py[l0i] != py[r0i] || py[l1i] != py[r1i]) {
-      *unsupported = 1;
+      const bool gaa = (flags & CMD_AA) != 0;
+      const float aaR = gaa ? 0.0f : 0.5f;
+      float gy = floorf(wr_max(wr_min(py[l0i], cy1), cy0) + aaR) + 0.5f;
+      int row = (int)(gy - 0.5f);
+      float gperp = (px[l1i] - px[l0i]) * (py[r1i] - py[r0i]) - (py[l1i] - py[l0i]) * (px[r1i] - px[r0i]);
+      k.gflipped = (px[l0i] > px[r0i] || (px[l0i] == px[r0i] && gperp > 0.0f)) ? 1 : 0;
+      k.gaa_mask = q.aa_edge_mask;
+      for (int i = 0; i < 4; i++) { k.gpx[i] = px[i]; k.gpy[i] = py[i]; }
+      k.gclip[0] = cx0; k.gclip[1] = cy0; k.gclip[2] = cx1; k.gclip[3] = cy1;
+      int gl0 = l0i, gl1 = l1i, gr0 = r0i, gr1 = r1i, lrow = row, rrow = row;
+      int n_ev = 0, first_row = row, last_row = row - 1;
+      bool overflow = false;
+#define WR_ADD_EVENT()                                                                             \
+  do {                                                                                             \
+    if (n_ev < 6) {                                                                                \
+      k.gev[n_ev].row = (short)row; k.gev[n_ev].lrow = (short)lrow; k.gev[n_ev].rrow = (short)rrow; \
+      k.gev[n_ev].l0 = (uint8_t)gl0; k.gev[n_ev].l1 = (uint8_t)gl1;                                \
+      k.gev[n_ev].r0 = (uint8_t)gr0; k.gev[n_ev].r1 = (uint8_t)gr1;                                \
+      n_ev++;                                                                                      \
+    } else overflow = true;                                                                        \
+  } while (0)
+      WR_ADD_EVENT();
+      float checkY = wr_min(wr_min(py[gl1], py[gr1]), cy1);
+      for (int guard = 0; guard < 40000; guard++) {
+        if (gy > checkY) {
+          if (gy > cy1) break;
+          bool changed = false, done = false;
+          if (gy > py[gl1]) {  // STEP_EDGE(l.., NEXT_POINT, r1i)
+            do {
+              gl0 = gl1;
+              gl1 = (gl1 + 1) & 3;
+              if (gl0 == gr1) { done = true; break; }
+            } while (gy > py[gl1]);
+            lrow = row;
+            changed = true;
+          }
+          if (!done && gy > py[gr1]) {  // STEP_EDGE(r.., PREV_POINT, l1i)
+            do {
+              gr0 = gr1;
+              gr1 = (gr1 + 3) & 3;
+              if (gr0 == gl1) { done = true; break; }
+            } while (gy > py[gr1]);
+            rrow = row;
+            changed = true;
+          }
+          if (done) break;
+          checkY = wr_min(ceilf(wr_min(py[gl1], py[gr1]) - aaR), cy1);
+          if (changed) WR_ADD_EVENT();
+        }
+        last_row = row;
+        row++;
+        gy = gy + 1.0f;
+      }
+#undef WR_ADD_EVENT
+      if (overflow) { *unsupported = 1; break; }
+      if (last_row < first_row) break;
+      k.gn_ev = n_ev;
+      float minx = wr_min(wr_min(px[0], px[1]), wr_min(px[2], px[3]));
+      float maxx = wr_max(wr_max(px[0], px[1]), wr_max(px[2], px[3]));
+      int gx0 = (int)floorf(wr_clamp(minx, cx0, cx1)), gx1 = (int)ceilf(wr_clamp(maxx, cx0, cx1));
+      if (gx1 <= gx0) break;
+      h.x0 = (short)gx0; h.x1 = (short)gx1; h.y0 = (short)first_row; h.y1 = (short)(last_row + 1);
+      h.flags = flags | CMD_GENERAL;
+      for (int i = 0; i < WR_NI; i++) {
+        k.i_lt[i] = q.interp[0][i]; k.i_lb[i] = q.interp[1][i];
+        k.i_rt[i] = q.interp[2][i]; k.i_rb[i] = q.interp[3][i];
+      }
+      ok = true;
       break;
     }
     float perp = (px[l1i] - px[l0i]) * (py[r1i] - py[r0i]) - (py[l1i] - py[l0i]) * (px[r1i] - px[r0i]);
@@ -252,7 +320,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
   } while (0);
   a.hot[idx] = h;
   if (ok) {
-    bool simple = (h.flags & CMD_CONST_COLOR) && !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR)) &&
+    bool simple = (h.flags & CMD_CONST_COLOR) && !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR | CMD_GENERAL)) &&
                   h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255;
     if (!simple) a.info->simple = 0;
     if (!(h.col[0] <= h.col[3] && h.col[1] <= h.col[3] && h.col[2] <= h.col[3])) a.info->premul_valid = 0;

@@ -107,7 +107,7 @@ struct BlendShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     r.pd = (1.0f - k.f[5]) * k.f[4] + k.f[5];
     r.kb = wr_chunk_base<2>(r.o, r.step, c, tx0, r.base);
   }

@@ -124,7 +124,7 @@ struct BoxShadowShader {
 
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& cm, int y, int tx0, bool rgba, Row& r) {
     const CmdCold& k = a.cold[cm.cold];
-    wr_row_interp<6>(k, cm, y, r.L0, r.step);
+    wr_row_interp<6>(a, k, cm, y, r.L0, r.step);
     int len = cm.x1 - cm.x0;
     r.body_len = (!rgba && len >= 4) ? (len & ~3) : 0;
     r.wneg = false;

@@ -68,7 +68,7 @@ struct ClipRectShader {
     const CmdCold& k = a.cold[c.cold];
     r.g = k.g;
     // interpolants at the span start (exact running sums of the edge walk)
-    wr_row_interp<4>(k, c, y, r.L0, r.step);
+    wr_row_interp<4>(a, k, c, y, r.L0, r.step);
     int len = c.x1 - c.x0;
     r.body_len = (!rgba && len >= 4) ? (len & ~3) : 0;
     r.span_ok = false;

@@ -14,7 +14,7 @@ struct CompositeShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     int len = c.x1 - c.x0;
     int body_len = (rgba && len >= 4) ? (len & ~3) : 0;
     float u[4], v[4];

@@ -220,7 +220,7 @@ struct GradientShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     int len = c.x1 - c.x0;
     r.body_len = (rgba && len >= 4 && k.i[1] != 0) ? (len & ~3) : 0;
     r.seg_done = 0;

@@ -15,7 +15,7 @@ struct ImageShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     // mix(gl_FragCoord.w, 1.0, v_perspective.x) = (1 - w) * p + w
     r.pd = (1.0f - k.f[7]) * k.f[6] + k.f[7];
     int len = c.x1 - c.x0;

@@ -80,7 +80,7 @@ struct MixBlendShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<4>(k, c, y, r.o, r.step);
+    wr_row_interp<4>(a, k, c, y, r.o, r.step);
     r.pd = (1.0f - k.g[1]) * k.g[0] + k.g[1];
     r.kb = wr_chunk_base<4>(r.o, r.step, c, tx0, r.base);
   }

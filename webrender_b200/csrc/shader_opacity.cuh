@@ -14,7 +14,7 @@ struct OpacityShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     r.pd = (1.0f - k.f[6]) * k.f[5] + k.f[6];
     int len = c.x1 - c.x0;
     int body_len = (rgba && len >= 4) ? (len & ~3) : 0;

@@ -16,7 +16,7 @@ struct QuadMaskShader {
     const CmdCold& k = a.cold[c.cold];
     r.g = k.g;
     float o[4];
-    wr_row_interp<4>(k, c, y, o, r.step);
+    wr_row_interp<4>(a, k, c, y, o, r.step);
     r.kb = wr_chunk_base<4>(o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs&, const CmdHot& c, const Row& r, int x, int, bool) {

@@ -12,7 +12,7 @@ struct TextShader {
   };
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool rgba, Row& r) {
     const CmdCold& k = a.cold[c.cold];
-    wr_row_interp<2>(k, c, y, r.o, r.step);
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
     int len = c.x1 - c.x0;
     bool span_ok = k.g[4] == 0.0f || k.g[4] == 1.0f;  // swgl_drawSpanRGBA8 guard on v_mask_swizzle.x
     int body_len = (rgba && len >= 4 && span_ok) ? (len & ~3) : 0;

@@ -75,8 +75,19 @@ def _rand_rect(rng, width, height, min_size=8, max_size=None, integer=True):
             float(np.float32(x0 + w + fy)), float(np.float32(y0 + h + fx)))
 
 
+def rotation_matrix(deg, cx, cy, sx=1.0, sy=1.0):
+    """2D rotation by `deg` about (cx, cy), optionally with non-uniform scale, as a 4x4."""
+    a = np.deg2rad(deg)
+    c, s = float(np.cos(a)), float(np.sin(a))
+    m = np.eye(4, dtype=np.float64)
+    m[0, 0], m[0, 1], m[1, 0], m[1, 1] = c * sx, -s * sy, s * sx, c * sy
+    m[0, 3] = cx - (m[0, 0] * cx + m[0, 1] * cy)
+    m[1, 3] = cy - (m[1, 0] * cx + m[1, 1] * cy)
+    return m.astype(np.float32)
+
+
 def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, with_masks=True,
-                      fractional=False, force_aa=False, device_pixel_scale=1.0):
+                      fractional=False, force_aa=False, device_pixel_scale=1.0, rotate=None):
     """Brush(Solid) batches the way draw_alpha_batch_container issues them
     (renderer/mod.rs:2804-2969): an opaque batch front-to-back with depth
     LEQUAL + write, then an alpha batch with premultiplied blending, depth test
@@ -91,11 +102,16 @@ def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, wi
     mask[:, rng.randint(0, mw, 40)] = 0
     z = 1
     opaque, alpha = [], []
+    # a rotated (non-axis-aligned) spatial node: transform id carries the "complex" bit
+    # (TransformPaletteId, gpu_types.rs:730-760), which turns edge AA on (brush.glsl:118-134)
+    xf = 0
+    if rotate is not None:
+        xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0, 1.0, 0.9), axis_aligned=False)
 
     def add(rect, clip_rect, color, opacity, clip_task, flags=0, edge=0):
         nonlocal z
         addr = t.push_gpu_cache([color])
-        hdr = t.add_prim_header(rect, clip_rect, z, addr, 0, pic, (int(opacity * 65535), 0, 0, 0))
+        hdr = t.add_prim_header(rect, clip_rect, z, addr, xf, pic, (int(opacity * 65535), 0, 0, 0))
         z += 1
         return brush_instance(hdr, clip_task, 0xFFFF, edge, flags, 0)
 
@@ -273,7 +289,7 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
 
 
 def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=abi.LINEAR, one_to_one=False,
-                fractional=False):
+                fractional=False, rotate=None):
     """Brush(Image) batches: an opaque batch (depth write, blending off) and an
     alpha batch (premultiplied over, depth test) sampling one RGBA8 atlas, with
     colour modes Image / ColorBitmap / Alpha(drop-shadow override), 1:1 and
@@ -289,6 +305,9 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
     atlas[..., :3] = (atlas[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)
     z = 1
     opaque, alpha = [], []
+    xf = 0
+    if rotate is not None:
+        xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0, 0.95, 1.0), axis_aligned=False)
 
     def add(rect, uv, color, color_mode, opacity, flags=0, segment=None, stretch=(-1.0, -1.0)):
         nonlocal z
@@ -299,7 +318,7 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
             seg_index = 0
         addr = t.push_gpu_cache(blocks)
         res = t.push_gpu_cache([uv, (0.0, 0.0, 0.0, 0.0)])
-        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic,
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), z, addr, xf, pic,
                                 (color_mode | (1 << 16), 0, int(opacity * 65535), 0))
         z += 1
         return brush_instance(hdr, CLIP_TASK_EMPTY, seg_index, 0, flags, res)
@@ -425,7 +444,7 @@ def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atla
 
 
 def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, full_frame=False, repeat=False,
-                   blend=abi.BLEND_NONE):
+                   blend=abi.BLEND_NONE, rotate=None):
     """Config D flavour (wrench/benchmarks/aligned-gradient.yaml / unaligned-gradient.yaml):
     Brush(LinearGradient) instances; under is_software non-tiled linear gradients
     stay uncached brushes (scene_building.rs:3392-3396).  Each has its own
@@ -435,6 +454,9 @@ def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, fu
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
     inst = []
+    gxf = 0
+    if rotate is not None:
+        gxf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0), axis_aligned=False)
     for i in range(n_grad):
         if full_frame:
             r = (0.0, 0.0, float(width), float(height))
@@ -459,7 +481,7 @@ def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, fu
         stretch = (rw, rh) if not repeat else (rw / 2.5, rh / 1.5)
         addr = t.push_gpu_cache([(start[0], start[1], end[0], end[1]),
                                  (1.0 if (repeat and i % 2) else 0.0, stretch[0], stretch[1], 0.0)])
-        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, addr, 0, pic, (lut, 0, 0, 0))
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, addr, gxf, pic, (lut, 0, 0, 0))
         inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
     textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
     feats = abi.FEAT_ALPHA_PASS if blend != abi.BLEND_NONE else 0
