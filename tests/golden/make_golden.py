@@ -32,7 +32,8 @@ CASES = [
     # config A: wrench/reftests/aa/rounded-rects.yaml (also checked against the reference's own PNG,
     # tests/test_golden.py::test_config_a_against_reference_png)
     ("config_a_rounded_rects", "config_a_frame", dict()),
-    ("image_scaled", "image_frame", dict(seed=2, fractional=True)),
+    ("image_scaled", "image_frame", dict(seed=2, fractional=True, n_opaque=0)),
+    ("image_one_to_one_depth", "image_frame", dict(seed=3, one_to_one=True)),
     ("text_run_fractional", "text_frame", dict(seed=3, width=480, height=270, n_runs=8, glyphs_per_run=20, fractional=True)),
     ("linear_gradient_alpha", "gradient_frame", dict(seed=2, blend=2)),
     ("box_shadow_fractional", "box_shadow_frame", dict(seed=2, fractional=True)),
