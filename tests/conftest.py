@@ -17,4 +17,5 @@ def _built():
     """Build the checker libs (and the CUDA lib if missing) once per session."""
     import __graft_entry__ as g
     g.build_cuda()      # no-op when libwrcu.so is newer than its sources
+    g.build_host()
     g.build_oracle()

@@ -1,0 +1,166 @@
+// wr_renderer.h — host-side mirror of the reference's frame-draw driver
+// (webrender/src/renderer/mod.rs) above the wrcu C ABI.
+//
+// The reference's `Renderer` is Rust; there is no Rust toolchain in this image,
+// so the same operator interface is restated in C++: same type and method names,
+// same argument meaning, same error behaviour (sticky GL-style errors polled by
+// check_gl_errors, mod.rs:1992).  Only the members the draw path reads are
+// mirrored; everything is plain data so a binding can fill it directly.
+#pragma once
+#include <stdint.h>
+
+#include <map>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../../include/wrcu.h"
+
+namespace wr {
+
+struct DeviceIntRect { int32_t x0, y0, x1, y1; };  // min/max corners (units.rs)
+
+// internal_types.rs BlendMode → the GL state set by set_blend_mode_* (device/gl.rs:3901-4017)
+enum class BlendMode {
+  None, Alpha, PremultipliedAlpha, PremultipliedDestOut, SubpixelDualSource, Advanced, MultiplyDualSource,
+  Screen, Exclusion, PlusLighter,
+};
+enum class MixBlendMode {  // api/src/display_item.rs:1251-1270 (only used with BlendMode::Advanced)
+  Normal, Multiply, Screen, Overlay, Darken, Lighten, ColorDodge, ColorBurn, HardLight, SoftLight, Difference,
+  Exclusion, Hue, Saturation, Color, Luminosity, PlusLighter,
+};
+
+// batch.rs:56-130
+enum class BatchKind {
+  QuadColorOrTexture, QuadMask, BrushSolid, BrushImage, BrushBlend, BrushMixBlend, BrushLinearGradient,
+  BrushOpacity, TextRun,
+};
+// batch.rs BatchFeatures / shade.rs feature strings
+enum BatchFeatures : uint32_t {
+  ALPHA_PASS = WRCU_FEAT_ALPHA_PASS, ANTIALIASING = WRCU_FEAT_ANTIALIASING, REPETITION = WRCU_FEAT_REPETITION,
+  DUAL_SOURCE_BLENDING = WRCU_FEAT_DUAL_SOURCE_BLENDING, ADVANCED_BLEND = WRCU_FEAT_ADVANCED_BLEND,
+  FAST_PATH = WRCU_FEAT_FAST_PATH, TEXTURE_2D = WRCU_FEAT_TEXTURE_2D,
+};
+
+struct BatchTextures {  // batch.rs:150-230: input colours + clip mask
+  wrcu_tex colors[3] = {0, 0, 0};
+  wrcu_tex clip_mask = 0;
+  static BatchTextures empty() { return BatchTextures(); }
+};
+struct BatchKey {  // batch.rs:233-237
+  BatchKind kind = BatchKind::BrushSolid;
+  BlendMode blend_mode = BlendMode::None;
+  MixBlendMode advanced_mode = MixBlendMode::Normal;
+  BatchTextures textures;
+};
+struct PrimitiveInstanceData { int32_t data[4]; };  // gpu_types.rs:254-256
+struct MaskInstance { int32_t prim[4]; int32_t clip[4]; };  // gpu_types.rs:614-624
+struct PrimitiveBatch {  // batch.rs:504-508
+  BatchKey key;
+  std::vector<uint8_t> instances;  // PrimitiveInstanceData (16 B) or MaskInstance (32 B) records
+  size_t instance_stride = 16;
+  uint32_t features = 0;
+};
+struct AlphaBatchContainer {  // batch.rs:549-558
+  std::vector<PrimitiveBatch> opaque_batches;  // in batch order; drawn reversed (front to back)
+  std::vector<PrimitiveBatch> alpha_batches;
+  std::optional<DeviceIntRect> task_scissor_rect;
+};
+
+// batch.rs:3596-3606
+struct ClipBatchList {
+  std::vector<uint8_t> slow_rectangles, fast_rectangles;  // ClipMaskInstanceRect, 200 B each
+  std::map<wrcu_tex, std::vector<uint8_t>> box_shadows;    // ClipMaskInstanceBoxShadow, 84 B each, per source texture
+};
+struct ClipBatcher { ClipBatchList primary_clips, secondary_clips; };
+
+struct PictureCacheTarget {  // render_target.rs:707-713
+  wrcu_tex surface = 0, depth = 0;
+  int32_t width = 0, height = 0;
+  AlphaBatchContainer alpha_batch_container;
+  std::optional<float> clear_depth;
+  bool has_clear_color = false;
+  float clear_color[4] = {0, 0, 0, 0};
+  DeviceIntRect dirty_rect = {0, 0, 0, 0};
+};
+struct ColorRenderTarget {  // render_target.rs:215-238 (members the path reads)
+  wrcu_tex texture = 0, depth = 0;
+  int32_t width = 0, height = 0;
+  std::vector<AlphaBatchContainer> alpha_batch_containers;
+  std::vector<PrimitiveBatch> prim_batches;  // quad prims into off-screen tasks (handle_prims, mod.rs:2199), blend off
+  std::vector<PrimitiveBatch> mask_batches;  // ps_quad_mask multiplied in (handle_clips, mod.rs:2278)
+  std::vector<DeviceIntRect> clears;         // cleared to transparent black
+};
+struct AlphaRenderTarget {  // render_target.rs:522-532
+  wrcu_tex texture = 0;
+  int32_t width = 0, height = 0;
+  ClipBatcher clip_batcher;
+  std::vector<DeviceIntRect> zero_clears, one_clears;
+};
+struct RenderPass {  // render_task_graph.rs:854-861
+  std::vector<AlphaRenderTarget> alpha;
+  std::vector<ColorRenderTarget> color;
+  std::vector<PictureCacheTarget> picture_cache;
+};
+
+// composite.rs: the tiles composite_simple draws
+struct CompositeInstance { float v[30]; };  // gpu_types.rs:288-310, 120 B
+enum class CompositeTileKind { Opaque, Clear, Alpha };
+struct CompositeTile {
+  CompositeTileKind kind = CompositeTileKind::Opaque;
+  wrcu_tex texture = 0;   // picture-cache texture, external surface, or the 1x1 dummy
+  CompositeInstance instance;
+  bool fast_path = false; // NO_UV_CLAMP | NO_COLOR_MODULATION (composite.rs get_rgb_features)
+};
+struct CompositeState {
+  std::vector<CompositeTile> tiles;  // in z order (back to front)
+  bool has_clear_color = true;
+  float clear_color[4] = {0, 0, 0, 0};
+};
+
+struct Frame {  // frame_builder.rs:1129 (members the path reads)
+  wrcu_frame_tables tables = {};
+  std::vector<RenderPass> passes;
+  CompositeState composite_state;
+  wrcu_tex framebuffer = 0;  // DrawTarget::Default stand-in
+  int32_t fb_width = 0, fb_height = 0;
+  bool present = false;      // run composite_simple
+};
+
+enum class RendererError { None, Shader, Thread, MaxTextureSize, SoftwareRasterizer, OutOfMemory };  // mod.rs:5700-5720
+
+struct RendererStats {  // mod.rs RendererStats
+  size_t total_draw_calls = 0, alpha_target_count = 0, color_target_count = 0;
+};
+
+class Renderer {
+ public:
+  explicit Renderer(wrcu_ctx* device) : device(device) {}
+  // Renderer::render → render_impl → draw_frame (mod.rs:1241, 1441, 4525)
+  RendererError render(const Frame& frame, RendererStats* stats);
+
+  void draw_frame(const Frame& frame, RendererStats& stats);
+  void draw_picture_cache_target(const PictureCacheTarget& target, RendererStats& stats);         // mod.rs:2669
+  void draw_color_target(const ColorRenderTarget& target, RendererStats& stats);                  // mod.rs:3486
+  void draw_alpha_target(const AlphaRenderTarget& target, RendererStats& stats);                  // mod.rs:3754
+  void draw_alpha_batch_container(const AlphaBatchContainer& c, bool has_depth, RendererStats& stats);  // mod.rs:2804
+  void draw_clip_batch_list(const ClipBatchList& list, int blend, RendererStats& stats);          // mod.rs:3695
+  void composite_simple(const Frame& frame, RendererStats& stats);                                // mod.rs:3340
+  void draw_tile_list(const std::vector<const CompositeTile*>& tiles, int blend, RendererStats& stats);  // mod.rs:3126
+  // draw_instanced_batch<T> (mod.rs:2022-2065)
+  void draw_instanced_batch(int kind, uint32_t features, const void* instances, size_t stride, size_t n,
+                            const BatchTextures& textures, RendererStats& stats);
+  RendererError check_gl_errors();  // mod.rs:1992
+  std::vector<std::string> renderer_errors;
+
+ private:
+  void bind_draw_target(wrcu_tex color, wrcu_tex depth, int w, int h);
+  wrcu_ctx* device;
+  wrcu_draw_state state = {};
+  int failed = 0;
+};
+
+int blend_key(BlendMode mode, MixBlendMode advanced);  // set_blend_mode_* → SWGL blend key
+int batch_kind_to_wrcu(BatchKind kind);                // Shaders::get (shade.rs:1206-1305)
+
+}  // namespace wr
