@@ -20,6 +20,7 @@
 #include "sample.cuh"
 #include "texspan.cuh"
 #include "wrcu_internal.h"
+#include "repeat_add.cuh"
 
 struct RasterArgs {
   TargetDev tgt;
@@ -77,7 +78,7 @@ WRD void wr_gen_edge_x(const CmdCold& k, int v0, int v1, int init_row, int y, fl
   float yScale = 1.0f / wr_max(k.gpy[v1] - k.gpy[v0], 1.0f / 256);
   float xs = (k.gpx[v1] - k.gpx[v0]) * yScale;
   float xx = k.gpx[v0] + (ys - k.gpy[v0]) * xs;
-  for (int r = init_row; r < y; r++) xx = xx + xs;
+  xx = wr_repeat_add(xx, xs, y - init_row);
   *x = xx;
   *slope = xs;
 }
@@ -173,8 +174,8 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
       float sl = (l1i[i] - l0i[i]) * lsc, sr = (r1i[i] - r0i[i]) * rsc;
       float li = l0i[i] + (lys - k.gpy[g.lv0]) * sl;
       float ri = r0i[i] + (rys - k.gpy[g.rv0]) * sr;
-      for (int r = g.lrow; r < y; r++) li = li + sl;
-      for (int r = g.rrow; r < y; r++) ri = ri + sr;
+      li = wr_repeat_add(li, sl, y - g.lrow);
+      ri = wr_repeat_add(ri, sr, y - g.rrow);
       float st = (ri - li) * stepScale;
       step[i] = st;
       o[i] = li + st * x0f;
@@ -193,10 +194,8 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
     float sr = __fmul_rn(__fsub_rn(k.i_rb[i], k.i_rt[i]), k.yscale);
     float li = __fadd_rn(k.i_lt[i], __fmul_rn(dy, sl));
     float ri = __fadd_rn(k.i_rt[i], __fmul_rn(dy, sr));
-    for (int r = 0; r < rows; r++) {
-      li = __fadd_rn(li, sl);
-      ri = __fadd_rn(ri, sr);
-    }
+    li = wr_repeat_add(li, sl, rows);
+    ri = wr_repeat_add(ri, sr, rows);
     float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
     step[i] = st;
     o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
@@ -237,7 +236,7 @@ WRD int wr_chunk_base(const float* o, const float* step, const CmdHot& c, int tx
       // init_interp: lane j of chunk 0 = lane j-1 + step (glsl.h:3083-3088);
       // every later chunk adds interp_step to each lane
       float l = v;
-      for (int s = 0; s < kb; s++) l = __fadd_rn(l, is);
+      l = wr_repeat_add(l, is, kb);
       base[j][i] = l;
       v = __fadd_rn(v, step[i]);
     }

@@ -19,6 +19,7 @@
 #pragma once
 #include "blend.cuh"
 #include "sample.cuh"
+#include "repeat_add.cuh"
 
 enum { TEX_NONE = 0, TEX_LINEAR = 1, TEX_NEAREST_FAST = 2, TEX_NEAREST_FALLBACK = 3, TEX_LINEAR_R8 = 4 };
 enum { LF_NEAREST = 0, LF_FALLBACK = 1, LF_UPSCALE = 2, LF_FAST = 3, LF_DOWNSCALE = 4 };
@@ -71,7 +72,7 @@ WRD int wr_needs_texture_linear(const TexView& t, float u0, float u1, float v0, 
 WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
   for (int j = 0; j < 4; j++) {
     float v = start[j];
-    for (int s = 0; s < kb; s++) v = v + step;
+    v = wr_repeat_add(v, step, kb);
     out[j] = v;
   }
 }
