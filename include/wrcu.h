@@ -88,7 +88,9 @@ enum {
   WRCU_FEAT_DUAL_SOURCE_BLENDING = 1u << 4,
   WRCU_FEAT_ADVANCED_BLEND = 1u << 5,
   WRCU_FEAT_GLYPH_TRANSFORM = 1u << 6,
-  WRCU_FEAT_TEXTURE_2D = 1u << 7
+  WRCU_FEAT_TEXTURE_2D = 1u << 7,
+  WRCU_FEAT_ALPHA_TARGET = 1u << 8, /* cs_blur into an R8 target    */
+  WRCU_FEAT_COLOR_TARGET = 1u << 9  /* cs_blur into an RGBA8 target */
 };
 
 /* Blend keys: exactly the set the reference's blend stage implements

@@ -17,6 +17,7 @@
 #include "ps_clear.h"
 #include "brush_blend.h"
 #include "brush_mix_blend.h"
+#include "cs_blur.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -46,5 +47,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "brush_blend ALPHA_PASS")) return brush_blend_ALPHA_PASS_program::loader;
   if (!strcmp(name, "brush_mix_blend")) return brush_mix_blend_program::loader;
   if (!strcmp(name, "brush_mix_blend ALPHA_PASS")) return brush_mix_blend_ALPHA_PASS_program::loader;
+  if (!strcmp(name, "cs_blur ALPHA_TARGET")) return cs_blur_ALPHA_TARGET_program::loader;
+  if (!strcmp(name, "cs_blur COLOR_TARGET")) return cs_blur_COLOR_TARGET_program::loader;
   return nullptr;
 }

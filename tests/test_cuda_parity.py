@@ -311,3 +311,10 @@ def test_rotated_full_size():
     f = scenes.brush_solid_frame(width=3840, height=2160, seed=3, rotate=23.0, fractional=True, with_masks=False,
                                  n_opaque=6, n_alpha=20)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("color", [False, True])
+def test_cs_blur(seed, color):
+    f = scenes.blur_frame(seed=seed, color=color)
+    assert_same(render(CudaDevice, f, ["mid", "target"]), render(OracleDevice, f, ["mid", "target"]))

@@ -191,3 +191,10 @@ def test_rotated_textured(rot, kind):
     else:
         f = scenes.gradient_frame(seed=2, rotate=rot)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("color", [False, True])
+def test_cs_blur(seed, color):
+    f = scenes.blur_frame(seed=seed, color=color)
+    assert_same(render(EmuDevice, f, ["mid", "target"]), render(OracleDevice, f, ["mid", "target"]))

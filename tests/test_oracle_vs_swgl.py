@@ -194,3 +194,12 @@ def test_rotated_textured(rot, kind):
     else:
         f = scenes.gradient_frame(seed=2, rotate=rot)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("color", [False, True])
+def test_cs_blur(seed, color):
+    """cs_blur ALPHA_TARGET / COLOR_TARGET: vertical then horizontal pass, clamped
+    sampling at region edges, zero radius, 16-bit saturating accumulation."""
+    f = scenes.blur_frame(seed=seed, color=color)
+    assert_same(render(SwglDevice, f, ["mid", "target"]), render(OracleDevice, f, ["mid", "target"]))

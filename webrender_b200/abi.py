@@ -48,10 +48,14 @@ FEAT_DUAL_SOURCE_BLENDING = 1 << 4
 FEAT_ADVANCED_BLEND = 1 << 5
 FEAT_GLYPH_TRANSFORM = 1 << 6
 FEAT_TEXTURE_2D = 1 << 7
+FEAT_ALPHA_TARGET = 1 << 8
+FEAT_COLOR_TARGET = 1 << 9
 FEATURE_NAMES = [
     (FEAT_ADVANCED_BLEND, "ADVANCED_BLEND"),
     (FEAT_ALPHA_PASS, "ALPHA_PASS"),
+    (FEAT_ALPHA_TARGET, "ALPHA_TARGET"),
     (FEAT_ANTIALIASING, "ANTIALIASING"),
+    (FEAT_COLOR_TARGET, "COLOR_TARGET"),
     (FEAT_DUAL_SOURCE_BLENDING, "DUAL_SOURCE_BLENDING"),
     (FEAT_FAST_PATH, "FAST_PATH"),
     (FEAT_GLYPH_TRANSFORM, "GLYPH_TRANSFORM"),

@@ -16,6 +16,7 @@
 #include "shader_opacity.cuh"
 #include "shader_blend.cuh"
 #include "shader_mix_blend.cuh"
+#include "shader_blur.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -639,6 +640,14 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_BLUR:
+      if (stride < 24) return wrcu_fail(c, WRCU_ERR_INVALID, "BlurInstance stride < 24");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "cs_blur without sColor0");
+      if (!(features & (WRCU_FEAT_ALPHA_TARGET | WRCU_FEAT_COLOR_TARGET)))
+        return wrcu_fail(c, WRCU_ERR_INVALID, "cs_blur needs ALPHA_TARGET or COLOR_TARGET");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_blur, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_BRUSH_MIX_BLEND:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr || !sa.color1.ptr)
@@ -753,6 +762,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
     case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
     case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER(MixBlendShader); break;
+    case WRCU_KIND_BLUR: LAUNCH_RASTER(BlurShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER
@@ -775,7 +785,8 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"ALPHA_PASS", WRCU_FEAT_ALPHA_PASS}, {"FAST_PATH", WRCU_FEAT_FAST_PATH},
       {"ANTIALIASING", WRCU_FEAT_ANTIALIASING}, {"REPETITION", WRCU_FEAT_REPETITION},
       {"DUAL_SOURCE_BLENDING", WRCU_FEAT_DUAL_SOURCE_BLENDING}, {"ADVANCED_BLEND", WRCU_FEAT_ADVANCED_BLEND},
-      {"GLYPH_TRANSFORM", WRCU_FEAT_GLYPH_TRANSFORM}, {"TEXTURE_2D", WRCU_FEAT_TEXTURE_2D}};
+      {"GLYPH_TRANSFORM", WRCU_FEAT_GLYPH_TRANSFORM}, {"TEXTURE_2D", WRCU_FEAT_TEXTURE_2D},
+      {"ALPHA_TARGET", WRCU_FEAT_ALPHA_TARGET}, {"COLOR_TARGET", WRCU_FEAT_COLOR_TARGET}};
   const char* sp = strchr(key, ' ');
   size_t nlen = sp ? (size_t)(sp - key) : strlen(key);
   *kind = 0;

@@ -274,3 +274,13 @@ def composite_instance(rect, clip_rect, color=(1.0, 1.0, 1.0, 1.0), uv_rect=(0.0
     buf[24:28] = uv_rect
     buf[28:30] = (float(flip[0]), float(flip[1]))
     return buf.view(np.uint8).copy()
+
+
+def blur_instance(task_address, src_task_address, direction, std_deviation, blur_region):
+    """BlurInstance, 24 bytes (gpu_types.rs:112-118): direction 0 = horizontal, 1 = vertical."""
+    buf = np.zeros(6, dtype=np.float32)
+    ints = buf.view(np.int32)
+    ints[0], ints[1], ints[2] = task_address, src_task_address, direction
+    buf[3] = std_deviation
+    buf[4:6] = blur_region
+    return buf.view(np.uint8).copy()

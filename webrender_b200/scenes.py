@@ -818,3 +818,39 @@ def config_a_frame():
             ((270, 50, 470, 250), (0.0, 1.0, 0.0, 1.0), ((16.0, 16.0), (32.0, 32.0), (48.0, 48.0), (64.0, 64.0))),
             ((490, 50, 990, 550), (0.0, 0.0, 1.0, 1.0), ((32.0, 16.0), (40.0, 24.0), (48.0, 64.0), (52.0, 80.0)))]
     return rounded_rects_frame(width=1036, height=604, spec=spec, surface=(1024, 512))
+
+
+def blur_frame(width=384, height=256, seed=1, color=False, sigmas=(1.0, 2.5, 6.0, 0.0)):
+    """cs_blur the way draw_blurs issues it (renderer/mod.rs:3675-3692; render
+    tasks from RenderTask::new_blur, render_task.rs): for each source region a
+    vertical pass into an intermediate target and a horizontal pass from it into
+    the final target — ALPHA_TARGET (R8 box-shadow masks) or COLOR_TARGET (RGBA8
+    filter blurs).  Regions sit at different offsets so the clamped sampling at
+    the region edges is exercised."""
+    from .gpu_types import blur_instance
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    fmt = abi.FMT_RGBA8 if color else abi.FMT_R8
+    sw, sh = 256, 192
+    src = tile_texture(sw, sh, seed + 5, opaque=False) if color else shadow_mask_texture(256, seed + 5)[:sh, :sw].copy()
+    vert, hori = [], []
+    x_cursor = 0
+    for i, sigma in enumerate(sigmas):
+        w, h = int(rng.randint(40, 90)), int(rng.randint(30, 120))
+        sx, sy = int(rng.randint(0, sw - w)), int(rng.randint(0, sh - h))
+        src_task = t.add_render_task((float(sx), float(sy), float(sx + w), float(sy + h)), 1.0, (0.0, 0.0))
+        mid_task = t.add_render_task((float(x_cursor), 4.0, float(x_cursor + w), float(4 + h)), 1.0, (0.0, 0.0))
+        dst_task = t.add_render_task((float(x_cursor + 2), 7.0, float(x_cursor + 2 + w), float(7 + h)), 1.0, (0.0, 0.0))
+        region = (float(w), float(h)) if i % 2 == 0 else (float(w - 6), float(h - 4))
+        vert.append(blur_instance(mid_task, src_task, 1, sigma, region))
+        hori.append(blur_instance(dst_task, mid_task, 0, sigma, region))
+        x_cursor += w + 6
+    feat = abi.FEAT_COLOR_TARGET if color else abi.FEAT_ALPHA_TARGET
+    textures = {"source": TextureDesc(fmt, sw, sh, data=src, filter=abi.LINEAR),
+                "mid": TextureDesc(fmt, width, height, filter=abi.LINEAR),
+                "target": TextureDesc(fmt, width, height, filter=abi.LINEAR)}
+    p0 = [Clear(color=(0.0, 0.0, 0.0, 0.0)),
+          Batch(abi.KIND_BLUR, np.stack(vert), features=feat, color=("source", "", ""))]
+    p1 = [Clear(color=(0.0, 0.0, 0.0, 0.0)),
+          Batch(abi.KIND_BLUR, np.stack(hori), features=feat, color=("mid", "", ""))]
+    return Frame(t.arrays(), textures, [[Target("mid", ops=p0)], [Target("target", ops=p1)]])
