@@ -18,6 +18,7 @@
 #include "brush_blend.h"
 #include "brush_mix_blend.h"
 #include "cs_blur.h"
+#include "cs_scale.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -49,5 +50,6 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "brush_mix_blend ALPHA_PASS")) return brush_mix_blend_ALPHA_PASS_program::loader;
   if (!strcmp(name, "cs_blur ALPHA_TARGET")) return cs_blur_ALPHA_TARGET_program::loader;
   if (!strcmp(name, "cs_blur COLOR_TARGET")) return cs_blur_COLOR_TARGET_program::loader;
+  if (!strcmp(name, "cs_scale TEXTURE_2D")) return cs_scale_TEXTURE_2D_program::loader;
   return nullptr;
 }

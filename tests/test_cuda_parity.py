@@ -318,3 +318,10 @@ def test_rotated_full_size():
 def test_cs_blur(seed, color):
     f = scenes.blur_frame(seed=seed, color=color)
     assert_same(render(CudaDevice, f, ["mid", "target"]), render(OracleDevice, f, ["mid", "target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["rgba", "r8", "nearest"])
+def test_cs_scale(seed, variant):
+    f = scenes.scale_frame(seed=seed, r8=variant == "r8", filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

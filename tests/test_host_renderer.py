@@ -19,7 +19,7 @@ HOST_LIB = os.path.join(ROOT, "webrender_b200", "libwrhost.so")
 SYMBOLS = ["wrh_renderer_create", "wrh_renderer_destroy", "wrh_frame_create", "wrh_frame_destroy", "wrh_frame_add_pass",
            "wrh_pass_add_picture_cache_target", "wrh_pass_add_color_target", "wrh_pass_add_alpha_target",
            "wrh_picture_target_add_batch", "wrh_color_target_add_batch", "wrh_alpha_target_add_clear",
-           "wrh_alpha_target_add_clips", "wrh_frame_set_framebuffer", "wrh_frame_add_composite_tile",
+           "wrh_alpha_target_add_clips", "wrh_target_add_blur_or_scale", "wrh_frame_set_framebuffer", "wrh_frame_add_composite_tile",
            "wrh_renderer_render", "wrh_renderer_last_error"]
 
 
@@ -40,6 +40,9 @@ CASES = [
     ("text", lambda: scenes.text_frame(seed=2, width=480, height=270, n_runs=8, glyphs_per_run=20), ["target"]),
     ("gradients", lambda: scenes.gradient_frame(seed=1, blend=abi.BLEND_PREMULTIPLIED_ALPHA), ["target"]),
     ("composite", lambda: scenes.composite_frame(seed=1), ["fb"]),
+    ("blur_a8", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
+    ("blur_rgba8", lambda: scenes.blur_frame(seed=2, color=True), ["mid", "target"]),
+    ("scale", lambda: scenes.scale_frame(seed=1), ["target"]),
 ]
 
 

@@ -203,3 +203,10 @@ def test_cs_blur(seed, color):
     sampling at region edges, zero radius, 16-bit saturating accumulation."""
     f = scenes.blur_frame(seed=seed, color=color)
     assert_same(render(SwglDevice, f, ["mid", "target"]), render(OracleDevice, f, ["mid", "target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["rgba", "r8", "nearest"])
+def test_cs_scale(seed, variant):
+    f = scenes.scale_frame(seed=seed, r8=variant == "r8", filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

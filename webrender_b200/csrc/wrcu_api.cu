@@ -17,6 +17,7 @@
 #include "shader_blend.cuh"
 #include "shader_mix_blend.cuh"
 #include "shader_blur.cuh"
+#include "shader_scale.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -640,6 +641,12 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_SCALE:
+      if (stride < 36) return wrcu_fail(c, WRCU_ERR_INVALID, "ScalingInstance stride < 36");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "cs_scale without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_scale, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_BLUR:
       if (stride < 24) return wrcu_fail(c, WRCU_ERR_INVALID, "BlurInstance stride < 24");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "cs_blur without sColor0");
@@ -763,6 +770,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
     case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER(MixBlendShader); break;
     case WRCU_KIND_BLUR: LAUNCH_RASTER(BlurShader); break;
+    case WRCU_KIND_SCALE: LAUNCH_RASTER(ScaleShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER

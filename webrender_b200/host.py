@@ -70,6 +70,7 @@ class HostRenderer:
         L.wrh_color_target_add_batch.argtypes = batch_args
         L.wrh_alpha_target_add_clear.argtypes = [vp, i32, i32, i32, C.POINTER(i32)]
         L.wrh_alpha_target_add_clips.argtypes = [vp, i32, i32, i32, i32, u32, vp, sz, i32]
+        L.wrh_target_add_blur_or_scale.argtypes = [vp, i32, i32, i32, i32, u32, vp, i32]
         L.wrh_frame_set_framebuffer.argtypes = [vp, u32, i32, i32, C.POINTER(C.c_float)]
         L.wrh_frame_add_composite_tile.argtypes = [vp, i32, u32, i32, C.POINTER(C.c_float)]
         L.wrh_renderer_render.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
@@ -114,6 +115,14 @@ class HostRenderer:
             L.wrh_frame_destroy(f)
         return handles, calls.value
 
+    def _add_blur_scale(self, f, p, target_kind, t, b, handles, ptr, n):
+        if b.kind == abi.KIND_SCALE:
+            which = 2
+        else:
+            direction = int(np.ascontiguousarray(b.instance_bytes()[0]).view(np.int32)[2])
+            which = 0 if direction == 1 else 1   # DIR_VERTICAL = 1 → vertical_blurs
+        self.lib.wrh_target_add_blur_or_scale(f, p, target_kind, t, which, handles[b.color[0]], ptr, n)
+
     def _add_target(self, f, p, frame, tgt, handles, keep):
         L = self.lib
         desc = frame.textures[tgt.texture]
@@ -143,6 +152,9 @@ class HostRenderer:
             for b in batches:
                 which = 0 if b.blend == abi.BLEND_NONE else 1
                 ptr, stride, n = inst(b)
+                if b.kind in (abi.KIND_BLUR, abi.KIND_SCALE):
+                    self._add_blur_scale(f, p, 0, t, b, handles, ptr, n)
+                    continue
                 if b.kind == abi.KIND_CLIP_RECTANGLE:
                     L.wrh_alpha_target_add_clips(f, p, t, which, 1 if b.features & abi.FEAT_FAST_PATH else 0, 0, ptr, stride, n)
                 elif b.kind == abi.KIND_CLIP_BOX_SHADOW:
@@ -164,10 +176,14 @@ class HostRenderer:
                     L.wrh_frame_add_composite_tile(f, kind, handles[b.color[0]], 1 if b.features & abi.FEAT_FAST_PATH else 0,
                                                    (C.c_float * 30)(*v))
             return
-        if kinds & {abi.KIND_QUAD_MASK} or (kinds == {abi.KIND_QUAD_TEXTURED} and all(b.blend == abi.BLEND_NONE for b in batches)):
+        if kinds & {abi.KIND_QUAD_MASK, abi.KIND_BLUR, abi.KIND_SCALE} or (
+                kinds == {abi.KIND_QUAD_TEXTURED} and all(b.blend == abi.BLEND_NONE for b in batches)):
             t = L.wrh_pass_add_color_target(f, p, tex, depth, desc.width, desc.height)
             for b in batches:
                 ptr, stride, n = inst(b)
+                if b.kind in (abi.KIND_BLUR, abi.KIND_SCALE):
+                    self._add_blur_scale(f, p, 1, t, b, handles, ptr, n)
+                    continue
                 lst = 1 if b.kind == abi.KIND_QUAD_MASK else (0 if b.blend == abi.BLEND_NONE else 2)
                 bm, adv = _blend_mode(b.blend if lst == 2 else abi.BLEND_NONE)
                 L.wrh_color_target_add_batch(f, p, t, lst, BATCH_KIND[b.kind], bm, adv, b.features, tex4(b), ptr, stride, n)

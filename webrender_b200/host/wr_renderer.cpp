@@ -154,6 +154,10 @@ void Renderer::draw_color_target(const ColorRenderTarget& t, RendererStats& stat
       if (wrcu_clear(device, rect, zero, t.depth ? &one : nullptr) != WRCU_OK) failed++;
     }
   }
+  // blurs and scalings of this target (mod.rs:3607-3640)
+  draw_blurs(t.vertical_blurs, true, stats);
+  draw_blurs(t.horizontal_blurs, true, stats);
+  handle_scaling(t.scalings, stats);
   // handle_prims (mod.rs:2199-2276): quad primitives of off-screen tasks, blending off
   for (const PrimitiveBatch& b : t.prim_batches)
     draw_instanced_batch(batch_kind_to_wrcu(b.key.kind), b.features, b.instances.data(), b.instance_stride,
@@ -185,6 +189,24 @@ void Renderer::draw_clip_batch_list(const ClipBatchList& list, int blend, Render
   }
 }
 
+void Renderer::draw_blurs(const BlurMap& blurs, bool color_target, RendererStats& stats) {
+  for (const auto& kv : blurs) {
+    BatchTextures tex;
+    tex.colors[0] = kv.first;  // BatchTextures::composite_rgb(texture)
+    draw_instanced_batch(WRCU_KIND_BLUR, color_target ? WRCU_FEAT_COLOR_TARGET : WRCU_FEAT_ALPHA_TARGET,
+                         kv.second.data(), sizeof(BlurInstance), kv.second.size(), tex, stats);
+  }
+}
+
+void Renderer::handle_scaling(const ScalingMap& scalings, RendererStats& stats) {
+  for (const auto& kv : scalings) {
+    BatchTextures tex;
+    tex.colors[0] = kv.first;
+    draw_instanced_batch(WRCU_KIND_SCALE, TEXTURE_2D, kv.second.data(), sizeof(ScalingInstance), kv.second.size(), tex,
+                         stats);
+  }
+}
+
 void Renderer::draw_alpha_target(const AlphaRenderTarget& t, RendererStats& stats) {
   stats.alpha_target_count++;
   bind_draw_target(t.texture, 0, t.width, t.height);
@@ -200,6 +222,10 @@ void Renderer::draw_alpha_target(const AlphaRenderTarget& t, RendererStats& stat
     int32_t rect[4] = {r.x0, r.y0, r.x1 - r.x0, r.y1 - r.y0};
     if (wrcu_clear(device, rect, one, nullptr) != WRCU_OK) failed++;
   }
+  // blurs: a standard two-pass separable implementation (mod.rs:3860-3884), then scalings
+  draw_blurs(t.vertical_blurs, false, stats);
+  draw_blurs(t.horizontal_blurs, false, stats);
+  handle_scaling(t.scalings, stats);
   // primary clips overwrite (blend off), secondary clips multiply (mod.rs:3903-3918)
   draw_clip_batch_list(t.clip_batcher.primary_clips, WRCU_BLEND_NONE, stats);
   draw_clip_batch_list(t.clip_batcher.secondary_clips, WRCU_BLEND_MULTIPLY, stats);
@@ -359,6 +385,26 @@ void wrh_alpha_target_add_clips(Frame* f, int pass, int target, int which, int s
   ClipBatchList& l = which == 0 ? cb.primary_clips : cb.secondary_clips;
   std::vector<uint8_t>& v = shape == 0 ? l.slow_rectangles : shape == 1 ? l.fast_rectangles : l.box_shadows[texture];
   v.insert(v.end(), (const uint8_t*)instances, (const uint8_t*)instances + stride * (size_t)n);
+}
+// target_kind: 0 = alpha target, 1 = colour target; which: 0 = vertical_blurs, 1 = horizontal_blurs, 2 = scalings
+void wrh_target_add_blur_or_scale(Frame* f, int pass, int target_kind, int target, int which, wrcu_tex source,
+                                  const void* instances, int n) {
+  BlurMap* vb; BlurMap* hb; ScalingMap* sc;
+  if (target_kind == 0) {
+    AlphaRenderTarget& t = f->passes[pass].alpha[target];
+    vb = &t.vertical_blurs; hb = &t.horizontal_blurs; sc = &t.scalings;
+  } else {
+    ColorRenderTarget& t = f->passes[pass].color[target];
+    vb = &t.vertical_blurs; hb = &t.horizontal_blurs; sc = &t.scalings;
+  }
+  if (which == 2) {
+    const ScalingInstance* p = (const ScalingInstance*)instances;
+    (*sc)[source].insert((*sc)[source].end(), p, p + n);
+  } else {
+    const BlurInstance* p = (const BlurInstance*)instances;
+    BlurMap& m = which == 0 ? *vb : *hb;
+    m[source].insert(m[source].end(), p, p + n);
+  }
 }
 void wrh_frame_set_framebuffer(Frame* f, wrcu_tex fb, int w, int h, const float* clear_color) {
   f->framebuffer = fb; f->fb_width = w; f->fb_height = h; f->present = true;

@@ -83,9 +83,16 @@ struct PictureCacheTarget {  // render_target.rs:707-713
   float clear_color[4] = {0, 0, 0, 0};
   DeviceIntRect dirty_rect = {0, 0, 0, 0};
 };
+struct BlurInstance { int32_t task_address, src_task_address, blur_direction; float blur_std_deviation, blur_region[2]; };  // gpu_types.rs:112-118
+struct ScalingInstance { float target_rect[4], source_rect[4], source_rect_type; };  // gpu_types.rs:124-128
+typedef std::map<wrcu_tex, std::vector<BlurInstance>> BlurMap;      // keyed by source texture
+typedef std::map<wrcu_tex, std::vector<ScalingInstance>> ScalingMap;
+
 struct ColorRenderTarget {  // render_target.rs:215-238 (members the path reads)
   wrcu_tex texture = 0, depth = 0;
   int32_t width = 0, height = 0;
+  BlurMap vertical_blurs, horizontal_blurs;
+  ScalingMap scalings;
   std::vector<AlphaBatchContainer> alpha_batch_containers;
   std::vector<PrimitiveBatch> prim_batches;  // quad prims into off-screen tasks (handle_prims, mod.rs:2199), blend off
   std::vector<PrimitiveBatch> mask_batches;  // ps_quad_mask multiplied in (handle_clips, mod.rs:2278)
@@ -96,6 +103,8 @@ struct AlphaRenderTarget {  // render_target.rs:522-532
   int32_t width = 0, height = 0;
   ClipBatcher clip_batcher;
   std::vector<DeviceIntRect> zero_clears, one_clears;
+  BlurMap vertical_blurs, horizontal_blurs;
+  ScalingMap scalings;
 };
 struct RenderPass {  // render_task_graph.rs:854-861
   std::vector<AlphaRenderTarget> alpha;
@@ -145,6 +154,8 @@ class Renderer {
   void draw_alpha_target(const AlphaRenderTarget& target, RendererStats& stats);                  // mod.rs:3754
   void draw_alpha_batch_container(const AlphaBatchContainer& c, bool has_depth, RendererStats& stats);  // mod.rs:2804
   void draw_clip_batch_list(const ClipBatchList& list, int blend, RendererStats& stats);          // mod.rs:3695
+  void draw_blurs(const BlurMap& blurs, bool color_target, RendererStats& stats);                 // mod.rs:3675
+  void handle_scaling(const ScalingMap& scalings, RendererStats& stats);                          // mod.rs:2472
   void composite_simple(const Frame& frame, RendererStats& stats);                                // mod.rs:3340
   void draw_tile_list(const std::vector<const CompositeTile*>& tiles, int blend, RendererStats& stats);  // mod.rs:3126
   // draw_instanced_batch<T> (mod.rs:2022-2065)

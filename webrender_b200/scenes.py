@@ -854,3 +854,37 @@ def blur_frame(width=384, height=256, seed=1, color=False, sigmas=(1.0, 2.5, 6.0
     p1 = [Clear(color=(0.0, 0.0, 0.0, 0.0)),
           Batch(abi.KIND_BLUR, np.stack(hori), features=feat, color=("mid", "", ""))]
     return Frame(t.arrays(), textures, [[Target("mid", ops=p0)], [Target("target", ops=p1)]])
+
+
+def scale_frame(width=384, height=256, seed=1, r8=False, filter=abi.LINEAR):
+    """cs_scale (handle_scaling, renderer/mod.rs:2472-2530): ScalingInstance
+    copies of source rects at 1:1, 2:1 down (the blur pipeline's downscale
+    steps), arbitrary scales and a flipped source rect; unnormalised uvs."""
+    rng = np.random.RandomState(seed)
+    fmt = abi.FMT_R8 if r8 else abi.FMT_RGBA8
+    sw, sh = 320, 200
+    src = shadow_mask_texture(320, seed + 3)[:sh, :sw].copy() if r8 else tile_texture(sw, sh, seed + 3, opaque=False)
+    inst = np.zeros((5, 9), dtype=np.float32)
+    x_cursor = 4
+    for i in range(5):
+        w, h = int(rng.randint(30, 70)), int(rng.randint(24, 110))
+        tx, ty = x_cursor, int(rng.randint(2, 40))
+        x_cursor += w + 5
+        if i == 0:
+            sw_, sh_ = w, h
+        elif i == 1:
+            sw_, sh_ = 2 * w, 2 * h
+        else:
+            sw_, sh_ = int(rng.randint(20, 140)), int(rng.randint(16, 90))
+        sx, sy = int(rng.randint(0, sw - sw_)), int(rng.randint(0, sh - sh_))
+        s = (float(sx), float(sy), float(sx + sw_), float(sy + sh_))
+        if i == 3:
+            s = (s[2], s[1], s[0], s[3])   # inverted u
+        inst[i, 0:4] = (tx, ty, tx + w, ty + h)
+        inst[i, 4:8] = s
+        inst[i, 8] = 1.0
+    textures = {"source": TextureDesc(fmt, sw, sh, data=src, filter=filter),
+                "target": TextureDesc(fmt, width, height)}
+    ops = [Clear(color=(0.0, 0.0, 0.0, 0.0)),
+           Batch(abi.KIND_SCALE, inst, features=abi.FEAT_TEXTURE_2D, color=("source", "", ""))]
+    return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
