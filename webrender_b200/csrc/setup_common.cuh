@@ -20,6 +20,7 @@ struct SetupArgs {
   CmdHot* hot;
   CmdCold* cold;
   BatchInfo* info;
+  BatchInfo* info_next;  // the NEXT batch's record, reset by this batch's setup kernel (ring of 4)
   int* err_counter;
   int blend_enabled;
   uint32_t features;
@@ -30,13 +31,27 @@ struct SetupArgs {
 
 // A setup kernel = one thread per instance running <name>_one.  Under the host
 // emulation (tests only) the same function is called in a plain loop.
+WRD void wr_reset_batch_info(BatchInfo* info) {
+  info->bx0 = 0x7fffffff; info->by0 = 0x7fffffff;
+  info->bx1 = -0x7fffffff; info->by1 = -0x7fffffff;
+  info->unsupported = 0;
+  info->simple = 1;
+  info->premul_valid = 1;
+}
+// Each setup kernel also re-arms the per-batch record the NEXT draw will use
+// (records rotate through a ring of 4; the one after the current was last read
+// three draws ago), so no separate initialisation launch is needed per draw.
 #ifdef WRCU_HOSTEMU
-#define WR_SETUP_KERNEL(name) \
-  static void name(const SetupArgs& a) { for (int i = 0; i < a.n; i++) name##_one(a, i); }
+#define WR_SETUP_KERNEL(name)                                     \
+  static void name(const SetupArgs& a) {                          \
+    wr_reset_batch_info(a.info_next);                             \
+    for (int i = 0; i < a.n; i++) name##_one(a, i);               \
+  }
 #else
 #define WR_SETUP_KERNEL(name)                              \
   __global__ void name(SetupArgs a) {                      \
     int idx = blockIdx.x * blockDim.x + threadIdx.x;       \
+    if (idx == 0) wr_reset_batch_info(a.info_next);        \
     if (idx < a.n) name##_one(a, idx);                     \
   }
 #endif

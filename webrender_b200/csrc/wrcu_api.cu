@@ -57,12 +57,8 @@ static int fmt_bpp(int fmt) {
 #endif
 
 // ---- small kernels ---------------------------------------------------------------
-WR_GLOBAL void wr_init_batch_info(BatchInfo* info) {
-  info->bx0 = 0x7fffffff; info->by0 = 0x7fffffff;
-  info->bx1 = -0x7fffffff; info->by1 = -0x7fffffff;
-  info->unsupported = 0;
-  info->simple = 1;
-  info->premul_valid = 1;
+WR_GLOBAL void wr_init_batch_info(BatchInfo* info, int n) {  // once, at context creation
+  for (int i = 0; i < n; i++) wr_reset_batch_info(info + i);
 }
 
 // Clear (swgl/src/gl.cc:2498-2518 → clear_buffer): fills a rect of a 4-byte or
@@ -145,12 +141,13 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   }
   cudaEventCreate(&c->t0);
   cudaEventCreate(&c->t1);
-  if (cudaMalloc((void**)&c->batch_info, sizeof(BatchInfo)) != cudaSuccess ||
+  if (cudaMalloc((void**)&c->batch_info, 4 * sizeof(BatchInfo)) != cudaSuccess ||
       cudaMalloc((void**)&c->dev_err, sizeof(int)) != cudaSuccess) {
     delete c;
     return WRCU_ERR_OOM;
   }
   cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
+  WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info, 4);
   *out = c;
   return WRCU_OK;
 }
@@ -591,15 +588,15 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.n = n;
   sa.hot = (CmdHot*)c->cmd_hot;
   sa.cold = (CmdCold*)c->cmd_cold;
-  sa.info = (BatchInfo*)c->batch_info;
+  BatchInfo* info_cur = (BatchInfo*)c->batch_info + (c->draw_seq & 3);
+  sa.info = info_cur;
+  sa.info_next = (BatchInfo*)c->batch_info + ((c->draw_seq + 1) & 3);
   sa.err_counter = c->dev_err;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
   sa.clip_mask = tex_view(c, st->clip_mask);
 
-  WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info);
-  c->stats.kernel_launches++;
   int sblocks = (n + 127) / 128;
   switch (kind) {
     case WRCU_KIND_QUAD_TEXTURED:
@@ -694,6 +691,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     default:
       return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);
   }
+  c->draw_seq++;  // only once the setup kernel (which re-arms the next record) is queued
   c->stats.kernel_launches++;
 
   RasterArgs ra;
@@ -701,7 +699,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   ra.tgt = T;
   ra.hot = (const CmdHot*)c->cmd_hot;
   ra.cold = (const CmdCold*)c->cmd_cold;
-  ra.info = (const BatchInfo*)c->batch_info;
+  ra.info = info_cur;
   ra.n = n;
   ra.blend = st->blend;
   ra.depth_mode = T.depth ? st->depth : WRCU_DEPTH_OFF;

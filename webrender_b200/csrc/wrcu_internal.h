@@ -102,7 +102,8 @@ struct wrcu_ctx {
   // scratch for commands
   void* cmd_hot = nullptr;
   void* cmd_cold = nullptr;
-  int* batch_info = nullptr;  // bbox etc.
+  int* batch_info = nullptr;  // ring of 4 BatchInfo records (bbox, flags)
+  unsigned draw_seq = 0;
   int* dev_err = nullptr;     // count of instances rejected by setup kernels (sticky until read)
   size_t cmd_cap = 0;
   // stats / timing
