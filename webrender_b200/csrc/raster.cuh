@@ -188,6 +188,28 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
   if (!isfinite(stepScale)) stepScale = 0.0f;
   float x0f = __fsub_rn(__fadd_rn((float)c.x0, 0.5f), k.xl);
   int rows = y - c.y0;
+#ifndef WRCU_HOSTEMU
+  // The 2N edge sums are independent and the whole warp is here (row_setup is
+  // warp-uniform): lane l < 2N walks one of them, the results are broadcast.
+  // One walk's worth of instructions instead of 2N.
+  const int wlane = threadIdx.x & 31;
+  float walked = 0.0f;
+  if (wlane < 2 * N) {
+    const int i = wlane >> 1;
+    const float* top = (wlane & 1) ? k.i_rt : k.i_lt;
+    const float* bot = (wlane & 1) ? k.i_rb : k.i_lb;
+    float sl = __fmul_rn(__fsub_rn(bot[i], top[i]), k.yscale);
+    walked = wr_repeat_add(__fadd_rn(top[i], __fmul_rn(dy, sl)), sl, rows);
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float li = __shfl_sync(0xFFFFFFFFu, walked, 2 * i);
+    float ri = __shfl_sync(0xFFFFFFFFu, walked, 2 * i + 1);
+    float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
+    step[i] = st;
+    o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
+  }
+#else
 #pragma unroll
   for (int i = 0; i < N; i++) {
     float sl = __fmul_rn(__fsub_rn(k.i_lb[i], k.i_lt[i]), k.yscale);
@@ -200,6 +222,7 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
     step[i] = st;
     o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
   }
+#endif
 }
 
 // Value of interpolant lanes at pixel x of the span: lane j of chunk k.  Chunk
@@ -430,16 +453,7 @@ static void wr_raster_solid_premult(const RasterArgs& a) {
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
 // S::source returns the fragment stage's output for one pixel as 16-bit lanes.
 template <class S, int FMT>
-__global__ void __launch_bounds__(WRCU_THREADS)
-wr_raster(RasterArgs a) {
-  __shared__ CmdHot sh[CHUNK_CMDS];
-  __shared__ int wsum[WRCU_THREADS / 32];
-  const int tx0 = blockIdx.x * WRCU_TILE_W, ty0 = blockIdx.y * WRCU_TILE_H;
-  const BatchInfo bi = *a.info;
-  if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
-  // whole-CTA early out: tile outside the batch's bounding box
-  if (tx0 >= bi.bx1 || tx0 + WRCU_TILE_W <= bi.bx0 || ty0 >= bi.by1 || ty0 + WRCU_TILE_H <= bi.by0)
-    return;
+WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
@@ -519,6 +533,25 @@ wr_raster(RasterArgs a) {
     }
   }
   if (zdirty) *(uint4*)(zrow + x) = make_uint4(zb[0], zb[1], zb[2], zb[3]);
+}
+
+// Persistent CTAs stride over the tiles of the batch's bounding box (known only
+// on the device), so a batch that touches a small part of a large target costs
+// a small launch, and a full-target batch fills the chip evenly.
+template <class S, int FMT>
+__global__ void __launch_bounds__(WRCU_THREADS)
+wr_raster(RasterArgs a) {
+  __shared__ CmdHot sh[CHUNK_CMDS];
+  __shared__ int wsum[WRCU_THREADS / 32];
+  const BatchInfo bi = *a.info;
+  if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
+  const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
+  const int bx1 = (min(bi.bx1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
+  const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
+  const int nx = bx1 - bx0, n_tiles = nx * (by1 - by0);
+  if (nx <= 0 || n_tiles <= 0) return;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum);
 }
 
 // ---- specialised hot kernel: solid quads, premultiplied-alpha over, no depth,

@@ -747,14 +747,18 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
 #endif
     c->stats.kernel_launches++;
   }
+  // generic kernels: persistent CTAs over the batch's tiles; 3 CTAs of 256 threads per SM
+  // cover every shader's register budget (<= 128 regs/thread would allow 2; most use 80)
+  const int total_tiles = (int)(grid.x * grid.y);
+  const int pgrid = total_tiles < c->sm_count * 3 ? total_tiles : c->sm_count * 3;
 #define LAUNCH_RASTER(S)                                                         \
   do {                                                                           \
     auto k_rgba = wr_raster<S, WRCU_FMT_RGBA8>;                                   \
     auto k_r8 = wr_raster<S, WRCU_FMT_R8>;                                        \
     if (T.fmt == WRCU_FMT_RGBA8)                                                 \
-      WR_LAUNCH(k_rgba, grid, WRCU_THREADS, c->stream, ra);                      \
+      WR_LAUNCH(k_rgba, pgrid, WRCU_THREADS, c->stream, ra);                     \
     else                                                                         \
-      WR_LAUNCH(k_r8, grid, WRCU_THREADS, c->stream, ra);                        \
+      WR_LAUNCH(k_r8, pgrid, WRCU_THREADS, c->stream, ra);                       \
   } while (0)
   switch (kind) {
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
