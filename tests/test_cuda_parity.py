@@ -325,3 +325,10 @@ def test_cs_blur(seed, color):
 def test_cs_scale(seed, variant):
     f = scenes.scale_frame(seed=seed, r8=variant == "r8", filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+def test_binned_batch_mixed_sizes():
+    """n >= 512 takes the bitmask-bin path: small commands scattered into per-tile
+    masks, large ones through the wide mask; blend order must survive."""
+    f = scenes.alpha_rects_frame(1920, 1080, 900, random_rects=True, seed=11, color=None)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

@@ -55,6 +55,7 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 
 // ---- CUDA runtime stand-ins operating on host memory ---------------------------
 typedef int cudaError_t;

@@ -39,6 +39,9 @@ struct RasterArgs {
   const float4* gpu_cache;  // component-transfer tables
   int n_gpu_cache;
   const GenRow* gen;  // per-thread row state of the current CMD_GENERAL command
+  const uint32_t* tile_mask;  // bitmask bins (see SetupArgs), nullptr = scan every command
+  const uint32_t* wide_mask;
+  int bin_words, bin_tiles_x;
 };
 
 #define CHUNK_CMDS 256
@@ -473,7 +476,18 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
     const int m = min(CHUNK_CMDS, a.n - base);
     int keep = 0;
     CmdHot mine;
-    if ((int)threadIdx.x < m) {
+    bool candidate = (int)threadIdx.x < m;
+    if (a.tile_mask) {
+      // bitmask bins: one word per warp tells which of its 32 commands can touch this tile
+      const int w = (base >> 5) + warp;
+      uint32_t word = 0;
+      if (w < a.bin_words)
+        word = __ldg(a.tile_mask + (size_t)((ty0 / WRCU_TILE_H) * a.bin_tiles_x + tx0 / WRCU_TILE_W) * a.bin_words + w) |
+               __ldg(a.wide_mask + w);
+      if (!__syncthreads_or(word != 0)) continue;  // nothing of this chunk reaches the tile
+      candidate = candidate && ((word >> lane) & 1u);
+    }
+    if (candidate) {
       mine = a.hot[base + threadIdx.x];
       keep = mine.x1 > tx0 && mine.x0 < tx0 + WRCU_TILE_W && mine.y1 > ty0 && mine.y0 < ty0 + WRCU_TILE_H &&
              mine.x1 > mine.x0;

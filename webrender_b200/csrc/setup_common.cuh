@@ -11,6 +11,8 @@
 #include "cmd.cuh"
 #include "wrcu_internal.h"
 
+#define WR_WIDE_TILES 64
+
 struct SetupArgs {
   FrameTablesDev tabs;
   TargetDev tgt;
@@ -21,6 +23,11 @@ struct SetupArgs {
   CmdCold* cold;
   BatchInfo* info;
   BatchInfo* info_next;  // the NEXT batch's record, reset by this batch's setup kernel (ring of 4)
+  // bitmask bins (large batches): bit i of tile_mask[tile * bin_words + i/32] = command i touches the tile;
+  // commands covering more than WR_WIDE_TILES tiles set their bit in wide_mask instead
+  uint32_t* tile_mask;
+  uint32_t* wide_mask;
+  int bin_words, bin_tiles_x;
   int* err_counter;
   int blend_enabled;
   uint32_t features;
@@ -341,6 +348,19 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     if (!(h.col[0] <= h.col[3] && h.col[1] <= h.col[3] && h.col[2] <= h.col[3])) a.info->premul_valid = 0;
     atomicMin(&a.info->bx0, (int)h.x0); atomicMin(&a.info->by0, (int)h.y0);
     atomicMax(&a.info->bx1, (int)h.x1); atomicMax(&a.info->by1, (int)h.y1);
+    if (a.tile_mask) {
+      const int tx_a = max((int)h.x0, 0) / WRCU_TILE_W, tx_b = (min((int)h.x1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
+      const int ty_a = max((int)h.y0, 0) / WRCU_TILE_H, ty_b = (min((int)h.y1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
+      const uint32_t bit = 1u << (idx & 31);
+      const int word = idx >> 5;
+      if ((tx_b - tx_a) * (ty_b - ty_a) > WR_WIDE_TILES) {
+        atomicOr(&a.wide_mask[word], bit);
+      } else {
+        for (int ty = ty_a; ty < ty_b; ty++)
+          for (int tx = tx_a; tx < tx_b; tx++)
+            atomicOr(&a.tile_mask[(size_t)(ty * a.bin_tiles_x + tx) * a.bin_words + word], bit);
+      }
+    }
   }
   // cold record is written by the caller after it fills the kind-specific part
   a.cold[idx] = k;

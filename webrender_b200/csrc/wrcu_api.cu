@@ -167,6 +167,7 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->cmd_cold) cudaFree(c->cmd_cold);
   if (c->batch_info) cudaFree(c->batch_info);
   if (c->dev_err) cudaFree(c->dev_err);
+  if (c->bin_mask) cudaFree(c->bin_mask);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
   if (c->copy_stream) {
@@ -595,6 +596,28 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
+  // Bitmask bins for batches with many instances: the per-tile command scan of the raster
+  // kernel costs tiles x n hot records of L2 traffic; with bins it reads n/32 words per tile.
+  {
+    const int tiles_x = (T.w + WRCU_TILE_W - 1) / WRCU_TILE_W, tiles_y = (T.h + WRCU_TILE_H - 1) / WRCU_TILE_H;
+    const size_t words = ((size_t)n + 31) / 32;
+    const size_t need = ((size_t)tiles_x * tiles_y + 1) * words;  // + the wide mask
+    if (n >= 512 && need * 4 <= (size_t)96 << 20) {
+      if (need > c->bin_cap_words) {
+        WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->bin_mask) cudaFree(c->bin_mask);
+        c->bin_mask = nullptr;
+        c->bin_cap_words = 0;
+        WRCU_CUDA(c, cudaMalloc((void**)&c->bin_mask, need * 4 * 2));
+        c->bin_cap_words = need * 2;
+      }
+      WRCU_CUDA(c, cudaMemsetAsync(c->bin_mask, 0, need * 4, c->stream));
+      sa.tile_mask = c->bin_mask;
+      sa.wide_mask = c->bin_mask + (size_t)tiles_x * tiles_y * words;
+      sa.bin_words = (int)words;
+      sa.bin_tiles_x = tiles_x;
+    }
+  }
   sa.clip_mask = tex_view(c, st->clip_mask);
 
   int sblocks = (n + 127) / 128;
@@ -710,6 +733,10 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   ra.gbuf_f = c->tables.gpu_buffer_f;
   ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
   ra.gpu_cache = c->tables.gpu_cache;
+  ra.tile_mask = sa.tile_mask;
+  ra.wide_mask = sa.wide_mask;
+  ra.bin_words = sa.bin_words;
+  ra.bin_tiles_x = sa.bin_tiles_x;
   ra.n_gpu_cache = c->tables.n_gpu_cache;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
   if (grid.x == 0 || grid.y == 0) return WRCU_OK;

@@ -104,6 +104,9 @@ struct wrcu_ctx {
   void* cmd_cold = nullptr;
   int* batch_info = nullptr;  // ring of 4 BatchInfo records (bbox, flags)
   unsigned draw_seq = 0;
+  // bitmask bins of the current batch (grown on demand)
+  uint32_t* bin_mask = nullptr;
+  size_t bin_cap_words = 0;
   int* dev_err = nullptr;     // count of instances rejected by setup kernels (sticky until read)
   size_t cmd_cap = 0;
   // stats / timing
