@@ -74,5 +74,5 @@ struct BatchInfo {
   int unsupported;         // instances the setup kernel had to reject
   int simple;              // 1 while every command is a plain solid quad (no mask/AA/texture, lanes<=255)
   int premul_valid;        // 1 while every command's colour lanes are <= its alpha lane
-  int pad[1];
+  int tile_counter;        // dynamic tile scheduler of the generic raster kernel
 };

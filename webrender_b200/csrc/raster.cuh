@@ -564,8 +564,16 @@ wr_raster(RasterArgs a) {
   const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
   const int nx = bx1 - bx0, n_tiles = nx * (by1 - by0);
   if (nx <= 0 || n_tiles <= 0) return;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+  // tiles are handed out dynamically: their cost varies with what lands on them
+  __shared__ int s_tile;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
+    __syncthreads();
+    const int t = s_tile;
+    if (t >= n_tiles) break;
     wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum);
+    __syncthreads();
+  }
 }
 
 // ---- specialised hot kernel: solid quads, premultiplied-alpha over, no depth,

@@ -44,6 +44,7 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
   info->unsupported = 0;
   info->simple = 1;
   info->premul_valid = 1;
+  info->tile_counter = 0;
 }
 // Each setup kernel also re-arms the per-batch record the NEXT draw will use
 // (records rotate through a ring of 4; the one after the current was last read
