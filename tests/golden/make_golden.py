@@ -41,6 +41,12 @@ CASES = [
     ("brush_opacity_scaled", "opacity_frame", dict(seed=2)),
     ("brush_blend_filters", "blend_frame", dict(seed=1)),
     ("brush_mix_blend_modes", "mix_blend_frame", dict(seed=2)),
+    ("cs_blur_a8", "blur_frame", dict(seed=2)),
+    ("cs_blur_rgba8", "blur_frame", dict(seed=1, color=True)),
+    ("cs_scale_rgba8", "scale_frame", dict(seed=2)),
+    ("rotated_brush_solid", "brush_solid_frame", dict(seed=2, rotate=-33.5, fractional=True)),
+    ("rotated_gradient", "gradient_frame", dict(seed=2, rotate=17.0, fractional=True, blend=2)),
+    ("ps_clear_depth", "clear_frame", dict(seed=1)),
 ]
 
 
