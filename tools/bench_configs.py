@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring of the config name to run alone")
     args = ap.parse_args()
     import torch
     from webrender_b200 import abi, multi_gpu, scenes
@@ -38,6 +39,8 @@ def main():
         ("images: 8 opaque + 20 alpha brush_image @4K-ish", scenes.image_frame(width=W, height=H, seed=1)),
     ]
     for name, frame in cfgs:
+        if args.only and args.only not in name:
+            continue
         handles = draw_frame(dev, frame)
         for _ in range(2):
             draw_frame(dev, frame, handles)
