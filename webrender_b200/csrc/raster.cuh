@@ -456,7 +456,7 @@ static void wr_raster_solid_premult(const RasterArgs& a) {
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
 // S::source returns the fragment stage's output for one pixel as 16-bit lanes.
 template <class S, int FMT>
-WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum) {
+WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, uint32_t* msk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
@@ -469,7 +469,21 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
   uint32_t* zrow = a.tgt.depth ? (uint32_t*)((uint8_t*)a.tgt.depth + (size_t)y * a.tgt.depth_pitch) : nullptr;
   const bool use_depth = a.depth_mode != WRCU_DEPTH_OFF && zrow != nullptr;
 
-  for (int base = 0; base < a.n; base += CHUNK_CMDS) {
+  // Commands are taken in chunks of CHUNK_CMDS.  With bitmask bins the tile's mask words for
+  // 8192 commands at a time are staged in shared memory first, so empty chunks are skipped
+  // without touching global memory or a barrier.
+  for (int sbase = 0; sbase < a.n; sbase += WRCU_THREADS * 32) {
+  if (a.tile_mask) {
+    __syncthreads();  // previous super-chunk's readers are done with msk
+    const int w = (sbase >> 5) + (int)threadIdx.x;
+    msk[threadIdx.x] = w < a.bin_words
+        ? (__ldg(a.tile_mask + (size_t)((ty0 / WRCU_TILE_H) * a.bin_tiles_x + tx0 / WRCU_TILE_W) * a.bin_words + w) |
+           __ldg(a.wide_mask + w))
+        : 0u;
+    __syncthreads();
+  }
+  const int send = min(a.n, sbase + WRCU_THREADS * 32);
+  for (int base = sbase; base < send; base += CHUNK_CMDS) {
     // Binning: each thread tests one command of the chunk against this tile; the
     // survivors' indices are compacted in batch order (ballot + prefix sum), so
     // the pixel loop only visits commands that touch the tile.
@@ -478,14 +492,9 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
     CmdHot mine;
     bool candidate = (int)threadIdx.x < m;
     if (a.tile_mask) {
-      // bitmask bins: one word per warp tells which of its 32 commands can touch this tile
-      const int w = (base >> 5) + warp;
-      uint32_t word = 0;
-      if (w < a.bin_words)
-        word = __ldg(a.tile_mask + (size_t)((ty0 / WRCU_TILE_H) * a.bin_tiles_x + tx0 / WRCU_TILE_W) * a.bin_words + w) |
-               __ldg(a.wide_mask + w);
-      if (!__syncthreads_or(word != 0)) continue;  // nothing of this chunk reaches the tile
-      candidate = candidate && ((word >> lane) & 1u);
+      const uint32_t* mw = msk + ((base - sbase) >> 5);
+      if (!(mw[0] | mw[1] | mw[2] | mw[3] | mw[4] | mw[5] | mw[6] | mw[7])) continue;  // CTA-uniform
+      candidate = candidate && ((mw[warp] >> lane) & 1u);
     }
     if (candidate) {
       mine = a.hot[base + threadIdx.x];
@@ -539,6 +548,7 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       }
     }
   }
+  }  // super-chunk
   if (dirty) {
     if (FMT == WRCU_FMT_RGBA8) {
       *(uint4*)(rowp + (size_t)x * 4) = make_uint4(px[0], px[1], px[2], px[3]);
@@ -566,12 +576,13 @@ wr_raster(RasterArgs a) {
   if (nx <= 0 || n_tiles <= 0) return;
   // tiles are handed out dynamically: their cost varies with what lands on them
   __shared__ int s_tile;
+  __shared__ uint32_t msk[WRCU_THREADS];
   for (;;) {
     if (threadIdx.x == 0) s_tile = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) break;
-    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum);
+    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, msk);
     __syncthreads();
   }
 }

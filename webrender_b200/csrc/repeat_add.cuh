@@ -39,12 +39,18 @@ WRD float wr_repeat_add(float x, float s, int n) {
         const int32_t X = (int32_t)((by & 0x007FFFFFu) | 0x00800000u);
         const float dq = __fdiv_rn(d, ulp);  // exact power-of-two scaling
         const int32_t D = (int32_t)dq * ((by >> 31) ? -1 : 1);  // signed step of |y|'s mantissa
-        int32_t m;
-        if (D > 0) m = (0x00FFFFFF - X) / D;
-        // stay strictly above the binade's bottom: an exact sum just below 2^e would round on
-        // the finer grid of the binade underneath
-        else if (D < 0) m = (X - 0x00800001) / (-D);
-        else m = n;
+        // steps left before the binade boundary = floor(room / |D|).  Both are < 2^24, so the
+        // correctly rounded float quotient is off by at most one: far cheaper than integer division.
+        // Going down, stay strictly above the binade's bottom: an exact sum just below 2^e would
+        // round on the finer grid of the binade underneath.
+        int32_t m = n;
+        if (D != 0) {
+          const int32_t room = D > 0 ? (0x00FFFFFF - X) : (X - 0x00800001);
+          const int32_t Da = D > 0 ? D : -D;
+          m = room < 0 ? 0 : (int32_t)__fdiv_rn((float)room, (float)Da);
+          if (m * Da > room) m--;
+          if ((m + 1) * Da <= room) m++;
+        }
         if (m > n) m = n;
         if (m > 0) {
           const int32_t X2 = X + m * D;
