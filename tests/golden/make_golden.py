@@ -47,6 +47,8 @@ CASES = [
     ("rotated_brush_solid", "brush_solid_frame", dict(seed=2, rotate=-33.5, fractional=True)),
     ("rotated_gradient", "gradient_frame", dict(seed=2, rotate=17.0, fractional=True, blend=2)),
     ("ps_clear_depth", "clear_frame", dict(seed=1)),
+    ("reftest_clip_mode", "reftest_clip_frame", dict(which="clip-mode")),
+    ("reftest_clip_ellipse", "reftest_clip_frame", dict(which="clip-ellipse")),
 ]
 
 

@@ -60,3 +60,26 @@ def test_oracle_matches_reference_golden(name):
 def test_cuda_matches_reference_golden(name):
     from webrender_b200.device import CudaDevice
     _check(CudaDevice, name, tolerant=name in CUDA_LSB_TOLERANT)
+
+
+@pytest.mark.parametrize("which,png,max_diff,max_px", [
+    ("clip-mode", "clip/clip-mode.png", 1, 4),        # fuzzy-if(platform(swgl),1,4)
+    ("clip-ellipse", "clip/clip-ellipse.png", 1, 80),  # fuzzy-if(platform(swgl),1,80)
+])
+def test_clip_reftests_against_reference_png(which, png, max_diff, max_px):
+    """wrench/reftests/clip/{clip-mode,clip-ellipse}.yaml (Clip and ClipOut rounded /
+    elliptical clips, incl. the frame builder's corner-overlap scaling) against the
+    reference's own PNGs under the reftest's fuzz.  Measured: 0 differing pixels."""
+    path = "/root/reference/wrench/reftests/" + png
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_clip_frame(which)
+    d_ = f.textures["target"]
+    out = render(OracleDevice, f, ["target"])["target"].reshape(d_.height, d_.width, 4)[..., [2, 1, 0, 3]].astype(int)
+    h, w = min(ref.shape[0], out.shape[0]), min(ref.shape[1], out.shape[1])
+    d = np.abs(out[:h, :w] - ref[:h, :w]).max(axis=2)
+    assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))
+    assert (ref[h:, :, :3] == 255).all() and (ref[:, w:, :3] == 255).all()
+    assert (out[h:, :, :3] == 255).all() and (out[:, w:, :3] == 255).all()

@@ -222,7 +222,8 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
         n_rects = len(spec)
     for i in range(n_rects):
         if spec is not None:
-            (sx0, sy0, sx1, sy1), scolor, sradii = spec[i]
+            (sx0, sy0, sx1, sy1), scolor, sradii = spec[i][:3]
+            smode = float(spec[i][3]) if len(spec[i]) > 3 else 0.0
             w, h = int(sx1 - sx0), int(sy1 - sy0)
         else:
             w, h = int(rng.randint(40, 220)), int(rng.randint(30, 160))
@@ -251,7 +252,7 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
         uniform = i % 2 == 0
         mode = float(i % 5 == 4)
         if spec is not None:
-            mode = 0.0
+            mode = smode
             uniform = not isinstance(sradii, (list, tuple))
         if spec is not None and uniform:
             r = float(sradii)
@@ -888,3 +889,38 @@ def scale_frame(width=384, height=256, seed=1, r8=False, filter=abi.LINEAR):
     ops = [Clear(color=(0.0, 0.0, 0.0, 0.0)),
            Batch(abi.KIND_SCALE, inst, features=abi.FEAT_TEXTURE_2D, color=("source", "", ""))]
     return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def _no_corner_overlap(radii, w, h):
+    """ensure_no_corner_overlap (webrender/src/border.rs:168-215) in f32."""
+    f = np.float32
+    (tl, tr, bl, br) = [(f(a), f(b)) for a, b in radii]
+    ratio = f(1.0)
+    for size, s1, s2 in ((f(w), tl[0] + tr[0], bl[0] + br[0]), (f(h), tl[1] + bl[1], tr[1] + br[1])):
+        if size > 0:
+            for ssum in (s1, s2):
+                if size < ssum:
+                    ratio = min(ratio, f(size / ssum))
+    if ratio < 1.0:
+        tl, tr, bl, br = [(f(a * ratio), f(b * ratio)) for a, b in (tl, tr, bl, br)]
+    return tuple((float(a), float(b)) for a, b in (tl, tr, bl, br))
+
+
+def reftest_clip_frame(which="clip-mode"):
+    """wrench/reftests/clip/clip-mode.yaml and clip-ellipse.yaml: 100x100 rects under
+    rounded-rect clips (uniform radius 32 / elliptical radii incl. over-large ones
+    that the frame builder scales down), alternately Clip and ClipOut, drawn the
+    Indirect way at the size of their reference images."""
+    red, green = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0)
+    spec = []
+    if which == "clip-mode":
+        spec = [((20, 20, 120, 120), red, 32.0, 0), ((130, 20, 230, 120), green, 32.0, 1)]
+        size = (250, 140)
+    else:
+        for row, (rx, ry) in enumerate([(32, 16), (16, 32), (128, 32), (32, 128)]):
+            y0 = 20 + 110 * row
+            rad = _no_corner_overlap(((rx, ry),) * 4, 100, 100)
+            spec.append(((20, y0, 120, y0 + 100), red, rad, 0))
+            spec.append(((130, y0, 230, y0 + 100), green, rad, 1))
+        size = (250, 470)
+    return rounded_rects_frame(width=size[0], height=size[1], spec=spec, surface=(512, 512))
