@@ -49,6 +49,8 @@ CASES = [
     ("ps_clear_depth", "clear_frame", dict(seed=1)),
     ("reftest_clip_mode", "reftest_clip_frame", dict(which="clip-mode")),
     ("reftest_clip_ellipse", "reftest_clip_frame", dict(which="clip-ellipse")),
+    ("reftest_gradient_linear", "reftest_gradient_frame", dict(which="linear")),
+    ("reftest_gradient_hard_stop", "reftest_gradient_frame", dict(which="linear-hard-stop")),
 ]
 
 

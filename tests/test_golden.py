@@ -83,3 +83,22 @@ def test_clip_reftests_against_reference_png(which, png, max_diff, max_px):
     assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))
     assert (ref[h:, :, :3] == 255).all() and (ref[:, w:, :3] == 255).all()
     assert (out[h:, :, :3] == 255).all() and (out[:, w:, :3] == 255).all()
+
+
+@pytest.mark.parametrize("which,png,max_diff,max_px", [
+    ("linear", "gradient/linear-ref.png", 0, 0),                       # == linear.yaml linear-ref.png
+    ("linear-reverse", "gradient/linear-ref.png", 0, 0),               # == linear-reverse.yaml linear-ref.png
+    ("linear-hard-stop", "gradient/linear-hard-stop-ref.png", 1, 4800),  # fuzzy-range(<=1,*4800)
+])
+def test_gradient_reftests_against_reference_png(which, png, max_diff, max_px):
+    """wrench/reftests/gradient/linear*.yaml as Brush(LinearGradient) against the
+    reference's own PNGs under each reftest's fuzz (measured: 0 / 0 / <=1 on 4800 px)."""
+    path = "/root/reference/wrench/reftests/" + png
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    out = render(OracleDevice, scenes.reftest_gradient_frame(which), ["target"])["target"]
+    out = out.reshape(300, 300, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref).max(axis=2)
+    assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))

@@ -924,3 +924,34 @@ def reftest_clip_frame(which="clip-mode"):
             spec.append(((130, y0, 230, y0 + 100), green, rad, 1))
         size = (250, 470)
     return rounded_rects_frame(width=size[0], height=size[1], spec=spec, surface=(512, 512))
+
+
+def reftest_gradient_frame(which="linear"):
+    """wrench/reftests/gradient/linear.yaml (four hard-stop bands), linear-reverse.yaml
+    and linear-hard-stop.yaml as ONE Brush(LinearGradient) each on a 300x300 white
+    page — the uncached brush path an `is_software` frame builder keeps."""
+    from .gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
+    W = H = 300
+    red, green, blue, black = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0), (0.0, 0.0, 0.0, 1.0)
+    if which == "linear":
+        start, end = (0.0, 100.0), (200.0, 100.0)
+        stops = [(0.0, red), (0.25, red), (0.25, green), (0.5, green), (0.5, blue), (0.75, blue), (0.75, black), (1.0, black)]
+    elif which == "linear-reverse":
+        start, end = (200.0, 100.0), (0.0, 100.0)
+        stops = [(0.0, black), (0.25, black), (0.25, blue), (0.5, blue), (0.5, green), (0.75, green), (0.75, red), (1.0, red)]
+    else:
+        # yaml: end (0,100), stops [0 blue, 0.5 red, 0.5 green].  The display-list builder
+        # normalises stops to [0, 1] and moves the end point accordingly
+        # (GradientBuilder::normalize, webrender_api/src/gradient_builder.rs)
+        start, end = (0.0, 0.0), (0.0, 50.0)
+        stops = [(0.0, blue), (1.0, red), (1.0, green)]
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    r = (50.0, 50.0, 250.0, 250.0)
+    lut = t.push_gpu_buffer_f(list(build_gradient_table(stops)))
+    addr = t.push_gpu_cache([(start[0], start[1], end[0], end[1]), (0.0, 200.0, 200.0, 0.0)])
+    hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, pic, (lut, 0, 0, 0))
+    inst = np.stack([brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)])
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H)}
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0)), Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, inst)]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
