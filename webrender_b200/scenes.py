@@ -933,12 +933,25 @@ def reftest_gradient_frame(which="linear"):
     from .gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
     W = H = 300
     red, green, blue, black = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0), (0.0, 0.0, 0.0, 1.0)
+    clear = (0.0, 0.0, 0.0, 0.0)
+    r = (50.0, 50.0, 250.0, 250.0)
+    blend = abi.BLEND_NONE
     if which == "linear":
         start, end = (0.0, 100.0), (200.0, 100.0)
         stops = [(0.0, red), (0.25, red), (0.25, green), (0.5, green), (0.5, blue), (0.75, blue), (0.75, black), (1.0, black)]
     elif which == "linear-reverse":
         start, end = (200.0, 100.0), (0.0, 100.0)
         stops = [(0.0, black), (0.25, black), (0.25, blue), (0.5, blue), (0.5, green), (0.75, green), (0.75, red), (1.0, red)]
+    elif which in ("premultiplied-aligned", "premultiplied-angle"):
+        # red -> transparent black -> green: stop colours are premultiplied when the table is
+        # built, the brush goes to the alpha pass (premultiplied over the white page)
+        start, end = ((0.0, 100.0), (200.0, 100.0)) if which.endswith("aligned") else ((0.0, 0.0), (200.0, 200.0))
+        stops = [(0.0, red), (0.5, clear), (1.0, green)]
+        blend = abi.BLEND_PREMULTIPLIED_ALPHA
+    elif which == "linear-stops":
+        r = (0.0, 0.0, 200.0, 200.0)
+        start, end = (0.0, 100.0), (200.0, 100.0)
+        stops = [(0.0, red), (0.5, green), (1.0, blue)]
     else:
         # yaml: end (0,100), stops [0 blue, 0.5 red, 0.5 green].  The display-list builder
         # normalises stops to [0, 1] and moves the end point accordingly
@@ -947,11 +960,12 @@ def reftest_gradient_frame(which="linear"):
         stops = [(0.0, blue), (1.0, red), (1.0, green)]
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
-    r = (50.0, 50.0, 250.0, 250.0)
     lut = t.push_gpu_buffer_f(list(build_gradient_table(stops)))
     addr = t.push_gpu_cache([(start[0], start[1], end[0], end[1]), (0.0, 200.0, 200.0, 0.0)])
     hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, pic, (lut, 0, 0, 0))
     inst = np.stack([brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)])
     textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H)}
-    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0)), Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, inst)]
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0)),
+           Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, inst, blend=blend,
+                 features=abi.FEAT_ALPHA_PASS if blend != abi.BLEND_NONE else 0)]
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
