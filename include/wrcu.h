@@ -76,7 +76,15 @@ typedef enum wrcu_kind {
   WRCU_KIND_COMPOSITE = 12,            /* composite [FAST_PATH]            */
   WRCU_KIND_CLEAR = 13,                /* ps_clear                         */
   WRCU_KIND_BLUR = 14,                 /* cs_blur      */
-  WRCU_KIND_SCALE = 15                 /* cs_scale                         */
+  WRCU_KIND_SCALE = 15,                /* cs_scale                         */
+  /* texture-cache-target render tasks (renderer/mod.rs:3931-4200) */
+  WRCU_KIND_FAST_LINEAR_GRADIENT = 16, /* cs_fast_linear_gradient          */
+  WRCU_KIND_LINEAR_GRADIENT = 17,      /* cs_linear_gradient               */
+  WRCU_KIND_RADIAL_GRADIENT = 18,      /* cs_radial_gradient               */
+  WRCU_KIND_CONIC_GRADIENT = 19,       /* cs_conic_gradient                */
+  WRCU_KIND_LINE_DECORATION = 20,      /* cs_line_decoration               */
+  WRCU_KIND_BORDER_SOLID = 21,         /* cs_border_solid                  */
+  WRCU_KIND_BORDER_SEGMENT = 22        /* cs_border_segment                */
 } wrcu_kind;
 
 /* Shader feature bits (webrender_build/src/shader_features.rs:64-247). */

@@ -126,6 +126,17 @@ ATTRIBS = {
     abi.KIND_BLUR: [("aBlurRenderTaskAddress", 1, "i"), ("aBlurSourceTaskAddress", 1, "i"),
                     ("aBlurDirection", 1, "i"), ("aBlurParams", 3, "f")],
     abi.KIND_SCALE: [("aScaleTargetRect", 4, "f"), ("aScaleSourceRect", 4, "f"), ("aSourceRectType", 1, "f")],
+    # cached gradient tasks (prim_store/gradient/{linear,radial,conic}.rs instance structs)
+    abi.KIND_FAST_LINEAR_GRADIENT: [("aTaskRect", 4, "f"), ("aColor0", 4, "f"), ("aColor1", 4, "f"),
+                                    ("aAxisSelect", 1, "f")],
+    abi.KIND_LINEAR_GRADIENT: [("aTaskRect", 4, "f"), ("aStartPoint", 2, "f"), ("aEndPoint", 2, "f"),
+                               ("aScale", 2, "f"), ("aExtendMode", 1, "i"), ("aGradientStopsAddress", 1, "i")],
+    abi.KIND_RADIAL_GRADIENT: [("aTaskRect", 4, "f"), ("aCenter", 2, "f"), ("aScale", 2, "f"),
+                               ("aStartRadius", 1, "f"), ("aEndRadius", 1, "f"), ("aXYRatio", 1, "f"),
+                               ("aExtendMode", 1, "i"), ("aGradientStopsAddress", 1, "i")],
+    abi.KIND_CONIC_GRADIENT: [("aTaskRect", 4, "f"), ("aCenter", 2, "f"), ("aScale", 2, "f"),
+                              ("aStartOffset", 1, "f"), ("aEndOffset", 1, "f"), ("aAngle", 1, "f"),
+                              ("aExtendMode", 1, "i"), ("aGradientStopsAddress", 1, "i")],
 }
 
 

@@ -19,6 +19,7 @@
 #include "brush_mix_blend.h"
 #include "cs_blur.h"
 #include "cs_scale.h"
+#include "cs_gradients.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -51,5 +52,9 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "cs_blur ALPHA_TARGET")) return cs_blur_ALPHA_TARGET_program::loader;
   if (!strcmp(name, "cs_blur COLOR_TARGET")) return cs_blur_COLOR_TARGET_program::loader;
   if (!strcmp(name, "cs_scale TEXTURE_2D")) return cs_scale_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "cs_fast_linear_gradient")) return cs_fast_linear_gradient_program::loader;
+  if (!strcmp(name, "cs_linear_gradient")) return cs_linear_gradient_program::loader;
+  if (!strcmp(name, "cs_radial_gradient")) return cs_radial_gradient_program::loader;
+  if (!strcmp(name, "cs_conic_gradient")) return cs_conic_gradient_program::loader;
   return nullptr;
 }

@@ -210,3 +210,19 @@ def test_cs_blur(seed, color):
 def test_cs_scale(seed, variant):
     f = scenes.scale_frame(seed=seed, r8=variant == "r8", filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+CS_GRADIENT_KINDS = {"fast_linear": abi.KIND_FAST_LINEAR_GRADIENT, "linear": abi.KIND_LINEAR_GRADIENT,
+                     "radial": abi.KIND_RADIAL_GRADIENT, "conic": abi.KIND_CONIC_GRADIENT}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["plain", "repeat", "hard"])
+@pytest.mark.parametrize("kind", list(CS_GRADIENT_KINDS))
+def test_cached_gradient_tasks(kind, variant, seed):
+    """cs_{fast_linear,linear,radial,conic}_gradient render tasks
+    (draw_texture_cache_target): span paths swgl_commitLinearGradientRGBA8
+    (tileRepeat off) and swgl_commitRadialGradientRGBA8 restated exactly."""
+    f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], seed=seed, repeat=variant == "repeat",
+                                     hard=variant == "hard")
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), kind + "/" + variant)

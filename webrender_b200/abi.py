@@ -20,7 +20,9 @@ NEAREST, LINEAR = 0, 1
 (KIND_QUAD_TEXTURED, KIND_QUAD_MASK, KIND_BRUSH_SOLID, KIND_BRUSH_IMAGE,
  KIND_BRUSH_LINEAR_GRADIENT, KIND_BRUSH_BLEND, KIND_BRUSH_MIX_BLEND,
  KIND_BRUSH_OPACITY, KIND_TEXT_RUN, KIND_CLIP_RECTANGLE, KIND_CLIP_BOX_SHADOW,
- KIND_COMPOSITE, KIND_CLEAR, KIND_BLUR, KIND_SCALE) = range(1, 16)
+ KIND_COMPOSITE, KIND_CLEAR, KIND_BLUR, KIND_SCALE,
+ KIND_FAST_LINEAR_GRADIENT, KIND_LINEAR_GRADIENT, KIND_RADIAL_GRADIENT, KIND_CONIC_GRADIENT,
+ KIND_LINE_DECORATION, KIND_BORDER_SOLID, KIND_BORDER_SEGMENT) = range(1, 23)
 
 KIND_PROGRAM = {
     KIND_QUAD_TEXTURED: "ps_quad_textured",
@@ -38,6 +40,13 @@ KIND_PROGRAM = {
     KIND_CLEAR: "ps_clear",
     KIND_BLUR: "cs_blur",
     KIND_SCALE: "cs_scale",
+    KIND_FAST_LINEAR_GRADIENT: "cs_fast_linear_gradient",
+    KIND_LINEAR_GRADIENT: "cs_linear_gradient",
+    KIND_RADIAL_GRADIENT: "cs_radial_gradient",
+    KIND_CONIC_GRADIENT: "cs_conic_gradient",
+    KIND_LINE_DECORATION: "cs_line_decoration",
+    KIND_BORDER_SOLID: "cs_border_solid",
+    KIND_BORDER_SEGMENT: "cs_border_segment",
 }
 
 FEAT_ALPHA_PASS = 1 << 0

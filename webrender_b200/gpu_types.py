@@ -284,3 +284,40 @@ def blur_instance(task_address, src_task_address, direction, std_deviation, blur
     buf[3] = std_deviation
     buf[4:6] = blur_region
     return buf.view(np.uint8).copy()
+
+
+# ---- cached gradient render tasks (draw_texture_cache_target) -------------------
+def fast_linear_gradient_instance(task_rect, color0, color1, axis_select):
+    """FastLinearGradientInstance, 52 bytes (prim_store/gradient/linear.rs:689-694)."""
+    buf = np.zeros(13, dtype=np.float32)
+    buf[0:4], buf[4:8], buf[8:12], buf[12] = task_rect, color0, color1, axis_select
+    return buf.view(np.uint8).copy()
+
+
+def linear_gradient_instance(task_rect, start, end, scale, extend_mode, stops_address):
+    """LinearGradientInstance, 48 bytes (prim_store/gradient/linear.rs:727-734)."""
+    buf = np.zeros(12, dtype=np.float32)
+    buf[0:4], buf[4:6], buf[6:8], buf[8:10] = task_rect, start, end, scale
+    ints = buf.view(np.int32)
+    ints[10], ints[11] = extend_mode, stops_address
+    return buf.view(np.uint8).copy()
+
+
+def radial_gradient_instance(task_rect, center, scale, start_radius, end_radius, ratio_xy, extend_mode, stops_address):
+    """RadialGradientInstance, 52 bytes (prim_store/gradient/radial.rs:375-384)."""
+    buf = np.zeros(13, dtype=np.float32)
+    buf[0:4], buf[4:6], buf[6:8] = task_rect, center, scale
+    buf[8], buf[9], buf[10] = start_radius, end_radius, ratio_xy
+    ints = buf.view(np.int32)
+    ints[11], ints[12] = extend_mode, stops_address
+    return buf.view(np.uint8).copy()
+
+
+def conic_gradient_instance(task_rect, center, scale, start_offset, end_offset, angle, extend_mode, stops_address):
+    """ConicGradientInstance, 52 bytes (prim_store/gradient/conic.rs:409-418)."""
+    buf = np.zeros(13, dtype=np.float32)
+    buf[0:4], buf[4:6], buf[6:8] = task_rect, center, scale
+    buf[8], buf[9], buf[10] = start_offset, end_offset, angle
+    ints = buf.view(np.int32)
+    ints[11], ints[12] = extend_mode, stops_address
+    return buf.view(np.uint8).copy()

@@ -491,6 +491,78 @@ def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, fu
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
 
 
+def _random_stops(rng, premultiplied_alpha=True, hard=False):
+    ns = int(rng.randint(2, 6))
+    offs = [0.0] + sorted(float(v) for v in rng.uniform(0.05, 0.95, ns - 2)) + [1.0]
+    if hard and ns >= 4:
+        offs[2] = offs[1]   # a hard stop
+    stops = []
+    for o in offs:
+        a = float(rng.uniform(0.3, 1.0)) if premultiplied_alpha else 1.0
+        stops.append((o, tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (a,)))
+    return stops
+
+
+def cached_gradient_frame(kind, width=1024, height=512, n_tasks=6, seed=1, repeat=False, hard=False,
+                          big=None):
+    """Gradient render tasks the way draw_texture_cache_target draws them
+    (renderer/mod.rs:4085-4183): blending off, one instance per cached task rect
+    in a texture-cache RGBA8 target.  kind = KIND_{FAST_LINEAR,LINEAR,RADIAL,CONIC}_GRADIENT.
+    Parameters follow the task builders in prim_store/gradient/{linear,radial,conic}.rs:
+    points/radii in task-local device pixels, `scale` = prim size / task size."""
+    from . import gpu_types as G
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    inst = []
+    x_cursor, y_cursor, row_h = 3, 2, 0
+    for i in range(n_tasks):
+        if big:
+            w, h = big
+            x0, y0 = 0, 0
+        else:
+            w, h = int(rng.randint(17, 330)), int(rng.randint(9, 200))
+            if x_cursor + w > width - 2:
+                x_cursor, y_cursor, row_h = 3, y_cursor + row_h + 3, 0
+            x0, y0 = x_cursor, y_cursor
+            x_cursor += w + 5
+            row_h = max(row_h, h)
+        rect = (float(x0), float(y0), float(x0 + w), float(y0 + h))
+        sc = (float(rng.uniform(1.0, 2.5)), float(rng.uniform(1.0, 2.5))) if i % 3 else (1.0, 1.0)
+        pw, ph = w * sc[0], h * sc[1]
+        ext = 1 if (repeat or (i % 4 == 3)) else 0
+        if kind == abi.KIND_FAST_LINEAR_GRADIENT:
+            c0 = tuple(float(v) for v in rng.uniform(0, 1, 4))
+            c1 = tuple(float(v) for v in rng.uniform(0, 1, 4))
+            inst.append(G.fast_linear_gradient_instance(rect, c0, c1, float(i % 2)))
+            continue
+        if (len(t.gpu_buffer_f) % 1024) + 260 > 1024:
+            t.push_gpu_buffer_f([(0, 0, 0, 0)] * ((-len(t.gpu_buffer_f)) % 1024))
+        lut = t.push_gpu_buffer_f(list(G.build_gradient_table(_random_stops(rng, True, hard))))
+        if kind == abi.KIND_LINEAR_GRADIENT:
+            start = (float(rng.uniform(-0.2, 0.6) * pw), float(rng.uniform(-0.2, 0.6) * ph))
+            end = (float(rng.uniform(0.3, 1.2) * pw), float(rng.uniform(-0.3, 1.2) * ph))
+            if i % 5 == 4:
+                end = (start[0], end[1] + 1.0)       # vertical: constant offset along a row
+            if ext:
+                end = (start[0] + (end[0] - start[0]) * 0.3, start[1] + (end[1] - start[1]) * 0.3)
+            inst.append(G.linear_gradient_instance(rect, start, end, sc, ext, lut))
+        elif kind == abi.KIND_RADIAL_GRADIENT:
+            center = (float(rng.uniform(-0.1, 1.1) * pw), float(rng.uniform(-0.1, 1.1) * ph))
+            r0 = float(rng.uniform(0, 0.2) * pw) if i % 2 else 0.0
+            r1 = r0 + float(rng.uniform(0.1, 0.9) * pw) * (0.3 if ext else 1.0)
+            ratio = float(rng.uniform(0.5, 2.0)) if i % 3 == 1 else 1.0
+            inst.append(G.radial_gradient_instance(rect, center, sc, r0, r1, ratio, ext, lut))
+        else:
+            center = (float(rng.uniform(0.1, 0.9) * pw), float(rng.uniform(0.1, 0.9) * ph))
+            so = float(rng.uniform(0.0, 0.3)) if i % 2 else 0.0
+            eo = so + (float(rng.uniform(0.2, 0.5)) if ext else 1.0 - so)
+            ang = float(rng.uniform(0, 2 * np.pi)) if i % 3 else 0.0
+            inst.append(G.conic_gradient_instance(rect, center, sc, so, eo, ang, ext, lut))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    ops = [Clear(color=(0.0, 0.0, 0.0, 0.0)), Batch(kind, np.stack(inst), blend=abi.BLEND_NONE)]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
 def shadow_mask_texture(size=256, seed=5):
     """A seeded stand-in for the blurred box-shadow masks cs_blur produces
     (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
