@@ -332,3 +332,37 @@ def test_binned_batch_mixed_sizes():
     masks, large ones through the wide mask; blend order must survive."""
     f = scenes.alpha_rects_frame(1920, 1080, 900, random_rects=True, seed=11, color=None)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+CS_GRADIENT_KINDS = {"fast_linear": abi.KIND_FAST_LINEAR_GRADIENT, "linear": abi.KIND_LINEAR_GRADIENT,
+                     "radial": abi.KIND_RADIAL_GRADIENT, "conic": abi.KIND_CONIC_GRADIENT}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["plain", "repeat", "hard"])
+@pytest.mark.parametrize("kind", list(CS_GRADIENT_KINDS))
+def test_cached_gradient_tasks(kind, variant, seed):
+    """Cached gradient render tasks (draw_texture_cache_target).  Bit-exact; the
+    conic gradient's angle comes from libm atan2f in the reference and from a
+    correctly rounded atan2 on the device, so a conic pixel whose offset lands
+    within an ulp of a LUT entry boundary may differ by 1 LSB."""
+    f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], seed=seed, repeat=variant == "repeat",
+                                     hard=variant == "hard")
+    a = render(CudaDevice, f, ["target"])["target"]
+    b = render(OracleDevice, f, ["target"])["target"]
+    if kind != "conic":
+        assert (a == b).all(), (kind, variant, int((a != b).sum()))
+        return
+    d = np.abs(a.astype(int) - b.astype(int))
+    # hard stops: a pixel exactly on the discontinuity may take either side
+    bad = (d > 1).reshape(d.shape[0], -1, 4).any(axis=2)
+    assert bad.sum() <= (8 if variant == "hard" else 0), (kind, variant, int(bad.sum()), int(d.max()))
+    assert (d > 0).reshape(d.shape[0], -1, 4).any(axis=2).mean() < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["linear", "radial"])
+def test_cached_gradient_full_width(kind):
+    """One 3840-wide task: the span walks cross 30 tiles per row."""
+    f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], width=3840, height=64, n_tasks=1, seed=5,
+                                     big=(3840, 64))
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)

@@ -205,3 +205,23 @@ def test_cs_blur(seed, color):
 def test_cs_scale(seed, variant):
     f = scenes.scale_frame(seed=seed, r8=variant == "r8", filter=abi.NEAREST if variant == "nearest" else abi.LINEAR)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+CS_GRADIENT_KINDS = {"fast_linear": abi.KIND_FAST_LINEAR_GRADIENT, "linear": abi.KIND_LINEAR_GRADIENT,
+                     "radial": abi.KIND_RADIAL_GRADIENT, "conic": abi.KIND_CONIC_GRADIENT}
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["plain", "repeat", "hard"])
+@pytest.mark.parametrize("kind", list(CS_GRADIENT_KINDS))
+def test_cached_gradient_tasks(kind, variant, seed):
+    f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], seed=seed, repeat=variant == "repeat",
+                                     hard=variant == "hard")
+    assert_same(render(EmuDevice, f), render(OracleDevice, f), kind + "/" + variant)
+
+
+@pytest.mark.parametrize("kind", ["linear", "radial"])
+def test_cached_gradient_wide_task(kind):
+    """One 700-wide task: the span walk is resumed in six tiles per row."""
+    f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], width=704, height=40, n_tasks=1, seed=5, big=(700, 37))
+    assert_same(render(EmuDevice, f), render(OracleDevice, f), kind)

@@ -376,18 +376,8 @@ WRD void wr_setup_brush_linear_gradient_one(const SetupArgs& a, int idx) {
   float dd = dirx * dirx + diry * diry;
   float sdx = dirx / dd, sdy = diry / dd;
   int address = vs.ph.user_data[0];
-  // swgl_validateGradient (swgl_ext.h:1336-1348): 130 entries x 2 texels inside one row
-  int ax = (int)((uint32_t)address % 1024U);
-  bool valid = address >= 0 && ax + 260 <= 1024 && address + 260 <= T.n_gpu_buffer_f;
-  uint32_t merge[5] = {0, 0, 0, 0, 0};
-  if (valid) {
-    float4 prev = __ldg(T.gpu_buffer_f + address + 1);
-    for (int e = 0; e < 129; e++) {
-      float4 nx = __ldg(T.gpu_buffer_f + address + 2 * (e + 1) + 1);
-      if (prev.x == nx.x && prev.y == nx.y && prev.z == nx.z && prev.w == nx.w) merge[e >> 5] |= 1u << (e & 31);
-      prev = nx;
-    }
-  }
+  uint32_t merge[5];
+  bool valid = wr_grad_validate_merge(T, address, merge);
   float white[4] = {1.0f, 1.0f, 1.0f, 1.0f};
   wr_pack_color(q, white);
   int unsupported = 0;
@@ -400,6 +390,7 @@ WRD void wr_setup_brush_linear_gradient_one(const SetupArgs& a, int idx) {
     k->f[3] = (float)(extend_mode == 1);
     k->i[0] = address;
     k->i[1] = valid ? 1 : 0;
+    k->i[2] = 0;  // tileRepeat on
     for (int i = 0; i < 5; i++) k->g[i] = __uint_as_float(merge[i]);
   }
   wr_finish_setup(a, unsupported);

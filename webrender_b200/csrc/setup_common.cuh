@@ -31,6 +31,7 @@ struct SetupArgs {
   int* err_counter;
   int blend_enabled;
   uint32_t features;
+  int kind;  // WRCU_KIND_* (setup functions shared by several kinds)
   TexView color0;
   TexView color1;
   TexView clip_mask;
@@ -366,4 +367,21 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
   // cold record is written by the caller after it fills the kind-specific part
   a.cold[idx] = k;
   return ok;
+}
+
+// swgl_validateGradient (swgl_ext.h:1336-1348): the 130-entry x 2-texel table must
+// sit inside one 1024-texel row of gpu_buffer_f.  Also precomputes the span
+// routines' can_merge test (stops[e].stepColor == stops[e+1].stepColor) as bit e.
+WRD bool wr_grad_validate_merge(const FrameTablesDev& T, int address, uint32_t* merge) {
+  for (int i = 0; i < 5; i++) merge[i] = 0;
+  int ax = (int)((uint32_t)address % 1024U);
+  bool valid = address >= 0 && ax + 260 <= 1024 && address + 260 <= T.n_gpu_buffer_f;
+  if (!valid) return false;
+  float4 prev = __ldg(T.gpu_buffer_f + address + 1);
+  for (int e = 0; e < 129; e++) {
+    float4 nx = __ldg(T.gpu_buffer_f + address + 2 * (e + 1) + 1);
+    if (prev.x == nx.x && prev.y == nx.y && prev.z == nx.z && prev.w == nx.w) merge[e >> 5] |= 1u << (e & 31);
+    prev = nx;
+  }
+  return true;
 }

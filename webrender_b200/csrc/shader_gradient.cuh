@@ -18,6 +18,7 @@
 // CmdCold for linear gradients:
 //  f[0..1] v_scale_dir, f[2] v_start_offset, f[3] v_gradient_repeat,
 //  i[0] v_gradient_address, i[1] table passes swgl_validateGradient,
+//  i[2] != 0: tileRepeat off (cs_linear_gradient: v_pos is not wrapped to [0,1)),
 //  g[0..4] merge mask (bit e: step[e] == step[e+1]), as float bit patterns
 #define GRAD_SIZE 128.0f
 
@@ -83,7 +84,7 @@ struct GradRowConst {
 WRD void wr_grad_offsets(const CmdCold& k, const GradWalk& w, float* off, float* rx0, float* ry0) {
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    float rx = wr_fract(w.px[j]), ry = wr_fract(w.py[j]);
+    float rx = k.i[2] ? w.px[j] : wr_fract(w.px[j]), ry = k.i[2] ? w.py[j] : wr_fract(w.py[j]);
     if (j == 0) { *rx0 = rx; *ry0 = ry; }
     float o = rx * k.f[0] + ry * k.f[1] - k.f[2];
     if (k.f[3] != 0.0f) o = wr_fract(o);
@@ -241,12 +242,12 @@ struct GradientShader {
     if (!isfinite(rc.delta)) { r.body_len = 0; return; }
     rc.dcx0 = 0.25f * (float)r.body_len; rc.dcx1 = 0.0f;
     rc.dcy0 = rc.dcx0; rc.dcy1 = 0.0f;
-    if (rc.psx != 0.0f) {
+    if (!k.i[2] && rc.psx != 0.0f) {
       float rr = 1.0f / rc.psx;
       rc.dcx0 = (rc.psx >= 0.0f ? 1.0f : 0.0f) * rr;
       rc.dcx1 = 1.0f * rr;
     }
-    if (rc.psy != 0.0f) {
+    if (!k.i[2] && rc.psy != 0.0f) {
       float rr = 1.0f / rc.psy;
       rc.dcy0 = (rc.psy >= 0.0f ? 1.0f : 0.0f) * rr;
       rc.dcy1 = 1.0f * rr;
@@ -301,7 +302,8 @@ struct GradientShader {
     // fragment path (brush_linear_gradient.glsl:73-91, gradient.glsl:45-61)
     float p[2];
     wr_interp_at<2>(r.o, r.step, rel, p);
-    float offset = (wr_fract(p[0]) * k.f[0] + wr_fract(p[1]) * k.f[1]) - k.f[2];
+    if (!k.i[2]) { p[0] = wr_fract(p[0]); p[1] = wr_fract(p[1]); }
+    float offset = (p[0] * k.f[0] + p[1] * k.f[1]) - k.f[2];
     offset = offset - floorf(offset) * k.f[3];
     float xx = wr_clamp(1.0f + offset * GRAD_SIZE, 0.0f, 1.0f + GRAD_SIZE);
     float ei = floorf(xx), ef = xx - ei;

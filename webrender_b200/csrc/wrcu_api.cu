@@ -18,6 +18,7 @@
 #include "shader_mix_blend.cuh"
 #include "shader_blur.cuh"
 #include "shader_scale.cuh"
+#include "shader_cs_gradient.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -667,6 +668,16 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_scale, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_FAST_LINEAR_GRADIENT:
+    case WRCU_KIND_LINEAR_GRADIENT:
+    case WRCU_KIND_RADIAL_GRADIENT:
+    case WRCU_KIND_CONIC_GRADIENT:
+      if (stride < (kind == WRCU_KIND_LINEAR_GRADIENT ? 48u : 52u))
+        return wrcu_fail(c, WRCU_ERR_INVALID, "gradient task instance stride too small");
+      sa.features = features;
+      sa.kind = kind;
+      WR_LAUNCH(wr_setup_cs_gradient, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_BLUR:
       if (stride < 24) return wrcu_fail(c, WRCU_ERR_INVALID, "BlurInstance stride < 24");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "cs_blur without sColor0");
@@ -800,6 +811,10 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER(MixBlendShader); break;
     case WRCU_KIND_BLUR: LAUNCH_RASTER(BlurShader); break;
     case WRCU_KIND_SCALE: LAUNCH_RASTER(ScaleShader); break;
+    case WRCU_KIND_FAST_LINEAR_GRADIENT: LAUNCH_RASTER(FastLinearShader); break;
+    case WRCU_KIND_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
+    case WRCU_KIND_RADIAL_GRADIENT: LAUNCH_RASTER(RadialShader); break;
+    case WRCU_KIND_CONIC_GRADIENT: LAUNCH_RASTER(ConicShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER
@@ -817,7 +832,9 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"brush_mix_blend", WRCU_KIND_BRUSH_MIX_BLEND}, {"brush_opacity", WRCU_KIND_BRUSH_OPACITY},
       {"ps_text_run", WRCU_KIND_TEXT_RUN}, {"cs_clip_rectangle", WRCU_KIND_CLIP_RECTANGLE},
       {"cs_clip_box_shadow", WRCU_KIND_CLIP_BOX_SHADOW}, {"composite", WRCU_KIND_COMPOSITE},
-      {"ps_clear", WRCU_KIND_CLEAR}, {"cs_blur", WRCU_KIND_BLUR}, {"cs_scale", WRCU_KIND_SCALE}};
+      {"ps_clear", WRCU_KIND_CLEAR}, {"cs_blur", WRCU_KIND_BLUR}, {"cs_scale", WRCU_KIND_SCALE},
+      {"cs_fast_linear_gradient", WRCU_KIND_FAST_LINEAR_GRADIENT}, {"cs_linear_gradient", WRCU_KIND_LINEAR_GRADIENT},
+      {"cs_radial_gradient", WRCU_KIND_RADIAL_GRADIENT}, {"cs_conic_gradient", WRCU_KIND_CONIC_GRADIENT}};
   static const struct { const char* name; uint32_t bit; } feats[] = {
       {"ALPHA_PASS", WRCU_FEAT_ALPHA_PASS}, {"FAST_PATH", WRCU_FEAT_FAST_PATH},
       {"ANTIALIASING", WRCU_FEAT_ANTIALIASING}, {"REPETITION", WRCU_FEAT_REPETITION},
