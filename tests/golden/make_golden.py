@@ -51,6 +51,13 @@ CASES = [
     ("reftest_clip_ellipse", "reftest_clip_frame", dict(which="clip-ellipse")),
     ("reftest_gradient_linear", "reftest_gradient_frame", dict(which="linear")),
     ("reftest_gradient_hard_stop", "reftest_gradient_frame", dict(which="linear-hard-stop")),
+    # cached gradient render tasks (kind = wrcu_kind value)
+    ("cs_fast_linear_gradient", "cached_gradient_frame", dict(kind=16, width=512, height=256, n_tasks=4, seed=2)),
+    ("cs_linear_gradient", "cached_gradient_frame", dict(kind=17, width=512, height=256, n_tasks=4, seed=2)),
+    ("cs_radial_gradient", "cached_gradient_frame", dict(kind=18, width=512, height=256, n_tasks=4, seed=4)),
+    ("cs_radial_gradient_repeat", "cached_gradient_frame", dict(kind=18, width=512, height=256, n_tasks=4, seed=3,
+                                                                 repeat=True, hard=True)),
+    ("cs_conic_gradient", "cached_gradient_frame", dict(kind=19, width=512, height=256, n_tasks=4, seed=2)),
 ]
 
 
@@ -59,10 +66,15 @@ def main():
     from oracle.backends import SwglDevice
     from webrender_b200 import scenes
     index = {}
+    regenerate_all = "--all" in sys.argv   # default: only cases whose fixture is missing
     for name, builder, kwargs in CASES:
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path) and not regenerate_all:
+            index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(np.load(path).files)}
+            continue
         frame = getattr(scenes, builder)(**kwargs)
         out = render(SwglDevice, frame)
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        np.savez_compressed(path, **out)
         index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(out)}
         print(name, {k: v.shape for k, v in out.items()})
     json.dump(index, open(os.path.join(HERE, "index.json"), "w"), indent=1, sort_keys=True)
