@@ -107,6 +107,8 @@ SLOTS = dict(sColor0=0, sColor1=1, sColor2=2, sGpuCache=3, sTransformPalette=4, 
 _PRIM = [("aData", 4, "i")]
 _CLIP_COMMON = [("aClipDeviceArea", 4, "f"), ("aClipOrigins", 4, "f"), ("aDevicePixelScale", 1, "f"),
                 ("aTransformIds", 2, "i")]
+_BORDER = [("aTaskOrigin", 2, "f"), ("aRect", 4, "f"), ("aColor0", 4, "f"), ("aColor1", 4, "f"), ("aFlags", 1, "i"),
+           ("aWidths", 2, "f"), ("aRadii", 2, "f"), ("aClipParams1", 4, "f"), ("aClipParams2", 4, "f")]
 ATTRIBS = {
     abi.KIND_QUAD_TEXTURED: _PRIM, abi.KIND_BRUSH_SOLID: _PRIM, abi.KIND_BRUSH_IMAGE: _PRIM,
     abi.KIND_BRUSH_LINEAR_GRADIENT: _PRIM, abi.KIND_BRUSH_BLEND: _PRIM, abi.KIND_BRUSH_MIX_BLEND: _PRIM,
@@ -134,6 +136,9 @@ ATTRIBS = {
     abi.KIND_RADIAL_GRADIENT: [("aTaskRect", 4, "f"), ("aCenter", 2, "f"), ("aScale", 2, "f"),
                                ("aStartRadius", 1, "f"), ("aEndRadius", 1, "f"), ("aXYRatio", 1, "f"),
                                ("aExtendMode", 1, "i"), ("aGradientStopsAddress", 1, "i")],
+    abi.KIND_LINE_DECORATION: [("aTaskRect", 4, "f"), ("aLocalSize", 2, "f"), ("aWavyLineThickness", 1, "f"),
+                               ("aStyle", 1, "i"), ("aAxisSelect", 1, "f")],
+    abi.KIND_BORDER_SOLID: _BORDER, abi.KIND_BORDER_SEGMENT: _BORDER,
     abi.KIND_CONIC_GRADIENT: [("aTaskRect", 4, "f"), ("aCenter", 2, "f"), ("aScale", 2, "f"),
                               ("aStartOffset", 1, "f"), ("aEndOffset", 1, "f"), ("aAngle", 1, "f"),
                               ("aExtendMode", 1, "i"), ("aGradientStopsAddress", 1, "i")],

@@ -20,6 +20,7 @@
 #include "cs_blur.h"
 #include "cs_scale.h"
 #include "cs_gradients.h"
+#include "cs_border_line.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -56,5 +57,8 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "cs_linear_gradient")) return cs_linear_gradient_program::loader;
   if (!strcmp(name, "cs_radial_gradient")) return cs_radial_gradient_program::loader;
   if (!strcmp(name, "cs_conic_gradient")) return cs_conic_gradient_program::loader;
+  if (!strcmp(name, "cs_line_decoration")) return cs_line_decoration_program::loader;
+  if (!strcmp(name, "cs_border_solid")) return cs_border_solid_program::loader;
+  if (!strcmp(name, "cs_border_segment")) return cs_border_segment_program::loader;
   return nullptr;
 }

@@ -226,3 +226,21 @@ def test_cached_gradient_tasks(kind, variant, seed):
     f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], seed=seed, repeat=variant == "repeat",
                                      hard=variant == "hard")
     assert_same(render(SwglDevice, f), render(OracleDevice, f), kind + "/" + variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_line_decoration_tasks(seed):
+    """cs_line_decoration: solid / dotted / dashed / wavy masks at several device scales."""
+    f = scenes.line_decoration_frame(seed=seed)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("scale", [1.0, 1.5])
+@pytest.mark.parametrize("kind", ["solid", "segment"])
+def test_border_tasks(kind, scale, seed):
+    """cs_border_solid / cs_border_segment: corner and edge tasks with elliptical
+    corner clips, adjacent-corner clips, double/groove/ridge styling, dash and dot clips."""
+    f = scenes.border_frame(abi.KIND_BORDER_SOLID if kind == "solid" else abi.KIND_BORDER_SEGMENT, seed=seed,
+                            scale=scale)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), kind)

@@ -321,3 +321,31 @@ def conic_gradient_instance(task_rect, center, scale, start_offset, end_offset, 
     ints = buf.view(np.int32)
     ints[11], ints[12] = extend_mode, stops_address
     return buf.view(np.uint8).copy()
+
+
+# ---- border / line-decoration render tasks ------------------------------------------
+SEGMENT_TOP_LEFT, SEGMENT_TOP_RIGHT, SEGMENT_BOTTOM_RIGHT, SEGMENT_BOTTOM_LEFT = 0, 1, 2, 3
+SEGMENT_LEFT, SEGMENT_TOP, SEGMENT_RIGHT, SEGMENT_BOTTOM = 4, 5, 6, 7
+(BORDER_STYLE_NONE, BORDER_STYLE_SOLID, BORDER_STYLE_DOUBLE, BORDER_STYLE_DOTTED, BORDER_STYLE_DASHED,
+ BORDER_STYLE_HIDDEN, BORDER_STYLE_GROOVE, BORDER_STYLE_RIDGE, BORDER_STYLE_INSET, BORDER_STYLE_OUTSET) = range(10)
+BORDER_CLIP_NONE, BORDER_CLIP_DASH_CORNER, BORDER_CLIP_DASH_EDGE, BORDER_CLIP_DOT = 0, 1, 2, 3
+
+
+def border_instance(task_origin, local_rect, color0, color1, segment, style0, style1, do_aa, widths, radius,
+                    clip_kind=0, clip_params=(0,) * 8):
+    """BorderInstance, 108 bytes (gpu_types.rs:193-202); flags as border.rs:920-923:
+    segment | style0 << 8 | style1 << 16 | clip_kind << 24 | do_aa << 28."""
+    buf = np.zeros(27, dtype=np.float32)
+    buf[0:2], buf[2:6], buf[6:10], buf[10:14] = task_origin, local_rect, color0, color1
+    buf.view(np.int32)[14] = segment | (style0 << 8) | (style1 << 16) | (clip_kind << 24) | (int(bool(do_aa)) << 28)
+    buf[15:17], buf[17:19], buf[19:27] = widths, radius, clip_params
+    return buf.view(np.uint8).copy()
+
+
+def line_decoration_instance(task_rect, local_size, wavy_line_thickness, style, axis_select):
+    """LineDecorationJob, 36 bytes (render_target.rs:1184-1190); style: 0 solid, 1 dotted, 2 dashed, 3 wavy."""
+    buf = np.zeros(9, dtype=np.float32)
+    buf[0:4], buf[4:6], buf[6] = task_rect, local_size, wavy_line_thickness
+    buf.view(np.int32)[7] = style
+    buf[8] = axis_select
+    return buf.view(np.uint8).copy()

@@ -563,6 +563,200 @@ def cached_gradient_frame(kind, width=1024, height=512, n_tasks=6, seed=1, repea
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
 
 
+class _ShelfPacker:
+    """Places render-task rects in a texture-cache target, shelf by shelf."""
+
+    def __init__(self, width, height, pad=2):
+        self.w, self.h, self.pad = width, height, pad
+        self.x, self.y, self.row_h = pad, pad, 0
+
+    def place(self, w, h):
+        if self.x + w > self.w - self.pad:
+            self.x, self.y, self.row_h = self.pad, self.y + self.row_h + self.pad, 0
+        if self.y + h > self.h - self.pad:
+            return None
+        x0, y0 = self.x, self.y
+        self.x += w + self.pad
+        self.row_h = max(self.row_h, h)
+        return x0, y0
+
+
+def line_decoration_frame(width=512, height=256, n_tasks=24, seed=1):
+    """cs_line_decoration tasks (renderer/mod.rs:4059-4083): premultiplied-alpha
+    blending on, one LineDecorationJob per cached tile: solid / dotted / dashed /
+    wavy, horizontal and vertical, at device scales 1, 1.5 and 2 (the task rect is
+    the local size times the device scale, so the AA range varies)."""
+    from . import gpu_types as G
+    rng = np.random.RandomState(seed)
+    pack = _ShelfPacker(width, height)
+    inst = []
+    for i in range(n_tasks):
+        style = i % 4
+        vertical = (i // 4) % 2
+        t = float(rng.choice([1.0, 1.5, 2.0, 3.0, 5.0, 8.0]))
+        scale = float(rng.choice([1.0, 1.5, 2.0]))
+        if style == 2:      # dashed: period x thickness
+            size = (6.0 * t, t)
+        elif style == 1:    # dotted: two diameters x diameter
+            size = (2.0 * t, t)
+        elif style == 3:    # wavy
+            lt = max(t, 1.0)
+            h = float(np.ceil(lt * 3.0 + rng.randint(0, 4)))
+            slope, flat = h - lt, max((lt - 1.0) * 2.0, 1.0)
+            size = (2.0 * (slope + flat), h)
+        else:
+            size = (float(rng.randint(8, 40)), t)
+        if vertical:
+            size = (size[1], size[0])
+        tw, th = int(np.ceil(size[0] * scale)), int(np.ceil(size[1] * scale))
+        at = pack.place(tw, th)
+        if at is None:
+            break
+        rect = (float(at[0]), float(at[1]), float(at[0] + tw), float(at[1] + th))
+        inst.append(G.line_decoration_instance(rect, size, t, style, float(vertical)))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    ops = [Clear(color=(0.0, 0.0, 0.0, 0.0)),
+           Batch(abi.KIND_LINE_DECORATION, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA)]
+    return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
+
+
+def _ellipse_point_tangent(rx, ry, theta):
+    c, s = float(np.cos(theta)), float(np.sin(theta))
+    return (rx * c, ry * s), (-rx * s, ry * c)
+
+
+def border_frame(kind, width=1024, height=512, n_borders=6, seed=1, scale=1.0):
+    """Border render tasks (renderer/mod.rs:4015-4057): premultiplied-alpha blending
+    on; per border four corner tasks and four edge tasks as border.rs:904-1243
+    builds them (task-local rects, adjacent-corner clips, dash/dot clip
+    parameters).  kind = KIND_BORDER_SOLID (solid styles, optional AA) or
+    KIND_BORDER_SEGMENT (double/dotted/dashed/groove/ridge/inset/outset).
+    Dash and dot positions along a corner use uniform ellipse angles where the
+    reference solves for arc length (the frame builder is outside this path)."""
+    from . import gpu_types as G
+    rng = np.random.RandomState(seed)
+    pack = _ShelfPacker(width, height)
+    inst = []
+    f32 = np.float32
+    solid = kind == abi.KIND_BORDER_SOLID
+    styles = [G.BORDER_STYLE_DOUBLE, G.BORDER_STYLE_DOTTED, G.BORDER_STYLE_DASHED, G.BORDER_STYLE_GROOVE,
+              G.BORDER_STYLE_RIDGE, G.BORDER_STYLE_INSET, G.BORDER_STYLE_OUTSET]
+
+    def rcolor(black=False):
+        a = float(rng.uniform(0.4, 1.0))
+        rgb = (0.0, 0.0, 0.0) if black else tuple(float(v) for v in rng.uniform(0, 1, 3))
+        return tuple(float(f32(c * a)) for c in rgb) + (a,)
+
+    for b in range(n_borders):
+        wl, wt, wr, wb = [float(f32(rng.choice([1.0, 2.0, 3.0, 4.5, 6.0, 9.0, 14.0]) * scale)) for _ in range(4)]
+        box_w, box_h = float(rng.randint(120, 260)) * scale, float(rng.randint(90, 200)) * scale
+        radii = {}
+        for c in range(4):
+            if b % 3 == 2:
+                radii[c] = (0.0, 0.0)
+            else:
+                radii[c] = (float(f32(rng.uniform(4, 50) * scale)), float(f32(rng.uniform(4, 50) * scale)))
+        do_aa = bool(b % 4 != 3) if solid else True
+        if solid:
+            st = [G.BORDER_STYLE_SOLID] * 4            # left, top, right, bottom
+        else:
+            st = [int(styles[(b + k * (1 if b % 2 else 0)) % len(styles)]) for k in range(4)]
+        col = [rcolor(black=(not solid and b % 5 == 4 and k == 0)) for k in range(4)]
+        side_w = [wl, wt, wr, wb]
+        # corner: (segment, side0 = horizontal-adjacent edge index, side1, widths (x, y), radius)
+        corners = [(G.SEGMENT_TOP_LEFT, 0, 1, (wl, wt), radii[0]), (G.SEGMENT_TOP_RIGHT, 1, 2, (wr, wt), radii[1]),
+                   (G.SEGMENT_BOTTOM_RIGHT, 2, 3, (wr, wb), radii[2]), (G.SEGMENT_BOTTOM_LEFT, 3, 0, (wl, wb), radii[3])]
+        corner_size = {}
+        for seg, s0, s1, wd, rad in corners:
+            corner_size[seg] = (max(rad[0], wd[0]), max(rad[1], wd[1]))
+        # outer corner points of the box, per corner segment
+        outer_pt = {0: (0.0, 0.0), 1: (box_w, 0.0), 2: (box_w, box_h), 3: (0.0, box_h)}
+        corner_org = {0: (0.0, 0.0), 1: (box_w - corner_size[1][0], 0.0),
+                      2: (box_w - corner_size[2][0], box_h - corner_size[2][1]), 3: (0.0, box_h - corner_size[3][1])}
+        h_adj = {0: 1, 1: 0, 2: 3, 3: 2}
+        v_adj = {0: 3, 1: 2, 2: 1, 3: 0}
+        for seg, s0, s1, wd, rad in corners:
+            cw, ch = corner_size[seg]
+            tw, th = int(np.ceil(cw)), int(np.ceil(ch))
+            at = pack.place(tw, th)
+            if at is None:
+                continue
+            org = corner_org[seg]
+            rect = (0.0, 0.0, float(f32(cw)), float(f32(ch)))
+            base = dict(task_origin=(float(at[0]), float(at[1])), local_rect=rect, color0=col[s0], color1=col[s1],
+                        segment=seg, style0=st[s0], style1=st[s1], do_aa=do_aa, widths=wd, radius=rad)
+            hseg, vseg = h_adj[seg], v_adj[seg]
+            adj = (outer_pt[hseg][0] - org[0], outer_pt[hseg][1] - org[1]) + radii[hseg] + \
+                  (outer_pt[vseg][0] - org[0], outer_pt[vseg][1] - org[1]) + radii[vseg]
+            adj = tuple(float(f32(v)) for v in adj)
+            os_ = {0: (0.0, 0.0), 1: (1.0, 0.0), 2: (1.0, 1.0), 3: (0.0, 1.0)}[seg]
+            outer = (os_[0] * rad[0], os_[1] * rad[1])
+            sign = (1.0 - 2.0 * os_[0], 1.0 - 2.0 * os_[1])
+            if not solid and st[s0] == G.BORDER_STYLE_DASHED and rad[0] > 0 and rad[1] > 0:
+                n_dash = 3
+                for k in range(n_dash):
+                    th0 = (np.pi / 2) * (2 * k) / (2 * n_dash - 1) if k else 0.0
+                    th0 = (np.pi / 2) * max(0.0, (2 * k - 0.5)) / (2 * n_dash - 1)
+                    th1 = (np.pi / 2) * (2 * k + 1.0) / (2 * n_dash - 1)
+                    pts = []
+                    for th_ in (th0, th1):
+                        p, t = _ellipse_point_tangent(rad[0], rad[1], th_)
+                        pts += [outer[0] + sign[0] * (rad[0] - p[0]), outer[1] + sign[1] * (rad[1] - p[1]),
+                                -t[0] * sign[0], -t[1] * sign[1]]
+                    inst.append(G.border_instance(clip_kind=G.BORDER_CLIP_DASH_CORNER,
+                                                  clip_params=tuple(float(f32(v)) for v in pts), **base))
+            elif not solid and st[s0] == G.BORDER_STYLE_DOTTED:
+                if rad[0] < wd[0] / 2 or rad[1] < wd[1] / 2:
+                    dd = 0.5 * (wd[0] + wd[1])
+                    inst.append(G.border_instance(clip_kind=G.BORDER_CLIP_DOT,
+                                                  clip_params=(wd[0] / 2, wd[1] / 2, 0.5 * dd, 0, 0, 0, 0, 0), **base))
+                else:
+                    irx, iry = abs(rad[0] - wd[0] * 0.5), abs(rad[1] - wd[1] * 0.5)
+                    n_dot = 4
+                    for k in range(n_dot):
+                        th_ = (np.pi / 2) * k / (n_dot - 1)
+                        p, _ = _ellipse_point_tangent(irx, iry, th_)
+                        cx = outer[0] + sign[0] * (rad[0] - p[0])
+                        cy = outer[1] + sign[1] * (rad[1] - p[1])
+                        dia = wd[0] + (wd[1] - wd[0]) * k / (n_dot - 1)
+                        inst.append(G.border_instance(clip_kind=G.BORDER_CLIP_DOT,
+                                                      clip_params=(float(f32(cx)), float(f32(cy)), float(f32(0.5 * dia)),
+                                                                   0, 0, 0, 0, 0), **base))
+            else:
+                inst.append(G.border_instance(clip_params=adj, **base))
+        # edges: (segment, side index, vertical)
+        for seg, side, vertical in ((G.SEGMENT_LEFT, 0, True), (G.SEGMENT_TOP, 1, False),
+                                    (G.SEGMENT_RIGHT, 2, True), (G.SEGMENT_BOTTOM, 3, False)):
+            wdt = side_w[side]
+            style = st[side]
+            if style == G.BORDER_STYLE_DASHED:
+                length = 6.0 * wdt          # task = one dash period (border.rs get_edge_info)
+            elif style == G.BORDER_STYLE_DOTTED:
+                length = 2.0 * wdt
+            else:
+                length = 8.0
+            size = (wdt, length) if vertical else (length, wdt)
+            tw, th = int(np.ceil(size[0])), int(np.ceil(size[1]))
+            at = pack.place(tw, th)
+            if at is None:
+                continue
+            rect = (0.0, 0.0, float(f32(size[0])), float(f32(size[1])))
+            base = dict(task_origin=(float(at[0]), float(at[1])), local_rect=rect, color0=col[side], color1=col[side],
+                        segment=seg, style0=style, style1=style, do_aa=do_aa, widths=(wdt, wdt), radius=(0.0, 0.0))
+            if not solid and style == G.BORDER_STYLE_DASHED:
+                half = (size[1] if vertical else size[0]) * 0.25
+                cp = (0.0, half) if vertical else (half, 0.0)
+                inst.append(G.border_instance(clip_kind=G.BORDER_CLIP_DASH_EDGE, clip_params=cp + (0,) * 6, **base))
+            elif not solid and style == G.BORDER_STYLE_DOTTED:
+                cp = (wdt * 0.5, wdt, wdt * 0.5) if vertical else (wdt, wdt * 0.5, wdt * 0.5)
+                inst.append(G.border_instance(clip_kind=G.BORDER_CLIP_DOT, clip_params=cp + (0,) * 5, **base))
+            else:
+                inst.append(G.border_instance(**base))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    ops = [Clear(color=(0.0, 0.0, 0.0, 0.0)), Batch(kind, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA)]
+    return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
+
+
 def shadow_mask_texture(size=256, seed=5):
     """A seeded stand-in for the blurred box-shadow masks cs_blur produces
     (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
