@@ -366,3 +366,19 @@ def test_cached_gradient_full_width(kind):
     f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], width=3840, height=64, n_tasks=1, seed=5,
                                      big=(3840, 64))
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_line_decoration_tasks(seed):
+    f = scenes.line_decoration_frame(seed=seed)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("scale", [1.0, 1.5])
+@pytest.mark.parametrize("kind", ["solid", "segment"])
+def test_border_tasks(kind, scale, seed):
+    """cs_border_solid / cs_border_segment render tasks (draw_texture_cache_target)."""
+    f = scenes.border_frame(abi.KIND_BORDER_SOLID if kind == "solid" else abi.KIND_BORDER_SEGMENT, seed=seed,
+                            scale=scale)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)

@@ -225,3 +225,18 @@ def test_cached_gradient_wide_task(kind):
     """One 700-wide task: the span walk is resumed in six tiles per row."""
     f = scenes.cached_gradient_frame(CS_GRADIENT_KINDS[kind], width=704, height=40, n_tasks=1, seed=5, big=(700, 37))
     assert_same(render(EmuDevice, f), render(OracleDevice, f), kind)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_line_decoration_tasks(seed):
+    f = scenes.line_decoration_frame(seed=seed)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("scale", [1.0, 1.5])
+@pytest.mark.parametrize("kind", ["solid", "segment"])
+def test_border_tasks(kind, scale, seed):
+    f = scenes.border_frame(abi.KIND_BORDER_SOLID if kind == "solid" else abi.KIND_BORDER_SEGMENT, seed=seed,
+                            scale=scale)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f), kind)

@@ -19,6 +19,7 @@
 #include "shader_blur.cuh"
 #include "shader_scale.cuh"
 #include "shader_cs_gradient.cuh"
+#include "shader_border.cuh"
 #include "setup_brush.cuh"
 #include "setup_clip.cuh"
 #include "setup_quad.cuh"
@@ -668,6 +669,18 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_scale, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_LINE_DECORATION:
+      if (stride < 36) return wrcu_fail(c, WRCU_ERR_INVALID, "LineDecorationJob stride < 36");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_line_decoration, sblocks, 128, c->stream, sa);
+      break;
+    case WRCU_KIND_BORDER_SOLID:
+    case WRCU_KIND_BORDER_SEGMENT:
+      if (stride < 108) return wrcu_fail(c, WRCU_ERR_INVALID, "BorderInstance stride < 108");
+      sa.features = features;
+      sa.kind = kind;
+      WR_LAUNCH(wr_setup_border, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_FAST_LINEAR_GRADIENT:
     case WRCU_KIND_LINEAR_GRADIENT:
     case WRCU_KIND_RADIAL_GRADIENT:
@@ -815,6 +828,9 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_RADIAL_GRADIENT: LAUNCH_RASTER(RadialShader); break;
     case WRCU_KIND_CONIC_GRADIENT: LAUNCH_RASTER(ConicShader); break;
+    case WRCU_KIND_LINE_DECORATION: LAUNCH_RASTER(LineDecorationShader); break;
+    case WRCU_KIND_BORDER_SOLID: LAUNCH_RASTER(BorderSolidShader); break;
+    case WRCU_KIND_BORDER_SEGMENT: LAUNCH_RASTER(BorderSegmentShader); break;
     default: LAUNCH_RASTER(QuadShader); break;
   }
 #undef LAUNCH_RASTER
@@ -834,7 +850,9 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"cs_clip_box_shadow", WRCU_KIND_CLIP_BOX_SHADOW}, {"composite", WRCU_KIND_COMPOSITE},
       {"ps_clear", WRCU_KIND_CLEAR}, {"cs_blur", WRCU_KIND_BLUR}, {"cs_scale", WRCU_KIND_SCALE},
       {"cs_fast_linear_gradient", WRCU_KIND_FAST_LINEAR_GRADIENT}, {"cs_linear_gradient", WRCU_KIND_LINEAR_GRADIENT},
-      {"cs_radial_gradient", WRCU_KIND_RADIAL_GRADIENT}, {"cs_conic_gradient", WRCU_KIND_CONIC_GRADIENT}};
+      {"cs_radial_gradient", WRCU_KIND_RADIAL_GRADIENT}, {"cs_conic_gradient", WRCU_KIND_CONIC_GRADIENT},
+      {"cs_line_decoration", WRCU_KIND_LINE_DECORATION}, {"cs_border_solid", WRCU_KIND_BORDER_SOLID},
+      {"cs_border_segment", WRCU_KIND_BORDER_SEGMENT}};
   static const struct { const char* name; uint32_t bit; } feats[] = {
       {"ALPHA_PASS", WRCU_FEAT_ALPHA_PASS}, {"FAST_PATH", WRCU_FEAT_FAST_PATH},
       {"ANTIALIASING", WRCU_FEAT_ANTIALIASING}, {"REPETITION", WRCU_FEAT_REPETITION},
