@@ -240,3 +240,8 @@ def test_border_tasks(kind, scale, seed):
     f = scenes.border_frame(abi.KIND_BORDER_SOLID if kind == "solid" else abi.KIND_BORDER_SEGMENT, seed=seed,
                             scale=scale)
     assert_same(render(EmuDevice, f), render(OracleDevice, f), kind)
+
+
+def test_texture_cache_target_all_task_lists():
+    f = scenes.texture_cache_frame(seed=1)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f))

@@ -18,6 +18,7 @@ HOST_LIB = os.path.join(ROOT, "webrender_b200", "libwrhost.so")
 
 SYMBOLS = ["wrh_renderer_create", "wrh_renderer_destroy", "wrh_frame_create", "wrh_frame_destroy", "wrh_frame_add_pass",
            "wrh_pass_add_picture_cache_target", "wrh_pass_add_color_target", "wrh_pass_add_alpha_target",
+           "wrh_pass_add_texture_cache_target", "wrh_texture_cache_target_add_clear", "wrh_texture_cache_target_add_tasks",
            "wrh_picture_target_add_batch", "wrh_color_target_add_batch", "wrh_alpha_target_add_clear",
            "wrh_alpha_target_add_clips", "wrh_target_add_blur_or_scale", "wrh_frame_set_framebuffer", "wrh_frame_add_composite_tile",
            "wrh_renderer_render", "wrh_renderer_last_error"]
@@ -43,6 +44,9 @@ CASES = [
     ("blur_a8", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
     ("blur_rgba8", lambda: scenes.blur_frame(seed=2, color=True), ["mid", "target"]),
     ("scale", lambda: scenes.scale_frame(seed=1), ["target"]),
+    ("texture_cache_target", lambda: scenes.texture_cache_frame(seed=1), ["target"]),
+    ("texture_cache_linear_gradients", lambda: scenes.cached_gradient_frame(abi.KIND_LINEAR_GRADIENT, seed=2), ["target"]),
+    ("texture_cache_conic_gradients", lambda: scenes.cached_gradient_frame(abi.KIND_CONIC_GRADIENT, seed=1), ["target"]),
 ]
 
 

@@ -244,3 +244,10 @@ def test_border_tasks(kind, scale, seed):
     f = scenes.border_frame(abi.KIND_BORDER_SOLID if kind == "solid" else abi.KIND_BORDER_SEGMENT, seed=seed,
                             scale=scale)
     assert_same(render(SwglDevice, f), render(OracleDevice, f), kind)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_texture_cache_target_all_task_lists(seed):
+    """All task lists of one texture-cache target in draw_texture_cache_target's order."""
+    f = scenes.texture_cache_frame(seed=seed)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f))

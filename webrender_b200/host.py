@@ -26,6 +26,9 @@ LIB_PATH = os.path.join(_HERE, "libwrhost.so")
 BATCH_KIND = {abi.KIND_QUAD_TEXTURED: 0, abi.KIND_QUAD_MASK: 1, abi.KIND_BRUSH_SOLID: 2, abi.KIND_BRUSH_IMAGE: 3,
               abi.KIND_BRUSH_BLEND: 4, abi.KIND_BRUSH_MIX_BLEND: 5, abi.KIND_BRUSH_LINEAR_GRADIENT: 6,
               abi.KIND_BRUSH_OPACITY: 7, abi.KIND_TEXT_RUN: 8}
+CACHE_TASK_KINDS = {abi.KIND_BORDER_SOLID, abi.KIND_BORDER_SEGMENT, abi.KIND_LINE_DECORATION,
+                    abi.KIND_FAST_LINEAR_GRADIENT, abi.KIND_LINEAR_GRADIENT, abi.KIND_RADIAL_GRADIENT,
+                    abi.KIND_CONIC_GRADIENT}
 BM_NONE, BM_ALPHA, BM_PREMULT, BM_DEST_OUT, BM_SUBPX_DUAL, BM_ADVANCED, BM_MULT_DUAL, BM_SCREEN, BM_EXCL, BM_PLUS = range(10)
 
 
@@ -65,6 +68,9 @@ class HostRenderer:
         L.wrh_pass_add_picture_cache_target.argtypes = [vp, i32, u32, u32, i32, i32, C.POINTER(C.c_float), C.POINTER(i32)]
         L.wrh_pass_add_color_target.argtypes = [vp, i32, u32, u32, i32, i32]
         L.wrh_pass_add_alpha_target.argtypes = [vp, i32, u32, i32, i32]
+        L.wrh_pass_add_texture_cache_target.argtypes = [vp, i32, u32, i32, i32]
+        L.wrh_texture_cache_target_add_clear.argtypes = [vp, i32, i32, C.POINTER(i32)]
+        L.wrh_texture_cache_target_add_tasks.argtypes = [vp, i32, i32, i32, vp, i32]
         batch_args = [vp, i32, i32, i32, i32, i32, i32, u32, C.POINTER(u32), vp, sz, i32]
         L.wrh_picture_target_add_batch.argtypes = batch_args
         L.wrh_color_target_add_batch.argtypes = batch_args
@@ -142,6 +148,17 @@ class HostRenderer:
             keep.append(a)
             return a.ctypes.data, a.shape[1], a.shape[0]
 
+        if kinds and kinds <= CACHE_TASK_KINDS:
+            # texture-cache target (draw_texture_cache_target, mod.rs:3931)
+            t = L.wrh_pass_add_texture_cache_target(f, p, tex, desc.width, desc.height)
+            for c in clears:
+                r = c.rect if c.rect else (0, 0, desc.width, desc.height)
+                L.wrh_texture_cache_target_add_clear(f, p, t, (C.c_int32 * 4)(r[0], r[1], r[0] + r[2], r[1] + r[3]))
+            for b in batches:
+                ptr, stride, n = inst(b)
+                if L.wrh_texture_cache_target_add_tasks(f, p, t, b.kind, ptr, n) != 0:
+                    raise ValueError("texture-cache target: unexpected task kind")
+            return
         if desc.fmt == abi.FMT_R8:
             t = L.wrh_pass_add_alpha_target(f, p, tex, desc.width, desc.height)
             for c in clears:

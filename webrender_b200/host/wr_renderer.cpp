@@ -232,6 +232,50 @@ void Renderer::draw_alpha_target(const AlphaRenderTarget& t, RendererStats& stat
   state.blend = WRCU_BLEND_NONE;
 }
 
+// draw_texture_cache_target (mod.rs:3931-4200): cached render tasks — clears, borders and line
+// decorations (premultiplied-alpha blending on), gradients (blending off), horizontal blurs.
+void Renderer::draw_texture_cache_target(const TextureCacheRenderTarget& t, RendererStats& stats) {
+  bind_draw_target(t.texture, 0, t.width, t.height);
+  state.depth = WRCU_DEPTH_OFF;
+  state.scissor_enabled = 0;
+  state.blend = WRCU_BLEND_NONE;
+  const float zero[4] = {0, 0, 0, 0};
+  for (const DeviceIntRect& r : t.clears) {
+    int32_t rect[4] = {r.x0, r.y0, r.x1 - r.x0, r.y1 - r.y0};
+    if (wrcu_clear(device, rect, zero, nullptr) != WRCU_OK) failed++;
+  }
+  const BatchTextures none;
+  if (!t.border_segments_solid.empty() || !t.border_segments_complex.empty()) {
+    state.blend = WRCU_BLEND_PREMULTIPLIED_ALPHA;
+    if (!t.border_segments_solid.empty())
+      draw_instanced_batch(WRCU_KIND_BORDER_SOLID, 0, t.border_segments_solid.data(), sizeof(BorderInstance),
+                           t.border_segments_solid.size(), none, stats);
+    if (!t.border_segments_complex.empty())
+      draw_instanced_batch(WRCU_KIND_BORDER_SEGMENT, 0, t.border_segments_complex.data(), sizeof(BorderInstance),
+                           t.border_segments_complex.size(), none, stats);
+    state.blend = WRCU_BLEND_NONE;
+  }
+  if (!t.line_decorations.empty()) {
+    state.blend = WRCU_BLEND_PREMULTIPLIED_ALPHA;
+    draw_instanced_batch(WRCU_KIND_LINE_DECORATION, 0, t.line_decorations.data(), sizeof(LineDecorationJob),
+                         t.line_decorations.size(), none, stats);
+    state.blend = WRCU_BLEND_NONE;
+  }
+  if (!t.fast_linear_gradients.empty())
+    draw_instanced_batch(WRCU_KIND_FAST_LINEAR_GRADIENT, 0, t.fast_linear_gradients.data(),
+                         sizeof(FastLinearGradientInstance), t.fast_linear_gradients.size(), none, stats);
+  if (!t.linear_gradients.empty())
+    draw_instanced_batch(WRCU_KIND_LINEAR_GRADIENT, 0, t.linear_gradients.data(), sizeof(LinearGradientInstance),
+                         t.linear_gradients.size(), none, stats);
+  if (!t.radial_gradients.empty())
+    draw_instanced_batch(WRCU_KIND_RADIAL_GRADIENT, 0, t.radial_gradients.data(), sizeof(RadialGradientInstance),
+                         t.radial_gradients.size(), none, stats);
+  if (!t.conic_gradients.empty())
+    draw_instanced_batch(WRCU_KIND_CONIC_GRADIENT, 0, t.conic_gradients.data(), sizeof(ConicGradientInstance),
+                         t.conic_gradients.size(), none, stats);
+  draw_blurs(t.horizontal_blurs, true, stats);
+}
+
 void Renderer::draw_tile_list(const std::vector<const CompositeTile*>& tiles, int blend, RendererStats& stats) {
   // batches break whenever the texture or the shader parameters change (mod.rs:3289-3316)
   state.blend = blend;
@@ -277,6 +321,7 @@ void Renderer::draw_frame(const Frame& frame, RendererStats& stats) {
   // bind_frame_data + gpu buffers + gpu cache (mod.rs:4418, 4551-4558) in one call
   if (wrcu_frame_begin(device, &frame.tables) != WRCU_OK) { failed++; return; }
   for (const RenderPass& pass : frame.passes) {
+    for (const TextureCacheRenderTarget& t : pass.texture_cache) draw_texture_cache_target(t, stats);
     for (const PictureCacheTarget& t : pass.picture_cache) draw_picture_cache_target(t, stats);
     for (const AlphaRenderTarget& t : pass.alpha) draw_alpha_target(t, stats);
     for (const ColorRenderTarget& t : pass.color) draw_color_target(t, stats);
@@ -339,6 +384,31 @@ int wrh_pass_add_alpha_target(Frame* f, int pass, wrcu_tex texture, int w, int h
   t.texture = texture; t.width = w; t.height = h;
   f->passes[pass].alpha.push_back(t);
   return (int)f->passes[pass].alpha.size() - 1;
+}
+int wrh_pass_add_texture_cache_target(Frame* f, int pass, wrcu_tex texture, int w, int h) {
+  TextureCacheRenderTarget t;
+  t.texture = texture; t.width = w; t.height = h;
+  f->passes[pass].texture_cache.push_back(t);
+  return (int)f->passes[pass].texture_cache.size() - 1;
+}
+void wrh_texture_cache_target_add_clear(Frame* f, int pass, int target, const int32_t* rect) {
+  f->passes[pass].texture_cache[target].clears.push_back(DeviceIntRect{rect[0], rect[1], rect[2], rect[3]});
+}
+// kind: the WRCU_KIND_* of the task list the instances go to
+int wrh_texture_cache_target_add_tasks(Frame* f, int pass, int target, int kind, const void* instances, int n) {
+  TextureCacheRenderTarget& t = f->passes[pass].texture_cache[target];
+#define WRH_APPEND(vec, T) { const T* p = (const T*)instances; (vec).insert((vec).end(), p, p + n); return 0; }
+  switch (kind) {
+    case WRCU_KIND_BORDER_SOLID: WRH_APPEND(t.border_segments_solid, BorderInstance)
+    case WRCU_KIND_BORDER_SEGMENT: WRH_APPEND(t.border_segments_complex, BorderInstance)
+    case WRCU_KIND_LINE_DECORATION: WRH_APPEND(t.line_decorations, LineDecorationJob)
+    case WRCU_KIND_FAST_LINEAR_GRADIENT: WRH_APPEND(t.fast_linear_gradients, FastLinearGradientInstance)
+    case WRCU_KIND_LINEAR_GRADIENT: WRH_APPEND(t.linear_gradients, LinearGradientInstance)
+    case WRCU_KIND_RADIAL_GRADIENT: WRH_APPEND(t.radial_gradients, RadialGradientInstance)
+    case WRCU_KIND_CONIC_GRADIENT: WRH_APPEND(t.conic_gradients, ConicGradientInstance)
+    default: return -1;
+  }
+#undef WRH_APPEND
 }
 static PrimitiveBatch make_batch(int kind, int blend_mode, int advanced, uint32_t features, const uint32_t* textures,
                                  const void* instances, size_t stride, int n) {

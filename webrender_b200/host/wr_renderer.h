@@ -106,7 +106,29 @@ struct AlphaRenderTarget {  // render_target.rs:522-532
   BlurMap vertical_blurs, horizontal_blurs;
   ScalingMap scalings;
 };
+// Instances of the render tasks drawn into texture-cache targets (the records travel as raw bytes:
+// BorderInstance 108 B gpu_types.rs:193-202, LineDecorationJob 36 B render_target.rs:1184-1190,
+// Fast/Linear/Radial/ConicGradientInstance 52/48/52/52 B prim_store/gradient/*.rs)
+struct BorderInstance { float task_origin[2], local_rect[4], color0[4], color1[4]; int32_t flags; float widths[2], radius[2], clip_params[8]; };
+struct LineDecorationJob { float task_rect[4], local_size[2], wavy_line_thickness; int32_t style; float axis_select; };
+struct FastLinearGradientInstance { float task_rect[4], color0[4], color1[4], axis_select; };
+struct LinearGradientInstance { float task_rect[4], start[2], end[2], scale[2]; int32_t extend_mode, gradient_stops_address; };
+struct RadialGradientInstance { float task_rect[4], center[2], scale[2], start_radius, end_radius, ratio_xy; int32_t extend_mode, gradient_stops_address; };
+struct ConicGradientInstance { float task_rect[4], center[2], scale[2], start_offset, end_offset, angle; int32_t extend_mode, gradient_stops_address; };
+struct TextureCacheRenderTarget {  // render_target.rs:717-729
+  wrcu_tex texture = 0;
+  int32_t width = 0, height = 0;
+  BlurMap horizontal_blurs;
+  std::vector<BorderInstance> border_segments_complex, border_segments_solid;
+  std::vector<DeviceIntRect> clears;
+  std::vector<LineDecorationJob> line_decorations;
+  std::vector<FastLinearGradientInstance> fast_linear_gradients;
+  std::vector<LinearGradientInstance> linear_gradients;
+  std::vector<RadialGradientInstance> radial_gradients;
+  std::vector<ConicGradientInstance> conic_gradients;
+};
 struct RenderPass {  // render_task_graph.rs:854-861
+  std::vector<TextureCacheRenderTarget> texture_cache;
   std::vector<AlphaRenderTarget> alpha;
   std::vector<ColorRenderTarget> color;
   std::vector<PictureCacheTarget> picture_cache;
@@ -152,6 +174,7 @@ class Renderer {
   void draw_picture_cache_target(const PictureCacheTarget& target, RendererStats& stats);         // mod.rs:2669
   void draw_color_target(const ColorRenderTarget& target, RendererStats& stats);                  // mod.rs:3486
   void draw_alpha_target(const AlphaRenderTarget& target, RendererStats& stats);                  // mod.rs:3754
+  void draw_texture_cache_target(const TextureCacheRenderTarget& target, RendererStats& stats);   // mod.rs:3931
   void draw_alpha_batch_container(const AlphaBatchContainer& c, bool has_depth, RendererStats& stats);  // mod.rs:2804
   void draw_clip_batch_list(const ClipBatchList& list, int blend, RendererStats& stats);          // mod.rs:3695
   void draw_blurs(const BlurMap& blurs, bool color_target, RendererStats& stats);                 // mod.rs:3675

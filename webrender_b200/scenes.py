@@ -757,6 +757,39 @@ def border_frame(kind, width=1024, height=512, n_borders=6, seed=1, scale=1.0):
     return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
 
 
+def texture_cache_frame(seed=1, width=1024, height=1024):
+    """One texture-cache target carrying every task list draw_texture_cache_target
+    walks (renderer/mod.rs:3931-4200), in its order: clears, solid borders, complex
+    borders, line decorations (premultiplied-alpha blending), then fast-linear and
+    radial gradients (blending off).  Built from the per-kind scenes, each moved to
+    its own band of the target."""
+    bands = [(abi.KIND_BORDER_SOLID, border_frame(abi.KIND_BORDER_SOLID, width=width, height=300, n_borders=3, seed=seed), 0),
+             (abi.KIND_BORDER_SEGMENT, border_frame(abi.KIND_BORDER_SEGMENT, width=width, height=300, n_borders=4,
+                                                    seed=seed + 1, scale=1.5), 300),
+             (abi.KIND_LINE_DECORATION, line_decoration_frame(width=width, height=100, n_tasks=16, seed=seed), 600),
+             (abi.KIND_FAST_LINEAR_GRADIENT, cached_gradient_frame(abi.KIND_FAST_LINEAR_GRADIENT, width=width, height=150,
+                                                                    n_tasks=4, seed=seed), 700),
+             (abi.KIND_RADIAL_GRADIENT, cached_gradient_frame(abi.KIND_RADIAL_GRADIENT, width=width, height=170,
+                                                               n_tasks=4, seed=seed), 850)]
+    ops = [Clear(color=(0.0, 0.0, 0.0, 0.0))]
+    tables = None
+    for kind, f, dy in bands:
+        b = [op for op in f.passes[0][0].ops if isinstance(op, Batch)][0]
+        rows = np.ascontiguousarray(b.instance_bytes()).copy()
+        fl = rows.view(np.float32)
+        if kind in (abi.KIND_BORDER_SOLID, abi.KIND_BORDER_SEGMENT):
+            fl[:, 1] += dy                    # task_origin.y
+        else:
+            fl[:, 1] += dy                    # task_rect.y0 / y1
+            fl[:, 3] += dy
+        keep = fl[:, 3] <= height if kind not in (abi.KIND_BORDER_SOLID, abi.KIND_BORDER_SEGMENT) else np.ones(len(fl), bool)
+        ops.append(Batch(kind, rows[keep], blend=b.blend))
+        if kind == abi.KIND_RADIAL_GRADIENT:
+            tables = f.tables
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    return Frame(tables, textures, [[Target("target", ops=ops)]])
+
+
 def shadow_mask_texture(size=256, seed=5):
     """A seeded stand-in for the blurred box-shadow masks cs_blur produces
     (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
