@@ -84,7 +84,9 @@ typedef enum wrcu_kind {
   WRCU_KIND_CONIC_GRADIENT = 19,       /* cs_conic_gradient                */
   WRCU_KIND_LINE_DECORATION = 20,      /* cs_line_decoration               */
   WRCU_KIND_BORDER_SOLID = 21,         /* cs_border_solid                  */
-  WRCU_KIND_BORDER_SEGMENT = 22        /* cs_border_segment                */
+  WRCU_KIND_BORDER_SEGMENT = 22,       /* cs_border_segment                */
+  WRCU_KIND_QUAD_RADIAL_GRADIENT = 23, /* ps_quad_radial_gradient          */
+  WRCU_KIND_QUAD_CONIC_GRADIENT = 24   /* ps_quad_conic_gradient           */
 } wrcu_kind;
 
 /* Shader feature bits (webrender_build/src/shader_features.rs:64-247). */

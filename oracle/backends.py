@@ -110,7 +110,7 @@ _CLIP_COMMON = [("aClipDeviceArea", 4, "f"), ("aClipOrigins", 4, "f"), ("aDevice
 _BORDER = [("aTaskOrigin", 2, "f"), ("aRect", 4, "f"), ("aColor0", 4, "f"), ("aColor1", 4, "f"), ("aFlags", 1, "i"),
            ("aWidths", 2, "f"), ("aRadii", 2, "f"), ("aClipParams1", 4, "f"), ("aClipParams2", 4, "f")]
 ATTRIBS = {
-    abi.KIND_QUAD_TEXTURED: _PRIM, abi.KIND_BRUSH_SOLID: _PRIM, abi.KIND_BRUSH_IMAGE: _PRIM,
+    abi.KIND_QUAD_TEXTURED: _PRIM, abi.KIND_QUAD_RADIAL_GRADIENT: _PRIM, abi.KIND_QUAD_CONIC_GRADIENT: _PRIM, abi.KIND_BRUSH_SOLID: _PRIM, abi.KIND_BRUSH_IMAGE: _PRIM,
     abi.KIND_BRUSH_LINEAR_GRADIENT: _PRIM, abi.KIND_BRUSH_BLEND: _PRIM, abi.KIND_BRUSH_MIX_BLEND: _PRIM,
     abi.KIND_BRUSH_OPACITY: _PRIM, abi.KIND_TEXT_RUN: _PRIM,
     abi.KIND_QUAD_MASK: [("aData", 4, "i"), ("aClipData", 4, "i")],

@@ -21,6 +21,7 @@
 #include "cs_scale.h"
 #include "cs_gradients.h"
 #include "cs_border_line.h"
+#include "ps_quad_gradients.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -60,5 +61,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "cs_line_decoration")) return cs_line_decoration_program::loader;
   if (!strcmp(name, "cs_border_solid")) return cs_border_solid_program::loader;
   if (!strcmp(name, "cs_border_segment")) return cs_border_segment_program::loader;
+  if (!strcmp(name, "ps_quad_radial_gradient")) return ps_quad_radial_gradient_program::loader;
+  if (!strcmp(name, "ps_quad_conic_gradient")) return ps_quad_conic_gradient_program::loader;
   return nullptr;
 }

@@ -382,3 +382,19 @@ def test_border_tasks(kind, scale, seed):
     f = scenes.border_frame(abi.KIND_BORDER_SOLID if kind == "solid" else abi.KIND_BORDER_SEGMENT, seed=seed,
                             scale=scale)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind)
+
+
+QUAD_GRADIENT_KINDS = {"radial": abi.KIND_QUAD_RADIAL_GRADIENT, "conic": abi.KIND_QUAD_CONIC_GRADIENT}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled", "rotated", "opaque"])
+@pytest.mark.parametrize("kind", list(QUAD_GRADIENT_KINDS))
+def test_quad_gradients(kind, variant, seed):
+    """ps_quad_radial_gradient / ps_quad_conic_gradient (the conic's approx_atan2 is a
+    polynomial, so both are bit-exact)."""
+    f = scenes.quad_gradient_frame(QUAD_GRADIENT_KINDS[kind], seed=seed, fractional=variant in ("fractional", "scaled"),
+                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0,
+                                   rotate=23.0 if variant == "rotated" else None,
+                                   blend=abi.BLEND_NONE if variant == "opaque" else abi.BLEND_PREMULTIPLIED_ALPHA)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), kind + "/" + variant)

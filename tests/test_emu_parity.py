@@ -245,3 +245,17 @@ def test_border_tasks(kind, scale, seed):
 def test_texture_cache_target_all_task_lists():
     f = scenes.texture_cache_frame(seed=1)
     assert_same(render(EmuDevice, f), render(OracleDevice, f))
+
+
+QUAD_GRADIENT_KINDS = {"radial": abi.KIND_QUAD_RADIAL_GRADIENT, "conic": abi.KIND_QUAD_CONIC_GRADIENT}
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled", "rotated", "opaque"])
+@pytest.mark.parametrize("kind", list(QUAD_GRADIENT_KINDS))
+def test_quad_gradients(kind, variant, seed):
+    f = scenes.quad_gradient_frame(QUAD_GRADIENT_KINDS[kind], seed=seed, fractional=variant in ("fractional", "scaled"),
+                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0,
+                                   rotate=23.0 if variant == "rotated" else None,
+                                   blend=abi.BLEND_NONE if variant == "opaque" else abi.BLEND_PREMULTIPLIED_ALPHA)
+    assert_same(render(EmuDevice, f), render(OracleDevice, f), kind + "/" + variant)

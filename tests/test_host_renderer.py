@@ -44,6 +44,8 @@ CASES = [
     ("blur_a8", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
     ("blur_rgba8", lambda: scenes.blur_frame(seed=2, color=True), ["mid", "target"]),
     ("scale", lambda: scenes.scale_frame(seed=1), ["target"]),
+    ("quad_radial_gradients", lambda: scenes.quad_gradient_frame(abi.KIND_QUAD_RADIAL_GRADIENT, seed=2), ["target"]),
+    ("quad_conic_gradients", lambda: scenes.quad_gradient_frame(abi.KIND_QUAD_CONIC_GRADIENT, seed=1, fractional=True), ["target"]),
     ("texture_cache_target", lambda: scenes.texture_cache_frame(seed=1), ["target"]),
     ("texture_cache_linear_gradients", lambda: scenes.cached_gradient_frame(abi.KIND_LINEAR_GRADIENT, seed=2), ["target"]),
     ("texture_cache_conic_gradients", lambda: scenes.cached_gradient_frame(abi.KIND_CONIC_GRADIENT, seed=1), ["target"]),

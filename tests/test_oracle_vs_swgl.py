@@ -251,3 +251,19 @@ def test_texture_cache_target_all_task_lists(seed):
     """All task lists of one texture-cache target in draw_texture_cache_target's order."""
     f = scenes.texture_cache_frame(seed=seed)
     assert_same(render(SwglDevice, f), render(OracleDevice, f))
+
+
+QUAD_GRADIENT_KINDS = {"radial": abi.KIND_QUAD_RADIAL_GRADIENT, "conic": abi.KIND_QUAD_CONIC_GRADIENT}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["integer", "fractional", "scaled", "rotated", "opaque"])
+@pytest.mark.parametrize("kind", list(QUAD_GRADIENT_KINDS))
+def test_quad_gradients(kind, variant, seed):
+    """ps_quad_radial_gradient (span: swgl_commitRadialGradientRGBA8) and
+    ps_quad_conic_gradient (approx_atan2 polynomial, fragment only)."""
+    f = scenes.quad_gradient_frame(QUAD_GRADIENT_KINDS[kind], seed=seed, fractional=variant in ("fractional", "scaled"),
+                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0,
+                                   rotate=23.0 if variant == "rotated" else None,
+                                   blend=abi.BLEND_NONE if variant == "opaque" else abi.BLEND_PREMULTIPLIED_ALPHA)
+    assert_same(render(SwglDevice, f), render(OracleDevice, f), kind + "/" + variant)

@@ -22,7 +22,8 @@ NEAREST, LINEAR = 0, 1
  KIND_BRUSH_OPACITY, KIND_TEXT_RUN, KIND_CLIP_RECTANGLE, KIND_CLIP_BOX_SHADOW,
  KIND_COMPOSITE, KIND_CLEAR, KIND_BLUR, KIND_SCALE,
  KIND_FAST_LINEAR_GRADIENT, KIND_LINEAR_GRADIENT, KIND_RADIAL_GRADIENT, KIND_CONIC_GRADIENT,
- KIND_LINE_DECORATION, KIND_BORDER_SOLID, KIND_BORDER_SEGMENT) = range(1, 23)
+ KIND_LINE_DECORATION, KIND_BORDER_SOLID, KIND_BORDER_SEGMENT,
+ KIND_QUAD_RADIAL_GRADIENT, KIND_QUAD_CONIC_GRADIENT) = range(1, 25)
 
 KIND_PROGRAM = {
     KIND_QUAD_TEXTURED: "ps_quad_textured",
@@ -47,6 +48,8 @@ KIND_PROGRAM = {
     KIND_LINE_DECORATION: "cs_line_decoration",
     KIND_BORDER_SOLID: "cs_border_solid",
     KIND_BORDER_SEGMENT: "cs_border_segment",
+    KIND_QUAD_RADIAL_GRADIENT: "ps_quad_radial_gradient",
+    KIND_QUAD_CONIC_GRADIENT: "ps_quad_conic_gradient",
 }
 
 FEAT_ALPHA_PASS = 1 << 0

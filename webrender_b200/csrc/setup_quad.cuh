@@ -250,3 +250,61 @@ WRD void wr_setup_clear_one(const SetupArgs& a, int idx) {
   }
 }
 WR_SETUP_KERNEL(wr_setup_clear)
+
+// ps_quad_radial_gradient / ps_quad_conic_gradient pattern_vertex
+// (ps_quad_radial_gradient.glsl:37-58, ps_quad_conic_gradient.glsl:46-60) on top of
+// the quad vertex stage.  Cold layout: shader_cs_gradient.cuh (+ g[8..11] v_color, i[3] = 1).
+WRD void wr_setup_quad_gradient_one(const SetupArgs& a, int idx) {
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  QuadOut q;
+  QuadPrimInfo pi;
+  memset(&q, 0, sizeof q);
+  wr_quad_primitive_info(a, aData, q, pi);
+  const FrameTablesDev& T = a.tabs;
+  const bool radial = a.kind == WRCU_KIND_QUAD_RADIAL_GRADIENT;
+  float4 d0 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, pi.pattern_input[0]);
+  float4 d1 = wr_fetch(T.gpu_buffer_f, T.n_gpu_buffer_f, pi.pattern_input[0] + 1);
+  const int address = pi.pattern_input[1];
+  float dd = d1.y - d1.x;
+  float rscale = dd != 0.0f ? 1.0f / dd : 0.0f;
+  float fc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  fc[3] = d1.w;
+  for (int v = 0; v < 4; v++) {
+    float px = (pi.local_pos[v].x - pi.prim_bounds[0]) * d0.z - d0.x;
+    float py = (pi.local_pos[v].y - pi.prim_bounds[1]) * d0.w - d0.y;
+    if (radial) {
+      px = px * rscale;
+      py = py * rscale;
+      py *= d1.z;
+    }
+    q.interp[v][0] = px;
+    q.interp[v][1] = py;
+  }
+  q.n_interp = 2;
+  if (radial) {
+    fc[0] = d1.x * rscale;
+  } else {
+    fc[5] = rscale;
+    fc[4] = 3.141592653589793f / 2.0f - d1.z;
+    fc[2] = d1.x * rscale;
+  }
+  if (pi.quad_flags & WR_QF_IS_MASK) q.flags |= CMD_OUT_RRRR;
+  uint32_t merge[5];
+  bool valid = wr_grad_validate_merge(T, address, merge);
+  float white[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+  wr_pack_color(q, white);
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    for (int i = 0; i < 8; i++) k->f[i] = fc[i];
+    for (int i = 0; i < 5; i++) k->g[i] = __uint_as_float(merge[i]);
+    for (int i = 0; i < 4; i++) k->g[8 + i] = pi.color[i];
+    k->i[0] = address;
+    k->i[1] = valid ? 1 : 0;
+    k->i[2] = 1;
+    k->i[3] = 1;
+  }
+  wr_finish_setup(a, unsupported);
+}
+WR_SETUP_KERNEL(wr_setup_quad_gradient)

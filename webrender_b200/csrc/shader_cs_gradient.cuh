@@ -23,19 +23,40 @@ WRD int wr_f2i_x86(float v) {
   return (int)v;
 }
 
-// sample_gradient (gradient.glsl:45-61) + pack for one pixel
-WRD Px wr_grad_fragment(const RasterArgs& a, const CmdCold& k, float offset) {
+// sample_gradient (gradient.glsl:45-61) for one pixel
+WRD void wr_grad_sample_float(const RasterArgs& a, const CmdCold& k, float offset, float* out) {
   offset = offset - floorf(offset) * k.f[3];
   float xx = wr_clamp(1.0f + offset * GRAD_SIZE, 0.0f, 1.0f + GRAD_SIZE);
   float ei = floorf(xx), ef = xx - ei;
   int addr = k.i[0] + 2 * (int)ei;
   float4 t0 = wr_grad_texel(a, addr, 0), t1 = wr_grad_texel(a, addr, 1);
+  out[0] = t0.x + t1.x * ef;
+  out[1] = t0.y + t1.y * ef;
+  out[2] = t0.z + t1.z * ef;
+  out[3] = t0.w + t1.w * ef;
+}
+WRD Px wr_grad_pack(const float* c) {
   Px o;
-  o.r = wr_round_pixel(t0.x + t1.x * ef, 255.0f) & 0xFFFF;
-  o.g = wr_round_pixel(t0.y + t1.y * ef, 255.0f) & 0xFFFF;
-  o.b = wr_round_pixel(t0.z + t1.z * ef, 255.0f) & 0xFFFF;
-  o.a = wr_round_pixel(t0.w + t1.w * ef, 255.0f) & 0xFFFF;
+  o.r = wr_round_pixel(c[0], 255.0f) & 0xFFFF;
+  o.g = wr_round_pixel(c[1], 255.0f) & 0xFFFF;
+  o.b = wr_round_pixel(c[2], 255.0f) & 0xFFFF;
+  o.a = wr_round_pixel(c[3], 255.0f) & 0xFFFF;
   return o;
+}
+WRD Px wr_grad_fragment(const RasterArgs& a, const CmdCold& k, float offset) {
+  float c[4];
+  wr_grad_sample_float(a, k, offset, c);
+  return wr_grad_pack(c);
+}
+// ps_quad.glsl:406-417 main() around a gradient pattern_fragment: v_color * sample, .rrrr for mask quads
+// (base colour in g[8..11])
+WRD Px wr_quad_grad_fragment(const RasterArgs& a, const CmdHot& c, const CmdCold& k, float offset) {
+  float smp[4], col[4];
+  wr_grad_sample_float(a, k, offset, smp);
+#pragma unroll
+  for (int ch = 0; ch < 4; ch++) col[ch] = (k.g[8 + ch] * 1.0f) * smp[ch];
+  if (c.flags & CMD_OUT_RRRR) col[1] = col[2] = col[3] = col[0];
+  return wr_grad_pack(col);
 }
 
 // ---- cs_fast_linear_gradient: mix(vColor0, vColor1, vPos), no span shader --------
@@ -293,7 +314,44 @@ struct RadialShader {
     if (rel < r.body_len) return r.out[x - r.own0];
     float p[2];
     wr_interp_at<2>(r.o, r.step, rel, p);
-    return wr_grad_fragment(a, k, sqrtf(p[0] * p[0] + p[1] * p[1]) - k.f[0]);
+    float offset = sqrtf(p[0] * p[0] + p[1] * p[1]) - k.f[0];
+    if (k.i[3]) return wr_quad_grad_fragment(a, c, k, offset);  // ps_quad_radial_gradient
+    return wr_grad_fragment(a, k, offset);
+  }
+};
+
+// ---- ps_quad_conic_gradient (ps_quad_conic_gradient.glsl:67-92): fragment shader only --
+// if_then_else(c, a, b) is mix(b, a, c) (shared.glsl:205): (a - b) * c + b, not a select
+WRD float wr_approx_atan2(float y, float x) {
+  float ax = fabsf(x), ay = fabsf(y);
+  float slope = wr_min(ax, ay) / wr_max(ax, ay);
+  float s2 = slope * slope;
+  float r = ((-0.0464964749f * s2 + 0.15931422f) * s2 - 0.327622764f) * s2 * slope + slope;
+  float t = 1.57079637f - r;
+  r = (t - r) * (ay > ax ? 1.0f : 0.0f) + r;
+  t = 3.14159274f - r;
+  r = (t - r) * (x < 0.0f ? 1.0f : 0.0f) + r;
+  return r * copysignf(1.0f, y);
+}
+struct QuadConicShader {
+  struct Row {
+    float o[2], step[2];
+    float base[4][2];
+    int kb;
+  };
+  WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool, Row& r) {
+    const CmdCold& k = a.cold[c.cold];
+    wr_row_interp<2>(a, k, c, y, r.o, r.step);
+    r.kb = wr_chunk_base<2>(r.o, r.step, c, tx0, r.base);
+  }
+  WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
+    const CmdCold& k = a.cold[c.cold];
+    int rel = x - c.x0;
+    float p[2];
+    wr_chunk_lane<2>(r.base, r.step, r.kb, rel >> 2, rel & 3, p);
+    float angle = wr_approx_atan2(p[1], p[0]) + k.f[4];
+    float offset = wr_fract(angle / (2.0f * 3.141592653589793f)) * k.f[5] - k.f[2];
+    return wr_quad_grad_fragment(a, c, k, offset);
   }
 };
 
@@ -388,6 +446,7 @@ WRD void wr_setup_cs_gradient_one(const SetupArgs& a, int idx) {
     k->i[0] = address;
     k->i[1] = valid ? 1 : 0;
     k->i[2] = 1;
+    k->i[3] = 0;
   }
   wr_finish_setup(a, unsupported);
 }

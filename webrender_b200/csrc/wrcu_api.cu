@@ -669,6 +669,13 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       sa.features = features;
       WR_LAUNCH(wr_setup_scale, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_QUAD_RADIAL_GRADIENT:
+    case WRCU_KIND_QUAD_CONIC_GRADIENT:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      sa.features = features;
+      sa.kind = kind;
+      WR_LAUNCH(wr_setup_quad_gradient, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_LINE_DECORATION:
       if (stride < 36) return wrcu_fail(c, WRCU_ERR_INVALID, "LineDecorationJob stride < 36");
       sa.features = features;
@@ -828,6 +835,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_RADIAL_GRADIENT: LAUNCH_RASTER(RadialShader); break;
     case WRCU_KIND_CONIC_GRADIENT: LAUNCH_RASTER(ConicShader); break;
+    case WRCU_KIND_QUAD_RADIAL_GRADIENT: LAUNCH_RASTER(RadialShader); break;
+    case WRCU_KIND_QUAD_CONIC_GRADIENT: LAUNCH_RASTER(QuadConicShader); break;
     case WRCU_KIND_LINE_DECORATION: LAUNCH_RASTER(LineDecorationShader); break;
     case WRCU_KIND_BORDER_SOLID: LAUNCH_RASTER(BorderSolidShader); break;
     case WRCU_KIND_BORDER_SEGMENT: LAUNCH_RASTER(BorderSegmentShader); break;
@@ -852,7 +861,8 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"cs_fast_linear_gradient", WRCU_KIND_FAST_LINEAR_GRADIENT}, {"cs_linear_gradient", WRCU_KIND_LINEAR_GRADIENT},
       {"cs_radial_gradient", WRCU_KIND_RADIAL_GRADIENT}, {"cs_conic_gradient", WRCU_KIND_CONIC_GRADIENT},
       {"cs_line_decoration", WRCU_KIND_LINE_DECORATION}, {"cs_border_solid", WRCU_KIND_BORDER_SOLID},
-      {"cs_border_segment", WRCU_KIND_BORDER_SEGMENT}};
+      {"cs_border_segment", WRCU_KIND_BORDER_SEGMENT}, {"ps_quad_radial_gradient", WRCU_KIND_QUAD_RADIAL_GRADIENT},
+      {"ps_quad_conic_gradient", WRCU_KIND_QUAD_CONIC_GRADIENT}};
   static const struct { const char* name; uint32_t bit; } feats[] = {
       {"ALPHA_PASS", WRCU_FEAT_ALPHA_PASS}, {"FAST_PATH", WRCU_FEAT_FAST_PATH},
       {"ANTIALIASING", WRCU_FEAT_ANTIALIASING}, {"REPETITION", WRCU_FEAT_REPETITION},

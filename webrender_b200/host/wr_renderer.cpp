@@ -58,6 +58,8 @@ int batch_kind_to_wrcu(BatchKind kind) {
     case BatchKind::BrushLinearGradient: return WRCU_KIND_BRUSH_LINEAR_GRADIENT;
     case BatchKind::BrushOpacity: return WRCU_KIND_BRUSH_OPACITY;
     case BatchKind::TextRun: return WRCU_KIND_TEXT_RUN;
+    case BatchKind::QuadRadialGradient: return WRCU_KIND_QUAD_RADIAL_GRADIENT;
+    case BatchKind::QuadConicGradient: return WRCU_KIND_QUAD_CONIC_GRADIENT;
   }
   return 0;
 }

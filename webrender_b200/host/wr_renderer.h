@@ -34,6 +34,7 @@ enum class MixBlendMode {  // api/src/display_item.rs:1251-1270 (only used with 
 enum class BatchKind {
   QuadColorOrTexture, QuadMask, BrushSolid, BrushImage, BrushBlend, BrushMixBlend, BrushLinearGradient,
   BrushOpacity, TextRun,
+  QuadRadialGradient, QuadConicGradient,  // BatchKind::Quad(PatternKind::RadialGradient / ConicGradient), pattern.rs
 };
 // batch.rs BatchFeatures / shade.rs feature strings
 enum BatchFeatures : uint32_t {

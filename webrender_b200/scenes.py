@@ -790,6 +790,48 @@ def texture_cache_frame(seed=1, width=1024, height=1024):
     return Frame(tables, textures, [[Target("target", ops=ops)]])
 
 
+def quad_gradient_frame(kind, width=640, height=360, n_quads=8, seed=1, fractional=False, blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                        rotate=None, device_pixel_scale=1.0):
+    """Quad(RadialGradient) / Quad(ConicGradient) primitives through the quad path
+    (prim_store/gradient/{radial,conic}.rs `write_prim_gpu_blocks` → ps_quad_*_gradient):
+    pattern_input = (gradient parameter blocks, stops LUT) in gpu_buffer_f."""
+    from . import gpu_types as G
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    task = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
+    xf = 0
+    if rotate is not None:
+        xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0), axis_aligned=False)
+    inst = []
+    for i in range(n_quads):
+        r = _rand_rect(rng, int(width / device_pixel_scale), int(height / device_pixel_scale), 24, 300,
+                       integer=not fractional)
+        rw, rh = r[2] - r[0], r[3] - r[1]
+        ext = 1.0 if i % 3 == 2 else 0.0
+        if (len(t.gpu_buffer_f) % 1024) + 260 > 1024:
+            t.push_gpu_buffer_f([(0, 0, 0, 0)] * ((-len(t.gpu_buffer_f)) % 1024))
+        lut = t.push_gpu_buffer_f(list(G.build_gradient_table(_random_stops(rng, True, hard=(i % 4 == 3)))))
+        sc = (1.0, 1.0) if i % 2 == 0 else (float(rng.uniform(0.5, 2.0)), float(rng.uniform(0.5, 2.0)))
+        center = (float(rng.uniform(0.1, 0.9) * rw * sc[0]), float(rng.uniform(0.1, 0.9) * rh * sc[1]))
+        if kind == abi.KIND_QUAD_RADIAL_GRADIENT:
+            r0 = float(rng.uniform(0, 0.2) * rw) if i % 2 else 0.0
+            r1 = r0 + float(rng.uniform(0.15, 0.9) * rw) * (0.35 if ext else 1.0)
+            ratio = float(rng.uniform(0.5, 2.0)) if i % 3 == 1 else 1.0
+            params = t.push_gpu_buffer_f([center + sc, (r0, r1, ratio, ext)])
+        else:
+            so = float(rng.uniform(0.0, 0.3)) if i % 2 else 0.0
+            eo = so + (float(rng.uniform(0.2, 0.5)) if ext else 1.0 - so)
+            ang = float(rng.uniform(0, 2 * np.pi)) if i % 3 else 0.0
+            params = t.push_gpu_buffer_f([center + sc, (so, eo, ang, ext)])
+        a = float(rng.uniform(0.4, 1.0)) if i % 2 else 1.0
+        prim_f = t.add_quad_prim(r, r, (a, a, a, a))
+        prim_i = t.add_quad_header(xf, i + 1, pattern_input=(params, lut))
+        inst.append(quad_instance(prim_i, prim_f, QF_APPLY_DEVICE_CLIP, 0, PART_ALL, INVALID_SEGMENT_INDEX, task))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0)), Batch(kind, np.stack(inst), blend=blend)]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
 def shadow_mask_texture(size=256, seed=5):
     """A seeded stand-in for the blurred box-shadow masks cs_blur produces
     (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
