@@ -201,6 +201,44 @@ int wrcu_texture_destroy(wrcu_ctx* ctx, wrcu_tex tex);   /* DeleteTexture   */
 int wrcu_read_pixels(wrcu_ctx* ctx, wrcu_tex tex, int x, int y, int w, int h,
                      void* out, size_t dst_stride);
 
+/* ---- update path (the step before the draws) ---------- */
+/* Batched texture-cache upload: update_texture_cache → upload_to_texture_cache
+ * (renderer/mod.rs:1795-1990, renderer/upload.rs:67-330).  The reference packs
+ * the frame's small updates into PBO-backed staging buffers and copies them into
+ * place; here `staging` (host memory; page-locked memory from wrcu_host_alloc is
+ * copied without an intermediate pass) crosses PCIe in ONE transfer and one
+ * kernel scatters every rect into the texture.  Rect i reads `h` rows of
+ * `w * bytes_per_pixel` bytes, `stride` bytes apart, starting `offset` bytes
+ * into `staging`. */
+typedef struct wrcu_upload_rect {
+  int32_t x, y, w, h;   /* destination rect in the texture                  */
+  uint64_t offset;      /* byte offset of the first row inside `staging`    */
+  uint64_t stride;      /* byte distance between source rows                */
+} wrcu_upload_rect;
+int wrcu_texture_upload_batch(wrcu_ctx* ctx, wrcu_tex tex,
+                              const wrcu_upload_rect* rects, size_t n_rects,
+                              const void* staging, size_t staging_bytes);
+/* Texture-to-texture copy of a rect at 1:1: the texture-cache copies of
+ * update_texture_cache (renderer/mod.rs:1808-1850, ps_copy) and handle_blits
+ * (renderer/mod.rs:2438-2470).  src_rect = x, y, w, h. */
+int wrcu_texture_copy(wrcu_ctx* ctx, wrcu_tex src, wrcu_tex dst,
+                      const int32_t src_rect[4], int dst_x, int dst_y);
+/* GPU cache updates: GpuCacheUpdateList applied by GpuCacheTexture::update +
+ * flush (renderer/gpu_cache.rs:218-380, res/gpu_cache_update.glsl; update list
+ * gpu_cache.rs:296-345).  The cache persists on the device across frames as
+ * `height` rows of 1024 16-byte blocks (grown keeping its contents; `clear`
+ * zeroes it first).  Each Copy scatters block_count blocks from
+ * blocks[block_index..] to row v, column u.  Once this has been called,
+ * wrcu_frame_begin accepts tables->gpu_cache == NULL (with gpu_cache_texels 0)
+ * and binds the persistent cache, as the reference binds its GPU cache texture. */
+typedef struct wrcu_gpu_cache_copy {
+  uint32_t block_index, block_count;
+  uint16_t u, v;        /* GpuCacheAddress                                  */
+} wrcu_gpu_cache_copy;
+int wrcu_gpu_cache_update(wrcu_ctx* ctx, int height, int clear,
+                          const wrcu_gpu_cache_copy* updates, size_t n_updates,
+                          const float* blocks, size_t n_blocks);
+
 /* ---- frame --------------------------------------------------------------- */
 /* bind_frame_data + gpu_buffer textures + prepare_gpu_cache
  * (renderer/mod.rs:4418, 4551-4558, 1536). */

@@ -172,12 +172,14 @@ class SwglDevice:
         g.ClearDepth.argtypes = [C.c_double]
         g.BlendColor.argtypes = [C.c_float] * 4
         g.DrawElementsInstanced.argtypes = [C.c_uint, C.c_int, C.c_uint, C.c_ssize_t, C.c_int]
+        g.BlitFramebuffer.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_uint]
         self.ctx = g.CreateContext()
         g.MakeCurrent(self.ctx)
         self.tex = {}        # handle -> (fmt, w, h)
         self.fbos = {}       # (color, depth) -> fbo
         self.programs = {}   # key -> (program id, attrib list)
         self.table_tex = {}
+        self.gpu_cache_shadow = None
         self.cur = None
         # static quad geometry (renderer/vertex.rs:1075-1076)
         self.quad_vbo = self._gen("GenBuffers")
@@ -243,6 +245,38 @@ class SwglDevice:
         self.gl.DeleteTexture(tex)
         del self.tex[tex]
 
+    # -- update path: the reference's plumbing, call for call -------------------------
+    def texture_upload_batch(self, tex, rects, staging):
+        """upload_to_texture_cache (renderer/upload.rs): one TexSubImage2D per rect."""
+        staging = np.ascontiguousarray(staging).view(np.uint8).reshape(-1)
+        bpp = abi.FMT_BPP[self.tex[tex][0]]
+        for (x, y, w, h, offset, stride) in rects:
+            rows = np.stack([staging[offset + r * stride: offset + r * stride + w * bpp] for r in range(h)])
+            self.texture_upload(tex, x, y, w, h, rows)
+
+    def texture_copy(self, src, dst, src_rect, dst_x, dst_y):
+        """blit_render_target (device/gl.rs:2310-2370 → BlitFramebuffer, gl.cc)."""
+        g = self.gl
+        x, y, w, h = src_rect
+        g.BindFramebuffer(_G["READ_FRAMEBUFFER"], self._fbo(src, 0))
+        g.BindFramebuffer(_G["DRAW_FRAMEBUFFER"], self._fbo(dst, 0))
+        g.Disable(_G["SCISSOR_TEST"])
+        g.BlitFramebuffer(x, y, x + w, y + h, dst_x, dst_y, dst_x + w, dst_y + h, _G["COLOR_BUFFER_BIT"], _G["NEAREST"])
+
+    def gpu_cache_update(self, height, clear, updates, blocks):
+        """GpuCacheBus::PixelBuffer (renderer/gpu_cache.rs:256-290, 324-356): a CPU shadow of the
+        rows is patched and the dirty rows re-uploaded to the persistent RGBAF32 texture."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.float32).reshape(-1, 4)
+        if self.gpu_cache_shadow is None or height > self.gpu_cache_shadow.shape[0]:
+            n = np.zeros((height, 1024, 4), np.float32)
+            if self.gpu_cache_shadow is not None:
+                n[: self.gpu_cache_shadow.shape[0]] = self.gpu_cache_shadow
+            self.gpu_cache_shadow = n
+        if clear:
+            self.gpu_cache_shadow[:] = 0
+        for (bi, bc, u, v) in updates:
+            self.gpu_cache_shadow[v, u:u + bc] = blocks[bi:bi + bc]
+
     def _fbo(self, color, depth):
         key = (color, depth)
         if key not in self.fbos:
@@ -276,7 +310,10 @@ class SwglDevice:
                      gpu_buffer_f=("sGpuBufferF", abi.FMT_RGBAF32),
                      gpu_buffer_i=("sGpuBufferI", abi.FMT_RGBAI32))
         for key, (sampler, fmt) in names.items():
-            arr = np.ascontiguousarray(tables[key])
+            src = tables[key]
+            if src is None and key == "gpu_cache":
+                src = self.gpu_cache_shadow.reshape(-1, 4)
+            arr = np.ascontiguousarray(src)
             n = arr.size // 4
             rows = max(1, (n + 1023) // 1024)
             buf = np.zeros((rows * 1024, 4), dtype=arr.dtype if n else (np.float32 if fmt == abi.FMT_RGBAF32 else np.int32))

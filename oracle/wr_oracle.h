@@ -32,6 +32,11 @@ int wro_texture_create(wro_ctx* ctx, int format, int width, int height, wrcu_tex
 int wro_texture_set_filter(wro_ctx* ctx, wrcu_tex tex, int filter);
 int wro_texture_upload(wro_ctx* ctx, wrcu_tex tex, int x, int y, int w, int h,
                        const void* data, size_t src_stride);
+int wro_texture_upload_batch(wro_ctx* ctx, wrcu_tex tex, const wrcu_upload_rect* rects, size_t n_rects,
+                             const void* staging, size_t staging_bytes);
+int wro_texture_copy(wro_ctx* ctx, wrcu_tex src, wrcu_tex dst, const int32_t src_rect[4], int dst_x, int dst_y);
+int wro_gpu_cache_update(wro_ctx* ctx, int height, int clear, const wrcu_gpu_cache_copy* updates, size_t n_updates,
+                         const float* blocks, size_t n_blocks);
 int wro_texture_destroy(wro_ctx* ctx, wrcu_tex tex);
 int wro_read_pixels(wro_ctx* ctx, wrcu_tex tex, int x, int y, int w, int h,
                     void* out, size_t dst_stride);

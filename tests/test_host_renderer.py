@@ -21,7 +21,8 @@ SYMBOLS = ["wrh_renderer_create", "wrh_renderer_destroy", "wrh_frame_create", "w
            "wrh_pass_add_texture_cache_target", "wrh_texture_cache_target_add_clear", "wrh_texture_cache_target_add_tasks",
            "wrh_picture_target_add_batch", "wrh_color_target_add_batch", "wrh_alpha_target_add_clear",
            "wrh_alpha_target_add_clips", "wrh_target_add_blur_or_scale", "wrh_frame_set_framebuffer", "wrh_frame_add_composite_tile",
-           "wrh_renderer_render", "wrh_renderer_last_error"]
+           "wrh_renderer_render", "wrh_renderer_last_error",
+           "wrh_renderer_queue_gpu_cache_updates", "wrh_renderer_queue_texture_update", "wrh_renderer_queue_texture_copy"]
 
 
 def test_host_library_exports():
@@ -72,3 +73,55 @@ def test_host_renderer_matches_oracle(name, make, targets):
     finally:
         hr.close()
         dev.close()
+
+
+@pytest.mark.gpu
+def test_host_renderer_update_path():
+    """Renderer::update_texture_cache / update_gpu_cache ahead of draw_frame: the atlas arrives as
+    queued TextureCacheUpdates, the GPU cache as a GpuCacheUpdateList, a second frame patches both."""
+    from webrender_b200.device import CudaDevice
+    from webrender_b200.host import HostRenderer
+    from update_path import _cache_update_list
+    rng = np.random.RandomState(5)
+    frame = scenes.text_frame(seed=2, width=480, height=270, n_runs=8, glyphs_per_run=20)
+    desc = frame.textures["atlas"]
+    bpp = abi.FMT_BPP[desc.fmt]
+    data = np.ascontiguousarray(desc.data).view(np.uint8).reshape(desc.height, -1)[:, : desc.width * bpp]
+    cache = np.ascontiguousarray(frame.tables["gpu_cache"], np.float32).reshape(-1, 4)
+    height = max(1, (len(cache) + 1023) // 1024)
+    dev, odev = CudaDevice(0), OracleDevice()
+    hr = HostRenderer(dev)
+    try:
+        handles = {"atlas": dev.texture_create(desc.fmt, desc.width, desc.height)}
+        dev.texture_set_filter(handles["atlas"], desc.filter)
+        tile = 96
+        for y in range(0, desc.height, tile):
+            for x in range(0, desc.width, tile):
+                w, h = min(tile, desc.width - x), min(tile, desc.height - y)
+                hr.queue_texture_update(handles["atlas"], (x, y, x + w, y + h), data[y:y + h, x * bpp:], bpp)
+        updates, blocks = _cache_update_list(cache, rng)
+        hr.queue_gpu_cache_updates(height, True, updates, blocks)
+        tables = dict(frame.tables)
+        tables["gpu_cache"] = None
+        f1 = type(frame)(tables, frame.textures, frame.passes)
+        handles, _ = hr.render(f1, handles)
+        want = render(OracleDevice, frame, ["target"])["target"]
+        d = frame.textures["target"]
+        got = dev.read_pixels(handles["target"], 0, 0, d.width, d.height, 4)
+        assert np.array_equal(got, want)
+        # frame 2: halve a few cached colours; only the changed blocks travel
+        changed = sorted(rng.choice(len(cache), size=10, replace=False))
+        patched = cache.copy()
+        patched[changed] *= np.float32(0.5)
+        hr.queue_gpu_cache_updates(height, False, [(i, 1, a % 1024, a // 1024) for i, a in enumerate(changed)],
+                                   patched[changed])
+        handles, _ = hr.render(f1, handles)
+        t2 = dict(frame.tables)
+        t2["gpu_cache"] = patched
+        want2 = render(OracleDevice, type(frame)(t2, frame.textures, frame.passes), ["target"])["target"]
+        got2 = dev.read_pixels(handles["target"], 0, 0, d.width, d.height, 4)
+        assert np.array_equal(got2, want2)
+    finally:
+        hr.close()
+        dev.close()
+        odev.close()

@@ -111,6 +111,15 @@ class FrameTables(C.Structure):
     ]
 
 
+class UploadRect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("offset", C.c_uint64), ("stride", C.c_uint64)]
+
+
+class GpuCacheCopy(C.Structure):
+    _fields_ = [("block_index", C.c_uint32), ("block_count", C.c_uint32), ("u", C.c_uint16), ("v", C.c_uint16)]
+
+
 class DrawState(C.Structure):
     _fields_ = [
         ("blend", C.c_int32),
@@ -144,4 +153,5 @@ SYMBOLS = [
     "wrcu_reset_stats", "wrcu_timer_begin", "wrcu_timer_end",
     "wrcu_texture_device_ptr", "wrcu_stream", "wrcu_host_alloc", "wrcu_host_free",
     "wrcu_read_pixels_async", "wrcu_fence_wait",
+    "wrcu_texture_upload_batch", "wrcu_texture_copy", "wrcu_gpu_cache_update",
 ]

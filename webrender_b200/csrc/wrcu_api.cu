@@ -4,6 +4,7 @@
 // setup_*.cuh.  There is no CPU rasterisation path in this library.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <vector>
 
 #include "raster.cuh"
 #include "shader_clip_rect.cuh"
@@ -99,6 +100,61 @@ __global__ void wr_clear_u8(uint8_t* base, int pitch, int x0, int y0, int x1, in
 }
 
 #endif
+
+// ---- update path kernels -------------------------------------------
+struct UploadRectDev { int x, y, w, h; unsigned long long offset, stride; };
+// Scatter staged rects into a texture: CTA (x = rect, y = row slice); a row is moved 16 bytes per
+// thread where source and destination are both 16-byte aligned, bytewise otherwise.
+WR_GLOBAL void wr_upload_scatter(uint8_t* dst, int pitch, int bpp, const UploadRectDev* rects, int n,
+                                 const uint8_t* staging) {
+#ifdef WRCU_HOSTEMU
+  for (int i = 0; i < n; i++) {
+    const UploadRectDev r = rects[i];
+    for (int row = 0; row < r.h; row++)
+      memcpy(dst + (size_t)(r.y + row) * pitch + (size_t)r.x * bpp, staging + r.offset + (size_t)row * r.stride,
+             (size_t)r.w * bpp);
+  }
+#else
+  const UploadRectDev r = rects[blockIdx.x];
+  const size_t row_bytes = (size_t)r.w * bpp;
+  for (int row = blockIdx.y; row < r.h; row += gridDim.y) {
+    const uint8_t* s = staging + r.offset + (size_t)row * r.stride;
+    uint8_t* d = dst + (size_t)(r.y + row) * pitch + (size_t)r.x * bpp;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      const size_t nv = row_bytes >> 4;
+      for (size_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4*)d)[i] = __ldg((const uint4*)s + i);
+      for (size_t i = (nv << 4) + threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = s[i];
+    } else if (bpp == 4 && (((uintptr_t)s | (uintptr_t)d) & 3) == 0) {
+      for (size_t i = threadIdx.x; i < (size_t)r.w; i += blockDim.x) ((uint32_t*)d)[i] = __ldg((const uint32_t*)s + i);
+    } else {
+      for (size_t i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = s[i];
+    }
+  }
+#endif
+}
+struct GpuCacheCopyDev { unsigned block_index, block_count; unsigned short u, v; };
+// GpuCacheUpdate::Copy: one warp per update, a 16-byte block per lane (gpu_cache_update.glsl
+// draws one point per block).
+WR_GLOBAL void wr_gpu_cache_scatter(float4* cache, int rows, const GpuCacheCopyDev* updates, int n,
+                                    const float4* blocks, int n_blocks) {
+#ifdef WRCU_HOSTEMU
+  for (int i = 0; i < n; i++) {
+    const GpuCacheCopyDev u = updates[i];
+    for (unsigned b = 0; b < u.block_count; b++) {
+      size_t dsti = (size_t)u.v * 1024 + u.u + b;
+      if (u.v < rows && u.u + b < 1024 && u.block_index + b < (unsigned)n_blocks) cache[dsti] = blocks[u.block_index + b];
+    }
+  }
+#else
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const GpuCacheCopyDev u = updates[warp];
+  if (u.v >= rows) return;
+  for (unsigned b = lane; b < u.block_count; b += 32)
+    if (u.u + b < 1024 && u.block_index + b < (unsigned)n_blocks)
+      cache[(size_t)u.v * 1024 + u.u + b] = __ldg(blocks + u.block_index + b);
+#endif
+}
 
 // ---- context -----------------------------------------------------------------------
 extern "C" int wrcu_abi_version(void) { return WRCU_ABI_VERSION; }
@@ -225,7 +281,8 @@ static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
 #define REBASE(p) if (p) p = (decltype(p))((uint8_t*)(p) + delta)
     REBASE(c->tables.prim_headers_f); REBASE(c->tables.prim_headers_i);
     REBASE(c->tables.transforms); REBASE(c->tables.render_tasks);
-    REBASE(c->tables.gpu_cache); REBASE(c->tables.gpu_buffer_f); REBASE(c->tables.gpu_buffer_i);
+    if (!c->gpu_cache_bound) REBASE(c->tables.gpu_cache);
+    REBASE(c->tables.gpu_buffer_f); REBASE(c->tables.gpu_buffer_i);
 #undef REBASE
     cudaFreeHost(a->host);
     cudaFree(a->dev);
@@ -409,6 +466,103 @@ extern "C" int wrcu_fence_wait(wrcu_ctx* c, uint64_t fence) {
   return WRCU_OK;
 }
 
+// ---- update path ---------------------------------------------------------------------
+extern "C" int wrcu_texture_upload_batch(wrcu_ctx* c, wrcu_tex id, const wrcu_upload_rect* rects, size_t n,
+                                         const void* staging, size_t staging_bytes) {
+  WrTexture* t = get_tex(c, id);
+  if (!t || (n && (!rects || !staging))) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_upload_batch: bad arguments");
+  if (!n) return WRCU_OK;
+  for (size_t i = 0; i < n; i++) {
+    const wrcu_upload_rect& r = rects[i];
+    size_t row = (size_t)r.w * t->bpp;
+    if (r.x < 0 || r.y < 0 || r.w <= 0 || r.h <= 0 || r.x + r.w > t->w || r.y + r.h > t->h || r.stride < row ||
+        r.offset + (size_t)(r.h - 1) * r.stride + row > staging_bytes)
+      return wrcu_fail(c, WRCU_ERR_INVALID, "texture_upload_batch: rect %zu out of range", i);
+  }
+  cudaSetDevice(c->device);
+  if (t->pending_read) {
+    int rc0 = wait_fence(c, t->pending_read, true);
+    if (rc0 != WRCU_OK) return rc0;
+    t->pending_read = 0;
+  }
+  int rc;
+  void *dstage = nullptr, *drects = nullptr;
+  if ((rc = stage(c, staging, staging_bytes, &dstage)) != WRCU_OK) return rc;
+  std::vector<UploadRectDev> hr(n);
+  int max_h = 1;
+  for (size_t i = 0; i < n; i++) {
+    hr[i] = UploadRectDev{rects[i].x, rects[i].y, rects[i].w, rects[i].h, rects[i].offset, rects[i].stride};
+    max_h = max(max_h, rects[i].h);
+  }
+  // the second stage() may grow (reallocate) the arena: keep the blob by offset
+  Arena* a = &c->arena[c->cur_arena];
+  const size_t blob_off = (size_t)((uint8_t*)dstage - a->dev);
+  if ((rc = stage(c, hr.data(), n * sizeof(UploadRectDev), &drects)) != WRCU_OK) return rc;
+  dstage = a->dev + blob_off;
+  dim3 grid((unsigned)n, (unsigned)min(max_h, 64));
+  WR_LAUNCH(wr_upload_scatter, grid, 128, c->stream, t->dptr, (int)t->pitch, t->bpp, (const UploadRectDev*)drects,
+            (int)n, (const uint8_t*)dstage);
+  c->stats.kernel_launches++;
+  WRCU_CUDA(c, cudaGetLastError());
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_texture_copy(wrcu_ctx* c, wrcu_tex src, wrcu_tex dst, const int32_t r[4], int dx, int dy) {
+  WrTexture *s = get_tex(c, src), *d = get_tex(c, dst);
+  if (!s || !d || !r || s->bpp != d->bpp || r[2] <= 0 || r[3] <= 0 || r[0] < 0 || r[1] < 0 || r[0] + r[2] > s->w ||
+      r[1] + r[3] > s->h || dx < 0 || dy < 0 || dx + r[2] > d->w || dy + r[3] > d->h)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "texture_copy: bad arguments");
+  cudaSetDevice(c->device);
+  WRCU_CUDA(c, cudaMemcpy2DAsync(d->dptr + (size_t)dy * d->pitch + (size_t)dx * d->bpp, d->pitch,
+                                 s->dptr + (size_t)r[1] * s->pitch + (size_t)r[0] * s->bpp, s->pitch,
+                                 (size_t)r[2] * s->bpp, r[3], cudaMemcpyDeviceToDevice, c->stream));
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_gpu_cache_update(wrcu_ctx* c, int height, int clear, const wrcu_gpu_cache_copy* updates,
+                                     size_t n_updates, const float* blocks, size_t n_blocks) {
+  if (height <= 0 || height > 65536 || (n_updates && (!updates || !blocks)))
+    return wrcu_fail(c, WRCU_ERR_INVALID, "gpu_cache_update: bad arguments");
+  cudaSetDevice(c->device);
+  if (height > c->gpu_cache_rows) {  // ensure_texture (renderer/gpu_cache.rs:103-155): grow, keep contents
+    float4* n = nullptr;
+    WRCU_CUDA(c, cudaMalloc((void**)&n, (size_t)height * 1024 * sizeof(float4)));
+    WRCU_CUDA(c, cudaMemsetAsync(n, 0, (size_t)height * 1024 * sizeof(float4), c->stream));
+    if (c->gpu_cache_dev) {
+      WRCU_CUDA(c, cudaMemcpyAsync(n, c->gpu_cache_dev, (size_t)c->gpu_cache_rows * 1024 * sizeof(float4),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+      WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->gpu_cache_dev);
+    }
+    if (c->gpu_cache_bound) c->tables.gpu_cache = n;
+    c->gpu_cache_dev = n;
+    c->gpu_cache_rows = height;
+    if (c->gpu_cache_bound) c->tables.n_gpu_cache = height * 1024;
+  }
+  if (clear)
+    WRCU_CUDA(c, cudaMemsetAsync(c->gpu_cache_dev, 0, (size_t)c->gpu_cache_rows * 1024 * sizeof(float4), c->stream));
+  if (!n_updates) return WRCU_OK;
+  for (size_t i = 0; i < n_updates; i++)
+    if ((size_t)updates[i].block_index + updates[i].block_count > n_blocks || updates[i].v >= c->gpu_cache_rows ||
+        updates[i].u + updates[i].block_count > 1024)
+      return wrcu_fail(c, WRCU_ERR_INVALID, "gpu_cache_update: update %zu out of range", i);
+  int rc;
+  void *dblocks = nullptr, *dupd = nullptr;
+  if ((rc = stage(c, blocks, n_blocks * 16, &dblocks)) != WRCU_OK) return rc;
+  static_assert(sizeof(wrcu_gpu_cache_copy) == sizeof(GpuCacheCopyDev), "update record layout");
+  Arena* a = &c->arena[c->cur_arena];
+  const size_t blocks_off = (size_t)((uint8_t*)dblocks - a->dev);
+  if ((rc = stage(c, updates, n_updates * sizeof(wrcu_gpu_cache_copy), &dupd)) != WRCU_OK) return rc;
+  dblocks = a->dev + blocks_off;
+  int threads = 128, warps_per_block = threads / 32;
+  int grid = (int)((n_updates + warps_per_block - 1) / warps_per_block);
+  WR_LAUNCH(wr_gpu_cache_scatter, grid, threads, c->stream, c->gpu_cache_dev, c->gpu_cache_rows,
+            (const GpuCacheCopyDev*)dupd, (int)n_updates, (const float4*)dblocks, (int)n_blocks);
+  c->stats.kernel_launches++;
+  WRCU_CUDA(c, cudaGetLastError());
+  return WRCU_OK;
+}
+
 // ---- frame ---------------------------------------------------------------------------
 extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null tables");
@@ -436,6 +590,13 @@ extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
   TAB(transforms, transforms_texels, float4)
   TAB(render_tasks, render_tasks_texels, float4)
   TAB(gpu_cache, gpu_cache_texels, float4)
+  c->gpu_cache_bound = false;
+  if (!t->gpu_cache && !t->gpu_cache_texels && c->gpu_cache_dev) {
+    // the persistent GPU cache texture maintained by wrcu_gpu_cache_update
+    c->tables.gpu_cache = c->gpu_cache_dev;
+    c->tables.n_gpu_cache = c->gpu_cache_rows * 1024;
+    c->gpu_cache_bound = true;
+  }
   TAB(gpu_buffer_f, gpu_buffer_f_texels, float4)
   TAB(gpu_buffer_i, gpu_buffer_i_texels, int4)
 #undef TAB

@@ -120,6 +120,10 @@ struct wrcu_ctx {
   cudaEvent_t fence_ev[N_FENCES] = {};
   uint64_t fence_id[N_FENCES] = {};
   uint64_t next_fence = 1;
+  // persistent GPU cache (wrcu_gpu_cache_update): rows of 1024 float4 blocks
+  float4* gpu_cache_dev = nullptr;
+  int gpu_cache_rows = 0;
+  bool gpu_cache_bound = false;  // this frame's tables.gpu_cache is the persistent cache (not in an arena)
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
 };
 

@@ -47,6 +47,9 @@ def bind_prefixed(lib, prefix):
     f("draw_batch").argtypes = [vp, i32, u32, C.POINTER(abi.DrawState), vp, sz, i32]
     f("last_error_string").argtypes = [vp]
     f("last_error_string").restype = C.c_char_p
+    f("texture_upload_batch").argtypes = [vp, u32, C.POINTER(abi.UploadRect), sz, vp, sz]
+    f("texture_copy").argtypes = [vp, u32, u32, C.POINTER(i32), i32, i32]
+    f("gpu_cache_update").argtypes = [vp, i32, i32, C.POINTER(abi.GpuCacheCopy), sz, vp, sz]
 
 
 class DeviceBase:
@@ -77,6 +80,23 @@ class DeviceBase:
     def texture_destroy(self, tex):
         self._check(self._f("texture_destroy")(self.ctx, tex))
 
+    # -- update path ------------------------------------------
+    def texture_upload_batch(self, tex, rects, staging):
+        """rects: [(x, y, w, h, offset, stride)]; staging: one contiguous uint8 blob."""
+        staging = np.ascontiguousarray(staging).view(np.uint8).reshape(-1)
+        arr = (abi.UploadRect * len(rects))(*[abi.UploadRect(*[int(v) for v in r]) for r in rects])
+        self._check(self._f("texture_upload_batch")(self.ctx, tex, arr, len(rects), staging.ctypes.data, staging.size))
+
+    def texture_copy(self, src, dst, src_rect, dst_x, dst_y):
+        self._check(self._f("texture_copy")(self.ctx, src, dst, (C.c_int32 * 4)(*src_rect), dst_x, dst_y))
+
+    def gpu_cache_update(self, height, clear, updates, blocks):
+        """updates: [(block_index, block_count, u, v)] (GpuCacheUpdate::Copy); blocks: (n, 4) float32."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.float32).reshape(-1, 4)
+        arr = (abi.GpuCacheCopy * max(1, len(updates)))(*[abi.GpuCacheCopy(*[int(v) for v in u]) for u in updates])
+        self._check(self._f("gpu_cache_update")(self.ctx, height, 1 if clear else 0, arr, len(updates),
+                                                blocks.ctypes.data if len(blocks) else None, len(blocks)))
+
     def read_pixels(self, tex, x, y, w, h, bpp):
         out = np.empty((h, w * bpp), dtype=np.uint8)
         self._check(self._f("read_pixels")(self.ctx, tex, x, y, w, h, out.ctypes.data, out.strides[0]))
@@ -87,6 +107,10 @@ class DeviceBase:
         self._keep = []
         for name in ("prim_headers_f", "prim_headers_i", "transforms", "render_tasks", "gpu_cache",
                      "gpu_buffer_f", "gpu_buffer_i"):
+            if tables[name] is None:   # gpu_cache: bind the persistent cache (wrcu_gpu_cache_update)
+                setattr(t, name, None)
+                setattr(t, name + "_texels", 0)
+                continue
             arr = np.ascontiguousarray(tables[name])
             self._keep.append(arr)
             setattr(t, name, arr.ctypes.data if arr.size else None)

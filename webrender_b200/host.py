@@ -57,6 +57,7 @@ class HostRenderer:
         if not os.path.exists(lib_path):
             raise WrcuError(abi.ERR_NO_DEVICE, f"{lib_path} not built — run __graft_entry__.build()")
         self.dev = dev
+        self._pending_keep = []
         L = self.lib = C.CDLL(lib_path)
         vp, i32, u32, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_size_t
         L.wrh_renderer_create.restype = vp
@@ -69,6 +70,9 @@ class HostRenderer:
         L.wrh_pass_add_picture_cache_target.argtypes = [vp, i32, u32, u32, i32, i32, C.POINTER(C.c_float), C.POINTER(i32)]
         L.wrh_pass_add_color_target.argtypes = [vp, i32, u32, u32, i32, i32]
         L.wrh_pass_add_alpha_target.argtypes = [vp, i32, u32, i32, i32]
+        L.wrh_renderer_queue_gpu_cache_updates.argtypes = [vp, i32, i32, vp, i32, vp, i32]
+        L.wrh_renderer_queue_texture_update.argtypes = [vp, u32, C.POINTER(i32), vp, sz, i32]
+        L.wrh_renderer_queue_texture_copy.argtypes = [vp, u32, u32, C.POINTER(i32), C.POINTER(i32)]
         L.wrh_pass_add_texture_cache_target.argtypes = [vp, i32, u32, i32, i32]
         L.wrh_texture_cache_target_add_clear.argtypes = [vp, i32, i32, C.POINTER(i32)]
         L.wrh_texture_cache_target_add_tasks.argtypes = [vp, i32, i32, i32, vp, i32]
@@ -90,6 +94,23 @@ class HostRenderer:
             self.lib.wrh_renderer_destroy(self.r)
             self.r = None
 
+    # -- update path: queued like the backend thread's update lists, applied by the next render() ----
+    def queue_gpu_cache_updates(self, height, clear, updates, blocks):
+        blocks = np.ascontiguousarray(blocks, dtype=np.float32).reshape(-1, 4)
+        arr = (abi.GpuCacheCopy * max(1, len(updates)))(*[abi.GpuCacheCopy(*[int(v) for v in u]) for u in updates])
+        self.lib.wrh_renderer_queue_gpu_cache_updates(self.r, height, 1 if clear else 0, arr, len(updates),
+                                                      blocks.ctypes.data if len(blocks) else None, len(blocks))
+
+    def queue_texture_update(self, tex, rect, rows, bpp):
+        """rect = (x0, y0, x1, y1); rows: 2-D uint8 array (h, >= w * bpp), kept alive until render()."""
+        rows = np.ascontiguousarray(rows)
+        self._pending_keep.append(rows)
+        self.lib.wrh_renderer_queue_texture_update(self.r, tex, (C.c_int32 * 4)(*rect), rows.ctypes.data,
+                                                   rows.strides[0], bpp)
+
+    def queue_texture_copy(self, src, dst, src_rect, dst_rect):
+        self.lib.wrh_renderer_queue_texture_copy(self.r, src, dst, (C.c_int32 * 4)(*src_rect), (C.c_int32 * 4)(*dst_rect))
+
     def render(self, frame: Frame, handles=None):
         """Build the wr::Frame for `frame`, render it, return (handles, draw_calls)."""
         dev, L = self.dev, self.lib
@@ -104,6 +125,8 @@ class HostRenderer:
         keep = []
         for name in ("prim_headers_f", "prim_headers_i", "transforms", "render_tasks", "gpu_cache", "gpu_buffer_f",
                      "gpu_buffer_i"):
+            if frame.tables[name] is None:   # persistent GPU cache
+                continue
             arr = np.ascontiguousarray(frame.tables[name])
             keep.append(arr)
             setattr(tabs, name, arr.ctypes.data if arr.size else None)
@@ -120,6 +143,7 @@ class HostRenderer:
                 raise WrcuError(err, "RendererError: " + L.wrh_renderer_last_error(self.r).decode())
         finally:
             L.wrh_frame_destroy(f)
+            self._pending_keep = []
         return handles, calls.value
 
     def _add_blur_scale(self, f, p, target_kind, t, b, handles, ptr, n):

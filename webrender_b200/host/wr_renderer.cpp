@@ -332,6 +332,52 @@ void Renderer::draw_frame(const Frame& frame, RendererStats& stats) {
   if (wrcu_frame_end(device) != WRCU_OK) failed++;
 }
 
+// update_gpu_cache (mod.rs:1498-1535): every pending list goes to the device in order; the cache
+// persists there (wrcu_gpu_cache_update), so a frame carries only the blocks that changed.
+void Renderer::update_gpu_cache() {
+  for (const GpuCacheUpdateList& list : pending_gpu_cache_updates) {
+    static_assert(sizeof(GpuCacheUpdate) == sizeof(wrcu_gpu_cache_copy), "GpuCacheUpdate layout");
+    bool clear = list.clear || pending_gpu_cache_clear;
+    pending_gpu_cache_clear = false;
+    if (wrcu_gpu_cache_update(device, list.height, clear ? 1 : 0, (const wrcu_gpu_cache_copy*)list.updates.data(),
+                              list.updates.size(), list.blocks.empty() ? nullptr : list.blocks[0].data,
+                              list.blocks.size()) != WRCU_OK)
+      failed++;
+  }
+  pending_gpu_cache_updates.clear();
+}
+
+// update_texture_cache (mod.rs:1795-1990): copies between cache textures first (defragmentation),
+// then each texture's updates as ONE batched upload — the rows are packed into a staging blob the
+// way upload_to_texture_cache packs them into PBO staging buffers (renderer/upload.rs:67-330).
+void Renderer::update_texture_cache() {
+  for (const TextureUpdateList& list : pending_texture_updates) {
+    for (const auto& kv : list.copies)
+      for (const TextureCacheCopy& cp : kv.second) {
+        int32_t r[4] = {cp.src_rect.x0, cp.src_rect.y0, cp.src_rect.x1 - cp.src_rect.x0, cp.src_rect.y1 - cp.src_rect.y0};
+        if (wrcu_texture_copy(device, kv.first.first, kv.first.second, r, cp.dst_rect.x0, cp.dst_rect.y0) != WRCU_OK) failed++;
+      }
+    for (const auto& kv : list.updates) {
+      std::vector<wrcu_upload_rect> rects;
+      std::vector<uint8_t> staging;
+      for (const TextureCacheUpdate& u : kv.second) {
+        const int w = u.rect.x1 - u.rect.x0, h = u.rect.y1 - u.rect.y0;
+        if (w <= 0 || h <= 0 || !u.data) continue;
+        // rows are repacked at a 16-byte aligned offset and pitch (only the rect's bytes are read)
+        const size_t row = (size_t)w * u.bytes_per_pixel, pitch = (row + 15) & ~(size_t)15;
+        size_t off = (staging.size() + 15) & ~(size_t)15;
+        staging.resize(off + pitch * (size_t)h);
+        for (int y = 0; y < h; y++) memcpy(staging.data() + off + pitch * (size_t)y, u.data + u.stride * (size_t)y, row);
+        rects.push_back(wrcu_upload_rect{u.rect.x0, u.rect.y0, w, h, (uint64_t)off, (uint64_t)pitch});
+      }
+      if (!rects.empty() &&
+          wrcu_texture_upload_batch(device, kv.first, rects.data(), rects.size(), staging.data(), staging.size()) != WRCU_OK)
+        failed++;
+    }
+  }
+  pending_texture_updates.clear();
+}
+
 RendererError Renderer::check_gl_errors() {
   int e = wrcu_get_error(device);
   if (e == WRCU_ERR_OOM) return RendererError::OutOfMemory;
@@ -346,6 +392,9 @@ RendererError Renderer::check_gl_errors() {
 
 RendererError Renderer::render(const Frame& frame, RendererStats* stats) {
   RendererStats local;
+  // render_impl (mod.rs:1441-1560): resource updates first, then the frame
+  update_texture_cache();
+  update_gpu_cache();
   draw_frame(frame, stats ? *stats : local);
   return check_gl_errors();
 }
@@ -492,6 +541,36 @@ void wrh_frame_add_composite_tile(Frame* f, int kind, wrcu_tex texture, int fast
   f->composite_state.tiles.push_back(t);
 }
 // returns RendererError as int; *draw_calls receives RendererStats.total_draw_calls
+// update path: queue a GpuCacheUpdateList / texture updates for the next render
+void wrh_renderer_queue_gpu_cache_updates(Renderer* r, int height, int clear, const wrcu_gpu_cache_copy* updates, int n_updates,
+                                          const float* blocks, int n_blocks) {
+  GpuCacheUpdateList l;
+  l.clear = clear != 0;
+  l.height = height;
+  for (int i = 0; i < n_updates; i++)
+    l.updates.push_back(GpuCacheUpdate{updates[i].block_index, updates[i].block_count, GpuCacheAddress{updates[i].u, updates[i].v}});
+  l.blocks.resize((size_t)n_blocks);
+  if (n_blocks) memcpy(l.blocks.data(), blocks, (size_t)n_blocks * 16);
+  r->pending_gpu_cache_updates.push_back(std::move(l));
+}
+// `data` must stay valid until the next wrh_renderer_render
+void wrh_renderer_queue_texture_update(Renderer* r, wrcu_tex texture, const int32_t* rect, const void* data, size_t stride,
+                                       int bytes_per_pixel) {
+  if (r->pending_texture_updates.empty()) r->pending_texture_updates.emplace_back();
+  TextureCacheUpdate u;
+  u.rect = DeviceIntRect{rect[0], rect[1], rect[2], rect[3]};
+  u.data = (const uint8_t*)data;
+  u.stride = stride;
+  u.bytes_per_pixel = (uint32_t)bytes_per_pixel;
+  r->pending_texture_updates.back().updates[texture].push_back(u);
+}
+void wrh_renderer_queue_texture_copy(Renderer* r, wrcu_tex src, wrcu_tex dst, const int32_t* src_rect, const int32_t* dst_rect) {
+  if (r->pending_texture_updates.empty()) r->pending_texture_updates.emplace_back();
+  TextureCacheCopy c;
+  c.src_rect = DeviceIntRect{src_rect[0], src_rect[1], src_rect[2], src_rect[3]};
+  c.dst_rect = DeviceIntRect{dst_rect[0], dst_rect[1], dst_rect[2], dst_rect[3]};
+  r->pending_texture_updates.back().copies[std::make_pair(src, dst)].push_back(c);
+}
 int wrh_renderer_render(Renderer* r, const Frame* f, uint64_t* draw_calls) {
   RendererStats stats;
   RendererError e = r->render(*f, &stats);

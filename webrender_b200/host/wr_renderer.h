@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <utility>
 #include <optional>
 #include <string>
 #include <vector>
@@ -159,6 +160,29 @@ struct Frame {  // frame_builder.rs:1129 (members the path reads)
   bool present = false;      // run composite_simple
 };
 
+// ---- update path: what the backend thread hands the renderer before a frame (mod.rs:1441-1560) ----
+struct GpuCacheAddress { uint16_t u, v; };                                          // gpu_cache.rs:88-92
+struct GpuCacheUpdate { uint32_t block_index, block_count; GpuCacheAddress address; };  // GpuCacheUpdate::Copy, gpu_cache.rs:299-305
+struct GpuBlockData { float data[4]; };
+struct GpuCacheUpdateList {  // gpu_cache.rs:327-345
+  uint64_t frame_id = 0;
+  bool clear = false;
+  int32_t height = 0;
+  std::vector<GpuCacheUpdate> updates;
+  std::vector<GpuBlockData> blocks;
+};
+struct TextureCacheUpdate {  // texture_cache.rs TextureCacheUpdate with TextureUpdateSource::Bytes
+  DeviceIntRect rect;
+  const uint8_t* data = nullptr;  // first row of the rect
+  size_t stride = 0;              // bytes between rows
+  uint32_t bytes_per_pixel = 4;   // from the cache texture's ImageFormat
+};
+struct TextureCacheCopy { DeviceIntRect src_rect, dst_rect; };  // texture_cache.rs TextureCacheCopy
+struct TextureUpdateList {  // texture_cache.rs:  per-texture updates + (src, dst) copies
+  std::map<wrcu_tex, std::vector<TextureCacheUpdate>> updates;
+  std::map<std::pair<wrcu_tex, wrcu_tex>, std::vector<TextureCacheCopy>> copies;
+};
+
 enum class RendererError { None, Shader, Thread, MaxTextureSize, SoftwareRasterizer, OutOfMemory };  // mod.rs:5700-5720
 
 struct RendererStats {  // mod.rs RendererStats
@@ -185,6 +209,12 @@ class Renderer {
   // draw_instanced_batch<T> (mod.rs:2022-2065)
   void draw_instanced_batch(int kind, uint32_t features, const void* instances, size_t stride, size_t n,
                             const BatchTextures& textures, RendererStats& stats);
+  // update path: lists queued by update_document, applied at the top of render_impl
+  void update_gpu_cache();      // mod.rs:1498-1535 → GpuCacheTexture::update / flush (renderer/gpu_cache.rs:218-380)
+  void update_texture_cache();  // mod.rs:1795-1990 → upload_to_texture_cache (renderer/upload.rs)
+  std::vector<GpuCacheUpdateList> pending_gpu_cache_updates;
+  std::vector<TextureUpdateList> pending_texture_updates;
+  bool pending_gpu_cache_clear = false;
   RendererError check_gl_errors();  // mod.rs:1992
   std::vector<std::string> renderer_errors;
 
