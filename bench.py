@@ -166,6 +166,166 @@ def cpu_baseline_sample():
                       f"includes table upload + clear; SWGL built with g++ -O2 (generic, non-SSE-intrinsic paths)"}
 
 
+# ---- the other rows of SURVEY.md §8 (parity-test configurations and the §8f "next" rows), same bar:
+# device-timed with the reference's CPU implementation beside it.  Not the contract's bench line
+# (that is config B, the default); run with --workload NAME.
+def other_workloads():
+    from webrender_b200 import abi, scenes
+    return {
+        "b_prime": lambda: scenes.alpha_rects_frame(W, H, 1000, random_rects=True, seed=1, color=None),
+        "text": lambda: scenes.text_frame(width=W, height=H, n_runs=68, glyphs_per_run=89, seed=2, atlas_size=2048),
+        "gradients": lambda: scenes.gradient_frame(width=W, height=H, n_grad=10, full_frame=True),
+        "box_shadow": lambda: scenes.box_shadow_frame(width=1024, height=1024, n_clips=1, full_size=(1024, 1024), seed=7),
+        "clip_rects": lambda: scenes.clip_mask_frame(),
+        "composite": lambda: scenes.composite_frame(W, H, 1024, 512, seed=4),
+        "images": lambda: scenes.image_frame(width=W, height=H, seed=1),
+        "blur": lambda: scenes.blur_frame(seed=1, color=True),
+        "cache_linear_gradients": lambda: scenes.cached_gradient_frame(abi.KIND_LINEAR_GRADIENT, 2048, 2048, n_tasks=96, seed=1),
+        "cache_radial_gradients": lambda: scenes.cached_gradient_frame(abi.KIND_RADIAL_GRADIENT, 2048, 2048, n_tasks=96, seed=1),
+        "cache_conic_gradients": lambda: scenes.cached_gradient_frame(abi.KIND_CONIC_GRADIENT, 2048, 2048, n_tasks=96, seed=1),
+        "quad_radial_gradients": lambda: scenes.quad_gradient_frame(abi.KIND_QUAD_RADIAL_GRADIENT, W, H, n_quads=24, seed=1),
+        "borders_solid": lambda: scenes.border_frame(abi.KIND_BORDER_SOLID, 2048, 2048, n_borders=40, seed=1),
+        "borders_complex": lambda: scenes.border_frame(abi.KIND_BORDER_SEGMENT, 2048, 2048, n_borders=40, seed=1, scale=1.5),
+        "line_decorations": lambda: scenes.line_decoration_frame(1024, 1024, n_tasks=400, seed=1),
+    }
+
+
+def _frame_pixels(frame):
+    """Σ over batches of instance-rect areas where the instance starts with a device rect; else target area."""
+    t = frame.passes[-1][-1]
+    d = frame.textures[t.texture]
+    return d.width * d.height
+
+
+def run_other_workload(args):
+    import numpy as np
+    import torch
+    from webrender_b200 import abi
+    from webrender_b200.device import CudaDevice
+    from webrender_b200.frame import draw_frame
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the wrcu backend has no CPU path")
+    dev = CudaDevice(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if args.workload == "update_path":
+        line = run_update_path(dev, flush, args)
+        print(json.dumps(line))
+        dev.close()
+        return
+    make = other_workloads()[args.workload]
+    frame = make()
+    handles = draw_frame(dev, frame)
+    for _ in range(max(args.warmup, 3)):
+        draw_frame(dev, frame, handles)
+    dev.finish()
+    dev.reset_stats()
+    ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dev.timer_begin()
+        draw_frame(dev, frame, handles)
+        ms.append(dev.timer_end())
+    launches = dev.stats()["kernel_launches"] // max(1, args.steps)
+    ms.sort()
+    med = ms[len(ms) // 2]
+    line = {"metric": "frames/s of the named workload", "value": 1e3 / med, "unit": "frames/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": med, "higher_is_better": True,
+            "data": "synthetic", "config": {"workload": args.workload, "l2": "flushed between iterations"},
+            "gpu_launches": int(launches), "target_pixels": _frame_pixels(frame)}
+    if not args.no_cpu_baseline:
+        # the reference's own CPU implementation (SWGL, 1 core) on the same frame; bounded to ~15 s
+        from oracle.backends import OracleDevice, SwglDevice, have_swgl
+        kind = "reference" if have_swgl() else "port"
+        d = (SwglDevice if kind == "reference" else OracleDevice)()
+        h = draw_frame(d, frame)
+        best, reps, t_end = None, 0, time.perf_counter() + 15.0
+        while reps < 1 or (time.perf_counter() < t_end and reps < 5):
+            t0 = time.perf_counter()
+            draw_frame(d, frame, h)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            reps += 1
+        d.close()
+        line["cpu_baseline"] = {"value": 1.0 / best, "unit": "frames/s", "cores": 1, "kind": kind,
+                                "sample": f"the same frame, best of {reps}"}
+    print(json.dumps(line))
+    dev.close()
+
+
+def run_update_path(dev, flush, args):
+    """§8f rank 3: a 2048^2 R8 glyph atlas arriving as 1024 tile uploads out of one staging blob, and a
+    64K-block GPU cache arriving as ~5K Copy records; host memory in, device memory out, per step."""
+    import numpy as np
+    import torch
+    from webrender_b200 import abi
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    rng = np.random.RandomState(1)
+    size, tile = 2048, 64
+    atlas = rng.randint(0, 256, (size, size)).astype(np.uint8)
+    rects, off, blob = [], 0, []
+    for y in range(0, size, tile):
+        for x in range(0, size, tile):
+            rects.append((x, y, tile, tile, off, tile))
+            blob.append(np.ascontiguousarray(atlas[y:y + tile, x:x + tile]).reshape(-1))
+            off += tile * tile
+    staging = np.concatenate(blob)
+    cache = rng.uniform(0, 1, (65536, 4)).astype(np.float32)
+    updates, a = [], 0
+    while a < len(cache):
+        c = int(min(rng.randint(1, 25), len(cache) - a, 1024 - (a % 1024)))
+        updates.append((a, c, a % 1024, a // 1024))
+        a += c
+    tex = dev.texture_create(abi.FMT_R8, size, size)
+    zero = dict(prim_headers_f=np.zeros((0, 4), np.float32), prim_headers_i=np.zeros((0, 4), np.int32),
+                transforms=np.zeros((0, 4), np.float32), render_tasks=np.zeros((0, 4), np.float32),
+                gpu_cache=None, gpu_buffer_f=np.zeros((0, 4), np.float32), gpu_buffer_i=np.zeros((0, 4), np.int32))
+
+    def step():
+        dev.gpu_cache_update(64, False, updates, cache)
+        dev.frame_begin(zero)
+        dev.texture_upload_batch(tex, rects, staging)
+        dev.frame_end()
+
+    for _ in range(3):
+        step()
+    dev.finish()
+    ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        dev.finish()
+        ms.append((time.perf_counter() - t0) * 1e3)
+    ms.sort()
+    med = ms[len(ms) // 2]
+    got = dev.read_pixels(tex, 0, 0, size, size, 1)
+    assert np.array_equal(got, atlas), "uploaded atlas differs"
+    nbytes = staging.size + cache.nbytes
+    line = {"metric": "update-path throughput (host memory in, device memory out)", "value": nbytes / (med * 1e-3) / 1e9,
+            "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": med, "higher_is_better": True,
+            "data": "synthetic", "gpu_launches": 2,
+            "config": {"workload": "update_path", "atlas": "2048^2 R8 in 1024 64x64 rects", "gpu_cache_blocks": len(cache),
+                       "gpu_cache_updates": len(updates), "timing": "host wall clock incl. ctypes marshalling, synchronised"}}
+    if not args.no_cpu_baseline:
+        from oracle.backends import OracleDevice, SwglDevice, have_swgl
+        kind = "reference" if have_swgl() else "port"
+        d = (SwglDevice if kind == "reference" else OracleDevice)()
+        t = d.texture_create(abi.FMT_R8, size, size)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            d.gpu_cache_update(64, False, updates, cache)
+            d.texture_upload_batch(t, rects, staging)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        d.close()
+        line["cpu_baseline"] = {"value": nbytes / best / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
+                                "sample": "the same update lists through the reference's TexSubImage2D plumbing, best of 3"}
+    return line
+
+
 def run_config_e(dev, rank, world, steps, barrier):
     """One 8192x4096 frame = 64 picture-cache tiles of 1024x512 (config-B' rect
     list cut per tile), tiles round-robin over the ranks, one NCCL gather to
@@ -208,11 +368,16 @@ def main():
     ap.add_argument("--impl", default="wrcu", choices=["wrcu", "reference"])
     ap.add_argument("--ref-rects", type=int, default=400, help="layers per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config_b",
+                    help="config_b (the contract's bench line) or one of the other §8 rows: see other_workloads(), update_path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "wrcu" else args.warmup
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload != "config_b":
+        run_other_workload(args)
         return
 
     import numpy as np
