@@ -277,14 +277,18 @@ def run_update_path(dev, flush, args):
         updates.append((a, c, a % 1024, a // 1024))
         a += c
     tex = dev.texture_create(abi.FMT_R8, size, size)
+    # what a host holds between frames: #[repr(C)] arrays, and the pixels in page-locked memory (the PBO analogue)
+    rect_arr, upd_arr = dev.upload_rects(rects), dev.gpu_cache_copies(updates)
+    pinned = dev.host_alloc(staging.shape, np.uint8)
+    pinned[:] = staging
     zero = dict(prim_headers_f=np.zeros((0, 4), np.float32), prim_headers_i=np.zeros((0, 4), np.int32),
                 transforms=np.zeros((0, 4), np.float32), render_tasks=np.zeros((0, 4), np.float32),
                 gpu_cache=None, gpu_buffer_f=np.zeros((0, 4), np.float32), gpu_buffer_i=np.zeros((0, 4), np.int32))
 
     def step():
-        dev.gpu_cache_update(64, False, updates, cache)
+        dev.gpu_cache_update(64, False, upd_arr, cache)
         dev.frame_begin(zero)
-        dev.texture_upload_batch(tex, rects, staging)
+        dev.texture_upload_batch(tex, rect_arr, pinned)
         dev.frame_end()
 
     for _ in range(3):

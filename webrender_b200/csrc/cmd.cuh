@@ -58,7 +58,12 @@ struct __align__(16) CmdCold {
   float gpx[4], gpy[4];
   float gclip[4];
   struct { short row, lrow, rrow; uint8_t l0, l1, r0, r1; } gev[6];
-  int gn_ev, gflipped, gaa_mask, gpad;
+  int gn_ev, gflipped, gaa_mask;
+  // Row table (axis-aligned quads of >= WR_ROW_TAB_MIN rows with interpolants): the edge
+  // interpolants of every row, 2*row_n floats per row (left, right per interpolant) from float
+  // offset row_off of RasterArgs.row_tab; -1 = none, wr_row_interp walks the sums itself.
+  int row_off;
+  int row_n, rpad[3];
 };
 
 // Per-(command,row) state of a general quad, computed by wr_general_row.
@@ -75,4 +80,6 @@ struct BatchInfo {
   int simple;              // 1 while every command is a plain solid quad (no mask/AA/texture, lanes<=255)
   int premul_valid;        // 1 while every command's colour lanes are <= its alpha lane
   int tile_counter;        // dynamic tile scheduler of the generic raster kernel
+  int row_alloc;           // floats of the row-table pool handed out to this batch's commands
 };
+#define WR_ROW_TAB_MIN 16

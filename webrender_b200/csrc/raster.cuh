@@ -42,6 +42,7 @@ struct RasterArgs {
   const uint32_t* tile_mask;  // bitmask bins (see SetupArgs), nullptr = scan every command
   const uint32_t* wide_mask;
   int bin_words, bin_tiles_x;
+  const float* row_tab;  // row tables written by the setup kernel (CmdCold::row_off)
 };
 
 #define CHUNK_CMDS 256
@@ -191,6 +192,18 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
   if (!isfinite(stepScale)) stepScale = 0.0f;
   float x0f = __fsub_rn(__fadd_rn((float)c.x0, 0.5f), k.xl);
   int rows = y - c.y0;
+  if (k.row_off >= 0 && k.row_n == N) {
+    // the setup kernel already walked the edge sums of every row of this command
+    const float* t = a.row_tab + k.row_off + (size_t)rows * (2 * N);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float li = __ldg(t + 2 * i), ri = __ldg(t + 2 * i + 1);
+      float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
+      step[i] = st;
+      o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
+    }
+    return;
+  }
 #ifndef WRCU_HOSTEMU
   // The 2N edge sums are independent and the whole warp is here (row_setup is
   // warp-uniform): lane l < 2N walks one of them, the results are broadcast.

@@ -9,6 +9,7 @@
 #pragma once
 #include "blend.cuh"
 #include "cmd.cuh"
+#include "repeat_add.cuh"
 #include "wrcu_internal.h"
 
 #define WR_WIDE_TILES 64
@@ -32,6 +33,8 @@ struct SetupArgs {
   int blend_enabled;
   uint32_t features;
   int kind;  // WRCU_KIND_* (setup functions shared by several kinds)
+  float* row_tab;   // row-table pool (see CmdCold::row_off), row_cap floats
+  int row_cap;
   TexView color0;
   TexView color1;
   TexView clip_mask;
@@ -46,22 +49,64 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
   info->simple = 1;
   info->premul_valid = 1;
   info->tile_counter = 0;
+  info->row_alloc = 0;
 }
 // Each setup kernel also re-arms the per-batch record the NEXT draw will use
 // (records rotate through a ring of 4; the one after the current was last read
 // three draws ago), so no separate initialisation launch is needed per draw.
+// Row tables.  The raster kernel needs, for every (command,row) it touches, the edge
+// interpolants of that row — running sums down the quad's edges (rasterize.h:880-930).  A
+// full-height quad is touched by ~30 tiles per row, each of which would otherwise re-walk
+// the sums (wr_repeat_add, O(binades)); instead the setup kernel writes them once: after its
+// 32 instances are emitted, the warp fills the table of each in turn, lanes split over the
+// 2N edge sums x blocks of rows (a block starts with one wr_repeat_add, then plain additions —
+// the reference's own sequence).
+WRD void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
+  const CmdHot c = a.hot[cidx];
+  const CmdCold& k = a.cold[cidx];
+  const int E = 2 * k.row_n, rows = c.y1 - c.y0;
+  if (E <= 0 || E > 32) return;
+  const int nblk = 32 / E;
+  const int e = lane % E, blk = lane / E;
+  if (blk >= nblk) return;
+  const int per = (rows + nblk - 1) / nblk;
+  const int r0 = blk * per, r1 = min(rows, r0 + per);
+  if (r0 >= r1) return;
+  const int i = e >> 1;
+  const float top = (e & 1) ? k.i_rt[i] : k.i_lt[i], bot = (e & 1) ? k.i_rb[i] : k.i_lb[i];
+  const float sl = __fmul_rn(__fsub_rn(bot, top), k.yscale);
+  const float dy = __fsub_rn((float)c.y0 + 0.5f, k.yt);
+  float v = wr_repeat_add(__fadd_rn(top, __fmul_rn(dy, sl)), sl, r0);
+  float* t = a.row_tab + k.row_off + e;
+  for (int r = r0; r < r1; r++) {
+    t[(size_t)r * E] = v;
+    v = __fadd_rn(v, sl);
+  }
+}
 #ifdef WRCU_HOSTEMU
 #define WR_SETUP_KERNEL(name)                                     \
   static void name(const SetupArgs& a) {                          \
     wr_reset_batch_info(a.info_next);                             \
-    for (int i = 0; i < a.n; i++) name##_one(a, i);               \
+    for (int i = 0; i < a.n; i++) {                               \
+      name##_one(a, i);                                           \
+      if (a.cold[i].row_off >= 0)                                 \
+        for (int lane = 0; lane < 32; lane++) wr_fill_row_table(a, i, lane); \
+    }                                                             \
   }
 #else
-#define WR_SETUP_KERNEL(name)                              \
-  __global__ void name(SetupArgs a) {                      \
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;       \
-    if (idx == 0) wr_reset_batch_info(a.info_next);        \
-    if (idx < a.n) name##_one(a, idx);                     \
+#define WR_SETUP_KERNEL(name)                                                  \
+  __global__ void name(SetupArgs a) {                                          \
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;                           \
+    if (idx == 0) wr_reset_batch_info(a.info_next);                            \
+    if (idx < a.n) name##_one(a, idx);                                         \
+    __syncwarp();                                                              \
+    unsigned m = __ballot_sync(0xFFFFFFFFu, idx < a.n && a.cold[idx].row_off >= 0); \
+    const int lane = threadIdx.x & 31, wbase = idx - lane;                     \
+    while (m) {                                                                \
+      const int src = __ffs((int)m) - 1;                                       \
+      m &= m - 1;                                                              \
+      wr_fill_row_table(a, wbase + src, lane);                                 \
+    }                                                                          \
   }
 #endif
 
@@ -144,6 +189,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
   h.cold = idx;
   CmdCold k;
   memset(&k, 0, sizeof k);
+  k.row_off = -1;
   bool ok = false;
   do {
     if (q.pos[1].w != q.pos[0].w || q.pos[2].w != q.pos[0].w || q.pos[3].w != q.pos[0].w) {
@@ -343,6 +389,14 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     ok = true;
   } while (0);
   a.hot[idx] = h;
+  if (ok && a.row_tab && q.n_interp > 0 && !(h.flags & CMD_GENERAL) && (int)h.y1 - (int)h.y0 >= WR_ROW_TAB_MIN) {
+    const int need = ((int)h.y1 - (int)h.y0) * 2 * q.n_interp;
+    const int off = atomicAdd(&a.info->row_alloc, need);
+    if (off >= 0 && off + need <= a.row_cap) {  // pool exhausted: the raster kernel walks the sums itself
+      k.row_off = off;
+      k.row_n = q.n_interp;
+    }
+  }
   if (ok) {
     bool simple = (h.flags & CMD_CONST_COLOR) && !(h.flags & (CMD_MASK | CMD_AA | CMD_TEXTURED | CMD_OUT_RRRR | CMD_GENERAL)) &&
                   h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255;

@@ -206,6 +206,11 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   }
   cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
   WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info, 4);
+  c->row_cap = 16 << 20;  // 64 MiB of row tables per batch; commands beyond it fall back to walking
+  if (cudaMalloc((void**)&c->row_tab, (size_t)c->row_cap * sizeof(float)) != cudaSuccess) {
+    c->row_tab = nullptr;
+    c->row_cap = 0;
+  }
   *out = c;
   return WRCU_OK;
 }
@@ -224,6 +229,8 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->cmd_hot) cudaFree(c->cmd_hot);
   if (c->cmd_cold) cudaFree(c->cmd_cold);
   if (c->batch_info) cudaFree(c->batch_info);
+  if (c->row_tab) cudaFree(c->row_tab);
+  if (c->gpu_cache_dev) cudaFree(c->gpu_cache_dev);
   if (c->dev_err) cudaFree(c->dev_err);
   if (c->bin_mask) cudaFree(c->bin_mask);
   if (c->t0) cudaEventDestroy(c->t0);
@@ -261,7 +268,8 @@ extern "C" int wrcu_stream(wrcu_ctx* c, void** stream) {
 // ---- arena ---------------------------------------------------------------------------
 // Stage `bytes` of host data for the device: copy into the pinned arena (so the
 // caller may free its buffer on return) and queue the H2D copy on the stream.
-static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
+// Reserve `bytes` in the current arena (host and device side at the same offset).
+static int arena_reserve(wrcu_ctx* c, size_t bytes, size_t* off_out) {
   Arena* a = &c->arena[c->cur_arena];
   size_t off = align_up(a->used, 256);
   if (off + bytes > a->cap) {
@@ -290,9 +298,27 @@ static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
     a->dev = nd;
     a->cap = ncap;
   }
-  memcpy(a->host + off, src, bytes);
-  WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, bytes, cudaMemcpyHostToDevice, c->stream));
   a->used = off + bytes;
+  *off_out = off;
+  return WRCU_OK;
+}
+
+static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
+  size_t off = 0;
+  int rc = arena_reserve(c, bytes, &off);
+  if (rc != WRCU_OK) return rc;
+  Arena* a = &c->arena[c->cur_arena];
+  // page-locked memory handed out by wrcu_host_alloc goes to the device directly (the mapped-PBO
+  // case of the reference's upload path); anything else is first copied into the pinned arena
+  bool pinned = false;
+  for (const auto& ha : c->host_allocs)
+    if ((const uint8_t*)src >= ha.first && (const uint8_t*)src + bytes <= ha.first + ha.second) { pinned = true; break; }
+  if (pinned) {
+    WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    memcpy(a->host + off, src, bytes);
+    WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
   c->stats.h2d_bytes += bytes;
   *dev_out = a->dev + off;
   return WRCU_OK;
@@ -414,11 +440,16 @@ extern "C" int wrcu_host_alloc(wrcu_ctx* c, size_t bytes, void** out) {
   if (!out || bytes == 0) return wrcu_fail(c, WRCU_ERR_INVALID, "host_alloc: bad arguments");
   cudaSetDevice(c->device);
   WRCU_CUDA(c, cudaMallocHost(out, bytes));
+  c->host_allocs.push_back(std::make_pair((uint8_t*)*out, bytes));
   return WRCU_OK;
 }
 extern "C" int wrcu_host_free(wrcu_ctx* c, void* ptr) {
-  if (ptr) cudaFreeHost(ptr);
-  (void)c;
+  if (!ptr) return WRCU_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);  // a staged copy may still be reading it
+  for (size_t i = 0; i < c->host_allocs.size(); i++)
+    if (c->host_allocs[i].first == (uint8_t*)ptr) { c->host_allocs.erase(c->host_allocs.begin() + i); break; }
+  cudaFreeHost(ptr);
   return WRCU_OK;
 }
 
@@ -575,21 +606,41 @@ extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
     a->in_flight = false;
   }
   a->used = 0;
-  int rc;
-  void* p;
-#define TAB(field, count, T)                                                     \
-  c->tables.field = nullptr;                                                     \
-  c->tables.n_##field = (int)t->count;                                           \
-  if (t->count) {                                                                \
-    if (!t->field) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null " #field); \
-    if ((rc = stage(c, t->field, t->count * 16, &p)) != WRCU_OK) return rc;      \
-    c->tables.field = (const T*)p;                                               \
+  // all seven tables travel in ONE host-to-device copy (they are a few KB each)
+  struct TabDesc { const void* src; size_t texels; size_t off; };
+  TabDesc td[7] = {{t->prim_headers_f, t->prim_headers_f_texels, 0}, {t->prim_headers_i, t->prim_headers_i_texels, 0},
+                   {t->transforms, t->transforms_texels, 0},         {t->render_tasks, t->render_tasks_texels, 0},
+                   {t->gpu_cache, t->gpu_cache_texels, 0},           {t->gpu_buffer_f, t->gpu_buffer_f_texels, 0},
+                   {t->gpu_buffer_i, t->gpu_buffer_i_texels, 0}};
+  size_t total = 0;
+  for (int i = 0; i < 7; i++) {
+    if (td[i].texels && !td[i].src) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null table %d", i);
+    td[i].off = total;
+    total += (td[i].texels * 16 + 255) & ~(size_t)255;
   }
-  TAB(prim_headers_f, prim_headers_f_texels, float4)
-  TAB(prim_headers_i, prim_headers_i_texels, int4)
-  TAB(transforms, transforms_texels, float4)
-  TAB(render_tasks, render_tasks_texels, float4)
-  TAB(gpu_cache, gpu_cache_texels, float4)
+  uint8_t* dbase = nullptr;
+  c->tables = FrameTablesDev();  // last frame's pointers must not be rebased if the arena grows below
+  if (total) {
+    size_t off = 0;
+    int rc = arena_reserve(c, total, &off);
+    if (rc != WRCU_OK) return rc;
+    for (int i = 0; i < 7; i++)
+      if (td[i].texels) memcpy(a->host + off + td[i].off, td[i].src, td[i].texels * 16);
+    WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, total, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += total;
+    dbase = a->dev + off;
+  }
+#define TAB(i, field, T)                                                         \
+  c->tables.n_##field = (int)td[i].texels;                                        \
+  c->tables.field = td[i].texels ? (const T*)(dbase + td[i].off) : nullptr;
+  TAB(0, prim_headers_f, float4)
+  TAB(1, prim_headers_i, int4)
+  TAB(2, transforms, float4)
+  TAB(3, render_tasks, float4)
+  TAB(4, gpu_cache, float4)
+  TAB(5, gpu_buffer_f, float4)
+  TAB(6, gpu_buffer_i, int4)
+#undef TAB
   c->gpu_cache_bound = false;
   if (!t->gpu_cache && !t->gpu_cache_texels && c->gpu_cache_dev) {
     // the persistent GPU cache texture maintained by wrcu_gpu_cache_update
@@ -597,9 +648,6 @@ extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
     c->tables.n_gpu_cache = c->gpu_cache_rows * 1024;
     c->gpu_cache_bound = true;
   }
-  TAB(gpu_buffer_f, gpu_buffer_f_texels, float4)
-  TAB(gpu_buffer_i, gpu_buffer_i_texels, int4)
-#undef TAB
   return WRCU_OK;
 }
 
@@ -756,6 +804,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.info = info_cur;
   sa.info_next = (BatchInfo*)c->batch_info + ((c->draw_seq + 1) & 3);
   sa.err_counter = c->dev_err;
+  sa.row_tab = c->row_tab;
+  sa.row_cap = c->row_cap;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
@@ -922,6 +972,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
                       host_round_pixel(st->blend_color[0]) & 0xFFFF, host_round_pixel(st->blend_color[3]) & 0xFFFF};
   ra.color0 = sa.color0;
   ra.color1 = sa.color1;
+  ra.row_tab = c->row_tab;
   ra.gbuf_f = c->tables.gpu_buffer_f;
   ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
   ra.gpu_cache = c->tables.gpu_cache;
@@ -936,7 +987,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   // plain solid quads; the specialised and the generic kernel each return at
   // once when it is not their turn (the host never has to wait for the flag).
   bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
-                 ra.depth_mode == WRCU_DEPTH_OFF;
+                 ra.depth_mode == WRCU_DEPTH_OFF &&
+                 (kind == WRCU_KIND_QUAD_TEXTURED || kind == WRCU_KIND_BRUSH_SOLID);  // the only kinds that emit CMD_CONST_COLOR
   ra.fast_eligible = fast_ok ? 1 : 0;
   if (fast_ok) {
 #ifdef WRCU_HOSTEMU

@@ -23,6 +23,8 @@
 #define WRD_MEMBER __device__ static __forceinline__
 #endif
 #include <stdint.h>
+#include <utility>
+#include <vector>
 #include <stdio.h>
 #include <string.h>
 
@@ -124,6 +126,9 @@ struct wrcu_ctx {
   float4* gpu_cache_dev = nullptr;
   int gpu_cache_rows = 0;
   bool gpu_cache_bound = false;  // this frame's tables.gpu_cache is the persistent cache (not in an arena)
+  std::vector<std::pair<uint8_t*, size_t>> host_allocs;  // wrcu_host_alloc blocks (staged without a copy)
+  float* row_tab = nullptr;      // row-table pool of the current batch (CmdCold::row_off)
+  int row_cap = 0;               // floats
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
 };
 

@@ -84,8 +84,17 @@ class DeviceBase:
     def texture_upload_batch(self, tex, rects, staging):
         """rects: [(x, y, w, h, offset, stride)]; staging: one contiguous uint8 blob."""
         staging = np.ascontiguousarray(staging).view(np.uint8).reshape(-1)
-        arr = (abi.UploadRect * len(rects))(*[abi.UploadRect(*[int(v) for v in r]) for r in rects])
-        self._check(self._f("texture_upload_batch")(self.ctx, tex, arr, len(rects), staging.ctypes.data, staging.size))
+        arr = rects if isinstance(rects, C.Array) else self.upload_rects(rects)
+        self._check(self._f("texture_upload_batch")(self.ctx, tex, arr, len(arr), staging.ctypes.data, staging.size))
+
+    @staticmethod
+    def upload_rects(rects):
+        """The #[repr(C)] rect array for texture_upload_batch (build once, reuse across frames)."""
+        return (abi.UploadRect * len(rects))(*[abi.UploadRect(*[int(v) for v in r]) for r in rects])
+
+    @staticmethod
+    def gpu_cache_copies(updates):
+        return (abi.GpuCacheCopy * max(1, len(updates)))(*[abi.GpuCacheCopy(*[int(v) for v in u]) for u in updates])
 
     def texture_copy(self, src, dst, src_rect, dst_x, dst_y):
         self._check(self._f("texture_copy")(self.ctx, src, dst, (C.c_int32 * 4)(*src_rect), dst_x, dst_y))
@@ -93,8 +102,9 @@ class DeviceBase:
     def gpu_cache_update(self, height, clear, updates, blocks):
         """updates: [(block_index, block_count, u, v)] (GpuCacheUpdate::Copy); blocks: (n, 4) float32."""
         blocks = np.ascontiguousarray(blocks, dtype=np.float32).reshape(-1, 4)
-        arr = (abi.GpuCacheCopy * max(1, len(updates)))(*[abi.GpuCacheCopy(*[int(v) for v in u]) for u in updates])
-        self._check(self._f("gpu_cache_update")(self.ctx, height, 1 if clear else 0, arr, len(updates),
+        n = len(updates)
+        arr = updates if isinstance(updates, C.Array) else self.gpu_cache_copies(updates)
+        self._check(self._f("gpu_cache_update")(self.ctx, height, 1 if clear else 0, arr, n,
                                                 blocks.ctypes.data if len(blocks) else None, len(blocks)))
 
     def read_pixels(self, tex, x, y, w, h, bpp):
