@@ -61,12 +61,13 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
 // 32 instances are emitted, the warp fills the table of each in turn, lanes split over the
 // 2N edge sums x blocks of rows (a block starts with one wr_repeat_add, then plain additions —
 // the reference's own sequence).
+// tall commands: the 32 lanes split one command's 2N edge sums x blocks of rows
 WRD void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
   const CmdHot c = a.hot[cidx];
   const CmdCold& k = a.cold[cidx];
   const int E = 2 * k.row_n, rows = c.y1 - c.y0;
   if (E <= 0 || E > 32) return;
-  const int nblk = 32 / E;
+  const int nblk = min(32 / E, (rows + 255) / 256);
   const int e = lane % E, blk = lane / E;
   if (blk >= nblk) return;
   const int per = (rows + nblk - 1) / nblk;
@@ -83,6 +84,24 @@ WRD void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
     v = __fadd_rn(v, sl);
   }
 }
+// short commands: one lane walks one edge sum of one command from its first row (plain additions,
+// the reference's own sequence); 32 / 2N commands are filled at once
+WRD void wr_fill_row_edge(const SetupArgs& a, int cidx, int e) {
+  const CmdHot c = a.hot[cidx];
+  const CmdCold& k = a.cold[cidx];
+  const int E = 2 * k.row_n, rows = c.y1 - c.y0;
+  const int i = e >> 1;
+  const float top = (e & 1) ? k.i_rt[i] : k.i_lt[i], bot = (e & 1) ? k.i_rb[i] : k.i_lb[i];
+  const float sl = __fmul_rn(__fsub_rn(bot, top), k.yscale);
+  const float dy = __fsub_rn((float)c.y0 + 0.5f, k.yt);
+  float v = __fadd_rn(top, __fmul_rn(dy, sl));
+  float* t = a.row_tab + k.row_off + e;
+  for (int r = 0; r < rows; r++) {
+    t[(size_t)r * E] = v;
+    v = __fadd_rn(v, sl);
+  }
+}
+#define WR_ROW_TAB_TALL 512
 #ifdef WRCU_HOSTEMU
 #define WR_SETUP_KERNEL(name)                                     \
   static void name(const SetupArgs& a) {                          \
@@ -90,23 +109,39 @@ WRD void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
     for (int i = 0; i < a.n; i++) {                               \
       name##_one(a, i);                                           \
       if (a.cold[i].row_off >= 0)                                 \
-        for (int lane = 0; lane < 32; lane++) wr_fill_row_table(a, i, lane); \
+        for (int e = 0; e < 2 * a.cold[i].row_n; e++) wr_fill_row_edge(a, i, e); \
     }                                                             \
   }
 #else
+WRD void wr_fill_row_tables_warp(const SetupArgs& a, int idx) {
+  const int lane = threadIdx.x & 31, wbase = idx - lane;
+  const bool has = idx < a.n && a.cold[idx].row_off >= 0;
+  unsigned m = __ballot_sync(0xFFFFFFFFu, has);
+  if (!m) return;
+  const int myE = has ? 2 * a.cold[idx].row_n : 0;
+  const int myRows = has ? (int)a.hot[idx].y1 - (int)a.hot[idx].y0 : 0;
+  const int E0 = __shfl_sync(0xFFFFFFFFu, myE, __ffs((int)m) - 1);
+  unsigned mshort = __ballot_sync(0xFFFFFFFFu, has && myE == E0 && myRows <= WR_ROW_TAB_TALL);
+  unsigned mlong = m & ~mshort;
+  const int G = 32 / E0, slot = lane / E0, e = lane % E0;
+  while (mshort) {
+    const unsigned src = __fns(mshort, 0, slot + 1);  // lane of the slot-th pending command
+    if (slot < G && src < 32u) wr_fill_row_edge(a, wbase + (int)src, e);
+    for (int i = 0; i < G && mshort; i++) mshort &= mshort - 1;
+  }
+  while (mlong) {
+    const int src = __ffs((int)mlong) - 1;
+    mlong &= mlong - 1;
+    wr_fill_row_table(a, wbase + src, lane);
+  }
+}
 #define WR_SETUP_KERNEL(name)                                                  \
   __global__ void name(SetupArgs a) {                                          \
     int idx = blockIdx.x * blockDim.x + threadIdx.x;                           \
     if (idx == 0) wr_reset_batch_info(a.info_next);                            \
     if (idx < a.n) name##_one(a, idx);                                         \
     __syncwarp();                                                              \
-    unsigned m = __ballot_sync(0xFFFFFFFFu, idx < a.n && a.cold[idx].row_off >= 0); \
-    const int lane = threadIdx.x & 31, wbase = idx - lane;                     \
-    while (m) {                                                                \
-      const int src = __ffs((int)m) - 1;                                       \
-      m &= m - 1;                                                              \
-      wr_fill_row_table(a, wbase + src, lane);                                 \
-    }                                                                          \
+    wr_fill_row_tables_warp(a, idx);                                           \
   }
 #endif
 
