@@ -148,8 +148,10 @@ ATTRIBS = {
 class SwglDevice:
     """The reference rasteriser behind the wrcu device calls."""
 
-    def __init__(self):
-        self.gl = C.CDLL(SWGL_LIB)
+    def __init__(self, lib_path=None):
+        """lib_path: any library exporting SWGL's `extern "C"` surface (swgl_fns.rs:23-320) — by
+        default the reference build; tests also drive webrender_b200/libwrcu_gl.so through it."""
+        self.gl = C.CDLL(lib_path or SWGL_LIB)
         g = self.gl
         g.CreateContext.restype = C.c_void_p
         g.MakeCurrent.argtypes = [C.c_void_p]
@@ -174,6 +176,8 @@ class SwglDevice:
         g.DrawElementsInstanced.argtypes = [C.c_uint, C.c_int, C.c_uint, C.c_ssize_t, C.c_int]
         g.BlitFramebuffer.argtypes = [C.c_int] * 8 + [C.c_uint, C.c_uint]
         self.ctx = g.CreateContext()
+        if not self.ctx:
+            raise WrcuError(abi.ERR_NO_DEVICE, "CreateContext failed")
         g.MakeCurrent(self.ctx)
         self.tex = {}        # handle -> (fmt, w, h)
         self.fbos = {}       # (color, depth) -> fbo
