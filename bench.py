@@ -78,6 +78,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
 
 
+WORKLOAD_B = ("config B: examples/alpha_perf.rs scene, 1000 full-frame alpha=0.05 rects in one Quad(ColorOrTexture) "
+              "batch at 3840x2160, premultiplied-alpha blend, clear each frame")
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on
     this box's host cores: the unmodified SWGL rasteriser (oracle/_ref) when it
@@ -113,7 +117,9 @@ def run_reference(args):
         "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_t / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "config B: alpha_perf scene, full-width alpha rects, 3840 px wide bands"},
+        "config": {"workload": WORKLOAD_B,
+                   "sample": f"bounded per step: {n_rects} of the 1000 layers, the 3840x2160 frame cut into {cores} "
+                             f"bands of {band_h} rows, one per core"},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind,
                          "sample": f"{n_rects} full-band alpha rects on {cores} bands of {W}x{band_h} px per step "
                                    f"(one persistent SWGL context per core)"},
@@ -555,8 +561,7 @@ def main():
             "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "config B: examples/alpha_perf.rs scene, 1000 full-frame alpha=0.05 rects in one "
-                                   "Quad(ColorOrTexture) batch at 3840x2160, premultiplied-alpha blend, clear each frame",
+            "config": {"workload": WORKLOAD_B,
                        "pixel_layers_per_step": layers, "frames_per_gpu_per_step": 1,
                        "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the wrcu stream"},
             "clocks": clocks,
