@@ -9,6 +9,7 @@
 #include "cs_clip_rectangle.h"
 #include "ps_quad_mask.h"
 #include "brush_image.h"
+#include "brush_image_repeat.h"
 #include "ps_text_run.h"
 #include "brush_linear_gradient.h"
 #include "cs_clip_box_shadow.h"
@@ -63,5 +64,9 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "cs_border_segment")) return cs_border_segment_program::loader;
   if (!strcmp(name, "ps_quad_radial_gradient")) return ps_quad_radial_gradient_program::loader;
   if (!strcmp(name, "ps_quad_conic_gradient")) return ps_quad_conic_gradient_program::loader;
+  if (!strcmp(name, "brush_image ANTIALIASING,REPETITION,TEXTURE_2D"))
+    return brush_image_ANTIALIASING_REPETITION_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "brush_image ALPHA_PASS,ANTIALIASING,REPETITION,TEXTURE_2D"))
+    return brush_image_ALPHA_PASS_ANTIALIASING_REPETITION_TEXTURE_2D_program::loader;
   return nullptr;
 }

@@ -267,3 +267,14 @@ def test_quad_gradients(kind, variant, seed):
                                    rotate=23.0 if variant == "rotated" else None,
                                    blend=abi.BLEND_NONE if variant == "opaque" else abi.BLEND_PREMULTIPLIED_ALPHA)
     assert_same(render(SwglDevice, f), render(OracleDevice, f), kind + "/" + variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", ["linear", "nearest", "fractional", "scaled"])
+def test_brush_image_repetition(seed, variant):
+    """brush_image ANTIALIASING,REPETITION: tiled images and border-image segments through
+    swgl_commitTextureRepeat[Color]RGBA8 (blendTextureLinearRepeat / blendTextureNearestRepeat)."""
+    f = scenes.image_repeat_frame(seed=seed, filter=abi.NEAREST if variant == "nearest" else abi.LINEAR,
+                                  fractional=variant in ("fractional", "scaled"),
+                                  device_pixel_scale=1.5 if variant == "scaled" else 1.0)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -361,6 +361,86 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
     return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
 
 
+def image_repeat_frame(width=640, height=360, n_opaque=6, n_alpha=14, seed=1, filter=abi.LINEAR, fractional=False,
+                       device_pixel_scale=1.0):
+    """Tiled images and border-image segments: Brush(Image) with BatchFeatures::REPETITION
+    (shade.rs:985-1000 "ANTIALIASING,REPETITION"): stretch sizes smaller than the primitive
+    (background-repeat), segment-relative REPEAT_X / REPEAT_Y with ROUND and CENTERED flags and
+    texel-rect nine-patch middles (border-image-repeat), small (few-texel) tiles and 1:1 tiles."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
+    aw, ah = 256, 192
+    atlas = rng.randint(0, 256, size=(ah, aw, 4)).astype(np.uint8)
+    a = atlas[..., 3:4].astype(np.uint16)
+    atlas[..., :3] = (atlas[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)
+    z = 1
+    opaque, alpha = [], []
+
+    def add(rect, uv, color, color_mode, opacity, flags=0, segment=None, stretch=(-1.0, -1.0)):
+        nonlocal z
+        blocks = [color, (0.0, 0.0, 0.0, 0.0), (stretch[0], stretch[1], 0.0, 0.0)]
+        seg_index = 0xFFFF
+        if segment is not None:
+            blocks += [segment[0], segment[1]]
+            seg_index = 0
+        addr = t.push_gpu_cache(blocks)
+        res = t.push_gpu_cache([uv, (0.0, 0.0, 0.0, 0.0)])
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic,
+                                (color_mode | (1 << 16), 0, int(opacity * 65535), 0))
+        z += 1
+        return brush_instance(hdr, CLIP_TASK_EMPTY, seg_index, 0, flags, res)
+
+    def tile_uv(i):
+        if i % 5 == 4:
+            uw, uh = int(rng.randint(1, 4)), int(rng.randint(1, 4))       # a few texels: the solid-span test
+        else:
+            uw, uh = int(rng.randint(8, 64)), int(rng.randint(8, 48))
+        u0, v0 = int(rng.randint(0, aw - uw)), int(rng.randint(0, ah - uh))
+        return (float(u0), float(v0), float(u0 + uw), float(v0 + uh)), uw, uh
+
+    lw, lh = int(width / device_pixel_scale), int(height / device_pixel_scale)
+    for i in range(n_opaque):
+        r = _rand_rect(rng, lw, lh, 40, 260, integer=not fractional)
+        uv, uw, uh = tile_uv(i)
+        st = (float(uw), float(uh)) if i % 2 == 0 else (float(rng.uniform(6, 70)), float(rng.uniform(6, 50)))
+        opaque.append(add(r, uv, (1.0, 1.0, 1.0, 1.0), 4, 1.0, stretch=st))
+    for i in range(n_alpha):
+        r = _rand_rect(rng, lw, lh, 40, 260, integer=not fractional)
+        uv, uw, uh = tile_uv(i)
+        mode = [4, 4, 3, 0, 4][i % 5]
+        col = (1.0, 1.0, 1.0, 1.0) if i % 3 == 0 else tuple(float(v) for v in rng.uniform(0.2, 1.0, 4))
+        rw, rh = r[2] - r[0], r[3] - r[1]
+        k = i % 4
+        if k == 0:      # plain tiling by stretch size
+            alpha.append(add(r, uv, col, mode, rng.uniform(0.5, 1.0),
+                             stretch=(float(rng.uniform(7, 80)), float(rng.uniform(7, 60)))))
+        elif k == 1:    # segment-relative, repeat both axes with explicit sizes, rounded
+            seg = ((float(int(rw / 5)), float(int(rh / 5)), float(int(rw * 4 / 5)), float(int(rh * 4 / 5))),
+                   (0.0, 0.0, float(rng.uniform(9, 40)), float(rng.uniform(9, 30))))
+            alpha.append(add(r, uv, col, mode, rng.uniform(0.5, 1.0), flags=2 | 4 | 8 | 16 | 32, segment=seg))
+        elif k == 2:    # nine-patch middle with texel rect, repeat x centred
+            seg = ((float(int(rw / 4)), float(int(rh / 4)), float(int(rw * 3 / 4)), float(int(rh * 3 / 4))),
+                   (0.25, 0.25, 0.75, 0.75))
+            alpha.append(add(r, uv, col, mode, rng.uniform(0.5, 1.0), flags=2 | 512 | 256 | 4 | 64, segment=seg))
+        else:           # edge segment with texel rect, repeat y centred + rounded
+            seg = ((0.0, float(int(rh / 4)), float(int(rw / 4)), float(int(rh * 3 / 4))), (0.0, 0.25, 0.25, 0.75))
+            alpha.append(add(r, uv, col, mode, rng.uniform(0.5, 1.0), flags=2 | 512 | 8 | 32 | 128, segment=seg))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "depth": TextureDesc(abi.FMT_DEPTH24, width, height),
+                "atlas": TextureDesc(abi.FMT_RGBA8, aw, ah, atlas.reshape(ah, aw * 4), filter=filter)}
+    feats = abi.FEAT_TEXTURE_2D | abi.FEAT_REPETITION | abi.FEAT_ANTIALIASING
+    ops = [Clear(color=(0.2, 0.3, 0.4, 1.0), depth=1.0)]
+    if opaque:
+        ops.append(Batch(abi.KIND_BRUSH_IMAGE, np.stack(opaque[::-1]), blend=abi.BLEND_NONE, depth=abi.DEPTH_TEST_WRITE,
+                         features=feats, color=("atlas", "", "")))
+    if alpha:
+        ops.append(Batch(abi.KIND_BRUSH_IMAGE, np.stack(alpha), blend=abi.BLEND_PREMULTIPLIED_ALPHA, depth=abi.DEPTH_TEST,
+                         features=feats | abi.FEAT_ALPHA_PASS, color=("atlas", "", "")))
+    return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
+
+
 def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atlas_size=512, atlas="r8",
                device_pixel_scale=1.0, fractional=False, color_modes=(0,), with_masks=False):
     """Config C flavour (wrench/benchmarks/text-rendering.yaml): text runs as
