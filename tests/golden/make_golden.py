@@ -60,6 +60,7 @@ CASES = [
     ("cs_conic_gradient", "cached_gradient_frame", dict(kind=19, width=512, height=256, n_tasks=4, seed=2)),
     ("ps_quad_radial_gradient", "quad_gradient_frame", dict(kind=23, seed=2, width=480, height=270, fractional=True)),
     ("ps_quad_conic_gradient", "quad_gradient_frame", dict(kind=24, seed=3, width=480, height=270, rotate=-12.0)),
+    ("brush_image_repetition", "image_repeat_frame", dict(seed=2, n_opaque=0, width=480, height=270, fractional=True)),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

@@ -259,3 +259,14 @@ def test_quad_gradients(kind, variant, seed):
                                    rotate=23.0 if variant == "rotated" else None,
                                    blend=abi.BLEND_NONE if variant == "opaque" else abi.BLEND_PREMULTIPLIED_ALPHA)
     assert_same(render(EmuDevice, f), render(OracleDevice, f), kind + "/" + variant)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["linear", "nearest", "fractional", "scaled"])
+def test_brush_image_repetition(seed, variant):
+    """Exact.  (With opaque occluders in the same pass the known depth-run chunk-phase deviation
+    applies, as for every non-1:1 textured span: DESIGN.md §4.4; bounded in test_cuda_parity.)"""
+    f = scenes.image_repeat_frame(seed=seed, n_opaque=0, filter=abi.NEAREST if variant == "nearest" else abi.LINEAR,
+                                  fractional=variant in ("fractional", "scaled"),
+                                  device_pixel_scale=1.5 if variant == "scaled" else 1.0)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)

@@ -154,6 +154,7 @@ WR_SETUP_KERNEL(wr_setup_brush_solid)
 WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
   int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
   bool alpha_pass = (a.features & WRCU_FEAT_ALPHA_PASS) != 0;
+  const bool repetition = (a.features & WRCU_FEAT_REPETITION) != 0;
   QuadOut q;
   BrushVS vs;
   memset(&q, 0, sizeof q);
@@ -176,6 +177,44 @@ WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
       uv0[0] = r0.x + vs.segment_data.x * usx; uv0[1] = r0.y + vs.segment_data.y * usy;
       uv1[0] = r0.x + vs.segment_data.z * usx; uv1[1] = r0.y + vs.segment_data.w * usy;
     }
+    if (repetition) {  // brush_image.glsl:99-160
+      const float* pr = vs.ph.lr;
+      const float* sr = vs.segment_rect;
+      if (vs.brush_flags & 512) {
+        float rss[2] = {stretch[0], stretch[1]};
+        float hus[2] = {uv1[0] - uv0[0], uv1[1] - uv0[1]}, vus[2] = {uv1[0] - uv0[0], uv1[1] - uv0[1]};
+        if (vs.brush_flags & 256) {  // NINEPATCH_MIDDLE
+          rss[0] = sr[0] - pr[0];
+          rss[1] = sr[1] - pr[1];
+          const float epsilon = 0.001f;
+          vus[0] = uv0[0] - r0.x;
+          if (vus[0] < epsilon || rss[0] < epsilon) {
+            vus[0] = r0.z - uv1[0];
+            rss[0] = pr[2] - sr[2];
+          }
+          hus[1] = uv0[1] - r0.y;
+          if (hus[1] < epsilon || rss[1] < epsilon) {
+            hus[1] = r0.w - uv1[1];
+            rss[1] = pr[3] - sr[3];
+          }
+        }
+        if (vs.brush_flags & 4) stretch[0] = rss[1] * (hus[0] / hus[1]);
+        if (vs.brush_flags & 8) stretch[1] = rss[0] * (vus[1] / vus[0]);
+      } else {
+        if (vs.brush_flags & 4) stretch[0] = vs.segment_data.z - vs.segment_data.x;
+        if (vs.brush_flags & 8) stretch[1] = vs.segment_data.w - vs.segment_data.y;
+      }
+      if (vs.brush_flags & 16) {
+        float wdt = sr[2] - sr[0];
+        float nx = wr_max(1.0f, roundf(wdt / stretch[0]));
+        stretch[0] = wdt / nx;
+      }
+      if (vs.brush_flags & 32) {
+        float hgt = sr[3] - sr[1];
+        float ny = wr_max(1.0f, roundf(hgt / stretch[1]));
+        stretch[1] = hgt / ny;
+      }
+    }
   }
   float perspective = (vs.brush_flags & 1) ? 1.0f : 0.0f;
   if (vs.brush_flags & 2048) { uv0[0] *= tw; uv0[1] *= th; uv1[0] *= tw; uv1[1] *= th; }
@@ -187,6 +226,11 @@ WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
   int color_mode = vs.ph.user_data[0] & 0xffff, blend_mode = vs.ph.user_data[0] >> 16;
   int raster_space = vs.ph.user_data[1];
   float repeat[2] = {(lr[2] - lr[0]) / stretch[0], (lr[3] - lr[1]) / stretch[1]};
+  float noff[2] = {0.0f, 0.0f};  // normalized_offset (brush_image.glsl:213-249)
+  if (repetition) {
+    if (vs.brush_flags & 64) { float h = repeat[0] * 0.5f + 0.5f; noff[0] = 1.0f - (h - floorf(h)); }
+    if (vs.brush_flags & 128) { float h = repeat[1] * 0.5f + 0.5f; noff[1] = 1.0f - (h - floorf(h)); }
+  }
   for (int k = 0; k < 4; k++) {
     float fx = (vs.local_pos[k].x - lr[0]) / (lr[2] - lr[0]);
     float fy = (vs.local_pos[k].y - lr[1]) / (lr[3] - lr[1]);
@@ -204,8 +248,16 @@ WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
     float ux = ((uv1[0] - uv0[0]) * fx + uv0[0]) - minu[0];
     float uy = ((uv1[1] - uv0[1]) * fy + uv0[1]) - minu[1];
     ux *= repeat[0]; uy *= repeat[1];
+    if (repetition) {
+      ux += noff[0] * (maxu[0] - minu[0]);
+      uy += noff[1] * (maxu[1] - minu[1]);
+    }
     ux /= tw; uy /= th;
     if (perspective == 0.0f) { ux *= vs.world_pos[k].w; uy *= vs.world_pos[k].w; }
+    if (repetition) {  // brush_image.glsl:260-265
+      ux /= (maxu[0] / tw - minu[0] / tw);
+      uy /= (maxu[1] / th - minu[1] / th);
+    }
     q.interp[k][0] = ux;
     q.interp[k][1] = uy;
   }
@@ -250,6 +302,10 @@ WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
     for (int i = 0; i < 8; i++) { k->f[i] = fcold[i]; k->g[i] = gcold[i]; }
     k->i[0] = (int)shadow[0] | ((int)shadow[1] << 16);
     k->i[1] = (int)shadow[2] | ((int)shadow[3] << 16);
+    k->g[8] = maxu[0] / tw;  // v_uv_bounds.zw
+    k->g[9] = maxu[1] / th;
+    k->g[10] = (repetition && alpha_pass) ? repeat[0] + noff[0] : 0.0f;  // v_tile_repeat_bounds
+    k->g[11] = (repetition && alpha_pass) ? repeat[1] + noff[1] : 0.0f;
   }
   wr_finish_setup(a, unsupported);
 }

@@ -77,6 +77,60 @@ WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
   }
 }
 
+// blendTextureLinearDispatch's partition (swgl_ext.h:385-448) for a span whose quantised uv lanes,
+// steps, clamp bounds and filter are already in `r`: prefix through the fallback filter, interior
+// through the selected filter, remainder through the fallback; plus the running-sum bases of the
+// first chunk >= tile_rel inside each segment.
+WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int tile_rel) {
+  const int filter = r.filter;
+  r.before = 0;
+  r.inside = 0;
+  if (filter != LF_FALLBACK) {
+    // blendTextureLinearDispatch (swgl_ext.h:385-448)
+    float q0 = r.qu[0];
+    float beforeDist = wr_max(0.0f, r.minu) - q0;
+    if (beforeDist > 0) {
+      r.before = min(max((int)ceilf(beforeDist / r.ustep) * 4, 0), body_len);
+      q0 = q0 + (float)(r.before / 4) * r.ustep;
+    }
+    float insideDist = wr_min(r.maxu, (float)((t.w - 4) * 128)) - q0;
+    if (r.ustep > 0.0f && insideDist >= r.ustep) {
+      int inside = body_len - r.before;
+      if (filter == LF_DOWNSCALE) inside = min(((int)(insideDist * (0.5f / 128.0f))) & ~3, inside);
+      else if (filter == LF_UPSCALE) inside = min((int)(insideDist / r.ustep) * 4, inside);
+      else inside = min(((int)(insideDist * (1.0f / 128.0f))) & ~3, inside);
+      r.inside = max(inside, 0);
+    }
+    if (r.inside > 0) {
+      int ix0 = (int)wr_clamp(q0, r.minu, r.maxu), iy0 = (int)wr_clamp(r.qv[0], r.minv, r.maxv);
+      r.uiy0 = iy0;
+      int tx = ix0 >> 7, ty = iy0 >> 7;
+      r.fcx = wr_clamp_coord(tx, t.w - 1);
+      r.fcy = wr_clamp_coord(ty, t.h);
+      r.fnext = (ty >= 0 && ty < t.h - 1) ? 1 : 0;
+      int overread = tx > t.w - 2 ? -1 : 0;
+      r.ffx = (int)(short)((((ix0 & (tx >= 0 ? -1 : 0)) | overread) & 0x7F) - overread);
+      r.ffy = iy0 & 0x7F;
+    }
+  }
+  // running-sum bases per segment
+  {
+    float start[4];
+    for (int j = 0; j < 4; j++) start[j] = r.qu[j];
+    r.kb[0] = max(0, tile_rel >> 2);
+    if (r.before > 0) wr_tex_seq_base(start, r.ustep, min(r.kb[0], r.before >> 2), r.bu[0]);
+    if (r.before > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.before / 4) * r.ustep;
+    r.kb[1] = max(0, (tile_rel - r.before) >> 2);
+    if (r.inside > 0 && r.filter == LF_UPSCALE) wr_tex_seq_base(start, r.ustep, min(r.kb[1], r.inside >> 2), r.bu[1]);
+    if (r.inside > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.inside / 4) * r.ustep;
+    r.kb[2] = max(0, (tile_rel - r.before - r.inside) >> 2);
+    wr_tex_seq_base(start, r.ustep, r.kb[2], r.bu[2]);
+    wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
+    r.kb[0] = min(r.kb[0], r.before >> 2);
+    r.kb[1] = min(r.kb[1], r.inside >> 2);
+  }
+}
+
 WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sampler_filter, int body_len,
                           const float* u, const float* v, int tile_rel, TexRow& r,
                           int target_fmt = WRCU_FMT_RGBA8) {
@@ -135,52 +189,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
   r.minv = wr_max(wr_linear_quantize(bounds[1], t.h), 0.0f);
   r.maxu = wr_max(wr_linear_quantize(bounds[2], t.w), r.minu);
   r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
-  r.before = 0;
-  r.inside = 0;
-  if (filter != LF_FALLBACK) {
-    // blendTextureLinearDispatch (swgl_ext.h:385-448)
-    float q0 = r.qu[0];
-    float beforeDist = wr_max(0.0f, r.minu) - q0;
-    if (beforeDist > 0) {
-      r.before = min(max((int)ceilf(beforeDist / r.ustep) * 4, 0), body_len);
-      q0 = q0 + (float)(r.before / 4) * r.ustep;
-    }
-    float insideDist = wr_min(r.maxu, (float)((t.w - 4) * 128)) - q0;
-    if (r.ustep > 0.0f && insideDist >= r.ustep) {
-      int inside = body_len - r.before;
-      if (filter == LF_DOWNSCALE) inside = min(((int)(insideDist * (0.5f / 128.0f))) & ~3, inside);
-      else if (filter == LF_UPSCALE) inside = min((int)(insideDist / r.ustep) * 4, inside);
-      else inside = min(((int)(insideDist * (1.0f / 128.0f))) & ~3, inside);
-      r.inside = max(inside, 0);
-    }
-    if (r.inside > 0) {
-      int ix0 = (int)wr_clamp(q0, r.minu, r.maxu), iy0 = (int)wr_clamp(r.qv[0], r.minv, r.maxv);
-      r.uiy0 = iy0;
-      int tx = ix0 >> 7, ty = iy0 >> 7;
-      r.fcx = wr_clamp_coord(tx, t.w - 1);
-      r.fcy = wr_clamp_coord(ty, t.h);
-      r.fnext = (ty >= 0 && ty < t.h - 1) ? 1 : 0;
-      int overread = tx > t.w - 2 ? -1 : 0;
-      r.ffx = (int)(short)((((ix0 & (tx >= 0 ? -1 : 0)) | overread) & 0x7F) - overread);
-      r.ffy = iy0 & 0x7F;
-    }
-  }
-  // running-sum bases per segment
-  {
-    float start[4];
-    for (int j = 0; j < 4; j++) start[j] = r.qu[j];
-    r.kb[0] = max(0, tile_rel >> 2);
-    if (r.before > 0) wr_tex_seq_base(start, r.ustep, min(r.kb[0], r.before >> 2), r.bu[0]);
-    if (r.before > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.before / 4) * r.ustep;
-    r.kb[1] = max(0, (tile_rel - r.before) >> 2);
-    if (r.inside > 0 && r.filter == LF_UPSCALE) wr_tex_seq_base(start, r.ustep, min(r.kb[1], r.inside >> 2), r.bu[1]);
-    if (r.inside > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.inside / 4) * r.ustep;
-    r.kb[2] = max(0, (tile_rel - r.before - r.inside) >> 2);
-    wr_tex_seq_base(start, r.ustep, r.kb[2], r.bu[2]);
-    wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
-    r.kb[0] = min(r.kb[0], r.before >> 2);
-    r.kb[1] = min(r.kb[1], r.inside >> 2);
-  }
+  wr_tex_linear_partition(t, r, body_len, tile_rel);
 }
 
 // blendTextureLinearR8 (swgl_ext.h:634-650): R8 atlas through the fallback

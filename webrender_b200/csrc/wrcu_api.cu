@@ -845,8 +845,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       break;
     case WRCU_KIND_BRUSH_IMAGE:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
-      if (features & (WRCU_FEAT_REPETITION | WRCU_FEAT_DUAL_SOURCE_BLENDING))
-        return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "brush_image REPETITION / DUAL_SOURCE_BLENDING variants not built yet");
+      if (features & WRCU_FEAT_DUAL_SOURCE_BLENDING)
+        return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "brush_image DUAL_SOURCE_BLENDING variant not built (SWGL does not build it either)");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_image without sColor0");
       sa.features = features;
       WR_LAUNCH(wr_setup_brush_image, sblocks, 128, c->stream, sa);
@@ -1034,7 +1034,10 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   switch (kind) {
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
     case WRCU_KIND_QUAD_MASK: LAUNCH_RASTER(QuadMaskShader); break;
-    case WRCU_KIND_BRUSH_IMAGE: LAUNCH_RASTER(ImageShader); break;
+    case WRCU_KIND_BRUSH_IMAGE:
+      if (features & WRCU_FEAT_REPETITION) LAUNCH_RASTER(ImageRepeatShader);
+      else LAUNCH_RASTER(ImageShader);
+      break;
     case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
