@@ -11,6 +11,7 @@
 #include "brush_image.h"
 #include "brush_image_repeat.h"
 #include "ps_text_run.h"
+#include "ps_text_run_gt.h"
 #include "brush_linear_gradient.h"
 #include "cs_clip_box_shadow.h"
 #include "composite.h"
@@ -68,5 +69,9 @@ ProgramLoader load_shader(const char* name) {
     return brush_image_ANTIALIASING_REPETITION_TEXTURE_2D_program::loader;
   if (!strcmp(name, "brush_image ALPHA_PASS,ANTIALIASING,REPETITION,TEXTURE_2D"))
     return brush_image_ALPHA_PASS_ANTIALIASING_REPETITION_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "ps_text_run ALPHA_PASS,GLYPH_TRANSFORM,TEXTURE_2D"))
+    return ps_text_run_ALPHA_PASS_GLYPH_TRANSFORM_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "ps_text_run ALPHA_PASS,DUAL_SOURCE_BLENDING,GLYPH_TRANSFORM,TEXTURE_2D"))
+    return ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_GLYPH_TRANSFORM_TEXTURE_2D_program::loader;
   return nullptr;
 }

@@ -442,15 +442,25 @@ def image_repeat_frame(width=640, height=360, n_opaque=6, n_alpha=14, seed=1, fi
 
 
 def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atlas_size=512, atlas="r8",
-               device_pixel_scale=1.0, fractional=False, color_modes=(0,), with_masks=False):
+               device_pixel_scale=1.0, fractional=False, color_modes=(0,), with_masks=False, glyph_transform=None,
+               clip_runs=False):
     """Config C flavour (wrench/benchmarks/text-rendering.yaml): text runs as
     TextRun(Alpha) glyph instances blitting from a glyph atlas.  The atlas is
     synthetic (seeded coverage cells, w,h in [4,16]) — glyph rasterisation is
-    FreeType's job upstream and out of scope; the blit is what is under test."""
+    FreeType's job upstream and out of scope; the blit is what is under test.
+    glyph_transform = (degrees, sx, sy): runs under a rotated / scaled 2-D transform drawn with
+    BatchFeatures::GLYPH_TRANSFORM (glyphs rasterised in the transformed space, quads trimmed to the
+    glyph rect by gl_ClipDistance); clip_runs gives every other run a local clip rect that cuts
+    through its glyphs (the non-"inside" branch of ps_text_run.glsl:160-167)."""
     from .gpu_types import glyph_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
+    xf = 0
+    if glyph_transform is not None:
+        deg, gsx, gsy = glyph_transform
+        xf = t.add_transform(rotation_matrix(deg, width / (2.0 * device_pixel_scale), height / (2.0 * device_pixel_scale),
+                                             gsx, gsy), axis_aligned=(deg == 0))
     # atlas: grid of 16x16 cells each holding one glyph of random size
     cells = atlas_size // 16
     bpp = 1 if atlas == "r8" else 4
@@ -495,7 +505,10 @@ def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atla
         addr = t.push_gpu_cache(blocks)
         s = 1.0 / device_pixel_scale
         # local_rect.p0 = run origin (added to glyph offsets), local_rect.p1 = text_offset (batch.rs:1109-1340)
-        hdr = t.add_prim_header((base_x * s, base_y * s, 0.0, 0.0), (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic,
+        lclip = (-1e9, -1e9, 1e9, 1e9)
+        if clip_runs and r % 2 == 1:
+            lclip = (base_x * s + 7.3, base_y * s - 9.6, base_x * s + pen * 0.6, base_y * s - 2.2)
+        hdr = t.add_prim_header((base_x * s, base_y * s, 0.0, 0.0), lclip, z, addr, xf, pic,
                                 (65535, 0, 0, 0))
         z += 1
         clip_task = CLIP_TASK_EMPTY
@@ -519,7 +532,8 @@ def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atla
     ops = [Clear(color=(1.0, 1.0, 1.0, 1.0))]
     for mode, lst in sorted(inst_by_mode.items()):
         ops.append(Batch(abi.KIND_TEXT_RUN, np.stack(lst), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
-                         features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("atlas", "", ""),
+                         features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D |
+                         (abi.FEAT_GLYPH_TRANSFORM if glyph_transform is not None else 0), color=("atlas", "", ""),
                          clip_mask="mask" if mask is not None else ""))
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
 
