@@ -61,6 +61,8 @@ CASES = [
     ("ps_quad_radial_gradient", "quad_gradient_frame", dict(kind=23, seed=2, width=480, height=270, fractional=True)),
     ("ps_quad_conic_gradient", "quad_gradient_frame", dict(kind=24, seed=3, width=480, height=270, rotate=-12.0)),
     ("brush_image_repetition", "image_repeat_frame", dict(seed=2, n_opaque=0, width=480, height=270, fractional=True)),
+    ("text_run_glyph_transform", "text_frame", dict(seed=2, width=480, height=270, n_runs=8, glyphs_per_run=16, fractional=True,
+                                                     glyph_transform=(-33.0, 1.3, 0.9), clip_runs=True)),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

@@ -419,3 +419,18 @@ def test_brush_image_repetition_occluded(seed):
     b = render(OracleDevice, f, ["target"])["target"].astype(int)
     d = np.abs(a - b)
     assert d.max() <= 2 and (d > 0).mean() < 5e-3, (int(d.max()), float((d > 0).mean()))
+
+
+GLYPH_TRANSFORMS = {"identity": (0.0, 1.0, 1.0), "scaled": (0.0, 1.25, 0.8), "rotated": (17.0, 1.0, 1.0),
+                    "rotated_scaled": (-33.0, 1.3, 0.9), "quarter_turn": (90.0, 1.0, 1.0)}
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("atlas", ["r8", "rgba"])
+@pytest.mark.parametrize("xf", list(GLYPH_TRANSFORMS))
+def test_text_run_glyph_transform(xf, atlas, seed):
+    """ps_text_run GLYPH_TRANSFORM: quads trimmed per row by gl_ClipDistance; bit-exact."""
+    f = scenes.text_frame(seed=seed, width=480, height=270, n_runs=8, glyphs_per_run=16, atlas=atlas,
+                          color_modes=(0,) if atlas == "r8" else (0, 1, 2, 3), fractional=True,
+                          glyph_transform=GLYPH_TRANSFORMS[xf], clip_runs=True)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), xf)

@@ -270,3 +270,16 @@ def test_brush_image_repetition(seed, variant):
                                   fractional=variant in ("fractional", "scaled"),
                                   device_pixel_scale=1.5 if variant == "scaled" else 1.0)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+GLYPH_TRANSFORMS = {"identity": (0.0, 1.0, 1.0), "scaled": (0.0, 1.25, 0.8), "rotated": (17.0, 1.0, 1.0),
+                    "rotated_scaled": (-33.0, 1.3, 0.9), "quarter_turn": (90.0, 1.0, 1.0)}
+
+
+@pytest.mark.parametrize("atlas", ["r8", "rgba"])
+@pytest.mark.parametrize("xf", list(GLYPH_TRANSFORMS))
+def test_text_run_glyph_transform(xf, atlas):
+    f = scenes.text_frame(seed=1, width=480, height=270, n_runs=8, glyphs_per_run=16, atlas=atlas,
+                          color_modes=(0,) if atlas == "r8" else (0, 1, 2, 3), fractional=True,
+                          glyph_transform=GLYPH_TRANSFORMS[xf], clip_runs=True)
+    assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), xf)

@@ -19,6 +19,7 @@ enum : uint32_t {
   CMD_DROP_SHADOW = 1u << 7, // swgl_blendDropShadow override; colour in CmdCold.i[0..1]
   CMD_CONST_COLOR = 1u << 6, // fragment output is the constant colour in CmdHot.col
   CMD_GENERAL = 1u << 9,    // screen edges not axis-aligned: per-row spans from the edge walk (GenQuad)
+  CMD_CLIP_DIST = 1u << 10,  // gl_ClipDistance in interpolants 2..5 bounds every span (rasterize.h:566-596)
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
 };
 

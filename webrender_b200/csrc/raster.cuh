@@ -158,7 +158,8 @@ WRD bool wr_general_row(const CmdCold& k, const CmdHot& c, int y, GenRow& g, Cmd
 }
 
 template <int N>
-WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step) {
+WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step,
+                       float* li_out = nullptr, float* ri_out = nullptr) {
   if (c.flags & CMD_GENERAL) {
     // left.interp / right.interp of the walk at this row, then the span's start
     // value and per-pixel step (rasterize.h:1003-1017)
@@ -180,6 +181,7 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
       float ri = r0i[i] + (rys - k.gpy[g.rv0]) * sr;
       li = wr_repeat_add(li, sl, y - g.lrow);
       ri = wr_repeat_add(ri, sr, y - g.rrow);
+      if (li_out) { li_out[i] = li; ri_out[i] = ri; }
       float st = (ri - li) * stepScale;
       step[i] = st;
       o[i] = li + st * x0f;
@@ -198,6 +200,7 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
 #pragma unroll
     for (int i = 0; i < N; i++) {
       float li = __ldg(t + 2 * i), ri = __ldg(t + 2 * i + 1);
+      if (li_out) { li_out[i] = li; ri_out[i] = ri; }
       float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
       step[i] = st;
       o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
@@ -221,6 +224,7 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
   for (int i = 0; i < N; i++) {
     float li = __shfl_sync(0xFFFFFFFFu, walked, 2 * i);
     float ri = __shfl_sync(0xFFFFFFFFu, walked, 2 * i + 1);
+    if (li_out) { li_out[i] = li; ri_out[i] = ri; }
     float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
     step[i] = st;
     o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
@@ -234,6 +238,7 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
     float ri = __fadd_rn(k.i_rt[i], __fmul_rn(dy, sr));
     li = wr_repeat_add(li, sl, rows);
     ri = wr_repeat_add(ri, sr, rows);
+    if (li_out) { li_out[i] = li; ri_out[i] = ri; }
     float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
     step[i] = st;
     o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
@@ -256,6 +261,32 @@ WRD void wr_interp_at(const float* o, const float* step, int rel, float* out) {
     v = __fadd_rn(v, __fmul_rn(__fmul_rn(step[i], 4.0f), kf));     // then interp_step * chunks
     out[i] = v;
   }
+}
+
+// clip_distance_range (rasterize.h:566-596) for row y of a command whose vertex stage wrote
+// gl_ClipDistance (interpolants 2..5): narrows the row's span [c.x0, c.x1).  Warp-uniform.
+WRD bool wr_clip_dist_row(const RasterArgs& a, const CmdCold& k, CmdHot& c, int y) {
+  float o[6], st[6], li[6], ri[6];
+  wr_row_interp<6>(a, k, c, y, o, st, li, ri);
+  const bool gen = (c.flags & CMD_GENERAL) != 0;
+  const float lx = gen ? a.gen->lx : k.xl, rx = gen ? a.gen->rx : k.xr;
+  float start_m = -1.0e30f, end_m = 1.0e30f;
+#pragma unroll
+  for (int i = 2; i < 6; i++) {
+    const float lc = li[i], rc = ri[i];
+    const float clipStep = (rc - lc) / (rx - lx);
+    const float clipDist = wr_clamp(lx - lc * (1.0f / clipStep), 0.0f, 1.0e6f);
+    const float s_ = clipStep > 0.0f ? clipDist : (lc < 0.0f ? 1.0e6f : 0.0f);
+    const float e_ = clipStep < 0.0f ? clipDist : (rc >= 0.0f ? 1.0e6f : 0.0f);
+    start_m = wr_max(start_m, s_);
+    end_m = wr_min(end_m, e_);
+  }
+  const int cs = (int)floorf(start_m + 0.5f), ce = (int)floorf(end_m + 0.5f);
+  const int x0 = max((int)c.x0, cs), x1 = min((int)c.x1, ce);
+  if (x1 <= x0) return false;
+  c.x0 = (short)x0;
+  c.x1 = (short)x1;
+  return true;
 }
 
 // Fragment-path interpolants: the reference advances varyings once per 4-pixel
@@ -429,6 +460,7 @@ static void wr_raster(const RasterArgs& a) {
         const CmdHot c0 = c;
         if (!wr_general_row(a.cold[c0.cold], c0, y, g, c)) continue;
       }
+      if ((c.flags & CMD_CLIP_DIST) && !wr_clip_dist_row(ar, ar.cold[c.cold], c, y)) continue;
       const RasterArgs& a = ar;  // shadows: the shaders see the row state
       typename S::Row row;
       for (int tx0 = (c.x0 / WRCU_TILE_W) * WRCU_TILE_W; tx0 < c.x1; tx0 += WRCU_TILE_W) {
@@ -534,6 +566,10 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
         // rotated quad: this row's span comes from the edge walk (warp-uniform)
         const CmdHot c0 = c;
         if (!wr_general_row(a.cold[c0.cold], c0, y, grow, c)) continue;
+        if (c.x1 <= tx0 || c.x0 >= tx0 + WRCU_TILE_W) continue;
+      }
+      if (c.flags & CMD_CLIP_DIST) {
+        if (!wr_clip_dist_row(a, a.cold[c.cold], c, y)) continue;
         if (c.x1 <= tx0 || c.x0 >= tx0 + WRCU_TILE_W) continue;
       }
       if (!loaded) {

@@ -344,23 +344,70 @@ WRD void wr_setup_text_run_one(const SetupArgs& a, int idx) {
   float rgx = floorf(gox * grs + snx) / res_scale, rgy = floorf(goy * grs + sny) / res_scale;
   float ox = gsi * (r1.x + rgx) + tox, oy = gsi * (r1.y + rgy) + toy;
   float gr[4] = {ox, oy, ox + gsi * (r0.z - r0.x), oy + gsi * (r0.w - r0.y)};
+  // WR_FEATURE_GLYPH_TRANSFORM (ps_text_run.glsl:129-167, 222-231): the glyph rect lives in the
+  // transformed (glyph raster) space and the quad is its pre-image
+  const bool glyph_transform = (a.features & WRCU_FEAT_GLYPH_TRANSFORM) != 0;
+  float gt[4] = {1, 0, 0, 1}, gti[4] = {1, 0, 0, 1};  // column major: c0.x, c0.y, c1.x, c1.y
+  float lrect[4] = {gr[0], gr[1], gr[2], gr[3]};
+  bool inside = false;
+  if (glyph_transform) {
+    const float dps = task.device_pixel_scale;
+    const float* m = transform.m;
+    gt[0] = m[0] * dps; gt[1] = m[1] * dps; gt[2] = m[4] * dps; gt[3] = m[5] * dps;
+    const float gtx = m[12] * dps, gty = m[13] * dps;
+    const float det = gt[0] * gt[3] - gt[1] * gt[2];
+    const float idet = (float)(1.0 / (double)det);  // glsl.h:2905-2908: `* (1. / det)`
+    gti[0] = gt[3] * idet; gti[1] = -gt[1] * idet; gti[2] = -gt[2] * idet; gti[3] = gt[0] * idet;
+    const float rgx2 = floorf((gt[0] * gox + gt[2] * goy) + snx), rgy2 = floorf((gt[1] * gox + gt[3] * goy) + sny);
+    const float rtx = floorf(((gt[0] * tox + gt[2] * toy) + gtx) + 0.5f) - gtx;
+    const float rty = floorf(((gt[1] * tox + gt[3] * toy) + gty) + 0.5f) - gty;
+    const float orx = (r1.x + rgx2) + rtx, ory = (r1.y + rgy2) + rty;
+    gr[0] = orx; gr[1] = ory;
+    gr[2] = (orx + r0.z) - r0.x;
+    gr[3] = (ory + r0.w) - r0.y;
+    const float szx = gr[2] - gr[0], szy = gr[3] - gr[1];
+    const float hcx = gr[0] + szx * 0.5f, hcy = gr[1] + szy * 0.5f;
+    const float cx = gti[0] * hcx + gti[2] * hcy, cy = gti[1] * hcx + gti[3] * hcy;
+    const float hsx = szx * 0.5f, hsy = szy * 0.5f;
+    const float rdx = fabsf(gti[0]) * hsx + fabsf(gti[2]) * hsy, rdy = fabsf(gti[1]) * hsx + fabsf(gti[3]) * hsy;
+    lrect[0] = cx - rdx; lrect[1] = cy - rdy; lrect[2] = cx + rdx; lrect[3] = cy + rdy;
+    inside = ph.lcr[0] <= lrect[0] && ph.lcr[1] <= lrect[1] && lrect[2] <= ph.lcr[2] && lrect[3] <= ph.lcr[3];
+  }
   float fox = -task.ox + task.tx0, foy = -task.oy + task.ty0;
   float tw = (float)a.color0.w, th = (float)a.color0.h;
   float st0x = r0.x / tw, st0y = r0.y / th, st1x = r0.z / tw, st1y = r0.w / th;
   const float ax[4] = {0.0f, 1.0f, 1.0f, 0.0f}, ay[4] = {0.0f, 0.0f, 1.0f, 1.0f};
   for (int k = 0; k < 4; k++) {
     float lpx = (gr[2] - gr[0]) * ax[k] + gr[0], lpy = (gr[3] - gr[1]) * ay[k] + gr[1];
+    if (glyph_transform) {
+      if (inside) {
+        const float gx = lpx, gy = lpy;
+        lpx = gti[0] * gx + gti[2] * gy;
+        lpy = gti[1] * gx + gti[3] * gy;
+      } else {
+        lpx = (lrect[2] - lrect[0]) * ax[k] + lrect[0];
+        lpy = (lrect[3] - lrect[1]) * ay[k] + lrect[1];
+      }
+    }
     lpx = wr_clamp(lpx, ph.lcr[0], ph.lcr[2]);
     lpy = wr_clamp(lpy, ph.lcr[1], ph.lcr[3]);
     float4 world = wr_mat_mul(transform.m, make_float4(lpx, lpy, 0.0f, 1.0f));
     float dpx = world.x * task.device_pixel_scale, dpy = world.y * task.device_pixel_scale;
     q.pos[k] = wr_mat_mul(a.tgt.proj, make_float4(dpx + fox * world.w, dpy + foy * world.w, ph.z * world.w, world.w));
     float fx = (lpx - gr[0]) / (gr[2] - gr[0]), fy = (lpy - gr[1]) / (gr[3] - gr[1]);
+    if (glyph_transform) {
+      fx = ((gt[0] * lpx + gt[2] * lpy) - gr[0]) / (gr[2] - gr[0]);
+      fy = ((gt[1] * lpx + gt[3] * lpy) - gr[1]) / (gr[3] - gr[1]);
+      q.interp[k][2] = fx;  // gl_ClipDistance[0..3]
+      q.interp[k][3] = fy;
+      q.interp[k][4] = 1.0f - fx;
+      q.interp[k][5] = 1.0f - fy;
+    }
     q.interp[k][0] = (st1x - st0x) * fx + st0x;
     q.interp[k][1] = (st1y - st0y) * fy + st0y;
   }
-  q.n_interp = 2;
-  q.flags = CMD_TEXTURED;
+  q.n_interp = glyph_transform ? 6 : 2;
+  q.flags = CMD_TEXTURED | (glyph_transform ? CMD_CLIP_DIST : 0u);
   wr_write_clip(T, clip_address, task, q);
   bool dual = (a.features & WRCU_FEAT_DUAL_SOURCE_BLENDING) != 0;
   float vcolor[4] = {1.0f, 1.0f, 1.0f, 1.0f}, swz[3] = {0.0f, 0.0f, 0.0f};

@@ -858,8 +858,6 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       break;
     case WRCU_KIND_TEXT_RUN:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
-      if (features & WRCU_FEAT_GLYPH_TRANSFORM)
-        return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "ps_text_run GLYPH_TRANSFORM variant not built yet");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "ps_text_run without sColor0");
       sa.features = features;
       WR_LAUNCH(wr_setup_text_run, sblocks, 128, c->stream, sa);
