@@ -50,6 +50,18 @@ def _blend_mode(key):
     raise ValueError(f"blend key {key} has no BlendMode equivalent")
 
 
+class NativeFrame:
+    """A wr::Frame built by HostRenderer.build (owns the arrays its pointers refer to)."""
+
+    def __init__(self, hr, ptr, handles, keep):
+        self.hr, self.ptr, self.handles, self.keep = hr, ptr, handles, keep
+
+    def destroy(self):
+        if self.ptr:
+            self.hr.lib.wrh_frame_destroy(self.ptr)
+            self.ptr = None
+
+
 class HostRenderer:
     """wr::Renderer over a CudaDevice's context."""
 
@@ -111,8 +123,9 @@ class HostRenderer:
     def queue_texture_copy(self, src, dst, src_rect, dst_rect):
         self.lib.wrh_renderer_queue_texture_copy(self.r, src, dst, (C.c_int32 * 4)(*src_rect), (C.c_int32 * 4)(*dst_rect))
 
-    def render(self, frame: Frame, handles=None):
-        """Build the wr::Frame for `frame`, render it, return (handles, draw_calls)."""
+    def build(self, frame: Frame, handles=None):
+        """Build the native wr::Frame for `frame` (the frame builder's job upstream).  Returns a
+        NativeFrame to pass to render_native() any number of times; free it with destroy()."""
         dev, L = self.dev, self.lib
         handles = {} if handles is None else handles
         for name, t in frame.textures.items():
@@ -137,14 +150,28 @@ class HostRenderer:
                 p = L.wrh_frame_add_pass(f)
                 for tgt in rpass:
                     self._add_target(f, p, frame, tgt, handles, keep)
-            calls = C.c_uint64(0)
-            err = L.wrh_renderer_render(self.r, f, C.byref(calls))
-            if err != 0:
-                raise WrcuError(err, "RendererError: " + L.wrh_renderer_last_error(self.r).decode())
-        finally:
+        except Exception:
             L.wrh_frame_destroy(f)
-            self._pending_keep = []
-        return handles, calls.value
+            raise
+        return NativeFrame(self, f, handles, keep)
+
+    def render_native(self, nf):
+        """Renderer::render on a built frame: C++ only from here down to the kernels."""
+        calls = C.c_uint64(0)
+        err = self.lib.wrh_renderer_render(self.r, nf.ptr, C.byref(calls))
+        self._pending_keep = []
+        if err != 0:
+            raise WrcuError(err, "RendererError: " + self.lib.wrh_renderer_last_error(self.r).decode())
+        return calls.value
+
+    def render(self, frame: Frame, handles=None):
+        """Build the wr::Frame for `frame`, render it, return (handles, draw_calls)."""
+        nf = self.build(frame, handles)
+        try:
+            calls = self.render_native(nf)
+        finally:
+            nf.destroy()
+        return nf.handles, calls
 
     def _add_blur_scale(self, f, p, target_kind, t, b, handles, ptr, n):
         if b.kind == abi.KIND_SCALE:
