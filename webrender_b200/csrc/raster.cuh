@@ -513,6 +513,7 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
   uint8_t* rowp = a.tgt.color + (size_t)y * a.tgt.color_pitch;
   uint32_t* zrow = a.tgt.depth ? (uint32_t*)((uint8_t*)a.tgt.depth + (size_t)y * a.tgt.depth_pitch) : nullptr;
   const bool use_depth = a.depth_mode != WRCU_DEPTH_OFF && zrow != nullptr;
+  const bool cover_ok = a.blend == WRCU_BLEND_NONE && a.depth_mode == WRCU_DEPTH_OFF;
 
   // Commands are taken in chunks of CHUNK_CMDS.  With bitmask bins the tile's mask words for
   // 8192 commands at a time are staged in shared memory first, so empty chunks are skipped
@@ -541,14 +542,23 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       if (!(mw[0] | mw[1] | mw[2] | mw[3] | mw[4] | mw[5] | mw[6] | mw[7])) continue;  // CTA-uniform
       candidate = candidate && ((mw[warp] >> lane) & 1u);
     }
+    bool cover = false;
     if (candidate) {
       mine = a.hot[base + threadIdx.x];
       keep = mine.x1 > tx0 && mine.x0 < tx0 + WRCU_TILE_W && mine.y1 > ty0 && mine.y0 < ty0 + WRCU_TILE_H &&
              mine.x1 > mine.x0;
+      // Hidden-surface removal inside a batch: with blending and depth off a command that
+      // overwrites every writable pixel of this tile makes all earlier commands of the batch
+      // invisible here, so the pixel loop can start at the last such command.
+      cover = keep && cover_ok &&
+              !(mine.flags & (CMD_MASK | CMD_AA | CMD_GENERAL | CMD_CLIP_DIST | CMD_DROP_SHADOW | CMD_SUBPIXEL_TEXT)) &&
+              mine.x0 <= max(tx0, a.tgt.cx0) && mine.x1 >= min(tx0 + WRCU_TILE_W, a.tgt.cx1) &&
+              mine.y0 <= max(ty0, a.tgt.cy0) && mine.y1 >= min(ty0 + WRCU_TILE_H, a.tgt.cy1);
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
     __syncthreads();  // previous chunk fully consumed
     if (lane == 0) wsum[warp] = __popc(bal);
+    if (threadIdx.x == 0) wsum[WRCU_THREADS / 32] = 0;
     __syncthreads();
     int off = 0, total = 0;
 #pragma unroll
@@ -557,9 +567,12 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       if (w < warp) off += v;
       total += v;
     }
-    if (keep) sh[off + __popc(bal & ((1u << lane) - 1u))] = mine;
+    const int slot = off + __popc(bal & ((1u << lane) - 1u));
+    if (keep) sh[slot] = mine;
+    if (cover) atomicMax(&wsum[WRCU_THREADS / 32], slot);
     __syncthreads();
-    for (int i = 0; i < total; i++) {
+    const int first_cmd = wsum[WRCU_THREADS / 32];
+    for (int i = first_cmd; i < total; i++) {
       CmdHot c = sh[i];
       if (!row_ok || y < c.y0 || y >= c.y1) continue;          // warp-uniform
       if (c.flags & CMD_GENERAL) {
@@ -615,7 +628,7 @@ template <class S, int FMT>
 __global__ void __launch_bounds__(WRCU_THREADS)
 wr_raster(RasterArgs a) {
   __shared__ CmdHot sh[CHUNK_CMDS];
-  __shared__ int wsum[WRCU_THREADS / 32];
+  __shared__ int wsum[WRCU_THREADS / 32 + 1];  // per-warp survivor counts + the last covering command
   const BatchInfo bi = *a.info;
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
   const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
