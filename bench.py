@@ -463,8 +463,15 @@ def main():
         draw_step()
         kernel_ms.append(dev.timer_end())
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     st = dev.stats()
+    if rank == 0 and not sampler.lines:
+        # a short timed region can end before nvidia-smi's first 100 ms sample: keep the same load
+        # running (untimed) until one arrives, so the clocks line still describes the GPU under this work
+        t_lim = time.perf_counter() + 2.0
+        while not sampler.lines and time.perf_counter() < t_lim:
+            draw_step()
+            dev.finish()
+    clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(kernel_ms))
 
     # ---- the dominant kernel alone: CUDA events around the draw_batch region ------
