@@ -434,3 +434,9 @@ def test_text_run_glyph_transform(xf, atlas, seed):
                           color_modes=(0,) if atlas == "r8" else (0, 1, 2, 3), fractional=True,
                           glyph_transform=GLYPH_TRANSFORMS[xf], clip_runs=True)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), xf)
+
+
+def test_binned_batch_two_list_passes():
+    """9600 glyphs in one batch: the per-tile command list is built in two passes of 8192 commands."""
+    f = scenes.text_frame(seed=4, width=1920, height=1080, n_runs=120, glyphs_per_run=80, atlas_size=1024)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))

@@ -501,7 +501,7 @@ static void wr_raster_solid_premult(const RasterArgs& a) {
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
 // S::source returns the fragment stage's output for one pixel as 16-bit lanes.
 template <class S, int FMT>
-WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, uint32_t* msk) {
+WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, unsigned short* list) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
@@ -519,32 +519,56 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
   // 8192 commands at a time are staged in shared memory first, so empty chunks are skipped
   // without touching global memory or a barrier.
   for (int sbase = 0; sbase < a.n; sbase += WRCU_THREADS * 32) {
-  if (a.tile_mask) {
-    __syncthreads();  // previous super-chunk's readers are done with msk
-    const int w = (sbase >> 5) + (int)threadIdx.x;
-    msk[threadIdx.x] = w < a.bin_words
-        ? (__ldg(a.tile_mask + (size_t)((ty0 / WRCU_TILE_H) * a.bin_tiles_x + tx0 / WRCU_TILE_W) * a.bin_words + w) |
-           __ldg(a.wide_mask + w))
+  const int send = min(a.n, sbase + WRCU_THREADS * 32);
+  // With bitmask bins the set bits of the tile's mask words (one word per thread, 8192 commands per
+  // pass) are expanded into an ordered index list in shared memory; the chunk loop below then runs
+  // over that list, so a sparse batch (text: a few dozen of 6000 glyphs per tile) costs one chunk
+  // instead of a scan over every 256-command chunk.
+  int n_items = send - sbase;
+  const bool listed = a.tile_mask != nullptr;
+  if (listed) {
+    const int wi = (sbase >> 5) + (int)threadIdx.x;
+    uint32_t word = wi < a.bin_words
+        ? (__ldg(a.tile_mask + (size_t)((ty0 / WRCU_TILE_H) * a.bin_tiles_x + tx0 / WRCU_TILE_W) * a.bin_words + wi) |
+           __ldg(a.wide_mask + wi))
         : 0u;
+    const int cnt = __popc(word);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    __syncthreads();  // previous pass / tile done with wsum and the list
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int pos = incl - cnt;
+    n_items = 0;
+#pragma unroll
+    for (int w = 0; w < WRCU_THREADS / 32; w++) {
+      const int v = wsum[w];
+      if (w < warp) pos += v;
+      n_items += v;
+    }
+    while (word) {
+      const int b = __ffs((int)word) - 1;
+      word &= word - 1;
+      list[pos++] = (unsigned short)(threadIdx.x * 32 + b);
+    }
     __syncthreads();
   }
-  const int send = min(a.n, sbase + WRCU_THREADS * 32);
-  for (int base = sbase; base < send; base += CHUNK_CMDS) {
+  for (int ib = 0; ib < n_items; ib += CHUNK_CMDS) {
     // Binning: each thread tests one command of the chunk against this tile; the
     // survivors' indices are compacted in batch order (ballot + prefix sum), so
     // the pixel loop only visits commands that touch the tile.
-    const int m = min(CHUNK_CMDS, a.n - base);
+    const int m = min(CHUNK_CMDS, n_items - ib);
     int keep = 0;
     CmdHot mine;
-    bool candidate = (int)threadIdx.x < m;
-    if (a.tile_mask) {
-      const uint32_t* mw = msk + ((base - sbase) >> 5);
-      if (!(mw[0] | mw[1] | mw[2] | mw[3] | mw[4] | mw[5] | mw[6] | mw[7])) continue;  // CTA-uniform
-      candidate = candidate && ((mw[warp] >> lane) & 1u);
-    }
+    const bool candidate = (int)threadIdx.x < m;
+    const int cidx = candidate ? (listed ? sbase + (int)list[ib + threadIdx.x] : sbase + ib + (int)threadIdx.x) : 0;
     bool cover = false;
     if (candidate) {
-      mine = a.hot[base + threadIdx.x];
+      mine = a.hot[cidx];
       keep = mine.x1 > tx0 && mine.x0 < tx0 + WRCU_TILE_W && mine.y1 > ty0 && mine.y0 < ty0 + WRCU_TILE_H &&
              mine.x1 > mine.x0;
       // Hidden-surface removal inside a batch: with blending and depth off a command that
@@ -638,13 +662,13 @@ wr_raster(RasterArgs a) {
   if (nx <= 0 || n_tiles <= 0) return;
   // tiles are handed out dynamically: their cost varies with what lands on them
   __shared__ int s_tile;
-  __shared__ uint32_t msk[WRCU_THREADS];
+  __shared__ unsigned short list[WRCU_THREADS * 32];  // command indices of the tile's set mask bits, in order
   for (;;) {
     if (threadIdx.x == 0) s_tile = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) break;
-    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, msk);
+    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list);
     __syncthreads();
   }
 }
