@@ -648,8 +648,12 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
 // Persistent CTAs stride over the tiles of the batch's bounding box (known only
 // on the device), so a batch that touches a small part of a large target costs
 // a small launch, and a full-target batch fills the chip evenly.
+// Resident CTAs per SM the kernel is compiled for (register budget = 65536 / (256 * v)): shaders whose
+// work is latency-bound (many small commands) specialise this to 3.
+template <class S> struct WrMinCtas { enum { v = 2 }; };
+
 template <class S, int FMT>
-__global__ void __launch_bounds__(WRCU_THREADS)
+__global__ void __launch_bounds__(WRCU_THREADS, WrMinCtas<S>::v)
 wr_raster(RasterArgs a) {
   __shared__ CmdHot sh[CHUNK_CMDS];
   __shared__ int wsum[WRCU_THREADS / 32 + 1];  // per-warp survivor counts + the last covering command

@@ -111,3 +111,7 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
   }
 }
 WR_SETUP_KERNEL(wr_setup_composite)
+
+#ifndef WRCU_HOSTEMU
+template <> struct WrMinCtas<CompositeShader> { enum { v = 3 }; };
+#endif

@@ -53,3 +53,7 @@ struct TextShader {
     return o;
   }
 };
+
+#ifndef WRCU_HOSTEMU
+template <> struct WrMinCtas<TextShader> { enum { v = 3 }; };
+#endif
