@@ -63,6 +63,8 @@ CASES = [
     ("brush_image_repetition", "image_repeat_frame", dict(seed=2, n_opaque=0, width=480, height=270, fractional=True)),
     ("text_run_glyph_transform", "text_frame", dict(seed=2, width=480, height=270, n_runs=8, glyphs_per_run=16, fractional=True,
                                                      glyph_transform=(-33.0, 1.3, 0.9), clip_runs=True)),
+    ("reftest_premultiplied_radial", "reftest_cached_gradient_frame", dict(which="premultiplied-radial")),
+    ("reftest_conic_center", "reftest_cached_gradient_frame", dict(which="conic-center")),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

@@ -109,3 +109,25 @@ def test_gradient_reftests_against_reference_png(which, png, max_diff, max_px):
     d = np.abs(out[:h, :w] - ref[:h, :w]).max(axis=2)
     assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))
     assert (ref[h:, :, :3] == 255).all() and (ref[:, w:, :3] == 255).all()
+
+
+@pytest.mark.parametrize("which,png,max_diff,max_px", [
+    ("premultiplied-radial", "gradient/premultiplied-radial.png", 0, 0),   # == (exact); measured 0
+    ("premultiplied-conic", "gradient/premultiplied-conic.png", 1, 250),   # fuzzy(1,250); measured 1 on 4 px
+    ("conic-center", "gradient/conic-center.png", 0, 0),                   # == (exact); measured 0
+])
+def test_cached_gradient_reftests_against_reference_png(which, png, max_diff, max_px):
+    """wrench/reftests/gradient/{premultiplied-radial,premultiplied-conic,conic-center}.yaml drawn the way
+    the frame builder draws them — a cached cs_radial_gradient / cs_conic_gradient render task in a
+    texture-cache target, composited 1:1 with Brush(Image) — against the reference's OWN PNGs under each
+    reftest's fuzz.  Pins the texture-cache-target gradient programs and the image composite."""
+    path = "/root/reference/wrench/reftests/" + png
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    out = render(OracleDevice, scenes.reftest_cached_gradient_frame(which), ["target"])["target"]
+    out = out.reshape(300, 300, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref[:300, :300]).max(axis=2)
+    assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))
+    assert (ref[300:, :, :3] == 255).all() and (ref[:, 300:, :3] == 255).all()

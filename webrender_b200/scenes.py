@@ -926,6 +926,51 @@ def quad_gradient_frame(kind, width=640, height=360, n_quads=8, seed=1, fraction
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
 
 
+def reftest_cached_gradient_frame(which="premultiplied-radial"):
+    """wrench/reftests/gradient/premultiplied-radial.yaml, premultiplied-conic.yaml and
+    conic-center.yaml the way the frame builder draws them (prim_store/gradient/{radial,conic}.rs):
+    pass 0 renders the gradient as a cached 200x200 render task (cs_radial_gradient /
+    cs_conic_gradient, task size = stretch size, scale 1) into a texture-cache target; pass 1
+    composites the task 1:1 with Brush(Image) (premultiplied-alpha blend, white colour) onto
+    the white 300x300 page at (50,50)."""
+    from . import gpu_types as G
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    W = H = 300
+    red, green, blue, black = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0), (0.0, 0.0, 0.0, 1.0)
+    clear = (0.0, 0.0, 0.0, 0.0)
+    t = FrameTables()
+    task_rect = (0.0, 0.0, 200.0, 200.0)
+    if which == "conic-center":
+        stops = [(0.0, red), (0.25, red), (0.25, green), (0.5, green), (0.5, blue), (0.75, blue), (0.75, black), (1.0, black)]
+        center = (50.0, 50.0)
+    else:
+        stops = [(0.0, red), (0.5, clear), (1.0, green)]
+        center = (100.0, 100.0)
+    lut = t.push_gpu_buffer_f(list(G.build_gradient_table(stops)))
+    if which == "premultiplied-radial":
+        kind = abi.KIND_RADIAL_GRADIENT
+        inst = G.radial_gradient_instance(task_rect, center, (1.0, 1.0), 0.0, 100.0, 1.0, 0, lut)
+    else:
+        kind = abi.KIND_CONIC_GRADIENT
+        inst = G.conic_gradient_instance(task_rect, center, (1.0, 1.0), 0.0, 1.0, 0.0, 0, lut)
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    addr = t.push_gpu_cache([(1.0, 1.0, 1.0, 1.0), (1.0, 1.0, 1.0, 1.0), (200.0, 200.0, 0.0, 0.0)])
+    res = t.push_gpu_cache([task_rect, (0.0, 0.0, 0.0, 0.0)])
+    hdr = t.add_prim_header((50.0, 50.0, 250.0, 250.0), (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, pic,
+                            (4 | (1 << 16), 0, 65535, 0))
+    img = np.stack([brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, res)])
+    textures = {"cache": TextureDesc(abi.FMT_RGBA8, 256, 256, filter=abi.LINEAR),
+                "target": TextureDesc(abi.FMT_RGBA8, W, H)}
+    opaque = which == "conic-center"
+    p0 = Target("cache", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)), Batch(kind, np.stack([inst]), blend=abi.BLEND_NONE)])
+    p1 = Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                               Batch(abi.KIND_BRUSH_IMAGE, img,
+                                     blend=abi.BLEND_NONE if opaque else abi.BLEND_PREMULTIPLIED_ALPHA,
+                                     features=abi.FEAT_TEXTURE_2D | (0 if opaque else abi.FEAT_ALPHA_PASS),
+                                     color=("cache", "", ""))])
+    return Frame(t.arrays(), textures, [[p0], [p1]])
+
+
 def shadow_mask_texture(size=256, seed=5):
     """A seeded stand-in for the blurred box-shadow masks cs_blur produces
     (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
