@@ -54,7 +54,9 @@ typedef enum wrcu_format {
   WRCU_FMT_R8 = 2,      /* 1 B/px                                         */
   WRCU_FMT_RGBAF32 = 3, /* 16 B/texel (data textures, GPU cache)          */
   WRCU_FMT_RGBAI32 = 4, /* 16 B/texel                                     */
-  WRCU_FMT_DEPTH24 = 5  /* 4 B/px, 24-bit depth (rasterize.h:37)          */
+  WRCU_FMT_DEPTH24 = 5, /* 4 B/px, 24-bit depth (rasterize.h:37)          */
+  WRCU_FMT_RG8 = 6      /* 2 B/px, sample-only: the CbCr plane of NV12 video
+                           surfaces (gl.cc:247, TextureFormat::RG8)          */
 } wrcu_format;
 
 typedef enum wrcu_filter { WRCU_NEAREST = 0, WRCU_LINEAR = 1 } wrcu_filter;
@@ -73,7 +75,7 @@ typedef enum wrcu_kind {
   WRCU_KIND_TEXT_RUN = 9,              /* ps_text_run                      */
   WRCU_KIND_CLIP_RECTANGLE = 10,       /* cs_clip_rectangle [FAST_PATH]    */
   WRCU_KIND_CLIP_BOX_SHADOW = 11,      /* cs_clip_box_shadow               */
-  WRCU_KIND_COMPOSITE = 12,            /* composite [FAST_PATH]            */
+  WRCU_KIND_COMPOSITE = 12,            /* composite [FAST_PATH | YUV]      */
   WRCU_KIND_CLEAR = 13,                /* ps_clear                         */
   WRCU_KIND_BLUR = 14,                 /* cs_blur      */
   WRCU_KIND_SCALE = 15,                /* cs_scale                         */
@@ -100,7 +102,9 @@ enum {
   WRCU_FEAT_GLYPH_TRANSFORM = 1u << 6,
   WRCU_FEAT_TEXTURE_2D = 1u << 7,
   WRCU_FEAT_ALPHA_TARGET = 1u << 8, /* cs_blur into an R8 target    */
-  WRCU_FEAT_COLOR_TARGET = 1u << 9  /* cs_blur into an RGBA8 target */
+  WRCU_FEAT_COLOR_TARGET = 1u << 9, /* cs_blur into an RGBA8 target */
+  WRCU_FEAT_YUV = 1u << 10          /* composite: YUV video surfaces (composite.glsl:14-33),
+                                       8-bit PLANAR / NV12 / INTERLEAVED planes    */
 };
 
 /* Blend keys: exactly the set the reference's blend stage implements

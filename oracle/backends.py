@@ -63,7 +63,7 @@ class OracleDevice(DeviceBase):
 
 # ---- GL constants (swgl/src/gl_defs.h) ---------------------------------------
 GL = dict(
-    RGBA32F=0x8814, RGBA8=0x8058, R8=0x8229, RGBA32I=0x8D82, DEPTH_COMPONENT24=0x81A6,
+    RGBA32F=0x8814, RGBA8=0x8058, R8=0x8229, RG8=0x822B, RG=0x8227, RGBA32I=0x8D82, DEPTH_COMPONENT24=0x81A6,
     UNSIGNED_BYTE=0x1401, UNSIGNED_SHORT=0x1403, INT=0x1404, FLOAT=0x1406,
     RED=0x1903, RGBA=0x1908, RGBA_INTEGER=0x8D99, BGRA=0x80E1,
     ARRAY_BUFFER=0x8892, ELEMENT_ARRAY_BUFFER=0x8893,
@@ -211,9 +211,10 @@ class SwglDevice:
 
     # -- textures --------------------------------------------------------------
     _IFMT = {abi.FMT_RGBA8: _G["RGBA8"], abi.FMT_R8: _G["R8"], abi.FMT_RGBAF32: _G["RGBA32F"],
-             abi.FMT_RGBAI32: _G["RGBA32I"], abi.FMT_DEPTH24: _G["DEPTH_COMPONENT24"]}
+             abi.FMT_RGBAI32: _G["RGBA32I"], abi.FMT_DEPTH24: _G["DEPTH_COMPONENT24"], abi.FMT_RG8: _G["RG8"]}
     _XFER = {abi.FMT_RGBA8: (_G["BGRA"], _G["UNSIGNED_BYTE"]), abi.FMT_R8: (_G["RED"], _G["UNSIGNED_BYTE"]),
-             abi.FMT_RGBAF32: (_G["RGBA"], _G["FLOAT"]), abi.FMT_RGBAI32: (_G["RGBA_INTEGER"], _G["INT"])}
+             abi.FMT_RGBAF32: (_G["RGBA"], _G["FLOAT"]), abi.FMT_RGBAI32: (_G["RGBA_INTEGER"], _G["INT"]),
+             abi.FMT_RG8: (_G["RG"], _G["UNSIGNED_BYTE"])}
 
     def texture_create(self, fmt, w, h):
         g = self.gl

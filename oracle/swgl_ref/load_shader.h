@@ -15,6 +15,7 @@
 #include "brush_linear_gradient.h"
 #include "cs_clip_box_shadow.h"
 #include "composite.h"
+#include "composite_yuv.h"
 #include "brush_opacity.h"
 #include "ps_clear.h"
 #include "brush_blend.h"
@@ -45,6 +46,7 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "cs_clip_box_shadow TEXTURE_2D")) return cs_clip_box_shadow_TEXTURE_2D_program::loader;
   if (!strcmp(name, "composite TEXTURE_2D")) return composite_TEXTURE_2D_program::loader;
   if (!strcmp(name, "composite FAST_PATH,TEXTURE_2D")) return composite_FAST_PATH_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "composite TEXTURE_2D,YUV")) return composite_TEXTURE_2D_YUV_program::loader;
   if (!strcmp(name, "brush_opacity")) return brush_opacity_program::loader;
   if (!strcmp(name, "brush_opacity ALPHA_PASS")) return brush_opacity_ALPHA_PASS_program::loader;
   if (!strcmp(name, "brush_opacity ALPHA_PASS,ANTIALIASING")) return brush_opacity_ALPHA_PASS_ANTIALIASING_program::loader;

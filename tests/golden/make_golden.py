@@ -65,6 +65,10 @@ CASES = [
                                                      glyph_transform=(-33.0, 1.3, 0.9), clip_runs=True)),
     ("reftest_premultiplied_radial", "reftest_cached_gradient_frame", dict(which="premultiplied-radial")),
     ("reftest_conic_center", "reftest_cached_gradient_frame", dict(which="conic-center")),
+    ("composite_yuv_planar_rec709", "yuv_composite_frame", dict(fmt="planar", color_space=2, seed=1)),
+    ("composite_yuv_nv12_rec601_full", "yuv_composite_frame", dict(fmt="nv12", color_space=1, seed=2, fractional=True)),
+    ("composite_yuv_interleaved_rec2020", "yuv_composite_frame", dict(fmt="interleaved", color_space=4, seed=3)),
+    ("composite_yuv_planar_nearest_gbr", "yuv_composite_frame", dict(fmt="planar", color_space=6, seed=4, linear=False)),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

@@ -224,6 +224,31 @@ def test_composite_4k():
     assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]))
 
 
+
+YUV_FORMATS = ["planar", "nv12", "interleaved"]
+YUV_VARIANTS = ["opaque", "blend", "fractional", "nearest"]
+
+
+def _yuv_frame(fmt, color_space, variant):
+    return scenes.yuv_composite_frame(fmt, color_space, seed=1 + color_space, linear=variant != "nearest",
+                                      opaque=variant != "blend", fractional=variant == "fractional")
+
+
+@pytest.mark.parametrize("color_space", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("fmt", YUV_FORMATS)
+def test_composite_yuv_color_spaces(fmt, color_space):
+    """composite with WR_FEATURE_YUV (composite.glsl:83-130, 163-176, 197-214; yuv.glsl): 8-bit PLANAR / NV12 /\n    INTERLEAVED video surfaces in every YuvRangedColorSpace; span body through the fixed-point YUVMatrix\n    (composite.h:636-779), tails and nearest-filtered planes through sample_yuv's float matrix."""
+    f = _yuv_frame(fmt, color_space, "opaque")
+    assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), fmt)
+
+
+@pytest.mark.parametrize("variant", YUV_VARIANTS[1:])
+@pytest.mark.parametrize("fmt", YUV_FORMATS)
+def test_composite_yuv_variants(fmt, variant):
+    f = _yuv_frame(fmt, 2 if variant != "fractional" else 5, variant)
+    assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)
+
+
 OPACITY_VARIANTS = ["scaled", "fractional", "one_to_one", "nearest"]
 
 

@@ -65,6 +65,8 @@ CASES = [
     ("gradients", lambda: scenes.gradient_frame(seed=1, blend=abi.BLEND_PREMULTIPLIED_ALPHA), None),
     ("box_shadows", lambda: scenes.box_shadow_frame(seed=1), None),
     ("composite", lambda: scenes.composite_frame(seed=1), ["fb"]),
+    ("composite_yuv_nv12", lambda: scenes.yuv_composite_frame("nv12", 3, seed=2), ["fb"]),
+    ("composite_yuv_planar", lambda: scenes.yuv_composite_frame("planar", 4, seed=3, fractional=True), ["fb"]),
     ("blur", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
     ("texture_cache_target", lambda: scenes.texture_cache_frame(seed=1), None),
     ("quad_radial", lambda: scenes.quad_gradient_frame(abi.KIND_QUAD_RADIAL_GRADIENT, seed=2), None),

@@ -20,7 +20,7 @@ SYMBOLS = ["wrh_renderer_create", "wrh_renderer_destroy", "wrh_frame_create", "w
            "wrh_pass_add_picture_cache_target", "wrh_pass_add_color_target", "wrh_pass_add_alpha_target",
            "wrh_pass_add_texture_cache_target", "wrh_texture_cache_target_add_clear", "wrh_texture_cache_target_add_tasks",
            "wrh_picture_target_add_batch", "wrh_color_target_add_batch", "wrh_alpha_target_add_clear",
-           "wrh_alpha_target_add_clips", "wrh_target_add_blur_or_scale", "wrh_frame_set_framebuffer", "wrh_frame_add_composite_tile",
+           "wrh_alpha_target_add_clips", "wrh_target_add_blur_or_scale", "wrh_frame_set_framebuffer", "wrh_frame_add_composite_tile", "wrh_frame_add_composite_yuv_tile",
            "wrh_renderer_render", "wrh_renderer_last_error",
            "wrh_renderer_queue_gpu_cache_updates", "wrh_renderer_queue_texture_update", "wrh_renderer_queue_texture_copy"]
 
@@ -42,6 +42,8 @@ CASES = [
     ("text", lambda: scenes.text_frame(seed=2, width=480, height=270, n_runs=8, glyphs_per_run=20), ["target"]),
     ("gradients", lambda: scenes.gradient_frame(seed=1, blend=abi.BLEND_PREMULTIPLIED_ALPHA), ["target"]),
     ("composite", lambda: scenes.composite_frame(seed=1), ["fb"]),
+    ("composite_yuv_planar", lambda: scenes.yuv_composite_frame("planar", 2, seed=1), ["fb"]),
+    ("composite_yuv_nv12", lambda: scenes.yuv_composite_frame("nv12", 0, seed=2, opaque=False), ["fb"]),
     ("blur_a8", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
     ("blur_rgba8", lambda: scenes.blur_frame(seed=2, color=True), ["mid", "target"]),
     ("scale", lambda: scenes.scale_frame(seed=1), ["target"]),

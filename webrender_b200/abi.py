@@ -11,8 +11,8 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_OOM, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
 
 # wrcu_format
-FMT_RGBA8, FMT_R8, FMT_RGBAF32, FMT_RGBAI32, FMT_DEPTH24 = 1, 2, 3, 4, 5
-FMT_BPP = {FMT_RGBA8: 4, FMT_R8: 1, FMT_RGBAF32: 16, FMT_RGBAI32: 16, FMT_DEPTH24: 4}
+FMT_RGBA8, FMT_R8, FMT_RGBAF32, FMT_RGBAI32, FMT_DEPTH24, FMT_RG8 = 1, 2, 3, 4, 5, 6
+FMT_BPP = {FMT_RGBA8: 4, FMT_R8: 1, FMT_RGBAF32: 16, FMT_RGBAI32: 16, FMT_DEPTH24: 4, FMT_RG8: 2}
 
 NEAREST, LINEAR = 0, 1
 
@@ -62,6 +62,7 @@ FEAT_GLYPH_TRANSFORM = 1 << 6
 FEAT_TEXTURE_2D = 1 << 7
 FEAT_ALPHA_TARGET = 1 << 8
 FEAT_COLOR_TARGET = 1 << 9
+FEAT_YUV = 1 << 10
 FEATURE_NAMES = [
     (FEAT_ADVANCED_BLEND, "ADVANCED_BLEND"),
     (FEAT_ALPHA_PASS, "ALPHA_PASS"),
@@ -73,6 +74,7 @@ FEATURE_NAMES = [
     (FEAT_GLYPH_TRANSFORM, "GLYPH_TRANSFORM"),
     (FEAT_REPETITION, "REPETITION"),
     (FEAT_TEXTURE_2D, "TEXTURE_2D"),
+    (FEAT_YUV, "YUV"),
 ]
 
 

@@ -32,7 +32,8 @@ struct RasterArgs {
   int depth_mode;   // wrcu_depth
   Px blend_color;   // glBlendColor in lane order
   TexView color0;   // sColor0
-  TexView color1;   // sColor1 (brush_mix_blend source)
+  TexView color1;   // sColor1 (brush_mix_blend source, YUV chroma plane)
+  TexView color2;   // sColor2 (third YUV plane)
   int fast_eligible;  // host-side part of the solid-premult fast-path test
   const float4* gbuf_f;  // gpu_buffer_f (gradient LUTs)
   int n_gbuf_f;

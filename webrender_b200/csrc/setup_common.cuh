@@ -37,6 +37,7 @@ struct SetupArgs {
   int row_cap;
   TexView color0;
   TexView color1;
+  TexView color2;
   TexView clip_mask;
 };
 

@@ -14,6 +14,7 @@
 #include "shader_gradient.cuh"
 #include "shader_box_shadow.cuh"
 #include "shader_composite.cuh"
+#include "shader_composite_yuv.cuh"
 #include "shader_opacity.cuh"
 #include "shader_blend.cuh"
 #include "shader_mix_blend.cuh"
@@ -46,6 +47,7 @@ static int fmt_bpp(int fmt) {
     case WRCU_FMT_RGBAF32: return 16;
     case WRCU_FMT_RGBAI32: return 16;
     case WRCU_FMT_DEPTH24: return 4;
+    case WRCU_FMT_RG8: return 2;
   }
   return 0;
 }
@@ -809,6 +811,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
+  sa.color2 = tex_view(c, st->color[2]);
   // Bitmask bins for batches with many instances: the per-tile command scan of the raster
   // kernel costs tiles x n hot records of L2 traffic; with bins it reads n/32 words per tile.
   {
@@ -942,7 +945,8 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
       if (stride < 120) return wrcu_fail(c, WRCU_ERR_INVALID, "CompositeInstance stride < 120");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "composite without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_composite, sblocks, 128, c->stream, sa);
+      if (features & WRCU_FEAT_YUV) WR_LAUNCH(wr_setup_composite_yuv, sblocks, 128, c->stream, sa);
+      else WR_LAUNCH(wr_setup_composite, sblocks, 128, c->stream, sa);
       break;
     case WRCU_KIND_CLIP_BOX_SHADOW:
       if (stride < 84) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceBoxShadow stride < 84");
@@ -970,6 +974,7 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
                       host_round_pixel(st->blend_color[0]) & 0xFFFF, host_round_pixel(st->blend_color[3]) & 0xFFFF};
   ra.color0 = sa.color0;
   ra.color1 = sa.color1;
+  ra.color2 = sa.color2;
   ra.row_tab = c->row_tab;
   ra.gbuf_f = c->tables.gpu_buffer_f;
   ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
@@ -1039,7 +1044,10 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
     case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
-    case WRCU_KIND_COMPOSITE: LAUNCH_RASTER(CompositeShader); break;
+    case WRCU_KIND_COMPOSITE:
+      if (features & WRCU_FEAT_YUV) LAUNCH_RASTER(CompositeYuvShader);
+      else LAUNCH_RASTER(CompositeShader);
+      break;
     case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
     case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
     case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER(MixBlendShader); break;
@@ -1082,7 +1090,8 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"ANTIALIASING", WRCU_FEAT_ANTIALIASING}, {"REPETITION", WRCU_FEAT_REPETITION},
       {"DUAL_SOURCE_BLENDING", WRCU_FEAT_DUAL_SOURCE_BLENDING}, {"ADVANCED_BLEND", WRCU_FEAT_ADVANCED_BLEND},
       {"GLYPH_TRANSFORM", WRCU_FEAT_GLYPH_TRANSFORM}, {"TEXTURE_2D", WRCU_FEAT_TEXTURE_2D},
-      {"ALPHA_TARGET", WRCU_FEAT_ALPHA_TARGET}, {"COLOR_TARGET", WRCU_FEAT_COLOR_TARGET}};
+      {"ALPHA_TARGET", WRCU_FEAT_ALPHA_TARGET}, {"COLOR_TARGET", WRCU_FEAT_COLOR_TARGET},
+      {"YUV", WRCU_FEAT_YUV}};
   const char* sp = strchr(key, ' ');
   size_t nlen = sp ? (size_t)(sp - key) : strlen(key);
   *kind = 0;
@@ -1100,7 +1109,7 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
         *features |= f.bit;
         found = true;
       }
-    if (!found) return WRCU_ERR_UNSUPPORTED;  // TEXTURE_RECT, YUV, DEBUG_OVERDRAW, ...
+    if (!found) return WRCU_ERR_UNSUPPORTED;  // TEXTURE_RECT, TEXTURE_EXTERNAL, DEBUG_OVERDRAW, ...
     p = comma ? comma + 1 : nullptr;
   }
   return WRCU_OK;

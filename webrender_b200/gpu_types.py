@@ -276,6 +276,26 @@ def composite_instance(rect, clip_rect, color=(1.0, 1.0, 1.0, 1.0), uv_rect=(0.0
     return buf.view(np.uint8).copy()
 
 
+# YuvFormat / YuvRangedColorSpace (webrender_api/src/image.rs; yuv.glsl:7-11, 27-34)
+YUV_FORMAT_NV12, YUV_FORMAT_P010, YUV_FORMAT_NV16, YUV_FORMAT_PLANAR, YUV_FORMAT_INTERLEAVED = 0, 1, 2, 3, 4
+(YUV_REC601_NARROW, YUV_REC601_FULL, YUV_REC709_NARROW, YUV_REC709_FULL, YUV_REC2020_NARROW, YUV_REC2020_FULL,
+ YUV_GBR_IDENTITY) = range(7)
+
+
+def composite_yuv_instance(rect, clip_rect, color_space, yuv_format, bit_depth, uv_rects, flip=(False, False)):
+    """CompositeInstance::new_yuv (gpu_types.rs:358-378): white colour, params
+    [_, colour space, format, channel bit depth], one texel-space uv rect per plane."""
+    buf = np.zeros(30, dtype=np.float32)
+    buf[0:4] = rect
+    buf[4:8] = clip_rect
+    buf[8:12] = (1.0, 1.0, 1.0, 1.0)
+    buf[13], buf[14], buf[15] = float(color_space), float(yuv_format), float(bit_depth)
+    for i in range(3):
+        buf[16 + 4 * i:20 + 4 * i] = uv_rects[i]
+    buf[28:30] = (float(flip[0]), float(flip[1]))
+    return buf.view(np.uint8).copy()
+
+
 def blur_instance(task_address, src_task_address, direction, std_deviation, blur_region):
     """BlurInstance, 24 bytes (gpu_types.rs:112-118): direction 0 = horizontal, 1 = vertical."""
     buf = np.zeros(6, dtype=np.float32)

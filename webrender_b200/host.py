@@ -96,6 +96,7 @@ class HostRenderer:
         L.wrh_target_add_blur_or_scale.argtypes = [vp, i32, i32, i32, i32, u32, vp, i32]
         L.wrh_frame_set_framebuffer.argtypes = [vp, u32, i32, i32, C.POINTER(C.c_float)]
         L.wrh_frame_add_composite_tile.argtypes = [vp, i32, u32, i32, C.POINTER(C.c_float)]
+        L.wrh_frame_add_composite_yuv_tile.argtypes = [vp, i32, C.POINTER(u32), C.POINTER(C.c_float)]
         L.wrh_renderer_render.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
         L.wrh_renderer_last_error.restype = C.c_char_p
         L.wrh_renderer_last_error.argtypes = [vp]
@@ -242,6 +243,10 @@ class HostRenderer:
                 a = b.instance_bytes()
                 for row in a:
                     v = np.ascontiguousarray(row).view(np.float32)
+                    if b.features & abi.FEAT_YUV:
+                        planes = (C.c_uint32 * 3)(*[handles[nm] if nm else 0 for nm in b.color])
+                        L.wrh_frame_add_composite_yuv_tile(f, kind, planes, (C.c_float * 30)(*v))
+                        continue
                     L.wrh_frame_add_composite_tile(f, kind, handles[b.color[0]], 1 if b.features & abi.FEAT_FAST_PATH else 0,
                                                    (C.c_float * 30)(*v))
             return

@@ -287,12 +287,20 @@ void Renderer::draw_tile_list(const std::vector<const CompositeTile*>& tiles, in
     if (instances.empty()) return;
     BatchTextures tex;
     tex.colors[0] = cur->texture;
-    draw_instanced_batch(WRCU_KIND_COMPOSITE, TEXTURE_2D | (cur->fast_path ? FAST_PATH : 0u), instances.data(),
+    uint32_t features = TEXTURE_2D | (cur->fast_path ? FAST_PATH : 0u);
+    if (cur->yuv) {  // get_composite_shader(CompositeSurfaceFormat::Yuv, ..) (shade.rs)
+      tex.colors[1] = cur->planes[0];
+      tex.colors[2] = cur->planes[1];
+      features = TEXTURE_2D | WRCU_FEAT_YUV;
+    }
+    draw_instanced_batch(WRCU_KIND_COMPOSITE, features, instances.data(),
                          sizeof(CompositeInstance), instances.size(), tex, stats);
     instances.clear();
   };
   for (const CompositeTile* t : tiles) {
-    if (cur && (cur->texture != t->texture || cur->fast_path != t->fast_path)) flush();
+    if (cur && (cur->texture != t->texture || cur->fast_path != t->fast_path || cur->yuv != t->yuv ||
+                cur->planes[0] != t->planes[0] || cur->planes[1] != t->planes[1]))
+      flush();
     cur = t;
     instances.push_back(t->instance);
   }
@@ -537,6 +545,16 @@ void wrh_frame_add_composite_tile(Frame* f, int kind, wrcu_tex texture, int fast
   t.kind = (CompositeTileKind)kind;
   t.texture = texture;
   t.fast_path = fast_path != 0;
+  memcpy(t.instance.v, instance30, sizeof t.instance.v);
+  f->composite_state.tiles.push_back(t);
+}
+void wrh_frame_add_composite_yuv_tile(Frame* f, int kind, const wrcu_tex* planes3, const float* instance30) {
+  CompositeTile t;
+  t.kind = (CompositeTileKind)kind;
+  t.texture = planes3[0];
+  t.yuv = true;
+  t.planes[0] = planes3[1];
+  t.planes[1] = planes3[2];
   memcpy(t.instance.v, instance30, sizeof t.instance.v);
   f->composite_state.tiles.push_back(t);
 }

@@ -144,6 +144,10 @@ struct CompositeTile {
   wrcu_tex texture = 0;   // picture-cache texture, external surface, or the 1x1 dummy
   CompositeInstance instance;
   bool fast_path = false; // NO_UV_CLAMP | NO_COLOR_MODULATION (composite.rs get_rgb_features)
+  // ResolvedExternalSurfaceColorData::Yuv (composite.rs): CompositeSurfaceFormat::Yuv, planes in
+  // sColor0..2 (BatchTextures::composite_yuv); `texture` is plane 0
+  bool yuv = false;
+  wrcu_tex planes[2] = {0, 0};  // planes 1 and 2
 };
 struct CompositeState {
   std::vector<CompositeTile> tiles;  // in z order (back to front)

@@ -1113,6 +1113,77 @@ def composite_frame(width=640, height=384, tile_w=256, tile_h=128, seed=1, exter
     return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
 
 
+def yuv_planes(w, h, seed, fmt):
+    """Seeded 8-bit video frame: full-resolution luma, 4:2:0 chroma (interleaved: one BGRA
+    texture holding Cb, Y, Cr in its B, G, R bytes — APPLE_rgb_422 mapping, yuv.glsl:223-229)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    ph = rng.uniform(0, 6.28, 6)
+
+    def plane(pw, ph_, k, lo, hi):
+        y2, x2 = np.mgrid[0:ph_, 0:pw].astype(np.float64)
+        v = 0.5 + 0.5 * np.sin(x2 / (11.0 + 7 * k) + ph[k]) * np.cos(y2 / (13.0 + 5 * k) + ph[3 + k])
+        v += rng.uniform(-0.06, 0.06, (ph_, pw))
+        return np.clip(np.rint(lo + np.clip(v, 0, 1) * (hi - lo)), 0, 255).astype(np.uint8)
+    # the full byte range, so out-of-gamut / out-of-range samples exercise the saturating adds
+    if fmt == "interleaved":
+        y, u, v = plane(w, h, 0, 0, 255), plane(w, h, 1, 0, 255), plane(w, h, 2, 0, 255)
+        img = np.stack([u, y, v, np.full_like(y, 255)], axis=2)
+        return [img.reshape(h, w * 4)]
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    y, u, v = plane(w, h, 0, 0, 255), plane(cw, ch, 1, 0, 255), plane(cw, ch, 2, 0, 255)
+    if fmt == "nv12":
+        return [y, np.stack([u, v], axis=2).reshape(ch, cw * 2)]
+    return [y, u, v]
+
+
+def yuv_composite_frame(fmt="planar", color_space=2, seed=1, width=512, height=320, linear=True,
+                        opaque=True, fractional=False):
+    """External YUV video surfaces through `composite` with WR_FEATURE_YUV
+    (composite.glsl:14-33, 83-130, 163-176, 197-214; draw_tile_list renderer/mod.rs:3126-3334 with
+    CompositeSurfaceFormat::Yuv): 8-bit PLANAR (three R8 planes), NV12 (R8 + RG8) or INTERLEAVED
+    (one BGRA plane); 1:1, up- and down-scaled, flipped and clipped surfaces with texel-space uv
+    sub-rects, chroma at half resolution."""
+    from .gpu_types import (composite_yuv_instance, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED)
+    rng = np.random.RandomState(seed * 31 + color_space)
+    vw, vh = 192, 128
+    planes = yuv_planes(vw, vh, seed + 5, fmt)
+    filt = abi.LINEAR if linear else abi.NEAREST
+    textures = {"fb": TextureDesc(abi.FMT_RGBA8, width, height)}
+    if fmt == "planar":
+        names, yuv_format = ("vy", "vu", "vv"), YUV_FORMAT_PLANAR
+        fmts = (abi.FMT_R8, abi.FMT_R8, abi.FMT_R8)
+    elif fmt == "nv12":
+        names, yuv_format = ("vy", "vuv", ""), YUV_FORMAT_NV12
+        fmts = (abi.FMT_R8, abi.FMT_RG8)
+    else:
+        names, yuv_format = ("vyuv", "", ""), YUV_FORMAT_INTERLEAVED
+        fmts = (abi.FMT_RGBA8,)
+    for nm, f, pl in zip(names, fmts, planes):
+        textures[nm] = TextureDesc(f, pl.shape[1] // abi.FMT_BPP[f], pl.shape[0], data=pl, filter=filt)
+    chroma = 1.0 if fmt == "interleaved" else 0.5
+    insts = []
+    for i in range(6):
+        r = _rand_rect(rng, width, height, 40, 260, integer=not fractional)
+        ux, uy = float(2 * rng.randint(0, 30)), float(2 * rng.randint(0, 20))
+        if i == 0:      # 1:1
+            uw, uh = min(r[2] - r[0], vw - ux), min(r[3] - r[1], vh - uy)
+            uw, uh = float(int(uw) & ~1), float(int(uh) & ~1)
+            r = (r[0], r[1], r[0] + uw, r[1] + uh)
+        elif i == 1:    # the whole frame, scaled
+            ux, uy, uw, uh = 0.0, 0.0, float(vw), float(vh)
+        else:
+            uw, uh = float(2 * rng.randint(10, 60)), float(2 * rng.randint(8, 40))
+        clip = r if i == 1 else (r[0] + 3.0, r[1] + 2.0, r[2] - 5.0, r[3] - 1.0)
+        ry = (ux, uy, ux + uw, uy + uh)
+        rc = tuple(v * chroma for v in ry)
+        insts.append(composite_yuv_instance(r, clip, color_space, yuv_format, 8, (ry, rc, rc), flip=(i == 3, i == 4)))
+    ops = [Clear(color=(0.1, 0.2, 0.3, 1.0)),
+           Batch(abi.KIND_COMPOSITE, np.stack(insts), blend=abi.BLEND_NONE if opaque else abi.BLEND_PREMULTIPLIED_ALPHA,
+                 features=abi.FEAT_TEXTURE_2D | abi.FEAT_YUV, color=names)]
+    return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
+
+
 def _picture_source(t, rng, aw, ah, w, h, one_to_one):
     """gpu-cache entry of an off-screen picture's uv rect the way
     RenderTaskCache/resolve_location publishes it: uv rect, user data, and the
