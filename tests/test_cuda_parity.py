@@ -249,6 +249,13 @@ def test_composite_yuv_variants(fmt, variant):
     assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)
 
 
+@pytest.mark.parametrize("fmt", YUV_FORMATS)
+def test_composite_yuv_4k_video(fmt):
+    """A 1080p video frame scaled to the whole 3840x2160 framebuffer (the bench's video workloads)."""
+    f = scenes.video_frame(3840, 2160, 1920, 1080, fmt)
+    assert_same(render(CudaDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), fmt)
+
+
 OPACITY_VARIANTS = ["scaled", "fractional", "one_to_one", "nearest"]
 
 

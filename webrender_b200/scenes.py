@@ -1184,6 +1184,28 @@ def yuv_composite_frame(fmt="planar", color_space=2, seed=1, width=512, height=3
     return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
 
 
+def video_frame(width=3840, height=2160, vw=1920, vh=1080, fmt="nv12", color_space=2, seed=1):
+    """One full-screen video surface: a vw x vh 8-bit YUV frame (NV12 by default, Rec.709 narrow
+    range) scaled to the whole framebuffer by `composite` YUV — the compositor's video case."""
+    from .gpu_types import (composite_yuv_instance, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED)
+    planes = yuv_planes(vw, vh, seed, fmt)
+    names = {"planar": ("vy", "vu", "vv"), "nv12": ("vy", "vuv", ""), "interleaved": ("vyuv", "", "")}[fmt]
+    fmts = {"planar": (abi.FMT_R8,) * 3, "nv12": (abi.FMT_R8, abi.FMT_RG8), "interleaved": (abi.FMT_RGBA8,)}[fmt]
+    yuv_format = {"planar": YUV_FORMAT_PLANAR, "nv12": YUV_FORMAT_NV12, "interleaved": YUV_FORMAT_INTERLEAVED}[fmt]
+    textures = {"fb": TextureDesc(abi.FMT_RGBA8, width, height)}
+    for nm, f, pl in zip(names, fmts, planes):
+        textures[nm] = TextureDesc(f, pl.shape[1] // abi.FMT_BPP[f], pl.shape[0], data=pl, filter=abi.LINEAR)
+    r = (0.0, 0.0, float(width), float(height))
+    ry = (0.0, 0.0, float(vw), float(vh))
+    ch = 1.0 if fmt == "interleaved" else 0.5
+    rc = tuple(v * ch for v in ry)
+    inst = composite_yuv_instance(r, r, color_space, yuv_format, 8, (ry, rc, rc))
+    ops = [Clear(color=(0.0, 0.0, 0.0, 1.0)),
+           Batch(abi.KIND_COMPOSITE, inst[None, :], blend=abi.BLEND_NONE,
+                 features=abi.FEAT_TEXTURE_2D | abi.FEAT_YUV, color=names)]
+    return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
+
+
 def _picture_source(t, rng, aw, ah, w, h, one_to_one):
     """gpu-cache entry of an off-screen picture's uv rect the way
     RenderTaskCache/resolve_location publishes it: uv rect, user data, and the
