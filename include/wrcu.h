@@ -272,6 +272,17 @@ int wrcu_draw_batch(wrcu_ctx* ctx, int kind, uint32_t features,
                     const wrcu_draw_state* state, const void* instances,
                     size_t instance_stride, int n_instances);
 
+/* draw_tile_list (renderer/mod.rs:3126-3334) in one submission.  The reference has to break its
+ * CompositeInstance list into a GL draw whenever the tile texture changes (mod.rs:3289-3316): one
+ * draw per picture-cache tile.  Here the texture of every instance travels with it — `textures[i]`
+ * is sColor0 of instance i, `state->color[0]` is ignored — so a whole tile list with the same shader
+ * parameters (`features`: TEXTURE_2D, optionally FAST_PATH) and blend state is two kernel launches.
+ * Instances are drawn in order; results equal n wrcu_draw_batch(WRCU_KIND_COMPOSITE, ..) calls. */
+int wrcu_draw_composite_tiles(wrcu_ctx* ctx, uint32_t features,
+                              const wrcu_draw_state* state, const void* instances,
+                              size_t instance_stride, int n_instances,
+                              const wrcu_tex* textures);
+
 /* Program-key lookup: maps the reference's program name string
  * "<shader>[ FEAT,FEAT]" (swgl/build.rs:13-31, gl.cc:1431) to kind+features.
  * Returns WRCU_ERR_UNSUPPORTED for programs outside the hot path. */

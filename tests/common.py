@@ -4,11 +4,11 @@ import numpy as np
 from webrender_b200 import abi, draw_frame
 
 
-def render(device_cls, frame, targets=None):
+def render(device_cls, frame, targets=None, tile_lists=False):
     """Run `frame` through a device; return {name: uint8 array} of target contents."""
     d = device_cls()
     try:
-        handles = draw_frame(d, frame)
+        handles = draw_frame(d, frame, tile_lists=tile_lists)
         out = {}
         names = targets or sorted({t.texture for p in frame.passes for t in p})
         for n in names:

@@ -141,6 +141,15 @@ def test_composite(seed, variant):
 
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", COMPOSITE_VARIANTS)
+def test_composite_tile_lists(seed, variant):
+    """wrcu_draw_composite_tiles: draw_tile_list (renderer/mod.rs:3126-3334) submitted as runs of
+    instances with one texture each, against the reference's one draw per texture change."""
+    f = scenes.composite_frame(seed=seed, external="external" in variant, fractional="fractional" in variant)
+    assert_same(render(EmuDevice, f, ["fb"], tile_lists=True), render(OracleDevice, f, ["fb"]), variant)
+
+
 YUV_FORMATS = ["planar", "nv12", "interleaved"]
 YUV_VARIANTS = ["opaque", "blend", "fractional", "nearest"]
 

@@ -136,6 +136,13 @@ def test_composite(seed, variant):
 
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_composite_tile_lists_oracle(seed):
+    """The oracle's wro_draw_composite_tiles (one draw per instance) equals SWGL's per-texture draws."""
+    f = _composite_frame(seed, "external_fractional")
+    assert_same(render(SwglDevice, f, ["fb"]), render(OracleDevice, f, ["fb"], tile_lists=True), "tile lists")
+
+
 YUV_FORMATS = ["planar", "nv12", "interleaved"]
 YUV_VARIANTS = ["opaque", "blend", "fractional", "nearest"]
 

@@ -39,6 +39,7 @@ struct SetupArgs {
   TexView color1;
   TexView color2;
   TexView clip_mask;
+  const TexView* tex_list;  // wrcu_draw_composite_tiles: sColor0 of instance i (nullptr: color0 for all)
 };
 
 // A setup kernel = one thread per instance running <name>_one.  Under the host

@@ -6,7 +6,10 @@
 #include "setup_common.cuh"
 
 // CmdCold: f[0..3] uv bounds used by the span shader, g[0..3] vColor,
-//          g[4] FAST_PATH, g[5..8] vUVBounds (fragment clamp)
+//          g[4] FAST_PATH, g[5..8] vUVBounds (fragment clamp),
+//          g[12..19] the instance's sColor0 view (tile lists carry one texture per instance)
+WRD const TexView& wr_composite_tex(const CmdCold& k) { return *(const TexView*)&k.g[12]; }
+static_assert(sizeof(TexView) <= 32, "TexView must fit CmdCold::g[12..19]");
 struct CompositeShader {
   struct Row {
     float o[2], step[2];
@@ -24,11 +27,11 @@ struct CompositeShader {
       u[j] = uv[0];
       v[j] = uv[1];
     }
-    wr_tex_row_setup(a.color0, k.f, true, body_len, u, v, max(tx0, (int)c.x0) - (int)c.x0, r.tr);
+    wr_tex_row_setup(wr_composite_tex(k), k.f, true, body_len, u, v, max(tx0, (int)c.x0) - (int)c.x0, r.tr);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];
-    const TexView& t = a.color0;
+    const TexView& t = wr_composite_tex(k);
     int rel = x - c.x0;
     if (rel < r.tr.body_len) {
       Px col{c.col[0], c.col[1], c.col[2], c.col[3]};
@@ -68,7 +71,8 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
   bool fast = (a.features & WRCU_FEAT_FAST_PATH) != 0;
   float ub[4] = {wr_min(uvr[0], uvr[2]), wr_min(uvr[1], uvr[3]), wr_max(uvr[0], uvr[2]), wr_max(uvr[1], uvr[3])};
   bool unnorm = (int)f[13] == 1;
-  float tw = (float)a.color0.w, th = (float)a.color0.h;
+  const TexView tex0 = a.tex_list ? a.tex_list[idx] : a.color0;
+  float tw = (float)tex0.w, th = (float)tex0.h;
   if (unnorm) {
     ub[0] += 0.5f; ub[1] += 0.5f; ub[2] += -0.5f; ub[3] += -0.5f;
     ub[0] /= tw; ub[1] /= th; ub[2] /= tw; ub[3] /= th;
@@ -104,6 +108,7 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
     else for (int i = 0; i < 4; i++) k->f[i] = ub[i];
     for (int i = 0; i < 4; i++) { k->g[i] = f[8 + i]; k->g[5 + i] = ub[i]; }
     k->g[4] = fast ? 1.0f : 0.0f;
+    *(TexView*)&k->g[12] = tex0;
   }
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);

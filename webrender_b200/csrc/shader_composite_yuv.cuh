@@ -77,6 +77,7 @@ struct CompositeYuvShader {
   struct PlaneRow {
     float bu[4], bv[4];  // quantised uv lanes of chunk kb
     float ustep, vstep, minu, minv, maxu, maxv;
+    int exact;  // bit 0: u sums exact (wr_sum_exact), bit 1: v sums
   };
   struct Row {
     float o[6], step[6];
@@ -116,6 +117,7 @@ struct CompositeYuvShader {
         r.p[p].vstep = __fmul_rn(r.step[2 * p + 1], 4.0f);
         wr_tex_seq_base(lu, r.p[p].ustep, r.kb, r.p[p].bu);
         wr_tex_seq_base(lv, r.p[p].vstep, r.kb, r.p[p].bv);
+        r.p[p].exact = (wr_sum_exact(r.p[p].bu, r.p[p].ustep) ? 1 : 0) | (wr_sum_exact(r.p[p].bv, r.p[p].vstep) ? 2 : 0);
       }
     }
     if (!r.body_len) return;
@@ -138,6 +140,7 @@ struct CompositeYuvShader {
       pr.maxv = wr_max(wr_linear_quantize(b[3], t.h), pr.minv);
       wr_tex_seq_base(qu, pr.ustep, r.kb, pr.bu);
       wr_tex_seq_base(qv, pr.vstep, r.kb, pr.bv);
+      pr.exact = (wr_sum_exact(pr.bu, pr.ustep) ? 1 : 0) | (wr_sum_exact(pr.bv, pr.vstep) ? 2 : 0);
     }
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
@@ -150,8 +153,8 @@ struct CompositeYuvShader {
       int ii[3][2];
       for (int p = 0; p < planes; p++) {
         const PlaneRow& pr = r.p[p];
-        float qu = pr.bu[j], qv = pr.bv[j];
-        for (int s = r.kb; s < (rel >> 2); s++) { qu = qu + pr.ustep; qv = qv + pr.vstep; }
+        const int m = (rel >> 2) - r.kb;
+        float qu = wr_sum_at(pr.bu[j], pr.ustep, m, pr.exact & 1), qv = wr_sum_at(pr.bv[j], pr.vstep, m, pr.exact & 2);
         ii[p][0] = (int)wr_clamp(qu, pr.minu, pr.maxu);
         ii[p][1] = (int)wr_clamp(qv, pr.minv, pr.maxv);
       }
@@ -185,8 +188,9 @@ struct CompositeYuvShader {
     if (r.frag_accum) {
       int j = rel & 3;
       for (int p = 0; p < 3; p++) {
-        float qu = r.p[p].bu[j], qv = r.p[p].bv[j];
-        for (int s = r.kb; s < (rel >> 2); s++) { qu = qu + r.p[p].ustep; qv = qv + r.p[p].vstep; }
+        const int m = (rel >> 2) - r.kb;
+        float qu = wr_sum_at(r.p[p].bu[j], r.p[p].ustep, m, r.p[p].exact & 1);
+        float qv = wr_sum_at(r.p[p].bv[j], r.p[p].vstep, m, r.p[p].exact & 2);
         uv[2 * p] = qu;
         uv[2 * p + 1] = qv;
       }

@@ -39,6 +39,7 @@ struct TexRow {
   // of the three dispatch segments (prefix fallback / interior / remainder)
   int kb[3];
   float bu[3][4], bv[4];
+  int exact;  // bit s: segment s's u sums are exact (wr_sum_exact); bit 3: the v sums
 };
 
 // Texel access by texture format.  R8 texels travel in Px.r (the lane the R8
@@ -75,6 +76,33 @@ WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
     v = wr_repeat_add(v, step, kb);
     out[j] = v;
   }
+}
+
+// Running sums that never round: when the four lane bases and the step are multiples of one power of
+// two g and stay below 2^24 g over the tile's 32 chunks, every partial sum is exactly representable, so the
+// reference's chunk-by-chunk accumulation equals base + m*step and needs no per-pixel replay
+// (integer and half-texel scale factors — 1:1, 2x video, device-pixel-ratio 2 — all land here).
+WRD bool wr_sum_exact(const float* base, float step) {
+  // any power-of-two grid g works: all values multiples of g and below 2^24 * g
+  const float grids[3] = {256.0f, 16.0f, 2.0f};
+  for (int gi = 0; gi < 3; gi++) {
+    const float g = grids[gi];
+    float s = step * g;
+    bool ok = s == truncf(s);
+    float amax = 0.0f;
+    for (int j = 0; j < 4; j++) {
+      float b = base[j] * g;
+      ok = ok && b == truncf(b);
+      amax = wr_max(amax, fabsf(b));
+    }
+    if (ok && amax + 34.0f * fabsf(s) < 16777216.0f) return true;
+  }
+  return false;
+}
+WRD float wr_sum_at(float base, float step, int m, bool exact) {
+  if (exact) return base + (float)m * step;
+  for (int s = 0; s < m; s++) base = base + step;
+  return base;
 }
 
 // blendTextureLinearDispatch's partition (swgl_ext.h:385-448) for a span whose quantised uv lanes,
@@ -128,6 +156,9 @@ WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int 
     wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
     r.kb[0] = min(r.kb[0], r.before >> 2);
     r.kb[1] = min(r.kb[1], r.inside >> 2);
+    r.exact = (r.before > 0 && wr_sum_exact(r.bu[0], r.ustep) ? 1 : 0) |
+              (r.inside > 0 && r.filter == LF_UPSCALE && wr_sum_exact(r.bu[1], r.ustep) ? 2 : 0) |
+              (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
   }
 }
 
@@ -162,6 +193,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
       r.kb[2] = r.nsolid ? 0 : max(0, tile_rel >> 2);
       wr_tex_seq_base(r.qu, ustep, r.kb[2], r.bu[2]);
       wr_tex_seq_base(r.qv, vstep, r.kb[2], r.bv);
+      r.exact = (wr_sum_exact(r.bu[2], ustep) ? 4 : 0) | (wr_sum_exact(r.bv, vstep) ? 8 : 0);
       return;
     }
   }
@@ -215,6 +247,7 @@ WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len
   r.kb[2] = max(0, tile_rel >> 2);
   wr_tex_seq_base(r.qu, r.ustep, r.kb[2], r.bu[2]);
   wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
+  r.exact = (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
 }
 
 // Source texel (before colour modulation) of body pixel `rel` (0-based in the span).
@@ -225,14 +258,18 @@ WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
   }
   int j = rel & 3;
   if (r.mode == TEX_LINEAR_R8) {
-    float qu = r.bu[2][j], qv = r.bv[j];
-    for (int s = r.kb[2]; s < (rel >> 2); s++) { qu = qu + r.ustep; qv = qv + r.vstep; }
+    const int m = (rel >> 2) - r.kb[2];
+    float qu = wr_sum_at(r.bu[2][j], r.ustep, m, r.exact & 4), qv = wr_sum_at(r.bv[j], r.vstep, m, r.exact & 8);
     int rr = wr_texture_linear_r8(t, (int)wr_clamp(qu, r.minu, r.maxu), (int)wr_clamp(qv, r.minv, r.maxv));
     return Px{rr, rr, rr, rr};
   }
   if (r.mode == TEX_NEAREST_FALLBACK) {
     float su = r.bu[2][j], sv = r.bv[j];
-    if (!r.nsolid) for (int s = r.kb[2]; s < (rel >> 2); s++) { su = su + r.ustep; sv = sv + r.vstep; }
+    if (!r.nsolid) {
+      const int m = (rel >> 2) - r.kb[2];
+      su = wr_sum_at(su, r.ustep, m, r.exact & 4);
+      sv = wr_sum_at(sv, r.vstep, m, r.exact & 8);
+    }
     int ix = (int)wr_clamp(su, r.minu, r.maxu), iy = (int)wr_clamp(sv, r.minv, r.maxv);
     int cx = wr_clamp_coord(ix, t.w), cy = wr_clamp_coord(iy, t.h);
     return wr_tex_load_any(t, cy, cx);
@@ -242,21 +279,18 @@ WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
     // fallback filter (swgl_ext.h:172-184): uv += uv_step per chunk
     float qu, qv;
     if (rel < r.before) {
-      qu = r.bu[0][j];
-      for (int s = r.kb[0]; s < (rel >> 2); s++) qu = qu + r.ustep;
+      qu = wr_sum_at(r.bu[0][j], r.ustep, (rel >> 2) - r.kb[0], r.exact & 1);
       qv = r.qv[j];  // prefix exists only for constant-y filters
     } else {
       int p = rel - r.before - r.inside;
-      qu = r.bu[2][j];
-      qv = r.bv[j];
-      for (int s = r.kb[2]; s < (p >> 2); s++) { qu = qu + r.ustep; qv = qv + r.vstep; }
+      qu = wr_sum_at(r.bu[2][j], r.ustep, (p >> 2) - r.kb[2], r.exact & 4);
+      qv = wr_sum_at(r.bv[j], r.vstep, (p >> 2) - r.kb[2], r.exact & 8);
     }
     return wr_tex_linear_any(t, (int)wr_clamp(qu, r.minu, r.maxu), (int)wr_clamp(qv, r.minv, r.maxv));
   }
   int p = rel - r.before;
   if (r.filter == LF_UPSCALE) {
-    float qu = r.bu[1][j];
-    for (int s = r.kb[1]; s < (p >> 2); s++) qu = qu + r.ustep;
+    float qu = wr_sum_at(r.bu[1][j], r.ustep, (p >> 2) - r.kb[1], r.exact & 2);
     int ix = (p < 4) ? (int)wr_clamp(qu, r.minu, r.maxu) : (int)qu;
     return wr_tex_linear_any(t, ix, r.uiy0);
   }

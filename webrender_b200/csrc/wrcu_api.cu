@@ -753,8 +753,24 @@ static int ensure_cmd_capacity(wrcu_ctx* c, size_t n) {
   return WRCU_OK;
 }
 
+static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_draw_state* st,
+                           const void* instances, size_t stride, int n, const wrcu_tex* textures);
+
 extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const wrcu_draw_state* st,
                                const void* instances, size_t stride, int n) {
+  return draw_batch_impl(c, kind, features, st, instances, stride, n, nullptr);
+}
+
+extern "C" int wrcu_draw_composite_tiles(wrcu_ctx* c, uint32_t features, const wrcu_draw_state* st,
+                                         const void* instances, size_t stride, int n, const wrcu_tex* textures) {
+  if (!textures) return wrcu_fail(c, WRCU_ERR_INVALID, "draw_composite_tiles: no texture list");
+  if (features & WRCU_FEAT_YUV)
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_composite_tiles: YUV surfaces go through wrcu_draw_batch");
+  return draw_batch_impl(c, WRCU_KIND_COMPOSITE, features, st, instances, stride, n, textures);
+}
+
+static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_draw_state* st,
+                           const void* instances, size_t stride, int n, const wrcu_tex* textures) {
   if (!st || !instances || n < 0 || stride == 0)
     return wrcu_fail(c, WRCU_ERR_INVALID, "draw_batch: bad arguments");
   if (n == 0) return WRCU_OK;
@@ -769,6 +785,18 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   c->stats.instances += (uint64_t)n;
 
   int rc;
+  size_t views_off = 0;
+  if (textures) {
+    // one sampler view per instance, staged ahead of the instances
+    std::vector<TexView> views((size_t)n);
+    for (int i = 0; i < n; i++) {
+      views[(size_t)i] = tex_view(c, textures[i]);
+      if (!views[(size_t)i].ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "draw_composite_tiles: instance %d has no texture", i);
+    }
+    void* dviews = nullptr;
+    if ((rc = stage(c, views.data(), views.size() * sizeof(TexView), &dviews)) != WRCU_OK) return rc;
+    views_off = (size_t)((uint8_t*)dviews - c->arena[c->cur_arena].dev);
+  }
   void* dinst = nullptr;
   if ((rc = stage(c, instances, stride * (size_t)n, &dinst)) != WRCU_OK) return rc;
   if ((rc = ensure_cmd_capacity(c, (size_t)n)) != WRCU_OK) return rc;
@@ -812,6 +840,10 @@ extern "C" int wrcu_draw_batch(wrcu_ctx* c, int kind, uint32_t features, const w
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
   sa.color2 = tex_view(c, st->color[2]);
+  if (textures) {
+    sa.tex_list = (const TexView*)(c->arena[c->cur_arena].dev + views_off);  // (the arena may have grown since)
+    sa.color0 = tex_view(c, textures[0]);
+  }
   // Bitmask bins for batches with many instances: the per-tile command scan of the raster
   // kernel costs tiles x n hot records of L2 traffic; with bins it reads n/32 words per tile.
   {

@@ -45,6 +45,7 @@ def bind_prefixed(lib, prefix):
     f("target_bind").argtypes = [vp, u32, u32, C.POINTER(C.c_float), C.POINTER(i32)]
     f("clear").argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     f("draw_batch").argtypes = [vp, i32, u32, C.POINTER(abi.DrawState), vp, sz, i32]
+    f("draw_composite_tiles").argtypes = [vp, u32, C.POINTER(abi.DrawState), vp, sz, i32, C.POINTER(C.c_uint32)]
     f("last_error_string").argtypes = [vp]
     f("last_error_string").restype = C.c_char_p
     f("texture_upload_batch").argtypes = [vp, u32, C.POINTER(abi.UploadRect), sz, vp, sz]
@@ -156,6 +157,21 @@ class DeviceBase:
         inst = np.ascontiguousarray(inst)
         n, stride = inst.shape
         self._check(self._f("draw_batch")(self.ctx, kind, features, C.byref(st), inst.ctypes.data, stride, n))
+
+    def draw_composite_tiles(self, features, blend, scissor, blend_color, inst, textures):
+        """wrcu_draw_composite_tiles: one CompositeInstance list, one texture per instance."""
+        st = abi.DrawState()
+        st.blend, st.depth = blend, abi.DEPTH_OFF
+        st.scissor_enabled = 1 if scissor is not None else 0
+        if scissor is not None:
+            for i in range(4):
+                st.scissor[i] = scissor[i]
+        for i in range(4):
+            st.blend_color[i] = blend_color[i]
+        inst = np.ascontiguousarray(inst)
+        n, stride = inst.shape
+        tex = (C.c_uint32 * n)(*textures)
+        self._check(self._f("draw_composite_tiles")(self.ctx, features, C.byref(st), inst.ctypes.data, stride, n, tex))
 
 
 class CudaDevice(DeviceBase):

@@ -66,9 +66,10 @@ class Frame:
     passes: List[List[Target]]
 
 
-def draw_frame(dev, frame: Frame, handles: Optional[Dict[str, int]] = None):
+def draw_frame(dev, frame: Frame, handles: Optional[Dict[str, int]] = None, tile_lists: bool = False):
     """Renderer::draw_frame restated over the wrcu device calls.  Returns the
-    name → texture handle map (textures are created on first use)."""
+    name → texture handle map (textures are created on first use).  tile_lists: submit runs of
+    composite batches through wrcu_draw_composite_tiles (what the C++ host's draw_tile_list does)."""
     handles = {} if handles is None else handles
     for name, t in frame.textures.items():
         if name not in handles:
@@ -82,9 +83,15 @@ def draw_frame(dev, frame: Frame, handles: Optional[Dict[str, int]] = None):
             desc = frame.textures[tgt.texture]
             dev.target_bind(handles[tgt.texture], handles.get(tgt.depth, 0) if tgt.depth else 0,
                             ortho(desc.width, desc.height), (0, 0, desc.width, desc.height))
-            for op in tgt.ops:
+            ops = _fuse_tile_lists(tgt.ops) if tile_lists else tgt.ops
+            for op in ops:
                 if isinstance(op, Clear):
                     dev.clear(op.rect, op.color, op.depth)
+                elif isinstance(op, _TileList):
+                    b = op.batches[0]
+                    inst = np.concatenate([x.instance_bytes() for x in op.batches])
+                    tex = [handles[x.color[0]] for x in op.batches for _ in range(x.instance_bytes().shape[0])]
+                    dev.draw_composite_tiles(b.features, b.blend, b.scissor, b.blend_color, inst, tex)
                 else:
                     dev.draw_batch(op.kind, op.features, op.blend, op.depth,
                                    [handles.get(n, 0) if n else 0 for n in op.color],
@@ -92,3 +99,25 @@ def draw_frame(dev, frame: Frame, handles: Optional[Dict[str, int]] = None):
                                    op.scissor, op.blend_color, op.instance_bytes())
     dev.frame_end()
     return handles
+
+
+class _TileList:
+    def __init__(self, batches):
+        self.batches = batches
+
+
+def _fuse_tile_lists(ops):
+    """draw_tile_list's grouping for wrcu_draw_composite_tiles: consecutive RGBA composite batches with the
+    same shader parameters and blend state become one submission, whatever their textures."""
+    from . import abi
+    out = []
+    for op in ops:
+        ok = (not isinstance(op, Clear) and op.kind == abi.KIND_COMPOSITE and not (op.features & abi.FEAT_YUV)
+              and not op.clip_mask)
+        if ok and out and isinstance(out[-1], _TileList):
+            p = out[-1].batches[0]
+            if (p.features, p.blend, p.scissor, tuple(p.blend_color)) == (op.features, op.blend, op.scissor, tuple(op.blend_color)):
+                out[-1].batches.append(op)
+                continue
+        out.append(_TileList([op]) if ok else op)
+    return out

@@ -241,6 +241,8 @@ class HostRenderer:
             for b in opaque + rest:
                 kind = 0 if b.blend == abi.BLEND_NONE else (1 if b.blend == abi.BLEND_PREMULTIPLIED_DEST_OUT else 2)
                 a = b.instance_bytes()
+                if kind == 0:
+                    a = a[::-1]   # composite_simple walks opaque tiles front to back: keep the batch's draw order
                 for row in a:
                     v = np.ascontiguousarray(row).view(np.float32)
                     if b.features & abi.FEAT_YUV:

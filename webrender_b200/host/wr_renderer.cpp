@@ -279,30 +279,40 @@ void Renderer::draw_texture_cache_target(const TextureCacheRenderTarget& t, Rend
 }
 
 void Renderer::draw_tile_list(const std::vector<const CompositeTile*>& tiles, int blend, RendererStats& stats) {
-  // batches break whenever the texture or the shader parameters change (mod.rs:3289-3316)
+  // The reference breaks the instance list whenever the texture or the shader parameters change
+  // (mod.rs:3289-3316) — a GL draw binds one sColor0.  wrcu_draw_composite_tiles carries the texture
+  // per instance, so a run of tiles only breaks on the shader parameters (FAST_PATH; RGBA vs YUV).
   state.blend = blend;
   std::vector<CompositeInstance> instances;
+  std::vector<wrcu_tex> textures;
   const CompositeTile* cur = nullptr;
   auto flush = [&]() {
     if (instances.empty()) return;
-    BatchTextures tex;
-    tex.colors[0] = cur->texture;
-    uint32_t features = TEXTURE_2D | (cur->fast_path ? FAST_PATH : 0u);
-    if (cur->yuv) {  // get_composite_shader(CompositeSurfaceFormat::Yuv, ..) (shade.rs)
+    if (cur->yuv) {  // get_composite_shader(CompositeSurfaceFormat::Yuv, ..) (shade.rs); planes in sColor0..2
+      BatchTextures tex;
+      tex.colors[0] = cur->texture;
       tex.colors[1] = cur->planes[0];
       tex.colors[2] = cur->planes[1];
-      features = TEXTURE_2D | WRCU_FEAT_YUV;
+      draw_instanced_batch(WRCU_KIND_COMPOSITE, TEXTURE_2D | WRCU_FEAT_YUV, instances.data(), sizeof(CompositeInstance),
+                           instances.size(), tex, stats);
+    } else {
+      state.clip_mask = 0;
+      if (wrcu_draw_composite_tiles(device, TEXTURE_2D | (cur->fast_path ? FAST_PATH : 0u), &state, instances.data(),
+                                    sizeof(CompositeInstance), (int)instances.size(), textures.data()) != WRCU_OK)
+        failed++;
+      stats.total_draw_calls++;
     }
-    draw_instanced_batch(WRCU_KIND_COMPOSITE, features, instances.data(),
-                         sizeof(CompositeInstance), instances.size(), tex, stats);
     instances.clear();
+    textures.clear();
   };
   for (const CompositeTile* t : tiles) {
-    if (cur && (cur->texture != t->texture || cur->fast_path != t->fast_path || cur->yuv != t->yuv ||
-                cur->planes[0] != t->planes[0] || cur->planes[1] != t->planes[1]))
-      flush();
+    bool brk = cur && (cur->fast_path != t->fast_path || cur->yuv != t->yuv);
+    if (cur && t->yuv && !brk)
+      brk = cur->texture != t->texture || cur->planes[0] != t->planes[0] || cur->planes[1] != t->planes[1];
+    if (brk) flush();
     cur = t;
     instances.push_back(t->instance);
+    textures.push_back(t->texture);
   }
   flush();
 }
