@@ -101,47 +101,61 @@ struct CompositeYuvShader {
     r.body_len = ok ? (len & ~3) : 0;
     r.kb = max(0, (max(tx0, (int)c.x0) - (int)c.x0) >> 2);
     r.frag_accum = !r.body_len && len >= 4;
-    if (r.frag_accum) {
-      // No span shader ran (a NEAREST plane): the fragment loop advances the varyings chunk by
-      // chunk (run() → step_interp_inputs, vUV += interp_step), a running sum.  Scaled video
-      // often samples exactly on texel boundaries, where the sum's rounding decides the texel.
-      for (int p = 0; p < 3; p++) {
-        float lu[4], lv[4];
-        for (int j = 0; j < 4; j++) {
-          float uv[6];
-          wr_interp_at<6>(r.o, r.step, j, uv);
-          lu[j] = uv[2 * p];
-          lv[j] = uv[2 * p + 1];
-        }
-        r.p[p].ustep = __fmul_rn(r.step[2 * p], 4.0f);
-        r.p[p].vstep = __fmul_rn(r.step[2 * p + 1], 4.0f);
-        wr_tex_seq_base(lu, r.p[p].ustep, r.kb, r.p[p].bu);
-        wr_tex_seq_base(lv, r.p[p].vstep, r.kb, r.p[p].bv);
-        r.p[p].exact = (wr_sum_exact(r.p[p].bu, r.p[p].ustep) ? 1 : 0) | (wr_sum_exact(r.p[p].bv, r.p[p].vstep) ? 2 : 0);
-      }
-    }
-    if (!r.body_len) return;
-    for (int p = 0; p < planes; p++) {  // LINEAR_QUANTIZE_UV (swgl_ext.h:160-168) per plane
+    if (!r.body_len && !r.frag_accum) return;
+    // Start lanes and per-chunk steps of the six running sums (three planes x u,v).  Span body:
+    // LINEAR_QUANTIZE_UV (swgl_ext.h:160-168) per plane.  No span shader (a NEAREST plane): the
+    // fragment loop advances the varyings chunk by chunk (run() -> step_interp_inputs, vUV +=
+    // interp_step) — scaled video samples exactly on texel boundaries, where that sum's rounding
+    // decides the texel.
+    float uvj[4][6];
+    for (int j = 0; j < 4; j++) wr_interp_at<6>(r.o, r.step, j, uvj[j]);
+    float q[3][2][4], st[3][2];
+    for (int p = 0; p < 3; p++) {
       const TexView& t = plane(a, p);
       PlaneRow& pr = r.p[p];
-      float qu[4], qv[4];
-      for (int j = 0; j < 4; j++) {
-        float uv[6];
-        wr_interp_at<6>(r.o, r.step, j, uv);
-        qu[j] = wr_linear_quantize(uv[2 * p], t.w);
-        qv[j] = wr_linear_quantize(uv[2 * p + 1], t.h);
+      for (int ax = 0; ax < 2; ax++) {
+        for (int j = 0; j < 4; j++)
+          q[p][ax][j] = r.body_len ? wr_linear_quantize(uvj[j][2 * p + ax], ax ? t.h : t.w) : uvj[j][2 * p + ax];
+        st[p][ax] = r.body_len ? 4.0f * (q[p][ax][1] - q[p][ax][0]) : __fmul_rn(r.step[2 * p + ax], 4.0f);
       }
-      pr.ustep = 4.0f * (qu[1] - qu[0]);
-      pr.vstep = 4.0f * (qv[1] - qv[0]);
-      const float* b = k.g + 4 * p;
-      pr.minu = wr_max(wr_linear_quantize(b[0], t.w), 0.0f);
-      pr.minv = wr_max(wr_linear_quantize(b[1], t.h), 0.0f);
-      pr.maxu = wr_max(wr_linear_quantize(b[2], t.w), pr.minu);
-      pr.maxv = wr_max(wr_linear_quantize(b[3], t.h), pr.minv);
-      wr_tex_seq_base(qu, pr.ustep, r.kb, pr.bu);
-      wr_tex_seq_base(qv, pr.vstep, r.kb, pr.bv);
-      pr.exact = (wr_sum_exact(pr.bu, pr.ustep) ? 1 : 0) | (wr_sum_exact(pr.bv, pr.vstep) ? 2 : 0);
+      pr.ustep = st[p][0];
+      pr.vstep = st[p][1];
+      if (r.body_len) {
+        const float* b = k.g + 4 * p;
+        pr.minu = wr_max(wr_linear_quantize(b[0], t.w), 0.0f);
+        pr.minv = wr_max(wr_linear_quantize(b[1], t.h), 0.0f);
+        pr.maxu = wr_max(wr_linear_quantize(b[2], t.w), pr.minu);
+        pr.maxv = wr_max(wr_linear_quantize(b[3], t.h), pr.minv);
+      }
     }
+#ifdef WRCU_HOSTEMU
+    for (int p = 0; p < 3; p++) {
+      wr_tex_seq_base(q[p][0], st[p][0], r.kb, r.p[p].bu);
+      wr_tex_seq_base(q[p][1], st[p][1], r.kb, r.p[p].bv);
+    }
+#else
+    {
+      // 24 independent walks, the whole warp is here: lane l < 24 takes (plane, axis, chunk lane)
+      // = (l >> 3, (l >> 2) & 1, l & 3); the results are broadcast (see wr_tex_bases)
+      const int l = threadIdx.x & 31, lp = l >> 3, lax = (l >> 2) & 1, lj = l & 3;
+      float x = 0.0f, sx = 0.0f;
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int ax = 0; ax < 2; ax++)
+          if (lp == p && lax == ax) { x = wr_sel4(q[p][ax], lj); sx = st[p][ax]; }
+      const float val = l < 24 ? wr_repeat_add(x, sx, r.kb) : 0.0f;
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          r.p[p].bu[j] = __shfl_sync(0xFFFFFFFFu, val, p * 8 + j);
+          r.p[p].bv[j] = __shfl_sync(0xFFFFFFFFu, val, p * 8 + 4 + j);
+        }
+    }
+#endif
+    for (int p = 0; p < 3; p++)
+      r.p[p].exact = (wr_sum_exact(r.p[p].bu, r.p[p].ustep) ? 1 : 0) | (wr_sum_exact(r.p[p].bv, r.p[p].vstep) ? 2 : 0);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];

@@ -78,6 +78,34 @@ WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
   }
 }
 
+// The running-sum bases of one textured row — up to three x segments and the y lanes, four chunk
+// lanes each — are 16 independent wr_repeat_add walks.  row_setup runs with the whole warp
+// converged on the same (command,row), so lane l < 16 walks one of them and the results are
+// broadcast: one walk's worth of instructions instead of sixteen (a 4K-wide scaled span crosses
+// ~18 binades per walk by its last tile).
+WRD float wr_sel4(const float* a, int j) { return j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3])); }
+WRD void wr_tex_bases(const float* s0, int n0, const float* s1, int n1, const float* s2, int n2, float ustep,
+                      const float* sv, int nv, float vstep, float (*bu)[4], float* bv) {
+#ifdef WRCU_HOSTEMU
+  wr_tex_seq_base(s0, ustep, n0, bu[0]);
+  wr_tex_seq_base(s1, ustep, n1, bu[1]);
+  wr_tex_seq_base(s2, ustep, n2, bu[2]);
+  wr_tex_seq_base(sv, vstep, nv, bv);
+#else
+  const int l = threadIdx.x & 31, g = (l >> 2) & 3, j = l & 3;
+  const float x = g == 0 ? wr_sel4(s0, j) : (g == 1 ? wr_sel4(s1, j) : (g == 2 ? wr_sel4(s2, j) : wr_sel4(sv, j)));
+  const int n = g == 0 ? n0 : (g == 1 ? n1 : (g == 2 ? n2 : nv));
+  const float val = l < 16 ? wr_repeat_add(x, g == 3 ? vstep : ustep, n) : 0.0f;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    bu[0][q] = __shfl_sync(0xFFFFFFFFu, val, q);
+    bu[1][q] = __shfl_sync(0xFFFFFFFFu, val, 4 + q);
+    bu[2][q] = __shfl_sync(0xFFFFFFFFu, val, 8 + q);
+    bv[q] = __shfl_sync(0xFFFFFFFFu, val, 12 + q);
+  }
+#endif
+}
+
 // Running sums that never round: when the four lane bases and the step are multiples of one power of
 // two g and stay below 2^24 g over the tile's 32 chunks, every partial sum is exactly representable, so the
 // reference's chunk-by-chunk accumulation equals base + m*step and needs no per-pixel replay
@@ -143,17 +171,18 @@ WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int 
   }
   // running-sum bases per segment
   {
-    float start[4];
-    for (int j = 0; j < 4; j++) start[j] = r.qu[j];
+    float s0[4], s1[4], s2[4];
+    for (int j = 0; j < 4; j++) {
+      s0[j] = r.qu[j];
+      s1[j] = r.before > 0 ? s0[j] + (float)(r.before / 4) * r.ustep : s0[j];
+      s2[j] = r.inside > 0 ? s1[j] + (float)(r.inside / 4) * r.ustep : s1[j];
+    }
     r.kb[0] = max(0, tile_rel >> 2);
-    if (r.before > 0) wr_tex_seq_base(start, r.ustep, min(r.kb[0], r.before >> 2), r.bu[0]);
-    if (r.before > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.before / 4) * r.ustep;
     r.kb[1] = max(0, (tile_rel - r.before) >> 2);
-    if (r.inside > 0 && r.filter == LF_UPSCALE) wr_tex_seq_base(start, r.ustep, min(r.kb[1], r.inside >> 2), r.bu[1]);
-    if (r.inside > 0) for (int j = 0; j < 4; j++) start[j] = start[j] + (float)(r.inside / 4) * r.ustep;
     r.kb[2] = max(0, (tile_rel - r.before - r.inside) >> 2);
-    wr_tex_seq_base(start, r.ustep, r.kb[2], r.bu[2]);
-    wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
+    wr_tex_bases(s0, r.before > 0 ? min(r.kb[0], r.before >> 2) : 0,
+                 s1, (r.inside > 0 && r.filter == LF_UPSCALE) ? min(r.kb[1], r.inside >> 2) : 0,
+                 s2, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv);
     r.kb[0] = min(r.kb[0], r.before >> 2);
     r.kb[1] = min(r.kb[1], r.inside >> 2);
     r.exact = (r.before > 0 && wr_sum_exact(r.bu[0], r.ustep) ? 1 : 0) |
@@ -191,8 +220,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
                  ((int)r.minv >= (int)r.maxv || fabsf(vstep) * (float)body_len * 1.0f < 0.5f);
       for (int j = 0; j < 4; j++) { r.qu[j] = u[j] * (float)t.w; r.qv[j] = v[j] * (float)t.h; }
       r.kb[2] = r.nsolid ? 0 : max(0, tile_rel >> 2);
-      wr_tex_seq_base(r.qu, ustep, r.kb[2], r.bu[2]);
-      wr_tex_seq_base(r.qv, vstep, r.kb[2], r.bv);
+      wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], ustep, r.qv, r.kb[2], vstep, r.bu, r.bv);
       r.exact = (wr_sum_exact(r.bu[2], ustep) ? 4 : 0) | (wr_sum_exact(r.bv, vstep) ? 8 : 0);
       return;
     }
@@ -245,8 +273,7 @@ WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len
   r.maxu = wr_max(wr_linear_quantize(bounds[2], t.w), r.minu);
   r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
   r.kb[2] = max(0, tile_rel >> 2);
-  wr_tex_seq_base(r.qu, r.ustep, r.kb[2], r.bu[2]);
-  wr_tex_seq_base(r.qv, r.vstep, r.kb[2], r.bv);
+  wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv);
   r.exact = (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
 }
 
