@@ -256,7 +256,7 @@ struct BoxShadowShader {
                 TexRow tr;
                 tr.mode = TEX_NONE;
                 if (!run.center)
-                  wr_tex_row_setup(a.color0, run.ub, false, run.n, run.u, run.v, rel_run, tr, WRCU_FMT_R8);
+                  wr_tex_row_setup(a.color0, run.ub, false, run.n, run.u, run.v, rel_run, tr, WRCU_FMT_R8, false);
                 r8 = run_pixel(a, k, run, tr, rel_run);
                 break;
               }

@@ -246,7 +246,7 @@ struct ImageRepeatShader {
           tr.ustep = rc.su * rc.scx;
           tr.vstep = rc.sv * rc.scy;
           tr.minu = rc.minu; tr.minv = rc.minv; tr.maxu = rc.maxu; tr.maxv = rc.maxv;
-          wr_tex_linear_partition(t, tr, tr.body_len, p & ~3);
+          wr_tex_linear_partition(t, tr, tr.body_len, p & ~3, false);  // per-lane: no warp cooperation
         } else {
 #pragma unroll
           for (int q = 0; q < 4; q++) {

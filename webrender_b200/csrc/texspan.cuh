@@ -84,14 +84,20 @@ WRD void wr_tex_seq_base(const float* start, float step, int kb, float* out) {
 // broadcast: one walk's worth of instructions instead of sixteen (a 4K-wide scaled span crosses
 // ~18 binades per walk by its last tile).
 WRD float wr_sel4(const float* a, int j) { return j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3])); }
+// `coop` must be false wherever lanes arrive with different arguments (per-pixel callers).
 WRD void wr_tex_bases(const float* s0, int n0, const float* s1, int n1, const float* s2, int n2, float ustep,
-                      const float* sv, int nv, float vstep, float (*bu)[4], float* bv) {
-#ifdef WRCU_HOSTEMU
-  wr_tex_seq_base(s0, ustep, n0, bu[0]);
-  wr_tex_seq_base(s1, ustep, n1, bu[1]);
-  wr_tex_seq_base(s2, ustep, n2, bu[2]);
-  wr_tex_seq_base(sv, vstep, nv, bv);
-#else
+                      const float* sv, int nv, float vstep, float (*bu)[4], float* bv, bool coop) {
+#ifndef WRCU_HOSTEMU
+  if (!coop)
+#endif
+  {
+    wr_tex_seq_base(s0, ustep, n0, bu[0]);
+    wr_tex_seq_base(s1, ustep, n1, bu[1]);
+    wr_tex_seq_base(s2, ustep, n2, bu[2]);
+    wr_tex_seq_base(sv, vstep, nv, bv);
+    return;
+  }
+#ifndef WRCU_HOSTEMU
   const int l = threadIdx.x & 31, g = (l >> 2) & 3, j = l & 3;
   const float x = g == 0 ? wr_sel4(s0, j) : (g == 1 ? wr_sel4(s1, j) : (g == 2 ? wr_sel4(s2, j) : wr_sel4(sv, j)));
   const int n = g == 0 ? n0 : (g == 1 ? n1 : (g == 2 ? n2 : nv));
@@ -137,7 +143,7 @@ WRD float wr_sum_at(float base, float step, int m, bool exact) {
 // steps, clamp bounds and filter are already in `r`: prefix through the fallback filter, interior
 // through the selected filter, remainder through the fallback; plus the running-sum bases of the
 // first chunk >= tile_rel inside each segment.
-WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int tile_rel) {
+WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int tile_rel, bool coop = true) {
   const int filter = r.filter;
   r.before = 0;
   r.inside = 0;
@@ -182,7 +188,7 @@ WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int 
     r.kb[2] = max(0, (tile_rel - r.before - r.inside) >> 2);
     wr_tex_bases(s0, r.before > 0 ? min(r.kb[0], r.before >> 2) : 0,
                  s1, (r.inside > 0 && r.filter == LF_UPSCALE) ? min(r.kb[1], r.inside >> 2) : 0,
-                 s2, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv);
+                 s2, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv, coop);
     r.kb[0] = min(r.kb[0], r.before >> 2);
     r.kb[1] = min(r.kb[1], r.inside >> 2);
     r.exact = (r.before > 0 && wr_sum_exact(r.bu[0], r.ustep) ? 1 : 0) |
@@ -193,7 +199,7 @@ WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int 
 
 WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sampler_filter, int body_len,
                           const float* u, const float* v, int tile_rel, TexRow& r,
-                          int target_fmt = WRCU_FMT_RGBA8) {
+                          int target_fmt = WRCU_FMT_RGBA8, bool coop = true) {
   r.body_len = body_len;
   r.mode = TEX_NONE;
   if (body_len == 0 || t.fmt != target_fmt) {
@@ -220,7 +226,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
                  ((int)r.minv >= (int)r.maxv || fabsf(vstep) * (float)body_len * 1.0f < 0.5f);
       for (int j = 0; j < 4; j++) { r.qu[j] = u[j] * (float)t.w; r.qv[j] = v[j] * (float)t.h; }
       r.kb[2] = r.nsolid ? 0 : max(0, tile_rel >> 2);
-      wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], ustep, r.qv, r.kb[2], vstep, r.bu, r.bv);
+      wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], ustep, r.qv, r.kb[2], vstep, r.bu, r.bv, coop);
       r.exact = (wr_sum_exact(r.bu[2], ustep) ? 4 : 0) | (wr_sum_exact(r.bv, vstep) ? 8 : 0);
       return;
     }
@@ -249,7 +255,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
   r.minv = wr_max(wr_linear_quantize(bounds[1], t.h), 0.0f);
   r.maxu = wr_max(wr_linear_quantize(bounds[2], t.w), r.minu);
   r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
-  wr_tex_linear_partition(t, r, body_len, tile_rel);
+  wr_tex_linear_partition(t, r, body_len, tile_rel, coop);
 }
 
 // blendTextureLinearR8 (swgl_ext.h:634-650): R8 atlas through the fallback
@@ -273,7 +279,7 @@ WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len
   r.maxu = wr_max(wr_linear_quantize(bounds[2], t.w), r.minu);
   r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
   r.kb[2] = max(0, tile_rel >> 2);
-  wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv);
+  wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv, true);
   r.exact = (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
 }
 
