@@ -117,7 +117,10 @@ WRD void wr_tex_bases(const float* s0, int n0, const float* s1, int n1, const fl
 // reference's chunk-by-chunk accumulation equals base + m*step and needs no per-pixel replay
 // (integer and half-texel scale factors — 1:1, 2x video, device-pixel-ratio 2 — all land here).
 WRD bool wr_sum_exact(const float* base, float step) {
-  // any power-of-two grid g works: all values multiples of g and below 2^24 * g
+  // any power-of-two grid g works: all values multiples of g and below 2^24 * g.  The step decides
+  // almost always (a scale factor that is not a dyadic rational is on no grid): test it first.
+  const float s2 = step * 256.0f;
+  if (s2 != truncf(s2)) return false;
   const float grids[3] = {256.0f, 16.0f, 2.0f};
   for (int gi = 0; gi < 3; gi++) {
     const float g = grids[gi];
