@@ -82,6 +82,8 @@ struct CompositeYuvShader {
   struct Row {
     float o[6], step[6];
     int body_len, kb, frag_accum;
+    const float* chain;  // u running sums of every chunk of the span, from the setup kernel (see wr_yuv_chain_table)
+    int nch;
     PlaneRow p[3];
   };
   WRD_MEMBER const TexView& plane(const RasterArgs& a, int p) {
@@ -128,6 +130,27 @@ struct CompositeYuvShader {
         pr.maxv = wr_max(wr_linear_quantize(b[3], t.h), pr.minv);
       }
     }
+    r.chain = nullptr;
+    if (r.body_len && k.i[2] >= 0) {
+      // The setup kernel walked the u sums of this surface once (they are the same on every row of an
+      // axis-aligned surface, and v does not move along a row).  Valid for this row iff the row's
+      // start lanes and steps are bit-identical to the ones the table was built from.
+      const float* T = a.row_tab + k.i[2];
+      bool same = true;
+      for (int p = 0; p < planes; p++) {
+        for (int j = 0; j < 4; j++) same = same && __float_as_uint(q[p][0][j]) == __float_as_uint(__ldg(T + p * 4 + j));
+        same = same && __float_as_uint(st[p][0]) == __float_as_uint(__ldg(T + 12 + p)) && st[p][1] == 0.0f;
+      }
+      if (same) {
+        r.chain = T + 16;
+        r.nch = k.i[3];
+        for (int p = 0; p < 3; p++) {
+          for (int j = 0; j < 4; j++) { r.p[p].bu[j] = q[p][0][j]; r.p[p].bv[j] = q[p][1][j]; }
+          r.p[p].exact = 0;
+        }
+        return;
+      }
+    }
 #ifdef WRCU_HOSTEMU
     for (int p = 0; p < 3; p++) {
       wr_tex_seq_base(q[p][0], st[p][0], r.kb, r.p[p].bu);
@@ -168,7 +191,14 @@ struct CompositeYuvShader {
       for (int p = 0; p < planes; p++) {
         const PlaneRow& pr = r.p[p];
         const int m = (rel >> 2) - r.kb;
-        float qu = wr_sum_at(pr.bu[j], pr.ustep, m, pr.exact & 1), qv = wr_sum_at(pr.bv[j], pr.vstep, m, pr.exact & 2);
+        float qu, qv;
+        if (r.chain) {
+          qu = __ldg(r.chain + (size_t)(p * 4 + j) * r.nch + (rel >> 2));
+          qv = pr.bv[j];
+        } else {
+          qu = wr_sum_at(pr.bu[j], pr.ustep, m, pr.exact & 1);
+          qv = wr_sum_at(pr.bv[j], pr.vstep, m, pr.exact & 2);
+        }
         ii[p][0] = (int)wr_clamp(qu, pr.minu, pr.maxu);
         ii[p][1] = (int)wr_clamp(qv, pr.minv, pr.maxv);
       }
@@ -295,6 +325,65 @@ WRD YuvFixed wr_yuv_fixed_from(const float* bias, const float* m, int rescale) {
   return o;
 }
 
+// The u running sums of a video surface, once per command instead of once per (row, tile).
+// blendYUVFallback advances each plane's quantised uv by uv_step per 4-pixel chunk from the span
+// start; a tile in the middle of a 4K-wide span needs the sum after up to 959 additions.  For an
+// axis-aligned surface the start lanes and the step of u are the same on every row and v does not
+// change along a row, so the whole u sequence — 12 chains (3 planes x 4 chunk lanes) x one value per
+// chunk — is walked here with plain additions (the reference's own sequence) into the row-table
+// pool.  Header: the 12 start lanes + 3 steps the table was built from; the raster kernel uses the
+// table only on rows whose own start lanes and steps are bit-identical.
+WRD void wr_yuv_chain_table(const SetupArgs& a, int idx, int planes, const TexView* const* tv) {
+  const CmdHot h = a.hot[idx];
+  CmdCold& k = a.cold[idx];
+  if (!a.row_tab || (h.flags & CMD_GENERAL) || h.x1 <= h.x0) return;
+  const int len = (int)h.x1 - (int)h.x0;
+  if (len < 4) return;
+  const int nch = (len >> 2) + 1;
+  const int need = 16 + 12 * nch;
+  const int off = atomicAdd(&a.info->row_alloc, need);
+  if (off < 0 || off + need > a.row_cap) return;  // pool exhausted: the raster kernel walks the sums itself
+  // the first row's interpolants, as wr_row_interp computes them (rows = 0)
+  float o[6], step[6];
+  {
+    float y0c = (float)h.y0 + 0.5f;
+    float dy = __fsub_rn(y0c, k.yt);
+    float stepScale = __fdiv_rn(1.0f, __fsub_rn(k.xr, k.xl));
+    if (!isfinite(stepScale)) stepScale = 0.0f;
+    float x0f = __fsub_rn(__fadd_rn((float)h.x0, 0.5f), k.xl);
+    for (int i = 0; i < 6; i++) {
+      float sl = __fmul_rn(__fsub_rn(k.i_lb[i], k.i_lt[i]), k.yscale);
+      float sr = __fmul_rn(__fsub_rn(k.i_rb[i], k.i_rt[i]), k.yscale);
+      float li = __fadd_rn(k.i_lt[i], __fmul_rn(dy, sl));
+      float ri = __fadd_rn(k.i_rt[i], __fmul_rn(dy, sr));
+      float st = __fmul_rn(__fsub_rn(ri, li), stepScale);
+      step[i] = st;
+      o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
+    }
+  }
+  float* T = a.row_tab + off;
+  float v[12], st[3];
+  for (int j = 0; j < 4; j++) {
+    float uv[6];
+    wr_interp_at<6>(o, step, j, uv);
+    for (int p = 0; p < 3; p++) v[p * 4 + j] = p < planes ? wr_linear_quantize(uv[2 * p], tv[p]->w) : 0.0f;
+  }
+  for (int p = 0; p < 3; p++) st[p] = 4.0f * (v[p * 4 + 1] - v[p * 4 + 0]);
+  for (int q = 0; q < 12; q++) T[q] = v[q];
+  for (int p = 0; p < 3; p++) T[12 + p] = st[p];
+  T[15] = 0.0f;
+  float* C = T + 16;
+  for (int m = 0; m < nch; m++) {
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+      C[(size_t)q * nch + m] = v[q];
+      v[q] = v[q] + st[q >> 2];
+    }
+  }
+  k.i[2] = off;
+  k.i[3] = nch;
+}
+
 // composite vertex stage, YUV branch (composite.glsl:73-130)
 WRD void wr_setup_composite_yuv_one(const SetupArgs& a, int idx) {
   const float* f = (const float*)(a.instances + (size_t)idx * a.stride);
@@ -350,6 +439,9 @@ WRD void wr_setup_composite_yuv_one(const SetupArgs& a, int idx) {
     mi[4] = m.y_coeff; mi[5] = m.y_bias; mi[6] = m.uv_bias; mi[7] = m.br_y_mask;
     k->i[0] = format;
     k->i[1] = planes;
+    k->i[2] = -1;
+    k->i[3] = 0;
+    wr_yuv_chain_table(a, idx, planes, tv);
   }
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);
