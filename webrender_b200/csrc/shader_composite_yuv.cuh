@@ -333,6 +333,29 @@ WRD YuvFixed wr_yuv_fixed_from(const float* bias, const float* m, int rescale) {
 // chunk — is walked here with plain additions (the reference's own sequence) into the row-table
 // pool.  Header: the 12 start lanes + 3 steps the table was built from; the raster kernel uses the
 // table only on rows whose own start lanes and steps are bit-identical.
+// One of the 24 half-chains of command idx: chain q = part % 12 (plane q / 4, chunk lane q % 4), half
+// part / 12.  The second half starts from the exact sum at its first chunk (wr_repeat_add), then both
+// proceed by plain additions.
+WRD void wr_yuv_chain_fill(const SetupArgs& a, int idx, int part) {
+  const CmdCold& k = a.cold[idx];
+  float* T = a.row_tab + k.i[2];
+  const int nch = k.i[3], q = part % 12, half = part / 12;
+#ifdef WRCU_HOSTEMU
+  const int m0 = 0, m1 = nch;
+  if (half) return;
+#else
+  const int mid = nch >> 1;
+  const int m0 = half ? mid : 0, m1 = half ? nch : mid;
+#endif
+  const float st = T[12 + (q >> 2)];
+  float v = wr_repeat_add(T[q], st, m0);
+  float* C = T + 16 + (size_t)q * nch;
+  for (int m = m0; m < m1; m++) {
+    C[m] = v;
+    v = v + st;
+  }
+}
+
 WRD void wr_yuv_chain_table(const SetupArgs& a, int idx, int planes, const TexView* const* tv) {
   const CmdHot h = a.hot[idx];
   CmdCold& k = a.cold[idx];
@@ -372,16 +395,11 @@ WRD void wr_yuv_chain_table(const SetupArgs& a, int idx, int planes, const TexVi
   for (int q = 0; q < 12; q++) T[q] = v[q];
   for (int p = 0; p < 3; p++) T[12 + p] = st[p];
   T[15] = 0.0f;
-  float* C = T + 16;
-  for (int m = 0; m < nch; m++) {
-#pragma unroll
-    for (int q = 0; q < 12; q++) {
-      C[(size_t)q * nch + m] = v[q];
-      v[q] = v[q] + st[q >> 2];
-    }
-  }
   k.i[2] = off;
   k.i[3] = nch;
+#ifdef WRCU_HOSTEMU
+  for (int q = 0; q < 12; q++) wr_yuv_chain_fill(a, idx, q);
+#endif
 }
 
 // composite vertex stage, YUV branch (composite.glsl:73-130)
@@ -448,4 +466,24 @@ WRD void wr_setup_composite_yuv_one(const SetupArgs& a, int idx) {
     atomicAdd(a.err_counter, 1);
   }
 }
+#ifdef WRCU_HOSTEMU
 WR_SETUP_KERNEL(wr_setup_composite_yuv)
+#else
+// WR_SETUP_KERNEL plus the chain tables: after its 32 instances are emitted the warp fills the table of
+// each in turn, 24 lanes on the 12 chains x 2 halves (a single thread would take ~70 us for a 4K span).
+__global__ void wr_setup_composite_yuv(SetupArgs a) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) wr_reset_batch_info(a.info_next);
+  if (idx < a.n) wr_setup_composite_yuv_one(a, idx);
+  __syncwarp();
+  wr_fill_row_tables_warp(a, idx);
+  const int lane = threadIdx.x & 31, wbase = idx - lane;
+  const bool has = idx < a.n && a.hot[idx].x1 > a.hot[idx].x0 && a.cold[idx].i[2] >= 0;
+  unsigned m = __ballot_sync(0xFFFFFFFFu, has);
+  while (m) {
+    const int src = __ffs((int)m) - 1;
+    m &= m - 1;
+    if (lane < 24) wr_yuv_chain_fill(a, wbase + src, lane);
+  }
+}
+#endif

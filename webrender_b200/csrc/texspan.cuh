@@ -87,6 +87,10 @@ WRD float wr_sel4(const float* a, int j) { return j == 0 ? a[0] : (j == 1 ? a[1]
 // `coop` must be false wherever lanes arrive with different arguments (per-pixel callers).
 WRD void wr_tex_bases(const float* s0, int n0, const float* s1, int n1, const float* s2, int n2, float ustep,
                       const float* sv, int nv, float vstep, float (*bu)[4], float* bv, bool coop) {
+  if ((n0 | n1 | n2 | nv) == 0) {  // first tile of a span (every glyph): nothing to walk
+    for (int j = 0; j < 4; j++) { bu[0][j] = s0[j]; bu[1][j] = s1[j]; bu[2][j] = s2[j]; bv[j] = sv[j]; }
+    return;
+  }
 #ifndef WRCU_HOSTEMU
   if (!coop)
 #endif
@@ -194,7 +198,8 @@ WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int 
                  s2, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv, coop);
     r.kb[0] = min(r.kb[0], r.before >> 2);
     r.kb[1] = min(r.kb[1], r.inside >> 2);
-    r.exact = (r.before > 0 && wr_sum_exact(r.bu[0], r.ustep) ? 1 : 0) |
+    r.exact = body_len <= 32 ? 0 :  // short spans: the replay is at most 8 additions, not worth the test
+              (r.before > 0 && wr_sum_exact(r.bu[0], r.ustep) ? 1 : 0) |
               (r.inside > 0 && r.filter == LF_UPSCALE && wr_sum_exact(r.bu[1], r.ustep) ? 2 : 0) |
               (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
   }
@@ -230,7 +235,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
       for (int j = 0; j < 4; j++) { r.qu[j] = u[j] * (float)t.w; r.qv[j] = v[j] * (float)t.h; }
       r.kb[2] = r.nsolid ? 0 : max(0, tile_rel >> 2);
       wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], ustep, r.qv, r.kb[2], vstep, r.bu, r.bv, coop);
-      r.exact = (wr_sum_exact(r.bu[2], ustep) ? 4 : 0) | (wr_sum_exact(r.bv, vstep) ? 8 : 0);
+      r.exact = body_len <= 32 ? 0 : (wr_sum_exact(r.bu[2], ustep) ? 4 : 0) | (wr_sum_exact(r.bv, vstep) ? 8 : 0);
       return;
     }
   }
@@ -283,7 +288,7 @@ WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len
   r.maxv = wr_max(wr_linear_quantize(bounds[3], t.h), r.minv);
   r.kb[2] = max(0, tile_rel >> 2);
   wr_tex_bases(r.qu, 0, r.qu, 0, r.qu, r.kb[2], r.ustep, r.qv, r.kb[2], r.vstep, r.bu, r.bv, true);
-  r.exact = (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
+  r.exact = body_len <= 32 ? 0 : (wr_sum_exact(r.bu[2], r.ustep) ? 4 : 0) | (wr_sum_exact(r.bv, r.vstep) ? 8 : 0);
 }
 
 // Source texel (before colour modulation) of body pixel `rel` (0-based in the span).
