@@ -497,6 +497,10 @@ static void wr_raster_solid_premult(const RasterArgs& a) {
   }
 }
 #else
+// Shaders whose Row holds only warp-uniform state (nothing computed for "this lane's pixels") may have
+// narrow spans shaded one pixel per lane (see wr_raster_tile).
+template <class S> struct WrNarrowSpans { enum { v = 0 }; };
+
 // ---- the generic tile kernel (any command kind via the shader policy S, any
 // blend key).  S::row_setup computes per-(command,row) constants once per warp
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
@@ -627,11 +631,45 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       }
       typename S::Row row;
       S::row_setup(a, c, y, tx0, FMT == WRCU_FMT_RGBA8, row);
+      const int nxs = max((int)c.x0, tx0), nw = min((int)c.x1, tx0 + WRCU_TILE_W) - nxs;
+      if (WrNarrowSpans<S>::v && nw <= 32) {
+        // Narrow span (a glyph row is ~12 pixels): with 4 pixels per lane only 3-4 lanes would work
+        // through four pixel slots.  Instead lane i takes pixel nxs + i: the destination pixels are
+        // gathered from their owners, shaded in ONE slot, and scattered back.  (Only for shaders
+        // whose Row is warp-uniform — S::source must not depend on which lane asks.)
+        const int gx = nxs + lane - tx0;  // tile-relative pixel of this lane
+        const int owner = (gx >> 2) & 31, slot = gx & 3;
+        uint32_t g0 = __shfl_sync(0xFFFFFFFFu, px[0], owner), g1 = __shfl_sync(0xFFFFFFFFu, px[1], owner);
+        uint32_t g2 = __shfl_sync(0xFFFFFFFFu, px[2], owner), g3 = __shfl_sync(0xFFFFFFFFu, px[3], owner);
+        uint32_t mypx = slot == 0 ? g0 : (slot == 1 ? g1 : (slot == 2 ? g2 : g3));
+        uint32_t myz = 0;
+        if (use_depth) {
+          uint32_t z0 = __shfl_sync(0xFFFFFFFFu, zb[0], owner), z1 = __shfl_sync(0xFFFFFFFFu, zb[1], owner);
+          uint32_t z2 = __shfl_sync(0xFFFFFFFFu, zb[2], owner), z3 = __shfl_sync(0xFFFFFFFFu, zb[3], owner);
+          myz = slot == 0 ? z0 : (slot == 1 ? z1 : (slot == 2 ? z2 : z3));
+        }
+        bool d1 = false, zd1 = false;
+        if (lane < nw) wr_shade_pixel<S, FMT>(a, c, row, nxs + lane, y, use_depth, mypx, myz, d1, zd1);
+        const unsigned dmask = __ballot_sync(0xFFFFFFFFu, d1), zmask = __ballot_sync(0xFFFFFFFFu, zd1);
+        if (dmask | zmask) {
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            const int from = x + p - nxs;  // lane that shaded this pixel
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, mypx, from & 31);
+            const uint32_t vz = use_depth ? __shfl_sync(0xFFFFFFFFu, myz, from & 31) : 0u;
+            if (from >= 0 && from < nw) {
+              if ((dmask >> from) & 1u) { px[p] = v; dirty = true; }
+              if ((zmask >> from) & 1u) { zb[p] = vz; zdirty = true; }
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         int xx = x + p;
         if (xx < c.x0 || xx >= c.x1) continue;
         wr_shade_pixel<S, FMT>(a, c, row, xx, y, use_depth, px[p], zb[p], dirty, zdirty);
+      }
       }
     }
   }

@@ -56,4 +56,5 @@ struct TextShader {
 
 #ifndef WRCU_HOSTEMU
 template <> struct WrMinCtas<TextShader> { enum { v = 3 }; };
+template <> struct WrNarrowSpans<TextShader> { enum { v = 1 }; };  // glyph rows: ~12 pixels of a 128-pixel warp row
 #endif
