@@ -88,7 +88,9 @@ typedef enum wrcu_kind {
   WRCU_KIND_BORDER_SOLID = 21,         /* cs_border_solid                  */
   WRCU_KIND_BORDER_SEGMENT = 22,       /* cs_border_segment                */
   WRCU_KIND_QUAD_RADIAL_GRADIENT = 23, /* ps_quad_radial_gradient          */
-  WRCU_KIND_QUAD_CONIC_GRADIENT = 24   /* ps_quad_conic_gradient           */
+  WRCU_KIND_QUAD_CONIC_GRADIENT = 24,  /* ps_quad_conic_gradient           */
+  WRCU_KIND_BRUSH_YUV_IMAGE = 25       /* brush_yuv_image [ALPHA_PASS] YUV: BrushBatchKind::YuvImage
+                                          (batch.rs:60-86), planes in color[0..2]  */
 } wrcu_kind;
 
 /* Shader feature bits (webrender_build/src/shader_features.rs:64-247). */

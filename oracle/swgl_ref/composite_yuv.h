@@ -62,33 +62,9 @@ struct composite_yuv_vert : VertexShaderImpl, WrCommon {
     return vec4_scalar(0.0f, narrow.y, identity.z, identity.w);
   }
 
-  // yuv.glsl:163-178
-  void write_uv_rect(vec2_scalar uv0, vec2_scalar uv1, vec2 f, vec2_scalar texture_size, vec2& uv,
-                     vec4_scalar& uv_bounds) {
-    uv = mix(vec2(uv0), vec2(uv1), f);
-    uv_bounds = make_vec4(uv0 + vec2_scalar(0.5f), uv1 - vec2_scalar(0.5f));
-    uv /= vec2(texture_size);
-    uv_bounds /= texture_size.sel(X, Y, X, Y);
-  }
-
-  // composite.glsl:73-130 (YUV branch)
-  void main() {
-    vec4_scalar device_rect = mix(aDeviceRect, aDeviceRect.sel(Z, W, X, Y), aFlip.sel(X, Y, X, Y));
-    vec2 world_pos = mix(device_rect.sel(X, Y), device_rect.sel(Z, W), aPosition);
-    vec2 clipped_world_pos = clamp(world_pos, vec2(aDeviceClipRect.sel(X, Y)), vec2(aDeviceClipRect.sel(Z, W)));
-    vec2 uv = (clipped_world_pos - vec2(device_rect.sel(X, Y))) / vec2(device_rect.sel(Z, W) - device_rect.sel(X, Y));
-
-    // fetch_yuv_primitive (composite.glsl:63-70)
-    int color_space = int(aParams.y);
-    int yuv_format = int(aParams.z);
-    int channel_bit_depth = int(aParams.w);
-
-    vRescaleFactor = 0;
-    if (channel_bit_depth > 8 && yuv_format != 1 /* YUV_FORMAT_P010 */) {
-      vRescaleFactor = 16 - channel_bit_depth;
-    }
-
-    // get_yuv_color_info (yuv.glsl:98-142)
+  // get_yuv_color_info + get_rgb_from_ycbcr_info (yuv.glsl:98-161)
+  static void color_matrix(int color_space, int yuv_format, int channel_bit_depth, vec3_scalar& vYcbcrBias,
+                           mat3_scalar& vRgbFromDebiasedYcbcr) {
     float channel_max = 255.0f;
     if (channel_bit_depth > 8) {
       if (yuv_format == 1) channel_max = float((1 << channel_bit_depth) - 1);
@@ -120,6 +96,35 @@ struct composite_yuv_vert : VertexShaderImpl, WrCommon {
     mat3_scalar yuv_from_debiased_ycbcr(vec3_scalar(scale.x, 0.0f, 0.0f), vec3_scalar(0.0f, scale.y, 0.0f),
                                         vec3_scalar(0.0f, 0.0f, scale.y));
     vRgbFromDebiasedYcbcr = rgb_from_yuv * yuv_from_debiased_ycbcr;
+  }
+
+  // yuv.glsl:163-178
+  void write_uv_rect(vec2_scalar uv0, vec2_scalar uv1, vec2 f, vec2_scalar texture_size, vec2& uv,
+                     vec4_scalar& uv_bounds) {
+    uv = mix(vec2(uv0), vec2(uv1), f);
+    uv_bounds = make_vec4(uv0 + vec2_scalar(0.5f), uv1 - vec2_scalar(0.5f));
+    uv /= vec2(texture_size);
+    uv_bounds /= texture_size.sel(X, Y, X, Y);
+  }
+
+  // composite.glsl:73-130 (YUV branch)
+  void main() {
+    vec4_scalar device_rect = mix(aDeviceRect, aDeviceRect.sel(Z, W, X, Y), aFlip.sel(X, Y, X, Y));
+    vec2 world_pos = mix(device_rect.sel(X, Y), device_rect.sel(Z, W), aPosition);
+    vec2 clipped_world_pos = clamp(world_pos, vec2(aDeviceClipRect.sel(X, Y)), vec2(aDeviceClipRect.sel(Z, W)));
+    vec2 uv = (clipped_world_pos - vec2(device_rect.sel(X, Y))) / vec2(device_rect.sel(Z, W) - device_rect.sel(X, Y));
+
+    // fetch_yuv_primitive (composite.glsl:63-70)
+    int color_space = int(aParams.y);
+    int yuv_format = int(aParams.z);
+    int channel_bit_depth = int(aParams.w);
+
+    vRescaleFactor = 0;
+    if (channel_bit_depth > 8 && yuv_format != 1 /* YUV_FORMAT_P010 */) {
+      vRescaleFactor = 16 - channel_bit_depth;
+    }
+
+    color_matrix(color_space, yuv_format, channel_bit_depth, vYcbcrBias, vRgbFromDebiasedYcbcr);
     vYuvFormat.x = yuv_format;
 
     write_uv_rect(aUvRect0.sel(X, Y), aUvRect0.sel(Z, W), uv, make_vec2(textureSize(sColor0, 0)), vUV_y, vUVBounds_y);

@@ -16,6 +16,7 @@
 #include "cs_clip_box_shadow.h"
 #include "composite.h"
 #include "composite_yuv.h"
+#include "brush_yuv_image.h"
 #include "brush_opacity.h"
 #include "ps_clear.h"
 #include "brush_blend.h"
@@ -47,6 +48,9 @@ ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "composite TEXTURE_2D")) return composite_TEXTURE_2D_program::loader;
   if (!strcmp(name, "composite FAST_PATH,TEXTURE_2D")) return composite_FAST_PATH_TEXTURE_2D_program::loader;
   if (!strcmp(name, "composite TEXTURE_2D,YUV")) return composite_TEXTURE_2D_YUV_program::loader;
+  if (!strcmp(name, "brush_yuv_image TEXTURE_2D,YUV")) return brush_yuv_image_TEXTURE_2D_YUV_program::loader;
+  if (!strcmp(name, "brush_yuv_image ALPHA_PASS,TEXTURE_2D,YUV")) return brush_yuv_image_ALPHA_PASS_TEXTURE_2D_YUV_program::loader;
+  if (!strcmp(name, "brush_yuv_image ALPHA_PASS,ANTIALIASING,TEXTURE_2D,YUV")) return brush_yuv_image_ALPHA_PASS_ANTIALIASING_TEXTURE_2D_YUV_program::loader;
   if (!strcmp(name, "brush_opacity")) return brush_opacity_program::loader;
   if (!strcmp(name, "brush_opacity ALPHA_PASS")) return brush_opacity_ALPHA_PASS_program::loader;
   if (!strcmp(name, "brush_opacity ALPHA_PASS,ANTIALIASING")) return brush_opacity_ALPHA_PASS_ANTIALIASING_program::loader;

@@ -69,6 +69,9 @@ CASES = [
     ("composite_yuv_nv12_rec601_full", "yuv_composite_frame", dict(fmt="nv12", color_space=1, seed=2, fractional=True)),
     ("composite_yuv_interleaved_rec2020", "yuv_composite_frame", dict(fmt="interleaved", color_space=4, seed=3)),
     ("composite_yuv_planar_nearest_gbr", "yuv_composite_frame", dict(fmt="planar", color_space=6, seed=4, linear=False)),
+    ("brush_yuv_image_nv12_alpha", "yuv_image_frame", dict(fmt="nv12", color_space=2, seed=1)),
+    ("brush_yuv_image_planar_opaque", "yuv_image_frame", dict(fmt="planar", color_space=0, seed=2, alpha_pass=False)),
+    ("brush_yuv_image_interleaved_rotated", "yuv_image_frame", dict(fmt="interleaved", color_space=3, seed=3, rotate=17.0)),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

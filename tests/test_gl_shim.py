@@ -66,6 +66,7 @@ CASES = [
     ("box_shadows", lambda: scenes.box_shadow_frame(seed=1), None),
     ("composite", lambda: scenes.composite_frame(seed=1), ["fb"]),
     ("composite_yuv_nv12", lambda: scenes.yuv_composite_frame("nv12", 3, seed=2), ["fb"]),
+    ("brush_yuv_image", lambda: scenes.yuv_image_frame("planar", 1, seed=2, fractional=True), ["target"]),
     ("composite_yuv_planar", lambda: scenes.yuv_composite_frame("planar", 4, seed=3, fractional=True), ["fb"]),
     ("blur", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
     ("texture_cache_target", lambda: scenes.texture_cache_frame(seed=1), None),

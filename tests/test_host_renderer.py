@@ -44,6 +44,7 @@ CASES = [
     ("composite", lambda: scenes.composite_frame(seed=1), ["fb"]),
     ("composite_yuv_planar", lambda: scenes.yuv_composite_frame("planar", 2, seed=1), ["fb"]),
     ("composite_yuv_nv12", lambda: scenes.yuv_composite_frame("nv12", 0, seed=2, opaque=False), ["fb"]),
+    ("brush_yuv_image", lambda: scenes.yuv_image_frame("nv12", 2, seed=1), ["target"]),
     ("blur_a8", lambda: scenes.blur_frame(seed=1), ["mid", "target"]),
     ("blur_rgba8", lambda: scenes.blur_frame(seed=2, color=True), ["mid", "target"]),
     ("scale", lambda: scenes.scale_frame(seed=1), ["target"]),

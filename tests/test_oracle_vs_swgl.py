@@ -167,6 +167,24 @@ def test_composite_yuv_variants(fmt, variant):
     assert_same(render(SwglDevice, f, ["fb"]), render(OracleDevice, f, ["fb"]), variant)
 
 
+YUV_IMAGE_VARIANTS = ["alpha", "opaque", "fractional", "nearest", "rotated"]
+
+
+def _yuv_image_frame(fmt, variant, color_space=2):
+    return scenes.yuv_image_frame(fmt, color_space, seed=1 + color_space, linear=variant != "nearest",
+                                  alpha_pass=variant != "opaque", fractional=variant == "fractional",
+                                  rotate=17.0 if variant == "rotated" else None)
+
+
+@pytest.mark.parametrize("variant", YUV_IMAGE_VARIANTS)
+@pytest.mark.parametrize("fmt", YUV_FORMATS)
+def test_brush_yuv_image(fmt, variant):
+    """Brush(YuvImage) (brush_yuv_image.glsl): video frames as primitives — opaque and alpha pass, AA edges,
+    clip masks, a rotated spatial node, NEAREST planes (fragment path with sample_yuv's ALPHA_PASS clamp)."""
+    f = _yuv_image_frame(fmt, variant, 5 if variant == "fractional" else 2)
+    assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
 OPACITY_VARIANTS = ["scaled", "fractional", "one_to_one", "nearest"]
 
 

@@ -23,7 +23,7 @@ NEAREST, LINEAR = 0, 1
  KIND_COMPOSITE, KIND_CLEAR, KIND_BLUR, KIND_SCALE,
  KIND_FAST_LINEAR_GRADIENT, KIND_LINEAR_GRADIENT, KIND_RADIAL_GRADIENT, KIND_CONIC_GRADIENT,
  KIND_LINE_DECORATION, KIND_BORDER_SOLID, KIND_BORDER_SEGMENT,
- KIND_QUAD_RADIAL_GRADIENT, KIND_QUAD_CONIC_GRADIENT) = range(1, 25)
+ KIND_QUAD_RADIAL_GRADIENT, KIND_QUAD_CONIC_GRADIENT, KIND_BRUSH_YUV_IMAGE) = range(1, 26)
 
 KIND_PROGRAM = {
     KIND_QUAD_TEXTURED: "ps_quad_textured",
@@ -50,6 +50,7 @@ KIND_PROGRAM = {
     KIND_BORDER_SEGMENT: "cs_border_segment",
     KIND_QUAD_RADIAL_GRADIENT: "ps_quad_radial_gradient",
     KIND_QUAD_CONIC_GRADIENT: "ps_quad_conic_gradient",
+    KIND_BRUSH_YUV_IMAGE: "brush_yuv_image",
 }
 
 FEAT_ALPHA_PASS = 1 << 0

@@ -12,6 +12,7 @@
 #pragma once
 #include "raster.cuh"
 #include "setup_common.cuh"
+#include "setup_brush.cuh"
 #include "texspan.cuh"
 
 // textureLinearPlanarRG8 for one lane (texture.h:589-638)
@@ -72,7 +73,8 @@ WRD Px wr_yuv_convert(const YuvFixed& m, int y, int u, int v) {
 }
 
 // CmdCold: g[0..11] vUVBounds_y/u/v, g[12..14] vYcbcrBias, g[15..23] vRgbFromDebiasedYcbcr
-// (column-major), g[24..31] YuvFixed (int bits); i[0] = vYuvFormat.x, i[1] = planes
+// (column-major), g[24..31] YuvFixed (int bits), g[32] != 0: clamp rgb (brush_yuv_image ALPHA_PASS,
+// yuv.glsl:239-243); i[0] = vYuvFormat.x, i[1] = planes, i[2..3] the u chain table
 struct CompositeYuvShader {
   struct PlaneRow {
     float bu[4], bv[4];  // quantised uv lanes of chunk kb
@@ -261,6 +263,8 @@ struct CompositeYuvShader {
     float col[3];
     for (int q = 0; q < 3; q++)
       col[q] = __fadd_rn(__fadd_rn(__fmul_rn(k.g[15 + q], dv[0]), __fmul_rn(k.g[18 + q], dv[1])), __fmul_rn(k.g[21 + q], dv[2]));
+    if (k.g[32] != 0.0f)
+      for (int q = 0; q < 3; q++) col[q] = wr_clamp(col[q], 0.0f, 1.0f);
     Px o;
     o.r = wr_round_pixel(col[0], 255.0f) & 0xFFFF;
     o.g = wr_round_pixel(col[1], 255.0f) & 0xFFFF;
@@ -459,6 +463,7 @@ WRD void wr_setup_composite_yuv_one(const SetupArgs& a, int idx) {
     k->i[1] = planes;
     k->i[2] = -1;
     k->i[3] = 0;
+    k->g[32] = 0.0f;
     wr_yuv_chain_table(a, idx, planes, tv);
   }
   if (unsupported) {
@@ -466,24 +471,88 @@ WRD void wr_setup_composite_yuv_one(const SetupArgs& a, int idx) {
     atomicAdd(a.err_counter, 1);
   }
 }
-#ifdef WRCU_HOSTEMU
-WR_SETUP_KERNEL(wr_setup_composite_yuv)
-#else
 // WR_SETUP_KERNEL plus the chain tables: after its 32 instances are emitted the warp fills the table of
 // each in turn, 24 lanes on the 12 chains x 2 halves (a single thread would take ~70 us for a 4K span).
-__global__ void wr_setup_composite_yuv(SetupArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) wr_reset_batch_info(a.info_next);
-  if (idx < a.n) wr_setup_composite_yuv_one(a, idx);
-  __syncwarp();
-  wr_fill_row_tables_warp(a, idx);
-  const int lane = threadIdx.x & 31, wbase = idx - lane;
-  const bool has = idx < a.n && a.hot[idx].x1 > a.hot[idx].x0 && a.cold[idx].i[2] >= 0;
-  unsigned m = __ballot_sync(0xFFFFFFFFu, has);
-  while (m) {
-    const int src = __ffs((int)m) - 1;
-    m &= m - 1;
-    if (lane < 24) wr_yuv_chain_fill(a, wbase + src, lane);
+#ifdef WRCU_HOSTEMU
+#define WR_SETUP_KERNEL_YUV(name) WR_SETUP_KERNEL(name)
+#else
+#define WR_SETUP_KERNEL_YUV(name)                                                              \
+  __global__ void name(SetupArgs a) {                                                          \
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;                                           \
+    if (idx == 0) wr_reset_batch_info(a.info_next);                                            \
+    if (idx < a.n) name##_one(a, idx);                                                         \
+    __syncwarp();                                                                              \
+    wr_fill_row_tables_warp(a, idx);                                                           \
+    const int lane = threadIdx.x & 31, wbase = idx - lane;                                     \
+    const bool has = idx < a.n && a.hot[idx].x1 > a.hot[idx].x0 && a.cold[idx].i[2] >= 0;      \
+    unsigned m = __ballot_sync(0xFFFFFFFFu, has);                                              \
+    while (m) {                                                                                \
+      const int src = __ffs((int)m) - 1;                                                       \
+      m &= m - 1;                                                                              \
+      if (lane < 24) wr_yuv_chain_fill(a, wbase + src, lane);                                  \
+    }                                                                                          \
   }
-}
 #endif
+WR_SETUP_KERNEL_YUV(wr_setup_composite_yuv)
+
+// brush_yuv_image vertex stage (brush_yuv_image.glsl:41-93): BrushBatchKind::YuvImage — video frames drawn
+// as primitives inside a picture.  The brush vertex stage, then fetch_yuv_primitive / write_uv_rect; the
+// fragment and span stages are composite's (CompositeYuvShader).
+WRD void wr_setup_brush_yuv_image_one(const SetupArgs& a, int idx) {
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  QuadOut q;
+  BrushVS vs;
+  memset(&q, 0, sizeof q);
+  wr_brush_vertex(a, aData, 1, q, vs);
+  const FrameTablesDev& T = a.tabs;
+  float4 data = wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.ph.specific_prim_address);
+  int bit_depth = (int)data.x, color_space = (int)data.y, format = (int)data.z;
+  int planes = format == 3 ? 3 : (format == 0 ? 2 : (format == 4 ? 1 : 0));
+  const TexView* tv[3] = {&a.color0, &a.color1, &a.color2};
+  bool bad = bit_depth != 8 || planes == 0;
+  for (int p = 0; p < planes; p++) bad = bad || !tv[p]->ptr;
+  if (bad) {
+    a.hot[idx] = CmdHot{};
+    wr_finish_setup(a, 1);
+    return;
+  }
+  const float* lr = vs.ph.lr;
+  float4 uvr[3];
+  for (int p = 0; p < 3; p++) uvr[p] = p < planes ? wr_fetch(T.gpu_cache, T.n_gpu_cache, vs.ph.user_data[p]) : make_float4(0, 0, 0, 0);
+  for (int kx = 0; kx < 4; kx++) {
+    float fx = (vs.local_pos[kx].x - lr[0]) / (lr[2] - lr[0]);
+    float fy = (vs.local_pos[kx].y - lr[1]) / (lr[3] - lr[1]);
+    for (int p = 0; p < planes; p++) {
+      q.interp[kx][2 * p] = ((uvr[p].z - uvr[p].x) * fx + uvr[p].x) / (float)tv[p]->w;
+      q.interp[kx][2 * p + 1] = ((uvr[p].w - uvr[p].y) * fy + uvr[p].y) / (float)tv[p]->h;
+    }
+  }
+  q.n_interp = 6;
+  q.flags |= CMD_TEXTURED;
+  q.col[0] = q.col[1] = q.col[2] = q.col[3] = 255;
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    for (int p = 0; p < 3; p++) {
+      float tw = (float)tv[p]->w, th = (float)tv[p]->h;
+      k->g[4 * p + 0] = (uvr[p].x + 0.5f) / tw;
+      k->g[4 * p + 1] = (uvr[p].y + 0.5f) / th;
+      k->g[4 * p + 2] = (uvr[p].z - 0.5f) / tw;
+      k->g[4 * p + 3] = (uvr[p].w - 0.5f) / th;
+    }
+    wr_yuv_color_matrix(color_space, format, bit_depth, &k->g[12], &k->g[15]);
+    YuvFixed m = wr_yuv_fixed_from(&k->g[12], &k->g[15], 0);
+    int* mi = (int*)(k->g + 24);
+    mi[0] = m.bu; mi[1] = m.rv; mi[2] = m.gu; mi[3] = m.gv;
+    mi[4] = m.y_coeff; mi[5] = m.y_bias; mi[6] = m.uv_bias; mi[7] = m.br_y_mask;
+    k->i[0] = format;
+    k->i[1] = planes;
+    k->i[2] = -1;
+    k->i[3] = 0;
+    k->g[32] = (a.features & WRCU_FEAT_ALPHA_PASS) ? 1.0f : 0.0f;
+    wr_yuv_chain_table(a, idx, planes, tv);
+  }
+  wr_finish_setup(a, unsupported);
+}
+WR_SETUP_KERNEL_YUV(wr_setup_brush_yuv_image)

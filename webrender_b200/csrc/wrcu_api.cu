@@ -973,6 +973,12 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       sa.features = features;
       WR_LAUNCH(wr_setup_brush_opacity, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_BRUSH_YUV_IMAGE:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_yuv_image without sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_brush_yuv_image, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_COMPOSITE:
       if (stride < 120) return wrcu_fail(c, WRCU_ERR_INVALID, "CompositeInstance stride < 120");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "composite without sColor0");
@@ -1076,6 +1082,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
+    case WRCU_KIND_BRUSH_YUV_IMAGE: LAUNCH_RASTER(CompositeYuvShader); break;
     case WRCU_KIND_COMPOSITE:
       if (features & WRCU_FEAT_YUV) LAUNCH_RASTER(CompositeYuvShader);
       else LAUNCH_RASTER(CompositeShader);
@@ -1110,7 +1117,7 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"brush_linear_gradient", WRCU_KIND_BRUSH_LINEAR_GRADIENT}, {"brush_blend", WRCU_KIND_BRUSH_BLEND},
       {"brush_mix_blend", WRCU_KIND_BRUSH_MIX_BLEND}, {"brush_opacity", WRCU_KIND_BRUSH_OPACITY},
       {"ps_text_run", WRCU_KIND_TEXT_RUN}, {"cs_clip_rectangle", WRCU_KIND_CLIP_RECTANGLE},
-      {"cs_clip_box_shadow", WRCU_KIND_CLIP_BOX_SHADOW}, {"composite", WRCU_KIND_COMPOSITE},
+      {"cs_clip_box_shadow", WRCU_KIND_CLIP_BOX_SHADOW}, {"composite", WRCU_KIND_COMPOSITE}, {"brush_yuv_image", WRCU_KIND_BRUSH_YUV_IMAGE},
       {"ps_clear", WRCU_KIND_CLEAR}, {"cs_blur", WRCU_KIND_BLUR}, {"cs_scale", WRCU_KIND_SCALE},
       {"cs_fast_linear_gradient", WRCU_KIND_FAST_LINEAR_GRADIENT}, {"cs_linear_gradient", WRCU_KIND_LINEAR_GRADIENT},
       {"cs_radial_gradient", WRCU_KIND_RADIAL_GRADIENT}, {"cs_conic_gradient", WRCU_KIND_CONIC_GRADIENT},

@@ -36,6 +36,7 @@ enum class BatchKind {
   QuadColorOrTexture, QuadMask, BrushSolid, BrushImage, BrushBlend, BrushMixBlend, BrushLinearGradient,
   BrushOpacity, TextRun,
   QuadRadialGradient, QuadConicGradient,  // BatchKind::Quad(PatternKind::RadialGradient / ConicGradient), pattern.rs
+  BrushYuvImage,                          // BatchKind::Brush(BrushBatchKind::YuvImage(..)), batch.rs:60-86
 };
 // batch.rs BatchFeatures / shade.rs feature strings
 enum BatchFeatures : uint32_t {

@@ -1184,6 +1184,70 @@ def yuv_composite_frame(fmt="planar", color_space=2, seed=1, width=512, height=3
     return Frame(FrameTables().arrays(), textures, [[Target("fb", ops=ops)]])
 
 
+def yuv_image_frame(fmt="planar", color_space=2, seed=1, width=512, height=320, linear=True, alpha_pass=True,
+                    fractional=False, with_masks=True, rotate=None):
+    """Brush(YuvImage) batch (BrushBatchKind::YuvImage, batch.rs:60-86; prim_store/image.rs
+    YuvImageData::write_prim_gpu_blocks): video frames drawn as primitives inside a picture — prim data
+    [channel_bit_depth, colour space, format, 0], user data = the gpu-cache addresses of the planes'
+    ImageSource entries.  Opaque pass (blend off) or alpha pass (premultiplied blend; AA edges, clip
+    masks, optionally a rotated spatial node)."""
+    from .gpu_types import (brush_instance, CLIP_TASK_EMPTY, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12,
+                            YUV_FORMAT_INTERLEAVED)
+    rng = np.random.RandomState(seed * 17 + color_space)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    vw, vh = 192, 128
+    planes = yuv_planes(vw, vh, seed + 9, fmt)
+    filt = abi.LINEAR if linear else abi.NEAREST
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height)}
+    if fmt == "planar":
+        names, yuv_format, fmts = ("vy", "vu", "vv"), YUV_FORMAT_PLANAR, (abi.FMT_R8,) * 3
+    elif fmt == "nv12":
+        names, yuv_format, fmts = ("vy", "vuv", ""), YUV_FORMAT_NV12, (abi.FMT_R8, abi.FMT_RG8)
+    else:
+        names, yuv_format, fmts = ("vyuv", "", ""), YUV_FORMAT_INTERLEAVED, (abi.FMT_RGBA8,)
+    for nm, f, pl in zip(names, fmts, planes):
+        textures[nm] = TextureDesc(f, pl.shape[1] // abi.FMT_BPP[f], pl.shape[0], data=pl, filter=filt)
+    chroma = 1.0 if fmt == "interleaved" else 0.5
+    xf = 0
+    if rotate is not None:
+        xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0, 1.0, 0.9), axis_aligned=False)
+    if with_masks and alpha_pass:
+        mask = rng.randint(0, 256, size=(256, 256)).astype(np.uint8)
+        mask[rng.randint(0, 256, 40)[:, None], :] = 255
+        mask[:, rng.randint(0, 256, 40)] = 0
+        textures["mask"] = TextureDesc(abi.FMT_R8, 256, 256, data=mask, filter=abi.NEAREST)
+    inst = []
+    for i in range(7):
+        r = _rand_rect(rng, width, height, 40, 240, integer=not fractional)
+        ux, uy = float(2 * rng.randint(0, 30)), float(2 * rng.randint(0, 20))
+        if i == 0:
+            uw, uh = float(int(min(r[2] - r[0], vw - ux)) & ~1), float(int(min(r[3] - r[1], vh - uy)) & ~1)
+            r = (r[0], r[1], r[0] + uw, r[1] + uh)
+        else:
+            uw, uh = float(2 * rng.randint(10, 60)), float(2 * rng.randint(8, 40))
+        ry = (ux, uy, ux + uw, uy + uh)
+        rc = tuple(v * chroma for v in ry)
+        srcs = [t.push_gpu_cache([rr, (0.0, 0.0, 0.0, 0.0)]) for rr in (ry, rc, rc)]
+        spec = t.push_gpu_cache([(8.0, float(color_space), float(yuv_format), 0.0)])
+        clip = r if i % 3 else (r[0] + 4.0, r[1] + 3.0, r[2] - 6.0, r[3] - 2.0)
+        clip_task = CLIP_TASK_EMPTY
+        if with_masks and alpha_pass and i % 3 == 1:
+            w_, h_ = int(min(r[2] - r[0], 120)), int(min(r[3] - r[1], 100))
+            mx, my = int(rng.randint(0, 256 - w_)), int(rng.randint(0, 256 - h_))
+            clip_task = t.add_render_task((float(mx), float(my), float(mx + w_), float(my + h_)), 1.0,
+                                          (float(int(r[0])), float(int(r[1]))))
+        hdr = t.add_prim_header(r, clip, i + 1, spec, xf, pic, (srcs[0], srcs[1], srcs[2], 0))
+        edge = 0xF if (alpha_pass and (fractional or rotate is not None)) else 0
+        inst.append(brush_instance(hdr, clip_task, 0xFFFF, edge, 0, 0))
+    feats = abi.FEAT_TEXTURE_2D | abi.FEAT_YUV | (abi.FEAT_ALPHA_PASS if alpha_pass else 0)
+    ops = [Clear(color=(0.2, 0.3, 0.1, 1.0)),
+           Batch(abi.KIND_BRUSH_YUV_IMAGE, np.stack(inst),
+                 blend=abi.BLEND_PREMULTIPLIED_ALPHA if alpha_pass else abi.BLEND_NONE,
+                 features=feats, color=names, clip_mask="mask" if (with_masks and alpha_pass) else "")]
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
 def video_frame(width=3840, height=2160, vw=1920, vh=1080, fmt="nv12", color_space=2, seed=1):
     """One full-screen video surface: a vw x vh 8-bit YUV frame (NV12 by default, Rec.709 narrow
     range) scaled to the whole framebuffer by `composite` YUV — the compositor's video case."""
