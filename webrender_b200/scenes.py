@@ -1248,6 +1248,61 @@ def yuv_image_frame(fmt="planar", color_space=2, seed=1, width=512, height=320, 
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
 
 
+def reftest_yuv_frame(ref_dir="/root/reference/wrench/reftests/image"):
+    """wrench/reftests/image/yuv.yaml the way the frame builder draws it: three `yuv-image` items of 427x640 at
+    1:1 — planar (three R8 planes), interleaved (one BGRA image: Cb, Y, Cr in B, G, R) and NV12 with the CbCr
+    plane loaded as a BGRA image (wrench turns RGB PNGs into BGRA8: Cb in R, Cr in G — sampleYUV's RGBA8 branch,
+    swgl_ext.h:1069-1075) — Color8, Rec709, limited range (yaml_frame_reader.rs:1203-1206), as opaque
+    Brush(YuvImage) primitives on the white 1323x658 page.  Reads the reference's own plane PNGs."""
+    from PIL import Image
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED
+    import os
+
+    def load(name):
+        im = Image.open(os.path.join(ref_dir, name))
+        if im.mode == "L":
+            return abi.FMT_R8, np.array(im, dtype=np.uint8)
+        rgb = np.array(im.convert("RGB"), dtype=np.uint8)
+        bgra = np.concatenate([rgb[..., ::-1], np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
+        return abi.FMT_RGBA8, bgra.reshape(rgb.shape[0], rgb.shape[1] * 4)
+    from .gpu_types import composite_instance
+    W, H = 1323, 658
+    t = FrameTables()
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H)}
+    for nm, fn in (("y", "spacex-y.png"), ("u", "spacex-u.png"), ("v", "spacex-v.png"), ("uv", "spacex-uv.png"),
+                   ("yuv", "spacex-yuv.png")):
+        f, data = load(fn)
+        textures[nm] = TextureDesc(f, 427, 640, data=data, filter=abi.LINEAR)
+    items = [(10.0, YUV_FORMAT_PLANAR, ("y", "u", "v")), (447.0, YUV_FORMAT_INTERLEAVED, ("yuv", "", "")),
+             (887.0, YUV_FORMAT_NV12, ("y", "uv", ""))]
+    src = t.push_gpu_cache([(0.0, 0.0, 427.0, 640.0), (0.0, 0.0, 0.0, 0.0)])
+    # the page is a picture cache: 1024x512 tiles, each its own target with its own picture task (content origin =
+    # the tile's page position), every primitive drawn into every tile it touches — the edge walks restart per tile
+    tile_targets, comp = [], []
+    for ty in range(2):
+        for tx in range(2):
+            name = "tile%d%d" % (ty, tx)
+            textures[name] = TextureDesc(abi.FMT_RGBA8, 1024, 512)
+            pic = t.add_render_task((0.0, 0.0, 1024.0, 512.0), 1.0, (1024.0 * tx, 512.0 * ty))
+            ops = [Clear(color=(1.0, 1.0, 1.0, 1.0))]
+            for i, (x0, fmt, names) in enumerate(items):
+                r = (x0, 10.0, x0 + 427.0, 650.0)
+                if r[2] <= 1024.0 * tx or r[0] >= 1024.0 * (tx + 1):
+                    continue
+                spec = t.push_gpu_cache([(8.0, 2.0, float(fmt), 0.0)])   # Color8, Rec709Narrow
+                hdr = t.add_prim_header(r, r, i + 1, spec, 0, pic, (src, src, src, 0))
+                inst = brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)
+                ops.append(Batch(abi.KIND_BRUSH_YUV_IMAGE, inst[None, :], blend=abi.BLEND_NONE,
+                                 features=abi.FEAT_TEXTURE_2D | abi.FEAT_YUV, color=names))
+            tile_targets.append(Target(name, ops=ops))
+            rect = (1024.0 * tx, 512.0 * ty, 1024.0 * (tx + 1), 512.0 * (ty + 1))
+            clip = (rect[0], rect[1], min(rect[2], float(W)), min(rect[3], float(H)))
+            comp.append(Batch(abi.KIND_COMPOSITE, composite_instance(rect, clip)[None, :], blend=abi.BLEND_NONE,
+                              features=abi.FEAT_FAST_PATH | abi.FEAT_TEXTURE_2D, color=(name, "", "")))
+    final = Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0))] + comp)
+    return Frame(t.arrays(), textures, [tile_targets, [final]])
+
+
 def video_frame(width=3840, height=2160, vw=1920, vh=1080, fmt="nv12", color_space=2, seed=1):
     """One full-screen video surface: a vw x vh 8-bit YUV frame (NV12 by default, Rec.709 narrow
     range) scaled to the whole framebuffer by `composite` YUV — the compositor's video case."""
