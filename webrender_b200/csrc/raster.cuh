@@ -42,6 +42,8 @@ struct RasterArgs {
   const GenRow* gen;  // per-thread row state of the current CMD_GENERAL command
   const uint32_t* tile_mask;  // bitmask bins (see SetupArgs), nullptr = scan every command
   const uint32_t* wide_mask;
+  const uint32_t* tile_any;  // see SetupArgs
+  int any_words;
   int bin_words, bin_tiles_x;
   const float* row_tab;  // row tables written by the setup kernel (CmdCold::row_off)
 };
@@ -707,7 +709,17 @@ wr_raster(RasterArgs a) {
   __shared__ int s_tile;
   __shared__ unsigned short list[WRCU_THREADS * 32];  // command indices of the tile's set mask bits, in order
   for (;;) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
+    if (threadIdx.x == 0) {
+      // binned batches: pass over tiles no command touches (text: ~7 of 8 tiles of a 4K page) with one load each
+      int tn;
+      for (;;) {
+        tn = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
+        if (tn >= n_tiles || !a.tile_any || !a.tile_mask) break;
+        const int tid = (by0 + tn / nx) * a.bin_tiles_x + bx0 + tn % nx;
+        if (a.tile_any[a.any_words] || ((a.tile_any[tid >> 5] >> (tid & 31)) & 1u)) break;
+      }
+      s_tile = tn;
+    }
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) break;

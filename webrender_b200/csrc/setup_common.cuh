@@ -28,6 +28,10 @@ struct SetupArgs {
   // commands covering more than WR_WIDE_TILES tiles set their bit in wide_mask instead
   uint32_t* tile_mask;
   uint32_t* wide_mask;
+  // bit t of tile_any = some command's bit is set in tile t's mask; word any_words = a wide command exists.
+  // Lets the raster kernel's tile scheduler pass over empty tiles with one load each.
+  uint32_t* tile_any;
+  int any_words;
   int bin_words, bin_tiles_x;
   int* err_counter;
   int blend_enabled;
@@ -448,10 +452,14 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
       const int word = idx >> 5;
       if ((tx_b - tx_a) * (ty_b - ty_a) > WR_WIDE_TILES) {
         atomicOr(&a.wide_mask[word], bit);
+        if (a.tile_any) atomicOr(&a.tile_any[a.any_words], 1u);
       } else {
         for (int ty = ty_a; ty < ty_b; ty++)
-          for (int tx = tx_a; tx < tx_b; tx++)
-            atomicOr(&a.tile_mask[(size_t)(ty * a.bin_tiles_x + tx) * a.bin_words + word], bit);
+          for (int tx = tx_a; tx < tx_b; tx++) {
+            const int tid = ty * a.bin_tiles_x + tx;
+            atomicOr(&a.tile_mask[(size_t)tid * a.bin_words + word], bit);
+            if (a.tile_any) atomicOr(&a.tile_any[tid >> 5], 1u << (tid & 31));
+          }
       }
     }
   }

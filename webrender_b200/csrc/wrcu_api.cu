@@ -849,7 +849,8 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   {
     const int tiles_x = (T.w + WRCU_TILE_W - 1) / WRCU_TILE_W, tiles_y = (T.h + WRCU_TILE_H - 1) / WRCU_TILE_H;
     const size_t words = ((size_t)n + 31) / 32;
-    const size_t need = ((size_t)tiles_x * tiles_y + 1) * words;  // + the wide mask
+    const size_t any_words = ((size_t)tiles_x * tiles_y + 31) / 32;
+    const size_t need = ((size_t)tiles_x * tiles_y + 1) * words + any_words + 1;  // + the wide mask + the tile-any bitmap
     if (n >= 512 && need * 4 <= (size_t)96 << 20) {
       if (need > c->bin_cap_words) {
         WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -864,6 +865,8 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       sa.wide_mask = c->bin_mask + (size_t)tiles_x * tiles_y * words;
       sa.bin_words = (int)words;
       sa.bin_tiles_x = tiles_x;
+      sa.tile_any = sa.wide_mask + words;
+      sa.any_words = (int)any_words;
     }
   }
   sa.clip_mask = tex_view(c, st->clip_mask);
@@ -1020,6 +1023,8 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   ra.tile_mask = sa.tile_mask;
   ra.wide_mask = sa.wide_mask;
   ra.bin_words = sa.bin_words;
+  ra.tile_any = sa.tile_any;
+  ra.any_words = sa.any_words;
   ra.bin_tiles_x = sa.bin_tiles_x;
   ra.n_gpu_cache = c->tables.n_gpu_cache;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
