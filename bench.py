@@ -82,6 +82,28 @@ WORKLOAD_B = ("config B: examples/alpha_perf.rs scene, 1000 full-frame alpha=0.0
               "batch at 3840x2160, premultiplied-alpha blend, clear each frame")
 
 
+def usable_cores():
+    """Host cores this process may actually run on: the affinity mask, further limited by the cgroup CPU
+    quota (os.cpu_count() reports the machine's cores, which over-subscribed the reference arm in round 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:  # cgroup v2, then v1
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(float(q[0]) / float(q[1]))))
+    except (OSError, ValueError, IndexError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on
     this box's host cores: the unmodified SWGL rasteriser (oracle/_ref) when it
@@ -94,7 +116,7 @@ def run_reference(args):
         return
     from oracle.backends import have_swgl
     kind = "reference" if have_swgl() else "port"
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     n_rects = args.ref_rects
     band_h = max(8, H // cores)
     times = []
@@ -119,7 +141,10 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD_B,
                    "sample": f"bounded per step: {n_rects} of the 1000 layers, the 3840x2160 frame cut into {cores} "
-                             f"bands of {band_h} rows, one per core"},
+                             f"bands of {band_h} rows, one per core ({cores * band_h} of {H} rows); every layer is "
+                             f"the same full-band rect, so Mpix/s is a rate on homogeneous work and compares "
+                             f"directly with the wrcu arm's 1000-layer frame",
+                   "cores": cores, "os_cpu_count": os.cpu_count()},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind,
                          "sample": f"{n_rects} full-band alpha rects on {cores} bands of {W}x{band_h} px per step "
                                    f"(one persistent SWGL context per core)"},
@@ -344,6 +369,65 @@ def run_update_path(dev, flush, args):
     return line
 
 
+def roofline_sweep(dev, flush, steps, peak):
+    """Config B geometry (full-frame alpha rects in one batch at 3840x2160) at L layers, and B' (1000 seeded
+    random rects): where the brush pass is memory-bound and where the on-chip layer loop takes over.
+    Per entry: raster-kernel time (CUDA events around the raster kernel alone, L2 flushed), batch time
+    (setup + raster), algorithmic GB/s (8 B per pixel-layer), and GB/s on the DRAM bytes the tile-resident
+    kernel actually moves (target once in, once out = 2 x 33.2 MB; ncu-measured figures per L are in
+    profiles/) with its fraction of the measured HBM peak."""
+    import torch
+    from webrender_b200 import abi, scenes
+    from webrender_b200.frame import Batch, Clear
+    from webrender_b200.gpu_types import ortho
+    tgt = dev.texture_create(abi.FMT_RGBA8, W, H)
+    proj = ortho(W, H)
+    out = []
+    dev.profile_enable(True)
+    cases = [(str(L), lambda L=L: scenes.alpha_rects_frame(W, H, L)) for L in (1, 2, 4, 8, 16, 64, 256, 1000)]
+    cases.append(("b_prime", lambda: scenes.alpha_rects_frame(W, H, 1000, random_rects=True, seed=1, color=None)))
+    for name, make in cases:
+        frame = make()
+        layers = scenes.pixel_layers_of_quad_batch(frame)
+        tdesc = frame.passes[0][0]
+        clear_op = [op for op in tdesc.ops if isinstance(op, Clear)][0]
+        batch = [op for op in tdesc.ops if isinstance(op, Batch)][0]
+        inst = batch.instance_bytes()
+        k_ms, b_ms = [], []
+        for it in range(steps + 2):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            dev.frame_begin(frame.tables)
+            dev.target_bind(tgt, 0, proj, (0, 0, W, H))
+            dev.clear(None, clear_op.color, None)
+            flush.fill_(2)  # the clear leaves the target in L2: evict it again so the batch reads DRAM
+            torch.cuda.synchronize()
+            dev.timer_begin()
+            dev.draw_batch(batch.kind, batch.features, batch.blend, batch.depth, [0, 0, 0], 0, None,
+                           batch.blend_color, inst)
+            t = dev.timer_end()
+            dev.frame_end()
+            if it >= 2:
+                b_ms.append(t)
+                k_ms.append(dev.last_raster_ms())
+        k_ms.sort()
+        b_ms.sort()
+        km, bm = k_ms[len(k_ms) // 2], b_ms[len(b_ms) // 2]
+        dram = 2 * W * H * 4 if name != "b_prime" else None
+        e = {"layers": name, "pixel_layers": layers, "raster_kernel_ms": km, "batch_ms": bm,
+             "Mpix_s": layers / (km * 1e-3) / 1e6,
+             "algorithmic_GBs": layers * BYTES_PER_PIXEL_LAYER / (km * 1e-3) / 1e9}
+        e["algorithmic_frac"] = e["algorithmic_GBs"] / peak
+        if dram:
+            e["dram_bytes_model"] = dram
+            e["dram_GBs"] = dram / (km * 1e-3) / 1e9
+            e["dram_frac_of_hbm"] = e["dram_GBs"] / peak
+        out.append(e)
+    dev.profile_enable(False)
+    dev.texture_destroy(tgt)
+    return out
+
+
 def run_config_e(dev, rank, world, steps, barrier):
     """One 8192x4096 frame = 64 picture-cache tiles of 1024x512 (config-B' rect
     list cut per tile), tiles round-robin over the ranks, one NCCL gather to
@@ -386,6 +470,7 @@ def main():
     ap.add_argument("--impl", default="wrcu", choices=["wrcu", "reference"])
     ap.add_argument("--ref-rects", type=int, default=400, help="layers per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the layer-depth roofline sweep")
     ap.add_argument("--workload", default="config_b",
                     help="config_b (the contract's bench line) or one of the other §8 rows: see other_workloads(), update_path")
     args = ap.parse_args()
@@ -595,6 +680,8 @@ def main():
                          "note": "algorithmic bytes = 8 B per pixel-layer (SURVEY.md §8d); the tile-resident kernel "
                                  "keeps layers on chip, so DRAM traffic is ~2 x 33 MB per launch and achieved may exceed peak"},
         }
+        if not args.no_sweep:
+            line["roofline_sweep"] = roofline_sweep(dev, flush, max(5, min(args.steps, 10)), peak)
         if config_e is not None:
             line["config_e"] = config_e
         if not args.no_cpu_baseline:

@@ -306,6 +306,12 @@ int wrcu_reset_stats(wrcu_ctx* ctx);
 int wrcu_timer_begin(wrcu_ctx* ctx);
 int wrcu_timer_end(wrcu_ctx* ctx, float* elapsed_ms); /* synchronises */
 
+/* Profiling aid: while enabled, every draw brackets its RASTER kernel(s) (the vertex-stage setup
+ * kernel excluded) with CUDA events on the context's stream; wrcu_last_raster_ms synchronises and
+ * returns the duration of the most recent draw's raster work.  Used by bench.py's roofline lines. */
+int wrcu_profile_enable(wrcu_ctx* ctx, int on);
+int wrcu_last_raster_ms(wrcu_ctx* ctx, float* elapsed_ms);
+
 /* Raw device pointer + pitch of a texture (GetColorBuffer, gl.cc:2317): valid
  * until the texture is destroyed.  Used by the multi-GPU tile gather. */
 int wrcu_texture_device_ptr(wrcu_ctx* ctx, wrcu_tex tex, void** dptr,
@@ -327,6 +333,13 @@ int wrcu_host_free(wrcu_ctx* ctx, void* ptr);
 int wrcu_read_pixels_async(wrcu_ctx* ctx, wrcu_tex tex, int x, int y, int w,
                            int h, void* out, size_t dst_stride, uint64_t* fence);
 int wrcu_fence_wait(wrcu_ctx* ctx, uint64_t fence);
+/* glFenceSync (device/gl.rs:3243 insert_fence_sync via UploadPBOPool, renderer/upload.rs:449-470):
+ * a fence behind everything queued so far.  Ownership rule for page-locked upload buffers: a
+ * wrcu_host_alloc buffer passed to wrcu_texture_upload / wrcu_texture_upload_batch is read by the
+ * GPU in place (no intermediate copy) and stays BUSY until a fence inserted after the call has been
+ * waited on (or wrcu_finish) — exactly how the reference recycles its upload PBOs.  Every other
+ * array (instances, tables, texture lists, GPU-cache blocks) is copied before the call returns. */
+int wrcu_fence_insert(wrcu_ctx* ctx, uint64_t* fence);
 
 #ifdef __cplusplus
 }

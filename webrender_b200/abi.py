@@ -155,6 +155,7 @@ SYMBOLS = [
     "wrcu_draw_batch", "wrcu_draw_composite_tiles", "wrcu_program_from_name", "wrcu_get_stats",
     "wrcu_reset_stats", "wrcu_timer_begin", "wrcu_timer_end",
     "wrcu_texture_device_ptr", "wrcu_stream", "wrcu_host_alloc", "wrcu_host_free",
-    "wrcu_read_pixels_async", "wrcu_fence_wait",
+    "wrcu_read_pixels_async", "wrcu_fence_wait", "wrcu_fence_insert",
+    "wrcu_profile_enable", "wrcu_last_raster_ms",
     "wrcu_texture_upload_batch", "wrcu_texture_copy", "wrcu_gpu_cache_update",
 ]

@@ -82,5 +82,6 @@ struct BatchInfo {
   int premul_valid;        // 1 while every command's colour lanes are <= its alpha lane
   int tile_counter;        // dynamic tile scheduler of the generic raster kernel
   int row_alloc;           // floats of the row-table pool handed out to this batch's commands
+  int all_copy;            // composite: 1 while every command is an opaque 1:1 tile copy (tma.cuh)
 };
 #define WR_ROW_TAB_MIN 16

@@ -46,6 +46,8 @@ struct RasterArgs {
   int any_words;
   int bin_words, bin_tiles_x;
   const float* row_tab;  // row tables written by the setup kernel (CmdCold::row_off)
+  const void* tmaps;     // device table of CUtensorMap records, indexed by TexView::tmap_id
+  int copy_eligible;     // composite: a copy-class batch (BatchInfo::all_copy) is drawn by wr_composite_copy
 };
 
 #define CHUNK_CMDS 256
@@ -700,6 +702,7 @@ wr_raster(RasterArgs a) {
   __shared__ int wsum[WRCU_THREADS / 32 + 1];  // per-warp survivor counts + the last covering command
   const BatchInfo bi = *a.info;
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
+  if (a.copy_eligible && bi.all_copy) return;  // handled by wr_composite_copy
   const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
   const int bx1 = (min(bi.bx1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
   const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;

@@ -44,6 +44,7 @@ struct SetupArgs {
   TexView color2;
   TexView clip_mask;
   const TexView* tex_list;  // wrcu_draw_composite_tiles: sColor0 of instance i (nullptr: color0 for all)
+  int depth_on;             // the draw tests depth (copy-class composites are refused)
 };
 
 // A setup kernel = one thread per instance running <name>_one.  Under the host
@@ -56,6 +57,7 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
   info->premul_valid = 1;
   info->tile_counter = 0;
   info->row_alloc = 0;
+  info->all_copy = 1;
 }
 // Each setup kernel also re-arms the per-batch record the NEXT draw will use
 // (records rotate through a ring of 4; the one after the current was last read

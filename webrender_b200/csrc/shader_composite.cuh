@@ -4,6 +4,7 @@
 #pragma once
 #include "raster.cuh"
 #include "setup_common.cuh"
+#include "tma.cuh"
 
 // CmdCold: f[0..3] uv bounds used by the span shader, g[0..3] vColor,
 //          g[4] FAST_PATH, g[5..8] vUVBounds (fragment clamp),
@@ -109,13 +110,165 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
     for (int i = 0; i < 4; i++) { k->g[i] = f[8 + i]; k->g[5 + i] = ub[i]; }
     k->g[4] = fast ? 1.0f : 0.0f;
     *(TexView*)&k->g[12] = tex0;
+    // Copy class (tma.cuh): an opaque, untinted instance whose texels map 1:1 onto whole pixels is a
+    // rectangle copy.  u must be exact (unit step, texel centres: every partial sum of the span walk is
+    // then a small dyadic rational, so no rounding can occur); v may carry the rounding of
+    // yScale = 1/height (rasterize.h:851-861) and is checked row by row against the sampler's
+    // tolerance: within 1/1024 texel of a centre both the nearest (floor) and the 7-bit linear
+    // (fraction 0) filters return exactly that texel.
+    bool copyc = false;
+    const CmdHot h = a.hot[idx];
+    const int tiw = tex0.w, tih = tex0.h;
+    if (!a.blend_enabled && !a.depth_on && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 &&
+        tex0.tmap_id && is_white && !(h.flags & (CMD_GENERAL | CMD_AA | CMD_MASK | CMD_CLIP_DIST)) &&
+        (tiw & (tiw - 1)) == 0 && (tih & (tih - 1)) == 0 && k->xl == floorf(k->xl) && k->xr == floorf(k->xr) &&
+        k->i_lt[0] == k->i_lb[0] && k->i_rt[0] == k->i_rb[0] && k->i_lt[1] == k->i_rt[1] && k->i_lb[1] == k->i_rb[1]) {
+      const float su = (k->i_rt[0] - k->i_lt[0]) / (k->xr - k->xl);
+      const float u0 = k->i_lt[0] + ((float)h.x0 + 0.5f - k->xl) * su;
+      const float txf = u0 * tw - 0.5f;
+      const float sl = (k->i_lb[1] - k->i_lt[1]) * k->yscale;
+      float v = k->i_lt[1] + ((float)h.y0 + 0.5f - k->yt) * sl;
+      const float tyf = floorf(v * th);
+      const int rows = (int)h.y1 - (int)h.y0;
+      bool okc = su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
+                 tyf >= 0.0f && tyf + (float)rows <= th;
+      for (int r = 0; okc && r < rows; r++) {
+        okc = fabsf(v * th - (tyf + (float)r + 0.5f)) <= (1.0f / 1024.0f);
+        v = v + sl;  // Edge::nextRow (rasterize.h:880-884)
+      }
+      if (okc) {
+        copyc = true;
+        k->i[0] = (int)txf;
+        k->i[1] = (int)tyf;
+      }
+    }
+    if (!copyc) a.info->all_copy = 0;
   }
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);
     atomicAdd(a.err_counter, 1);
   }
 }
+#ifdef WRCU_HOSTEMU
 WR_SETUP_KERNEL(wr_setup_composite)
+#else
+__global__ void wr_setup_composite(SetupArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) wr_reset_batch_info(a.info_next);
+  if (idx < a.n) wr_setup_composite_one(a, idx);
+  __syncwarp();
+  wr_fill_row_tables_warp(a, idx);
+  // The copy kernel moves boxes of different instances concurrently: a copy-class batch must not
+  // overlap itself (picture-cache tiles never do; surfaces that do keep the ordered tile kernel).
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) a.info->all_copy = 0;
+    return;
+  }
+  __syncthreads();
+  if (idx < a.n) {
+    const CmdHot me = a.hot[idx];
+    if (me.x1 > me.x0 && me.y1 > me.y0)
+      for (int j = 0; j < idx; j++) {
+        const CmdHot o = a.hot[j];
+        if (o.x1 > o.x0 && o.y1 > o.y0 && o.x0 < me.x1 && me.x0 < o.x1 && o.y0 < me.y1 && me.y0 < o.y1) a.info->all_copy = 0;
+      }
+  }
+}
+
+// ---- copy-class composite: the tile list as 2-D bulk-tensor copies (see tma.cuh) ----------------
+// Work items = 256x16-pixel boxes of every instance's rect, dealt round-robin to the persistent CTAs.
+// Thread 0 pipelines the boxes that lie wholly inside their rect through the copy engine
+// (WR_TMA_STAGES shared-memory slots, loads two boxes ahead of the stores); warps 1..3 copy the
+// ragged-edge boxes with plain accesses meanwhile.
+struct WrCopyItem { int inst, bx, by; };
+__global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a) {
+  extern __shared__ __align__(128) uint8_t wr_copy_smem[];
+  __shared__ __align__(8) uint64_t full[WR_TMA_STAGES];
+  const BatchInfo bi = *a.info;
+  if (!bi.all_copy) return;  // the ordered tile kernel draws this batch
+  const CUtensorMap* maps = (const CUtensorMap*)a.tmaps;
+  const CUtensorMap* dst_map = maps + a.tgt.tmap_id;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WR_TMA_STAGES; s++) wr_mbar_init(&full[s], 1);
+    wr_fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // ---- the copy engine's driver: every full box of this CTA, loads DEPTH boxes ahead of stores ----
+    constexpr int DEPTH = WR_TMA_STAGES - 2;
+    int ring_inst[WR_TMA_STAGES], ring_x[WR_TMA_STAGES], ring_y[WR_TMA_STAGES];
+    int issued = 0, stored = 0;
+    int g = 0;  // global box counter over all instances
+    auto store_one = [&]() {
+      const int s = stored % WR_TMA_STAGES;
+      wr_mbar_wait(&full[s], (uint32_t)((stored / WR_TMA_STAGES) & 1));
+      wr_tma_store_2d(dst_map, ring_x[s], ring_y[s], wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES);
+      wr_tma_commit();
+      stored++;
+    };
+    for (int i = 0; i < a.n; i++) {
+      const CmdHot c = a.hot[i];
+      const int w = (int)c.x1 - (int)c.x0, hgt = (int)c.y1 - (int)c.y0;
+      if (w <= 0 || hgt <= 0) continue;
+      const CmdCold& k = a.cold[c.cold];
+      const int sx0 = k.i[0], sy0 = k.i[1];
+      const CUtensorMap* src_map = maps + wr_composite_tex(k).tmap_id;
+      const int nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W, nby = (hgt + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H;
+      const int nb = nbx * nby;
+      // first box of this instance that belongs to this CTA
+      int b = ((int)blockIdx.x - g % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;
+      for (; b < nb; b += gridDim.x) {
+        const int bx = (b % nbx) * WR_TMA_BOX_W, by = (b / nbx) * WR_TMA_BOX_H;
+        if (bx + WR_TMA_BOX_W > w || by + WR_TMA_BOX_H > hgt) continue;  // ragged edge: the other warps
+        const int s = issued % WR_TMA_STAGES;
+        if (issued >= WR_TMA_STAGES) wr_tma_wait_read<1>();  // the store that last read slot s has drained
+        ring_x[s] = (int)c.x0 + bx;
+        ring_y[s] = (int)c.y0 + by;
+        ring_inst[s] = i;
+        wr_mbar_expect_tx(&full[s], WR_TMA_BOX_BYTES);
+        wr_tma_load_2d(wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES, src_map, sx0 + bx, sy0 + by, &full[s]);
+        issued++;
+        if (issued - stored > DEPTH) store_one();
+      }
+      g += nb;
+    }
+    while (stored < issued) store_one();
+    wr_tma_wait_all<0>();  // stores complete before the CTA's shared memory is released
+    (void)ring_inst;
+  } else if (threadIdx.x >= 32) {
+    // ---- ragged-edge boxes: plain row copies, 16 bytes per thread where both sides are aligned ----
+    const int t = threadIdx.x - 32, nt = WR_TMA_THREADS - 32;
+    int g = 0;
+    for (int i = 0; i < a.n; i++) {
+      const CmdHot c = a.hot[i];
+      const int w = (int)c.x1 - (int)c.x0, hgt = (int)c.y1 - (int)c.y0;
+      if (w <= 0 || hgt <= 0) continue;
+      const CmdCold& k = a.cold[c.cold];
+      const TexView& tv = wr_composite_tex(k);
+      const int nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W, nby = (hgt + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H;
+      const int nb = nbx * nby;
+      int b = ((int)blockIdx.x - g % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;
+      for (; b < nb; b += gridDim.x) {
+        const int bx = (b % nbx) * WR_TMA_BOX_W, by = (b / nbx) * WR_TMA_BOX_H;
+        if (bx + WR_TMA_BOX_W <= w && by + WR_TMA_BOX_H <= hgt) continue;  // full box: the copy engine
+        const int bw = min(WR_TMA_BOX_W, w - bx), bh = min(WR_TMA_BOX_H, hgt - by);
+        for (int r = 0; r < bh; r++) {
+          const uint32_t* sp = (const uint32_t*)(tv.ptr + (size_t)(k.i[1] + by + r) * tv.pitch) + k.i[0] + bx;
+          uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)c.y0 + by + r) * a.tgt.color_pitch) + (int)c.x0 + bx;
+          if ((((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
+            const int nv = bw >> 2;
+            for (int q = t; q < nv; q += nt) ((uint4*)dp)[q] = __ldg((const uint4*)sp + q);
+            for (int q = (nv << 2) + t; q < bw; q += nt) dp[q] = __ldg(sp + q);
+          } else {
+            for (int q = t; q < bw; q += nt) dp[q] = __ldg(sp + q);
+          }
+        }
+      }
+      g += nb;
+    }
+  }
+}
+#endif
 
 #ifndef WRCU_HOSTEMU
 template <> struct WrMinCtas<CompositeShader> { enum { v = 3 }; };

@@ -201,6 +201,8 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   }
   cudaEventCreate(&c->t0);
   cudaEventCreate(&c->t1);
+  cudaEventCreate(&c->p0);
+  cudaEventCreate(&c->p1);
   if (cudaMalloc((void**)&c->batch_info, 4 * sizeof(BatchInfo)) != cudaSuccess ||
       cudaMalloc((void**)&c->dev_err, sizeof(int)) != cudaSuccess) {
     delete c;
@@ -208,6 +210,19 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   }
   cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
   WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info, 4);
+#ifndef WRCU_HOSTEMU
+  {  // TMA tensor maps: encoder entry point from the driver (no libcuda link), device table of records
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess && fn &&
+        cudaMalloc(&c->tmaps_dev, (size_t)wrcu_ctx::MAX_TEX * sizeof(CUtensorMap)) == cudaSuccess)
+      c->tmap_encode = fn;
+    else
+      c->tmaps_dev = nullptr;
+    cudaGetLastError();
+  }
+#endif
   c->row_cap = 16 << 20;  // 64 MiB of row tables per batch; commands beyond it fall back to walking
   if (cudaMalloc((void**)&c->row_tab, (size_t)c->row_cap * sizeof(float)) != cudaSuccess) {
     c->row_tab = nullptr;
@@ -232,11 +247,14 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->cmd_cold) cudaFree(c->cmd_cold);
   if (c->batch_info) cudaFree(c->batch_info);
   if (c->row_tab) cudaFree(c->row_tab);
+  if (c->tmaps_dev) cudaFree(c->tmaps_dev);
   if (c->gpu_cache_dev) cudaFree(c->gpu_cache_dev);
   if (c->dev_err) cudaFree(c->dev_err);
   if (c->bin_mask) cudaFree(c->bin_mask);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
+  if (c->p0) cudaEventDestroy(c->p0);
+  if (c->p1) cudaEventDestroy(c->p1);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
@@ -305,7 +323,11 @@ static int arena_reserve(wrcu_ctx* c, size_t bytes, size_t* off_out) {
   return WRCU_OK;
 }
 
-static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
+// `zero_copy_ok`: only the texture-upload entry points pass true — their header contract says a
+// wrcu_host_alloc buffer stays busy until a fence taken after the call (wrcu_fence_insert) has been
+// waited on.  Instances, tables and texture lists are ALWAYS copied into the arena before the call
+// returns (glBufferData ownership, include/wrcu.h conventions).
+static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out, bool zero_copy_ok = false) {
   size_t off = 0;
   int rc = arena_reserve(c, bytes, &off);
   if (rc != WRCU_OK) return rc;
@@ -313,6 +335,7 @@ static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
   // page-locked memory handed out by wrcu_host_alloc goes to the device directly (the mapped-PBO
   // case of the reference's upload path); anything else is first copied into the pinned arena
   bool pinned = false;
+  if (zero_copy_ok)
   for (const auto& ha : c->host_allocs)
     if ((const uint8_t*)src >= ha.first && (const uint8_t*)src + bytes <= ha.first + ha.second) { pinned = true; break; }
   if (pinned) {
@@ -327,9 +350,10 @@ static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out) {
 }
 
 // ---- textures ----------------------------------------------------------------------
+static void make_tensor_map(wrcu_ctx* c, int id);
 extern "C" int wrcu_texture_create(wrcu_ctx* c, int format, int w, int h, wrcu_tex* out) {
   int bpp = fmt_bpp(format);
-  if (!bpp || w <= 0 || h <= 0 || w > 32768 || h > 32768 || !out)
+  if (!bpp || w <= 0 || h <= 0 || w > 32767 || h > 32767 || !out)
     return wrcu_fail(c, WRCU_ERR_INVALID, "texture_create: bad arguments");
   cudaSetDevice(c->device);
   for (int i = 1; i < wrcu_ctx::MAX_TEX; i++) {
@@ -343,12 +367,42 @@ extern "C" int wrcu_texture_create(wrcu_ctx* c, int format, int w, int h, wrcu_t
       WRCU_CUDA(c, cudaMalloc((void**)&t.dptr, t.pitch * rows));
       WRCU_CUDA(c, cudaMemsetAsync(t.dptr, 0, t.pitch * rows, c->stream));
       t.live = true;
+      make_tensor_map(c, i);
       *out = (wrcu_tex)i;
       return WRCU_OK;
     }
   }
   return wrcu_fail(c, WRCU_ERR_OOM, "texture_create: out of texture handles");
 }
+
+#ifndef WRCU_HOSTEMU
+// One 2-D tensor map per RGBA8 texture: u32 elements, box WR_TMA_BOX_W x WR_TMA_BOX_H, no swizzle
+// (the boxes are only ever moved, never read by threads).  The 128-byte record is built on the host
+// and copied into slot `id` of the context's device table; kernels address it as tmaps + id.
+static void make_tensor_map(wrcu_ctx* c, int id) {
+  WrTexture& t = c->tex[id];
+  t.has_tmap = false;
+  if (!c->tmap_encode || !c->tmaps_dev || t.fmt != WRCU_FMT_RGBA8 || t.w < WR_TMA_BOX_W || t.h < WR_TMA_BOX_H) return;
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {(cuuint64_t)t.w, (cuuint64_t)t.h};
+  const cuuint64_t strides[1] = {(cuuint64_t)t.pitch};
+  const cuuint32_t box[2] = {WR_TMA_BOX_W, WR_TMA_BOX_H};
+  const cuuint32_t estr[2] = {1, 1};
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  CUresult r = ((EncodeFn)c->tmap_encode)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, t.dptr, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return;
+  if (cudaMemcpyAsync((uint8_t*)c->tmaps_dev + (size_t)id * sizeof(CUtensorMap), &m, sizeof m, cudaMemcpyHostToDevice,
+                      c->stream) != cudaSuccess)
+    return;
+  t.has_tmap = true;
+}
+#else
+static void make_tensor_map(wrcu_ctx*, int) {}
+#endif
 
 static WrTexture* get_tex(wrcu_ctx* c, wrcu_tex id) {
   return (id > 0 && id < wrcu_ctx::MAX_TEX && c->tex[id].live) ? &c->tex[id] : nullptr;
@@ -373,7 +427,7 @@ extern "C" int wrcu_texture_upload(wrcu_ctx* c, wrcu_tex id, int x, int y, int w
   size_t need = row * h;
   void* dsrc = nullptr;
   if (src_stride == row) {
-    int rc = stage(c, data, need, &dsrc);
+    int rc = stage(c, data, need, &dsrc, true);
     if (rc) return rc;
   } else {
     // stage row by row (host memcpy), single device copy
@@ -455,6 +509,7 @@ extern "C" int wrcu_host_free(wrcu_ctx* c, void* ptr) {
   return WRCU_OK;
 }
 
+static int ensure_copy_stream(wrcu_ctx* c);
 static int wait_fence(wrcu_ctx* c, uint64_t fence, bool on_stream) {
   if (fence == 0) return WRCU_OK;
   int slot = (int)(fence % wrcu_ctx::N_FENCES);
@@ -470,12 +525,7 @@ extern "C" int wrcu_read_pixels_async(wrcu_ctx* c, wrcu_tex id, int x, int y, in
   if (!t || !out || !fence || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
     return wrcu_fail(c, WRCU_ERR_INVALID, "read_pixels_async: bad arguments");
   cudaSetDevice(c->device);
-  if (!c->copy_stream) {
-    WRCU_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    WRCU_CUDA(c, cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
-    for (int i = 0; i < wrcu_ctx::N_FENCES; i++)
-      WRCU_CUDA(c, cudaEventCreateWithFlags(&c->fence_ev[i], cudaEventDisableTiming));
-  }
+  { int rce = ensure_copy_stream(c); if (rce != WRCU_OK) return rce; }
   uint64_t id64 = c->next_fence++;
   int slot = (int)(id64 % wrcu_ctx::N_FENCES);
   if (c->fence_id[slot]) WRCU_CUDA(c, cudaEventSynchronize(c->fence_ev[slot]));  // ring wrapped: oldest copy must be done
@@ -488,6 +538,31 @@ extern "C" int wrcu_read_pixels_async(wrcu_ctx* c, wrcu_tex id, int x, int y, in
   c->fence_id[slot] = id64;
   t->pending_read = id64;
   c->stats.d2h_bytes += row * h;
+  *fence = id64;
+  return WRCU_OK;
+}
+
+static int ensure_copy_stream(wrcu_ctx* c) {
+  if (c->copy_stream) return WRCU_OK;
+  WRCU_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  WRCU_CUDA(c, cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
+  for (int i = 0; i < wrcu_ctx::N_FENCES; i++)
+    WRCU_CUDA(c, cudaEventCreateWithFlags(&c->fence_ev[i], cudaEventDisableTiming));
+  return WRCU_OK;
+}
+
+// glFenceSync on the draw stream: everything queued so far (uploads reading wrcu_host_alloc memory
+// included) has completed once wrcu_fence_wait(fence) returns.
+extern "C" int wrcu_fence_insert(wrcu_ctx* c, uint64_t* fence) {
+  if (!fence) return wrcu_fail(c, WRCU_ERR_INVALID, "fence_insert: null fence");
+  cudaSetDevice(c->device);
+  int rc = ensure_copy_stream(c);
+  if (rc != WRCU_OK) return rc;
+  uint64_t id64 = c->next_fence++;
+  int slot = (int)(id64 % wrcu_ctx::N_FENCES);
+  if (c->fence_id[slot]) WRCU_CUDA(c, cudaEventSynchronize(c->fence_ev[slot]));
+  WRCU_CUDA(c, cudaEventRecord(c->fence_ev[slot], c->stream));
+  c->fence_id[slot] = id64;
   *fence = id64;
   return WRCU_OK;
 }
@@ -520,7 +595,7 @@ extern "C" int wrcu_texture_upload_batch(wrcu_ctx* c, wrcu_tex id, const wrcu_up
   }
   int rc;
   void *dstage = nullptr, *drects = nullptr;
-  if ((rc = stage(c, staging, staging_bytes, &dstage)) != WRCU_OK) return rc;
+  if ((rc = stage(c, staging, staging_bytes, &dstage, true)) != WRCU_OK) return rc;
   std::vector<UploadRectDev> hr(n);
   int max_h = 1;
   for (size_t i = 0; i < n; i++) {
@@ -600,6 +675,17 @@ extern "C" int wrcu_gpu_cache_update(wrcu_ctx* c, int height, int clear, const w
 extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null tables");
   cudaSetDevice(c->device);
+  // Uploads and GPU-cache updates issued since the last wrcu_frame_end (Renderer::render runs
+  // update_texture_cache / update_gpu_cache before draw_frame) were staged into the outgoing arena
+  // AFTER its `done` event was recorded: re-record it so the next reuse of that arena waits for them
+  // too.  (Also covers arena 0 before the very first frame.)
+  {
+    Arena* out = &c->arena[c->cur_arena];
+    if (out->used > 0) {
+      WRCU_CUDA(c, cudaEventRecord(out->done, c->stream));
+      out->in_flight = true;
+    }
+  }
   // switch arena; wait until the frame that last used it has drained
   c->cur_arena ^= 1;
   Arena* a = &c->arena[c->cur_arena];
@@ -687,10 +773,20 @@ extern "C" int wrcu_target_bind(wrcu_ctx* c, wrcu_tex color, wrcu_tex depth, con
 
 static inline int host_round_pixel(float v) { return (int)(v * 255.0f + 0.5f); }
 
+// A texture with an asynchronous readback in flight must not be written before the copy has read it
+// (hosts that cache their target binding skip wrcu_target_bind, so draws and clears check as well).
+static int wait_pending_read(wrcu_ctx* c, WrTexture* t) {
+  if (!t || !t->pending_read) return WRCU_OK;
+  int rc = wait_fence(c, t->pending_read, true);
+  if (rc == WRCU_OK) t->pending_read = 0;
+  return rc;
+}
+
 extern "C" int wrcu_clear(wrcu_ctx* c, const int32_t rect[4], const float color[4], const float* depth) {
   WrTexture* t = get_tex(c, c->color_tex);
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "clear: no target bound");
   cudaSetDevice(c->device);
+  { int rcw = wait_pending_read(c, t); if (rcw != WRCU_OK) return rcw; }
   int x0 = 0, y0 = 0, x1 = t->w, y1 = t->h;
   if (rect) {
     x0 = rect[0] > 0 ? rect[0] : 0;
@@ -737,6 +833,7 @@ static TexView tex_view(wrcu_ctx* c, wrcu_tex id) {
   v.pitch = (int)t->pitch;
   v.filter = t->w >= 2 ? t->filter : WRCU_NEAREST;  // init_filter, gl.cc:870-877
   v.fmt = t->fmt;
+  v.tmap_id = t->has_tmap ? (int)id : 0;
   return v;
 }
 
@@ -781,6 +878,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   if (st->blend == WRCU_BLEND_SUBPIXEL_DUAL_SOURCE)
     return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "GL dual-source blending: SWGL hosts use the subpixel-text blend override instead");
   cudaSetDevice(c->device);
+  { int rcw = wait_pending_read(c, tgt); if (rcw != WRCU_OK) return rcw; }
   c->stats.draw_calls++;
   c->stats.instances += (uint64_t)n;
 
@@ -814,12 +912,15 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   memcpy(T.proj, c->proj, sizeof T.proj);
   memcpy(T.vp, c->vp, sizeof T.vp);
   T.cx0 = 0; T.cy0 = 0; T.cx1 = tgt->w; T.cy1 = tgt->h;
+  T.tmap_id = tgt->has_tmap ? (int)c->color_tex : 0;
   if (st->scissor_enabled) {
     T.cx0 = max(T.cx0, st->scissor[0]);
     T.cy0 = max(T.cy0, st->scissor[1]);
     T.cx1 = min(T.cx1, st->scissor[0] + st->scissor[2]);
     T.cy1 = min(T.cy1, st->scissor[1] + st->scissor[3]);
   }
+
+  if (T.cx1 <= T.cx0 || T.cy1 <= T.cy0) return WRCU_OK;  // scissor misses the target: SWGL draws nothing
 
   SetupArgs sa;
   memset(&sa, 0, sizeof sa);
@@ -837,6 +938,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   sa.row_tab = c->row_tab;
   sa.row_cap = c->row_cap;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
+  sa.depth_on = T.depth != nullptr;
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
   sa.color2 = tex_view(c, st->color[2]);
@@ -1027,11 +1129,13 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   ra.any_words = sa.any_words;
   ra.bin_tiles_x = sa.bin_tiles_x;
   ra.n_gpu_cache = c->tables.n_gpu_cache;
+  ra.tmaps = c->tmaps_dev;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
   if (grid.x == 0 || grid.y == 0) return WRCU_OK;
   // Device-side dispatch: the setup kernel decides whether the whole batch is
   // plain solid quads; the specialised and the generic kernel each return at
   // once when it is not their turn (the host never has to wait for the flag).
+  if (c->profile) WRCU_CUDA(c, cudaEventRecord(c->p0, c->stream));
   bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
                  ra.depth_mode == WRCU_DEPTH_OFF &&
                  (kind == WRCU_KIND_QUAD_TEXTURED || kind == WRCU_KIND_BRUSH_SOLID);  // the only kinds that emit CMD_CONST_COLOR
@@ -1089,8 +1193,22 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
     case WRCU_KIND_BRUSH_YUV_IMAGE: LAUNCH_RASTER(CompositeYuvShader); break;
     case WRCU_KIND_COMPOSITE:
-      if (features & WRCU_FEAT_YUV) LAUNCH_RASTER(CompositeYuvShader);
-      else LAUNCH_RASTER(CompositeShader);
+      if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
+#ifndef WRCU_HOSTEMU
+      if (c->tmaps_dev && T.tmap_id && st->blend == WRCU_BLEND_NONE && !T.depth) {
+        // copy-class tile lists (decided on the device, BatchInfo::all_copy) go through the copy engine;
+        // whichever of the two kernels is not in charge returns at once
+        const size_t smem = (size_t)WR_TMA_STAGES * WR_TMA_BOX_BYTES;
+        if (!c->copy_attr_set) {
+          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          c->copy_attr_set = true;
+        }
+        ra.copy_eligible = 1;
+        wr_composite_copy<<<c->sm_count * 3, WR_TMA_THREADS, smem, c->stream>>>(ra);
+        c->stats.kernel_launches++;
+      }
+#endif
+      LAUNCH_RASTER(CompositeShader);
       break;
     case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
     case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
@@ -1110,6 +1228,10 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   }
 #undef LAUNCH_RASTER
   c->stats.kernel_launches++;
+  if (c->profile) {
+    WRCU_CUDA(c, cudaEventRecord(c->p1, c->stream));
+    c->profile_valid = true;
+  }
   WRCU_CUDA(c, cudaGetLastError());
   return WRCU_OK;
 }
@@ -1166,6 +1288,17 @@ extern "C" int wrcu_get_stats(wrcu_ctx* c, wrcu_stats* out) {
 }
 extern "C" int wrcu_reset_stats(wrcu_ctx* c) {
   memset(&c->stats, 0, sizeof c->stats);
+  return WRCU_OK;
+}
+extern "C" int wrcu_profile_enable(wrcu_ctx* c, int on) {
+  c->profile = on != 0;
+  c->profile_valid = false;
+  return WRCU_OK;
+}
+extern "C" int wrcu_last_raster_ms(wrcu_ctx* c, float* ms) {
+  if (!ms || !c->profile_valid) return wrcu_fail(c, WRCU_ERR_INVALID, "last_raster_ms: no profiled draw");
+  WRCU_CUDA(c, cudaEventSynchronize(c->p1));
+  WRCU_CUDA(c, cudaEventElapsedTime(ms, c->p0, c->p1));
   return WRCU_OK;
 }
 extern "C" int wrcu_timer_begin(wrcu_ctx* c) {

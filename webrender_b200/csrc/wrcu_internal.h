@@ -39,6 +39,7 @@ struct WrTexture {
   size_t pitch = 0;
   uint8_t* dptr = nullptr;
   bool live = false;
+  bool has_tmap = false;      // a 2-D TMA tensor map of this texture sits in the context's device table
   uint64_t pending_read = 0;  // fence of an in-flight async readback of this texture
 };
 
@@ -49,6 +50,7 @@ struct TexView {
   int pitch;   // bytes
   int filter;  // WRCU_NEAREST / WRCU_LINEAR (already demoted if w < 2)
   int fmt;
+  int tmap_id;  // index of this texture's TMA tensor map in the context's device table; 0 = none
 };
 
 // Device pointers to the per-frame data tables (16-byte texels).
@@ -75,6 +77,7 @@ struct TargetDev {
   int vp[4];
   // scissor ∩ target bounds, as ints
   int cx0, cy0, cx1, cy1;
+  int tmap_id;  // TMA tensor map of the colour target (0 = none)
 };
 
 // Bump arena: pinned host staging + device mirror, double-buffered per frame.
@@ -114,6 +117,8 @@ struct wrcu_ctx {
   // stats / timing
   wrcu_stats stats = {};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEvent_t p0 = nullptr, p1 = nullptr;  // wrcu_profile_enable: around the last draw's raster kernels
+  bool profile = false, profile_valid = false;
   int sm_count = 148;
   // asynchronous readback: second stream + a ring of fences
   static const int N_FENCES = 8;
@@ -130,6 +135,11 @@ struct wrcu_ctx {
   float* row_tab = nullptr;      // row-table pool of the current batch (CmdCold::row_off)
   int row_cap = 0;               // floats
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
+  // TMA: one 128-byte CUtensorMap per RGBA8 texture (box 256x16 px), built on the host at texture
+  // creation (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint) and kept in a device table
+  void* tmaps_dev = nullptr;
+  void* tmap_encode = nullptr;
+  bool copy_attr_set = false;
 };
 
 int wrcu_fail(wrcu_ctx* c, int code, const char* fmt, ...);

@@ -196,6 +196,9 @@ class CudaDevice(DeviceBase):
         self.lib.wrcu_read_pixels_async.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                                     C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         self.lib.wrcu_fence_wait.argtypes = [C.c_void_p, C.c_uint64]
+        self.lib.wrcu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        self.lib.wrcu_last_raster_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        self.lib.wrcu_fence_insert.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         ctx = C.c_void_p()
         rc = self.lib.wrcu_ctx_create(device_ordinal, C.byref(ctx))
         if rc != 0:
@@ -229,6 +232,14 @@ class CudaDevice(DeviceBase):
         self._check(self.lib.wrcu_timer_end(self.ctx, C.byref(ms)))
         return ms.value
 
+    def profile_enable(self, on=True):
+        self._check(self.lib.wrcu_profile_enable(self.ctx, 1 if on else 0))
+
+    def last_raster_ms(self):
+        ms = C.c_float(0)
+        self._check(self.lib.wrcu_last_raster_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
     def texture_device_ptr(self, tex):
         p, pitch = C.c_void_p(), C.c_size_t()
         self._check(self.lib.wrcu_texture_device_ptr(self.ctx, tex, C.byref(p), C.byref(pitch)))
@@ -250,6 +261,12 @@ class CudaDevice(DeviceBase):
         f = C.c_uint64(0)
         self._check(self.lib.wrcu_read_pixels_async(self.ctx, tex, x, y, w, h, out.ctypes.data, out.strides[0],
                                                     C.byref(f)))
+        return f.value
+
+    def fence_insert(self):
+        """glFenceSync on the draw stream; page-locked upload buffers are free again once it is waited on."""
+        f = C.c_uint64(0)
+        self._check(self.lib.wrcu_fence_insert(self.ctx, C.byref(f)))
         return f.value
 
     def fence_wait(self, fence):

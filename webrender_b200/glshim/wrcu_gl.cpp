@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -43,7 +44,7 @@ enum {
   GL_OUT_OF_MEMORY = 0x0505,
   GL_RGBA32F = 0x8814, GL_RGBA8 = 0x8058, GL_R8 = 0x8229, GL_RG8 = 0x822B, GL_RG = 0x8227, GL_RGBA32I = 0x8D82, GL_DEPTH_COMPONENT24 = 0x81A6,
   GL_DEPTH_COMPONENT16 = 0x81A5, GL_DEPTH_COMPONENT32 = 0x81A7, GL_BGRA8 = 0x93A1,
-  GL_UNSIGNED_BYTE = 0x1401, GL_UNSIGNED_SHORT = 0x1403, GL_INT = 0x1404, GL_FLOAT = 0x1406,
+  GL_BYTE = 0x1400, GL_UNSIGNED_BYTE = 0x1401, GL_SHORT = 0x1402, GL_UNSIGNED_SHORT = 0x1403, GL_INT = 0x1404, GL_FLOAT = 0x1406,
   GL_RED = 0x1903, GL_RGBA = 0x1908, GL_RGBA_INTEGER = 0x8D99, GL_BGRA = 0x80E1,
   GL_ARRAY_BUFFER = 0x8892, GL_ELEMENT_ARRAY_BUFFER = 0x8893, GL_PIXEL_PACK_BUFFER = 0x88EB,
   GL_PIXEL_UNPACK_BUFFER = 0x88EC,
@@ -359,6 +360,10 @@ void upload(Tex& t, int x, int y, int w, int h, GLenum format, const void* data)
   }
   if (!src || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t.w || y + h > t.h) { set_error(GL_INVALID_VALUE); return; }
   const size_t src_stride = (size_t)(ctx->unpack_row_length > 0 ? ctx->unpack_row_length : w) * bpp;
+  if (ctx->unpack_buffer) {  // the whole source image must lie inside the PBO
+    const size_t off = (size_t)(uintptr_t)data, need = (size_t)(h - 1) * src_stride + (size_t)w * bpp;
+    if (off + need > ctx->buf[ctx->unpack_buffer].data.size()) { set_error(GL_INVALID_OPERATION); return; }
+  }
   if (!t.shadow.empty()) {
     for (int r = 0; r < h; r++)
       memcpy(t.shadow.data() + ((size_t)(y + r) * t.w + x) * 16, src + (size_t)r * src_stride, (size_t)w * 16);
@@ -734,7 +739,27 @@ void DrawElementsInstanced(GLenum mode, GLsizei count, GLenum type, GLintptr, GL
   }
   if (!ibuf || stride <= 0) { set_error(GL_INVALID_OPERATION); return; }
   Buf& ib = ctx->buf[ibuf];
-  if (first + (size_t)stride * (size_t)instancecount > ib.data.size() + (size_t)stride) { set_error(GL_INVALID_OPERATION); return; }
+  // every fetched attribute must lie inside the buffer; the last record may be shorter than the stride,
+  // in which case the records are repacked (the backend copies stride * n bytes)
+  size_t rec_end = 0;
+  for (int i = 0; i < 16; i++) {
+    const Attr& a = v.a[i];
+    if (!a.enabled || a.divisor != 1) continue;
+    const size_t tb = (a.type == GL_UNSIGNED_BYTE || a.type == GL_BYTE) ? 1 : (a.type == GL_UNSIGNED_SHORT || a.type == GL_SHORT) ? 2 : 4;
+    rec_end = std::max(rec_end, a.offset - first + (size_t)a.size * tb);
+  }
+  if (rec_end > (size_t)stride ||
+      first + (size_t)stride * (size_t)(instancecount - 1) + rec_end > ib.data.size()) { set_error(GL_INVALID_OPERATION); return; }
+  const uint8_t* inst_ptr = ib.data.data() + first;
+  std::vector<uint8_t> padded;
+  if (first + (size_t)stride * (size_t)instancecount > ib.data.size()) {
+    padded.assign((size_t)stride * (size_t)instancecount, 0);
+    memcpy(padded.data(), inst_ptr, ib.data.size() - first);
+    inst_ptr = padded.data();
+  }
+  // SWGL implements LEQUAL and LESS only (gl.cc:1352-1361 asserts on anything else); the renderer's
+  // batches use LEQUAL (renderer/mod.rs:2829).  Anything else is refused rather than drawn as LEQUAL.
+  if (ctx->depth_test && ctx->depth_func != GL_LEQUAL) { set_error(GL_INVALID_ENUM); return; }
   if (!sync_tables()) return;
   if (!bind_target(ctx->draw_fbo, p.uTransform)) return;
   wrcu_draw_state st;
@@ -754,7 +779,7 @@ void DrawElementsInstanced(GLenum mode, GLsizei count, GLenum type, GLintptr, GL
   st.scissor_enabled = ctx->scissor_test ? 1 : 0;
   memcpy(st.scissor, ctx->scissor, sizeof st.scissor);
   memcpy(st.blend_color, ctx->blend_color, sizeof st.blend_color);
-  check(wrcu_draw_batch(ctx->dev, p.kind, p.feats, &st, ib.data.data() + first, (size_t)stride, instancecount));
+  check(wrcu_draw_batch(ctx->dev, p.kind, p.feats, &st, inst_ptr, (size_t)stride, instancecount));
 }
 
 // ---- readback and copies --------------------------------------------------------------------------
@@ -763,12 +788,15 @@ void ReadPixels(GLint x, GLint y, GLsizei width, GLsizei height, GLenum format, 
   wrcu_tex depth = 0;
   if (!fbo_attachments(ctx->read_fbo, &color, &depth)) { set_error(GL_INVALID_OPERATION); return; }
   uint8_t* dst = (uint8_t*)data;
-  if (ctx->pack_buffer) {
-    Buf& b = ctx->buf[ctx->pack_buffer];
-    dst = b.data.data() + (size_t)(uintptr_t)data;
-  }
   const int bpp = bytes_per_pixel(color->ifmt);
   const size_t stride = (size_t)(ctx->pack_row_length > 0 ? ctx->pack_row_length : width) * bpp;
+  if (width <= 0 || height <= 0) { set_error(GL_INVALID_VALUE); return; }
+  if (ctx->pack_buffer) {
+    Buf& b = ctx->buf[ctx->pack_buffer];
+    const size_t off = (size_t)(uintptr_t)data, need = (size_t)(height - 1) * stride + (size_t)width * bpp;
+    if (off > b.data.size() || off + need > b.data.size()) { set_error(GL_INVALID_OPERATION); return; }
+    dst = b.data.data() + off;
+  }
   check(wrcu_read_pixels(ctx->dev, color->dev, x, y, width, height, dst, stride));
   if (bpp == 4 && format == GL_RGBA)
     for (int r = 0; r < height; r++) {
