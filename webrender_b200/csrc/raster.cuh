@@ -46,6 +46,13 @@ struct RasterArgs {
   int any_words;
   int bin_words, bin_tiles_x;
   const float* row_tab;  // row tables written by the setup kernel (CmdCold::row_off)
+  // Depth runs (rasterize.h:601-657): with depth testing on, the reference draws each maximal run of
+  // passing samples of a span as a span of its own.  rl != nullptr while a run AFTER the first of a
+  // (command,row) is being shaded: the four chunk lanes of every interpolant (rl[lane * WR_NI + i]) as
+  // the walk over the earlier runs left them.  fail_pool: per (command,row) bitmaps of failing samples
+  // written by wr_depth_fail_rows (CmdCold::fail_off).
+  const float* rl;
+  const uint32_t* fail_pool;
   const void* tmaps;     // device table of CUtensorMap records, indexed by TexView::tmap_id
   int copy_eligible;     // composite: a copy-class batch (BatchInfo::all_copy) is drawn by wr_composite_copy
 };
@@ -163,8 +170,8 @@ WRD bool wr_general_row(const CmdCold& k, const CmdHot& c, int y, GenRow& g, Cmd
 }
 
 template <int N>
-WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step,
-                       float* li_out = nullptr, float* ri_out = nullptr) {
+WRD void wr_row_interp_raw(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step,
+                           float* li_out, float* ri_out) {
   if (c.flags & CMD_GENERAL) {
     // left.interp / right.interp of the walk at this row, then the span's start
     // value and per-pixel step (rasterize.h:1003-1017)
@@ -251,18 +258,63 @@ WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, i
 #endif
 }
 
+template <int N>
+WRD void wr_row_interp(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step,
+                       float* li_out = nullptr, float* ri_out = nullptr) {
+  wr_row_interp_raw<N>(a, k, c, y, o, step, li_out, ri_out);
+  if (a.rl) {  // a later depth run of this row: lane 0 continues from the walk, not from the span equation
+#pragma unroll
+    for (int i = 0; i < N; i++) o[i] = a.rl[i];
+  }
+}
+
+// The chunk lanes across a passing depth run of n pixels (draw_depth_span, rasterize.h:612-657): the
+// `drawn` pixels a span shader committed advance them in one step (DISPATCH_DRAW_SPAN:
+// step_interp_inputs(drawn), swgl_ext.h:1916-1923), every remaining chunk — a partial tail included —
+// by one interp_step per run().  `is` = interp_step = 4 * step.
+WRD float wr_run_advance(float v, float is, int n, int drawn) {
+  if (drawn > 0) v = __fadd_rn(v, __fmul_rn(is, __fmul_rn((float)drawn, 0.25f)));
+  return wr_repeat_add(v, is, (n - drawn + 3) >> 2);
+}
+// ... and across the failed samples up to the next run: skip(skip - pad), pad = what the partial tail
+// chunk of the previous run over-advanced (rasterize.h:649-656).
+WRD float wr_run_skip(float v, float is, int prev_len, int skip) {
+  const int pad = (prev_len & 3) ? 4 - (prev_len & 3) : 0;
+  return __fadd_rn(v, __fmul_rn(is, __fmul_rn((float)(skip - pad), 0.25f)));
+}
+// How a shader takes part in the depth-run walk: n = interpolants per vertex its Row is built from
+// (0: the shader's source does not depend on them), drawn() = pixels of the run its span shader
+// committed (from the Row that row_setup built for that run).
+template <class S> struct WrRun {
+  enum { n = 0 };
+  WRD_MEMBER int drawn(const typename S::Row&) { return 0; }
+};
+
 // Value of interpolant lanes at pixel x of the span: lane j of chunk k.  Chunk
 // offset accumulates sequentially as init_interp does (glsl.h:3083-3088), then
 // the chunk advance is one multiply-add (step_interp_inputs(drawn) after a
 // span body; exact for the 1:1 mappings that dominate).
 template <int N>
-WRD void wr_interp_at(const float* o, const float* step, int rel, float* out) {
+WRD void wr_interp_at_plain(const float* o, const float* step, int rel, float* out) {  // setup kernels: no depth runs
   int j = rel & 3;
   float kf = (float)(rel >> 2);
 #pragma unroll
   for (int i = 0; i < N; i++) {
     float v = o[i];
-    for (int s = 0; s < j; s++) v = __fadd_rn(v, step[i]);         // init_interp lanes first,
+    for (int s = 0; s < j; s++) v = __fadd_rn(v, step[i]);
+    v = __fadd_rn(v, __fmul_rn(__fmul_rn(step[i], 4.0f), kf));
+    out[i] = v;
+  }
+}
+template <int N>
+WRD void wr_interp_at(const RasterArgs& a, const float* o, const float* step, int rel, float* out) {
+  int j = rel & 3;
+  float kf = (float)(rel >> 2);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float v = o[i];
+    if (a.rl) v = a.rl[j * WR_NI + i];                              // a later depth run: the lanes as the walk left them
+    else for (int s = 0; s < j; s++) v = __fadd_rn(v, step[i]);    // init_interp lanes first,
     v = __fadd_rn(v, __fmul_rn(__fmul_rn(step[i], 4.0f), kf));     // then interp_step * chunks
     out[i] = v;
   }
@@ -300,7 +352,7 @@ WRD bool wr_clip_dist_row(const RasterArgs& a, const CmdCold& k, CmdHot& c, int 
 // once per command/row/tile); wr_chunk_lane finishes the walk for one pixel
 // (at most 32 more additions inside a 128-pixel tile).
 template <int N>
-WRD int wr_chunk_base(const float* o, const float* step, const CmdHot& c, int tx0, float (*base)[N]) {
+WRD int wr_chunk_base(const RasterArgs& a, const float* o, const float* step, const CmdHot& c, int tx0, float (*base)[N]) {
   int kb = max(0, (max(tx0, (int)c.x0) - (int)c.x0) >> 2);
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -310,7 +362,7 @@ WRD int wr_chunk_base(const float* o, const float* step, const CmdHot& c, int tx
     for (int j = 0; j < 4; j++) {
       // init_interp: lane j of chunk 0 = lane j-1 + step (glsl.h:3083-3088);
       // every later chunk adds interp_step to each lane
-      float l = v;
+      float l = a.rl ? a.rl[j * WR_NI + i] : v;
       l = wr_repeat_add(l, is, kb);
       base[j][i] = l;
       v = __fadd_rn(v, step[i]);
@@ -350,7 +402,7 @@ struct QuadShader {
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       u[j] = uv[0];
       v[j] = uv[1];
     }
@@ -375,7 +427,7 @@ struct QuadShader {
     // fragment path: fs_sample_color0 (sample_color0.glsl:25-31), v_color == 1
     const CmdCold& k = a.cold[c.cold];
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     float tex[4];
     wr_tex_fragment(t, wr_clamp(uv[0], k.f[0], k.f[2]), wr_clamp(uv[1], k.f[1], k.f[3]), tex);
     Px o;

@@ -44,7 +44,7 @@ struct SetupArgs {
   TexView color2;
   TexView clip_mask;
   const TexView* tex_list;  // wrcu_draw_composite_tiles: sColor0 of instance i (nullptr: color0 for all)
-  int depth_on;             // the draw tests depth (copy-class composites are refused)
+  int copy_ok;              // composite: blend off or premultiplied-alpha over, no depth → copy class possible
 };
 
 // A setup kernel = one thread per instance running <name>_one.  Under the host

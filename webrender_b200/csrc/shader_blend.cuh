@@ -109,7 +109,7 @@ struct BlendShader {
     const CmdCold& k = a.cold[c.cold];
     wr_row_interp<2>(a, k, c, y, r.o, r.step);
     r.pd = (1.0f - k.f[5]) * k.f[4] + k.f[5];
-    r.kb = wr_chunk_base<2>(r.o, r.step, c, tx0, r.base);
+    r.kb = wr_chunk_base<2>(a, r.o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];

@@ -59,7 +59,7 @@ struct PosRow {
 WRD void wr_pos_row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, PosRow& r) {
   const CmdCold& k = a.cold[c.cold];
   wr_row_interp<2>(a, k, c, y, r.o, r.step);
-  r.kb = wr_chunk_base<2>(r.o, r.step, c, tx0, r.base);
+  r.kb = wr_chunk_base<2>(a, r.o, r.step, c, tx0, r.base);
 }
 WRD void wr_pos_at(const PosRow& r, int rel, float* p, float* aa_range) {
   const int kc = rel >> 2, j = rel & 3;

@@ -144,7 +144,7 @@ struct BoxShadowShader {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       float p[6];
-      wr_interp_at<6>(r.L0, r.step, j, p);
+      wr_interp_at<6>(a, r.L0, r.step, j, p);
       l.ulx[j] = p[4] * w; l.uly[j] = p[5] * w;
       l.lx[j] = p[0] * w;  l.ly[j] = p[1] * w;
     }

@@ -24,7 +24,7 @@ struct CompositeShader {
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       u[j] = uv[0];
       v[j] = uv[1];
     }
@@ -39,7 +39,7 @@ struct CompositeShader {
       return px_apply_color(wr_tex_body(t, r.tr, rel), col);
     }
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     bool fast = k.g[4] != 0.0f;
     float cu = uv[0], cv = uv[1];
     if (!fast) {
@@ -119,27 +119,26 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
     bool copyc = false;
     const CmdHot h = a.hot[idx];
     const int tiw = tex0.w, tih = tex0.h;
-    if (!a.blend_enabled && !a.depth_on && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 &&
+    if (a.copy_ok && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 &&
         tex0.tmap_id && is_white && !(h.flags & (CMD_GENERAL | CMD_AA | CMD_MASK | CMD_CLIP_DIST)) &&
         (tiw & (tiw - 1)) == 0 && (tih & (tih - 1)) == 0 && k->xl == floorf(k->xl) && k->xr == floorf(k->xr) &&
         k->i_lt[0] == k->i_lb[0] && k->i_rt[0] == k->i_rb[0] && k->i_lt[1] == k->i_rt[1] && k->i_lb[1] == k->i_rb[1]) {
+      k->i[2] = 0;
       const float su = (k->i_rt[0] - k->i_lt[0]) / (k->xr - k->xl);
       const float u0 = k->i_lt[0] + ((float)h.x0 + 0.5f - k->xl) * su;
       const float txf = u0 * tw - 0.5f;
       const float sl = (k->i_lb[1] - k->i_lt[1]) * k->yscale;
-      float v = k->i_lt[1] + ((float)h.y0 + 0.5f - k->yt) * sl;
+      const float v = k->i_lt[1] + ((float)h.y0 + 0.5f - k->yt) * sl;
       const float tyf = floorf(v * th);
       const int rows = (int)h.y1 - (int)h.y0;
-      bool okc = su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
-                 tyf >= 0.0f && tyf + (float)rows <= th;
-      for (int r = 0; okc && r < rows; r++) {
-        okc = fabsf(v * th - (tyf + (float)r + 0.5f)) <= (1.0f / 1024.0f);
-        v = v + sl;  // Edge::nextRow (rasterize.h:880-884)
-      }
-      if (okc) {
-        copyc = true;
+      if (su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
+          tyf >= 0.0f && tyf + (float)rows <= th && fabsf(v * th - (tyf + 0.5f)) <= (1.0f / 1024.0f)) {
         k->i[0] = (int)txf;
         k->i[1] = (int)tyf;
+        // an exact row step needs no further proof; otherwise the rows are checked against the row table
+        // (wr_composite_check_rows, warp-cooperative) and the candidate needs one
+        if (sl * th == 1.0f) copyc = true;
+        else if (k->row_off >= 0 && k->row_n == 2) { k->i[2] = 1; copyc = true; }
       }
     }
     if (!copyc) a.info->all_copy = 0;
@@ -152,12 +151,33 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
 #ifdef WRCU_HOSTEMU
 WR_SETUP_KERNEL(wr_setup_composite)
 #else
+// Copy-class candidates whose row step carries the rounding of yScale: every row's v (the left-edge sum
+// of interpolant 1 in the row table the warp has just filled) must sit within 1/1024 texel of its texel
+// centre.  The warp takes its candidates one at a time, rows strided over the lanes.
+__device__ void wr_composite_check_rows(const SetupArgs& a, int idx) {
+  const int lane = threadIdx.x & 31, wbase = idx - lane;
+  unsigned m = __ballot_sync(0xFFFFFFFFu, idx < a.n && a.hot[idx].x1 > a.hot[idx].x0 && a.cold[idx].i[2] == 1);
+  while (m) {
+    const int ci = wbase + __ffs((int)m) - 1;
+    m &= m - 1;
+    const CmdHot h = a.hot[ci];
+    const CmdCold& k = a.cold[ci];
+    const float th = (float)wr_composite_tex(k).h;
+    const float* t = a.row_tab + k.row_off;
+    const int rows = (int)h.y1 - (int)h.y0;
+    bool bad = false;
+    for (int r = lane; r < rows; r += 32) bad = bad || fabsf(t[(size_t)r * 4 + 2] * th - ((float)(k.i[1] + r) + 0.5f)) > (1.0f / 1024.0f);
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) a.info->all_copy = 0;
+  }
+}
 __global__ void wr_setup_composite(SetupArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) wr_reset_batch_info(a.info_next);
   if (idx < a.n) wr_setup_composite_one(a, idx);
   __syncwarp();
   wr_fill_row_tables_warp(a, idx);
+  __syncwarp();
+  wr_composite_check_rows(a, idx);
   // The copy kernel moves boxes of different instances concurrently: a copy-class batch must not
   // overlap itself (picture-cache tiles never do; surfaces that do keep the ordered tile kernel).
   if (gridDim.x > 1) {
@@ -177,10 +197,83 @@ __global__ void wr_setup_composite(SetupArgs a) {
 
 // ---- copy-class composite: the tile list as 2-D bulk-tensor copies (see tma.cuh) ----------------
 // Work items = 256x16-pixel boxes of every instance's rect, dealt round-robin to the persistent CTAs.
-// Thread 0 pipelines the boxes that lie wholly inside their rect through the copy engine
-// (WR_TMA_STAGES shared-memory slots, loads two boxes ahead of the stores); warps 1..3 copy the
-// ragged-edge boxes with plain accesses meanwhile.
-struct WrCopyItem { int inst, bx, by; };
+// Boxes wholly inside their rect go through the copy engine; ragged-edge boxes are moved by the
+// CTA's threads with plain accesses.
+//   opaque (blend off):  thread 0 alone drives a ring of WR_TMA_STAGES shared-memory slots — bulk load
+//     of the source box, bulk store of the same bytes into the framebuffer, loads two boxes ahead of
+//     the stores — while warps 1..3 copy the ragged boxes.
+//   premultiplied-alpha over (alpha tiles): each slot holds the source box AND the destination box
+//     (one barrier, two bulk loads); the 128 threads blend in shared memory (blend.h:473-474), then
+//     thread 0 bulk-stores the destination box and refills the slot that has just drained.
+struct WrBoxIter {
+  int i = -1, b = 0, nb = 0, nbx = 1, g = 0, w = 0, h = 0;
+  bool started = false;
+  CmdHot c;
+  // next box of this CTA that is (full == want_full); false when the batch is exhausted
+  __device__ bool next(const RasterArgs& a, bool want_full, int& bx, int& by) {
+    const int G = (int)gridDim.x;
+    for (;;) {
+      if (started) b += G;
+      started = true;
+      while (i < 0 || b >= nb) {
+        if (i >= 0) g += nb;
+        i++;
+        if (i >= a.n) return false;
+        c = a.hot[i];
+        w = (int)c.x1 - (int)c.x0;
+        h = (int)c.y1 - (int)c.y0;
+        if (w <= 0 || h <= 0) { nb = 0; b = 0; continue; }
+        nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W;
+        nb = nbx * ((h + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H);
+        b = ((int)blockIdx.x - g % G + G) % G;
+      }
+      bx = (b % nbx) * WR_TMA_BOX_W;
+      by = (b / nbx) * WR_TMA_BOX_H;
+      const bool full = bx + WR_TMA_BOX_W <= w && by + WR_TMA_BOX_H <= h;
+      if (full == want_full) return true;
+    }
+  }
+};
+
+WRD uint32_t wr_over_px(uint32_t d, uint32_t s) {  // premultiplied-alpha over, one BGRA8 pixel
+  const uint32_t cc = 255u - (s >> 24);
+  const uint32_t rb = wr_premult_over_pair(d & 0x00FF00FFu, s & 0x00FF00FFu, cc);
+  const uint32_t ga = wr_premult_over_pair((d >> 8) & 0x00FF00FFu, (s >> 8) & 0x00FF00FFu, cc);
+  return rb | (ga << 8);
+}
+
+// ragged-edge boxes by plain accesses: `t` of `nt` threads share the rows of each box
+template <bool BLEND>
+__device__ void wr_copy_ragged(const RasterArgs& a, int t, int nt) {
+  WrBoxIter it;
+  int bx, by;
+  while (it.next(a, false, bx, by)) {
+    const CmdCold& k = a.cold[it.c.cold];
+    const TexView& tv = wr_composite_tex(k);
+    const int bw = min(WR_TMA_BOX_W, it.w - bx), bh = min(WR_TMA_BOX_H, it.h - by);
+    for (int r = 0; r < bh; r++) {
+      const uint32_t* sp = (const uint32_t*)(tv.ptr + (size_t)(k.i[1] + by + r) * tv.pitch) + k.i[0] + bx;
+      uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)it.c.y0 + by + r) * a.tgt.color_pitch) + (int)it.c.x0 + bx;
+      if ((((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
+        const int nv = bw >> 2;
+        for (int q = t; q < nv; q += nt) {
+          uint4 sv = __ldg((const uint4*)sp + q);
+          if (BLEND) {
+            const uint4 dv = ((const uint4*)dp)[q];
+            sv = make_uint4(wr_over_px(dv.x, sv.x), wr_over_px(dv.y, sv.y), wr_over_px(dv.z, sv.z), wr_over_px(dv.w, sv.w));
+          }
+          ((uint4*)dp)[q] = sv;
+        }
+        for (int q = (nv << 2) + t; q < bw; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
+      } else {
+        for (int q = t; q < bw; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
+      }
+    }
+  }
+}
+
+#define WR_TMA_BLEND_STAGES 3
+template <bool BLEND>
 __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a) {
   extern __shared__ __align__(128) uint8_t wr_copy_smem[];
   __shared__ __align__(8) uint64_t full[WR_TMA_STAGES];
@@ -191,82 +284,95 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
   if (threadIdx.x == 0) {
     for (int s = 0; s < WR_TMA_STAGES; s++) wr_mbar_init(&full[s], 1);
     wr_fence_mbar_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // ---- the copy engine's driver: every full box of this CTA, loads DEPTH boxes ahead of stores ----
-    constexpr int DEPTH = WR_TMA_STAGES - 2;
-    int ring_inst[WR_TMA_STAGES], ring_x[WR_TMA_STAGES], ring_y[WR_TMA_STAGES];
-    int issued = 0, stored = 0;
-    int g = 0;  // global box counter over all instances
-    auto store_one = [&]() {
-      const int s = stored % WR_TMA_STAGES;
-      wr_mbar_wait(&full[s], (uint32_t)((stored / WR_TMA_STAGES) & 1));
-      wr_tma_store_2d(dst_map, ring_x[s], ring_y[s], wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES);
-      wr_tma_commit();
-      stored++;
-    };
+    wr_tma_acquire_map(dst_map);
     for (int i = 0; i < a.n; i++) {
       const CmdHot c = a.hot[i];
-      const int w = (int)c.x1 - (int)c.x0, hgt = (int)c.y1 - (int)c.y0;
-      if (w <= 0 || hgt <= 0) continue;
-      const CmdCold& k = a.cold[c.cold];
-      const int sx0 = k.i[0], sy0 = k.i[1];
-      const CUtensorMap* src_map = maps + wr_composite_tex(k).tmap_id;
-      const int nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W, nby = (hgt + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H;
-      const int nb = nbx * nby;
-      // first box of this instance that belongs to this CTA
-      int b = ((int)blockIdx.x - g % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;
-      for (; b < nb; b += gridDim.x) {
-        const int bx = (b % nbx) * WR_TMA_BOX_W, by = (b / nbx) * WR_TMA_BOX_H;
-        if (bx + WR_TMA_BOX_W > w || by + WR_TMA_BOX_H > hgt) continue;  // ragged edge: the other warps
+      if (c.x1 > c.x0 && c.y1 > c.y0) wr_tma_acquire_map(maps + wr_composite_tex(a.cold[c.cold]).tmap_id);
+    }
+  }
+  __syncthreads();
+  int bx, by;
+  if (!BLEND) {
+    if (threadIdx.x == 0) {
+      // ---- the copy engine's driver: every full box of this CTA, loads DEPTH boxes ahead of stores ----
+      constexpr int DEPTH = WR_TMA_STAGES - 2;
+      int ring_x[WR_TMA_STAGES] = {0}, ring_y[WR_TMA_STAGES] = {0};
+      int issued = 0, stored = 0;
+      auto store_one = [&]() {
+        const int s = stored % WR_TMA_STAGES;
+        wr_mbar_wait(&full[s], (uint32_t)((stored / WR_TMA_STAGES) & 1));
+        wr_tma_store_2d(dst_map, ring_x[s], ring_y[s], wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES);
+        wr_tma_commit();
+        stored++;
+      };
+      WrBoxIter it;
+      while (it.next(a, true, bx, by)) {
+        const CmdCold& k = a.cold[it.c.cold];
         const int s = issued % WR_TMA_STAGES;
         if (issued >= WR_TMA_STAGES) wr_tma_wait_read<1>();  // the store that last read slot s has drained
-        ring_x[s] = (int)c.x0 + bx;
-        ring_y[s] = (int)c.y0 + by;
-        ring_inst[s] = i;
+        ring_x[s] = (int)it.c.x0 + bx;
+        ring_y[s] = (int)it.c.y0 + by;
         wr_mbar_expect_tx(&full[s], WR_TMA_BOX_BYTES);
-        wr_tma_load_2d(wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES, src_map, sx0 + bx, sy0 + by, &full[s]);
+        wr_tma_load_2d(wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES, maps + wr_composite_tex(k).tmap_id, k.i[0] + bx,
+                       k.i[1] + by, &full[s]);
         issued++;
         if (issued - stored > DEPTH) store_one();
       }
-      g += nb;
+      while (stored < issued) store_one();
+      wr_tma_wait_all<0>();  // stores complete before the CTA's shared memory is released
+    } else if (threadIdx.x >= 32) {
+      wr_copy_ragged<false>(a, threadIdx.x - 32, WR_TMA_THREADS - 32);
     }
-    while (stored < issued) store_one();
-    wr_tma_wait_all<0>();  // stores complete before the CTA's shared memory is released
-    (void)ring_inst;
-  } else if (threadIdx.x >= 32) {
-    // ---- ragged-edge boxes: plain row copies, 16 bytes per thread where both sides are aligned ----
-    const int t = threadIdx.x - 32, nt = WR_TMA_THREADS - 32;
-    int g = 0;
-    for (int i = 0; i < a.n; i++) {
-      const CmdHot c = a.hot[i];
-      const int w = (int)c.x1 - (int)c.x0, hgt = (int)c.y1 - (int)c.y0;
-      if (w <= 0 || hgt <= 0) continue;
-      const CmdCold& k = a.cold[c.cold];
-      const TexView& tv = wr_composite_tex(k);
-      const int nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W, nby = (hgt + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H;
-      const int nb = nbx * nby;
-      int b = ((int)blockIdx.x - g % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;
-      for (; b < nb; b += gridDim.x) {
-        const int bx = (b % nbx) * WR_TMA_BOX_W, by = (b / nbx) * WR_TMA_BOX_H;
-        if (bx + WR_TMA_BOX_W <= w && by + WR_TMA_BOX_H <= hgt) continue;  // full box: the copy engine
-        const int bw = min(WR_TMA_BOX_W, w - bx), bh = min(WR_TMA_BOX_H, hgt - by);
-        for (int r = 0; r < bh; r++) {
-          const uint32_t* sp = (const uint32_t*)(tv.ptr + (size_t)(k.i[1] + by + r) * tv.pitch) + k.i[0] + bx;
-          uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)c.y0 + by + r) * a.tgt.color_pitch) + (int)c.x0 + bx;
-          if ((((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
-            const int nv = bw >> 2;
-            for (int q = t; q < nv; q += nt) ((uint4*)dp)[q] = __ldg((const uint4*)sp + q);
-            for (int q = (nv << 2) + t; q < bw; q += nt) dp[q] = __ldg(sp + q);
-          } else {
-            for (int q = t; q < bw; q += nt) dp[q] = __ldg(sp + q);
-          }
-        }
-      }
-      g += nb;
-    }
+    return;
   }
+  // ---- blended: all threads walk the CTA's full boxes in step; thread 0 also feeds the ring ----
+  constexpr int ST = WR_TMA_BLEND_STAGES, DEPTH = ST - 1;
+  WrBoxIter prod, cons;
+  auto issue = [&](int n) {  // thread 0: source and destination box of the producer's current item → slot n % ST
+    const CmdCold& k = a.cold[prod.c.cold];
+    uint8_t* slot = wr_copy_smem + (size_t)(n % ST) * 2 * WR_TMA_BOX_BYTES;
+    wr_mbar_expect_tx(&full[n % ST], 2 * WR_TMA_BOX_BYTES);
+    wr_tma_load_2d(slot, maps + wr_composite_tex(k).tmap_id, k.i[0] + bx, k.i[1] + by, &full[n % ST]);
+    wr_tma_load_2d(slot + WR_TMA_BOX_BYTES, dst_map, (int)prod.c.x0 + bx, (int)prod.c.y0 + by, &full[n % ST]);
+  };
+  int nload = 0;
+  bool more = true;
+  if (threadIdx.x == 0)
+    for (int d = 0; d < DEPTH && more; d++) {
+      more = prod.next(a, true, bx, by);
+      if (more) issue(nload++);
+    }
+  int j = 0;
+  while (cons.next(a, true, bx, by)) {
+    const int s = j % ST;
+    wr_mbar_wait(&full[s], (uint32_t)((j / ST) & 1));
+    uint4* sp = (uint4*)(wr_copy_smem + (size_t)s * 2 * WR_TMA_BOX_BYTES);
+    uint4* dp = sp + WR_TMA_BOX_BYTES / 16;
+#pragma unroll 4
+    for (int q = threadIdx.x; q < WR_TMA_BOX_BYTES / 16; q += WR_TMA_THREADS) {
+      const uint4 sv = sp[q], dv = dp[q];
+      dp[q] = make_uint4(wr_over_px(dv.x, sv.x), wr_over_px(dv.y, sv.y), wr_over_px(dv.z, sv.z), wr_over_px(dv.w, sv.w));
+    }
+    wr_fence_proxy_async();  // the blended box → visible to the copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      wr_tma_store_2d(dst_map, (int)cons.c.x0 + bx, (int)cons.c.y0 + by, dp);
+      wr_tma_commit();
+      if (more) {
+        int pbx = bx, pby = by;  // (issue() reads bx/by of the producer's item)
+        more = prod.next(a, true, bx, by);
+        if (more) {
+          wr_tma_wait_read<1>();  // item j-1's store (slot (j + DEPTH) % ST) has finished reading shared memory
+          issue(nload++);
+        }
+        bx = pbx; by = pby;
+      }
+    }
+    j++;
+  }
+  if (threadIdx.x == 0) wr_tma_wait_all<0>();
+  __syncthreads();
+  wr_copy_ragged<true>(a, threadIdx.x, WR_TMA_THREADS);
 }
 #endif
 

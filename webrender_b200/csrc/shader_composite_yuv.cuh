@@ -112,7 +112,7 @@ struct CompositeYuvShader {
     // interp_step) — scaled video samples exactly on texel boundaries, where that sum's rounding
     // decides the texel.
     float uvj[4][6];
-    for (int j = 0; j < 4; j++) wr_interp_at<6>(r.o, r.step, j, uvj[j]);
+    for (int j = 0; j < 4; j++) wr_interp_at<6>(a, r.o, r.step, j, uvj[j]);
     float q[3][2][4], st[3][2];
     for (int p = 0; p < 3; p++) {
       const TexView& t = plane(a, p);
@@ -241,7 +241,7 @@ struct CompositeYuvShader {
         uv[2 * p + 1] = qv;
       }
     } else {
-      wr_interp_at<6>(r.o, r.step, rel, uv);
+      wr_interp_at<6>(a, r.o, r.step, rel, uv);
     }
     float cc[3][2];
     for (int p = 0; p < 3; p++) {
@@ -392,7 +392,7 @@ WRD void wr_yuv_chain_table(const SetupArgs& a, int idx, int planes, const TexVi
   float v[12], st[3];
   for (int j = 0; j < 4; j++) {
     float uv[6];
-    wr_interp_at<6>(o, step, j, uv);
+    wr_interp_at_plain<6>(o, step, j, uv);
     for (int p = 0; p < 3; p++) v[p * 4 + j] = p < planes ? wr_linear_quantize(uv[2 * p], tv[p]->w) : 0.0f;
   }
   for (int p = 0; p < 3; p++) st[p] = 4.0f * (v[p * 4 + 1] - v[p * 4 + 0]);

@@ -69,7 +69,7 @@ struct FastLinearShader {
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool, Row& r) {
     const CmdCold& k = a.cold[c.cold];
     wr_row_interp<1>(a, k, c, y, r.o, r.step);
-    r.kb = wr_chunk_base<1>(r.o, r.step, c, tx0, r.base);
+    r.kb = wr_chunk_base<1>(a, r.o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];
@@ -95,7 +95,7 @@ struct ConicShader {
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool, Row& r) {
     const CmdCold& k = a.cold[c.cold];
     wr_row_interp<2>(a, k, c, y, r.o, r.step);
-    r.kb = wr_chunk_base<2>(r.o, r.step, c, tx0, r.base);
+    r.kb = wr_chunk_base<2>(a, r.o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];
@@ -162,7 +162,7 @@ struct RadialShader {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       float p[2];
-      wr_interp_at<2>(r.o, r.step, j, p);
+      wr_interp_at<2>(a, r.o, r.step, j, p);
       px[j] = p[0];
       py[j] = p[1];
     }
@@ -313,7 +313,7 @@ struct RadialShader {
     int rel = x - c.x0;
     if (rel < r.body_len) return r.out[x - r.own0];
     float p[2];
-    wr_interp_at<2>(r.o, r.step, rel, p);
+    wr_interp_at<2>(a, r.o, r.step, rel, p);
     float offset = sqrtf(p[0] * p[0] + p[1] * p[1]) - k.f[0];
     if (k.i[3]) return wr_quad_grad_fragment(a, c, k, offset);  // ps_quad_radial_gradient
     return wr_grad_fragment(a, k, offset);
@@ -342,7 +342,7 @@ struct QuadConicShader {
   WRD_MEMBER void row_setup(const RasterArgs& a, const CmdHot& c, int y, int tx0, bool, Row& r) {
     const CmdCold& k = a.cold[c.cold];
     wr_row_interp<2>(a, k, c, y, r.o, r.step);
-    r.kb = wr_chunk_base<2>(r.o, r.step, c, tx0, r.base);
+    r.kb = wr_chunk_base<2>(a, r.o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];

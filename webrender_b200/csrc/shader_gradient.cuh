@@ -229,7 +229,7 @@ struct GradientShader {
     GradWalk& w = r.w;
     for (int j = 0; j < 4; j++) {
       float p[2];
-      wr_interp_at<2>(r.o, r.step, j, p);
+      wr_interp_at<2>(a, r.o, r.step, j, p);
       w.px[j] = p[0];
       w.py[j] = p[1];
     }
@@ -301,7 +301,7 @@ struct GradientShader {
     }
     // fragment path (brush_linear_gradient.glsl:73-91, gradient.glsl:45-61)
     float p[2];
-    wr_interp_at<2>(r.o, r.step, rel, p);
+    wr_interp_at<2>(a, r.o, r.step, rel, p);
     if (!k.i[2]) { p[0] = wr_fract(p[0]); p[1] = wr_fract(p[1]); }
     float offset = (p[0] * k.f[0] + p[1] * k.f[1]) - k.f[2];
     offset = offset - floorf(offset) * k.f[3];

@@ -23,7 +23,7 @@ struct ImageShader {
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       u[j] = uv[0] * r.pd + k.f[4];
       v[j] = uv[1] * r.pd + k.f[5];
     }
@@ -39,7 +39,7 @@ struct ImageShader {
       return px_apply_color(wr_tex_body(t, r.tr, rel), col);
     }
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     float ru = uv[0] * r.pd + k.f[4], rv = uv[1] * r.pd + k.f[5];
     float texel[4], col[4];
     wr_tex_fragment(t, wr_clamp(ru, k.f[0], k.f[2]), wr_clamp(rv, k.f[1], k.f[3]), texel);
@@ -143,7 +143,7 @@ struct ImageRepeatShader {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       w.u[j] = uv[0] * r.pd;
       w.v[j] = uv[1] * r.pd;
     }
@@ -261,7 +261,7 @@ struct ImageRepeatShader {
     }
     // fragment path: compute_repeated_uvs (brush_image.glsl:319-352)
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     const float usx = k.g[8] - k.f[4], usy = k.g[9] - k.f[5];
     float lu = uv[0] * r.pd, lv = uv[1] * r.pd, ru, rv;
     if (k.g[6] != 0.0f) {

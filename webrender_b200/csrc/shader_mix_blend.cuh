@@ -82,7 +82,7 @@ struct MixBlendShader {
     const CmdCold& k = a.cold[c.cold];
     wr_row_interp<4>(a, k, c, y, r.o, r.step);
     r.pd = (1.0f - k.g[1]) * k.g[0] + k.g[1];
-    r.kb = wr_chunk_base<4>(r.o, r.step, c, tx0, r.base);
+    r.kb = wr_chunk_base<4>(a, r.o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const CmdCold& k = a.cold[c.cold];

@@ -21,7 +21,7 @@ struct OpacityShader {
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       u[j] = uv[0] * r.pd;
       v[j] = uv[1] * r.pd;
     }
@@ -36,7 +36,7 @@ struct OpacityShader {
       return px_apply_color(wr_tex_body(t, r.tr, rel), col);
     }
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     float texel[4];
     wr_tex_fragment(t, wr_clamp(uv[0] * r.pd, k.f[0], k.f[2]), wr_clamp(uv[1] * r.pd, k.f[1], k.f[3]), texel);
     Px o;

@@ -17,7 +17,7 @@ struct QuadMaskShader {
     r.g = k.g;
     float o[4];
     wr_row_interp<4>(a, k, c, y, o, r.step);
-    r.kb = wr_chunk_base<4>(o, r.step, c, tx0, r.base);
+    r.kb = wr_chunk_base<4>(a, o, r.step, c, tx0, r.base);
   }
   WRD_MEMBER Px source(const RasterArgs&, const CmdHot& c, const Row& r, int x, int, bool) {
     const float* g = r.g;

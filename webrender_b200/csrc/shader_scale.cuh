@@ -18,7 +18,7 @@ struct ScaleShader {
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       u[j] = uv[0];
       v[j] = uv[1];
     }
@@ -30,7 +30,7 @@ struct ScaleShader {
     int rel = x - c.x0;
     if (rel < r.tr.body_len) return wr_tex_body(t, r.tr, rel);
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     float col[4];
     wr_tex_fragment(t, wr_clamp(uv[0], k.f[0], k.f[2]), wr_clamp(uv[1], k.f[1], k.f[3]), col);
     Px o;

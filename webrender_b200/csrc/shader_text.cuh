@@ -19,7 +19,7 @@ struct TextShader {
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
-      wr_interp_at<2>(r.o, r.step, j, uv);
+      wr_interp_at<2>(a, r.o, r.step, j, uv);
       u[j] = uv[0];
       v[j] = uv[1];
     }
@@ -36,7 +36,7 @@ struct TextShader {
       return px_apply_color(wr_tex_body(t, r.tr, rel), col);
     }
     float uv[2];
-    wr_interp_at<2>(r.o, r.step, rel, uv);
+    wr_interp_at<2>(a, r.o, r.step, rel, uv);
     float mask[4], col[4];
     wr_tex_fragment(t, wr_clamp(uv[0], k.f[0], k.f[2]), wr_clamp(uv[1], k.f[1], k.f[3]), mask);
     if (k.g[6] != 0.0f) mask[1] = mask[2] = mask[3] = mask[0];

@@ -77,6 +77,12 @@ template <int N>
 __device__ __forceinline__ void wr_tma_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// A tensor map that lives in global memory and was (re)written since the copy engine last fetched it
+// — a texture handle recycled for another texture — must be re-acquired through the tensormap proxy
+// before use, or the engine may run on its cached copy of the old descriptor.
+__device__ __forceinline__ void wr_tma_acquire_map(const CUtensorMap* map) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void wr_tma_prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -938,7 +938,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   sa.row_tab = c->row_tab;
   sa.row_cap = c->row_cap;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
-  sa.depth_on = T.depth != nullptr;
+  sa.copy_ok = !T.depth && (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA);
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
   sa.color2 = tex_view(c, st->color[2]);
@@ -1195,16 +1195,19 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     case WRCU_KIND_COMPOSITE:
       if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
 #ifndef WRCU_HOSTEMU
-      if (c->tmaps_dev && T.tmap_id && st->blend == WRCU_BLEND_NONE && !T.depth) {
+      if (c->tmaps_dev && T.tmap_id && !T.depth &&
+          (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA)) {
         // copy-class tile lists (decided on the device, BatchInfo::all_copy) go through the copy engine;
         // whichever of the two kernels is not in charge returns at once
-        const size_t smem = (size_t)WR_TMA_STAGES * WR_TMA_BOX_BYTES;
+        const size_t smem0 = (size_t)WR_TMA_STAGES * WR_TMA_BOX_BYTES, smem1 = (size_t)WR_TMA_BLEND_STAGES * 2 * WR_TMA_BOX_BYTES;
         if (!c->copy_attr_set) {
-          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
           c->copy_attr_set = true;
         }
         ra.copy_eligible = 1;
-        wr_composite_copy<<<c->sm_count * 3, WR_TMA_THREADS, smem, c->stream>>>(ra);
+        if (st->blend == WRCU_BLEND_NONE) wr_composite_copy<false><<<c->sm_count * 3, WR_TMA_THREADS, smem0, c->stream>>>(ra);
+        else wr_composite_copy<true><<<c->sm_count * 2, WR_TMA_THREADS, smem1, c->stream>>>(ra);
         c->stats.kernel_launches++;
       }
 #endif
