@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdint.h>
 #include <vector>
+#include <stdlib.h>
 #include "../../webrender_b200/csrc/tma.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
@@ -67,7 +68,8 @@ static int check(const char* what, uint32_t* d_dst, size_t dpitch, int dx, int d
   printf("%-44s : %s (%d bad)\n", what, bad ? "MISMATCH" : "ok", bad);
   return bad != 0;
 }
-int main() {
+int main(int argc, char** argv) {
+  const int which = argc > 1 ? atoi(argv[1]) : -1;
   void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
   enc = (EncodeFn)fn;
@@ -90,18 +92,36 @@ int main() {
   CK(cudaFuncSetAttribute(copy_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_TMA_BOX_BYTES));
   CK(cudaFuncSetAttribute(copy_box_param, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_TMA_BOX_BYTES));
   int fails = 0;
-  copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 0, 0, 0, 0);
-  fails += check("param maps, aligned coords", d_dst, dp, 0, 0, h.data(), SW, 0, 0);
-  copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 17, 5, 1041, 33);
-  fails += check("param maps, odd coords (17,5)->(1041,33)", d_dst, dp, 1041, 33, h.data(), SW, 17, 5);
+  if (which == 0) { copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 0, 0, 0, 0);
+  fails += check("param maps, aligned coords", d_dst, dp, 0, 0, h.data(), SW, 0, 0); }
+  if (which == 1) { copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 17, 5, 1041, 33);
+  fails += check("param maps, odd coords (17,5)->(1041,33)", d_dst, dp, 1041, 33, h.data(), SW, 17, 5); }
+  if (which == 7) { copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 16, 5, 1040, 33);
+  fails += check("param maps, 4-px aligned x, odd y", d_dst, dp, 1040, 33, h.data(), SW, 16, 5); }
+  if (which == 8) { copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 17, 5, 1040, 33);
+  fails += check("param maps, odd src x, aligned dst x", d_dst, dp, 1040, 33, h.data(), SW, 17, 5); }
+  if (which == 9) { copy_box_param<<<1, 32, WR_TMA_BOX_BYTES>>>(ms, md, 16, 5, 1041, 33);
+  fails += check("param maps, aligned src x, odd dst x", d_dst, dp, 1041, 33, h.data(), SW, 16, 5); }
+  if (which == 2) { copy_box<false><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 256, 16, 512, 64);
+  fails += check("global maps, no fence", d_dst, dp, 512, 64, h.data(), SW, 256, 16); }
+  if (which == 3) { copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 256, 32, 512, 128);
+  fails += check("global maps, acquire fence", d_dst, dp, 512, 128, h.data(), SW, 256, 32); }
+  if (which == 4) {
   copy_box<false><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 256, 16, 512, 64);
-  fails += check("global maps, no fence", d_dst, dp, 512, 64, h.data(), SW, 256, 16);
-  copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 256, 32, 512, 128);
-  fails += check("global maps, acquire fence", d_dst, dp, 512, 128, h.data(), SW, 256, 32);
+  fails += check("global maps, first use", d_dst, dp, 512, 64, h.data(), SW, 256, 16);
   // rewrite slot 1 with another texture's map: does the next kernel see the new descriptor?
   CK(cudaMemcpy(table + 1, &ms2, sizeof ms2, cudaMemcpyHostToDevice));
   copy_box<false><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 0, 64, 768, 256);
-  fails += check("global maps, slot rewritten, no fence", d_dst, dp, 768, 256, h2.data(), SW, 0, 64);
+  fails += check("global maps, slot rewritten, no fence", d_dst, dp, 768, 256, h2.data(), SW, 0, 64); }
+  if (which == 5) {
+  copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 256, 16, 512, 64);
+  fails += check("global maps, first use (fenced)", d_dst, dp, 512, 64, h.data(), SW, 256, 16);
+  CK(cudaMemcpy(table + 1, &ms2, sizeof ms2, cudaMemcpyHostToDevice));
+  copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 0, 64, 768, 256);
+  fails += check("global maps, slot rewritten, acquire fence", d_dst, dp, 768, 256, h2.data(), SW, 0, 64); }
+  if (which == 6) {
+  copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 256, 16, 512, 64);
+  fails += check("global maps, first use (fenced)", d_dst, dp, 512, 64, h.data(), SW, 256, 16);
   CK(cudaMemcpy(table + 1, &ms, sizeof ms, cudaMemcpyHostToDevice));
   copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 0, 80, 768, 512);
   fails += check("global maps, slot rewritten, acquire fence", d_dst, dp, 768, 512, h.data(), SW, 0, 80);
@@ -112,7 +132,7 @@ int main() {
   CUtensorMap ms3; if (make(&ms3, d_src3, SW, SH, sp)) return 1;
   CK(cudaMemcpy(table + 1, &ms3, sizeof ms3, cudaMemcpyHostToDevice));
   copy_box<true><<<1, 32, WR_TMA_BOX_BYTES>>>(table + 1, table + 2, 0, 96, 1024, 600);
-  fails += check("global maps, realloc'd, acquire fence", d_dst, dp, 1024, 600, h2.data(), SW, 0, 96);
+  fails += check("global maps, realloc'd, acquire fence", d_dst, dp, 1024, 600, h2.data(), SW, 0, 96); }
   printf("probe: %d failing case(s)\n", fails);
   return 0;
 }

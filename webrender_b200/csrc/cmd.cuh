@@ -20,6 +20,8 @@ enum : uint32_t {
   CMD_CONST_COLOR = 1u << 6, // fragment output is the constant colour in CmdHot.col
   CMD_GENERAL = 1u << 9,    // screen edges not axis-aligned: per-row spans from the edge walk (GenQuad)
   CMD_CLIP_DIST = 1u << 10,  // gl_ClipDistance in interpolants 2..5 bounds every span (rasterize.h:566-596)
+  CMD_COPY = 1u << 11,      // composite: an opaque / premultiplied-over 1:1 rectangle copy, drawn by wr_composite_copy when
+                            // the batch allows it (BatchInfo::all_copy)
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
 };
 
@@ -64,7 +66,11 @@ struct __align__(16) CmdCold {
   // interpolants of every row, 2*row_n floats per row (left, right per interpolant) from float
   // offset row_off of RasterArgs.row_tab; -1 = none, wr_row_interp walks the sums itself.
   int row_off;
-  int row_n, rpad[3];
+  int row_n;
+  // Depth runs: word offset of this command's failing-sample bitmaps in the batch's pool (-1 = none):
+  // per row of the hot rect 1 + fail_w words — [0] the number of failing samples inside the row's span,
+  // then bit i of the bitmap = sample hot.x0 + i fails the depth test (or lies outside the row's span).
+  int fail_off, fail_w, rpad;
 };
 
 // Per-(command,row) state of a general quad, computed by wr_general_row.
@@ -82,6 +88,7 @@ struct BatchInfo {
   int premul_valid;        // 1 while every command's colour lanes are <= its alpha lane
   int tile_counter;        // dynamic tile scheduler of the generic raster kernel
   int row_alloc;           // floats of the row-table pool handed out to this batch's commands
-  int all_copy;            // composite: 1 while every command is an opaque 1:1 tile copy (tma.cuh)
+  int all_copy;            // composite: 1 while no two commands of the batch overlap: CMD_COPY commands go to wr_composite_copy
+  int fail_alloc;          // words of the depth-run bitmap pool handed out to this batch's commands
 };
 #define WR_ROW_TAB_MIN 16

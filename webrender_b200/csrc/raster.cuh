@@ -290,6 +290,54 @@ template <class S> struct WrRun {
   WRD_MEMBER int drawn(const typename S::Row&) { return 0; }
 };
 
+// The walk itself, shared by the tile kernel and the host emulation: begin() before a run is shaded
+// (sets a.rl), end() after it with the run's span-shader pixel count.
+template <class S>
+struct WrRunWalk {
+  enum { NL = WrRun<S>::n };
+  float lanes[4 * WR_NI];
+  float is[WR_NI];
+  bool first;
+  int prev_end, prev_len;
+  WRD_METHOD void reset() { first = true; prev_end = 0; prev_len = 0; }
+  WRD_METHOD void begin(RasterArgs& a, const CmdCold& k, const CmdHot& cr, int y) {
+    a.rl = nullptr;
+    if (NL == 0) return;
+    if (first) {
+      // leading failed samples are skipped before init_span: the first run's interpolants come from the
+      // span equation at its own start (rasterize.h:984-1017), its lanes accumulate as init_interp does
+      float o[NL ? NL : 1], st[NL ? NL : 1];
+      wr_row_interp<(NL ? NL : 1)>(a, k, cr, y, o, st);
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        is[i] = __fmul_rn(st[i], 4.0f);
+        float v = o[i];
+        lanes[i] = v;
+        v = __fadd_rn(v, st[i]); lanes[WR_NI + i] = v;
+        v = __fadd_rn(v, st[i]); lanes[2 * WR_NI + i] = v;
+        v = __fadd_rn(v, st[i]); lanes[3 * WR_NI + i] = v;
+      }
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < NL; i++) lanes[j * WR_NI + i] = wr_run_skip(lanes[j * WR_NI + i], is[i], prev_len, (int)cr.x0 - prev_end);
+    a.rl = lanes;
+  }
+  WRD_METHOD void end(RasterArgs& a, const CmdHot& cr, int drawn) {
+    const int n = (int)cr.x1 - (int)cr.x0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int i = 0; i < NL; i++) lanes[j * WR_NI + i] = wr_run_advance(lanes[j * WR_NI + i], is[i], n, drawn);
+    first = false;
+    prev_end = cr.x1;
+    prev_len = n;
+    a.rl = nullptr;
+  }
+};
+
 // Value of interpolant lanes at pixel x of the span: lane j of chunk k.  Chunk
 // offset accumulates sequentially as init_interp does (glsl.h:3083-3088), then
 // the chunk advance is one multiply-add (step_interp_inputs(drawn) after a
@@ -444,6 +492,11 @@ struct QuadShader {
   }
 };
 
+template <> struct WrRun<QuadShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const QuadShader::Row& r) { return r.tr.body_len; }
+};
+
 // One pixel of one command through depth test, fragment stage, AA/mask
 // modifiers and the blend stage.  Shared by the tile kernel and (tests only) the
 // host emulation.  px = packed destination pixel (RGBA8) or value (R8).
@@ -518,18 +571,40 @@ static void wr_raster(const RasterArgs& a) {
         if (!wr_general_row(a.cold[c0.cold], c0, y, g, c)) continue;
       }
       if ((c.flags & CMD_CLIP_DIST) && !wr_clip_dist_row(ar, ar.cold[c.cold], c, y)) continue;
-      const RasterArgs& a = ar;  // shadows: the shaders see the row state
       typename S::Row row;
-      for (int tx0 = (c.x0 / WRCU_TILE_W) * WRCU_TILE_W; tx0 < c.x1; tx0 += WRCU_TILE_W) {
-      S::row_setup(a, c, y, tx0, FMT == WRCU_FMT_RGBA8, row);
-      for (int xx = max((int)c.x0, tx0); xx < min((int)c.x1, tx0 + WRCU_TILE_W); xx++) {
-        uint32_t px = FMT == WRCU_FMT_RGBA8 ? ((uint32_t*)rowp)[xx] : rowp[xx];
-        uint32_t zb = use_depth ? zrow[xx] : 0;
-        bool dirty = false, zdirty = false;
-        wr_shade_pixel<S, FMT>(a, c, row, xx, y, use_depth, px, zb, dirty, zdirty);
-        if (dirty) { if (FMT == WRCU_FMT_RGBA8) ((uint32_t*)rowp)[xx] = px; else rowp[xx] = (uint8_t)px; }
-        if (zdirty) zrow[xx] = zb;
-      }
+      // With depth testing on, every maximal run of passing samples is drawn as a span of its own
+      // (draw_depth_span, rasterize.h:612-657): chunk phase, span-shader body and tail restart at the run.
+      WrRunWalk<S> walk;
+      walk.reset();
+      int xs = c.x0;
+      while (xs < c.x1) {
+        CmdHot cr = c;
+        if (use_depth) {
+          while (xs < c.x1 && !(c.z <= zrow[xs])) xs++;
+          int s0 = xs;
+          while (xs < c.x1 && c.z <= zrow[xs]) xs++;
+          if (xs == s0) break;
+          cr.x0 = (short)s0;
+          cr.x1 = (short)xs;
+          walk.begin(ar, ar.cold[c.cold], cr, y);
+        } else {
+          xs = c.x1;
+        }
+        const RasterArgs& a = ar;  // shadows: the shaders see the row state
+        int drawn = 0;
+        for (int tx0 = (cr.x0 / WRCU_TILE_W) * WRCU_TILE_W; tx0 < cr.x1; tx0 += WRCU_TILE_W) {
+          S::row_setup(a, cr, y, tx0, FMT == WRCU_FMT_RGBA8, row);
+          if (tx0 <= cr.x0) drawn = WrRun<S>::drawn(row);
+          for (int xx = max((int)cr.x0, tx0); xx < min((int)cr.x1, tx0 + WRCU_TILE_W); xx++) {
+            uint32_t px = FMT == WRCU_FMT_RGBA8 ? ((uint32_t*)rowp)[xx] : rowp[xx];
+            uint32_t zb = use_depth ? zrow[xx] : 0;
+            bool dirty = false, zdirty = false;
+            wr_shade_pixel<S, FMT>(a, cr, row, xx, y, use_depth, px, zb, dirty, zdirty);
+            if (dirty) { if (FMT == WRCU_FMT_RGBA8) ((uint32_t*)rowp)[xx] = px; else rowp[xx] = (uint8_t)px; }
+            if (zdirty) zrow[xx] = zb;
+          }
+        }
+        if (use_depth) walk.end(ar, cr, drawn);
       }
     }
   }
@@ -557,12 +632,25 @@ static void wr_raster_solid_premult(const RasterArgs& a) {
 // narrow spans shaded one pixel per lane (see wr_raster_tile).
 template <class S> struct WrNarrowSpans { enum { v = 0 }; };
 
+// first index in [from, to) of a bit equal to `want` in the bitmap `w`; `to` when there is none (warp-uniform)
+WRD int wr_bits_next(const uint32_t* w, int from, int to, bool want) {
+  while (from < to) {
+    uint32_t v = __ldg(w + (from >> 5));
+    if (!want) v = ~v;
+    v &= 0xFFFFFFFFu << (from & 31);
+    if (v) return min((from & ~31) + __ffs((int)v) - 1, to);
+    from = (from & ~31) + 32;
+  }
+  return to;
+}
+
 // ---- the generic tile kernel (any command kind via the shader policy S, any
 // blend key).  S::row_setup computes per-(command,row) constants once per warp
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
 // S::source returns the fragment stage's output for one pixel as 16-bit lanes.
 template <class S, int FMT>
-WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, unsigned short* list) {
+WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, unsigned short* list,
+                        const bool skip_copy) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
@@ -631,7 +719,7 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
     if (candidate) {
       mine = a.hot[cidx];
       keep = mine.x1 > tx0 && mine.x0 < tx0 + WRCU_TILE_W && mine.y1 > ty0 && mine.y0 < ty0 + WRCU_TILE_H &&
-             mine.x1 > mine.x0;
+             mine.x1 > mine.x0 && !(skip_copy && (mine.flags & CMD_COPY));
       // Hidden-surface removal inside a batch: with blending and depth off a command that
       // overwrites every writable pixel of this tile makes all earlier commands of the batch
       // invisible here, so the pixel loop can start at the last such command.
@@ -660,6 +748,7 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
     for (int i = first_cmd; i < total; i++) {
       CmdHot c = sh[i];
       if (!row_ok || y < c.y0 || y >= c.y1) continue;          // warp-uniform
+      const int bit0 = c.x0;  // sample of bit 0 of the command's failing-sample bitmaps (the hot rect's x0)
       if (c.flags & CMD_GENERAL) {
         // rotated quad: this row's span comes from the edge walk (warp-uniform)
         const CmdHot c0 = c;
@@ -686,7 +775,37 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
         }
       }
       typename S::Row row;
-      S::row_setup(a, c, y, tx0, FMT == WRCU_FMT_RGBA8, row);
+      // With depth testing on, each maximal run of passing samples of the row's span is drawn as a span of
+      // its own (draw_depth_span, rasterize.h:612-657).  The runs are walked in order up to this tile
+      // (warp-uniform; the failing-sample bitmap was written by wr_depth_fail_rows before this kernel
+      // started), because a run's chunk lanes continue from the previous run's.  Without depth testing, or
+      // when every sample of the span passes, the span is its only run.
+      const CmdCold& kc = a.cold[c.cold];
+      const uint32_t* frow = (use_depth && kc.fail_off >= 0)
+          ? a.fail_pool + (size_t)kc.fail_off + (size_t)(y - (int)c.y0) * (kc.fail_w + 1) : nullptr;
+      const bool runs = frow && __ldg(frow) != 0u;
+      WrRunWalk<S> walk;
+      walk.reset();
+      int xs = c.x0;
+      for (;;) {
+        CmdHot cr = c;
+        bool here = true;
+        if (runs) {
+          if (xs >= c.x1) break;
+          const int s0 = bit0 + wr_bits_next(frow + 1, xs - bit0, (int)c.x1 - bit0, false);
+          if (s0 >= c.x1 || s0 >= tx0 + WRCU_TILE_W) break;
+          const int e0 = bit0 + wr_bits_next(frow + 1, s0 - bit0, (int)c.x1 - bit0, true);
+          xs = e0;
+          here = e0 > tx0;
+          if (WrRun<S>::n == 0 && !here) continue;  // nothing carries over from runs left of the tile
+          cr.x0 = (short)s0;
+          cr.x1 = (short)e0;
+          walk.begin(a, kc, cr, y);
+        }
+        // (for a run left of the tile only its span-shader pixel count is needed)
+        S::row_setup(a, cr, y, here ? tx0 : ((int)cr.x0 & ~(WRCU_TILE_W - 1)), FMT == WRCU_FMT_RGBA8, row);
+        if (here) {
+          const CmdHot& c = cr;
       const int nxs = max((int)c.x0, tx0), nw = min((int)c.x1, tx0 + WRCU_TILE_W) - nxs;
       if (WrNarrowSpans<S>::v && nw <= 32) {
         // Narrow span (a glyph row is ~12 pixels): with 4 pixels per lane only 3-4 lanes would work
@@ -727,6 +846,10 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
         wr_shade_pixel<S, FMT>(a, c, row, xx, y, use_depth, px[p], zb[p], dirty, zdirty);
       }
       }
+        }
+        if (!runs) break;
+        walk.end(a, cr, WrRun<S>::drawn(row));
+      }
     }
   }
   }  // super-chunk
@@ -754,7 +877,7 @@ wr_raster(RasterArgs a) {
   __shared__ int wsum[WRCU_THREADS / 32 + 1];  // per-warp survivor counts + the last covering command
   const BatchInfo bi = *a.info;
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
-  if (a.copy_eligible && bi.all_copy) return;  // handled by wr_composite_copy
+  const bool skip_copy = a.copy_eligible && bi.all_copy;  // CMD_COPY commands are drawn by wr_composite_copy
   const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
   const int bx1 = (min(bi.bx1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
   const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
@@ -778,8 +901,105 @@ wr_raster(RasterArgs a) {
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) break;
-    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list);
+    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list, skip_copy);
     __syncthreads();
+  }
+}
+
+// ---- depth runs: which samples of each (command,row) fail the depth test ---------------------------
+// The reference keeps depth as runs per row and draws a span run by run (rasterize.h:5-257, 601-657);
+// where a run starts decides chunk phase, span-shader body vs tail and the interpolant sums, and a run
+// may start far left of the tile a CTA is drawing.  This kernel runs between the setup and the raster
+// kernel and writes, for every command that asked for it (CmdCold::fail_off) and every row, the bitmap of
+// failing samples over the command's hot rect:
+//   fails(x) = x outside the row's span, or  z > depth_before_batch(x),
+//              or (depth writes on) z > z' of an EARLIER command of this batch covering (x, y)
+// — with LEQUAL and writes the depth a command sees is the minimum over what was there and everything
+// drawn before it, whether those draws passed or not.  One CTA per command (earlier commands that can
+// occlude it are collected once into shared memory), one warp per row.
+#define WR_FAIL_CAND 1024
+WRD bool wr_row_span_of(RasterArgs& ar, GenRow& g, const CmdHot& c0, int y, int& x0, int& x1) {
+  if (y < c0.y0 || y >= c0.y1 || c0.x1 <= c0.x0) return false;
+  CmdHot c = c0;
+  const CmdCold& k = ar.cold[c0.cold];
+  ar.gen = &g;
+  if ((c0.flags & CMD_GENERAL) && !wr_general_row(k, c0, y, g, c)) return false;
+  if ((c.flags & CMD_CLIP_DIST) && !wr_clip_dist_row(ar, k, c, y)) return false;
+  x0 = c.x0;
+  x1 = c.x1;
+  return x1 > x0;
+}
+__global__ void __launch_bounds__(128) wr_depth_fail_rows(RasterArgs a, uint32_t* pool) {
+  __shared__ unsigned short cand[WR_FAIL_CAND];
+  __shared__ int ncand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  RasterArgs ar = a;
+  GenRow g;
+  for (int ci = blockIdx.x; ci < a.n; ci += gridDim.x) {
+    const CmdHot c0 = a.hot[ci];
+    const CmdCold& k = a.cold[c0.cold];
+    if (k.fail_off < 0 || c0.x1 <= c0.x0) continue;  // CTA-uniform
+    int nc = 0;
+    if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) {
+      __syncthreads();
+      if (threadIdx.x == 0) ncand = 0;
+      __syncthreads();
+      for (int j = threadIdx.x; j < ci; j += blockDim.x) {
+        const CmdHot o = a.hot[j];
+        if (o.x1 > o.x0 && o.z < c0.z && o.x0 < c0.x1 && c0.x0 < o.x1 && o.y0 < c0.y1 && c0.y0 < o.y1) {
+          const int p = atomicAdd(&ncand, 1);
+          if (p < WR_FAIL_CAND) cand[p] = (unsigned short)j;
+        }
+      }
+      __syncthreads();
+      nc = ncand;
+    }
+    const int W = k.fail_w, rows = (int)c0.y1 - (int)c0.y0;
+    for (int r = warp; r < rows; r += nwarps) {
+      const int y = (int)c0.y0 + r;
+      int sx0 = 0, sx1 = 0;
+      wr_row_span_of(ar, g, c0, y, sx0, sx1);
+      uint32_t* out = pool + (size_t)k.fail_off + (size_t)r * (W + 1);
+      const uint32_t* zrow = (const uint32_t*)((const uint8_t*)a.tgt.depth + (size_t)y * a.tgt.depth_pitch);
+      int cnt = 0;
+      for (int wb = 0; wb < W; wb += 32) {
+        const int nwords = min(32, W - wb);
+        uint32_t mine = 0;
+        for (int i = 0; i < nwords; i++) {
+          const int xx = (int)c0.x0 + (wb + i) * 32 + lane;
+          const bool pass = xx >= sx0 && xx < sx1 && c0.z <= zrow[xx];
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, !pass);
+          if (lane == i) mine = bal;
+        }
+        const int wx0 = (int)c0.x0 + (wb + lane) * 32;  // first sample of this lane's word
+        auto or_span = [&](int ox0, int ox1) {
+          const int lo = max(ox0 - wx0, 0), hi = min(ox1 - wx0, 32);
+          if (hi > lo) mine |= (hi - lo == 32) ? 0xFFFFFFFFu : (((1u << (hi - lo)) - 1u) << lo);
+        };
+        if (nc > WR_FAIL_CAND) {
+          // more occluder candidates than the list holds: test every earlier command directly
+          for (int j = 0; j < ci; j++) {
+            const CmdHot o = a.hot[j];
+            int ox0, ox1;
+            if (o.z < c0.z && wr_row_span_of(ar, g, o, y, ox0, ox1)) or_span(ox0, ox1);
+          }
+        } else {
+          for (int q = 0; q < nc; q++) {
+            const CmdHot o = a.hot[cand[q]];
+            int ox0, ox1;
+            if (wr_row_span_of(ar, g, o, y, ox0, ox1)) or_span(ox0, ox1);
+          }
+        }
+        if (lane < nwords) {
+          out[1 + wb + lane] = mine;
+          const int lo = max(sx0 - wx0, 0), hi = min(sx1 - wx0, 32);
+          if (hi > lo) cnt += __popc(mine & ((hi - lo == 32) ? 0xFFFFFFFFu : (((1u << (hi - lo)) - 1u) << lo)));
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+      if (lane == 0) out[0] = (uint32_t)cnt;
+    }
   }
 }
 

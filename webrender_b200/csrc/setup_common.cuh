@@ -44,6 +44,8 @@ struct SetupArgs {
   TexView color2;
   TexView clip_mask;
   const TexView* tex_list;  // wrcu_draw_composite_tiles: sColor0 of instance i (nullptr: color0 for all)
+  int depth_runs;           // depth test on and the kind's shading depends on where passing runs start:
+  int fail_cap;             //   commands get a failing-sample bitmap (CmdCold::fail_off) from a pool of fail_cap words
   int copy_ok;              // composite: blend off or premultiplied-alpha over, no depth → copy class possible
 };
 
@@ -58,6 +60,7 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
   info->tile_counter = 0;
   info->row_alloc = 0;
   info->all_copy = 1;
+  info->fail_alloc = 0;
 }
 // Each setup kernel also re-arms the per-batch record the NEXT draw will use
 // (records rotate through a ring of 4; the one after the current was last read
@@ -233,6 +236,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
   CmdCold k;
   memset(&k, 0, sizeof k);
   k.row_off = -1;
+  k.fail_off = -1;
   bool ok = false;
   do {
     if (q.pos[1].w != q.pos[0].w || q.pos[2].w != q.pos[0].w || q.pos[3].w != q.pos[0].w) {
@@ -438,6 +442,18 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     if (off >= 0 && off + need <= a.row_cap) {  // pool exhausted: the raster kernel walks the sums itself
       k.row_off = off;
       k.row_n = q.n_interp;
+    }
+  }
+  if (ok && a.depth_runs &&
+      (!(h.flags & CMD_CONST_COLOR) || (h.flags & (CMD_AA | CMD_MASK | CMD_TEXTURED | CMD_OUT_RRRR)))) {
+    // the shading of this command depends on where its passing depth runs start (chunk phase, span-shader
+    // body vs fragment tail, interpolant sums): wr_depth_fail_rows records them row by row
+    const int W = ((int)h.x1 - (int)h.x0 + 31) >> 5;
+    const int need = ((int)h.y1 - (int)h.y0) * (W + 1);
+    const int off = atomicAdd(&a.info->fail_alloc, need);
+    if (off >= 0 && off + need <= a.fail_cap) {
+      k.fail_off = off;
+      k.fail_w = W;
     }
   }
   if (ok) {

@@ -232,3 +232,9 @@ WRD void wr_setup_brush_blend_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_brush_blend)
+
+// no span shader: every chunk of a run goes through run()
+template <> struct WrRun<BlendShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const BlendShader::Row&) { return 0; }
+};

@@ -131,7 +131,8 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
       const float v = k->i_lt[1] + ((float)h.y0 + 0.5f - k->yt) * sl;
       const float tyf = floorf(v * th);
       const int rows = (int)h.y1 - (int)h.y0;
-      if (su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
+      // (the copy engine addresses boxes in 16-byte units: both origins on 4-pixel boundaries)
+      if (((int)h.x0 & 3) == 0 && ((int)txf & 3) == 0 && su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
           tyf >= 0.0f && tyf + (float)rows <= th && fabsf(v * th - (tyf + 0.5f)) <= (1.0f / 1024.0f)) {
         k->i[0] = (int)txf;
         k->i[1] = (int)tyf;
@@ -141,7 +142,7 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
         else if (k->row_off >= 0 && k->row_n == 2) { k->i[2] = 1; copyc = true; }
       }
     }
-    if (!copyc) a.info->all_copy = 0;
+    if (copyc) a.hot[idx].flags |= CMD_COPY;
   }
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);
@@ -167,7 +168,7 @@ __device__ void wr_composite_check_rows(const SetupArgs& a, int idx) {
     const int rows = (int)h.y1 - (int)h.y0;
     bool bad = false;
     for (int r = lane; r < rows; r += 32) bad = bad || fabsf(t[(size_t)r * 4 + 2] * th - ((float)(k.i[1] + r) + 0.5f)) > (1.0f / 1024.0f);
-    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) a.info->all_copy = 0;
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) a.hot[ci].flags &= ~CMD_COPY;
   }
 }
 __global__ void wr_setup_composite(SetupArgs a) {
@@ -222,7 +223,7 @@ struct WrBoxIter {
         c = a.hot[i];
         w = (int)c.x1 - (int)c.x0;
         h = (int)c.y1 - (int)c.y0;
-        if (w <= 0 || h <= 0) { nb = 0; b = 0; continue; }
+        if (w <= 0 || h <= 0 || !(c.flags & CMD_COPY)) { nb = 0; b = 0; continue; }
         nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W;
         nb = nbx * ((h + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H);
         b = ((int)blockIdx.x - g % G + G) % G;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
     wr_tma_acquire_map(dst_map);
     for (int i = 0; i < a.n; i++) {
       const CmdHot c = a.hot[i];
-      if (c.x1 > c.x0 && c.y1 > c.y0) wr_tma_acquire_map(maps + wr_composite_tex(a.cold[c.cold]).tmap_id);
+      if (c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY)) wr_tma_acquire_map(maps + wr_composite_tex(a.cold[c.cold]).tmap_id);
     }
   }
   __syncthreads();

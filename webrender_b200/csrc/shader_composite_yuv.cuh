@@ -556,3 +556,8 @@ WRD void wr_setup_brush_yuv_image_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL_YUV(wr_setup_brush_yuv_image)
+
+template <> struct WrRun<CompositeYuvShader> {  // brush_yuv_image draws under depth test; composite never does
+  enum { n = 6 };
+  WRD_MEMBER int drawn(const CompositeYuvShader::Row& r) { return r.body_len; }
+};

@@ -451,3 +451,8 @@ WRD void wr_setup_cs_gradient_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_cs_gradient)
+
+template <> struct WrRun<RadialShader> {  // ps_quad_radial_gradient
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const RadialShader::Row& r) { return r.body_len; }
+};

@@ -317,3 +317,8 @@ struct GradientShader {
     return o;
   }
 };
+
+template <> struct WrRun<GradientShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const GradientShader::Row& r) { return r.body_len; }
+};

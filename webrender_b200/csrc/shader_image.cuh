@@ -292,3 +292,13 @@ struct ImageRepeatShader {
     return o;
   }
 };
+
+// depth-run walk (raster.cuh WrRunWalk): interpolants = v_uv; span shader = swgl_commitTexture*
+template <> struct WrRun<ImageShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const ImageShader::Row& r) { return r.tr.body_len; }
+};
+template <> struct WrRun<ImageRepeatShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const ImageRepeatShader::Row& r) { return r.body_len; }
+};

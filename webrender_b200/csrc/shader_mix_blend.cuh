@@ -169,3 +169,8 @@ WRD void wr_setup_brush_mix_blend_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_brush_mix_blend)
+
+template <> struct WrRun<MixBlendShader> {
+  enum { n = 4 };
+  WRD_MEMBER int drawn(const MixBlendShader::Row&) { return 0; }
+};

@@ -103,3 +103,8 @@ WRD void wr_setup_brush_opacity_one(const SetupArgs& a, int idx) {
   wr_finish_setup(a, unsupported);
 }
 WR_SETUP_KERNEL(wr_setup_brush_opacity)
+
+template <> struct WrRun<OpacityShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const OpacityShader::Row& r) { return r.tr.body_len; }
+};

@@ -58,3 +58,8 @@ struct TextShader {
 template <> struct WrMinCtas<TextShader> { enum { v = 3 }; };
 template <> struct WrNarrowSpans<TextShader> { enum { v = 1 }; };  // glyph rows: ~12 pixels of a 128-pixel warp row
 #endif
+
+template <> struct WrRun<TextShader> {
+  enum { n = 2 };
+  WRD_MEMBER int drawn(const TextShader::Row& r) { return r.tr.body_len; }
+};

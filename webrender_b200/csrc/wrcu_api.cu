@@ -248,6 +248,7 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->batch_info) cudaFree(c->batch_info);
   if (c->row_tab) cudaFree(c->row_tab);
   if (c->tmaps_dev) cudaFree(c->tmaps_dev);
+  if (c->fail_pool) cudaFree(c->fail_pool);
   if (c->gpu_cache_dev) cudaFree(c->gpu_cache_dev);
   if (c->dev_err) cudaFree(c->dev_err);
   if (c->bin_mask) cudaFree(c->bin_mask);
@@ -938,6 +939,36 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   sa.row_tab = c->row_tab;
   sa.row_cap = c->row_cap;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
+#ifndef WRCU_HOSTEMU
+  {
+    // Depth runs matter to kinds whose shading depends on the position inside a span (AA ramps, span
+    // shader vs fragment tail, interpolated varyings).  Plain solids with blending off never do (their
+    // AA / mask flags are dropped, setup_common.cuh wr_emit_quad).
+    bool kind_runs = false;
+    switch (kind) {
+      case WRCU_KIND_BRUSH_SOLID: kind_runs = st->blend != WRCU_BLEND_NONE; break;
+      case WRCU_KIND_QUAD_TEXTURED: case WRCU_KIND_BRUSH_IMAGE: case WRCU_KIND_BRUSH_LINEAR_GRADIENT:
+      case WRCU_KIND_BRUSH_BLEND: case WRCU_KIND_BRUSH_MIX_BLEND: case WRCU_KIND_BRUSH_OPACITY: case WRCU_KIND_TEXT_RUN:
+      case WRCU_KIND_BRUSH_YUV_IMAGE: case WRCU_KIND_QUAD_RADIAL_GRADIENT: case WRCU_KIND_QUAD_CONIC_GRADIENT:
+        kind_runs = true; break;
+      default: break;
+    }
+    if (kind_runs && T.depth) {
+      if (!c->fail_pool) {
+        c->fail_cap = 16 << 20;  // 64 MiB of bitmaps per batch; commands beyond it keep span-relative phase
+        if (cudaMalloc((void**)&c->fail_pool, (size_t)c->fail_cap * 4) != cudaSuccess) {
+          c->fail_pool = nullptr;
+          c->fail_cap = 0;
+          cudaGetLastError();
+        }
+      }
+      if (c->fail_pool) {
+        sa.depth_runs = 1;
+        sa.fail_cap = c->fail_cap;
+      }
+    }
+  }
+#endif
   sa.copy_ok = !T.depth && (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA);
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
@@ -1135,6 +1166,15 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   // Device-side dispatch: the setup kernel decides whether the whole batch is
   // plain solid quads; the specialised and the generic kernel each return at
   // once when it is not their turn (the host never has to wait for the flag).
+#ifndef WRCU_HOSTEMU
+  if (sa.depth_runs) {
+    // depth runs: the failing-sample bitmaps of this batch, before any of its depth writes
+    ra.fail_pool = c->fail_pool;
+    const int fgrid = n < c->sm_count * 8 ? n : c->sm_count * 8;
+    wr_depth_fail_rows<<<fgrid, 128, 0, c->stream>>>(ra, c->fail_pool);
+    c->stats.kernel_launches++;
+  }
+#endif
   if (c->profile) WRCU_CUDA(c, cudaEventRecord(c->p0, c->stream));
   bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
                  ra.depth_mode == WRCU_DEPTH_OFF &&

@@ -17,10 +17,12 @@
 #include "hostemu_shim.h"  // tests only: g++ build of the device functions (symbols wremu_*)
 #define WRD static inline
 #define WRD_MEMBER static inline
+#define WRD_METHOD inline
 #else
 #include <cuda_runtime.h>
 #define WRD __device__ __forceinline__
 #define WRD_MEMBER __device__ static __forceinline__
+#define WRD_METHOD __device__ __forceinline__
 #endif
 #include <stdint.h>
 #include <utility>
@@ -137,6 +139,8 @@ struct wrcu_ctx {
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
   // TMA: one 128-byte CUtensorMap per RGBA8 texture (box 256x16 px), built on the host at texture
   // creation (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint) and kept in a device table
+  uint32_t* fail_pool = nullptr;  // depth-run bitmaps of the current batch (CmdCold::fail_off)
+  int fail_cap = 0;               // words
   void* tmaps_dev = nullptr;
   void* tmap_encode = nullptr;
   bool copy_attr_set = false;

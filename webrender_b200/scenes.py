@@ -87,7 +87,7 @@ def rotation_matrix(deg, cx, cy, sx=1.0, sy=1.0):
 
 
 def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, with_masks=True,
-                      fractional=False, force_aa=False, device_pixel_scale=1.0, rotate=None):
+                      fractional=False, force_aa=False, device_pixel_scale=1.0, rotate=None, occlude_alpha=False):
     """Brush(Solid) batches the way draw_alpha_batch_container issues them
     (renderer/mod.rs:2804-2969): an opaque batch front-to-back with depth
     LEQUAL + write, then an alpha batch with premultiplied blending, depth test
@@ -116,11 +116,17 @@ def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, wi
         return brush_instance(hdr, clip_task, 0xFFFF, edge, flags, 0)
 
     s = 1.0 / device_pixel_scale
+    # occlude_alpha: the opaque prims sit IN FRONT of the alpha prims (larger z ids), so alpha spans are cut
+    # into passing depth runs by them (an opaque box over translucent content)
+    if occlude_alpha:
+        z = 10000
     for _ in range(n_opaque):
         r = _rand_rect(rng, width, height, 16, integer=not fractional)
         r = tuple(v * s for v in r)
         c = tuple(float(v) for v in rng.uniform(0, 1, 3)) + (1.0,)
         opaque.append(add(r, (-1e9, -1e9, 1e9, 1e9), c, 1.0, CLIP_TASK_EMPTY))
+    if occlude_alpha:
+        z = 1
     for i in range(n_alpha):
         r = _rand_rect(rng, width, height, 16, integer=not fractional)
         a = rng.uniform(0.1, 1.0)
@@ -290,7 +296,7 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
 
 
 def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=abi.LINEAR, one_to_one=False,
-                fractional=False, rotate=None):
+                fractional=False, rotate=None, occlude_alpha=False):
     """Brush(Image) batches: an opaque batch (depth write, blending off) and an
     alpha batch (premultiplied over, depth test) sampling one RGBA8 atlas, with
     colour modes Image / ColorBitmap / Alpha(drop-shadow override), 1:1 and
@@ -333,9 +339,13 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
         u0, v0 = int(rng.randint(0, aw - uw)), int(rng.randint(0, ah - uh))
         return (float(u0), float(v0), float(u0 + uw), float(v0 + uh))
 
+    if occlude_alpha:  # opaque prims in front of the alpha prims: alpha spans split into depth runs
+        z = 10000
     for _ in range(n_opaque):
         r = _rand_rect(rng, width, height, 16, 200, integer=not fractional)
         opaque.append(add(r, rand_uv(r[2] - r[0], r[3] - r[1]), (1.0, 1.0, 1.0, 1.0), 4, 1.0))
+    if occlude_alpha:
+        z = 1
     for i in range(n_alpha):
         r = _rand_rect(rng, width, height, 16, 200, integer=not fractional)
         mode = [4, 4, 3, 0, 4][i % 5]
@@ -362,7 +372,7 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
 
 
 def image_repeat_frame(width=640, height=360, n_opaque=6, n_alpha=14, seed=1, filter=abi.LINEAR, fractional=False,
-                       device_pixel_scale=1.0):
+                       device_pixel_scale=1.0, occlude_alpha=False):
     """Tiled images and border-image segments: Brush(Image) with BatchFeatures::REPETITION
     (shade.rs:985-1000 "ANTIALIASING,REPETITION"): stretch sizes smaller than the primitive
     (background-repeat), segment-relative REPEAT_X / REPEAT_Y with ROUND and CENTERED flags and
@@ -401,11 +411,15 @@ def image_repeat_frame(width=640, height=360, n_opaque=6, n_alpha=14, seed=1, fi
         return (float(u0), float(v0), float(u0 + uw), float(v0 + uh)), uw, uh
 
     lw, lh = int(width / device_pixel_scale), int(height / device_pixel_scale)
+    if occlude_alpha:
+        z = 10000
     for i in range(n_opaque):
         r = _rand_rect(rng, lw, lh, 40, 260, integer=not fractional)
         uv, uw, uh = tile_uv(i)
         st = (float(uw), float(uh)) if i % 2 == 0 else (float(rng.uniform(6, 70)), float(rng.uniform(6, 50)))
         opaque.append(add(r, uv, (1.0, 1.0, 1.0, 1.0), 4, 1.0, stretch=st))
+    if occlude_alpha:
+        z = 1
     for i in range(n_alpha):
         r = _rand_rect(rng, lw, lh, 40, 260, integer=not fractional)
         uv, uw, uh = tile_uv(i)
