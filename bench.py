@@ -435,38 +435,89 @@ def roofline_sweep(dev, flush, steps, peak):
     return out
 
 
-def run_config_e(dev, rank, world, steps, barrier):
-    """One 8192x4096 frame = 64 picture-cache tiles of 1024x512 (config-B' rect
-    list cut per tile), tiles round-robin over the ranks, one NCCL gather to
-    rank 0, composite there.  Strong scaling of a single frame; wall time per
-    frame is the max over ranks between barriers."""
+def run_config_e(dev, rank, world, local, steps, barrier):
+    """Config E: ONE 8192x4096 frame = 64 picture-cache tiles of 1024x512 (the config-B'
+    rect list cut per tile), tiles round-robin over the ranks.  No gather: every rank composites its own
+    tiles straight into rank 0's exported framebuffer (bulk-tensor stores over NVLink), ordered by stream
+    flags (webrender_b200/multi_gpu.py DirectShardedRenderer).  Strong scaling of a single frame: device
+    time per frame (CUDA events on each rank's stream, max over ranks), with the same code on ONE GPU
+    (rank 0, all 64 tiles) measured in the same run as the reference."""
     import zlib
     import torch
     import torch.distributed as dist
     from webrender_b200 import multi_gpu
+    from webrender_b200.device import CudaDevice
     scene = multi_gpu.tiled_alpha_scene()
-    sr = multi_gpu.ShardedRenderer(dev, scene, rank, world)
-    for _ in range(2):
+    sr = multi_gpu.DirectShardedRenderer(dev, scene, rank, world)
+    blobs = [None] * world
+    if world > 1:
+        dist.all_gather_object(blobs, sr.blob)
+    else:
+        blobs = [sr.blob]
+    sr.connect(blobs)
+    for _ in range(3):
         sr.render()
     barrier()
-    t0 = time.perf_counter()
+    dev.timer_begin()
     for _ in range(steps):
         sr.render()
+    ms = dev.timer_end() / steps
     barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
     out = None
     if rank == 0:
         crc = zlib.crc32(sr.read_framebuffer().tobytes())
-        single = multi_gpu.ShardedRenderer(dev, scene, 0, 1)
-        single.render()
+        # the same frame on one GPU (a second context on this device)
+        d1 = CudaDevice(local)
+        single = multi_gpu.DirectShardedRenderer(d1, scene, 0, 1)
+        single.connect([single.blob])
+        for _ in range(3):
+            single.render()
+        d1.finish()
+        d1.timer_begin()
+        for _ in range(steps):
+            single.render()
+        ms1 = d1.timer_end() / steps
         crc1 = zlib.crc32(single.read_framebuffer().tobytes())
-        ms = float(dt[0]) / steps * 1e3
+        single.close()
+        d1.close()
         out = {"workload": "config E: 8192x4096 frame, 64 tiles of 1024x512, 1000 seeded alpha rects cut per tile",
-               "ms_per_frame": ms, "fps": 1e3 / ms, "Mpix_s": scene.pixel_layers / (ms * 1e-3) / 1e6,
-               "tiles_per_rank": sr.per_rank, "exchange": "torch.distributed gather over NCCL, device memory",
+               "scaling": "strong", "n_gpus": world, "ms_per_frame": ms, "fps": 1e3 / ms,
+               "Mpix_s": scene.pixel_layers / (ms * 1e-3) / 1e6, "tiles_per_rank": (len(scene.tiles) + world - 1) // world,
+               "one_gpu_ms_per_frame": ms1, "speedup_vs_one_gpu": ms1 / ms, "efficiency": ms1 / ms / world,
+               "exchange": "none staged: each rank's composite kernel stores its tiles into rank 0's framebuffer "
+                           "(CUDA IPC mapping, TMA bulk stores over NVLink); stream-ordered flags, no host sync per frame",
+               "nvlink_bytes_per_frame": int(sum((x1 - x0) * (y1 - y0) * 4 for i, (x0, y0, x1, y1) in enumerate(scene.rects)
+                                                 if i % world != 0)),
+               "timing": "CUDA events on each rank's stream over %d frames, max over ranks" % steps,
                "framebuffer_crc32": crc, "matches_single_gpu": bool(crc == crc1)}
+    sr.close()
     return out
+
+
+def pin_to_gpu_numa_node(local):
+    """Run this rank (and allocate its page-locked buffers) on the NUMA node its GPU hangs off: with 8 ranks
+    on one host the e2e readbacks otherwise cross the socket interconnect (round 1: 0.74 e2e efficiency)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def main():
@@ -477,6 +528,7 @@ def main():
     ap.add_argument("--impl", default="wrcu", choices=["wrcu", "reference"])
     ap.add_argument("--ref-rects", type=int, default=400, help="layers per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config-e", action="store_true", help="also run the sharded 8K frame (always on for --gpus > 1)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the layer-depth roofline sweep")
     ap.add_argument("--workload", default="config_b",
                     help="config_b (the contract's bench line) or one of the other §8 rows: see other_workloads(), update_path")
@@ -500,6 +552,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the wrcu backend has no CPU path")
     torch.cuda.set_device(local)
+    numa_node = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -646,9 +699,9 @@ def main():
     # ---- config E, informational: ONE 8K frame whose 64 tiles are
     # sharded over the ranks, gathered to rank 0 over NCCL and composited there ----
     config_e = None
-    if world > 1:
+    if world > 1 or args.config_e:
         try:
-            config_e = run_config_e(dev, rank, world, max(3, args.steps // 4), barrier)
+            config_e = run_config_e(dev, rank, world, local, max(5, args.steps), barrier)
         except Exception as e:  # keep the headline line even if the extra fails
             config_e = {"error": repr(e)[:200]}
 
@@ -670,7 +723,11 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD_B,
                        "pixel_layers_per_step": layers, "frames_per_gpu_per_step": 1,
-                       "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the wrcu stream"},
+                       "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events on the wrcu stream",
+                       "multi_gpu": "value: every rank renders its own config-B frame (independent render targets, no "
+                                    "data-path collective: weak scaling); config_e: ONE 8K frame sharded by tile over the "
+                                    "ranks into a shared framebuffer (strong scaling, its own one-GPU reference)",
+                       "numa_node_rank0": numa_node},
             "clocks": clocks,
             "gpu_launches": int(st["kernel_launches"]),
             "e2e": {"value": world * layers * args.steps / e2e_s / 1e6, "unit": "Mpix/s",

@@ -319,6 +319,43 @@ int wrcu_texture_device_ptr(wrcu_ctx* ctx, wrcu_tex tex, void** dptr,
 /* The CUDA stream (cudaStream_t) the context queues work on. */
 int wrcu_stream(wrcu_ctx* ctx, void** stream);
 
+/* ---- multi-GPU: the tiles of ONE frame sharded over GPUs ----------------------
+ * Picture-cache tiles are independent render targets (frame_builder.rs:995-1057): each GPU draws its
+ * share with no data-path communication.  The one exchange step — finished tiles into the
+ * framebuffer that is presented — needs no collective and no staging either: the compositing GPU
+ * EXPORTS its framebuffer texture, every other context IMPORTS it (CUDA IPC between processes, the
+ * raw mapping inside one process; peer access over NVLink / NVSwitch) and binds it as the target of
+ * its own `composite` tile list, so the copy kernel's bulk-tensor stores land in the remote
+ * framebuffer directly.  Ordering between contexts is by flag words in device memory, written and
+ * polled on the CUDA streams — no host synchronisation per frame.
+ * One process per GPU (torchrun) or several contexts in one process both work. */
+typedef struct wrcu_ipc_texture {
+  uint8_t handle[64];          /* cudaIpcMemHandle_t                                  */
+  uint64_t pid, address;       /* exporting process and its device address            */
+  uint64_t pitch;
+  int32_t format, width, height, device;
+} wrcu_ipc_texture;
+int wrcu_texture_export(wrcu_ctx* ctx, wrcu_tex tex, wrcu_ipc_texture* out);
+/* The imported texture aliases the exporter's memory: usable as a render target or sampler
+ * source; wrcu_texture_destroy unmaps it. */
+int wrcu_texture_import(wrcu_ctx* ctx, const wrcu_ipc_texture* in, wrcu_tex* out);
+typedef struct wrcu_ipc_flags {
+  uint8_t handle[64];
+  uint64_t pid, address;
+  int32_t count, device;
+} wrcu_ipc_flags;
+/* This context's flag words (`count` x u32 in device memory, zeroed); `out` is what peers open. */
+int wrcu_peer_flags_create(wrcu_ctx* ctx, int count, wrcu_ipc_flags* out);
+/* Map a peer's flag words; *peer_id identifies it in wrcu_peer_signal. */
+int wrcu_peer_flags_open(wrcu_ctx* ctx, const wrcu_ipc_flags* in, int* peer_id);
+/* Stream-ordered: once everything queued on this context so far has completed (its stores to
+ * imported textures included), peer.flags[slot] = value. */
+int wrcu_peer_signal(wrcu_ctx* ctx, int peer_id, int slot, uint32_t value);
+/* Stream-ordered: work queued on this context after the call starts only when this context's own
+ * flags[slot] >= value (wrap-safe).  A peer that never signals is reported after ~2 s as
+ * WRCU_ERR_CUDA at the next synchronisation instead of hanging the GPU. */
+int wrcu_peer_wait(wrcu_ctx* ctx, int slot, uint32_t value);
+
 /* ---- asynchronous readback (the reference's PBO path) ----------------------- */
 /* Page-locked host memory for uploads/readbacks: create_pbo_with_size /
  * map_pbo_for_readback (device/gl.rs:3146, 3241).  Buffers from here make

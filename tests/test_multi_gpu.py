@@ -82,3 +82,54 @@ def test_single_gpu_tiled_matches_oracle():
     b = multi_gpu.ShardedRenderer(OracleDevice(), scene, 0, 1)
     b.render()
     assert (a.read_framebuffer() == b.read_framebuffer()).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_direct_sharded_contexts_share_one_framebuffer(world):
+    """The product exchange: `world` contexts (here on one GPU, in one process — the same
+    calls a rank per GPU makes) draw their tiles and composite them straight into rank 0's exported
+    framebuffer, ordered by stream flags only.  Two frames; bytes equal the oracle's single-device frame."""
+    from oracle.backends import OracleDevice
+    from webrender_b200.device import CudaDevice
+    scene = multi_gpu.tiled_alpha_scene(width=2048, height=1024, tile_w=512, tile_h=256, n_rects=160, seed=5)
+    devs = [CudaDevice(0) for _ in range(world)]
+    rs = [multi_gpu.DirectShardedRenderer(devs[r], scene, r, world) for r in range(world)]
+    blobs = [r.blob for r in rs]
+    for r in rs:
+        r.connect(blobs)
+    for _ in range(2):
+        rs[0].begin()
+        for r in rs[1:]:
+            r.draw()
+        rs[0].draw()
+        rs[0].end()
+    got = rs[0].read_framebuffer()
+    ref = multi_gpu.ShardedRenderer(OracleDevice(), scene, 0, 1)
+    ref.render()
+    assert (got == ref.read_framebuffer()).all()
+    for r in rs[::-1]:
+        r.close()
+    for d in devs[::-1]:
+        d.close()
+
+
+def test_rank_frames_merge_tables():
+    """Host logic of the per-rank frame: the merged tables address the same data the per-tile frames did."""
+    from oracle.backends import OracleDevice
+    from webrender_b200.frame import draw_frame
+    scene = _small_scene()
+    mine = multi_gpu.assign_tiles(len(scene.tiles), 2)[1]
+    tiles_frame, comp_frame = multi_gpu.rank_frames(scene, mine)
+    dev = OracleDevice()
+    handles = draw_frame(dev, tiles_frame)
+    for i in mine:
+        d2 = OracleDevice()
+        h2 = draw_frame(d2, scene.tiles[i])
+        x0, y0, x1, y1 = scene.rects[i]
+        a = dev.read_pixels(handles["tile%d" % i], 0, 0, x1 - x0, y1 - y0, 4)
+        b = d2.read_pixels(h2["tile"], 0, 0, x1 - x0, y1 - y0, 4)
+        assert (a == b).all()
+        d2.close()
+    assert [op.color[0] for op in comp_frame.passes[0][0].ops] == ["tile%d" % i for i in mine]
+    dev.close()

@@ -157,5 +157,17 @@ SYMBOLS = [
     "wrcu_texture_device_ptr", "wrcu_stream", "wrcu_host_alloc", "wrcu_host_free",
     "wrcu_read_pixels_async", "wrcu_fence_wait", "wrcu_fence_insert",
     "wrcu_profile_enable", "wrcu_last_raster_ms",
+    "wrcu_texture_export", "wrcu_texture_import", "wrcu_peer_flags_create", "wrcu_peer_flags_open",
+    "wrcu_peer_signal", "wrcu_peer_wait",
     "wrcu_texture_upload_batch", "wrcu_texture_copy", "wrcu_gpu_cache_update",
 ]
+
+
+class IpcTexture(C.Structure):   # wrcu_ipc_texture
+    _fields_ = [("handle", C.c_uint8 * 64), ("pid", C.c_uint64), ("address", C.c_uint64), ("pitch", C.c_uint64),
+                ("format", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("device", C.c_int32)]
+
+
+class IpcFlags(C.Structure):     # wrcu_ipc_flags
+    _fields_ = [("handle", C.c_uint8 * 64), ("pid", C.c_uint64), ("address", C.c_uint64),
+                ("count", C.c_int32), ("device", C.c_int32)]

@@ -90,5 +90,6 @@ struct BatchInfo {
   int row_alloc;           // floats of the row-table pool handed out to this batch's commands
   int all_copy;            // composite: 1 while no two commands of the batch overlap: CMD_COPY commands go to wr_composite_copy
   int fail_alloc;          // words of the depth-run bitmap pool handed out to this batch's commands
+  int n_noncopy;           // composite: drawn commands that are not CMD_COPY (0: the tile kernel has nothing to do)
 };
 #define WR_ROW_TAB_MIN 16

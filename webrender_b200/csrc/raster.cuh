@@ -648,7 +648,7 @@ WRD int wr_bits_next(const uint32_t* w, int from, int to, bool want) {
 // blend key).  S::row_setup computes per-(command,row) constants once per warp
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
 // S::source returns the fragment stage's output for one pixel as 16-bit lanes.
-template <class S, int FMT>
+template <class S, int FMT, bool RUNS>
 WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, unsigned short* list,
                         const bool skip_copy) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -781,9 +781,9 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       // started), because a run's chunk lanes continue from the previous run's.  Without depth testing, or
       // when every sample of the span passes, the span is its only run.
       const CmdCold& kc = a.cold[c.cold];
-      const uint32_t* frow = (use_depth && kc.fail_off >= 0)
+      const uint32_t* frow = (RUNS && use_depth && kc.fail_off >= 0)
           ? a.fail_pool + (size_t)kc.fail_off + (size_t)(y - (int)c.y0) * (kc.fail_w + 1) : nullptr;
-      const bool runs = frow && __ldg(frow) != 0u;
+      const bool runs = RUNS && frow && __ldg(frow) != 0u;
       WrRunWalk<S> walk;
       walk.reset();
       int xs = c.x0;
@@ -870,7 +870,9 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
 // work is latency-bound (many small commands) specialise this to 3.
 template <class S> struct WrMinCtas { enum { v = 2 }; };
 
-template <class S, int FMT>
+// RUNS: the variant that reproduces depth runs (launched for depth-tested batches of the kinds whose
+// shading depends on them); the plain variant carries none of that code.
+template <class S, int FMT, bool RUNS = false>
 __global__ void __launch_bounds__(WRCU_THREADS, WrMinCtas<S>::v)
 wr_raster(RasterArgs a) {
   __shared__ CmdHot sh[CHUNK_CMDS];
@@ -878,6 +880,7 @@ wr_raster(RasterArgs a) {
   const BatchInfo bi = *a.info;
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
   const bool skip_copy = a.copy_eligible && bi.all_copy;  // CMD_COPY commands are drawn by wr_composite_copy
+  if (skip_copy && bi.n_noncopy == 0) return;
   const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
   const int bx1 = (min(bi.bx1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
   const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
@@ -901,7 +904,7 @@ wr_raster(RasterArgs a) {
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) break;
-    wr_raster_tile<S, FMT>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list, skip_copy);
+    wr_raster_tile<S, FMT, RUNS>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list, skip_copy);
     __syncthreads();
   }
 }
@@ -1053,8 +1056,12 @@ WRD void wr_fast_blend8(uint32_t* rb, uint32_t* ga, uint32_t c, uint32_t krb, ui
   }
 }
 
+// `v0`, `v1`: this thread's pixels of the tile, loaded by the caller one tile ahead (software prefetch: the
+// loads of tile t+1 are in flight while tile t is classified and blended — a shallow batch is a
+// read-modify-write of the target at HBM speed, and the tile-at-a-time dependency chain
+// load → blend → store would otherwise leave half the memory pipeline idle).
 template <bool VALID>
-WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb, int* wsum) {
+WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb, int* wsum, const uint4 v0, const uint4 v1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4;
   const int y0 = ty0 + warp, y1 = ty0 + warp + 4;
@@ -1097,8 +1104,7 @@ WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb
     __syncthreads();
     if (total == 0) continue;
     if (!loaded) {
-      loaded = true;  // lazy tile load: first chunk with a command on this tile
-      const uint4 v0 = *(const uint4*)p0, v1 = *(const uint4*)p1;
+      loaded = true;  // first chunk with a command on this tile: unpack the prefetched pixels
       const uint32_t pv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
       for (int p = 0; p < 8; p++) {
@@ -1163,10 +1169,21 @@ wr_raster_solid_premult(RasterArgs a) {
   const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
   const int nx = bx1 - bx0, n_tiles = nx * (by1 - by0);
   if (nx <= 0 || n_tiles <= 0) return;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto tile_px = [&](int t, int row) {  // this thread's 16 bytes of row `row` (0 / 1 → tile rows warp, warp + 4)
     const int tx0 = (bx0 + t % nx) * WRCU_TILE_W, ty0 = (by0 + t / nx) * WRCU_TILE_H;
-    if (bi.premul_valid) wr_fast_tile<true>(a, tx0, ty0, fa, fb, wsum);
-    else wr_fast_tile<false>(a, tx0, ty0, fa, fb, wsum);
+    return (const uint4*)(a.tgt.color + (size_t)(ty0 + warp + 4 * row) * a.tgt.color_pitch + (size_t)(tx0 + lane * 4) * 4);
+  };
+  int t = blockIdx.x;
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+  if (t < n_tiles) { n0 = *tile_px(t, 0); n1 = *tile_px(t, 1); }
+  for (; t < n_tiles; t += gridDim.x) {
+    const uint4 v0 = n0, v1 = n1;
+    const int tn = t + gridDim.x;
+    if (tn < n_tiles) { n0 = *tile_px(tn, 0); n1 = *tile_px(tn, 1); }  // next tile: issued now, used next iteration
+    const int tx0 = (bx0 + t % nx) * WRCU_TILE_W, ty0 = (by0 + t / nx) * WRCU_TILE_H;
+    if (bi.premul_valid) wr_fast_tile<true>(a, tx0, ty0, fa, fb, wsum, v0, v1);
+    else wr_fast_tile<false>(a, tx0, ty0, fa, fb, wsum, v0, v1);
   }
 }
 #endif  // !WRCU_HOSTEMU

@@ -61,6 +61,7 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
   info->row_alloc = 0;
   info->all_copy = 1;
   info->fail_alloc = 0;
+  info->n_noncopy = 0;
 }
 // Each setup kernel also re-arms the per-batch record the NEXT draw will use
 // (records rotate through a ring of 4; the one after the current was last read

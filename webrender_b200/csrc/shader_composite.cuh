@@ -131,8 +131,7 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
       const float v = k->i_lt[1] + ((float)h.y0 + 0.5f - k->yt) * sl;
       const float tyf = floorf(v * th);
       const int rows = (int)h.y1 - (int)h.y0;
-      // (the copy engine addresses boxes in 16-byte units: both origins on 4-pixel boundaries)
-      if (((int)h.x0 & 3) == 0 && ((int)txf & 3) == 0 && su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
+      if (su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
           tyf >= 0.0f && tyf + (float)rows <= th && fabsf(v * th - (tyf + 0.5f)) <= (1.0f / 1024.0f)) {
         k->i[0] = (int)txf;
         k->i[1] = (int)tyf;
@@ -143,6 +142,7 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
       }
     }
     if (copyc) a.hot[idx].flags |= CMD_COPY;
+    else atomicAdd(&a.info->n_noncopy, 1);
   }
   if (unsupported) {
     atomicAdd(&a.info->unsupported, 1);
@@ -168,7 +168,10 @@ __device__ void wr_composite_check_rows(const SetupArgs& a, int idx) {
     const int rows = (int)h.y1 - (int)h.y0;
     bool bad = false;
     for (int r = lane; r < rows; r += 32) bad = bad || fabsf(t[(size_t)r * 4 + 2] * th - ((float)(k.i[1] + r) + 0.5f)) > (1.0f / 1024.0f);
-    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) a.hot[ci].flags &= ~CMD_COPY;
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) {
+      a.hot[ci].flags &= ~CMD_COPY;
+      atomicAdd(&a.info->n_noncopy, 1);
+    }
   }
 }
 __global__ void wr_setup_composite(SetupArgs a) {
@@ -208,7 +211,7 @@ __global__ void wr_setup_composite(SetupArgs a) {
 //     thread 0 bulk-stores the destination box and refills the slot that has just drained.
 struct WrBoxIter {
   int i = -1, b = 0, nb = 0, nbx = 1, g = 0, w = 0, h = 0;
-  bool started = false;
+  bool started = false, aligned = false;
   CmdHot c;
   // next box of this CTA that is (full == want_full); false when the batch is exhausted
   __device__ bool next(const RasterArgs& a, bool want_full, int& bx, int& by) {
@@ -226,11 +229,14 @@ struct WrBoxIter {
         if (w <= 0 || h <= 0 || !(c.flags & CMD_COPY)) { nb = 0; b = 0; continue; }
         nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W;
         nb = nbx * ((h + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H);
+        aligned = (((int)c.x0 | a.cold[c.cold].i[0]) & 3) == 0;
         b = ((int)blockIdx.x - g % G + G) % G;
       }
       bx = (b % nbx) * WR_TMA_BOX_W;
       by = (b / nbx) * WR_TMA_BOX_H;
-      const bool full = bx + WR_TMA_BOX_W <= w && by + WR_TMA_BOX_H <= h;
+      // the copy engine takes whole boxes whose source and destination start on 16-byte boundaries
+      // (box origins off them fault: tools/probe/tma_probe.cu); everything else is moved by threads
+      const bool full = aligned && bx + WR_TMA_BOX_W <= w && by + WR_TMA_BOX_H <= h;
       if (full == want_full) return true;
     }
   }

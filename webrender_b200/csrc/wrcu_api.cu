@@ -236,8 +236,18 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < wrcu_ctx::MAX_TEX; i++)
-    if (c->tex[i].live) cudaFree(c->tex[i].dptr);
+  for (int i = 0; i < wrcu_ctx::MAX_TEX; i++) {
+    if (!c->tex[i].live) continue;
+    if (!c->tex[i].imported) cudaFree(c->tex[i].dptr);
+#ifndef WRCU_HOSTEMU
+    else if (c->tex[i].ipc_mapped) cudaIpcCloseMemHandle(c->tex[i].dptr);
+#endif
+  }
+#ifndef WRCU_HOSTEMU
+  for (auto& pf : c->peers)
+    if (pf.ipc) cudaIpcCloseMemHandle(pf.ptr);
+#endif
+  if (c->flags) cudaFree(c->flags);
   for (int i = 0; i < 2; i++) {
     if (c->arena[i].host) cudaFreeHost(c->arena[i].host);
     if (c->arena[i].dev) cudaFree(c->arena[i].dev);
@@ -450,7 +460,10 @@ extern "C" int wrcu_texture_destroy(wrcu_ctx* c, wrcu_tex id) {
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_destroy: bad handle");
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(t->dptr);
+  if (!t->imported) cudaFree(t->dptr);
+#ifndef WRCU_HOSTEMU
+  else if (t->ipc_mapped) cudaIpcCloseMemHandle(t->dptr);
+#endif
   *t = WrTexture();
   if (c->color_tex == id) c->color_tex = 0;
   if (c->depth_tex == id) c->depth_tex = 0;
@@ -471,6 +484,10 @@ static int sync_and_check(wrcu_ctx* c) {
   int n = 0;
   WRCU_CUDA(c, cudaMemcpyAsync(&n, c->dev_err, sizeof n, cudaMemcpyDeviceToHost, c->stream));
   WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n >= (1 << 20)) {
+    cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
+    return wrcu_fail(c, WRCU_ERR_CUDA, "wrcu_peer_wait: a peer did not signal within 2 s (%d wait(s) timed out)", n >> 20);
+  }
   if (n) {
     cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
     return wrcu_fail(c, WRCU_ERR_UNSUPPORTED,
@@ -669,6 +686,172 @@ extern "C" int wrcu_gpu_cache_update(wrcu_ctx* c, int height, int clear, const w
             (const GpuCacheCopyDev*)dupd, (int)n_updates, (const float4*)dblocks, (int)n_blocks);
   c->stats.kernel_launches++;
   WRCU_CUDA(c, cudaGetLastError());
+  return WRCU_OK;
+}
+
+// ---- multi-GPU: shared framebuffer + stream-ordered flags -----------------------
+#ifdef WRCU_HOSTEMU
+static uint64_t wr_pid() { return 1; }
+#else
+#include <unistd.h>
+static uint64_t wr_pid() { return (uint64_t)getpid(); }
+__global__ void wr_flag_signal(uint32_t* flag, uint32_t value) {
+  __threadfence_system();  // (the stores of earlier kernels are already performed at their completion)
+  *(volatile uint32_t*)flag = value;
+  __threadfence_system();
+}
+__global__ void wr_flag_wait(const uint32_t* flag, uint32_t value, int* timeout_counter) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int32_t)(v - value) >= 0) return;
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 2000000000ull) {  // 2 s: the peer is gone; do not hold the GPU
+      atomicAdd(timeout_counter, 1 << 20);
+      return;
+    }
+  }
+}
+#endif
+// make `dev` reachable from this context's device
+static int enable_peer(wrcu_ctx* c, int dev) {
+#ifndef WRCU_HOSTEMU
+  if (dev == c->device) return WRCU_OK;
+  int can = 0;
+  WRCU_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, dev));
+  if (!can) return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "device %d cannot access device %d", c->device, dev);
+  cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+    return wrcu_fail(c, WRCU_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+  cudaGetLastError();
+#endif
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_texture_export(wrcu_ctx* c, wrcu_tex id, wrcu_ipc_texture* out) {
+  WrTexture* t = get_tex(c, id);
+  if (!t || !out || t->imported) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_export: bad arguments");
+  cudaSetDevice(c->device);
+  memset(out, 0, sizeof *out);
+#ifndef WRCU_HOSTEMU
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof out->handle, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  WRCU_CUDA(c, cudaIpcGetMemHandle(&h, t->dptr));
+  memcpy(out->handle, &h, sizeof h);
+#endif
+  out->pid = wr_pid();
+  out->address = (uint64_t)(uintptr_t)t->dptr;
+  out->pitch = t->pitch;
+  out->format = t->fmt; out->width = t->w; out->height = t->h; out->device = c->device;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_texture_import(wrcu_ctx* c, const wrcu_ipc_texture* in, wrcu_tex* out) {
+  if (!in || !out || !fmt_bpp(in->format) || in->width <= 0 || in->height <= 0)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "texture_import: bad arguments");
+  cudaSetDevice(c->device);
+  void* p = nullptr;
+  bool ipc = false;
+  if (in->pid == wr_pid()) {
+    int rc = enable_peer(c, in->device);
+    if (rc != WRCU_OK) return rc;
+    p = (void*)(uintptr_t)in->address;
+  } else {
+#ifndef WRCU_HOSTEMU
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in->handle, sizeof h);
+    WRCU_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ipc = true;
+#else
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "texture_import: no IPC in the host emulation");
+#endif
+  }
+  for (int i = 1; i < wrcu_ctx::MAX_TEX; i++) {
+    if (c->tex[i].live) continue;
+    WrTexture& t = c->tex[i];
+    t = WrTexture();
+    t.fmt = in->format; t.w = in->width; t.h = in->height; t.bpp = fmt_bpp(in->format);
+    t.pitch = (size_t)in->pitch;
+    t.dptr = (uint8_t*)p;
+    t.imported = true;
+    t.ipc_mapped = ipc;
+    t.live = true;
+    make_tensor_map(c, i);
+    *out = (wrcu_tex)i;
+    return WRCU_OK;
+  }
+  return wrcu_fail(c, WRCU_ERR_OOM, "texture_import: out of texture handles");
+}
+
+extern "C" int wrcu_peer_flags_create(wrcu_ctx* c, int count, wrcu_ipc_flags* out) {
+  if (!out || count <= 0 || count > 4096 || c->flags) return wrcu_fail(c, WRCU_ERR_INVALID, "peer_flags_create: bad arguments");
+  cudaSetDevice(c->device);
+  WRCU_CUDA(c, cudaMalloc((void**)&c->flags, (size_t)count * 4));
+  WRCU_CUDA(c, cudaMemset(c->flags, 0, (size_t)count * 4));
+  c->n_flags = count;
+  memset(out, 0, sizeof *out);
+#ifndef WRCU_HOSTEMU
+  cudaIpcMemHandle_t h;
+  WRCU_CUDA(c, cudaIpcGetMemHandle(&h, c->flags));
+  memcpy(out->handle, &h, sizeof h);
+#endif
+  out->pid = wr_pid();
+  out->address = (uint64_t)(uintptr_t)c->flags;
+  out->count = count;
+  out->device = c->device;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_peer_flags_open(wrcu_ctx* c, const wrcu_ipc_flags* in, int* peer_id) {
+  if (!in || !peer_id || in->count <= 0) return wrcu_fail(c, WRCU_ERR_INVALID, "peer_flags_open: bad arguments");
+  cudaSetDevice(c->device);
+  wrcu_ctx::PeerFlags pf = {nullptr, in->count, false};
+  if (in->pid == wr_pid()) {
+    int rc = enable_peer(c, in->device);
+    if (rc != WRCU_OK) return rc;
+    pf.ptr = (uint32_t*)(uintptr_t)in->address;
+  } else {
+#ifndef WRCU_HOSTEMU
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in->handle, sizeof h);
+    void* p = nullptr;
+    WRCU_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    pf.ptr = (uint32_t*)p;
+    pf.ipc = true;
+#else
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "peer_flags_open: no IPC in the host emulation");
+#endif
+  }
+  c->peers.push_back(pf);
+  *peer_id = (int)c->peers.size() - 1;
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_peer_signal(wrcu_ctx* c, int peer_id, int slot, uint32_t value) {
+  if (peer_id < 0 || peer_id >= (int)c->peers.size() || slot < 0 || slot >= c->peers[peer_id].count)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "peer_signal: bad arguments");
+  cudaSetDevice(c->device);
+#ifndef WRCU_HOSTEMU
+  wr_flag_signal<<<1, 1, 0, c->stream>>>(c->peers[peer_id].ptr + slot, value);
+  c->stats.kernel_launches++;
+  WRCU_CUDA(c, cudaGetLastError());
+#else
+  c->peers[peer_id].ptr[slot] = value;
+#endif
+  return WRCU_OK;
+}
+
+extern "C" int wrcu_peer_wait(wrcu_ctx* c, int slot, uint32_t value) {
+  if (!c->flags || slot < 0 || slot >= c->n_flags) return wrcu_fail(c, WRCU_ERR_INVALID, "peer_wait: bad arguments");
+  cudaSetDevice(c->device);
+#ifndef WRCU_HOSTEMU
+  wr_flag_wait<<<1, 1, 0, c->stream>>>(c->flags + slot, value, c->dev_err);
+  c->stats.kernel_launches++;
+  WRCU_CUDA(c, cudaGetLastError());
+#endif
   return WRCU_OK;
 }
 
@@ -1221,17 +1404,29 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     else                                                                         \
       WR_LAUNCH(k_r8, pgrid, WRCU_THREADS, c->stream, ra);                       \
   } while (0)
+  // kinds drawn under depth test: the depth-run variant when this batch has failing-sample bitmaps
+#ifdef WRCU_HOSTEMU
+#define LAUNCH_RASTER_RUNS(S) LAUNCH_RASTER(S)
+#else
+#define LAUNCH_RASTER_RUNS(S)                                                    \
+  do {                                                                           \
+    if (sa.depth_runs && T.fmt == WRCU_FMT_RGBA8) {                              \
+      auto k_runs = wr_raster<S, WRCU_FMT_RGBA8, true>;                           \
+      WR_LAUNCH(k_runs, pgrid, WRCU_THREADS, c->stream, ra);                     \
+    } else LAUNCH_RASTER(S);                                                     \
+  } while (0)
+#endif
   switch (kind) {
     case WRCU_KIND_CLIP_RECTANGLE: LAUNCH_RASTER(ClipRectShader); break;
     case WRCU_KIND_QUAD_MASK: LAUNCH_RASTER(QuadMaskShader); break;
     case WRCU_KIND_BRUSH_IMAGE:
-      if (features & WRCU_FEAT_REPETITION) LAUNCH_RASTER(ImageRepeatShader);
-      else LAUNCH_RASTER(ImageShader);
+      if (features & WRCU_FEAT_REPETITION) LAUNCH_RASTER_RUNS(ImageRepeatShader);
+      else LAUNCH_RASTER_RUNS(ImageShader);
       break;
-    case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER(TextShader); break;
-    case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
+    case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER_RUNS(TextShader); break;
+    case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER_RUNS(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
-    case WRCU_KIND_BRUSH_YUV_IMAGE: LAUNCH_RASTER(CompositeYuvShader); break;
+    case WRCU_KIND_BRUSH_YUV_IMAGE: LAUNCH_RASTER_RUNS(CompositeYuvShader); break;
     case WRCU_KIND_COMPOSITE:
       if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
 #ifndef WRCU_HOSTEMU
@@ -1253,23 +1448,24 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
 #endif
       LAUNCH_RASTER(CompositeShader);
       break;
-    case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER(OpacityShader); break;
-    case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER(BlendShader); break;
-    case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER(MixBlendShader); break;
+    case WRCU_KIND_BRUSH_OPACITY: LAUNCH_RASTER_RUNS(OpacityShader); break;
+    case WRCU_KIND_BRUSH_BLEND: LAUNCH_RASTER_RUNS(BlendShader); break;
+    case WRCU_KIND_BRUSH_MIX_BLEND: LAUNCH_RASTER_RUNS(MixBlendShader); break;
     case WRCU_KIND_BLUR: LAUNCH_RASTER(BlurShader); break;
     case WRCU_KIND_SCALE: LAUNCH_RASTER(ScaleShader); break;
     case WRCU_KIND_FAST_LINEAR_GRADIENT: LAUNCH_RASTER(FastLinearShader); break;
     case WRCU_KIND_LINEAR_GRADIENT: LAUNCH_RASTER(GradientShader); break;
     case WRCU_KIND_RADIAL_GRADIENT: LAUNCH_RASTER(RadialShader); break;
     case WRCU_KIND_CONIC_GRADIENT: LAUNCH_RASTER(ConicShader); break;
-    case WRCU_KIND_QUAD_RADIAL_GRADIENT: LAUNCH_RASTER(RadialShader); break;
-    case WRCU_KIND_QUAD_CONIC_GRADIENT: LAUNCH_RASTER(QuadConicShader); break;
+    case WRCU_KIND_QUAD_RADIAL_GRADIENT: LAUNCH_RASTER_RUNS(RadialShader); break;
+    case WRCU_KIND_QUAD_CONIC_GRADIENT: LAUNCH_RASTER_RUNS(QuadConicShader); break;
     case WRCU_KIND_LINE_DECORATION: LAUNCH_RASTER(LineDecorationShader); break;
     case WRCU_KIND_BORDER_SOLID: LAUNCH_RASTER(BorderSolidShader); break;
     case WRCU_KIND_BORDER_SEGMENT: LAUNCH_RASTER(BorderSegmentShader); break;
-    default: LAUNCH_RASTER(QuadShader); break;
+    default: LAUNCH_RASTER_RUNS(QuadShader); break;
   }
 #undef LAUNCH_RASTER
+#undef LAUNCH_RASTER_RUNS
   c->stats.kernel_launches++;
   if (c->profile) {
     WRCU_CUDA(c, cudaEventRecord(c->p1, c->stream));

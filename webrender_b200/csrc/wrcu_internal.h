@@ -41,6 +41,8 @@ struct WrTexture {
   size_t pitch = 0;
   uint8_t* dptr = nullptr;
   bool live = false;
+  bool imported = false;      // aliases another context's memory (wrcu_texture_import): never freed here
+  bool ipc_mapped = false;    //   ... through cudaIpcOpenMemHandle (another process)
   bool has_tmap = false;      // a 2-D TMA tensor map of this texture sits in the context's device table
   uint64_t pending_read = 0;  // fence of an in-flight async readback of this texture
 };
@@ -139,6 +141,11 @@ struct wrcu_ctx {
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
   // TMA: one 128-byte CUtensorMap per RGBA8 texture (box 256x16 px), built on the host at texture
   // creation (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint) and kept in a device table
+  // multi-GPU flags (wrcu_peer_*): own flag words + mapped peers
+  uint32_t* flags = nullptr;
+  int n_flags = 0;
+  struct PeerFlags { uint32_t* ptr; int count; bool ipc; };
+  std::vector<PeerFlags> peers;
   uint32_t* fail_pool = nullptr;  // depth-run bitmaps of the current batch (CmdCold::fail_off)
   int fail_cap = 0;               // words
   void* tmaps_dev = nullptr;

@@ -198,6 +198,12 @@ class CudaDevice(DeviceBase):
         self.lib.wrcu_fence_wait.argtypes = [C.c_void_p, C.c_uint64]
         self.lib.wrcu_profile_enable.argtypes = [C.c_void_p, C.c_int]
         self.lib.wrcu_last_raster_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        self.lib.wrcu_texture_export.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.IpcTexture)]
+        self.lib.wrcu_texture_import.argtypes = [C.c_void_p, C.POINTER(abi.IpcTexture), C.POINTER(C.c_uint32)]
+        self.lib.wrcu_peer_flags_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.IpcFlags)]
+        self.lib.wrcu_peer_flags_open.argtypes = [C.c_void_p, C.POINTER(abi.IpcFlags), C.POINTER(C.c_int)]
+        self.lib.wrcu_peer_signal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+        self.lib.wrcu_peer_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         self.lib.wrcu_fence_insert.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         ctx = C.c_void_p()
         rc = self.lib.wrcu_ctx_create(device_ordinal, C.byref(ctx))
@@ -262,6 +268,36 @@ class CudaDevice(DeviceBase):
         self._check(self.lib.wrcu_read_pixels_async(self.ctx, tex, x, y, w, h, out.ctypes.data, out.strides[0],
                                                     C.byref(f)))
         return f.value
+
+    # -- multi-GPU: shared framebuffer + stream-ordered flags -----------------------
+    def texture_export(self, tex):
+        """bytes of a wrcu_ipc_texture other contexts / processes can import"""
+        h = abi.IpcTexture()
+        self._check(self.lib.wrcu_texture_export(self.ctx, tex, C.byref(h)))
+        return bytes(h)
+
+    def texture_import(self, blob):
+        h = abi.IpcTexture.from_buffer_copy(blob)
+        out = C.c_uint32(0)
+        self._check(self.lib.wrcu_texture_import(self.ctx, C.byref(h), C.byref(out)))
+        return out.value
+
+    def peer_flags_create(self, count):
+        h = abi.IpcFlags()
+        self._check(self.lib.wrcu_peer_flags_create(self.ctx, count, C.byref(h)))
+        return bytes(h)
+
+    def peer_flags_open(self, blob):
+        h = abi.IpcFlags.from_buffer_copy(blob)
+        out = C.c_int(0)
+        self._check(self.lib.wrcu_peer_flags_open(self.ctx, C.byref(h), C.byref(out)))
+        return out.value
+
+    def peer_signal(self, peer_id, slot, value):
+        self._check(self.lib.wrcu_peer_signal(self.ctx, peer_id, slot, value & 0xFFFFFFFF))
+
+    def peer_wait(self, slot, value):
+        self._check(self.lib.wrcu_peer_wait(self.ctx, slot, value & 0xFFFFFFFF))
 
     def fence_insert(self):
         """glFenceSync on the draw stream; page-locked upload buffers are free again once it is waited on."""

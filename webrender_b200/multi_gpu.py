@@ -20,7 +20,7 @@ import numpy as np
 from . import abi
 from .frame import Batch, Clear, Frame, Target, TextureDesc, draw_frame
 from .gpu_types import (FrameTables, INVALID_SEGMENT_INDEX, PART_ALL, QF_APPLY_DEVICE_CLIP, composite_instance,
-                        quad_instance)
+                        ortho, quad_instance)
 
 
 @dataclass
@@ -89,6 +89,146 @@ def composite_ops(scene: TiledScene, names: List[str]) -> List[object]:
         ops.append(Batch(abi.KIND_COMPOSITE, composite_instance(rf, rf)[None, :], blend=abi.BLEND_NONE,
                          features=abi.FEAT_FAST_PATH | abi.FEAT_TEXTURE_2D, color=(name, "", "")))
     return ops
+
+
+def rank_frames(scene: TiledScene, mine: List[int], composite_clear=None):
+    """The two frames a rank draws for its share `mine` of the scene's tiles, the way one wr::Frame holds
+    many picture-cache targets: (1) ONE frame whose single pass has a PictureCacheTarget per tile, all
+    sharing one set of per-frame tables (one table upload per rank and frame instead of one per tile);
+    (2) the `composite` frame: one tile list for the rank's tiles into the texture named "fb"
+    (composite_simple, renderer/mod.rs:3340-3484; `composite_clear` = the framebuffer clear colour, or
+    None when another context clears it)."""
+    from .frame import Target as _T
+    t = FrameTables()
+    textures, targets = {}, []
+    off = {k: 0 for k in ("prim_headers_f", "prim_headers_i", "transforms", "render_tasks", "gpu_cache",
+                          "gpu_buffer_f", "gpu_buffer_i")}
+    merged = {k: [] for k in off}
+    for i in mine:
+        f = scene.tiles[i]
+        name = "tile%d" % i
+        textures[name] = f.textures["tile"]
+        tgt = f.passes[0][0]
+        ops = []
+        # re-base the tile's table addresses onto the merged tables (quad instances carry three of them:
+        # prim_address_i → gpu_buffer_i, prim_address_f → gpu_buffer_f, render task address)
+        base_i, base_f, base_t = off["gpu_buffer_i"], off["gpu_buffer_f"], off["render_tasks"] // 2
+        for op in tgt.ops:
+            if isinstance(op, Batch):
+                inst = op.instances.copy()
+                inst[:, 0] += base_i
+                inst[:, 1] += base_f
+                inst[:, 3] += base_t
+                ops.append(Batch(op.kind, inst, blend=op.blend, depth=op.depth, features=op.features, color=op.color,
+                                 clip_mask=op.clip_mask))
+            else:
+                ops.append(op)
+        targets.append(_T(name, ops=ops))
+        for k in off:
+            arr = f.tables[k]
+            if k == "transforms" and off[k]:
+                continue  # every tile frame carries the identity palette entry only: keep one copy
+            merged[k].append(arr)
+            off[k] += len(arr)
+    tables = {}
+    for k, lst in merged.items():
+        dt = np.int32 if k.endswith("_i") else np.float32
+        tables[k] = np.ascontiguousarray(np.concatenate(lst)) if lst else np.zeros((0, 4), dt)
+    tiles_frame = Frame(tables, textures, [targets])
+    names = ["tile%d" % i for i in mine]
+    ops = [Clear(color=composite_clear)] if composite_clear is not None else []
+    for name, i in zip(names, mine):
+        rf = tuple(float(v) for v in scene.rects[i])
+        ops.append(Batch(abi.KIND_COMPOSITE, composite_instance(rf, rf)[None, :], blend=abi.BLEND_NONE,
+                         features=abi.FEAT_FAST_PATH | abi.FEAT_TEXTURE_2D, color=(name, "", "")))
+    ctex = {"fb": TextureDesc(abi.FMT_RGBA8, scene.width, scene.height)}
+    ctex.update({n: textures[n] for n in names})
+    comp_frame = Frame(FrameTables().arrays(), ctex, [[Target("fb", ops=ops)]])
+    return tiles_frame, comp_frame
+
+
+class DirectShardedRenderer:
+    """One frame's tiles sharded over GPUs with NO gather: the compositing context (rank 0) exports its
+    framebuffer, every other context imports it (CUDA IPC across processes, raw mapping inside one
+    process) and runs `composite` for its own tiles with that framebuffer as the render target — the copy
+    kernel's bulk-tensor stores go over NVLink straight into rank 0's memory.  Ordering is by flag words
+    polled on the CUDA streams (wrcu_peer_signal / wrcu_peer_wait); the host never synchronises inside
+    a frame.  Per frame and rank the host makes two native Renderer::render calls (C++ host mirror).
+
+    Set-up plumbing, once: every rank publishes `self.blob` (a few hundred bytes: the framebuffer and flag
+    handles) and calls connect() with the list of all ranks' blobs — torch.distributed.all_gather_object
+    between processes, a plain list in-process."""
+
+    CLEAR = (0.0, 0.0, 0.0, 0.0)
+
+    def __init__(self, dev, scene: TiledScene, rank, world):
+        from .host import HostRenderer
+        self.dev, self.scene, self.rank, self.world = dev, scene, rank, world
+        self.mine = assign_tiles(len(scene.tiles), world)[rank]
+        self.frame_no = 0
+        self.hr = HostRenderer(dev)
+        fb_blob = b""
+        if rank == 0:
+            self.fb = dev.texture_create(abi.FMT_RGBA8, scene.width, scene.height)
+            fb_blob = dev.texture_export(self.fb)
+        self.blob = (fb_blob, dev.peer_flags_create(world + 1))
+
+    def connect(self, blobs):
+        dev, rank, world, scene = self.dev, self.rank, self.world, self.scene
+        if rank != 0:
+            self.fb = dev.texture_import(blobs[0][0])
+            self.peer0 = dev.peer_flags_open(blobs[0][1])
+            self.peers = {}
+        else:
+            self.peers = {r: dev.peer_flags_open(blobs[r][1]) for r in range(1, world)}
+        tiles_frame, comp_frame = rank_frames(scene, self.mine)
+        self.nf_tiles = self.hr.build(tiles_frame)
+        handles = {"fb": self.fb}
+        handles.update({n: h for n, h in self.nf_tiles.handles.items() if n.startswith("tile")})
+        self.nf_comp = self.hr.build(comp_frame, handles)
+        self.proj = ortho(scene.width, scene.height)
+
+    # the frame is queued in three steps so several in-process contexts can be driven from one thread
+    def begin(self):
+        """rank 0: clear the framebuffer, then let the others composite into it"""
+        self.frame_no += 1
+        if self.rank == 0:
+            s = self.scene
+            self.dev.target_bind(self.fb, 0, self.proj, (0, 0, s.width, s.height))
+            self.dev.clear(None, self.CLEAR, None)
+            for r, pid in self.peers.items():
+                self.dev.peer_signal(pid, 0, self.frame_no)
+
+    def draw(self):
+        """every rank: its tiles, then its tile list into the (shared) framebuffer"""
+        if self.mine:
+            self.hr.render_native(self.nf_tiles)
+        if self.rank != 0:
+            self.dev.peer_wait(0, self.frame_no)          # rank 0 has cleared this frame's framebuffer
+        if self.mine:
+            self.hr.render_native(self.nf_comp)
+        if self.rank != 0:
+            self.dev.peer_signal(self.peer0, self.rank, self.frame_no)
+
+    def end(self):
+        """rank 0: the frame is complete once every other rank's stores have landed"""
+        if self.rank == 0:
+            for r in self.peers:
+                self.dev.peer_wait(r, self.frame_no)
+
+    def render(self):
+        self.begin()
+        self.draw()
+        self.end()
+
+    def read_framebuffer(self):
+        assert self.rank == 0
+        return self.dev.read_pixels(self.fb, 0, 0, self.scene.width, self.scene.height, 4)
+
+    def close(self):
+        self.nf_comp.destroy()
+        self.nf_tiles.destroy()
+        self.hr.close()
 
 
 class _DevMem:
