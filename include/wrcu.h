@@ -319,6 +319,19 @@ int wrcu_texture_device_ptr(wrcu_ctx* ctx, wrcu_tex tex, void** dptr,
 /* The CUDA stream (cudaStream_t) the context queues work on. */
 int wrcu_stream(wrcu_ctx* ctx, void** stream);
 
+/* ---- software-compositor blit ------------------------------------------------------------------
+ * `Composite` of the SWGL surface (swgl/src/composite.h:532-590), the call Gecko's SwCompositor
+ * (compositor/sw_compositor.rs) makes per tile: the `src_rect` (x, y, w, h) of one RGBA8 texture into
+ * the `dst_rect` of another, clipped to `clip_rect` (destination space) — integer-ratio nearest
+ * scaling (scale_blit, composite.h:166-282) or, when flipped in x or when the sizes differ under a
+ * LINEAR filter (and the source is at least 2 texels wide), the 7-bit bilinear filter (linear_blit,
+ * composite.h:353-417); `opaque` copies, otherwise premultiplied-alpha over.  Bit-exact with the
+ * reference's row walkers, including their per-chunk float running sums. */
+int wrcu_composite_blit(wrcu_ctx* ctx, wrcu_tex dst, wrcu_tex src,
+                        const int32_t src_rect[4], const int32_t dst_rect[4],
+                        int opaque, int flip_x, int flip_y, int filter_linear,
+                        const int32_t clip_rect[4]);
+
 /* ---- multi-GPU: the tiles of ONE frame sharded over GPUs ----------------------
  * Picture-cache tiles are independent render targets (frame_builder.rs:995-1057): each GPU draws its
  * share with no data-path communication.  The one exchange step — finished tiles into the

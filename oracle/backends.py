@@ -250,6 +250,35 @@ class SwglDevice:
         self.gl.DeleteTexture(tex)
         del self.tex[tex]
 
+    # -- SwCompositor's call sequence (compositor/sw_compositor.rs: lock, composite, unlock) -------
+    def sw_composite(self, dst, src, src_rect, dst_rect, opaque, flip_x, flip_y, linear, clip_rect):
+        g = self.gl
+        g.LockTexture.restype = C.c_void_p
+        g.LockTexture.argtypes = [C.c_uint]
+        g.UnlockResource.argtypes = [C.c_void_p]
+        g.Composite.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_ubyte] * 3 + [C.c_uint] + [C.c_int] * 4
+        ld, ls = g.LockTexture(dst), g.LockTexture(src)
+        g.Composite(ld, ls, *src_rect, *dst_rect, 1 if opaque else 0, 1 if flip_x else 0, 1 if flip_y else 0,
+                    _G["LINEAR"] if linear else _G["NEAREST"], *clip_rect)
+        g.UnlockResource(ls)
+        g.UnlockResource(ld)
+
+    def locked_pixels(self, tex):
+        """GetResourceBuffer on a locked texture → a copy of what the compositor would read"""
+        g = self.gl
+        g.LockTexture.restype = C.c_void_p
+        g.LockTexture.argtypes = [C.c_uint]
+        g.UnlockResource.argtypes = [C.c_void_p]
+        g.GetResourceBuffer.restype = C.c_void_p
+        g.GetResourceBuffer.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l = g.LockTexture(tex)
+        w, h, stride = C.c_int32(), C.c_int32(), C.c_int32()
+        p = g.GetResourceBuffer(l, C.byref(w), C.byref(h), C.byref(stride))
+        buf = (C.c_uint8 * (stride.value * h.value)).from_address(p)
+        out = np.frombuffer(buf, dtype=np.uint8).reshape(h.value, stride.value)[:, : w.value * 4].copy()
+        g.UnlockResource(l)
+        return out
+
     # -- update path: the reference's plumbing, call for call -------------------------
     def texture_upload_batch(self, tex, rects, staging):
         """upload_to_texture_cache (renderer/upload.rs): one TexSubImage2D per rect."""

@@ -356,3 +356,41 @@ def test_text_run_glyph_transform(xf, atlas):
                           color_modes=(0,) if atlas == "r8" else (0, 1, 2, 3), fractional=True,
                           glyph_transform=GLYPH_TRANSFORMS[xf], clip_runs=True)
     assert_same(render(EmuDevice, f, ["target"]), render(OracleDevice, f, ["target"]), xf)
+
+
+def test_sw_compositor_blit_math_against_swgl():
+    """wrcu_composite_blit's arithmetic (the device function, run on the host) against the unmodified reference's
+    Composite (swgl/src/composite.h:532-590): nearest / bilinear, flips, clips, over — bytes equal.  (The GPU
+    tier repeats this through libwrcu_gl.so's LockTexture / Composite / GetResourceBuffer.)"""
+    import ctypes as C
+    import numpy as np
+    from oracle.backends import SwglDevice, have_swgl
+    import test_gl_shim as T
+    if not have_swgl():
+        pytest.skip("oracle/_ref not built")
+    for case in T.SW_COMPOSITE_CASES:
+        name, (sw, sh), sr, dr, opaque, fx, fy, lin, cr = case
+        rng = np.random.RandomState(11)
+        src = rng.randint(0, 256, (sh, sw, 4)).astype(np.uint8)
+        al = src[..., 3:4].astype(np.uint16)
+        src[..., :3] = (src[..., :3].astype(np.uint16) * al // 255).astype(np.uint8)
+        dst = rng.randint(0, 256, (360, 640, 4)).astype(np.uint8)
+        d = SwglDevice()
+        ts, td = d.texture_create(abi.FMT_RGBA8, sw, sh), d.texture_create(abi.FMT_RGBA8, 640, 360)
+        d.texture_upload(ts, 0, 0, sw, sh, src.reshape(sh, sw * 4))
+        d.texture_upload(td, 0, 0, 640, 360, dst.reshape(360, 2560))
+        d.sw_composite(td, ts, sr, dr, opaque, fx, fy, lin, cr)
+        ref = d.locked_pixels(td)
+        d.close()
+        e = EmuDevice()
+        es, ed = e.texture_create(abi.FMT_RGBA8, sw, sh), e.texture_create(abi.FMT_RGBA8, 640, 360)
+        e.texture_upload(es, 0, 0, sw, sh, src.reshape(sh, sw * 4))
+        e.texture_upload(ed, 0, 0, 640, 360, dst.reshape(360, 2560))
+        f = e.lib.wremu_composite_blit
+        I4 = C.c_int32 * 4
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                      C.c_int, C.c_int, C.POINTER(C.c_int32)]
+        assert f(e.ctx, ed, es, I4(*sr), I4(*dr), int(opaque), int(fx), int(fy), int(lin), I4(*cr)) == 0
+        got = e.read_pixels(ed, 0, 0, 640, 360, 4)
+        e.close()
+        assert (got == ref).all(), name

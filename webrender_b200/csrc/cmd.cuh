@@ -22,6 +22,7 @@ enum : uint32_t {
   CMD_CLIP_DIST = 1u << 10,  // gl_ClipDistance in interpolants 2..5 bounds every span (rasterize.h:566-596)
   CMD_COPY = 1u << 11,      // composite: an opaque / premultiplied-over 1:1 rectangle copy, drawn by wr_composite_copy when
                             // the batch allows it (BatchInfo::all_copy)
+  CMD_RUNS = 1u << 12,      // has failing-sample bitmaps (CmdCold::fail_off): its depth runs are reproduced
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
 };
 

@@ -932,16 +932,28 @@ WRD bool wr_row_span_of(RasterArgs& ar, GenRow& g, const CmdHot& c0, int y, int&
   x1 = c.x1;
   return x1 > x0;
 }
-__global__ void __launch_bounds__(128) wr_depth_fail_rows(RasterArgs a, uint32_t* pool) {
+__global__ void __launch_bounds__(256) wr_depth_fail_rows(RasterArgs a, uint32_t* pool) {
+  // occluder candidates of the current command: index and hot rect (axis-aligned candidates are tested from
+  // shared memory alone; CMD_GENERAL / CMD_CLIP_DIST ones re-derive their row span)
   __shared__ unsigned short cand[WR_FAIL_CAND];
+  __shared__ short4 crect[WR_FAIL_CAND];
+  __shared__ unsigned char cgen[WR_FAIL_CAND];
   __shared__ int ncand;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int G = (int)gridDim.x;
   RasterArgs ar = a;
   GenRow g;
-  for (int ci = blockIdx.x; ci < a.n; ci += gridDim.x) {
+  // Work items = groups of `nwarps` rows of the commands that carry bitmaps (CMD_RUNS), dealt round-robin to
+  // the persistent CTAs: a tall command spreads over the grid, thousands of glyph-sized ones cost a CTA each.
+  int gbase = 0;
+  for (int ci = 0; ci < a.n; ci++) {
     const CmdHot c0 = a.hot[ci];
+    if (!(c0.flags & CMD_RUNS) || c0.x1 <= c0.x0) continue;  // CTA-uniform
+    const int rows = (int)c0.y1 - (int)c0.y0, ngroups = (rows + nwarps - 1) / nwarps;
+    const int first = ((int)blockIdx.x - gbase % G + G) % G;
+    gbase += ngroups;
+    if (first >= ngroups) continue;  // none of this command's row groups is ours
     const CmdCold& k = a.cold[c0.cold];
-    if (k.fail_off < 0 || c0.x1 <= c0.x0) continue;  // CTA-uniform
     int nc = 0;
     if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) {
       __syncthreads();
@@ -951,14 +963,20 @@ __global__ void __launch_bounds__(128) wr_depth_fail_rows(RasterArgs a, uint32_t
         const CmdHot o = a.hot[j];
         if (o.x1 > o.x0 && o.z < c0.z && o.x0 < c0.x1 && c0.x0 < o.x1 && o.y0 < c0.y1 && c0.y0 < o.y1) {
           const int p = atomicAdd(&ncand, 1);
-          if (p < WR_FAIL_CAND) cand[p] = (unsigned short)j;
+          if (p < WR_FAIL_CAND) {
+            cand[p] = (unsigned short)j;
+            crect[p] = make_short4(o.x0, o.y0, o.x1, o.y1);
+            cgen[p] = (o.flags & (CMD_GENERAL | CMD_CLIP_DIST)) ? 1 : 0;
+          }
         }
       }
       __syncthreads();
       nc = ncand;
     }
-    const int W = k.fail_w, rows = (int)c0.y1 - (int)c0.y0;
-    for (int r = warp; r < rows; r += nwarps) {
+    const int W = k.fail_w;
+    for (int grp = first; grp < ngroups; grp += G) {
+      const int r = grp * nwarps + warp;
+      if (r >= rows) continue;
       const int y = (int)c0.y0 + r;
       int sx0 = 0, sx1 = 0;
       wr_row_span_of(ar, g, c0, y, sx0, sx1);
@@ -968,11 +986,21 @@ __global__ void __launch_bounds__(128) wr_depth_fail_rows(RasterArgs a, uint32_t
       for (int wb = 0; wb < W; wb += 32) {
         const int nwords = min(32, W - wb);
         uint32_t mine = 0;
-        for (int i = 0; i < nwords; i++) {
-          const int xx = (int)c0.x0 + (wb + i) * 32 + lane;
-          const bool pass = xx >= sx0 && xx < sx1 && c0.z <= zrow[xx];
-          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, !pass);
-          if (lane == i) mine = bal;
+        // eight words (256 samples) per step: the depth loads of a step are independent, so their latencies overlap
+        for (int i0 = 0; i0 < nwords; i0 += 8) {
+          uint32_t zv[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int xx = (int)c0.x0 + (wb + i0 + u) * 32 + lane;
+            zv[u] = (i0 + u < nwords && xx >= sx0 && xx < sx1) ? zrow[xx] : 0u;  // 0 fails every z > 0
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int xx = (int)c0.x0 + (wb + i0 + u) * 32 + lane;
+            const bool pass = i0 + u < nwords && xx >= sx0 && xx < sx1 && c0.z <= zv[u];
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, !pass);
+            if (lane == i0 + u) mine = bal;
+          }
         }
         const int wx0 = (int)c0.x0 + (wb + lane) * 32;  // first sample of this lane's word
         auto or_span = [&](int ox0, int ox1) {
@@ -988,6 +1016,9 @@ __global__ void __launch_bounds__(128) wr_depth_fail_rows(RasterArgs a, uint32_t
           }
         } else {
           for (int q = 0; q < nc; q++) {
+            const short4 rc = crect[q];
+            if (y < rc.y || y >= rc.w) continue;
+            if (!cgen[q]) { or_span(rc.x, rc.z); continue; }
             const CmdHot o = a.hot[cand[q]];
             int ox0, ox1;
             if (wr_row_span_of(ar, g, o, y, ox0, ox1)) or_span(ox0, ox1);
@@ -1153,6 +1184,61 @@ WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb
     // whole tiles), so both rows can be stored unconditionally
     *(uint4*)p0 = make_uint4(rb[0] | (ga[0] << 8), rb[1] | (ga[1] << 8), rb[2] | (ga[2] << 8), rb[3] | (ga[3] << 8));
     *(uint4*)p1 = make_uint4(rb[4] | (ga[4] << 8), rb[5] | (ga[5] << 8), rb[6] | (ga[6] << 8), rb[7] | (ga[7] << 8));
+  }
+}
+
+// ---- shallow batches of plain solid quads: the streaming variant ---------------------------------------
+// With a handful of layers the pass is a read-modify-write of the target at HBM speed and the tile
+// machinery above (classification, compaction, three barriers per chunk, one tile in flight per CTA) is
+// pure latency.  Here every thread owns 2 x 4 pixels (two 16-byte accesses in flight), the <= FLAT_MAX
+// commands sit in shared memory, and a thread walks them in batch order testing coverage per pixel group —
+// the classic elementwise shape; the grid covers the batch's bounding box only.  Same blend arithmetic.
+#define FLAT_MAX 32
+#define FLAT_THREADS 256
+__global__ void __launch_bounds__(FLAT_THREADS) wr_raster_solid_flat(RasterArgs a) {
+  __shared__ int4 rect[FLAT_MAX];
+  __shared__ uint4 col[FLAT_MAX];
+  const BatchInfo bi = *a.info;
+  if (!bi.simple) return;  // mixed batch → generic kernel
+  if (threadIdx.x < a.n) {
+    const CmdHot c = a.hot[threadIdx.x];
+    rect[threadIdx.x] = make_int4(c.x0, c.x1 > c.x0 ? c.x1 : c.x0, c.y0, c.y1);
+    const uint32_t srb = (uint32_t)c.col[0] | ((uint32_t)c.col[2] << 16), sga = (uint32_t)c.col[1] | ((uint32_t)c.col[3] << 16);
+    col[threadIdx.x] = make_uint4(255u - c.col[3], srb, sga, 0u);
+  }
+  __syncthreads();
+  // the bounding box in units of 4 pixels x 2 rows
+  const int gx0 = max(bi.bx0, 0) >> 2, gx1 = (min(bi.bx1, a.tgt.w) + 3) >> 2;
+  const int gy0 = max(bi.by0, 0) >> 1, gy1 = (min(bi.by1, a.tgt.h) + 1) >> 1;
+  const int gw = gx1 - gx0, gh = gy1 - gy0;
+  if (gw <= 0 || gh <= 0) return;
+  const long long total = (long long)gw * gh;
+  for (long long g = (long long)blockIdx.x * FLAT_THREADS + threadIdx.x; g < total; g += (long long)gridDim.x * FLAT_THREADS) {
+    const int x = (gx0 + (int)(g % gw)) * 4, y = (gy0 + (int)(g / gw)) * 2;
+    uint4* p0 = (uint4*)(a.tgt.color + (size_t)y * a.tgt.color_pitch + (size_t)x * 4);
+    uint4* p1 = (uint4*)(a.tgt.color + (size_t)(y + 1) * a.tgt.color_pitch + (size_t)x * 4);
+    const uint4 v0 = *p0, v1 = *p1;  // (rows and columns past the target exist in the padded allocation)
+    uint32_t px[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    bool dirty = false;
+    for (int i = 0; i < a.n; i++) {
+      const int4 r = rect[i];
+      if (r.y <= x || r.x >= x + 4 || r.w <= y || r.z >= y + 2) continue;
+      const uint4 k = col[i];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int xx = x + (q & 3), yy = y + (q >> 2);
+        if (xx >= r.x && xx < r.y && yy >= r.z && yy < r.w) {
+          const uint32_t rb = wr_premult_over_pair(px[q] & 0x00FF00FFu, k.y, k.x);
+          const uint32_t ga = wr_premult_over_pair((px[q] >> 8) & 0x00FF00FFu, k.z, k.x);
+          px[q] = rb | (ga << 8);
+        }
+      }
+      dirty = true;
+    }
+    if (dirty) {
+      *p0 = make_uint4(px[0], px[1], px[2], px[3]);
+      *p1 = make_uint4(px[4], px[5], px[6], px[7]);
+    }
   }
 }
 

@@ -44,6 +44,7 @@ struct SetupArgs {
   TexView color2;
   TexView clip_mask;
   const TexView* tex_list;  // wrcu_draw_composite_tiles: sColor0 of instance i (nullptr: color0 for all)
+  int warp_per_inst;        // small batches: one WARP per instance (lane 0 runs the vertex stage, the warp fills its row table)
   int depth_runs;           // depth test on and the kind's shading depends on where passing runs start:
   int fail_cap;             //   commands get a failing-sample bitmap (CmdCold::fail_off) from a pool of fail_cap words
   int copy_ok;              // composite: blend off or premultiplied-alpha over, no depth → copy class possible
@@ -147,10 +148,45 @@ WRD void wr_fill_row_tables_warp(const SetupArgs& a, int idx) {
     wr_fill_row_table(a, wbase + src, lane);
   }
 }
+// One command's row table by a whole warp: the 2N edge sums x blocks of >= 16 rows spread over the lanes.
+WRD void wr_fill_row_table_spread(const SetupArgs& a, int cidx, int lane) {
+  const CmdHot c = a.hot[cidx];
+  const CmdCold& k = a.cold[cidx];
+  const int E = 2 * k.row_n, rows = c.y1 - c.y0;
+  if (E <= 0 || E > 32) return;
+  const int nblk = max(1, min(32 / E, rows / 16));
+  const int e = lane % E, blk = lane / E;
+  if (blk >= nblk) return;
+  const int per = (rows + nblk - 1) / nblk;
+  const int r0 = blk * per, r1 = min(rows, r0 + per);
+  if (r0 >= r1) return;
+  const int i = e >> 1;
+  const float top = (e & 1) ? k.i_rt[i] : k.i_lt[i], bot = (e & 1) ? k.i_rb[i] : k.i_lb[i];
+  const float sl = __fmul_rn(__fsub_rn(bot, top), k.yscale);
+  const float dy = __fsub_rn((float)c.y0 + 0.5f, k.yt);
+  float v = wr_repeat_add(__fadd_rn(top, __fmul_rn(dy, sl)), sl, r0);
+  float* t = a.row_tab + k.row_off + e;
+  for (int r = r0; r < r1; r++) {
+    t[(size_t)r * E] = v;
+    v = __fadd_rn(v, sl);
+  }
+}
+// Small batches (SetupArgs::warp_per_inst: what a page is mostly made of — a few instances per batch) are
+// latency, not throughput: one warp per instance, so the instances' dependent table fetches overlap and
+// each row table is filled by 32 lanes instead of one.
 #define WR_SETUP_KERNEL(name)                                                  \
   __global__ void name(SetupArgs a) {                                          \
     int idx = blockIdx.x * blockDim.x + threadIdx.x;                           \
     if (idx == 0) wr_reset_batch_info(a.info_next);                            \
+    if (a.warp_per_inst) {                                                     \
+      const int lane = threadIdx.x & 31;                                       \
+      idx >>= 5;                                                               \
+      if (idx >= a.n) return;                                                  \
+      if (lane == 0) name##_one(a, idx);                                       \
+      __syncwarp();                                                            \
+      if (a.cold[idx].row_off >= 0) wr_fill_row_table_spread(a, idx, lane);    \
+      return;                                                                  \
+    }                                                                          \
     if (idx < a.n) name##_one(a, idx);                                         \
     __syncwarp();                                                              \
     wr_fill_row_tables_warp(a, idx);                                           \
@@ -455,6 +491,8 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     if (off >= 0 && off + need <= a.fail_cap) {
       k.fail_off = off;
       k.fail_w = W;
+      h.flags |= CMD_RUNS;
+      a.hot[idx].flags = h.flags;
     }
   }
   if (ok) {

@@ -110,35 +110,37 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
     for (int i = 0; i < 4; i++) { k->g[i] = f[8 + i]; k->g[5 + i] = ub[i]; }
     k->g[4] = fast ? 1.0f : 0.0f;
     *(TexView*)&k->g[12] = tex0;
-    // Copy class (tma.cuh): an opaque, untinted instance whose texels map 1:1 onto whole pixels is a
-    // rectangle copy.  u must be exact (unit step, texel centres: every partial sum of the span walk is
-    // then a small dyadic rational, so no rounding can occur); v may carry the rounding of
-    // yScale = 1/height (rasterize.h:851-861) and is checked row by row against the sampler's
-    // tolerance: within 1/1024 texel of a centre both the nearest (floor) and the 7-bit linear
-    // (fraction 0) filters return exactly that texel.
+    // Copy class (tma.cuh): an untinted instance whose texels map 1:1 onto whole pixels is a rectangle copy
+    // (opaque) or a premultiplied-over of a rectangle (alpha tiles).  Device-space edges carry the rounding
+    // of the projection (x = 3072.00024), so "1:1" is judged the way the samplers do: a coordinate within
+    // 1/1024 texel of a texel centre gives exactly that texel through both the nearest filter (floor) and
+    // the 7-bit linear filter (fraction 0), and at unit step the span shaders step texels as integers
+    // (blendTextureNearestFast / the FAST linear filter, swgl_ext.h:284-371, 476-541) — so the first and the
+    // last pixel of the span decide u; v is walked row by row by the reference (Edge::nextRow) and is
+    // checked on every row of the row table unless its step is exact.
     bool copyc = false;
     const CmdHot h = a.hot[idx];
     const int tiw = tex0.w, tih = tex0.h;
+    k->i[2] = 0;
     if (a.copy_ok && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 &&
         tex0.tmap_id && is_white && !(h.flags & (CMD_GENERAL | CMD_AA | CMD_MASK | CMD_CLIP_DIST)) &&
-        (tiw & (tiw - 1)) == 0 && (tih & (tih - 1)) == 0 && k->xl == floorf(k->xl) && k->xr == floorf(k->xr) &&
+        (tiw & (tiw - 1)) == 0 && (tih & (tih - 1)) == 0 &&
         k->i_lt[0] == k->i_lb[0] && k->i_rt[0] == k->i_rb[0] && k->i_lt[1] == k->i_rt[1] && k->i_lb[1] == k->i_rb[1]) {
-      k->i[2] = 0;
+      const float tol = 1.0f / 1024.0f;
+      const int wpx = (int)h.x1 - (int)h.x0, rows = (int)h.y1 - (int)h.y0;
       const float su = (k->i_rt[0] - k->i_lt[0]) / (k->xr - k->xl);
       const float u0 = k->i_lt[0] + ((float)h.x0 + 0.5f - k->xl) * su;
-      const float txf = u0 * tw - 0.5f;
+      const float u1 = k->i_lt[0] + ((float)((int)h.x1 - 1) + 0.5f - k->xl) * su;
+      const float txf = floorf(u0 * tw);
       const float sl = (k->i_lb[1] - k->i_lt[1]) * k->yscale;
       const float v = k->i_lt[1] + ((float)h.y0 + 0.5f - k->yt) * sl;
       const float tyf = floorf(v * th);
-      const int rows = (int)h.y1 - (int)h.y0;
-      if (su * tw == 1.0f && txf == floorf(txf) && txf >= 0.0f && txf + (float)((int)h.x1 - (int)h.x0) <= tw &&
-          tyf >= 0.0f && tyf + (float)rows <= th && fabsf(v * th - (tyf + 0.5f)) <= (1.0f / 1024.0f)) {
+      if (fabsf(u0 * tw - (txf + 0.5f)) <= tol && fabsf(u1 * tw - (txf + (float)(wpx - 1) + 0.5f)) <= tol && txf >= 0.0f &&
+          txf + (float)wpx <= tw && tyf >= 0.0f && tyf + (float)rows <= th && fabsf(v * th - (tyf + 0.5f)) <= tol) {
         k->i[0] = (int)txf;
         k->i[1] = (int)tyf;
-        // an exact row step needs no further proof; otherwise the rows are checked against the row table
-        // (wr_composite_check_rows, warp-cooperative) and the candidate needs one
-        if (sl * th == 1.0f) copyc = true;
-        else if (k->row_off >= 0 && k->row_n == 2) { k->i[2] = 1; copyc = true; }
+        if (sl * th == 1.0f) copyc = true;                                      // exact row step: nothing can drift
+        else if (k->row_off >= 0 && k->row_n == 2) { k->i[2] = 1; copyc = true; }  // rows checked against the table
       }
     }
     if (copyc) a.hot[idx].flags |= CMD_COPY;
@@ -175,28 +177,37 @@ __device__ void wr_composite_check_rows(const SetupArgs& a, int idx) {
   }
 }
 __global__ void wr_setup_composite(SetupArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) wr_reset_batch_info(a.info_next);
+  if (a.warp_per_inst) {
+    const int lane = threadIdx.x & 31;
+    idx >>= 5;
+    if (idx >= a.n) return;
+    if (lane == 0) wr_setup_composite_one(a, idx);
+    __syncwarp();
+    if (a.cold[idx].row_off >= 0) wr_fill_row_table_spread(a, idx, lane);
+    __syncwarp();
+    // copy-class candidate whose row step is inexact: check its rows against the table just filled
+    const CmdHot h = a.hot[idx];
+    const CmdCold& k = a.cold[idx];
+    if (h.x1 > h.x0 && k.i[2] == 1) {
+      const float th = (float)wr_composite_tex(k).h;
+      const float* t = a.row_tab + k.row_off;
+      const int rows = (int)h.y1 - (int)h.y0;
+      bool bad = false;
+      for (int r = lane; r < rows; r += 32) bad = bad || fabsf(t[(size_t)r * 4 + 2] * th - ((float)(k.i[1] + r) + 0.5f)) > (1.0f / 1024.0f);
+      if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) {
+        a.hot[idx].flags &= ~CMD_COPY;
+        atomicAdd(&a.info->n_noncopy, 1);
+      }
+    }
+    return;
+  }
   if (idx < a.n) wr_setup_composite_one(a, idx);
   __syncwarp();
   wr_fill_row_tables_warp(a, idx);
   __syncwarp();
   wr_composite_check_rows(a, idx);
-  // The copy kernel moves boxes of different instances concurrently: a copy-class batch must not
-  // overlap itself (picture-cache tiles never do; surfaces that do keep the ordered tile kernel).
-  if (gridDim.x > 1) {
-    if (threadIdx.x == 0) a.info->all_copy = 0;
-    return;
-  }
-  __syncthreads();
-  if (idx < a.n) {
-    const CmdHot me = a.hot[idx];
-    if (me.x1 > me.x0 && me.y1 > me.y0)
-      for (int j = 0; j < idx; j++) {
-        const CmdHot o = a.hot[j];
-        if (o.x1 > o.x0 && o.y1 > o.y0 && o.x0 < me.x1 && me.x0 < o.x1 && o.y0 < me.y1 && me.y0 < o.y1) a.info->all_copy = 0;
-      }
-  }
 }
 
 // ---- copy-class composite: the tile list as 2-D bulk-tensor copies (see tma.cuh) ----------------

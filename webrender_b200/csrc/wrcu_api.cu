@@ -412,7 +412,11 @@ static void make_tensor_map(wrcu_ctx* c, int id) {
   t.has_tmap = true;
 }
 #else
-static void make_tensor_map(wrcu_ctx*, int) {}
+// host emulation: no copy engine, but the copy-class decision of the setup stage still runs (tests)
+static void make_tensor_map(wrcu_ctx* c, int id) {
+  WrTexture& t = c->tex[id];
+  t.has_tmap = t.fmt == WRCU_FMT_RGBA8 && t.w >= 256 && t.h >= 16;
+}
 #endif
 
 static WrTexture* get_tex(wrcu_ctx* c, wrcu_tex id) {
@@ -689,6 +693,133 @@ extern "C" int wrcu_gpu_cache_update(wrcu_ctx* c, int height, int clear, const w
   return WRCU_OK;
 }
 
+// ---- SwCompositor blit (swgl/src/composite.h:166-417, 532-590) -----------------------------------
+static int wait_pending_read(wrcu_ctx* c, WrTexture* t);
+static TexView tex_view(wrcu_ctx* c, wrcu_tex id);
+struct BlitArgs {
+  uint8_t* dst; int dst_pitch;
+  TexView src;
+  int dx0, dy0;                 // dstReq origin
+  int bx0, by0, bx1, by1;       // dstBounds, relative to dstReq
+  int sx0, sy0, sy1;            // srcReq.x0, .y0, .y1
+  // nearest: first source column/row (relative to srcReq) and the Bresenham fractions at dstBounds' corner
+  int sbx0, sby0, fracx0, fracy0, sw, sh, dw, dh, invert_y;
+  // linear: quantised uv at dstBounds' corner and per-pixel / per-row steps (x128)
+  float u0, v0, du, dv;
+  int opaque, linear;
+};
+WRD uint32_t wr_blit_over(uint32_t d, uint32_t s) {  // srcpx + dstpx - muldiv255(dstpx, alphas(srcpx)), saturating pack
+  const uint32_t cc = 255u - (s >> 24);
+  const uint32_t rb = wr_premult_over_pair(d & 0x00FF00FFu, s & 0x00FF00FFu, cc);
+  const uint32_t ga = wr_premult_over_pair((d >> 8) & 0x00FF00FFu, (s >> 8) & 0x00FF00FFu, cc);
+  return rb | (ga << 8);
+}
+WRD void wr_blit_pixel(const BlitArgs& a, int x, int y) {  // x, y relative to dstReq, inside dstBounds
+  uint32_t s;
+  if (!a.linear) {
+    // scale_row / the row stepping of scale_blit in closed form: `for (frac += srcW; frac >= dstW; frac -= dstW) src++`
+    const int col = a.sbx0 + (a.fracx0 + a.sw * (x - a.bx0)) / a.dw;
+    const int row = a.sby0 + (a.fracy0 + a.sh * (y - a.by0)) / a.dh;
+    const int sy = a.invert_y ? a.sy1 - 1 - row : a.sy0 + row;
+    s = *(const uint32_t*)(a.src.ptr + (size_t)sy * a.src.pitch + (size_t)(a.sx0 + col) * 4);
+  } else {
+    // linear_row_blit: uv = init_interp(srcUV, (srcDU, 0)); per 4-pixel chunk uv.x += 4 * srcDU; rows srcUV.y += srcDUV.y
+    const int i = x - a.bx0, j = i & 3, k = i >> 2;
+    float u = a.u0;
+    for (int q = 0; q < j; q++) u = __fadd_rn(u, a.du);
+    u = wr_repeat_add(u, __fmul_rn(4.0f, a.du), k);
+    const float v = wr_repeat_add(a.v0, a.dv, y - a.by0);
+    const Px p = wr_texture_linear_rgba8(a.src, (int)u, (int)v);
+    s = (uint32_t)wr_pack16(p.b) | ((uint32_t)wr_pack16(p.g) << 8) | ((uint32_t)wr_pack16(p.r) << 16) | ((uint32_t)wr_pack16(p.a) << 24);
+  }
+  uint32_t* d = (uint32_t*)(a.dst + (size_t)(a.dy0 + y) * a.dst_pitch) + a.dx0 + x;
+  *d = a.opaque ? s : wr_blit_over(*d, s);
+}
+#ifdef WRCU_HOSTEMU
+static void wr_sw_composite_blit(BlitArgs a) {
+  for (int y = a.by0; y < a.by1; y++)
+    for (int x = a.bx0; x < a.bx1; x++) wr_blit_pixel(a, x, y);
+}
+#else
+__global__ void wr_sw_composite_blit(BlitArgs a) {
+  const int x = a.bx0 + blockIdx.x * blockDim.x + threadIdx.x, y = a.by0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < a.bx1 && y < a.by1) wr_blit_pixel(a, x, y);
+}
+#endif
+
+struct IRect { int x0, y0, x1, y1; };
+static IRect irect_intersect(IRect a, IRect b) {
+  return IRect{a.x0 > b.x0 ? a.x0 : b.x0, a.y0 > b.y0 ? a.y0 : b.y0, a.x1 < b.x1 ? a.x1 : b.x1, a.y1 < b.y1 ? a.y1 : b.y1};
+}
+extern "C" int wrcu_composite_blit(wrcu_ctx* c, wrcu_tex dst_id, wrcu_tex src_id, const int32_t sr[4], const int32_t dr[4],
+                                   int opaque, int flip_x, int flip_y, int filter_linear, const int32_t cr[4]) {
+  WrTexture *d = get_tex(c, dst_id), *s = get_tex(c, src_id);
+  if (!d || !s || !sr || !dr || !cr || d->fmt != WRCU_FMT_RGBA8 || s->fmt != WRCU_FMT_RGBA8)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "composite_blit: needs two RGBA8 textures and three rects");
+  cudaSetDevice(c->device);
+  { int rcw = wait_pending_read(c, d); if (rcw != WRCU_OK) return rcw; }
+  const IRect srcReq{sr[0], sr[1], sr[0] + sr[2], sr[1] + sr[3]}, dstReq{dr[0], dr[1], dr[0] + dr[2], dr[1] + dr[3]};
+  if (srcReq.x1 <= srcReq.x0 || srcReq.y1 <= srcReq.y0 || dstReq.x1 <= dstReq.x0 || dstReq.y1 <= dstReq.y0) return WRCU_OK;
+  const IRect clip{cr[0] - dr[0], cr[1] - dr[1], cr[0] - dr[0] + cr[2], cr[1] - dr[1] + cr[3]};  // relative to dstReq
+  const int sw = sr[2], sh = sr[3], dw = dr[2], dh = dr[3];
+  const bool same = sw == dw && sh == dh;
+  const bool linear = s->w >= 2 && (flip_x || (!same && filter_linear));
+  BlitArgs a;
+  memset(&a, 0, sizeof a);
+  a.dst = d->dptr; a.dst_pitch = (int)d->pitch;
+  a.src = tex_view(c, src_id);
+  a.src.filter = WRCU_LINEAR;
+  a.dx0 = dstReq.x0; a.dy0 = dstReq.y0;
+  a.sx0 = srcReq.x0; a.sy0 = srcReq.y0; a.sy1 = srcReq.y1;
+  a.sw = sw; a.sh = sh; a.dw = dw; a.dh = dh;
+  a.opaque = opaque ? 1 : 0;
+  a.linear = linear ? 1 : 0;
+  a.invert_y = flip_y ? 1 : 0;
+  // dsttex.sample_bounds(dstReq) ∩ clipRect (Texture::sample_bounds, gl.cc:554-558)
+  IRect db = irect_intersect(IRect{0, 0, d->w, d->h}, dstReq);
+  db = IRect{db.x0 - dstReq.x0, db.y0 - dstReq.y0, db.x1 - dstReq.x0, db.y1 - dstReq.y0};
+  db = irect_intersect(db, clip);
+  if (linear) {
+    if (db.x1 <= db.x0 || db.y1 <= db.y0) return WRCU_OK;
+    float su = (float)srcReq.x0, sv = (float)srcReq.y0;
+    float du = (float)sw / (float)dw, dv = (float)sh / (float)dh;
+    if (flip_x) { su += (float)sw; du = -du; }
+    if (flip_y) { sv += (float)sh; dv = -dv; }
+    su += du * ((float)db.x0 + 0.5f);
+    sv += dv * ((float)db.y0 + 0.5f);
+    a.u0 = su * 128.0f + (0.5f - 0.5f * 128.0f);  // linearQuantize(srcUV, 128) (texture.h:428-430)
+    a.v0 = sv * 128.0f + (0.5f - 0.5f * 128.0f);
+    a.du = du * 128.0f;
+    a.dv = dv * 128.0f;
+  } else {
+    // scale_blit (composite.h:166-282): limit the destination so that no sample falls outside the source
+    IRect sb = irect_intersect(IRect{0, 0, s->w, s->h}, srcReq);
+    sb = IRect{sb.x0 - srcReq.x0, sb.y0 - srcReq.y0, sb.x1 - srcReq.x0, sb.y1 - srcReq.y0};
+    if (flip_y) { const int t0 = sh - sb.y1, t1 = sh - sb.y0; sb.y0 = t0; sb.y1 = t1; }  // invert_y
+    IRect sc{0 - srcReq.x0, 0 - srcReq.y0, s->w - srcReq.x0, s->h - srcReq.y0};  // srctex.bounds() - srcReq.origin()
+    if (flip_y) { const int t0 = sh - sc.y1, t1 = sh - sc.y0; sc.y0 = t0; sc.y1 = t1; }
+    // IntRect::scale(srcW, srcH, dstW, dstH, roundIn = true) (gl.cc:143-150), C integer division as there
+    sc = IRect{(sc.x0 * dw + (sw - 1)) / sw, (sc.y0 * dh + (sh - 1)) / sh, (sc.x1 * dw) / sw, (sc.y1 * dh) / sh};
+    db = irect_intersect(db, sc);
+    if (db.x1 <= db.x0 || db.y1 <= db.y0) return WRCU_OK;
+    const int fx = sw * db.x0, fy = sh * db.y0;
+    a.sbx0 = fx / dw > sb.x0 ? fx / dw : sb.x0;
+    a.sby0 = fy / dh > sb.y0 ? fy / dh : sb.y0;
+    a.fracx0 = fx % dw;
+    a.fracy0 = fy % dh;
+  }
+  a.bx0 = db.x0; a.by0 = db.y0; a.bx1 = db.x1; a.by1 = db.y1;
+#ifdef WRCU_HOSTEMU
+  wr_sw_composite_blit(a);
+#else
+  dim3 block(64, 4), grid((unsigned)((db.x1 - db.x0 + 63) / 64), (unsigned)((db.y1 - db.y0 + 3) / 4));
+  wr_sw_composite_blit<<<grid, block, 0, c->stream>>>(a);
+  WRCU_CUDA(c, cudaGetLastError());
+#endif
+  c->stats.kernel_launches++;
+  return WRCU_OK;
+}
+
 // ---- multi-GPU: shared framebuffer + stream-ordered flags -----------------------
 #ifdef WRCU_HOSTEMU
 static uint64_t wr_pid() { return 1; }
@@ -790,7 +921,9 @@ extern "C" int wrcu_peer_flags_create(wrcu_ctx* c, int count, wrcu_ipc_flags* ou
   if (!out || count <= 0 || count > 4096 || c->flags) return wrcu_fail(c, WRCU_ERR_INVALID, "peer_flags_create: bad arguments");
   cudaSetDevice(c->device);
   WRCU_CUDA(c, cudaMalloc((void**)&c->flags, (size_t)count * 4));
-  WRCU_CUDA(c, cudaMemset(c->flags, 0, (size_t)count * 4));
+  // zeroed before anyone can signal: the legacy-stream cudaMemset does not order against other contexts' streams
+  WRCU_CUDA(c, cudaMemsetAsync(c->flags, 0, (size_t)count * 4, c->stream));
+  WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n_flags = count;
   memset(out, 0, sizeof *out);
 #ifndef WRCU_HOSTEMU
@@ -1153,6 +1286,27 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   }
 #endif
   sa.copy_ok = !T.depth && (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA);
+  if (kind == WRCU_KIND_COMPOSITE && sa.copy_ok && !(features & WRCU_FEAT_YUV)) {
+    // The copy kernel moves boxes of different instances concurrently: a batch whose instances overlap keeps
+    // the ordered tile kernel.  Picture-cache tiles never overlap; checked here on the host copies of the
+    // CompositeInstance rects (device rect ∩ clip rect, rounded outwards), n is a tile list's length.
+    if (n > 256 || stride < 32) sa.copy_ok = 0;
+    else {
+      std::vector<float> bb((size_t)n * 4);
+      for (int i = 0; i < n; i++) {
+        const float* f = (const float*)((const uint8_t*)instances + (size_t)i * stride);
+        const float x0 = fminf(f[0], f[2]), x1 = fmaxf(f[0], f[2]), y0 = fminf(f[1], f[3]), y1 = fmaxf(f[1], f[3]);
+        bb[4 * i + 0] = floorf(fmaxf(x0, f[4])); bb[4 * i + 1] = floorf(fmaxf(y0, f[5]));
+        bb[4 * i + 2] = ceilf(fminf(x1, f[6]));  bb[4 * i + 3] = ceilf(fminf(y1, f[7]));
+      }
+      for (int i = 0; i < n && sa.copy_ok; i++) {
+        if (bb[4 * i + 2] <= bb[4 * i] || bb[4 * i + 3] <= bb[4 * i + 1]) continue;
+        for (int j = 0; j < i; j++)
+          if (bb[4 * j] < bb[4 * i + 2] && bb[4 * i] < bb[4 * j + 2] && bb[4 * j + 1] < bb[4 * i + 3] && bb[4 * i + 1] < bb[4 * j + 3] &&
+              bb[4 * j + 2] > bb[4 * j] && bb[4 * j + 3] > bb[4 * j + 1]) { sa.copy_ok = 0; break; }
+      }
+    }
+  }
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
   sa.color2 = tex_view(c, st->color[2]);
@@ -1188,6 +1342,12 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   sa.clip_mask = tex_view(c, st->clip_mask);
 
   int sblocks = (n + 127) / 128;
+#ifndef WRCU_HOSTEMU
+  if (n <= 64) {  // small batch: a warp per instance (setup_common.cuh WR_SETUP_KERNEL)
+    sa.warp_per_inst = 1;
+    sblocks = (n * 32 + 127) / 128;
+  }
+#endif
   switch (kind) {
     case WRCU_KIND_QUAD_TEXTURED:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "quad instance stride < 16");
@@ -1353,8 +1513,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   if (sa.depth_runs) {
     // depth runs: the failing-sample bitmaps of this batch, before any of its depth writes
     ra.fail_pool = c->fail_pool;
-    const int fgrid = n < c->sm_count * 8 ? n : c->sm_count * 8;
-    wr_depth_fail_rows<<<fgrid, 128, 0, c->stream>>>(ra, c->fail_pool);
+    wr_depth_fail_rows<<<c->sm_count * 4, 256, 0, c->stream>>>(ra, c->fail_pool);
     c->stats.kernel_launches++;
   }
 #endif
@@ -1375,6 +1534,15 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
         nb = 8;
       c->fast_ctas_per_sm = nb;
     }
+    if (n <= FLAT_MAX) {
+      // shallow batch: the streaming variant (8 pixels per thread over the bounding box; grid sized for the
+      // whole target, threads beyond the box leave at once)
+      const long long groups = ((long long)(T.w + 3) / 4) * ((T.h + 1) / 2);
+      long long blocks = (groups + FLAT_THREADS - 1) / FLAT_THREADS;
+      const long long cap = (long long)c->sm_count * 64;
+      if (blocks > cap) blocks = cap;
+      wr_raster_solid_flat<<<(unsigned)blocks, FLAT_THREADS, 0, c->stream>>>(ra);
+    } else {
     const int n_tiles = (int)(grid.x * grid.y);
     const int sms = c->sm_count > 0 ? c->sm_count : 148;
     int best_grid = n_tiles;
@@ -1388,6 +1556,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       }
     }
     wr_raster_solid_premult<<<best_grid, FAST_THREADS, 0, c->stream>>>(ra);
+    }
 #endif
     c->stats.kernel_launches++;
   }
@@ -1430,8 +1599,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     case WRCU_KIND_COMPOSITE:
       if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
 #ifndef WRCU_HOSTEMU
-      if (c->tmaps_dev && T.tmap_id && !T.depth &&
-          (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA)) {
+      if (c->tmaps_dev && T.tmap_id && sa.copy_ok) {
         // copy-class tile lists (decided on the device, BatchInfo::all_copy) go through the copy engine;
         // whichever of the two kernels is not in charge returns at once
         const size_t smem0 = (size_t)WR_TMA_STAGES * WR_TMA_BOX_BYTES, smem1 = (size_t)WR_TMA_BLEND_STAGES * 2 * WR_TMA_BOX_BYTES;

@@ -834,19 +834,57 @@ void BeginQuery(GLenum, GLuint) {}
 void EndQuery(GLenum) {}
 void GetQueryObjectui64v(GLuint, GLenum pname, GLuint64* params) { params[0] = pname == GL_QUERY_RESULT_AVAILABLE ? 1 : 0; }
 
-// ---- software-compositor hooks: CPU pointers into SWGL's own texture memory ----------------------
-void* LockFramebuffer(GLuint) { set_error(GL_INVALID_OPERATION); return nullptr; }
-void* LockTexture(GLuint) { set_error(GL_INVALID_OPERATION); return nullptr; }
-void LockResource(void*) {}
-void UnlockResource(void*) {}
-void* GetResourceBuffer(void*, int32_t* w, int32_t* h, int32_t* stride) {
-  if (w) *w = 0;
-  if (h) *h = 0;
-  if (stride) *stride = 0;
-  return nullptr;
+// ---- software-compositor hooks (swgl/src/composite.h:485-590; compositor/sw_compositor.rs) --------------
+// A locked resource is a texture pinned for the compositor: Composite() blits between two of them on the
+// device (wrcu_composite_blit); GetResourceBuffer() hands out a host copy of the pixels (the reference
+// returns its own CPU buffer) — read back at that moment, valid until the resource is unlocked.
+struct Locked {
+  GLuint tex = 0;
+  int locks = 0;
+  std::vector<uint8_t> host;
+};
+static std::map<GLuint, Locked*> g_locked;
+static Locked* lock_tex(GLuint id) {
+  Tex* t = tex_of(id);
+  if (!t || !t->dev) { set_error(GL_INVALID_OPERATION); return nullptr; }
+  Locked*& l = g_locked[id];
+  if (!l) { l = new Locked(); l->tex = id; }
+  l->locks++;
+  return l;
 }
-void Composite(void*, void*, GLint, GLint, GLsizei, GLsizei, GLint, GLint, GLsizei, GLsizei, GLboolean, GLboolean, GLboolean, GLenum,
-               GLint, GLint, GLsizei, GLsizei) { set_error(GL_INVALID_OPERATION); }
+void* LockTexture(GLuint tex) { return lock_tex(tex); }
+void* LockFramebuffer(GLuint fbo) {
+  auto it = ctx->fbo.find(fbo);
+  if (it == ctx->fbo.end() || !it->second.color) { set_error(GL_INVALID_OPERATION); return nullptr; }
+  return lock_tex(it->second.color);
+}
+void LockResource(void* r) { if (r) ((Locked*)r)->locks++; }
+void UnlockResource(void* r) {
+  if (!r) return;
+  Locked* l = (Locked*)r;
+  if (--l->locks <= 0) { l->locks = 0; std::vector<uint8_t>().swap(l->host); }
+}
+void* GetResourceBuffer(void* r, int32_t* w, int32_t* h, int32_t* stride) {
+  Locked* l = (Locked*)r;
+  Tex* t = l ? tex_of(l->tex) : nullptr;
+  if (w) *w = t ? t->w : 0;
+  if (h) *h = t ? t->h : 0;
+  if (stride) *stride = t ? t->w * bytes_per_pixel(t->ifmt) : 0;
+  if (!t) return nullptr;
+  const size_t row = (size_t)t->w * bytes_per_pixel(t->ifmt);
+  l->host.resize(row * t->h);
+  if (wrcu_read_pixels(ctx->dev, t->dev, 0, 0, t->w, t->h, l->host.data(), row) != WRCU_OK) { set_error(GL_INVALID_OPERATION); return nullptr; }
+  return l->host.data();
+}
+void Composite(void* dst, void* src, GLint sx, GLint sy, GLsizei sw, GLsizei sh, GLint dx, GLint dy, GLsizei dw, GLsizei dh,
+               GLboolean opaque, GLboolean flipX, GLboolean flipY, GLenum filter, GLint cx, GLint cy, GLsizei cw, GLsizei ch) {
+  if (!dst || !src) return;
+  Tex *d = tex_of(((Locked*)dst)->tex), *s = tex_of(((Locked*)src)->tex);
+  if (!d || !s || bytes_per_pixel(d->ifmt) != 4 || bytes_per_pixel(s->ifmt) != 4 || !d->dev || !s->dev) { set_error(GL_INVALID_OPERATION); return; }
+  const int32_t sr[4] = {sx, sy, sw, sh}, dr[4] = {dx, dy, dw, dh}, cr[4] = {cx, cy, cw, ch};
+  check(wrcu_composite_blit(ctx->dev, d->dev, s->dev, sr, dr, opaque ? 1 : 0, flipX ? 1 : 0, flipY ? 1 : 0,
+                            filter == GL_LINEAR ? 1 : 0, cr));
+}
 void CompositeYUV(void*, void*, void*, void*, int, GLuint, GLint, GLint, GLsizei, GLsizei, GLint, GLint, GLsizei, GLsizei, GLboolean,
                   GLboolean, GLint, GLint, GLsizei, GLsizei) { set_error(GL_INVALID_OPERATION); }
 
