@@ -713,9 +713,16 @@ def main():
         traffic, traffic_src = None, None
         prof = os.path.join(ROOT, "profiles", "hot_kernel.json")
         if os.path.exists(prof):
+            # ncu's DRAM bytes describe the kernel they were captured from: use them only while the source
+            # that defines the kernel is unchanged (tools/hot_kernel.py stamps its SHA-1 into the record)
+            import hashlib
             pj = json.load(open(prof))
-            traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
-            traffic_src = pj.get("source")
+            sha = hashlib.sha1(open(os.path.join(ROOT, "webrender_b200", "csrc", "raster.cuh"), "rb").read()).hexdigest()
+            if pj.get("raster_cuh_sha1") == sha:
+                traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
+                traffic_src = pj.get("source")
+            else:
+                traffic_src = "stale: profiles/hot_kernel.json was captured from another version of raster.cuh"
         line = {
             "metric": "Mpix/s composited at 3840x2160 (alpha-blend brush pass)",
             "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
