@@ -303,6 +303,38 @@ struct WrCommon {
     this->skip_w_func = &skip;                                                       \
   }
 
+// Fragment shaders with varyings (or reading gl_FragCoord.z/.w) also get the perspective variants the
+// translator emits (lib.rs:660-690, 716-745, 3576-3590, 3627-3631): the shader defines
+// read_perspective_inputs / step_perspective_inputs next to the plain pair and uses this macro instead.
+#define WR_FRAGMENT_ABI_W()                                                    \
+  static void run(FragmentShaderImpl* impl) {                                  \
+    Self* self = (Self*)impl;                                                  \
+    self->main();                                                              \
+    self->step_interp_inputs();                                                \
+  }                                                                            \
+  static void skip(FragmentShaderImpl* impl, int steps) {                      \
+    Self* self = (Self*)impl;                                                  \
+    self->step_interp_inputs(steps);                                           \
+  }                                                                            \
+  static void run_perspective(FragmentShaderImpl* impl) {                      \
+    Self* self = (Self*)impl;                                                  \
+    self->main();                                                              \
+    self->step_perspective_inputs();                                           \
+  }                                                                            \
+  static void skip_perspective(FragmentShaderImpl* impl, int steps) {          \
+    Self* self = (Self*)impl;                                                  \
+    self->step_perspective_inputs(steps);                                      \
+  }                                                                            \
+  void init_fragment_abi() {                                                   \
+    this->init_span_func = &read_interp_inputs;                                \
+    this->run_func = &run;                                                     \
+    this->skip_func = &skip;                                                   \
+    this->enable_perspective();                                                \
+    this->init_span_w_func = &read_perspective_inputs;                         \
+    this->run_w_func = &run_perspective;                                       \
+    this->skip_w_func = &skip_perspective;                                     \
+  }
+
 // Boilerplate for the program class (lib.rs:224-241).
 #define WR_PROGRAM(NAME, KEY)                                                  \
   struct NAME##_program : ProgramImpl, NAME##_frag {                           \

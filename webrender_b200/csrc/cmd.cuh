@@ -24,6 +24,9 @@ enum : uint32_t {
                             // the batch allows it (BatchInfo::all_copy)
   CMD_RUNS = 1u << 12,      // has failing-sample bitmaps (CmdCold::fail_off): its depth runs are reproduced
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
+  CMD_PERSP = 1u << 13,     // w differs between the vertices: draw_perspective (rasterize.h:1064-1545) — a clipped convex
+                            // polygon (PerspPoly in the row-table pool, CmdCold::row_off), per-row spans from its edge walk,
+                            // z/w and the interpolants (scaled by 1/w) stepped per sample; always set together with CMD_GENERAL
 };
 
 struct __align__(16) CmdHot {
@@ -72,6 +75,31 @@ struct __align__(16) CmdCold {
   // per row of the hot rect 1 + fail_w words — [0] the number of failing samples inside the row's span,
   // then bit i of the bitmap = sample hot.x0 + i fails the depth test (or lies outside the row's span).
   int fail_off, fail_w, rpad;
+};
+
+// CMD_PERSP: the polygon draw_perspective hands to draw_perspective_spans — up to 4 + 6 vertices after
+// clip_side (rasterize.h:1289-1420), in screen space with w = 1/clip.w, the vertex interpolants, the
+// clipped AA edge mask, the clip rect and the edge walk recorded as events (as CmdCold::gev).
+#define WR_PP_MAXV 10
+#define WR_PP_MAXEV 14
+struct PerspPoly {
+  int nump, n_ev, flipped, aa_mask;
+  float clip[4];
+  float px[WR_PP_MAXV], py[WR_PP_MAXV], pz[WR_PP_MAXV], pw[WR_PP_MAXV];
+  float interp[WR_PP_MAXV][WR_NI];
+  struct { short row, lrow, rrow; uint8_t l0, l1, r0, r1; } ev[WR_PP_MAXEV];
+};
+#define WR_PP_FLOATS ((int)((sizeof(PerspPoly) + 15) / 16 * 4))
+
+// Per-(command,row) state of a perspective polygon (wr_persp_row): the left / right Edge of
+// draw_perspective_spans at this row — (x, z, w) and which polygon edge each is on — and the span's
+// z/w start and step (rasterize.h:1236-1252).
+struct PerspRow {
+  const PerspPoly* poly;
+  float lx, lz, lw, rx, rz, rw;
+  float step_scale, x0f;   // 1 / (right.x - left.x), span.start + 0.5 - left.x
+  float zw0[2], step_zw[2];
+  int lv0, lv1, lrow, rv0, rv1, rrow;
 };
 
 // Per-(command,row) state of a general quad, computed by wr_general_row.

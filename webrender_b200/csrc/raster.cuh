@@ -40,6 +40,7 @@ struct RasterArgs {
   const float4* gpu_cache;  // component-transfer tables
   int n_gpu_cache;
   const GenRow* gen;  // per-thread row state of the current CMD_GENERAL command
+  const PerspRow* persp;  // ... of the current CMD_PERSP command (nullptr otherwise): varyings are w * interp_perspective
   const uint32_t* tile_mask;  // bitmask bins (see SetupArgs), nullptr = scan every command
   const uint32_t* wide_mask;
   const uint32_t* tile_any;  // see SetupArgs
@@ -55,6 +56,7 @@ struct RasterArgs {
   const uint32_t* fail_pool;
   const void* tmaps;     // device table of CUtensorMap records, indexed by TexView::tmap_id
   int copy_eligible;     // composite: a copy-class batch (BatchInfo::all_copy) is drawn by wr_composite_copy
+  int tmap_acquire;      // tensor-map table slots have been reused: acquire each map before use (tma.cuh)
 };
 
 #define CHUNK_CMDS 256
@@ -169,9 +171,151 @@ WRD bool wr_general_row(const CmdCold& k, const CmdHot& c, int y, GenRow& g, Cmd
   return sx1 > sx0;
 }
 
+// ---- perspective (draw_perspective_spans, rasterize.h:1064-1283) -------------------------------------
+#ifdef WRCU_HOSTEMU
+#define WRD_NOINLINE_R static
+#else
+#define WRD_NOINLINE_R __device__ __noinline__
+#endif
+// One Edge of the perspective walk at row y: Edge(y_init, p0, p1, ..) + (y - init row) nextRow() steps.
+WRD void wr_persp_edge(const PerspPoly& P, int v0, int v1, int init_row, int y, float* x, float* z, float* w, float* xslope) {
+  const float ys = (float)init_row + 0.5f;
+  const float yScale = 1.0f / wr_max(P.py[v1] - P.py[v0], 1.0f / 256);
+  const float dy = ys - P.py[v0];
+  const float xs = (P.px[v1] - P.px[v0]) * yScale, zs = (P.pz[v1] - P.pz[v0]) * yScale, ws = (P.pw[v1] - P.pw[v0]) * yScale;
+  *x = wr_repeat_add(P.px[v0] + dy * xs, xs, y - init_row);
+  *z = wr_repeat_add(P.pz[v0] + dy * zs, zs, y - init_row);
+  *w = wr_repeat_add(P.pw[v0] + dy * ws, ws, y - init_row);
+  *xslope = xs;
+}
+// The row's edges, aa_span and the z/w set-up of the span.  Fills g (AA ramps, as wr_general_row), pr and the
+// row's span in `out`; false = empty.
+WRD_NOINLINE_R bool wr_persp_row(const float* row_tab, const CmdCold& k, const CmdHot& c, int y, GenRow& g, PerspRow& pr, CmdHot& out) {
+  const PerspPoly& P = *(const PerspPoly*)(row_tab + k.row_off);
+  int e = 0;
+  for (int i = 1; i < P.n_ev; i++)
+    if (P.ev[i].row <= y) e = i;
+  const int l0 = P.ev[e].l0, l1 = P.ev[e].l1, r0 = P.ev[e].r0, r1 = P.ev[e].r1;
+  float lcx, lcz, lcw, lcs, rcx, rcz, rcw, rcs;
+  wr_persp_edge(P, l0, l1, P.ev[e].lrow, y, &lcx, &lcz, &lcw, &lcs);
+  wr_persp_edge(P, r0, r1, P.ev[e].rrow, y, &rcx, &rcz, &rcw, &rcs);
+  const int lcm = (P.aa_mask >> l1) & 1, rcm = (P.aa_mask >> r0) & 1;
+  float leftx, lefts, rightx, rights;
+  int lmask, rmask;
+  if (P.flipped) {
+    leftx = rcx; lefts = rcs; lmask = rcm; rightx = lcx; rights = lcs; rmask = lcm;
+    pr.lz = rcz; pr.lw = rcw; pr.rz = lcz; pr.rw = lcw;
+    pr.lv0 = r0; pr.lv1 = r1; pr.lrow = P.ev[e].rrow; pr.rv0 = l0; pr.rv1 = l1; pr.rrow = P.ev[e].lrow;
+  } else {
+    leftx = lcx; lefts = lcs; lmask = lcm; rightx = rcx; rights = rcs; rmask = rcm;
+    pr.lz = lcz; pr.lw = lcw; pr.rz = rcz; pr.rw = rcw;
+    pr.lv0 = l0; pr.lv1 = l1; pr.lrow = P.ev[e].lrow; pr.rv0 = r0; pr.rv1 = r1; pr.rrow = P.ev[e].rrow;
+  }
+  pr.poly = &P;
+  pr.lx = leftx;
+  pr.rx = rightx;
+  g.lx = leftx;
+  g.rx = rightx;
+  const float cx0 = P.clip[0], cx1 = P.clip[2];
+  const float cs0 = wr_clamp(wr_min(wr_min(P.px[l0], P.px[l1]), wr_min(P.px[r0], P.px[r1])), cx0, cx1);
+  const float cs1 = wr_clamp(wr_max(wr_max(P.px[l0], P.px[l1]), wr_max(P.px[r0], P.px[r1])), cx0, cx1);
+  int sx0, sx1;
+  out = c;
+  if (!(c.flags & CMD_AA)) {
+    sx0 = (int)floorf(wr_clamp(leftx, cs0, cs1) + 0.5f);
+    sx1 = (int)floorf(wr_clamp(rightx, cs0, cs1) + 0.5f);
+  } else {
+    int la0, la1, ra0, ra1;
+    if (lmask) {
+      float rad = 0.5f * fabsf(lefts);
+      la0 = (int)floorf(wr_clamp(leftx - rad, cs0, cs1));
+      la1 = (int)ceilf(wr_clamp(leftx + rad, cs0, cs1));
+      float dx = (-1.0f * 256.0f) * (1.0f / sqrtf(1.0f + lefts * lefts));
+      g.aa_l0 = 128.0f + dx * (leftx - 0.5f);
+      g.aa_ls = -dx;
+    } else {
+      la0 = la1 = (int)floorf(wr_clamp(leftx, cs0, cs1) + 0.5f);
+      g.aa_l0 = 256.0f;
+      g.aa_ls = 0.0f;
+    }
+    if (rmask) {
+      float rad = 0.5f * fabsf(rights);
+      ra0 = (int)floorf(wr_clamp(rightx - rad, cs0, cs1));
+      ra1 = (int)ceilf(wr_clamp(rightx + rad, cs0, cs1));
+      float dx = (1.0f * 256.0f) * (1.0f / sqrtf(1.0f + rights * rights));
+      g.aa_r0 = 128.0f + dx * (rightx - 0.5f);
+      g.aa_rs = -dx;
+    } else {
+      ra0 = ra1 = (int)floorf(wr_clamp(rightx, cs0, cs1) + 0.5f);
+      g.aa_r0 = 256.0f;
+      g.aa_rs = 0.0f;
+    }
+    out.aa_left_end = (short)la1;
+    out.aa_right_start = (short)ra0;
+    sx0 = la0;
+    sx1 = ra1;
+  }
+  out.x0 = (short)sx0;
+  out.x1 = (short)sx1;
+  if (sx1 <= sx0) return false;
+  float stepScale = 1.0f / (rightx - leftx);
+  if (!isfinite(stepScale)) stepScale = 0.0f;
+  pr.step_scale = stepScale;
+  pr.x0f = (float)sx0 + 0.5f - leftx;
+  pr.step_zw[0] = (pr.rz - pr.lz) * stepScale;
+  pr.step_zw[1] = (pr.rw - pr.lw) * stepScale;
+  pr.zw0[0] = pr.lz + pr.step_zw[0] * pr.x0f;
+  pr.zw0[1] = pr.lw + pr.step_zw[1] * pr.x0f;
+  return true;
+}
+// gl_FragCoord.z / .w (c = 0 / 1) of the sample `rel` pixels into the span: lane j of init_interp(zw, stepZW),
+// advanced one step_perspective() per chunk (program.h:145-148).
+WRD_NOINLINE_R float wr_persp_zw(const PerspRow& pr, int c, int rel) {
+  float v = pr.zw0[c];
+  const float st = pr.step_zw[c];
+  for (int s = 0; s < (rel & 3); s++) v = __fadd_rn(v, st);
+  return wr_repeat_add(v, __fmul_rn(st, 4.0f), rel >> 2);
+}
+// interp_perspective of the sample: lane j of init_interp(o, step) + one interp_step per chunk
+// (glsl-to-cxx read_perspective_inputs / step_perspective_inputs)
+WRD_NOINLINE_R float wr_persp_lane(float o, float step, int rel) {
+  float v = o;
+  for (int s = 0; s < (rel & 3); s++) v = __fadd_rn(v, step);
+  return wr_repeat_add(v, __fmul_rn(step, 4.0f), rel >> 2);
+}
+// left.interp / right.interp of the walk at this row (interpolants pre-multiplied by the vertices' 1/w)
+WRD_NOINLINE_R void wr_persp_edge_interp(const PerspRow& pr, int i, int y, float* li, float* ri) {
+  const PerspPoly& P = *pr.poly;
+  {
+    const float lsc = 1.0f / wr_max(P.py[pr.lv1] - P.py[pr.lv0], 1.0f / 256);
+    const float i0 = P.interp[pr.lv0][i] * P.pw[pr.lv0], i1 = P.interp[pr.lv1][i] * P.pw[pr.lv1];
+    const float sl = (i1 - i0) * lsc;
+    *li = wr_repeat_add(i0 + ((float)pr.lrow + 0.5f - P.py[pr.lv0]) * sl, sl, y - pr.lrow);
+  }
+  {
+    const float rsc = 1.0f / wr_max(P.py[pr.rv1] - P.py[pr.rv0], 1.0f / 256);
+    const float i0 = P.interp[pr.rv0][i] * P.pw[pr.rv0], i1 = P.interp[pr.rv1][i] * P.pw[pr.rv1];
+    const float sr = (i1 - i0) * rsc;
+    *ri = wr_repeat_add(i0 + ((float)pr.rrow + 0.5f - P.py[pr.rv0]) * sr, sr, y - pr.rrow);
+  }
+}
+
 template <int N>
 WRD void wr_row_interp_raw(const RasterArgs& a, const CmdCold& k, const CmdHot& c, int y, float* o, float* step,
                            float* li_out, float* ri_out) {
+  if (c.flags & CMD_PERSP) {
+    const PerspRow& pr = *a.persp;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float li, ri;
+      wr_persp_edge_interp(pr, i, y, &li, &ri);
+      if (li_out) { li_out[i] = li; ri_out[i] = ri; }
+      const float st = (ri - li) * pr.step_scale;
+      step[i] = st;
+      o[i] = li + st * pr.x0f;
+    }
+    return;
+  }
   if (c.flags & CMD_GENERAL) {
     // left.interp / right.interp of the walk at this row, then the span's start
     // value and per-pixel step (rasterize.h:1003-1017)
@@ -356,6 +500,12 @@ WRD void wr_interp_at_plain(const float* o, const float* step, int rel, float* o
 }
 template <int N>
 WRD void wr_interp_at(const RasterArgs& a, const float* o, const float* step, int rel, float* out) {
+  if (a.persp) {  // varying = w * interp_perspective, w = 1 / gl_FragCoord.w of the sample
+    const float w = 1.0f / wr_persp_zw(*a.persp, 1, rel);
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = wr_persp_lane(o[i], step[i], rel) * w;
+    return;
+  }
   int j = rel & 3;
   float kf = (float)(rel >> 2);
 #pragma unroll
@@ -420,13 +570,18 @@ WRD int wr_chunk_base(const RasterArgs& a, const float* o, const float* step, co
 }
 // lane j (0..3) of chunk k >= kb, given the lanes of chunk kb in base
 template <int N>
-WRD void wr_chunk_lane(const float (*base)[N], const float* step, int kb, int k, int j, float* out) {
+WRD void wr_chunk_lane(const RasterArgs& a, const float (*base)[N], const float* step, int kb, int k, int j, float* out) {
 #pragma unroll
   for (int i = 0; i < N; i++) {
     float is = __fmul_rn(step[i], 4.0f);
     float v = base[j][i];
     for (int s = kb; s < k; s++) v = __fadd_rn(v, is);
     out[i] = v;
+  }
+  if (a.persp) {  // the sums above are interp_perspective: the varying is w times that
+    const float w = 1.0f / wr_persp_zw(*a.persp, 1, 4 * k + j);
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = out[i] * w;
   }
 }
 
@@ -504,8 +659,11 @@ template <class S, int FMT>
 WRD void wr_shade_pixel(const RasterArgs& a, const CmdHot& c, const typename S::Row& row, int xx, int y,
                         bool use_depth, uint32_t& px, uint32_t& zb, bool& dirty, bool& zdirty) {
   if (use_depth) {
-    if (!(c.z <= zb)) return;  // GL_LEQUAL
-    if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) { zb = c.z; zdirty = true; }
+    uint32_t z = c.z;
+    // perspective: z varies per sample — packDepth() of the stepped gl_FragCoord.z (rasterize.h:345-347, 695-716)
+    if (a.persp) z = (uint32_t)(int)(wr_persp_zw(*a.persp, 0, xx - (int)c.x0) * 16777215.0f);
+    if (!((int)z <= (int)zb)) return;  // GL_LEQUAL (check_depth compares sign-extended I32 lanes)
+    if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) { zb = z; zdirty = true; }
   }
   Px src = S::source(a, c, row, xx, y, FMT == WRCU_FMT_RGBA8);
   if (a.blend != WRCU_BLEND_NONE) {
@@ -564,9 +722,15 @@ static void wr_raster(const RasterArgs& a) {
       CmdHot c = a.hot[i];
       if (y < c.y0 || y >= c.y1) continue;
       GenRow g;
+      PerspRow prow;
       RasterArgs ar = a;
       ar.gen = &g;
-      if (c.flags & CMD_GENERAL) {
+      ar.persp = nullptr;
+      if (c.flags & CMD_PERSP) {
+        const CmdHot c0 = c;
+        if (!wr_persp_row(a.row_tab, a.cold[c0.cold], c0, y, g, prow, c)) continue;
+        ar.persp = &prow;
+      } else if (c.flags & CMD_GENERAL) {
         const CmdHot c0 = c;
         if (!wr_general_row(a.cold[c0.cold], c0, y, g, c)) continue;
       }
@@ -579,7 +743,7 @@ static void wr_raster(const RasterArgs& a) {
       int xs = c.x0;
       while (xs < c.x1) {
         CmdHot cr = c;
-        if (use_depth) {
+        if (use_depth && !ar.persp) {
           while (xs < c.x1 && !(c.z <= zrow[xs])) xs++;
           int s0 = xs;
           while (xs < c.x1 && c.z <= zrow[xs]) xs++;
@@ -604,7 +768,7 @@ static void wr_raster(const RasterArgs& a) {
             if (zdirty) zrow[xx] = zb;
           }
         }
-        if (use_depth) walk.end(ar, cr, drawn);
+        if (use_depth && !ar.persp) walk.end(ar, cr, drawn);
       }
     }
   }
@@ -655,7 +819,9 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
   GenRow grow;
+  PerspRow prow;
   a.gen = &grow;
+  a.persp = nullptr;
   uint32_t px[4] = {0, 0, 0, 0};
   uint32_t zb[4] = {0, 0, 0, 0};
   bool loaded = false, dirty = false, zdirty = false;
@@ -749,7 +915,14 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       CmdHot c = sh[i];
       if (!row_ok || y < c.y0 || y >= c.y1) continue;          // warp-uniform
       const int bit0 = c.x0;  // sample of bit 0 of the command's failing-sample bitmaps (the hot rect's x0)
-      if (c.flags & CMD_GENERAL) {
+      a.persp = nullptr;
+      if (c.flags & CMD_PERSP) {
+        // perspective polygon: span, z/w and edge state of this row from its edge walk (warp-uniform)
+        const CmdHot c0 = c;
+        if (!wr_persp_row(a.row_tab, a.cold[c0.cold], c0, y, grow, prow, c)) continue;
+        if (c.x1 <= tx0 || c.x0 >= tx0 + WRCU_TILE_W) continue;
+        a.persp = &prow;
+      } else if (c.flags & CMD_GENERAL) {
         // rotated quad: this row's span comes from the edge walk (warp-uniform)
         const CmdHot c0 = c;
         if (!wr_general_row(a.cold[c0.cold], c0, y, grow, c)) continue;
@@ -926,7 +1099,10 @@ WRD bool wr_row_span_of(RasterArgs& ar, GenRow& g, const CmdHot& c0, int y, int&
   CmdHot c = c0;
   const CmdCold& k = ar.cold[c0.cold];
   ar.gen = &g;
-  if ((c0.flags & CMD_GENERAL) && !wr_general_row(k, c0, y, g, c)) return false;
+  if (c0.flags & CMD_PERSP) {
+    PerspRow pr;
+    if (!wr_persp_row(ar.row_tab, k, c0, y, g, pr, c)) return false;
+  } else if ((c0.flags & CMD_GENERAL) && !wr_general_row(k, c0, y, g, c)) return false;
   if ((c.flags & CMD_CLIP_DIST) && !wr_clip_dist_row(ar, k, c, y)) return false;
   x0 = c.x0;
   x1 = c.x1;

@@ -121,14 +121,14 @@ WRD void wr_fill_row_edge(const SetupArgs& a, int cidx, int e) {
     wr_reset_batch_info(a.info_next);                             \
     for (int i = 0; i < a.n; i++) {                               \
       name##_one(a, i);                                           \
-      if (a.cold[i].row_off >= 0)                                 \
+      if (a.cold[i].row_off >= 0 && a.cold[i].row_n > 0)          \
         for (int e = 0; e < 2 * a.cold[i].row_n; e++) wr_fill_row_edge(a, i, e); \
     }                                                             \
   }
 #else
 WRD void wr_fill_row_tables_warp(const SetupArgs& a, int idx) {
   const int lane = threadIdx.x & 31, wbase = idx - lane;
-  const bool has = idx < a.n && a.cold[idx].row_off >= 0;
+  const bool has = idx < a.n && a.cold[idx].row_off >= 0 && a.cold[idx].row_n > 0;
   unsigned m = __ballot_sync(0xFFFFFFFFu, has);
   if (!m) return;
   const int myE = has ? 2 * a.cold[idx].row_n : 0;
@@ -184,7 +184,7 @@ WRD void wr_fill_row_table_spread(const SetupArgs& a, int cidx, int lane) {
       if (idx >= a.n) return;                                                  \
       if (lane == 0) name##_one(a, idx);                                       \
       __syncwarp();                                                            \
-      if (a.cold[idx].row_off >= 0) wr_fill_row_table_spread(a, idx, lane);    \
+      if (a.cold[idx].row_off >= 0 && a.cold[idx].row_n > 0) wr_fill_row_table_spread(a, idx, lane); \
       return;                                                                  \
     }                                                                          \
     if (idx < a.n) name##_one(a, idx);                                         \
@@ -257,6 +257,233 @@ struct QuadOut {
   uint16_t col[4];
 };
 
+// ---- draw_perspective (rasterize.h:1422-1545): frustum clipping, projection, edge walk ----------------
+#ifdef WRCU_HOSTEMU
+#define WRD_NOINLINE static
+#else
+#define WRD_NOINLINE __device__ __noinline__
+#endif
+// clip_side<AXIS> (rasterize.h:1288-1420): clip the convex polygon against both planes -w <= c <= w of
+// one axis; intersection points get interpolated attributes, the AA edge mask follows the new edges.
+WRD_NOINLINE int wr_clip_side(int axis, int nump, const float (*p)[4], const float (*ip)[WR_NI], float (*op)[4],
+                              float (*oip)[WR_NI], int* edge_mask_io) {
+  enum { POSITIVE = 1, NEGATIVE = 2 };
+  int numClip = 0;
+  int edgeMask = *edge_mask_io, outEdgeMask = 0;
+  float prev[4] = {p[nump - 1][0], p[nump - 1][1], p[nump - 1][2], p[nump - 1][3]};
+  float prevI[WR_NI];
+  for (int i = 0; i < WR_NI; i++) prevI[i] = ip[nump - 1][i];
+  float prevCoord = prev[axis];
+  int prevMask = (prevCoord < -prev[3] ? NEGATIVE : 0) | (prevCoord > prev[3] ? POSITIVE : 0);
+  for (int i = 0; i < nump; i++, edgeMask >>= 1) {
+    float cur[4] = {p[i][0], p[i][1], p[i][2], p[i][3]};
+    float curI[WR_NI];
+    for (int j = 0; j < WR_NI; j++) curI[j] = ip[i][j];
+    const float curCoord = cur[axis];
+    const int curMask = (curCoord < -cur[3] ? NEGATIVE : 0) | (curCoord > cur[3] ? POSITIVE : 0);
+    if (!(curMask & prevMask)) {
+      if (prevMask) {  // an edge that was outside crosses inside
+        if (numClip >= nump + 2) return 0;
+        const float prevSide = (prevMask & NEGATIVE) && (!(prevMask & POSITIVE) ||
+                                                         prevCoord * (cur[3] - prev[3]) < prev[3] * (curCoord - prevCoord))
+                                   ? -1.0f : 1.0f;
+        const float prevDist = prevCoord - prevSide * prev[3];
+        const float curDist = curCoord - prevSide * cur[3];
+        float kk = prevDist / (prevDist - curDist);
+        float cl[4];
+        for (int j = 0; j < 4; j++) cl[j] = prev[j] + (cur[j] - prev[j]) * kk;
+        if (prevSide * cl[axis] > cl[3]) {
+          kk = nextafterf(kk, 1.0f);
+          for (int j = 0; j < 4; j++) cl[j] = prev[j] + (cur[j] - prev[j]) * kk;
+        }
+        for (int j = 0; j < 4; j++) op[numClip][j] = cl[j];
+        for (int j = 0; j < WR_NI; j++) oip[numClip][j] = prevI[j] + (curI[j] - prevI[j]) * kk;
+        numClip++;
+      }
+      if (curMask) {  // an edge that was inside crosses outside
+        if (numClip >= nump + 2) return 0;
+        const float curSide = (curMask & POSITIVE) && (!(curMask & NEGATIVE) ||
+                                                       prevCoord * (cur[3] - prev[3]) < prev[3] * (curCoord - prevCoord))
+                                  ? 1.0f : -1.0f;
+        const float prevDist = prevCoord - curSide * prev[3];
+        const float curDist = curCoord - curSide * cur[3];
+        float kk = prevDist / (prevDist - curDist);
+        float cl[4];
+        for (int j = 0; j < 4; j++) cl[j] = prev[j] + (cur[j] - prev[j]) * kk;
+        if (curSide * cl[axis] > cl[3]) {
+          kk = nextafterf(kk, 0.0f);
+          for (int j = 0; j < 4; j++) cl[j] = prev[j] + (cur[j] - prev[j]) * kk;
+        }
+        for (int j = 0; j < 4; j++) op[numClip][j] = cl[j];
+        for (int j = 0; j < WR_NI; j++) oip[numClip][j] = prevI[j] + (curI[j] - prevI[j]) * kk;
+        outEdgeMask |= (edgeMask & 1) << numClip;
+        numClip++;
+      }
+    }
+    if (!curMask) {
+      if (numClip >= nump + 2) return 0;
+      for (int j = 0; j < 4; j++) op[numClip][j] = cur[j];
+      for (int j = 0; j < WR_NI; j++) oip[numClip][j] = curI[j];
+      outEdgeMask |= (edgeMask & 1) << numClip;
+      numClip++;
+    }
+    for (int j = 0; j < 4; j++) prev[j] = cur[j];
+    for (int j = 0; j < WR_NI; j++) prevI[j] = curI[j];
+    prevCoord = curCoord;
+    prevMask = curMask;
+  }
+  *edge_mask_io = outEdgeMask;
+  return numClip;
+}
+
+// draw_perspective + the set-up part of draw_perspective_spans for one instance whose vertices differ in w.
+// Writes the polygon into the row-table pool; fills the hot rect (bounding box of the rows / columns the
+// walk can touch) and k.row_off.  Returns 1 = drawn, 0 = nothing to draw, -1 = cannot (pool exhausted).
+WRD_NOINLINE int wr_emit_persp(const SetupArgs& a, const QuadOut& q, uint32_t flags, float cx0, float cy0, float cx1,
+                               float cy1, CmdHot& h, CmdCold& k) {
+  float pc[WR_PP_MAXV][4], ic[WR_PP_MAXV][WR_NI];
+  float pt[WR_PP_MAXV][4], it[WR_PP_MAXV][WR_NI];
+  int nump = 4;
+  int aa_mask = q.aa_edge_mask;
+  for (int i = 0; i < 4; i++) {
+    pc[i][0] = q.pos[i].x; pc[i][1] = q.pos[i].y; pc[i][2] = q.pos[i].z; pc[i][3] = q.pos[i].w;
+    for (int j = 0; j < WR_NI; j++) ic[i][j] = q.interp[i][j];
+  }
+  const float scx = (float)a.tgt.vp[2] * 0.5f, scy = (float)a.tgt.vp[3] * 0.5f, scz = 1.0f * 0.5f;
+  const float ofx = (float)a.tgt.vp[0] + scx, ofy = (float)a.tgt.vp[1] + scy, ofz = 0.0f + scz;
+  bool inside = true;
+  for (int i = 0; i < 4; i++) inside = inside && (pc[i][2] > -pc[i][3] && pc[i][2] < pc[i][3]);
+  if (!inside) {
+    for (int i = 0; i < 4; i++) {
+      for (int j = 0; j < 4; j++) pt[i][j] = pc[i][j];
+      for (int j = 0; j < WR_NI; j++) it[i][j] = ic[i][j];
+    }
+    nump = wr_clip_side(2, nump, pt, it, pc, ic, &aa_mask);
+    if (nump < 3) return 0;
+    for (int i = 0; i < nump; i++) {
+      if (pc[i][3] <= 0.0f) {
+        nump = wr_clip_side(0, nump, pc, ic, pt, it, &aa_mask);
+        if (nump < 3) return 0;
+        nump = wr_clip_side(1, nump, pt, it, pc, ic, &aa_mask);
+        if (nump < 3) return 0;
+        break;
+      }
+    }
+  }
+  for (int i = 0; i < nump; i++) {
+    const float w = 1.0f / pc[i][3];
+    if (isfinite(w)) {
+      pc[i][0] = pc[i][0] * w * scx + ofx;
+      pc[i][1] = pc[i][1] * w * scy + ofy;
+      pc[i][2] = pc[i][2] * w * scz + ofz;
+      pc[i][3] = w;
+    } else {
+      pc[i][0] = pc[i][1] = pc[i][2] = pc[i][3] = 0.0f;
+    }
+  }
+  // ClipRect::overlaps
+  int sides = 0;
+  for (int i = 0; i < nump; i++) {
+    sides |= pc[i][0] < cx1 ? (pc[i][0] > cx0 ? 1 | 2 : 1) : 2;
+    sides |= pc[i][1] < cy1 ? (pc[i][1] > cy0 ? 4 | 8 : 4) : 8;
+  }
+  if (sides != 0xF) return 0;
+  if (!a.row_tab) return -1;
+  const int off = atomicAdd(&a.info->row_alloc, WR_PP_FLOATS);
+  if (off < 0 || off + WR_PP_FLOATS > a.row_cap) return -1;
+  PerspPoly& P = *(PerspPoly*)(a.row_tab + off);
+  P.nump = nump;
+  P.aa_mask = aa_mask;
+  P.clip[0] = cx0; P.clip[1] = cy0; P.clip[2] = cx1; P.clip[3] = cy1;
+  for (int i = 0; i < nump; i++) {
+    P.px[i] = pc[i][0]; P.py[i] = pc[i][1]; P.pz[i] = pc[i][2]; P.pw[i] = pc[i][3];
+    for (int j = 0; j < WR_NI; j++) P.interp[i][j] = ic[i][j];
+  }
+  // vertex selection (rasterize.h:1070-1110)
+  int top = 0;
+  for (int i = 1; i < nump; i++)
+    if (P.py[i] < P.py[top]) top = i;
+  int l0i = top;
+  for (int i = top + 1; i < nump && P.py[i] == P.py[top]; i++) l0i = i;
+  if (l0i == nump - 1)
+    for (int i = 0; i <= top && P.py[i] == P.py[top]; i++) l0i = i;
+  int r0i = top;
+  for (int i = top - 1; i >= 0 && P.py[i] == P.py[top]; i--) r0i = i;
+  if (r0i == 0)
+    for (int i = nump - 1; i >= top && P.py[i] == P.py[top]; i--) r0i = i;
+#define WR_PP_NEXT(i) ((i) + 1 < nump ? (i) + 1 : 0)
+#define WR_PP_PREV(i) ((i) - 1 >= 0 ? (i) - 1 : nump - 1)
+  int l1i = WR_PP_NEXT(l0i), r1i = WR_PP_PREV(r0i);
+  const bool aa = (flags & CMD_AA) != 0;
+  const float aaR = aa ? 0.0f : 0.5f;
+  float gy = floorf(wr_max(wr_min(P.py[l0i], cy1), cy0) + aaR) + 0.5f;
+  int row = (int)(gy - 0.5f);
+  {
+    const float perp = (P.px[l1i] - P.px[l0i]) * (P.py[r1i] - P.py[r0i]) - (P.py[l1i] - P.py[l0i]) * (P.px[r1i] - P.px[r0i]);
+    P.flipped = (P.px[l0i] > P.px[r0i] || (P.px[l0i] == P.px[r0i] && perp > 0.0f)) ? 1 : 0;
+  }
+  int lrow = row, rrow = row, n_ev = 0, first_row = row, last_row = row - 1;
+  bool overflow = false;
+#define WR_PP_EVENT()                                                                              \
+  do {                                                                                             \
+    if (n_ev < WR_PP_MAXEV) {                                                                      \
+      P.ev[n_ev].row = (short)row; P.ev[n_ev].lrow = (short)lrow; P.ev[n_ev].rrow = (short)rrow;   \
+      P.ev[n_ev].l0 = (uint8_t)l0i; P.ev[n_ev].l1 = (uint8_t)l1i;                                  \
+      P.ev[n_ev].r0 = (uint8_t)r0i; P.ev[n_ev].r1 = (uint8_t)r1i;                                  \
+      n_ev++;                                                                                      \
+    } else overflow = true;                                                                        \
+  } while (0)
+  WR_PP_EVENT();
+  float checkY = wr_min(wr_min(P.py[l1i], P.py[r1i]), cy1);
+  for (int guard = 0; guard < 40000; guard++) {
+    if (gy > checkY) {
+      if (gy > cy1) break;
+      bool changed = false, done = false;
+      if (gy > P.py[l1i]) {  // STEP_EDGE(y, l0i, l0, l1i, l1, NEXT_POINT, r1i)
+        do {
+          l0i = l1i;
+          l1i = WR_PP_NEXT(l1i);
+          if (l0i == r1i) { done = true; break; }
+        } while (gy > P.py[l1i]);
+        lrow = row;
+        changed = true;
+      }
+      if (!done && gy > P.py[r1i]) {  // STEP_EDGE(y, r0i, r0, r1i, r1, PREV_POINT, l1i)
+        do {
+          r0i = r1i;
+          r1i = WR_PP_PREV(r1i);
+          if (r0i == l1i) { done = true; break; }
+        } while (gy > P.py[r1i]);
+        rrow = row;
+        changed = true;
+      }
+      if (done) break;
+      checkY = wr_min(ceilf(wr_min(P.py[l1i], P.py[r1i]) - aaR), cy1);
+      if (changed) WR_PP_EVENT();
+    }
+    last_row = row;
+    row++;
+    gy = gy + 1.0f;
+  }
+#undef WR_PP_EVENT
+#undef WR_PP_NEXT
+#undef WR_PP_PREV
+  if (overflow) return -1;
+  if (last_row < first_row) return 0;
+  P.n_ev = n_ev;
+  float minx = P.px[0], maxx = P.px[0];
+  for (int i = 1; i < nump; i++) { minx = wr_min(minx, P.px[i]); maxx = wr_max(maxx, P.px[i]); }
+  const int gx0 = (int)floorf(wr_clamp(minx, cx0, cx1)), gx1 = (int)ceilf(wr_clamp(maxx, cx0, cx1));
+  if (gx1 <= gx0) return 0;
+  h.x0 = (short)gx0; h.x1 = (short)gx1; h.y0 = (short)first_row; h.y1 = (short)(last_row + 1);
+  // no span shaders in the perspective path: every chunk is fragment_shader->run<true>() (rasterize.h:1262-1270)
+  h.flags = (flags & ~CMD_SPAN_SOLID) | CMD_GENERAL | CMD_PERSP;
+  h.z = 0x7FFFFFFFu;  // never an occluder candidate of the depth-run prepass; the depth test uses the per-sample z
+  k.row_off = off;
+  k.row_n = -1;
+  return 1;
+}
+
 // draw_quad + the parts of draw_quad_spans that are per-instance constants for
 // a quad whose screen edges are vertical/horizontal.  Writes hot/cold; returns
 // false (and writes an empty command) when the instance draws nothing.
@@ -276,10 +503,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
   k.fail_off = -1;
   bool ok = false;
   do {
-    if (q.pos[1].w != q.pos[0].w || q.pos[2].w != q.pos[0].w || q.pos[3].w != q.pos[0].w) {
-      *unsupported = 1;  // draw_perspective
-      break;
-    }
+    const bool persp = q.pos[1].w != q.pos[0].w || q.pos[2].w != q.pos[0].w || q.pos[3].w != q.pos[0].w;
     float w = 1.0f / q.pos[0].w;
     if (!isfinite(w)) w = 0.0f;
     float px[4], py[4];
@@ -305,6 +529,13 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
       k.mask_pitch = a.clip_mask.pitch;
       k.cmx = (short)cmx;
       k.cmy = (short)cmy;
+    }
+    if (persp) {  // draw_perspective (rasterize.h:1422-1545)
+      if ((q.flags & CMD_CLIP_DIST) || a.tgt.fmt != WRCU_FMT_RGBA8) { *unsupported = 1; break; }
+      const int r = wr_emit_persp(a, q, flags, cx0, cy0, cx1, cy1, h, k);
+      if (r < 0) *unsupported = 1;
+      ok = r > 0;
+      break;
     }
     int sides = 0;
     for (int i = 0; i < 4; i++) {
@@ -481,7 +712,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
       k.row_n = q.n_interp;
     }
   }
-  if (ok && a.depth_runs &&
+  if (ok && a.depth_runs && !(h.flags & CMD_PERSP) &&
       (!(h.flags & CMD_CONST_COLOR) || (h.flags & (CMD_AA | CMD_MASK | CMD_TEXTURED | CMD_OUT_RRRR)))) {
     // the shading of this command depends on where its passing depth runs start (chunk phase, span-shader
     // body vs fragment tail, interpolant sums): wr_depth_fail_rows records them row by row

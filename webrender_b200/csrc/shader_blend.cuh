@@ -115,7 +115,7 @@ struct BlendShader {
     const CmdCold& k = a.cold[c.cold];
     int rel = x - c.x0;
     float uv[2];
-    wr_chunk_lane<2>(r.base, r.step, r.kb, rel >> 2, rel & 3, uv);
+    wr_chunk_lane<2>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, uv);
     float Cs[4];
     wr_tex_fragment(a.color0, wr_clamp(uv[0] * r.pd, k.f[0], k.f[2]), wr_clamp(uv[1] * r.pd, k.f[1], k.f[3]), Cs);
     float alpha = Cs[3];

@@ -220,12 +220,22 @@ __global__ void wr_setup_composite(SetupArgs a) {
 //   premultiplied-alpha over (alpha tiles): each slot holds the source box AND the destination box
 //     (one barrier, two bulk loads); the 128 threads blend in shared memory (blend.h:473-474), then
 //     thread 0 bulk-stores the destination box and refills the slot that has just drained.
+// The batch's copy commands, staged once per CTA into shared memory (index-preserving, so every CTA deals
+// the boxes the same way): rect, source origin, the source's tensor map and plain view.
+#define WR_COPY_MAX_CMDS 128
+struct WrCopyCmd {
+  short x0, y0;
+  int w, h;        // 0 x 0: not a copy command
+  int sx, sy;      // source origin (texels)
+  int tmap, aligned;
+  const uint8_t* sptr;
+  int spitch;
+};
 struct WrBoxIter {
-  int i = -1, b = 0, nb = 0, nbx = 1, g = 0, w = 0, h = 0;
-  bool started = false, aligned = false;
-  CmdHot c;
+  int i = -1, b = 0, nb = 0, nbx = 1, g = 0;
+  bool started = false;
   // next box of this CTA that is (full == want_full); false when the batch is exhausted
-  __device__ bool next(const RasterArgs& a, bool want_full, int& bx, int& by) {
+  __device__ bool next(const WrCopyCmd* cl, int n, bool want_full, int& bx, int& by) {
     const int G = (int)gridDim.x;
     for (;;) {
       if (started) b += G;
@@ -233,21 +243,19 @@ struct WrBoxIter {
       while (i < 0 || b >= nb) {
         if (i >= 0) g += nb;
         i++;
-        if (i >= a.n) return false;
-        c = a.hot[i];
-        w = (int)c.x1 - (int)c.x0;
-        h = (int)c.y1 - (int)c.y0;
-        if (w <= 0 || h <= 0 || !(c.flags & CMD_COPY)) { nb = 0; b = 0; continue; }
-        nbx = (w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W;
-        nb = nbx * ((h + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H);
-        aligned = (((int)c.x0 | a.cold[c.cold].i[0]) & 3) == 0;
+        if (i >= n) return false;
+        const WrCopyCmd& c = cl[i];
+        if (c.w <= 0 || c.h <= 0) { nb = 0; b = 0; continue; }
+        nbx = (c.w + WR_TMA_BOX_W - 1) / WR_TMA_BOX_W;
+        nb = nbx * ((c.h + WR_TMA_BOX_H - 1) / WR_TMA_BOX_H);
         b = ((int)blockIdx.x - g % G + G) % G;
       }
+      const WrCopyCmd& c = cl[i];
       bx = (b % nbx) * WR_TMA_BOX_W;
       by = (b / nbx) * WR_TMA_BOX_H;
       // the copy engine takes whole boxes whose source and destination start on 16-byte boundaries
       // (box origins off them fault: tools/probe/tma_probe.cu); everything else is moved by threads
-      const bool full = aligned && bx + WR_TMA_BOX_W <= w && by + WR_TMA_BOX_H <= h;
+      const bool full = c.aligned && bx + WR_TMA_BOX_W <= c.w && by + WR_TMA_BOX_H <= c.h;
       if (full == want_full) return true;
     }
   }
@@ -262,16 +270,15 @@ WRD uint32_t wr_over_px(uint32_t d, uint32_t s) {  // premultiplied-alpha over, 
 
 // ragged-edge boxes by plain accesses: `t` of `nt` threads share the rows of each box
 template <bool BLEND>
-__device__ void wr_copy_ragged(const RasterArgs& a, int t, int nt) {
+__device__ void wr_copy_ragged(const RasterArgs& a, const WrCopyCmd* cl, int n, int t, int nt) {
   WrBoxIter it;
   int bx, by;
-  while (it.next(a, false, bx, by)) {
-    const CmdCold& k = a.cold[it.c.cold];
-    const TexView& tv = wr_composite_tex(k);
-    const int bw = min(WR_TMA_BOX_W, it.w - bx), bh = min(WR_TMA_BOX_H, it.h - by);
+  while (it.next(cl, n, false, bx, by)) {
+    const WrCopyCmd& c = cl[it.i];
+    const int bw = min(WR_TMA_BOX_W, c.w - bx), bh = min(WR_TMA_BOX_H, c.h - by);
     for (int r = 0; r < bh; r++) {
-      const uint32_t* sp = (const uint32_t*)(tv.ptr + (size_t)(k.i[1] + by + r) * tv.pitch) + k.i[0] + bx;
-      uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)it.c.y0 + by + r) * a.tgt.color_pitch) + (int)it.c.x0 + bx;
+      const uint32_t* sp = (const uint32_t*)(c.sptr + (size_t)(c.sy + by + r) * c.spitch) + c.sx + bx;
+      uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)c.y0 + by + r) * a.tgt.color_pitch) + (int)c.x0 + bx;
       if ((((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
         const int nv = bw >> 2;
         for (int q = t; q < nv; q += nt) {
@@ -295,18 +302,40 @@ template <bool BLEND>
 __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a) {
   extern __shared__ __align__(128) uint8_t wr_copy_smem[];
   __shared__ __align__(8) uint64_t full[WR_TMA_STAGES];
+  __shared__ WrCopyCmd cl[WR_COPY_MAX_CMDS];
   const BatchInfo bi = *a.info;
   if (!bi.all_copy) return;  // the ordered tile kernel draws this batch
   const CUtensorMap* maps = (const CUtensorMap*)a.tmaps;
   const CUtensorMap* dst_map = maps + a.tgt.tmap_id;
+  const int n = min(a.n, WR_COPY_MAX_CMDS);
+  // Start-up, spread over the CTA's threads (one thread walking the list pays two dependent DRAM
+  // round trips per command): thread t stages command t.
+  for (int i = threadIdx.x; i < n; i += WR_TMA_THREADS) {
+    const CmdHot c = a.hot[i];
+    WrCopyCmd cc;
+    cc.x0 = c.x0; cc.y0 = c.y0;
+    cc.w = cc.h = 0;
+    cc.sx = cc.sy = cc.tmap = cc.aligned = 0; cc.sptr = nullptr; cc.spitch = 0;
+    if (c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY)) {
+      const CmdCold& k = a.cold[c.cold];
+      const TexView& tv = wr_composite_tex(k);
+      cc.w = (int)c.x1 - (int)c.x0;
+      cc.h = (int)c.y1 - (int)c.y0;
+      cc.sx = k.i[0]; cc.sy = k.i[1];
+      cc.tmap = tv.tmap_id;
+      cc.aligned = (((int)c.x0 | k.i[0]) & 3) == 0;
+      cc.sptr = tv.ptr;
+      cc.spitch = tv.pitch;
+      // a table slot that held another texture's map before (RasterArgs::tmap_acquire, see wrcu_api.cu
+      // make_tensor_map) must be re-read through the tensormap proxy
+      if (a.tmap_acquire) wr_tma_acquire_map(maps + tv.tmap_id);
+    }
+    cl[i] = cc;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < WR_TMA_STAGES; s++) wr_mbar_init(&full[s], 1);
     wr_fence_mbar_init();
-    wr_tma_acquire_map(dst_map);
-    for (int i = 0; i < a.n; i++) {
-      const CmdHot c = a.hot[i];
-      if (c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY)) wr_tma_acquire_map(maps + wr_composite_tex(a.cold[c.cold]).tmap_id);
-    }
+    if (a.tmap_acquire) wr_tma_acquire_map(dst_map);
   }
   __syncthreads();
   int bx, by;
@@ -324,44 +353,43 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
         stored++;
       };
       WrBoxIter it;
-      while (it.next(a, true, bx, by)) {
-        const CmdCold& k = a.cold[it.c.cold];
+      while (it.next(cl, n, true, bx, by)) {
+        const WrCopyCmd& c = cl[it.i];
         const int s = issued % WR_TMA_STAGES;
         if (issued >= WR_TMA_STAGES) wr_tma_wait_read<1>();  // the store that last read slot s has drained
-        ring_x[s] = (int)it.c.x0 + bx;
-        ring_y[s] = (int)it.c.y0 + by;
+        ring_x[s] = (int)c.x0 + bx;
+        ring_y[s] = (int)c.y0 + by;
         wr_mbar_expect_tx(&full[s], WR_TMA_BOX_BYTES);
-        wr_tma_load_2d(wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES, maps + wr_composite_tex(k).tmap_id, k.i[0] + bx,
-                       k.i[1] + by, &full[s]);
+        wr_tma_load_2d(wr_copy_smem + (size_t)s * WR_TMA_BOX_BYTES, maps + c.tmap, c.sx + bx, c.sy + by, &full[s]);
         issued++;
         if (issued - stored > DEPTH) store_one();
       }
       while (stored < issued) store_one();
       wr_tma_wait_all<0>();  // stores complete before the CTA's shared memory is released
     } else if (threadIdx.x >= 32) {
-      wr_copy_ragged<false>(a, threadIdx.x - 32, WR_TMA_THREADS - 32);
+      wr_copy_ragged<false>(a, cl, n, threadIdx.x - 32, WR_TMA_THREADS - 32);
     }
     return;
   }
   // ---- blended: all threads walk the CTA's full boxes in step; thread 0 also feeds the ring ----
   constexpr int ST = WR_TMA_BLEND_STAGES, DEPTH = ST - 1;
   WrBoxIter prod, cons;
-  auto issue = [&](int n) {  // thread 0: source and destination box of the producer's current item → slot n % ST
-    const CmdCold& k = a.cold[prod.c.cold];
-    uint8_t* slot = wr_copy_smem + (size_t)(n % ST) * 2 * WR_TMA_BOX_BYTES;
-    wr_mbar_expect_tx(&full[n % ST], 2 * WR_TMA_BOX_BYTES);
-    wr_tma_load_2d(slot, maps + wr_composite_tex(k).tmap_id, k.i[0] + bx, k.i[1] + by, &full[n % ST]);
-    wr_tma_load_2d(slot + WR_TMA_BOX_BYTES, dst_map, (int)prod.c.x0 + bx, (int)prod.c.y0 + by, &full[n % ST]);
+  auto issue = [&](int nn) {  // thread 0: source and destination box of the producer's current item → slot nn % ST
+    const WrCopyCmd& c = cl[prod.i];
+    uint8_t* slot = wr_copy_smem + (size_t)(nn % ST) * 2 * WR_TMA_BOX_BYTES;
+    wr_mbar_expect_tx(&full[nn % ST], 2 * WR_TMA_BOX_BYTES);
+    wr_tma_load_2d(slot, maps + c.tmap, c.sx + bx, c.sy + by, &full[nn % ST]);
+    wr_tma_load_2d(slot + WR_TMA_BOX_BYTES, dst_map, (int)c.x0 + bx, (int)c.y0 + by, &full[nn % ST]);
   };
   int nload = 0;
   bool more = true;
   if (threadIdx.x == 0)
     for (int d = 0; d < DEPTH && more; d++) {
-      more = prod.next(a, true, bx, by);
+      more = prod.next(cl, n, true, bx, by);
       if (more) issue(nload++);
     }
   int j = 0;
-  while (cons.next(a, true, bx, by)) {
+  while (cons.next(cl, n, true, bx, by)) {
     const int s = j % ST;
     wr_mbar_wait(&full[s], (uint32_t)((j / ST) & 1));
     uint4* sp = (uint4*)(wr_copy_smem + (size_t)s * 2 * WR_TMA_BOX_BYTES);
@@ -374,11 +402,11 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
     wr_fence_proxy_async();  // the blended box → visible to the copy engine
     __syncthreads();
     if (threadIdx.x == 0) {
-      wr_tma_store_2d(dst_map, (int)cons.c.x0 + bx, (int)cons.c.y0 + by, dp);
+      wr_tma_store_2d(dst_map, (int)cl[cons.i].x0 + bx, (int)cl[cons.i].y0 + by, dp);
       wr_tma_commit();
       if (more) {
         int pbx = bx, pby = by;  // (issue() reads bx/by of the producer's item)
-        more = prod.next(a, true, bx, by);
+        more = prod.next(cl, n, true, bx, by);
         if (more) {
           wr_tma_wait_read<1>();  // item j-1's store (slot (j + DEPTH) % ST) has finished reading shared memory
           issue(nload++);
@@ -390,7 +418,7 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
   }
   if (threadIdx.x == 0) wr_tma_wait_all<0>();
   __syncthreads();
-  wr_copy_ragged<true>(a, threadIdx.x, WR_TMA_THREADS);
+  wr_copy_ragged<true>(a, cl, n, threadIdx.x, WR_TMA_THREADS);
 }
 #endif
 

@@ -75,7 +75,7 @@ struct FastLinearShader {
     const CmdCold& k = a.cold[c.cold];
     int rel = x - c.x0;
     float t[1];
-    wr_chunk_lane<1>(r.base, r.step, r.kb, rel >> 2, rel & 3, t);
+    wr_chunk_lane<1>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, t);
     Px o;
     o.r = wr_round_pixel((k.g[4] - k.g[0]) * t[0] + k.g[0], 255.0f) & 0xFFFF;
     o.g = wr_round_pixel((k.g[5] - k.g[1]) * t[0] + k.g[1], 255.0f) & 0xFFFF;
@@ -101,7 +101,7 @@ struct ConicShader {
     const CmdCold& k = a.cold[c.cold];
     int rel = x - c.x0;
     float p[2];
-    wr_chunk_lane<2>(r.base, r.step, r.kb, rel >> 2, rel & 3, p);
+    wr_chunk_lane<2>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, p);
     float cx = p[0] - k.f[0], cy = p[1] - k.f[1];
 #ifdef WRCU_HOSTEMU
     float at = atan2f(cy, cx);
@@ -348,7 +348,7 @@ struct QuadConicShader {
     const CmdCold& k = a.cold[c.cold];
     int rel = x - c.x0;
     float p[2];
-    wr_chunk_lane<2>(r.base, r.step, r.kb, rel >> 2, rel & 3, p);
+    wr_chunk_lane<2>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, p);
     float angle = wr_approx_atan2(p[1], p[0]) + k.f[4];
     float offset = wr_fract(angle / (2.0f * 3.141592653589793f)) * k.f[5] - k.f[2];
     return wr_quad_grad_fragment(a, c, k, offset);

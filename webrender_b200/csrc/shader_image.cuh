@@ -19,7 +19,8 @@ struct ImageShader {
     // mix(gl_FragCoord.w, 1.0, v_perspective.x) = (1 - w) * p + w
     r.pd = (1.0f - k.f[7]) * k.f[6] + k.f[7];
     int len = c.x1 - c.x0;
-    int body_len = (rgba && len >= 4 && k.g[7] != 0.0f) ? (len & ~3) : 0;
+    // (perspective rows have no span body: every chunk is the fragment shader, rasterize.h:1262-1270)
+    int body_len = (rgba && len >= 4 && k.g[7] != 0.0f && !a.persp) ? (len & ~3) : 0;
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
@@ -40,7 +41,12 @@ struct ImageShader {
     }
     float uv[2];
     wr_interp_at<2>(a, r.o, r.step, rel, uv);
-    float ru = uv[0] * r.pd + k.f[4], rv = uv[1] * r.pd + k.f[5];
+    float pd = r.pd;
+    if (a.persp) {  // gl_FragCoord.w varies per sample
+      const float fw = wr_persp_zw(*a.persp, 1, rel);
+      pd = (1.0f - fw) * k.f[6] + fw;
+    }
+    float ru = uv[0] * pd + k.f[4], rv = uv[1] * pd + k.f[5];
     float texel[4], col[4];
     wr_tex_fragment(t, wr_clamp(ru, k.f[0], k.f[2]), wr_clamp(rv, k.f[1], k.f[3]), texel);
     if (k.g[6] != 0.0f) {

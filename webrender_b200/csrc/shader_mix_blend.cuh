@@ -88,7 +88,7 @@ struct MixBlendShader {
     const CmdCold& k = a.cold[c.cold];
     int rel = x - c.x0;
     float L[4];
-    wr_chunk_lane<4>(r.base, r.step, r.kb, rel >> 2, rel & 3, L);
+    wr_chunk_lane<4>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, L);
     float Cb[4], Cs[4], t[3], result[4];
     wr_tex_fragment(a.color0, wr_clamp(L[2], k.f[4], k.f[6]), wr_clamp(L[3], k.f[5], k.f[7]), Cb);
     wr_tex_fragment(a.color1, wr_clamp(L[0] * r.pd, k.f[0], k.f[2]), wr_clamp(L[1] * r.pd, k.f[1], k.f[3]), Cs);

@@ -19,13 +19,13 @@ struct QuadMaskShader {
     wr_row_interp<4>(a, k, c, y, o, r.step);
     r.kb = wr_chunk_base<4>(a, o, r.step, c, tx0, r.base);
   }
-  WRD_MEMBER Px source(const RasterArgs&, const CmdHot& c, const Row& r, int x, int, bool) {
+  WRD_MEMBER Px source(const RasterArgs& a, const CmdHot& c, const Row& r, int x, int, bool) {
     const float* g = r.g;
     int rel = x - c.x0, kc = rel >> 2, j = rel & 3;
     float L0[4], L1[4], Lj[4];
-    wr_chunk_lane<4>(r.base, r.step, r.kb, kc, 0, L0);
-    wr_chunk_lane<4>(r.base, r.step, r.kb, kc, 1, L1);
-    wr_chunk_lane<4>(r.base, r.step, r.kb, kc, j, Lj);
+    wr_chunk_lane<4>(a, r.base, r.step, r.kb, kc, 0, L0);
+    wr_chunk_lane<4>(a, r.base, r.step, r.kb, kc, 1, L1);
+    wr_chunk_lane<4>(a, r.base, r.step, r.kb, kc, j, Lj);
     float p0x = L0[0] / L0[3], p0y = L0[1] / L0[3];
     float p1x = L1[0] / L1[3], p1y = L1[1] / L1[3];
     float aa_range = 1.0f / (fabsf(p1x - p0x) + fabsf(p1y - p0y));

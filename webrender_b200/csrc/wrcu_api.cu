@@ -216,13 +216,22 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
     cudaDriverEntryPointQueryResult qr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
         qr == cudaDriverEntryPointSuccess && fn &&
-        cudaMalloc(&c->tmaps_dev, (size_t)wrcu_ctx::MAX_TEX * sizeof(CUtensorMap)) == cudaSuccess)
+        cudaMalloc(&c->tmaps_dev, (size_t)wrcu_ctx::TMAP_SLOTS * sizeof(CUtensorMap)) == cudaSuccess)
       c->tmap_encode = fn;
     else
       c->tmaps_dev = nullptr;
     cudaGetLastError();
   }
 #endif
+  {
+    // shallow solid batches: up to flat_max layers go to the streaming kernel, deeper ones to the tile kernel
+    // (crossover measured with tools/gpu_g.sh; WRCU_FLAT_MAX overrides it for that measurement)
+    const char* e = getenv("WRCU_FLAT_MAX");
+    c->flat_max = e ? atoi(e) : 2;
+#ifndef WRCU_HOSTEMU
+    if (c->flat_max > FLAT_MAX) c->flat_max = FLAT_MAX;
+#endif
+  }
   c->row_cap = 16 << 20;  // 64 MiB of row tables per batch; commands beyond it fall back to walking
   if (cudaMalloc((void**)&c->row_tab, (size_t)c->row_cap * sizeof(float)) != cudaSuccess) {
     c->row_tab = nullptr;
@@ -232,6 +241,9 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   return WRCU_OK;
 }
 
+#ifndef WRCU_HOSTEMU
+static void sig_forget(const uint32_t* base, int count);
+#endif
 extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -246,6 +258,9 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
 #ifndef WRCU_HOSTEMU
   for (auto& pf : c->peers)
     if (pf.ipc) cudaIpcCloseMemHandle(pf.ptr);
+#endif
+#ifndef WRCU_HOSTEMU
+  if (c->flags) sig_forget(c->flags, c->n_flags);
 #endif
   if (c->flags) cudaFree(c->flags);
   for (int i = 0; i < 2; i++) {
@@ -389,10 +404,15 @@ extern "C" int wrcu_texture_create(wrcu_ctx* c, int format, int w, int h, wrcu_t
 #ifndef WRCU_HOSTEMU
 // One 2-D tensor map per RGBA8 texture: u32 elements, box WR_TMA_BOX_W x WR_TMA_BOX_H, no swizzle
 // (the boxes are only ever moved, never read by threads).  The 128-byte record is built on the host
-// and copied into slot `id` of the context's device table; kernels address it as tmaps + id.
+// and copied into the next FRESH slot of the context's device table (TexView::tmap_id = the slot);
+// kernels address it as tmaps + slot.  A slot is never rewritten until the table wraps (65535 texture
+// creations), so no SM can hold a stale copy of a descriptor and the copy kernels need no
+// tensormap-proxy acquire — one per source texture and CTA had made that kernel's start-up its whole
+// cost.  After a wrap the kernels are told to acquire (RasterArgs::tmap_acquire).
 static void make_tensor_map(wrcu_ctx* c, int id) {
   WrTexture& t = c->tex[id];
   t.has_tmap = false;
+  t.tmap_slot = 0;
   if (!c->tmap_encode || !c->tmaps_dev || t.fmt != WRCU_FMT_RGBA8 || t.w < WR_TMA_BOX_W || t.h < WR_TMA_BOX_H) return;
   CUtensorMap m;
   const cuuint64_t dims[2] = {(cuuint64_t)t.w, (cuuint64_t)t.h};
@@ -406,9 +426,16 @@ static void make_tensor_map(wrcu_ctx* c, int id) {
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return;
-  if (cudaMemcpyAsync((uint8_t*)c->tmaps_dev + (size_t)id * sizeof(CUtensorMap), &m, sizeof m, cudaMemcpyHostToDevice,
+  int slot = c->tmap_next++;
+  if (slot >= wrcu_ctx::TMAP_SLOTS) {
+    c->tmap_wrapped = true;
+    slot = 1;
+    c->tmap_next = 2;
+  }
+  if (cudaMemcpyAsync((uint8_t*)c->tmaps_dev + (size_t)slot * sizeof(CUtensorMap), &m, sizeof m, cudaMemcpyHostToDevice,
                       c->stream) != cudaSuccess)
     return;
+  t.tmap_slot = slot;
   t.has_tmap = true;
 }
 #else
@@ -416,6 +443,7 @@ static void make_tensor_map(wrcu_ctx* c, int id) {
 static void make_tensor_map(wrcu_ctx* c, int id) {
   WrTexture& t = c->tex[id];
   t.has_tmap = t.fmt == WRCU_FMT_RGBA8 && t.w >= 256 && t.h >= 16;
+  t.tmap_slot = t.has_tmap ? id : 0;
 }
 #endif
 
@@ -847,6 +875,27 @@ __global__ void wr_flag_wait(const uint32_t* flag, uint32_t value, int* timeout_
   }
 }
 #endif
+// In-process peers (several contexts driven by one process): a signal is also recorded as a CUDA event, and
+// a wait that is queued after it takes the event instead of the polling kernel.  Two streams of one process
+// may share a hardware work queue, and a polling kernel at the head of that queue would keep the very
+// signal it waits for from starting (until its 2 s timeout); events are ordered by the driver.  Contexts in
+// different processes (one rank per GPU) only ever wait on flags written from another device.
+#ifndef WRCU_HOSTEMU
+#include <map>
+#include <mutex>
+struct WrSigRec { cudaEvent_t ev; uint32_t value; int device; };
+static std::mutex g_sig_mu;
+static std::map<uintptr_t, WrSigRec> g_sig;
+static void sig_forget(const uint32_t* base, int count) {
+  std::lock_guard<std::mutex> lk(g_sig_mu);
+  for (int i = 0; i < count; i++) {
+    auto it = g_sig.find((uintptr_t)(base + i));
+    if (it == g_sig.end()) continue;
+    cudaEventDestroy(it->second.ev);
+    g_sig.erase(it);
+  }
+}
+#endif
 // make `dev` reachable from this context's device
 static int enable_peer(wrcu_ctx* c, int dev) {
 #ifndef WRCU_HOSTEMU
@@ -971,6 +1020,18 @@ extern "C" int wrcu_peer_signal(wrcu_ctx* c, int peer_id, int slot, uint32_t val
   wr_flag_signal<<<1, 1, 0, c->stream>>>(c->peers[peer_id].ptr + slot, value);
   c->stats.kernel_launches++;
   WRCU_CUDA(c, cudaGetLastError());
+  if (!c->peers[peer_id].ipc) {
+    std::lock_guard<std::mutex> lk(g_sig_mu);
+    WrSigRec& r = g_sig[(uintptr_t)(c->peers[peer_id].ptr + slot)];
+    if (!r.ev) {
+      WRCU_CUDA(c, cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+      r.device = c->device;
+    }
+    if (r.device == c->device) {  // (an event is recorded on streams of the device it was created on)
+      WRCU_CUDA(c, cudaEventRecord(r.ev, c->stream));
+      r.value = value;
+    }
+  }
 #else
   c->peers[peer_id].ptr[slot] = value;
 #endif
@@ -981,6 +1042,14 @@ extern "C" int wrcu_peer_wait(wrcu_ctx* c, int slot, uint32_t value) {
   if (!c->flags || slot < 0 || slot >= c->n_flags) return wrcu_fail(c, WRCU_ERR_INVALID, "peer_wait: bad arguments");
   cudaSetDevice(c->device);
 #ifndef WRCU_HOSTEMU
+  {
+    std::lock_guard<std::mutex> lk(g_sig_mu);
+    auto it = g_sig.find((uintptr_t)(c->flags + slot));
+    if (it != g_sig.end() && it->second.ev && (int32_t)(it->second.value - value) >= 0) {
+      WRCU_CUDA(c, cudaStreamWaitEvent(c->stream, it->second.ev, 0));
+      return WRCU_OK;
+    }
+  }
   wr_flag_wait<<<1, 1, 0, c->stream>>>(c->flags + slot, value, c->dev_err);
   c->stats.kernel_launches++;
   WRCU_CUDA(c, cudaGetLastError());
@@ -1150,7 +1219,7 @@ static TexView tex_view(wrcu_ctx* c, wrcu_tex id) {
   v.pitch = (int)t->pitch;
   v.filter = t->w >= 2 ? t->filter : WRCU_NEAREST;  // init_filter, gl.cc:870-877
   v.fmt = t->fmt;
-  v.tmap_id = t->has_tmap ? (int)id : 0;
+  v.tmap_id = t->has_tmap ? t->tmap_slot : 0;
   return v;
 }
 
@@ -1183,6 +1252,7 @@ extern "C" int wrcu_draw_composite_tiles(wrcu_ctx* c, uint32_t features, const w
   return draw_batch_impl(c, WRCU_KIND_COMPOSITE, features, st, instances, stride, n, textures);
 }
 
+#define WR_COPY_MAX_CMDS_HOST 128  // = WR_COPY_MAX_CMDS (shader_composite.cuh): the copy kernel's staged command list
 static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_draw_state* st,
                            const void* instances, size_t stride, int n, const wrcu_tex* textures) {
   if (!st || !instances || n < 0 || stride == 0)
@@ -1229,7 +1299,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   memcpy(T.proj, c->proj, sizeof T.proj);
   memcpy(T.vp, c->vp, sizeof T.vp);
   T.cx0 = 0; T.cy0 = 0; T.cx1 = tgt->w; T.cy1 = tgt->h;
-  T.tmap_id = tgt->has_tmap ? (int)c->color_tex : 0;
+  T.tmap_id = tgt->has_tmap ? tgt->tmap_slot : 0;
   if (st->scissor_enabled) {
     T.cx0 = max(T.cx0, st->scissor[0]);
     T.cy0 = max(T.cy0, st->scissor[1]);
@@ -1290,7 +1360,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     // The copy kernel moves boxes of different instances concurrently: a batch whose instances overlap keeps
     // the ordered tile kernel.  Picture-cache tiles never overlap; checked here on the host copies of the
     // CompositeInstance rects (device rect ∩ clip rect, rounded outwards), n is a tile list's length.
-    if (n > 256 || stride < 32) sa.copy_ok = 0;
+    if (n > WR_COPY_MAX_CMDS_HOST || stride < 32) sa.copy_ok = 0;
     else {
       std::vector<float> bb((size_t)n * 4);
       for (int i = 0; i < n; i++) {
@@ -1504,6 +1574,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   ra.bin_tiles_x = sa.bin_tiles_x;
   ra.n_gpu_cache = c->tables.n_gpu_cache;
   ra.tmaps = c->tmaps_dev;
+  ra.tmap_acquire = c->tmap_wrapped ? 1 : 0;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
   if (grid.x == 0 || grid.y == 0) return WRCU_OK;
   // Device-side dispatch: the setup kernel decides whether the whole batch is
@@ -1534,7 +1605,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
         nb = 8;
       c->fast_ctas_per_sm = nb;
     }
-    if (n <= FLAT_MAX) {
+    if (n <= c->flat_max) {
       // shallow batch: the streaming variant (8 pixels per thread over the bounding box; grid sized for the
       // whole target, threads beyond the box leave at once)
       const long long groups = ((long long)(T.w + 3) / 4) * ((T.h + 1) / 2);

@@ -44,6 +44,7 @@ struct WrTexture {
   bool imported = false;      // aliases another context's memory (wrcu_texture_import): never freed here
   bool ipc_mapped = false;    //   ... through cudaIpcOpenMemHandle (another process)
   bool has_tmap = false;      // a 2-D TMA tensor map of this texture sits in the context's device table
+  int tmap_slot = 0;          //   ... in this slot
   uint64_t pending_read = 0;  // fence of an in-flight async readback of this texture
 };
 
@@ -138,6 +139,7 @@ struct wrcu_ctx {
   std::vector<std::pair<uint8_t*, size_t>> host_allocs;  // wrcu_host_alloc blocks (staged without a copy)
   float* row_tab = nullptr;      // row-table pool of the current batch (CmdCold::row_off)
   int row_cap = 0;               // floats
+  int flat_max = 2;          // solid batches of <= flat_max layers take the streaming kernel
   int fast_ctas_per_sm = 0;  // resident CTAs/SM of the solid-premult kernel (occupancy API)
   // TMA: one 128-byte CUtensorMap per RGBA8 texture (box 256x16 px), built on the host at texture
   // creation (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint) and kept in a device table
@@ -149,6 +151,9 @@ struct wrcu_ctx {
   uint32_t* fail_pool = nullptr;  // depth-run bitmaps of the current batch (CmdCold::fail_off)
   int fail_cap = 0;               // words
   void* tmaps_dev = nullptr;
+  static const int TMAP_SLOTS = 65536;  // 8 MiB of 128-byte records; slot 0 = none
+  int tmap_next = 1;
+  bool tmap_wrapped = false;     // slots are being reused: kernels acquire the maps they use
   void* tmap_encode = nullptr;
   bool copy_attr_set = false;
 };
