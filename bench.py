@@ -209,6 +209,7 @@ def other_workloads():
         "box_shadow": lambda: scenes.box_shadow_frame(width=1024, height=1024, n_clips=1, full_size=(1024, 1024), seed=7),
         "clip_rects": lambda: scenes.clip_mask_frame(),
         "composite": lambda: scenes.composite_frame(W, H, 1024, 512, seed=4),
+        "page": lambda: scenes.page_frame(W, H, 1024, 512, seed=1),
         "video_nv12": lambda: scenes.video_frame(W, H, 1920, 1080, "nv12"),
         "video_planar": lambda: scenes.video_frame(W, H, 1920, 1080, "planar"),
         "images": lambda: scenes.image_frame(width=W, height=H, seed=1),

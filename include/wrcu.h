@@ -89,8 +89,10 @@ typedef enum wrcu_kind {
   WRCU_KIND_BORDER_SEGMENT = 22,       /* cs_border_segment                */
   WRCU_KIND_QUAD_RADIAL_GRADIENT = 23, /* ps_quad_radial_gradient          */
   WRCU_KIND_QUAD_CONIC_GRADIENT = 24,  /* ps_quad_conic_gradient           */
-  WRCU_KIND_BRUSH_YUV_IMAGE = 25       /* brush_yuv_image [ALPHA_PASS] YUV: BrushBatchKind::YuvImage
+  WRCU_KIND_BRUSH_YUV_IMAGE = 25,      /* brush_yuv_image [ALPHA_PASS] YUV: BrushBatchKind::YuvImage
                                           (batch.rs:60-86), planes in color[0..2]  */
+  WRCU_KIND_SPLIT_COMPOSITE = 26       /* ps_split_composite: BatchKind::SplitComposite (batch.rs:74), instances =
+                                          SplitCompositeInstance (gpu_types.rs:531-552), surface in color[0] */
 } wrcu_kind;
 
 /* Shader feature bits (webrender_build/src/shader_features.rs:64-247). */

@@ -112,7 +112,7 @@ _BORDER = [("aTaskOrigin", 2, "f"), ("aRect", 4, "f"), ("aColor0", 4, "f"), ("aC
 ATTRIBS = {
     abi.KIND_QUAD_TEXTURED: _PRIM, abi.KIND_QUAD_RADIAL_GRADIENT: _PRIM, abi.KIND_QUAD_CONIC_GRADIENT: _PRIM, abi.KIND_BRUSH_SOLID: _PRIM, abi.KIND_BRUSH_IMAGE: _PRIM,
     abi.KIND_BRUSH_LINEAR_GRADIENT: _PRIM, abi.KIND_BRUSH_BLEND: _PRIM, abi.KIND_BRUSH_MIX_BLEND: _PRIM,
-    abi.KIND_BRUSH_OPACITY: _PRIM, abi.KIND_TEXT_RUN: _PRIM, abi.KIND_BRUSH_YUV_IMAGE: _PRIM,
+    abi.KIND_BRUSH_OPACITY: _PRIM, abi.KIND_TEXT_RUN: _PRIM, abi.KIND_BRUSH_YUV_IMAGE: _PRIM, abi.KIND_SPLIT_COMPOSITE: _PRIM,
     abi.KIND_QUAD_MASK: [("aData", 4, "i"), ("aClipData", 4, "i")],
     abi.KIND_CLIP_RECTANGLE: _CLIP_COMMON + [
         ("aClipLocalPos", 2, "f"), ("aClipLocalRect", 4, "f"), ("aClipMode", 1, "f"),

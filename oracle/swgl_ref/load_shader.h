@@ -26,6 +26,7 @@
 #include "cs_gradients.h"
 #include "cs_border_line.h"
 #include "ps_quad_gradients.h"
+#include "ps_split_composite.h"
 
 ProgramLoader load_shader(const char* name) {
   if (!strcmp(name, "ps_quad_textured")) return ps_quad_textured_program::loader;
@@ -79,5 +80,6 @@ ProgramLoader load_shader(const char* name) {
     return ps_text_run_ALPHA_PASS_GLYPH_TRANSFORM_TEXTURE_2D_program::loader;
   if (!strcmp(name, "ps_text_run ALPHA_PASS,DUAL_SOURCE_BLENDING,GLYPH_TRANSFORM,TEXTURE_2D"))
     return ps_text_run_ALPHA_PASS_DUAL_SOURCE_BLENDING_GLYPH_TRANSFORM_TEXTURE_2D_program::loader;
+  if (!strcmp(name, "ps_split_composite")) return ps_split_composite_program::loader;
   return nullptr;
 }

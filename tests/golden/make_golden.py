@@ -72,6 +72,14 @@ CASES = [
     ("brush_yuv_image_nv12_alpha", "yuv_image_frame", dict(fmt="nv12", color_space=2, seed=1)),
     ("brush_yuv_image_planar_opaque", "yuv_image_frame", dict(fmt="planar", color_space=0, seed=2, alpha_pass=False)),
     ("brush_yuv_image_interleaved_rotated", "yuv_image_frame", dict(fmt="interleaved", color_space=3, seed=3, rotate=17.0)),
+    # perspective (draw_perspective) and plane-split polygons: checked against the reference build directly; the
+    # plain-C port (oracle/wr_oracle.c) does not restate this path ("port": False → CPU tier skips it)
+    ("perspective_brush_solid_aa", "perspective_frame", dict(kind="solid", d=800.0, ry=35.0, rx=10.0, seed=4, force_aa=True,
+                                                              n_opaque=6, n_alpha=12), False),
+    ("perspective_brush_image_clipped", "perspective_frame", dict(kind="image", d=220.0, ry=60.0, rx=-30.0, seed=2), False),
+    ("split_composite", "split_composite_frame", dict(seed=1), False),
+    ("split_composite_near_plane", "split_composite_frame", dict(seed=2, d=220.0, ry=65.0, rx=20.0, perspective_interpolate=1),
+     False),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),
@@ -84,15 +92,17 @@ def main():
     from webrender_b200 import scenes
     index = {}
     regenerate_all = "--all" in sys.argv   # default: only cases whose fixture is missing
-    for name, builder, kwargs in CASES:
+    for case in CASES:
+        name, builder, kwargs = case[:3]
+        port = case[3] if len(case) > 3 else True   # False: the plain-C port does not restate this path
         path = os.path.join(HERE, name + ".npz")
         if os.path.exists(path) and not regenerate_all:
-            index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(np.load(path).files)}
+            index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(np.load(path).files), "port": port}
             continue
         frame = getattr(scenes, builder)(**kwargs)
         out = render(SwglDevice, frame)
         np.savez_compressed(path, **out)
-        index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(out)}
+        index[name] = {"builder": builder, "kwargs": kwargs, "targets": sorted(out), "port": port}
         print(name, {k: v.shape for k, v in out.items()})
     json.dump(index, open(os.path.join(HERE, "index.json"), "w"), indent=1, sort_keys=True)
 

@@ -518,3 +518,55 @@ def test_binned_batch_two_list_passes():
     """9600 glyphs in one batch: the per-tile command list is built in two passes of 8192 commands."""
     f = scenes.text_frame(seed=4, width=1920, height=1080, n_runs=120, glyphs_per_run=80, atlas_size=1024)
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
+# ---- perspective quads / plane-split polygons: against the reference build itself -------------------------
+# (oracle/_ref travels with the repo; the plain-C port does not restate draw_perspective)
+PERSP_CAMERAS = [(800.0, 35.0, 0.0), (800.0, -20.0, 15.0), (220.0, 60.0, -30.0), (220.0, 80.0, 40.0), (150.0, -70.0, 55.0)]
+
+
+def _swgl():
+    from oracle.backends import SwglDevice, have_swgl
+    if not have_swgl():
+        pytest.skip("oracle/_ref (the reference build) not present")
+    return SwglDevice
+
+
+@pytest.mark.parametrize("cam", PERSP_CAMERAS)
+@pytest.mark.parametrize("kind", ["solid", "solid_aa", "image", "image_nearest"])
+def test_perspective_brushes(kind, cam):
+    """draw_perspective (rasterize.h:1422-1545): near-plane clipping, polygon edge walk, per-sample z and
+    1/w-corrected varyings — byte-exact against SWGL."""
+    d, ry, rx = cam
+    if kind.startswith("image"):
+        f = scenes.perspective_frame("image", d=d, ry=ry, rx=rx, seed=2,
+                                     filter=abi.NEAREST if kind == "image_nearest" else abi.LINEAR)
+    else:
+        f = scenes.perspective_frame("solid", d=d, ry=ry, rx=rx, seed=4 if kind == "solid_aa" else 3,
+                                     force_aa=kind == "solid_aa", n_opaque=6, n_alpha=12)
+    assert_same(render(CudaDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
+
+
+def test_perspective_full_size():
+    """4K: long polygon edges (rows up to 2160) and spans up to 3840 samples of stepped z/w."""
+    f = scenes.perspective_frame("solid", width=3840, height=2160, d=3000.0, ry=50.0, rx=-20.0, seed=5, n_opaque=4,
+                                 n_alpha=10, with_masks=False)
+    assert_same(render(CudaDevice, f, ["target"]), render(_swgl(), f, ["target"]))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(d=220.0, ry=65.0, rx=20.0), dict(perspective_interpolate=1, seed=3),
+                                dict(d=1e9, ry=0.0, rx=0.0, seed=4), dict(seed=5, filter=abi.NEAREST),
+                                dict(seed=6, width=1920, height=1080, n_polys=40, d=900.0)])
+def test_split_composite(kw):
+    f = scenes.split_composite_frame(**kw)
+    assert_same(render(CudaDevice, f, ["target"]), render(_swgl(), f, ["target"]), str(kw))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_page_of_many_small_batches(seed):
+    """Three passes, ~40 draws of a few instances each (clip masks, picture-cache tiles with seven batches each,
+    the tile list): what bench.py --workload page times at 4K."""
+    f = scenes.page_frame(width=2048, height=1024, seed=seed)
+    names = ["mask", "tile0", "tile1", "tile2", "tile3", "fb"]
+    assert_same(render(CudaDevice, f, names), render(OracleDevice, f, names))
+    assert_same(render(CudaDevice, f, ["fb"], tile_lists=True), render(OracleDevice, f, ["fb"]))

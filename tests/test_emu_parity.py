@@ -394,3 +394,37 @@ def test_sw_compositor_blit_math_against_swgl():
         got = e.read_pixels(ed, 0, 0, 640, 360, 4)
         e.close()
         assert (got == ref).all(), name
+
+
+# ---- perspective quads / plane-split polygons: against the reference build itself -------------------------
+PERSP_CAMERAS = [(800.0, 35.0, 0.0), (800.0, -20.0, 15.0), (220.0, 60.0, -30.0), (220.0, 80.0, 40.0)]
+
+
+def _swgl():
+    from oracle.backends import SwglDevice, have_swgl
+    if not have_swgl():
+        pytest.skip("oracle/_ref (the reference build) not present")
+    return SwglDevice
+
+
+@pytest.mark.parametrize("cam", PERSP_CAMERAS)
+@pytest.mark.parametrize("kind", ["solid", "solid_aa", "image"])
+def test_perspective_brushes(kind, cam):
+    """draw_perspective (rasterize.h:1422-1545): w differs between the vertices — near-plane clipping (the d=220
+    cameras put part of the page behind the eye), the polygon edge walk, per-sample z and 1/w-corrected varyings."""
+    d, ry, rx = cam
+    kw = dict(seed=3, n_opaque=6, n_alpha=12)
+    if kind == "solid_aa":
+        kw.update(seed=4, force_aa=True)
+    f = scenes.perspective_frame("image" if kind == "image" else "solid", d=d, ry=ry, rx=rx,
+                                 **({"seed": 2} if kind == "image" else kw))
+    assert_same(render(EmuDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(d=220.0, ry=65.0, rx=20.0), dict(perspective_interpolate=1, seed=3),
+                                dict(d=1e9, ry=0.0, rx=0.0, seed=4), dict(seed=5, filter=abi.NEAREST)])
+def test_split_composite(kw):
+    """ps_split_composite: plane-split polygons (arbitrary convex quads) of a preserve-3d picture, with and
+    without perspective (d=1e9: the 2-D edge walk and the span shader), clip masks, depth test."""
+    f = scenes.split_composite_frame(**kw)
+    assert_same(render(EmuDevice, f, ["target"]), render(_swgl(), f, ["target"]), str(kw))

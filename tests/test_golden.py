@@ -50,9 +50,17 @@ def test_config_a_against_reference_png():
     assert d.max() <= 4 and int((d > 0).sum()) <= 27, (int(d.max()), int((d > 0).sum()))
 
 
-@pytest.mark.parametrize("name", sorted(INDEX))
+@pytest.mark.parametrize("name", sorted(n for n in INDEX if INDEX[n].get("port", True)))
 def test_oracle_matches_reference_golden(name):
     _check(OracleDevice, name)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in INDEX if not INDEX[n].get("port", True)))
+def test_emulated_kernels_match_reference_golden(name):
+    """Paths the plain-C port does not restate (perspective quads, plane-split polygons): the device code itself,
+    compiled for the host (tests/emu.py), against the reference's bytes."""
+    from emu import EmuDevice
+    _check(EmuDevice, name)
 
 
 @pytest.mark.gpu

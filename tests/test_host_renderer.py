@@ -42,6 +42,7 @@ CASES = [
     ("text", lambda: scenes.text_frame(seed=2, width=480, height=270, n_runs=8, glyphs_per_run=20), ["target"]),
     ("gradients", lambda: scenes.gradient_frame(seed=1, blend=abi.BLEND_PREMULTIPLIED_ALPHA), ["target"]),
     ("composite", lambda: scenes.composite_frame(seed=1), ["fb"]),
+    ("page", lambda: scenes.page_frame(width=2048, height=1024, seed=2), ["mask", "tile0", "tile3", "fb"]),
     ("composite_yuv_planar", lambda: scenes.yuv_composite_frame("planar", 2, seed=1), ["fb"]),
     ("composite_yuv_nv12", lambda: scenes.yuv_composite_frame("nv12", 0, seed=2, opaque=False), ["fb"]),
     ("brush_yuv_image", lambda: scenes.yuv_image_frame("nv12", 2, seed=1), ["target"]),

@@ -344,3 +344,11 @@ def test_text_run_glyph_transform(xf, atlas, seed):
                           color_modes=(0,) if atlas == "r8" else (0, 1, 2, 3), fractional=True,
                           glyph_transform=GLYPH_TRANSFORMS[xf], clip_runs=True)
     assert_same(render(SwglDevice, f, ["target"]), render(OracleDevice, f, ["target"]), xf)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_page_of_many_small_batches(seed):
+    """The multi-pass page scene (clip-mask pass, picture-cache tiles, tile list) through both CPU checkers."""
+    f = scenes.page_frame(width=2048, height=1024, seed=seed)
+    names = ["mask", "tile0", "tile3", "fb"]
+    assert_same(render(SwglDevice, f, names), render(OracleDevice, f, names))

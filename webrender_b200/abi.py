@@ -23,7 +23,7 @@ NEAREST, LINEAR = 0, 1
  KIND_COMPOSITE, KIND_CLEAR, KIND_BLUR, KIND_SCALE,
  KIND_FAST_LINEAR_GRADIENT, KIND_LINEAR_GRADIENT, KIND_RADIAL_GRADIENT, KIND_CONIC_GRADIENT,
  KIND_LINE_DECORATION, KIND_BORDER_SOLID, KIND_BORDER_SEGMENT,
- KIND_QUAD_RADIAL_GRADIENT, KIND_QUAD_CONIC_GRADIENT, KIND_BRUSH_YUV_IMAGE) = range(1, 26)
+ KIND_QUAD_RADIAL_GRADIENT, KIND_QUAD_CONIC_GRADIENT, KIND_BRUSH_YUV_IMAGE, KIND_SPLIT_COMPOSITE) = range(1, 27)
 
 KIND_PROGRAM = {
     KIND_QUAD_TEXTURED: "ps_quad_textured",
@@ -51,6 +51,7 @@ KIND_PROGRAM = {
     KIND_QUAD_RADIAL_GRADIENT: "ps_quad_radial_gradient",
     KIND_QUAD_CONIC_GRADIENT: "ps_quad_conic_gradient",
     KIND_BRUSH_YUV_IMAGE: "brush_yuv_image",
+    KIND_SPLIT_COMPOSITE: "ps_split_composite",
 }
 
 FEAT_ALPHA_PASS = 1 << 0

@@ -311,6 +311,91 @@ WRD void wr_setup_brush_image_one(const SetupArgs& a, int idx) {
 }
 WR_SETUP_KERNEL(wr_setup_brush_image)
 
+// ps_split_composite (ps_split_composite.glsl:64-118; SplitCompositeInstance, gpu_types.rs:531-552): one
+// polygon of a plane-split preserve-3d picture — four local points from the GPU cache, transformed
+// (usually with perspective: wr_emit_quad's draw_perspective branch) and textured from the picture's
+// surface.  The fragment / span stage is brush_image's opaque variant with uv bounds offset 0
+// (ps_split_composite.glsl:121-136), so the command is shaded by ImageShader.
+WRD void wr_setup_split_composite_one(const SetupArgs& a, int idx) {
+  int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);
+  const FrameTablesDev& T = a.tabs;
+  const int prim_header_index = aData.x, polygons_address = aData.y, render_task_index = aData.w;
+  const float ci_z = (float)aData.z;
+  QuadOut q;
+  memset(&q, 0, sizeof q);
+  const float4 data0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, polygons_address);
+  const float4 data1 = wr_fetch(T.gpu_cache, T.n_gpu_cache, polygons_address + 1);
+  const float lx[4] = {data0.x, data0.z, data1.x, data1.z}, ly[4] = {data0.y, data0.w, data1.y, data1.w};
+  DevPrimHeader ph = wr_fetch_prim_header(T, prim_header_index);
+  DevPictureTask task = wr_fetch_picture_task(T, render_task_index);
+  DevTransform transform = wr_fetch_transform(T, ph.transform_id);
+  const float4 r0 = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.user_data[0]);
+  const float uv0[2] = {r0.x, r0.y}, uv1[2] = {r0.z, r0.w};
+  const float dox = task.tx0 - task.ox, doy = task.ty0 - task.oy;  // dest_origin
+  const float tw = (float)a.color0.w, th = (float)a.color0.h;
+  const float4 tl = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.user_data[0] + 2);
+  const float4 tr = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.user_data[0] + 3);
+  const float4 bl = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.user_data[0] + 4);
+  const float4 br = wr_fetch(T.gpu_cache, T.n_gpu_cache, ph.user_data[0] + 5);
+  const float perspective = (float)ph.user_data[1];
+  const float ax[4] = {0.0f, 1.0f, 1.0f, 0.0f}, ay[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+  for (int i = 0; i < 4; i++) {
+    // bilerp(local[0], local[1], local[3], local[2], aPosition.y, aPosition.x)
+    const float t = ax[i], sgm = ay[i];
+    const float xx = (lx[1] - lx[0]) * t + lx[0], xy = (ly[1] - ly[0]) * t + ly[0];
+    const float yx = (lx[2] - lx[3]) * t + lx[3], yy = (ly[2] - ly[3]) * t + ly[3];
+    const float lpx = (yx - xx) * sgm + xx, lpy = (yy - xy) * sgm + xy;
+    const float4 world = wr_mat_mul(transform.m, make_float4(lpx, lpy, 0.0f, 1.0f));
+    q.pos[i] = wr_mat_mul(a.tgt.proj, make_float4(dox * world.w + world.x * task.device_pixel_scale,
+                                                  doy * world.w + world.y * task.device_pixel_scale, world.w * ci_z, world.w));
+    float fx = (lpx - ph.lr[0]) / (ph.lr[2] - ph.lr[0]);
+    float fy = (lpy - ph.lr[1]) / (ph.lr[3] - ph.lr[1]);
+    {  // get_image_quad_uv (prim_shared.glsl:202-210)
+      const float Xx = (tr.x - tl.x) * fx + tl.x, Xy = (tr.y - tl.y) * fx + tl.y, Xw = (tr.w - tl.w) * fx + tl.w;
+      const float Yx = (br.x - bl.x) * fx + bl.x, Yy = (br.y - bl.y) * fx + bl.y, Yw = (br.w - bl.w) * fx + bl.w;
+      const float Zx = (Yx - Xx) * fy + Xx, Zy = (Yy - Xy) * fy + Xy, Zw = (Yw - Xw) * fy + Xw;
+      fx = Zx / Zw;
+      fy = Zy / Zw;
+    }
+    const float ux = (uv1[0] - uv0[0]) * fx + uv0[0], uy = (uv1[1] - uv0[1]) * fy + uv0[1];
+    const float mixw = (1.0f - q.pos[i].w) * perspective + q.pos[i].w;  // mix(gl_Position.w, 1.0, perspective_interpolate)
+    q.interp[i][0] = ux / tw * mixw;
+    q.interp[i][1] = uy / th * mixw;
+  }
+  q.n_interp = 2;
+  q.flags = CMD_TEXTURED;
+  q.aa_edge_mask = 0;
+  wr_write_clip(T, ph.user_data[3], task, q);
+  const float minu[2] = {wr_min(uv0[0], uv1[0]), wr_min(uv0[1], uv1[1])};
+  const float maxu[2] = {wr_max(uv0[0], uv1[0]), wr_max(uv0[1], uv1[1])};
+  float fcold[8], gcold[8];
+  fcold[0] = (minu[0] + 0.5f) / tw; fcold[1] = (minu[1] + 0.5f) / th;
+  fcold[2] = (maxu[0] - 0.5f) / tw; fcold[3] = (maxu[1] - 0.5f) / th;
+  fcold[4] = 0.0f; fcold[5] = 0.0f;
+  fcold[6] = perspective;
+  float fw = 1.0f / q.pos[0].w;
+  if (!isfinite(fw)) fw = 0.0f;
+  fcold[7] = fw;
+  const float one[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+  for (int i = 0; i < 4; i++) gcold[i] = 1.0f;
+  gcold[4] = 1.0f; gcold[5] = 0.0f;
+  gcold[6] = 0.0f;  // colour = alpha (1) * texel
+  gcold[7] = 1.0f;  // swgl_drawSpanRGBA8 always commits (RGBA8 surface)
+  wr_pack_color(q, one);
+  int unsupported = 0;
+  bool ok = wr_emit_quad(a, idx, q, &unsupported);
+  if (ok) {
+    CmdCold* k = &a.cold[idx];
+    for (int i = 0; i < 8; i++) { k->f[i] = fcold[i]; k->g[i] = gcold[i]; }
+    k->i[0] = k->i[1] = 0;
+    k->g[8] = maxu[0] / tw;
+    k->g[9] = maxu[1] / th;
+    k->g[10] = k->g[11] = 0.0f;
+  }
+  wr_finish_setup(a, unsupported);
+}
+WR_SETUP_KERNEL(wr_setup_split_composite)
+
 // ps_text_run main (ps_text_run.glsl:98-264), no GLYPH_TRANSFORM
 WRD void wr_setup_text_run_one(const SetupArgs& a, int idx) {
   int4 aData = *(const int4*)(a.instances + (size_t)idx * a.stride);

@@ -48,6 +48,7 @@ struct SetupArgs {
   int depth_runs;           // depth test on and the kind's shading depends on where passing runs start:
   int fail_cap;             //   commands get a failing-sample bitmap (CmdCold::fail_off) from a pool of fail_cap words
   int copy_ok;              // composite: blend off or premultiplied-alpha over, no depth → copy class possible
+  int persp_ok;             // the kind's fragment stage is built for draw_perspective (per-sample 1/w); others are rejected
 };
 
 // A setup kernel = one thread per instance running <name>_one.  Under the host
@@ -531,7 +532,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
       k.cmy = (short)cmy;
     }
     if (persp) {  // draw_perspective (rasterize.h:1422-1545)
-      if ((q.flags & CMD_CLIP_DIST) || a.tgt.fmt != WRCU_FMT_RGBA8) { *unsupported = 1; break; }
+      if (!a.persp_ok || (q.flags & CMD_CLIP_DIST) || a.tgt.fmt != WRCU_FMT_RGBA8) { *unsupported = 1; break; }
       const int r = wr_emit_persp(a, q, flags, cx0, cy0, cx1, cy1, h, k);
       if (r < 0) *unsupported = 1;
       ok = r > 0;

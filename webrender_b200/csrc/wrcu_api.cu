@@ -523,7 +523,7 @@ static int sync_and_check(wrcu_ctx* c) {
   if (n) {
     cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
     return wrcu_fail(c, WRCU_ERR_UNSUPPORTED,
-                     "%d instance(s) need the general edge walker (rotation/perspective), not rasterised", n);
+                     "%d instance(s) not rasterised: perspective under a kind without the per-sample 1/w path, or resources exhausted", n);
   }
   return WRCU_OK;
 }
@@ -1336,6 +1336,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       case WRCU_KIND_QUAD_TEXTURED: case WRCU_KIND_BRUSH_IMAGE: case WRCU_KIND_BRUSH_LINEAR_GRADIENT:
       case WRCU_KIND_BRUSH_BLEND: case WRCU_KIND_BRUSH_MIX_BLEND: case WRCU_KIND_BRUSH_OPACITY: case WRCU_KIND_TEXT_RUN:
       case WRCU_KIND_BRUSH_YUV_IMAGE: case WRCU_KIND_QUAD_RADIAL_GRADIENT: case WRCU_KIND_QUAD_CONIC_GRADIENT:
+      case WRCU_KIND_SPLIT_COMPOSITE:
         kind_runs = true; break;
       default: break;
     }
@@ -1355,6 +1356,10 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     }
   }
 #endif
+  // draw_perspective (w differs between an instance's vertices): the kinds whose fragment stage carries the
+  // per-sample 1/w path; the solid colour case of ps_quad_textured shares brush_solid's shader
+  sa.persp_ok = kind == WRCU_KIND_BRUSH_SOLID || kind == WRCU_KIND_SPLIT_COMPOSITE ||
+                (kind == WRCU_KIND_BRUSH_IMAGE && !(features & WRCU_FEAT_REPETITION));
   sa.copy_ok = !T.depth && (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA);
   if (kind == WRCU_KIND_COMPOSITE && sa.copy_ok && !(features & WRCU_FEAT_YUV)) {
     // The copy kernel moves boxes of different instances concurrently: a batch whose instances overlap keeps
@@ -1522,6 +1527,13 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       sa.features = features;
       WR_LAUNCH(wr_setup_brush_opacity, sblocks, 128, c->stream, sa);
       break;
+    case WRCU_KIND_SPLIT_COMPOSITE:
+      if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
+      if (!sa.color0.ptr || sa.color0.fmt != WRCU_FMT_RGBA8)
+        return wrcu_fail(c, WRCU_ERR_INVALID, "ps_split_composite needs an RGBA8 surface in sColor0");
+      sa.features = features;
+      WR_LAUNCH(wr_setup_split_composite, sblocks, 128, c->stream, sa);
+      break;
     case WRCU_KIND_BRUSH_YUV_IMAGE:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_yuv_image without sColor0");
@@ -1667,6 +1679,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER_RUNS(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
     case WRCU_KIND_BRUSH_YUV_IMAGE: LAUNCH_RASTER_RUNS(CompositeYuvShader); break;
+    case WRCU_KIND_SPLIT_COMPOSITE: LAUNCH_RASTER_RUNS(ImageShader); break;
     case WRCU_KIND_COMPOSITE:
       if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
 #ifndef WRCU_HOSTEMU
@@ -1723,6 +1736,7 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
       {"brush_mix_blend", WRCU_KIND_BRUSH_MIX_BLEND}, {"brush_opacity", WRCU_KIND_BRUSH_OPACITY},
       {"ps_text_run", WRCU_KIND_TEXT_RUN}, {"cs_clip_rectangle", WRCU_KIND_CLIP_RECTANGLE},
       {"cs_clip_box_shadow", WRCU_KIND_CLIP_BOX_SHADOW}, {"composite", WRCU_KIND_COMPOSITE}, {"brush_yuv_image", WRCU_KIND_BRUSH_YUV_IMAGE},
+      {"ps_split_composite", WRCU_KIND_SPLIT_COMPOSITE},
       {"ps_clear", WRCU_KIND_CLEAR}, {"cs_blur", WRCU_KIND_BLUR}, {"cs_scale", WRCU_KIND_SCALE},
       {"cs_fast_linear_gradient", WRCU_KIND_FAST_LINEAR_GRADIENT}, {"cs_linear_gradient", WRCU_KIND_LINEAR_GRADIENT},
       {"cs_radial_gradient", WRCU_KIND_RADIAL_GRADIENT}, {"cs_conic_gradient", WRCU_KIND_CONIC_GRADIENT},

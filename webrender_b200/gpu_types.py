@@ -153,6 +153,11 @@ def brush_instance(prim_header_index, clip_task_address, segment_index, edge_fla
                     dtype=np.int64).astype(np.int32)
 
 
+def split_composite_instance(prim_header_index, polygons_address, z, render_task_address):
+    """SplitCompositeInstance → PrimitiveInstanceData (gpu_types.rs:531-552)."""
+    return np.array([prim_header_index, polygons_address, z, render_task_address], dtype=np.int64).astype(np.int32)
+
+
 def clip_rect_instance(sub_rect, task_origin, screen_origin, device_pixel_scale, clip_transform_id,
                        prim_transform_id, local_pos, local_rect, mode, radii):
     """ClipMaskInstanceRect, 200 bytes (gpu_types.rs:208-225, prim_store/mod.rs:774-813).

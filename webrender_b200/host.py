@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libwrhost.so")
 BATCH_KIND = {abi.KIND_QUAD_TEXTURED: 0, abi.KIND_QUAD_MASK: 1, abi.KIND_BRUSH_SOLID: 2, abi.KIND_BRUSH_IMAGE: 3,
               abi.KIND_BRUSH_BLEND: 4, abi.KIND_BRUSH_MIX_BLEND: 5, abi.KIND_BRUSH_LINEAR_GRADIENT: 6,
               abi.KIND_BRUSH_OPACITY: 7, abi.KIND_TEXT_RUN: 8, abi.KIND_QUAD_RADIAL_GRADIENT: 9,
-              abi.KIND_QUAD_CONIC_GRADIENT: 10, abi.KIND_BRUSH_YUV_IMAGE: 11}
+              abi.KIND_QUAD_CONIC_GRADIENT: 10, abi.KIND_BRUSH_YUV_IMAGE: 11, abi.KIND_SPLIT_COMPOSITE: 12}
 CACHE_TASK_KINDS = {abi.KIND_BORDER_SOLID, abi.KIND_BORDER_SEGMENT, abi.KIND_LINE_DECORATION,
                     abi.KIND_FAST_LINEAR_GRADIENT, abi.KIND_LINEAR_GRADIENT, abi.KIND_RADIAL_GRADIENT,
                     abi.KIND_CONIC_GRADIENT}

@@ -61,6 +61,7 @@ int batch_kind_to_wrcu(BatchKind kind) {
     case BatchKind::QuadRadialGradient: return WRCU_KIND_QUAD_RADIAL_GRADIENT;
     case BatchKind::QuadConicGradient: return WRCU_KIND_QUAD_CONIC_GRADIENT;
     case BatchKind::BrushYuvImage: return WRCU_KIND_BRUSH_YUV_IMAGE;
+    case BatchKind::SplitComposite: return WRCU_KIND_SPLIT_COMPOSITE;
   }
   return 0;
 }

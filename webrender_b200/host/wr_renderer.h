@@ -37,6 +37,7 @@ enum class BatchKind {
   BrushOpacity, TextRun,
   QuadRadialGradient, QuadConicGradient,  // BatchKind::Quad(PatternKind::RadialGradient / ConicGradient), pattern.rs
   BrushYuvImage,                          // BatchKind::Brush(BrushBatchKind::YuvImage(..)), batch.rs:60-86
+  SplitComposite,                         // BatchKind::SplitComposite (batch.rs:74): plane-split preserve-3d polygons
 };
 // batch.rs BatchFeatures / shade.rs feature strings
 enum BatchFeatures : uint32_t {

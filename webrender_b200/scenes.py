@@ -371,6 +371,276 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
     return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
 
 
+def page_frame(width=3840, height=2160, tile_w=1024, tile_h=512, seed=1, clips=12):
+    """What a page costs a compositor: MANY SMALL batches.  Three passes as draw_frame issues them
+    (renderer/mod.rs:4525-4841): (1) an alpha target of rounded-rect clip masks (cs_clip_rectangle, primary and
+    secondary, fast and general programs); (2) every picture-cache tile of the 4K page (1024x512 tiles) as its own
+    target: clear, opaque solids and images front to back with depth write, then alpha batches in order — masked /
+    anti-aliased solids, images, a linear gradient, two text runs; (3) the tile list composited into the framebuffer.
+    ~7 batches per tile x 20 tiles + masks + composite = ~150 draws of 2-60 instances each."""
+    from .gpu_types import (brush_instance, glyph_instance, clip_rect_instance, composite_instance,
+                            build_gradient_table, CLIP_TASK_EMPTY)
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    textures = {}
+    # ---- pass 1: clip masks into an R8 alpha target ------------------------------------------------------
+    mw, mh = 1024, 512
+    fast, slow, fast2 = [], [], []
+    mask_tasks = []   # (render task address of the mask region, w, h)
+    for i in range(clips):
+        w, h = int(rng.randint(60, 200)), int(rng.randint(40, 140))
+        tx, ty = (i % 4) * 256 + int(rng.randint(0, 40)), (i // 4) * 160 + int(rng.randint(0, 16))
+        sx, sy = int(rng.randint(0, tile_w - w)), int(rng.randint(0, tile_h - h))
+        rect = (float(sx + 2), float(sy + 2), float(sx + w - 2), float(sy + h - 2))
+        uniform = i % 2 == 0
+        if uniform:
+            r = float(rng.randint(4, 20))
+            radii = ((r, r),) * 4
+        else:
+            radii = tuple((float(rng.uniform(3, 28)), float(rng.uniform(3, 20))) for _ in range(4))
+        inst = clip_rect_instance((0.0, 0.0, float(w), float(h)), (float(tx), float(ty)), (float(sx), float(sy)),
+                                  1.0, 0, 0, (rect[0], rect[1]), rect, 0.0, radii)
+        (fast if uniform else slow).append(inst)
+        if i % 4 == 0:   # a secondary clip multiplied into the same region
+            r2 = (rect[0] + 10.0, rect[1] + 6.0, rect[2] - 14.0, rect[3] - 8.0)
+            fast2.append(clip_rect_instance((0.0, 0.0, float(w), float(h)), (float(tx), float(ty)), (float(sx), float(sy)),
+                                            1.0, 0, 0, (r2[0], r2[1]), r2, 0.0, ((8.0, 8.0),) * 4))
+        mask_tasks.append((t.add_render_task((float(tx), float(ty), float(tx + w), float(ty + h)), 1.0,
+                                             (float(sx), float(sy))), sx, sy, w, h))
+    mops = [Clear(color=(1.0, 1.0, 1.0, 1.0))]
+    for lst, feat, blend in ((slow, 0, abi.BLEND_NONE), (fast, abi.FEAT_FAST_PATH, abi.BLEND_NONE),
+                             (fast2, abi.FEAT_FAST_PATH, abi.BLEND_MULTIPLY)):
+        if lst:
+            mops.append(Batch(abi.KIND_CLIP_RECTANGLE, np.stack(lst), blend=blend, features=feat))
+    textures["mask"] = TextureDesc(abi.FMT_R8, mw, mh)
+    # ---- shared inputs: an image atlas and a glyph atlas --------------------------------------------------
+    aw, ah = 512, 512
+    atlas = rng.randint(0, 256, size=(ah, aw, 4)).astype(np.uint8)
+    al = atlas[..., 3:4].astype(np.uint16)
+    atlas[..., :3] = (atlas[..., :3].astype(np.uint16) * al // 255).astype(np.uint8)
+    textures["atlas"] = TextureDesc(abi.FMT_RGBA8, aw, ah, atlas.reshape(ah, aw * 4))
+    gsz = 512
+    cells = gsz // 16
+    gtex = np.zeros((gsz, gsz), dtype=np.uint8)
+    glyph_res = []
+    for gy in range(cells):
+        for gx in range(cells):
+            gw, gh = int(rng.randint(4, 17)), int(rng.randint(4, 17))
+            gtex[gy * 16: gy * 16 + gh, gx * 16: gx * 16 + gw] = rng.randint(0, 256, size=(gh, gw)).astype(np.uint8)
+            glyph_res.append((gx * 16, gy * 16, gw, gh))
+    textures["glyphs"] = TextureDesc(abi.FMT_R8, gsz, gsz, gtex)
+    glyph_addr = {}
+    # ---- pass 2: the picture-cache tiles ------------------------------------------------------------------
+    cols, rows = (width + tile_w - 1) // tile_w, (height + tile_h - 1) // tile_h
+    tile_targets, comp = [], []
+    ti = 0
+    for ry in range(rows):
+        for cx in range(cols):
+            name, dname = "tile%d" % ti, "tile%d_depth" % ti
+            textures[name] = TextureDesc(abi.FMT_RGBA8, tile_w, tile_h, filter=abi.NEAREST)
+            textures[dname] = TextureDesc(abi.FMT_DEPTH24, tile_w, tile_h)
+            ox, oy = float(cx * tile_w), float(ry * tile_h)
+            pic = t.add_render_task((0.0, 0.0, float(tile_w), float(tile_h)), 1.0, (ox, oy))
+            z = 1
+
+            def prim(rect, clip, blocks, user=(65535, 0, 0, 0), res=None, flags=0, edge=0, clip_task=CLIP_TASK_EMPTY):
+                nonlocal z
+                addr = t.push_gpu_cache(blocks)
+                hdr = t.add_prim_header(rect, clip, z, addr, 0, pic, user)
+                z += 1
+                return brush_instance(hdr, clip_task, 0xFFFF, edge, flags, 0 if res is None else res)
+
+            def local(r):  # a rect inside this tile, in page space
+                return (r[0] + ox, r[1] + oy, r[2] + ox, r[3] + oy)
+            noclip = (-1e9, -1e9, 1e9, 1e9)
+            z = 1000
+            osolid = [prim(local(_rand_rect(rng, tile_w, tile_h, 40, 400)), noclip,
+                           [tuple(float(v) for v in rng.uniform(0, 1, 3)) + (1.0,)]) for _ in range(6)]
+            oimg = []
+            for _ in range(3):
+                r = _rand_rect(rng, tile_w, tile_h, 40, 300)
+                uw, uh = min(int(r[2] - r[0]), aw - 1), min(int(r[3] - r[1]), ah - 1)
+                u0, v0 = int(rng.randint(0, aw - uw)), int(rng.randint(0, ah - uh))
+                res = t.push_gpu_cache([(float(u0), float(v0), float(u0 + uw), float(v0 + uh)), (0.0, 0.0, 0.0, 0.0)])
+                oimg.append(prim(local(r), noclip, [(1.0, 1.0, 1.0, 1.0), (0.0, 0.0, 0.0, 0.0), (-1.0, -1.0, 0.0, 0.0)],
+                                 user=(4 | (1 << 16), 0, 65535, 0), res=res))
+            z = 1
+            asolid = []
+            for i in range(8):
+                r = _rand_rect(rng, tile_w, tile_h, 30, 300)
+                a = float(rng.uniform(0.2, 0.9))
+                c = tuple(float(v * a) for v in rng.uniform(0, 1, 3)) + (a,)
+                ct = CLIP_TASK_EMPTY
+                if i % 3 == 0:
+                    task, sx, sy, w, h = mask_tasks[int(rng.randint(0, len(mask_tasks)))]
+                    r = (float(sx), float(sy), float(sx + w), float(sy + h))
+                    ct = task
+                asolid.append(prim(local(r), noclip, [c], user=(int(rng.uniform(0.4, 1.0) * 65535), 0, 0, 0),
+                                   flags=1024 if i % 2 else 0, edge=(i % 16) if i % 2 else 0, clip_task=ct))
+            aimg = []
+            for i in range(6):
+                r = _rand_rect(rng, tile_w, tile_h, 30, 260)
+                uw, uh = int(rng.randint(16, 200)), int(rng.randint(16, 160))
+                u0, v0 = int(rng.randint(0, aw - uw)), int(rng.randint(0, ah - uh))
+                res = t.push_gpu_cache([(float(u0), float(v0), float(u0 + uw), float(v0 + uh)), (0.0, 0.0, 0.0, 0.0)])
+                col = tuple(float(v) for v in rng.uniform(0.3, 1.0, 4))
+                aimg.append(prim(local(r), noclip, [col, (0.0, 0.0, 0.0, 0.0), (-1.0, -1.0, 0.0, 0.0)],
+                                 user=(4 | (1 << 16), 0, int(rng.uniform(0.5, 1.0) * 65535), 0), res=res))
+            grads = []
+            for i in range(2):
+                r = _rand_rect(rng, tile_w, tile_h, 100, 500)
+                stops = [(0.0, tuple(float(v * 0.8) for v in rng.uniform(0, 1, 3)) + (0.8,)),
+                         (1.0, tuple(float(v * 0.5) for v in rng.uniform(0, 1, 3)) + (0.5,))]
+                if (len(t.gpu_buffer_f) % 1024) + 260 > 1024:
+                    t.push_gpu_buffer_f([(0, 0, 0, 0)] * ((-len(t.gpu_buffer_f)) % 1024))
+                lut = t.push_gpu_buffer_f(list(build_gradient_table(stops)))
+                grads.append(prim(local(r), noclip, [(0.0, 0.0, float(r[2] - r[0]), float(r[3] - r[1])),
+                                                     (0.0, float(r[2] - r[0]), float(r[3] - r[1]), 0.0)], user=(lut, 0, 0, 0)))
+            glyphs = []
+            for run in range(2):
+                a = float(rng.uniform(0.6, 1.0))
+                color = tuple(float(v * a) for v in rng.uniform(0, 0.4, 3)) + (a,)
+                bx, by = float(rng.randint(0, tile_w - 500)) + ox, float(rng.randint(20, tile_h - 8)) + oy
+                pen, offs, gids = 0.0, [], []
+                for g in range(30):
+                    gid = int(rng.randint(0, len(glyph_res)))
+                    gids.append(gid)
+                    offs.append((pen, 0.0))
+                    pen += glyph_res[gid][2] + 1.0
+                blocks = [color] + [(offs[k][0], offs[k][1], offs[k + 1][0], offs[k + 1][1]) for k in range(0, 30, 2)]
+                addr = t.push_gpu_cache(blocks)
+                hdr = t.add_prim_header((bx, by, 0.0, 0.0), noclip, z, addr, 0, pic, (65535, 0, 0, 0))
+                z += 1
+                for g, gid in enumerate(gids):
+                    if gid not in glyph_addr:
+                        gx, gy, gw, gh = glyph_res[gid]
+                        glyph_addr[gid] = t.push_gpu_cache([(float(gx), float(gy), float(gx + gw), float(gy + gh)),
+                                                            (0.0, float(-gh), 1.0, 0.0)])
+                    glyphs.append(glyph_instance(hdr, CLIP_TASK_EMPTY, 0, 0, g, glyph_addr[gid]))
+            PM = abi.BLEND_PREMULTIPLIED_ALPHA
+            ops = [Clear(color=(1.0, 1.0, 1.0, 1.0), depth=1.0),
+                   Batch(abi.KIND_BRUSH_SOLID, np.stack(osolid[::-1]), blend=abi.BLEND_NONE, depth=abi.DEPTH_TEST_WRITE),
+                   Batch(abi.KIND_BRUSH_IMAGE, np.stack(oimg[::-1]), blend=abi.BLEND_NONE, depth=abi.DEPTH_TEST_WRITE,
+                         features=abi.FEAT_TEXTURE_2D, color=("atlas", "", "")),
+                   Batch(abi.KIND_BRUSH_SOLID, np.stack(asolid), blend=PM, depth=abi.DEPTH_TEST, features=abi.FEAT_ALPHA_PASS,
+                         clip_mask="mask"),
+                   Batch(abi.KIND_BRUSH_IMAGE, np.stack(aimg), blend=PM, depth=abi.DEPTH_TEST,
+                         features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("atlas", "", "")),
+                   Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, np.stack(grads), blend=PM, depth=abi.DEPTH_TEST,
+                         features=abi.FEAT_ALPHA_PASS),
+                   Batch(abi.KIND_TEXT_RUN, np.stack(glyphs), blend=PM, depth=abi.DEPTH_TEST,
+                         features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("glyphs", "", ""))]
+            tile_targets.append(Target(name, depth=dname, ops=ops))
+            rect = (ox, oy, ox + tile_w, oy + tile_h)
+            clip = (ox, oy, min(ox + tile_w, float(width)), min(oy + tile_h, float(height)))
+            comp.append(Batch(abi.KIND_COMPOSITE, composite_instance(rect, clip)[None, :], blend=abi.BLEND_NONE,
+                              features=abi.FEAT_FAST_PATH | abi.FEAT_TEXTURE_2D, color=(name, "", "")))
+            ti += 1
+    # ---- pass 3: the tile list into the framebuffer ---------------------------------------------------------
+    textures["fb"] = TextureDesc(abi.FMT_RGBA8, width, height)
+    fb = Target("fb", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0))] + comp)
+    return Frame(t.arrays(), textures, [[Target("mask", ops=mops)], tile_targets, [fb]])
+
+
+def perspective_matrix(width, height, d=800.0, ry=35.0, rx=0.0):
+    """A CSS-style perspective transform about the page centre: perspective(d) rotateX(rx) rotateY(ry).
+    With a small `d` and a steep angle part of the page lies behind the eye (w <= 0): the near-plane
+    clipping of draw_perspective (rasterize.h:1467-1521)."""
+    cx, cy = width / 2.0, height / 2.0
+    t1 = np.eye(4)
+    t1[0, 3], t1[1, 3] = -cx, -cy
+    a, b = np.deg2rad(ry), np.deg2rad(rx)
+    rym = np.array([[np.cos(a), 0, np.sin(a), 0], [0, 1, 0, 0], [-np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]])
+    rxm = np.array([[1, 0, 0, 0], [0, np.cos(b), -np.sin(b), 0], [0, np.sin(b), np.cos(b), 0], [0, 0, 0, 1]])
+    pm = np.eye(4)
+    pm[3, 2] = -1.0 / d
+    t2 = np.eye(4)
+    t2[0, 3], t2[1, 3] = cx, cy
+    return (t2 @ pm @ rxm @ rym @ t1).astype(np.float32)
+
+
+def with_transform(make_frame, matrix, **kw):
+    """Build one of the `rotate=` scenes with an arbitrary 4x4 (e.g. perspective_matrix) in place of the rotation."""
+    global rotation_matrix
+    saved = rotation_matrix
+    rotation_matrix = lambda *a, **k: matrix  # noqa: E731
+    try:
+        return make_frame(rotate=0.0, **kw)
+    finally:
+        rotation_matrix = saved
+
+
+def perspective_frame(kind="solid", width=640, height=360, d=800.0, ry=35.0, rx=0.0, **kw):
+    """Brush batches under a perspective spatial node (w differs between the vertices: draw_perspective,
+    rasterize.h:1422-1545): kind = "solid" (brush_solid_frame: opaque + alpha with masks / AA) or "image"
+    (image_frame: opaque + alpha pass sampling an atlas)."""
+    m = perspective_matrix(width, height, d, ry, rx)
+    make = {"solid": brush_solid_frame, "image": image_frame}[kind]
+    return with_transform(make, m, width=width, height=height, **kw)
+
+
+def split_composite_frame(width=640, height=360, n_polys=10, seed=1, d=600.0, ry=40.0, rx=-15.0,
+                          perspective_interpolate=0, with_masks=True, filter=abi.LINEAR):
+    """BatchKind::SplitComposite (batch.rs:74, 2040-2080): the polygons a plane-split preserve-3d picture is cut
+    into, each drawn by ps_split_composite from the picture's surface with premultiplied blending under the
+    depth test, behind a few opaque Brush(Solid) prims.  Polygon points are in the picture's local space; the
+    prim header carries the picture rect and its (perspective) transform, user_data = [ImageSource address,
+    perspective_interpolate, 0, clip task]; the ImageSource has the UvRectKind::Quad corner block."""
+    from .gpu_types import brush_instance, split_composite_instance, CLIP_TASK_EMPTY
+    rng = np.random.RandomState(seed)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
+    sw, sh = 256, 192
+    surf = rng.randint(0, 256, size=(sh, sw, 4)).astype(np.uint8)
+    al = surf[..., 3:4].astype(np.uint16)
+    surf[..., :3] = (surf[..., :3].astype(np.uint16) * al // 255).astype(np.uint8)
+    mw, mh = 256, 256
+    mask = rng.randint(0, 256, size=(mh, mw)).astype(np.uint8)
+    xf = t.add_transform(perspective_matrix(width, height, d, ry, rx), axis_aligned=False)
+    # opaque solids in front (larger z), some under the same transform
+    opaque = []
+    z = 5000
+    for i in range(4):
+        r = _rand_rect(rng, width, height, 30, 160)
+        c = tuple(float(v) for v in rng.uniform(0, 1, 3)) + (1.0,)
+        addr = t.push_gpu_cache([c])
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), z, addr, xf if i % 2 else 0, pic, (65535, 0, 0, 0))
+        z += 1
+        opaque.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+    polys = []
+    z = 1
+    for i in range(n_polys):
+        # the picture: a local rect, its surface region, and a convex quad inside it
+        r = _rand_rect(rng, width, height, 60, 300)
+        rw, rh = r[2] - r[0], r[3] - r[1]
+        uw, uh = int(rng.randint(20, 200)), int(rng.randint(20, 150))
+        u0, v0 = int(rng.randint(0, sw - uw)), int(rng.randint(0, sh - uh))
+        j = lambda s: float(rng.uniform(0.0, 0.3) * s)  # noqa: E731
+        pts = [(r[0] + j(rw), r[1] + j(rh)), (r[2] - j(rw), r[1] + j(rh)), (r[2] - j(rw), r[3] - j(rh)), (r[0] + j(rw), r[3] - j(rh))]
+        poly_addr = t.push_gpu_cache([(pts[0][0], pts[0][1], pts[1][0], pts[1][1]), (pts[2][0], pts[2][1], pts[3][0], pts[3][1])])
+        k = float(rng.uniform(0.8, 1.25))
+        res = t.push_gpu_cache([(float(u0), float(v0), float(u0 + uw), float(v0 + uh)), (0.0, 0.0, 0.0, 0.0),
+                                (0.0, 0.0, 0.0, 1.0), (k, 0.0, 0.0, k), (0.0, 1.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)])
+        clip_task = CLIP_TASK_EMPTY
+        if with_masks and i % 3 == 1:
+            w_, h_ = 100, 80
+            mx, my = int(rng.randint(0, mw - w_)), int(rng.randint(0, mh - h_))
+            sx, sy = int(rng.randint(0, width - w_)), int(rng.randint(0, height - h_))
+            clip_task = t.add_render_task((float(mx), float(my), float(mx + w_), float(my + h_)), 1.0, (float(sx), float(sy)))
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), z, 0, xf, pic, (res, perspective_interpolate, 0, clip_task))
+        polys.append(split_composite_instance(hdr, poly_addr, z, pic))
+        z += 1
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
+                "depth": TextureDesc(abi.FMT_DEPTH24, width, height),
+                "surface": TextureDesc(abi.FMT_RGBA8, sw, sh, surf.reshape(sh, sw * 4), filter=filter),
+                "mask": TextureDesc(abi.FMT_R8, mw, mh, mask)}
+    ops = [Clear(color=(1.0, 1.0, 1.0, 1.0), depth=1.0),
+           Batch(abi.KIND_BRUSH_SOLID, np.stack(opaque[::-1]), blend=abi.BLEND_NONE, depth=abi.DEPTH_TEST_WRITE),
+           Batch(abi.KIND_SPLIT_COMPOSITE, np.stack(polys), blend=abi.BLEND_PREMULTIPLIED_ALPHA, depth=abi.DEPTH_TEST,
+                 color=("surface", "", ""), clip_mask="mask")]
+    return Frame(t.arrays(), textures, [[Target("target", depth="depth", ops=ops)]])
+
+
 def image_repeat_frame(width=640, height=360, n_opaque=6, n_alpha=14, seed=1, filter=abi.LINEAR, fractional=False,
                        device_pixel_scale=1.0, occlude_alpha=False):
     """Tiled images and border-image segments: Brush(Image) with BatchFeatures::REPETITION
