@@ -107,7 +107,7 @@ WRD void wr_set_lum_sat(float* out, const float* base, const float* sref,
 
 // Generic blend of one RGBA8 pixel (all keys), blend.h:462-700.  `kc` is
 // ctx->blendcolor in B,G,R,A lane order.
-WRD Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
+WRD_SHARED Px wr_blend_rgba8(int key, Px src, Px dst, Px kc) {
   Px o = src;
   switch (key) {
     case WRCU_BLEND_NONE:

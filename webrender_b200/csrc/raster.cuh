@@ -106,7 +106,7 @@ WRD const float* wr_gen_vertex_interp(const CmdCold& k, int v) {
 
 // aa_span + the edge state of draw_quad_spans for row y of a general quad.
 // Fills g and the row's span in `out` (a copy of the hot record); false = empty.
-WRD bool wr_general_row(const CmdCold& k, const CmdHot& c, int y, GenRow& g, CmdHot& out) {
+WRD_SHARED bool wr_general_row(const CmdCold& k, const CmdHot& c, int y, GenRow& g, CmdHot& out) {
   int e = 0;
   for (int i = 1; i < k.gn_ev; i++)
     if (k.gev[i].row <= y) e = i;
@@ -520,7 +520,7 @@ WRD void wr_interp_at(const RasterArgs& a, const float* o, const float* step, in
 
 // clip_distance_range (rasterize.h:566-596) for row y of a command whose vertex stage wrote
 // gl_ClipDistance (interpolants 2..5): narrows the row's span [c.x0, c.x1).  Warp-uniform.
-WRD bool wr_clip_dist_row(const RasterArgs& a, const CmdCold& k, CmdHot& c, int y) {
+WRD_SHARED bool wr_clip_dist_row(const RasterArgs& a, const CmdCold& k, CmdHot& c, int y) {
   float o[6], st[6], li[6], ri[6];
   wr_row_interp<6>(a, k, c, y, o, st, li, ri);
   const bool gen = (c.flags & CMD_GENERAL) != 0;

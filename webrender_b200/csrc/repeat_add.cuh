@@ -15,7 +15,7 @@
 #pragma once
 #include "wrcu_internal.h"
 
-WRD float wr_repeat_add(float x, float s, int n) {
+WRD_SHARED float wr_repeat_add(float x, float s, int n) {
   if (n <= 0) return x;
   if (s == 0.0f || !(fabsf(x) < 3.0e38f) || !(fabsf(s) < 3.0e38f)) {
     for (int i = 0; i < n && i < 4; i++) x = __fadd_rn(x, s);  // inf/nan/zero step: a few steps settle it

@@ -49,6 +49,8 @@ struct SetupArgs {
   int fail_cap;             //   commands get a failing-sample bitmap (CmdCold::fail_off) from a pool of fail_cap words
   int copy_ok;              // composite: blend off or premultiplied-alpha over, no depth → copy class possible
   int persp_ok;             // the kind's fragment stage is built for draw_perspective (per-sample 1/w); others are rejected
+  int* pool_ctr;            // [0] floats of the row-table pool, [1] words of the depth-run bitmap pool handed out so far
+                            // (shared by every batch of a submission: wrcu_api.cu flush_pending)
 };
 
 // A setup kernel = one thread per instance running <name>_one.  Under the host
@@ -76,7 +78,7 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
 // 2N edge sums x blocks of rows (a block starts with one wr_repeat_add, then plain additions —
 // the reference's own sequence).
 // tall commands: the 32 lanes split one command's 2N edge sums x blocks of rows
-WRD void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
+WRD_SHARED void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
   const CmdHot c = a.hot[cidx];
   const CmdCold& k = a.cold[cidx];
   const int E = 2 * k.row_n, rows = c.y1 - c.y0;
@@ -100,7 +102,7 @@ WRD void wr_fill_row_table(const SetupArgs& a, int cidx, int lane) {
 }
 // short commands: one lane walks one edge sum of one command from its first row (plain additions,
 // the reference's own sequence); 32 / 2N commands are filled at once
-WRD void wr_fill_row_edge(const SetupArgs& a, int cidx, int e) {
+WRD_SHARED void wr_fill_row_edge(const SetupArgs& a, int cidx, int e) {
   const CmdHot c = a.hot[cidx];
   const CmdCold& k = a.cold[cidx];
   const int E = 2 * k.row_n, rows = c.y1 - c.y0;
@@ -119,7 +121,7 @@ WRD void wr_fill_row_edge(const SetupArgs& a, int cidx, int e) {
 #ifdef WRCU_HOSTEMU
 #define WR_SETUP_KERNEL(name)                                     \
   static void name(const SetupArgs& a) {                          \
-    wr_reset_batch_info(a.info_next);                             \
+    if (a.info_next) wr_reset_batch_info(a.info_next);            \
     for (int i = 0; i < a.n; i++) {                               \
       name##_one(a, i);                                           \
       if (a.cold[i].row_off >= 0 && a.cold[i].row_n > 0)          \
@@ -150,7 +152,7 @@ WRD void wr_fill_row_tables_warp(const SetupArgs& a, int idx) {
   }
 }
 // One command's row table by a whole warp: the 2N edge sums x blocks of >= 16 rows spread over the lanes.
-WRD void wr_fill_row_table_spread(const SetupArgs& a, int cidx, int lane) {
+WRD_SHARED void wr_fill_row_table_spread(const SetupArgs& a, int cidx, int lane) {
   const CmdHot c = a.hot[cidx];
   const CmdCold& k = a.cold[cidx];
   const int E = 2 * k.row_n, rows = c.y1 - c.y0;
@@ -175,10 +177,12 @@ WRD void wr_fill_row_table_spread(const SetupArgs& a, int cidx, int lane) {
 // Small batches (SetupArgs::warp_per_inst: what a page is mostly made of — a few instances per batch) are
 // latency, not throughput: one warp per instance, so the instances' dependent table fetches overlap and
 // each row table is filled by 32 lanes instead of one.
+// name##_block: the kernel body for the batch's thread `idx` (CTA-relative to the batch's first block), so that
+// one launch can run the set-up of MANY batches (wr_setup_multi, wrcu_api.cu): a page is ~150 batches of a few
+// instances, and a launch per batch made its set-up latency (~10 us: a chain of table fetches) the frame time.
 #define WR_SETUP_KERNEL(name)                                                  \
-  __global__ void name(SetupArgs a) {                                          \
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;                           \
-    if (idx == 0) wr_reset_batch_info(a.info_next);                            \
+  __device__ __noinline__ void name##_block(const SetupArgs& a, int idx) {     \
+    if (idx == 0 && a.info_next) wr_reset_batch_info(a.info_next);             \
     if (a.warp_per_inst) {                                                     \
       const int lane = threadIdx.x & 31;                                       \
       idx >>= 5;                                                               \
@@ -390,7 +394,7 @@ WRD_NOINLINE int wr_emit_persp(const SetupArgs& a, const QuadOut& q, uint32_t fl
   }
   if (sides != 0xF) return 0;
   if (!a.row_tab) return -1;
-  const int off = atomicAdd(&a.info->row_alloc, WR_PP_FLOATS);
+  const int off = atomicAdd(a.pool_ctr, WR_PP_FLOATS);
   if (off < 0 || off + WR_PP_FLOATS > a.row_cap) return -1;
   PerspPoly& P = *(PerspPoly*)(a.row_tab + off);
   P.nump = nump;
@@ -490,7 +494,7 @@ WRD_NOINLINE int wr_emit_persp(const SetupArgs& a, const QuadOut& q, uint32_t fl
 // false (and writes an empty command) when the instance draws nothing.
 // Sets *unsupported when the quad needs the general edge walker (rotation or
 // perspective), which this backend does not rasterise yet.
-WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupported) {
+WRD_SHARED bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupported) {
   CmdHot h;
   h.x0 = h.y0 = h.x1 = h.y1 = 0;
   h.flags = 0;
@@ -707,7 +711,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
   a.hot[idx] = h;
   if (ok && a.row_tab && q.n_interp > 0 && !(h.flags & CMD_GENERAL) && (int)h.y1 - (int)h.y0 >= WR_ROW_TAB_MIN) {
     const int need = ((int)h.y1 - (int)h.y0) * 2 * q.n_interp;
-    const int off = atomicAdd(&a.info->row_alloc, need);
+    const int off = atomicAdd(a.pool_ctr, need);
     if (off >= 0 && off + need <= a.row_cap) {  // pool exhausted: the raster kernel walks the sums itself
       k.row_off = off;
       k.row_n = q.n_interp;
@@ -719,7 +723,7 @@ WRD bool wr_emit_quad(const SetupArgs& a, int idx, const QuadOut& q, int* unsupp
     // body vs fragment tail, interpolant sums): wr_depth_fail_rows records them row by row
     const int W = ((int)h.x1 - (int)h.x0 + 31) >> 5;
     const int need = ((int)h.y1 - (int)h.y0) * (W + 1);
-    const int off = atomicAdd(&a.info->fail_alloc, need);
+    const int off = atomicAdd(a.pool_ctr + 1, need);
     if (off >= 0 && off + need <= a.fail_cap) {
       k.fail_off = off;
       k.fail_w = W;

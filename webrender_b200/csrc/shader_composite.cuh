@@ -176,9 +176,8 @@ __device__ void wr_composite_check_rows(const SetupArgs& a, int idx) {
     }
   }
 }
-__global__ void wr_setup_composite(SetupArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) wr_reset_batch_info(a.info_next);
+__device__ __noinline__ void wr_setup_composite_block(const SetupArgs& a, int idx) {
+  if (idx == 0 && a.info_next) wr_reset_batch_info(a.info_next);
   if (a.warp_per_inst) {
     const int lane = threadIdx.x & 31;
     idx >>= 5;

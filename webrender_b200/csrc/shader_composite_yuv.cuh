@@ -368,7 +368,7 @@ WRD void wr_yuv_chain_table(const SetupArgs& a, int idx, int planes, const TexVi
   if (len < 4) return;
   const int nch = (len >> 2) + 1;
   const int need = 16 + 12 * nch;
-  const int off = atomicAdd(&a.info->row_alloc, need);
+  const int off = atomicAdd(a.pool_ctr, need);
   if (off < 0 || off + need > a.row_cap) return;  // pool exhausted: the raster kernel walks the sums itself
   // the first row's interpolants, as wr_row_interp computes them (rows = 0)
   float o[6], step[6];
@@ -477,9 +477,8 @@ WRD void wr_setup_composite_yuv_one(const SetupArgs& a, int idx) {
 #define WR_SETUP_KERNEL_YUV(name) WR_SETUP_KERNEL(name)
 #else
 #define WR_SETUP_KERNEL_YUV(name)                                                              \
-  __global__ void name(SetupArgs a) {                                                          \
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;                                           \
-    if (idx == 0) wr_reset_batch_info(a.info_next);                                            \
+  __device__ __noinline__ void name##_block(const SetupArgs& a, int idx) {                     \
+    if (idx == 0 && a.info_next) wr_reset_batch_info(a.info_next);                             \
     if (idx < a.n) name##_one(a, idx);                                                         \
     __syncwarp();                                                                              \
     wr_fill_row_tables_warp(a, idx);                                                           \

@@ -150,7 +150,7 @@ WRD float wr_sum_at(float base, float step, int m, bool exact) {
 // steps, clamp bounds and filter are already in `r`: prefix through the fallback filter, interior
 // through the selected filter, remainder through the fallback; plus the running-sum bases of the
 // first chunk >= tile_rel inside each segment.
-WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int tile_rel, bool coop = true) {
+WRD_SHARED void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int tile_rel, bool coop = true) {
   const int filter = r.filter;
   r.before = 0;
   r.inside = 0;
@@ -205,7 +205,7 @@ WRD void wr_tex_linear_partition(const TexView& t, TexRow& r, int body_len, int 
   }
 }
 
-WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sampler_filter, int body_len,
+WRD_SHARED void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sampler_filter, int body_len,
                           const float* u, const float* v, int tile_rel, TexRow& r,
                           int target_fmt = WRCU_FMT_RGBA8, bool coop = true) {
   r.body_len = body_len;
@@ -268,7 +268,7 @@ WRD void wr_tex_row_setup(const TexView& t, const float* bounds, bool use_sample
 
 // blendTextureLinearR8 (swgl_ext.h:634-650): R8 atlas through the fallback
 // bilinear filter, expanded to four lanes (glyph blit into an RGBA8 target).
-WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len, const float* u, const float* v,
+WRD_SHARED void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len, const float* u, const float* v,
                              int tile_rel, TexRow& r) {
   r.mode = TEX_NONE;
   r.body_len = 0;
@@ -292,7 +292,7 @@ WRD void wr_tex_row_setup_r8(const TexView& t, const float* bounds, int body_len
 }
 
 // Source texel (before colour modulation) of body pixel `rel` (0-based in the span).
-WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
+WRD_SHARED Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
   if (r.mode == TEX_NEAREST_FAST) {
     int sx = min(max(r.nix + rel, r.nminx), r.nmaxx);
     return wr_tex_load_any(t, r.nry, sx);
@@ -361,7 +361,7 @@ WRD Px wr_tex_body(const TexView& t, const TexRow& r, int rel) {
 }
 
 // texture(sampler2D, vec2) → float RGBA (texture.h:948-975), uv already clamped
-WRD void wr_tex_fragment(const TexView& t, float cu, float cv, float* out) {
+WRD_SHARED void wr_tex_fragment(const TexView& t, float cu, float cv, float* out) {
   if (t.fmt == WRCU_FMT_R8) {
     int rr;
     if (t.filter == WRCU_LINEAR) {

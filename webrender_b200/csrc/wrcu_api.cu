@@ -40,6 +40,34 @@ int wrcu_fail(wrcu_ctx* c, int code, const char* fmt, ...) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- deferred submission ---------------------------------------------------------------------------
+// wrcu_clear / wrcu_draw_batch queue their work; flush_pending runs the queue: one H2D copy of everything
+// staged since the last flush (tables, instances, the job table), ONE set-up launch over all queued batches
+// (wr_setup_multi), then the clears and raster launches in submission order.  A page is ~150 batches of a
+// few instances: with a launch pair per batch its frame time was 150 x the ~10 us latency chain of a set-up
+// kernel; now that chain is paid once.  Everything else in the ABI flushes first, so callers see the same
+// ordering as before.
+struct PendingOp {
+  int type = 0;                 // 0 = clear, 1 = batch
+  // clear
+  uint8_t* c_ptr = nullptr; int c_pitch = 0, c_fmt = 0; uint32_t c_val = 0;
+  uint8_t* d_ptr = nullptr; int d_pitch = 0; uint32_t d_val = 0;
+  int cx0 = 0, cy0 = 0, cx1 = 0, cy1 = 0;
+  // batch
+  int kind = 0, blend = 0, n = 0, sblocks = 0;
+  uint32_t features = 0;
+  unsigned grid_x = 0, grid_y = 0;
+  size_t bin_need = 0, inst_off = 0, views_off = (size_t)-1;
+  SetupArgs sa;
+  RasterArgs ra;
+};
+static std::vector<PendingOp>& pending(wrcu_ctx* c) {
+  if (!c->pending_ops) c->pending_ops = new std::vector<PendingOp>();
+  return *(std::vector<PendingOp>*)c->pending_ops;
+}
+
+static int flush_pending(wrcu_ctx* c);
+
 static int fmt_bpp(int fmt) {
   switch (fmt) {
     case WRCU_FMT_RGBA8: return 4;
@@ -63,7 +91,11 @@ static int fmt_bpp(int fmt) {
 
 // ---- small kernels ---------------------------------------------------------------
 WR_GLOBAL void wr_init_batch_info(BatchInfo* info, int n) {  // once, at context creation
+#ifdef WRCU_HOSTEMU
   for (int i = 0; i < n; i++) wr_reset_batch_info(info + i);
+#else
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) wr_reset_batch_info(info + i);
+#endif
 }
 
 // Clear (swgl/src/gl.cc:2498-2518 → clear_buffer): fills a rect of a 4-byte or
@@ -203,13 +235,19 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   cudaEventCreate(&c->t1);
   cudaEventCreate(&c->p0);
   cudaEventCreate(&c->p1);
-  if (cudaMalloc((void**)&c->batch_info, 4 * sizeof(BatchInfo)) != cudaSuccess ||
-      cudaMalloc((void**)&c->dev_err, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc((void**)&c->batch_info, 2 * (size_t)wrcu_ctx::QMAX * sizeof(BatchInfo)) != cudaSuccess ||
+      cudaMalloc((void**)&c->dev_err, sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&c->pool_ctr, 4 * sizeof(int)) != cudaSuccess) {
     delete c;
     return WRCU_ERR_OOM;
   }
   cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
-  WR_LAUNCH(wr_init_batch_info, 1, 1, c->stream, (BatchInfo*)c->batch_info, 4);
+  cudaMemsetAsync(c->pool_ctr, 0, 4 * sizeof(int), c->stream);
+  WR_LAUNCH(wr_init_batch_info, 8, 128, c->stream, (BatchInfo*)c->batch_info, 2 * wrcu_ctx::QMAX);
+  {
+    const char* e = getenv("WRCU_IMMEDIATE");
+    c->immediate = e && atoi(e) != 0;
+  }
 #ifndef WRCU_HOSTEMU
   {  // TMA tensor maps: encoder entry point from the driver (no libcuda link), device table of records
     void* fn = nullptr;
@@ -247,6 +285,7 @@ static void sig_forget(const uint32_t* base, int count);
 extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  flush_pending(c);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < wrcu_ctx::MAX_TEX; i++) {
     if (!c->tex[i].live) continue;
@@ -271,6 +310,8 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->cmd_hot) cudaFree(c->cmd_hot);
   if (c->cmd_cold) cudaFree(c->cmd_cold);
   if (c->batch_info) cudaFree(c->batch_info);
+  if (c->pool_ctr) cudaFree(c->pool_ctr);
+  delete (std::vector<PendingOp>*)c->pending_ops;
   if (c->row_tab) cudaFree(c->row_tab);
   if (c->tmaps_dev) cudaFree(c->tmaps_dev);
   if (c->fail_pool) cudaFree(c->fail_pool);
@@ -300,6 +341,7 @@ extern "C" const char* wrcu_last_error_string(wrcu_ctx* c) { return c ? c->err :
 
 static int sync_and_check(wrcu_ctx* c);
 extern "C" int wrcu_finish(wrcu_ctx* c) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   cudaSetDevice(c->device);
   int rc = sync_and_check(c);
   if (c->copy_stream) WRCU_CUDA(c, cudaStreamSynchronize(c->copy_stream));
@@ -307,6 +349,7 @@ extern "C" int wrcu_finish(wrcu_ctx* c) {
 }
 
 extern "C" int wrcu_stream(wrcu_ctx* c, void** stream) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   *stream = (void*)c->stream;
   return WRCU_OK;
 }
@@ -315,10 +358,20 @@ extern "C" int wrcu_stream(wrcu_ctx* c, void** stream) {
 // Stage `bytes` of host data for the device: copy into the pinned arena (so the
 // caller may free its buffer on return) and queue the H2D copy on the stream.
 // Reserve `bytes` in the current arena (host and device side at the same offset).
+static int flush_pending(wrcu_ctx* c);
+static void mark_dirty(wrcu_ctx* c, size_t lo, size_t hi) {
+  if (c->dirty_hi <= c->dirty_lo) { c->dirty_lo = lo; c->dirty_hi = hi; return; }
+  if (lo < c->dirty_lo) c->dirty_lo = lo;
+  if (hi > c->dirty_hi) c->dirty_hi = hi;
+}
 static int arena_reserve(wrcu_ctx* c, size_t bytes, size_t* off_out) {
   Arena* a = &c->arena[c->cur_arena];
   size_t off = align_up(a->used, 256);
   if (off + bytes > a->cap) {
+    // queued batches hold pointers into this arena: run them before it moves
+    { int rcf = flush_pending(c); if (rcf != WRCU_OK) return rcf; }
+    a = &c->arena[c->cur_arena];
+    off = align_up(a->used, 256);
     // grow: finish outstanding work, then reallocate this arena larger
     WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
     size_t ncap = align_up((off + bytes) * 2, 1u << 20);
@@ -353,7 +406,10 @@ static int arena_reserve(wrcu_ctx* c, size_t bytes, size_t* off_out) {
 // wrcu_host_alloc buffer stays busy until a fence taken after the call (wrcu_fence_insert) has been
 // waited on.  Instances, tables and texture lists are ALWAYS copied into the arena before the call
 // returns (glBufferData ownership, include/wrcu.h conventions).
-static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out, bool zero_copy_ok = false) {
+// `defer`: the data is only read by kernels launched from flush_pending — no copy of its own, the arena range
+// [dirty_lo, dirty_hi) goes to the device in ONE cudaMemcpyAsync there (a page's 150 instance arrays and its
+// tables travel together instead of as 150 copy-engine operations).
+static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out, bool zero_copy_ok = false, bool defer = false) {
   size_t off = 0;
   int rc = arena_reserve(c, bytes, &off);
   if (rc != WRCU_OK) return rc;
@@ -368,7 +424,8 @@ static int stage(wrcu_ctx* c, const void* src, size_t bytes, void** dev_out, boo
     WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, src, bytes, cudaMemcpyHostToDevice, c->stream));
   } else {
     memcpy(a->host + off, src, bytes);
-    WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (defer) mark_dirty(c, off, off + bytes);
+    else WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, bytes, cudaMemcpyHostToDevice, c->stream));
   }
   c->stats.h2d_bytes += bytes;
   *dev_out = a->dev + off;
@@ -460,6 +517,7 @@ extern "C" int wrcu_texture_set_filter(wrcu_ctx* c, wrcu_tex id, int filter) {
 
 extern "C" int wrcu_texture_upload(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, int h,
                                    const void* data, size_t src_stride) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture* t = get_tex(c, id);
   if (!t || !data || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
     return wrcu_fail(c, WRCU_ERR_INVALID, "texture_upload: bad arguments");
@@ -488,6 +546,7 @@ extern "C" int wrcu_texture_upload(wrcu_ctx* c, wrcu_tex id, int x, int y, int w
 }
 
 extern "C" int wrcu_texture_destroy(wrcu_ctx* c, wrcu_tex id) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture* t = get_tex(c, id);
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_destroy: bad handle");
   cudaSetDevice(c->device);
@@ -503,6 +562,7 @@ extern "C" int wrcu_texture_destroy(wrcu_ctx* c, wrcu_tex id) {
 }
 
 extern "C" int wrcu_texture_device_ptr(wrcu_ctx* c, wrcu_tex id, void** dptr, size_t* pitch) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture* t = get_tex(c, id);
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_device_ptr: bad handle");
   *dptr = t->dptr;
@@ -518,7 +578,8 @@ static int sync_and_check(wrcu_ctx* c) {
   WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
   if (n >= (1 << 20)) {
     cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
-    return wrcu_fail(c, WRCU_ERR_CUDA, "wrcu_peer_wait: a peer did not signal within 2 s (%d wait(s) timed out)", n >> 20);
+    return wrcu_fail(c, WRCU_ERR_CUDA, "wrcu_peer_wait: a peer did not signal within 2 s (%d wait(s) timed out; counter 0x%x, "
+                     "%d polling waits and %d event waits queued by this context)", n >> 20, n, c->n_wait_kernel, c->n_wait_event);
   }
   if (n) {
     cudaMemsetAsync(c->dev_err, 0, sizeof(int), c->stream);
@@ -530,6 +591,7 @@ static int sync_and_check(wrcu_ctx* c) {
 
 extern "C" int wrcu_read_pixels(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, int h, void* out,
                                 size_t dst_stride) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture* t = get_tex(c, id);
   if (!t || !out || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
     return wrcu_fail(c, WRCU_ERR_INVALID, "read_pixels: bad arguments");
@@ -550,6 +612,7 @@ extern "C" int wrcu_host_alloc(wrcu_ctx* c, size_t bytes, void** out) {
   return WRCU_OK;
 }
 extern "C" int wrcu_host_free(wrcu_ctx* c, void* ptr) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   if (!ptr) return WRCU_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);  // a staged copy may still be reading it
@@ -571,6 +634,7 @@ static int wait_fence(wrcu_ctx* c, uint64_t fence, bool on_stream) {
 
 extern "C" int wrcu_read_pixels_async(wrcu_ctx* c, wrcu_tex id, int x, int y, int w, int h, void* out,
                                       size_t dst_stride, uint64_t* fence) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture* t = get_tex(c, id);
   if (!t || !out || !fence || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > t->w || y + h > t->h)
     return wrcu_fail(c, WRCU_ERR_INVALID, "read_pixels_async: bad arguments");
@@ -604,6 +668,7 @@ static int ensure_copy_stream(wrcu_ctx* c) {
 // glFenceSync on the draw stream: everything queued so far (uploads reading wrcu_host_alloc memory
 // included) has completed once wrcu_fence_wait(fence) returns.
 extern "C" int wrcu_fence_insert(wrcu_ctx* c, uint64_t* fence) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   if (!fence) return wrcu_fail(c, WRCU_ERR_INVALID, "fence_insert: null fence");
   cudaSetDevice(c->device);
   int rc = ensure_copy_stream(c);
@@ -627,6 +692,7 @@ extern "C" int wrcu_fence_wait(wrcu_ctx* c, uint64_t fence) {
 // ---- update path ---------------------------------------------------------------------
 extern "C" int wrcu_texture_upload_batch(wrcu_ctx* c, wrcu_tex id, const wrcu_upload_rect* rects, size_t n,
                                          const void* staging, size_t staging_bytes) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture* t = get_tex(c, id);
   if (!t || (n && (!rects || !staging))) return wrcu_fail(c, WRCU_ERR_INVALID, "texture_upload_batch: bad arguments");
   if (!n) return WRCU_OK;
@@ -666,6 +732,7 @@ extern "C" int wrcu_texture_upload_batch(wrcu_ctx* c, wrcu_tex id, const wrcu_up
 }
 
 extern "C" int wrcu_texture_copy(wrcu_ctx* c, wrcu_tex src, wrcu_tex dst, const int32_t r[4], int dx, int dy) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture *s = get_tex(c, src), *d = get_tex(c, dst);
   if (!s || !d || !r || s->bpp != d->bpp || r[2] <= 0 || r[3] <= 0 || r[0] < 0 || r[1] < 0 || r[0] + r[2] > s->w ||
       r[1] + r[3] > s->h || dx < 0 || dy < 0 || dx + r[2] > d->w || dy + r[3] > d->h)
@@ -679,6 +746,7 @@ extern "C" int wrcu_texture_copy(wrcu_ctx* c, wrcu_tex src, wrcu_tex dst, const 
 
 extern "C" int wrcu_gpu_cache_update(wrcu_ctx* c, int height, int clear, const wrcu_gpu_cache_copy* updates,
                                      size_t n_updates, const float* blocks, size_t n_blocks) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   if (height <= 0 || height > 65536 || (n_updates && (!updates || !blocks)))
     return wrcu_fail(c, WRCU_ERR_INVALID, "gpu_cache_update: bad arguments");
   cudaSetDevice(c->device);
@@ -781,6 +849,7 @@ static IRect irect_intersect(IRect a, IRect b) {
 }
 extern "C" int wrcu_composite_blit(wrcu_ctx* c, wrcu_tex dst_id, wrcu_tex src_id, const int32_t sr[4], const int32_t dr[4],
                                    int opaque, int flip_x, int flip_y, int filter_linear, const int32_t cr[4]) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WrTexture *d = get_tex(c, dst_id), *s = get_tex(c, src_id);
   if (!d || !s || !sr || !dr || !cr || d->fmt != WRCU_FMT_RGBA8 || s->fmt != WRCU_FMT_RGBA8)
     return wrcu_fail(c, WRCU_ERR_INVALID, "composite_blit: needs two RGBA8 textures and three rects");
@@ -1013,6 +1082,7 @@ extern "C" int wrcu_peer_flags_open(wrcu_ctx* c, const wrcu_ipc_flags* in, int* 
 }
 
 extern "C" int wrcu_peer_signal(wrcu_ctx* c, int peer_id, int slot, uint32_t value) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   if (peer_id < 0 || peer_id >= (int)c->peers.size() || slot < 0 || slot >= c->peers[peer_id].count)
     return wrcu_fail(c, WRCU_ERR_INVALID, "peer_signal: bad arguments");
   cudaSetDevice(c->device);
@@ -1039,6 +1109,7 @@ extern "C" int wrcu_peer_signal(wrcu_ctx* c, int peer_id, int slot, uint32_t val
 }
 
 extern "C" int wrcu_peer_wait(wrcu_ctx* c, int slot, uint32_t value) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   if (!c->flags || slot < 0 || slot >= c->n_flags) return wrcu_fail(c, WRCU_ERR_INVALID, "peer_wait: bad arguments");
   cudaSetDevice(c->device);
 #ifndef WRCU_HOSTEMU
@@ -1047,10 +1118,12 @@ extern "C" int wrcu_peer_wait(wrcu_ctx* c, int slot, uint32_t value) {
     auto it = g_sig.find((uintptr_t)(c->flags + slot));
     if (it != g_sig.end() && it->second.ev && (int32_t)(it->second.value - value) >= 0) {
       WRCU_CUDA(c, cudaStreamWaitEvent(c->stream, it->second.ev, 0));
+      c->n_wait_event++;
       return WRCU_OK;
     }
   }
   wr_flag_wait<<<1, 1, 0, c->stream>>>(c->flags + slot, value, c->dev_err);
+  c->n_wait_kernel++;
   c->stats.kernel_launches++;
   WRCU_CUDA(c, cudaGetLastError());
 #endif
@@ -1061,6 +1134,7 @@ extern "C" int wrcu_peer_wait(wrcu_ctx* c, int slot, uint32_t value) {
 extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
   if (!t) return wrcu_fail(c, WRCU_ERR_INVALID, "frame_begin: null tables");
   cudaSetDevice(c->device);
+  { int rcf = flush_pending(c); if (rcf != WRCU_OK) return rcf; }
   // Uploads and GPU-cache updates issued since the last wrcu_frame_end (Renderer::render runs
   // update_texture_cache / update_gpu_cache before draw_frame) were staged into the outgoing arena
   // AFTER its `done` event was recorded: re-record it so the next reuse of that arena waits for them
@@ -1100,7 +1174,7 @@ extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
     if (rc != WRCU_OK) return rc;
     for (int i = 0; i < 7; i++)
       if (td[i].texels) memcpy(a->host + off + td[i].off, td[i].src, td[i].texels * 16);
-    WRCU_CUDA(c, cudaMemcpyAsync(a->dev + off, a->host + off, total, cudaMemcpyHostToDevice, c->stream));
+    mark_dirty(c, off, off + total);  // copied with the first submission's instances (flush_pending)
     c->stats.h2d_bytes += total;
     dbase = a->dev + off;
   }
@@ -1127,6 +1201,7 @@ extern "C" int wrcu_frame_begin(wrcu_ctx* c, const wrcu_frame_tables* t) {
 
 extern "C" int wrcu_frame_end(wrcu_ctx* c) {
   cudaSetDevice(c->device);
+  { int rcf = flush_pending(c); if (rcf != WRCU_OK) return rcf; }
   Arena* a = &c->arena[c->cur_arena];
   WRCU_CUDA(c, cudaEventRecord(a->done, c->stream));
   a->in_flight = true;
@@ -1181,23 +1256,40 @@ extern "C" int wrcu_clear(wrcu_ctx* c, const int32_t rect[4], const float color[
     y1 = rect[1] + rect[3] < t->h ? rect[1] + rect[3] : t->h;
   }
   if (x1 <= x0 || y1 <= y0) return WRCU_OK;
-  dim3 grid((unsigned)((x1 - x0 + 1023) / 1024), (unsigned)(y1 - y0));
-  if (grid.x > 8) grid.x = 8;
+  // queued in order with the batches (flush_pending): a clear between two batches of a submission must stay there
+  PendingOp op;
+  op.type = 0;
+  op.cx0 = x0; op.cy0 = y0; op.cx1 = x1; op.cy1 = y1;
   if (color) {
     // ClearTexSubImage: round_pixel, truncating U8 convert, BGRA swizzle (gl.cc:2426-2481)
     uint32_t r = host_round_pixel(color[0]) & 0xFF, g = host_round_pixel(color[1]) & 0xFF;
     uint32_t b = host_round_pixel(color[2]) & 0xFF, a = host_round_pixel(color[3]) & 0xFF;
-    if (t->fmt == WRCU_FMT_RGBA8)
-      WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, t->dptr, (int)t->pitch, x0, y0, x1, y1,
-                                               b | (g << 8) | (r << 16) | (a << 24));
-    else
-      WR_LAUNCH(wr_clear_u8, grid, 256, c->stream, t->dptr, (int)t->pitch, x0, y0, x1, y1, (uint8_t)r);
-    c->stats.kernel_launches++;
+    op.c_ptr = t->dptr; op.c_pitch = (int)t->pitch; op.c_fmt = t->fmt;
+    op.c_val = t->fmt == WRCU_FMT_RGBA8 ? (b | (g << 8) | (r << 16) | (a << 24)) : r;
   }
   if (depth && c->depth_tex) {
     WrTexture* d = get_tex(c, c->depth_tex);
-    uint32_t z = (uint32_t)((double)*depth * 0xFFFFFF);  // gl.cc:2391
-    WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, d->dptr, (int)d->pitch, x0, y0, x1, y1, z);
+    op.d_ptr = d->dptr; op.d_pitch = (int)d->pitch;
+    op.d_val = (uint32_t)((double)*depth * 0xFFFFFF);  // gl.cc:2391
+  }
+  if (!op.c_ptr && !op.d_ptr) return WRCU_OK;
+  pending(c).push_back(op);
+  if (pending(c).size() >= (size_t)wrcu_ctx::QMAX || c->immediate) return flush_pending(c);
+  return WRCU_OK;
+}
+
+static int launch_clear(wrcu_ctx* c, const PendingOp& op) {
+  dim3 grid((unsigned)((op.cx1 - op.cx0 + 1023) / 1024), (unsigned)(op.cy1 - op.cy0));
+  if (grid.x > 8) grid.x = 8;
+  if (op.c_ptr) {
+    if (op.c_fmt == WRCU_FMT_RGBA8)
+      WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, op.c_ptr, op.c_pitch, op.cx0, op.cy0, op.cx1, op.cy1, op.c_val);
+    else
+      WR_LAUNCH(wr_clear_u8, grid, 256, c->stream, op.c_ptr, op.c_pitch, op.cx0, op.cy0, op.cx1, op.cy1, (uint8_t)op.c_val);
+    c->stats.kernel_launches++;
+  }
+  if (op.d_ptr) {
+    WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, op.d_ptr, op.d_pitch, op.cx0, op.cy0, op.cx1, op.cy1, op.d_val);
     c->stats.kernel_launches++;
   }
   WRCU_CUDA(c, cudaGetLastError());
@@ -1279,12 +1371,11 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       if (!views[(size_t)i].ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "draw_composite_tiles: instance %d has no texture", i);
     }
     void* dviews = nullptr;
-    if ((rc = stage(c, views.data(), views.size() * sizeof(TexView), &dviews)) != WRCU_OK) return rc;
+    if ((rc = stage(c, views.data(), views.size() * sizeof(TexView), &dviews, false, true)) != WRCU_OK) return rc;
     views_off = (size_t)((uint8_t*)dviews - c->arena[c->cur_arena].dev);
   }
   void* dinst = nullptr;
-  if ((rc = stage(c, instances, stride * (size_t)n, &dinst)) != WRCU_OK) return rc;
-  if ((rc = ensure_cmd_capacity(c, (size_t)n)) != WRCU_OK) return rc;
+  if ((rc = stage(c, instances, stride * (size_t)n, &dinst, false, true)) != WRCU_OK) return rc;
 
   TargetDev T;
   memset(&T, 0, sizeof T);
@@ -1311,19 +1402,12 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
 
   SetupArgs sa;
   memset(&sa, 0, sizeof sa);
-  sa.tabs = c->tables;
   sa.tgt = T;
-  sa.instances = (const uint8_t*)dinst;
+  const size_t inst_off = (size_t)((uint8_t*)dinst - c->arena[c->cur_arena].dev);  // pointers are resolved at flush
   sa.stride = (int)stride;
   sa.n = n;
-  sa.hot = (CmdHot*)c->cmd_hot;
-  sa.cold = (CmdCold*)c->cmd_cold;
-  BatchInfo* info_cur = (BatchInfo*)c->batch_info + (c->draw_seq & 3);
-  sa.info = info_cur;
-  sa.info_next = (BatchInfo*)c->batch_info + ((c->draw_seq + 1) & 3);
+  // (hot / cold / info / pool pointers are assigned when the submission is flushed)
   sa.err_counter = c->dev_err;
-  sa.row_tab = c->row_tab;
-  sa.row_cap = c->row_cap;
   sa.blend_enabled = st->blend != WRCU_BLEND_NONE;
 #ifndef WRCU_HOSTEMU
   {
@@ -1385,10 +1469,8 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   sa.color0 = tex_view(c, st->color[0]);
   sa.color1 = tex_view(c, st->color[1]);
   sa.color2 = tex_view(c, st->color[2]);
-  if (textures) {
-    sa.tex_list = (const TexView*)(c->arena[c->cur_arena].dev + views_off);  // (the arena may have grown since)
-    sa.color0 = tex_view(c, textures[0]);
-  }
+  if (textures) sa.color0 = tex_view(c, textures[0]);  // (sa.tex_list: resolved from views_off at flush)
+  size_t bin_need = 0;
   // Bitmask bins for batches with many instances: the per-tile command scan of the raster
   // kernel costs tiles x n hot records of L2 traffic; with bins it reads n/32 words per tile.
   {
@@ -1397,20 +1479,10 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     const size_t any_words = ((size_t)tiles_x * tiles_y + 31) / 32;
     const size_t need = ((size_t)tiles_x * tiles_y + 1) * words + any_words + 1;  // + the wide mask + the tile-any bitmap
     if (n >= 512 && need * 4 <= (size_t)96 << 20) {
-      if (need > c->bin_cap_words) {
-        WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (c->bin_mask) cudaFree(c->bin_mask);
-        c->bin_mask = nullptr;
-        c->bin_cap_words = 0;
-        WRCU_CUDA(c, cudaMalloc((void**)&c->bin_mask, need * 4 * 2));
-        c->bin_cap_words = need * 2;
-      }
-      WRCU_CUDA(c, cudaMemsetAsync(c->bin_mask, 0, need * 4, c->stream));
-      sa.tile_mask = c->bin_mask;
-      sa.wide_mask = c->bin_mask + (size_t)tiles_x * tiles_y * words;
+      // pointers into the submission's bin area are assigned at flush (PendingOp::bin_need)
+      bin_need = need;
       sa.bin_words = (int)words;
       sa.bin_tiles_x = tiles_x;
-      sa.tile_any = sa.wide_mask + words;
       sa.any_words = (int)any_words;
     }
   }
@@ -1426,11 +1498,11 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   switch (kind) {
     case WRCU_KIND_QUAD_TEXTURED:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "quad instance stride < 16");
-      WR_LAUNCH(wr_setup_quad_textured, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_quad_textured, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_SOLID:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
-      WR_LAUNCH(wr_setup_brush_solid, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_solid, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_IMAGE:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
@@ -1438,53 +1510,53 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
         return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "brush_image DUAL_SOURCE_BLENDING variant not built (SWGL does not build it either)");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_image without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_brush_image, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_image, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       sa.features = features;
-      WR_LAUNCH(wr_setup_brush_linear_gradient, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_linear_gradient, run by flush_pending */;
       break;
     case WRCU_KIND_TEXT_RUN:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "ps_text_run without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_text_run, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_text_run, run by flush_pending */;
       break;
     case WRCU_KIND_QUAD_MASK:
       if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "MaskInstance stride < 32");
       sa.features = features;
-      WR_LAUNCH(wr_setup_quad_mask, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_quad_mask, run by flush_pending */;
       break;
     case WRCU_KIND_CLIP_RECTANGLE:
       if (stride < 200) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceRect stride < 200");
       sa.features = features;
-      WR_LAUNCH(wr_setup_clip_rectangle, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_clip_rectangle, run by flush_pending */;
       break;
     case WRCU_KIND_SCALE:
       if (stride < 36) return wrcu_fail(c, WRCU_ERR_INVALID, "ScalingInstance stride < 36");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "cs_scale without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_scale, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_scale, run by flush_pending */;
       break;
     case WRCU_KIND_QUAD_RADIAL_GRADIENT:
     case WRCU_KIND_QUAD_CONIC_GRADIENT:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       sa.features = features;
       sa.kind = kind;
-      WR_LAUNCH(wr_setup_quad_gradient, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_quad_gradient, run by flush_pending */;
       break;
     case WRCU_KIND_LINE_DECORATION:
       if (stride < 36) return wrcu_fail(c, WRCU_ERR_INVALID, "LineDecorationJob stride < 36");
       sa.features = features;
-      WR_LAUNCH(wr_setup_line_decoration, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_line_decoration, run by flush_pending */;
       break;
     case WRCU_KIND_BORDER_SOLID:
     case WRCU_KIND_BORDER_SEGMENT:
       if (stride < 108) return wrcu_fail(c, WRCU_ERR_INVALID, "BorderInstance stride < 108");
       sa.features = features;
       sa.kind = kind;
-      WR_LAUNCH(wr_setup_border, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_border, run by flush_pending */;
       break;
     case WRCU_KIND_FAST_LINEAR_GRADIENT:
     case WRCU_KIND_LINEAR_GRADIENT:
@@ -1494,7 +1566,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
         return wrcu_fail(c, WRCU_ERR_INVALID, "gradient task instance stride too small");
       sa.features = features;
       sa.kind = kind;
-      WR_LAUNCH(wr_setup_cs_gradient, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_cs_gradient, run by flush_pending */;
       break;
     case WRCU_KIND_BLUR:
       if (stride < 24) return wrcu_fail(c, WRCU_ERR_INVALID, "BlurInstance stride < 24");
@@ -1502,70 +1574,65 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
       if (!(features & (WRCU_FEAT_ALPHA_TARGET | WRCU_FEAT_COLOR_TARGET)))
         return wrcu_fail(c, WRCU_ERR_INVALID, "cs_blur needs ALPHA_TARGET or COLOR_TARGET");
       sa.features = features;
-      WR_LAUNCH(wr_setup_blur, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_blur, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_MIX_BLEND:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr || !sa.color1.ptr)
         return wrcu_fail(c, WRCU_ERR_INVALID, "brush_mix_blend needs sColor0 (backdrop) and sColor1 (source)");
       sa.features = features;
-      WR_LAUNCH(wr_setup_brush_mix_blend, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_mix_blend, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_BLEND:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_blend without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_brush_blend, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_blend, run by flush_pending */;
       break;
     case WRCU_KIND_CLEAR:
       if (stride < 32) return wrcu_fail(c, WRCU_ERR_INVALID, "ClearInstance stride < 32");
-      WR_LAUNCH(wr_setup_clear, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_clear, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_OPACITY:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_opacity without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_brush_opacity, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_opacity, run by flush_pending */;
       break;
     case WRCU_KIND_SPLIT_COMPOSITE:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr || sa.color0.fmt != WRCU_FMT_RGBA8)
         return wrcu_fail(c, WRCU_ERR_INVALID, "ps_split_composite needs an RGBA8 surface in sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_split_composite, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_split_composite, run by flush_pending */;
       break;
     case WRCU_KIND_BRUSH_YUV_IMAGE:
       if (stride < 16) return wrcu_fail(c, WRCU_ERR_INVALID, "prim instance stride < 16");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "brush_yuv_image without sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_brush_yuv_image, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_brush_yuv_image, run by flush_pending */;
       break;
     case WRCU_KIND_COMPOSITE:
       if (stride < 120) return wrcu_fail(c, WRCU_ERR_INVALID, "CompositeInstance stride < 120");
       if (!sa.color0.ptr) return wrcu_fail(c, WRCU_ERR_INVALID, "composite without sColor0");
       sa.features = features;
-      if (features & WRCU_FEAT_YUV) WR_LAUNCH(wr_setup_composite_yuv, sblocks, 128, c->stream, sa);
-      else WR_LAUNCH(wr_setup_composite, sblocks, 128, c->stream, sa);
+      if (features & WRCU_FEAT_YUV) /* set-up: wr_setup_composite_yuv, run by flush_pending */;
+      else /* set-up: wr_setup_composite, run by flush_pending */;
       break;
     case WRCU_KIND_CLIP_BOX_SHADOW:
       if (stride < 84) return wrcu_fail(c, WRCU_ERR_INVALID, "ClipMaskInstanceBoxShadow stride < 84");
       if (!sa.color0.ptr || sa.color0.fmt != WRCU_FMT_R8)
         return wrcu_fail(c, WRCU_ERR_INVALID, "cs_clip_box_shadow needs an R8 shadow mask in sColor0");
       sa.features = features;
-      WR_LAUNCH(wr_setup_clip_box_shadow, sblocks, 128, c->stream, sa);
+      /* set-up: wr_setup_clip_box_shadow, run by flush_pending */;
       break;
     default:
       return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "draw_batch: kind %d not implemented", kind);
   }
-  c->draw_seq++;  // only once the setup kernel (which re-arms the next record) is queued
-  c->stats.kernel_launches++;
 
   RasterArgs ra;
   memset(&ra, 0, sizeof ra);
   ra.tgt = T;
-  ra.hot = (const CmdHot*)c->cmd_hot;
-  ra.cold = (const CmdCold*)c->cmd_cold;
-  ra.info = info_cur;
   ra.n = n;
   ra.blend = st->blend;
   ra.depth_mode = T.depth ? st->depth : WRCU_DEPTH_OFF;
@@ -1574,26 +1641,46 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   ra.color0 = sa.color0;
   ra.color1 = sa.color1;
   ra.color2 = sa.color2;
-  ra.row_tab = c->row_tab;
-  ra.gbuf_f = c->tables.gpu_buffer_f;
-  ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
-  ra.gpu_cache = c->tables.gpu_cache;
-  ra.tile_mask = sa.tile_mask;
-  ra.wide_mask = sa.wide_mask;
   ra.bin_words = sa.bin_words;
-  ra.tile_any = sa.tile_any;
   ra.any_words = sa.any_words;
   ra.bin_tiles_x = sa.bin_tiles_x;
-  ra.n_gpu_cache = c->tables.n_gpu_cache;
   ra.tmaps = c->tmaps_dev;
   ra.tmap_acquire = c->tmap_wrapped ? 1 : 0;
   dim3 grid((unsigned)((T.cx1 - 0 + WRCU_TILE_W - 1) / WRCU_TILE_W), (unsigned)((T.cy1 + WRCU_TILE_H - 1) / WRCU_TILE_H));
   if (grid.x == 0 || grid.y == 0) return WRCU_OK;
+  // ---- queue the batch: its set-up runs with every other queued batch's in ONE launch (flush_pending) ----
+  PendingOp op;
+  op.type = 1;
+  op.kind = kind;
+  op.features = features;
+  op.blend = st->blend;
+  op.n = n;
+  op.sblocks = sblocks;
+  op.bin_need = bin_need;
+  op.sa = sa;
+  op.ra = ra;
+  op.inst_off = inst_off;
+  op.views_off = textures ? views_off : (size_t)-1;
+  op.grid_x = grid.x;
+  op.grid_y = grid.y;
+  pending(c).push_back(op);
+  c->pend_instances += (size_t)n;
+  if (pending(c).size() >= (size_t)wrcu_ctx::QMAX || c->immediate) return flush_pending(c);
+  return WRCU_OK;
+}
+
+// The raster launches of one queued batch (its set-up has run): depth-run prepass, then the kernel(s) of its kind.
+static int launch_raster(wrcu_ctx* c, PendingOp& op) {
+  RasterArgs& ra = op.ra;
+  const TargetDev& T = ra.tgt;
+  const int kind = op.kind, n = op.n;
+  const uint32_t features = op.features;
+  dim3 grid(op.grid_x, op.grid_y);
   // Device-side dispatch: the setup kernel decides whether the whole batch is
   // plain solid quads; the specialised and the generic kernel each return at
   // once when it is not their turn (the host never has to wait for the flag).
 #ifndef WRCU_HOSTEMU
-  if (sa.depth_runs) {
+  if (op.sa.depth_runs) {
     // depth runs: the failing-sample bitmaps of this batch, before any of its depth writes
     ra.fail_pool = c->fail_pool;
     wr_depth_fail_rows<<<c->sm_count * 4, 256, 0, c->stream>>>(ra, c->fail_pool);
@@ -1601,7 +1688,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   }
 #endif
   if (c->profile) WRCU_CUDA(c, cudaEventRecord(c->p0, c->stream));
-  bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
+  bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && op.blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
                  ra.depth_mode == WRCU_DEPTH_OFF &&
                  (kind == WRCU_KIND_QUAD_TEXTURED || kind == WRCU_KIND_BRUSH_SOLID);  // the only kinds that emit CMD_CONST_COLOR
   ra.fast_eligible = fast_ok ? 1 : 0;
@@ -1662,7 +1749,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
 #else
 #define LAUNCH_RASTER_RUNS(S)                                                    \
   do {                                                                           \
-    if (sa.depth_runs && T.fmt == WRCU_FMT_RGBA8) {                              \
+    if (op.sa.depth_runs && T.fmt == WRCU_FMT_RGBA8) {                              \
       auto k_runs = wr_raster<S, WRCU_FMT_RGBA8, true>;                           \
       WR_LAUNCH(k_runs, pgrid, WRCU_THREADS, c->stream, ra);                     \
     } else LAUNCH_RASTER(S);                                                     \
@@ -1683,7 +1770,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     case WRCU_KIND_COMPOSITE:
       if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
 #ifndef WRCU_HOSTEMU
-      if (c->tmaps_dev && T.tmap_id && sa.copy_ok) {
+      if (c->tmaps_dev && T.tmap_id && op.sa.copy_ok) {
         // copy-class tile lists (decided on the device, BatchInfo::all_copy) go through the copy engine;
         // whichever of the two kernels is not in charge returns at once
         const size_t smem0 = (size_t)WR_TMA_STAGES * WR_TMA_BOX_BYTES, smem1 = (size_t)WR_TMA_BLEND_STAGES * 2 * WR_TMA_BOX_BYTES;
@@ -1693,7 +1780,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
           c->copy_attr_set = true;
         }
         ra.copy_eligible = 1;
-        if (st->blend == WRCU_BLEND_NONE) wr_composite_copy<false><<<c->sm_count * 3, WR_TMA_THREADS, smem0, c->stream>>>(ra);
+        if (op.blend == WRCU_BLEND_NONE) wr_composite_copy<false><<<c->sm_count * 3, WR_TMA_THREADS, smem0, c->stream>>>(ra);
         else wr_composite_copy<true><<<c->sm_count * 2, WR_TMA_THREADS, smem1, c->stream>>>(ra);
         c->stats.kernel_launches++;
       }
@@ -1724,6 +1811,207 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     c->profile_valid = true;
   }
   WRCU_CUDA(c, cudaGetLastError());
+  return WRCU_OK;
+}
+
+
+// ---- one set-up launch for every queued batch ---------------------------------------------------------
+struct __align__(16) SetupJob {
+  SetupArgs a;
+  int kind;
+  uint32_t features;
+  int first_block;   // of this job in the launch
+  int pad;
+};
+#ifndef WRCU_HOSTEMU
+__global__ void __launch_bounds__(128) wr_setup_multi(const SetupJob* jobs, const int* block_job, BatchInfo* reset, int n_reset,
+                                                      int* reset_ctr) {
+  __shared__ SetupJob sj;
+  if (blockIdx.x == 0) {  // re-arm the records the NEXT submission will use (the other half of the ring)
+    for (int i = threadIdx.x; i < n_reset; i += blockDim.x) wr_reset_batch_info(reset + i);
+    if (threadIdx.x < 2) reset_ctr[threadIdx.x] = 0;
+  }
+  const int j = __ldg(block_job + blockIdx.x);
+  {
+    const uint4* src = (const uint4*)(jobs + j);
+    uint4* dst = (uint4*)&sj;
+    for (int i = threadIdx.x; i < (int)(sizeof(SetupJob) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const SetupArgs& a = sj.a;
+  const int idx = ((int)blockIdx.x - sj.first_block) * (int)blockDim.x + (int)threadIdx.x;
+  switch (sj.kind) {
+    case WRCU_KIND_QUAD_TEXTURED: wr_setup_quad_textured_block(a, idx); break;
+    case WRCU_KIND_QUAD_MASK: wr_setup_quad_mask_block(a, idx); break;
+    case WRCU_KIND_BRUSH_SOLID: wr_setup_brush_solid_block(a, idx); break;
+    case WRCU_KIND_BRUSH_IMAGE: wr_setup_brush_image_block(a, idx); break;
+    case WRCU_KIND_BRUSH_LINEAR_GRADIENT: wr_setup_brush_linear_gradient_block(a, idx); break;
+    case WRCU_KIND_BRUSH_BLEND: wr_setup_brush_blend_block(a, idx); break;
+    case WRCU_KIND_BRUSH_MIX_BLEND: wr_setup_brush_mix_blend_block(a, idx); break;
+    case WRCU_KIND_BRUSH_OPACITY: wr_setup_brush_opacity_block(a, idx); break;
+    case WRCU_KIND_TEXT_RUN: wr_setup_text_run_block(a, idx); break;
+    case WRCU_KIND_CLIP_RECTANGLE: wr_setup_clip_rectangle_block(a, idx); break;
+    case WRCU_KIND_CLIP_BOX_SHADOW: wr_setup_clip_box_shadow_block(a, idx); break;
+    case WRCU_KIND_COMPOSITE:
+      if (sj.features & WRCU_FEAT_YUV) wr_setup_composite_yuv_block(a, idx);
+      else wr_setup_composite_block(a, idx);
+      break;
+    case WRCU_KIND_CLEAR: wr_setup_clear_block(a, idx); break;
+    case WRCU_KIND_BLUR: wr_setup_blur_block(a, idx); break;
+    case WRCU_KIND_SCALE: wr_setup_scale_block(a, idx); break;
+    case WRCU_KIND_FAST_LINEAR_GRADIENT: case WRCU_KIND_LINEAR_GRADIENT: case WRCU_KIND_RADIAL_GRADIENT:
+    case WRCU_KIND_CONIC_GRADIENT: wr_setup_cs_gradient_block(a, idx); break;
+    case WRCU_KIND_LINE_DECORATION: wr_setup_line_decoration_block(a, idx); break;
+    case WRCU_KIND_BORDER_SOLID: case WRCU_KIND_BORDER_SEGMENT: wr_setup_border_block(a, idx); break;
+    case WRCU_KIND_QUAD_RADIAL_GRADIENT: case WRCU_KIND_QUAD_CONIC_GRADIENT: wr_setup_quad_gradient_block(a, idx); break;
+    case WRCU_KIND_BRUSH_YUV_IMAGE: wr_setup_brush_yuv_image_block(a, idx); break;
+    case WRCU_KIND_SPLIT_COMPOSITE: wr_setup_split_composite_block(a, idx); break;
+    default: break;
+  }
+}
+#else
+static void setup_host(int kind, uint32_t features, const SetupArgs& a) {
+  switch (kind) {
+    case WRCU_KIND_QUAD_TEXTURED: wr_setup_quad_textured(a); break;
+    case WRCU_KIND_QUAD_MASK: wr_setup_quad_mask(a); break;
+    case WRCU_KIND_BRUSH_SOLID: wr_setup_brush_solid(a); break;
+    case WRCU_KIND_BRUSH_IMAGE: wr_setup_brush_image(a); break;
+    case WRCU_KIND_BRUSH_LINEAR_GRADIENT: wr_setup_brush_linear_gradient(a); break;
+    case WRCU_KIND_BRUSH_BLEND: wr_setup_brush_blend(a); break;
+    case WRCU_KIND_BRUSH_MIX_BLEND: wr_setup_brush_mix_blend(a); break;
+    case WRCU_KIND_BRUSH_OPACITY: wr_setup_brush_opacity(a); break;
+    case WRCU_KIND_TEXT_RUN: wr_setup_text_run(a); break;
+    case WRCU_KIND_CLIP_RECTANGLE: wr_setup_clip_rectangle(a); break;
+    case WRCU_KIND_CLIP_BOX_SHADOW: wr_setup_clip_box_shadow(a); break;
+    case WRCU_KIND_COMPOSITE:
+      if (features & WRCU_FEAT_YUV) wr_setup_composite_yuv(a);
+      else wr_setup_composite(a);
+      break;
+    case WRCU_KIND_CLEAR: wr_setup_clear(a); break;
+    case WRCU_KIND_BLUR: wr_setup_blur(a); break;
+    case WRCU_KIND_SCALE: wr_setup_scale(a); break;
+    case WRCU_KIND_FAST_LINEAR_GRADIENT: case WRCU_KIND_LINEAR_GRADIENT: case WRCU_KIND_RADIAL_GRADIENT:
+    case WRCU_KIND_CONIC_GRADIENT: wr_setup_cs_gradient(a); break;
+    case WRCU_KIND_LINE_DECORATION: wr_setup_line_decoration(a); break;
+    case WRCU_KIND_BORDER_SOLID: case WRCU_KIND_BORDER_SEGMENT: wr_setup_border(a); break;
+    case WRCU_KIND_QUAD_RADIAL_GRADIENT: case WRCU_KIND_QUAD_CONIC_GRADIENT: wr_setup_quad_gradient(a); break;
+    case WRCU_KIND_BRUSH_YUV_IMAGE: wr_setup_brush_yuv_image(a); break;
+    case WRCU_KIND_SPLIT_COMPOSITE: wr_setup_split_composite(a); break;
+    default: break;
+  }
+}
+#endif
+
+static int launch_clear(wrcu_ctx* c, const PendingOp& op);
+static int launch_raster(wrcu_ctx* c, PendingOp& op);
+
+static int flush_pending(wrcu_ctx* c) {
+  if (c->in_flush) return WRCU_OK;
+  std::vector<PendingOp>& q = pending(c);
+  if (q.empty() && c->dirty_hi <= c->dirty_lo) return WRCU_OK;
+  cudaSetDevice(c->device);
+  c->in_flush = true;
+  struct Guard { wrcu_ctx* c; std::vector<PendingOp>& q; ~Guard() { q.clear(); c->pend_instances = 0; c->in_flush = false; } } guard{c, q};
+  size_t total_n = 0, bin_total = 0;
+  int nb = 0, total_blocks = 0;
+  for (const PendingOp& op : q)
+    if (op.type == 1) { total_n += (size_t)op.n; bin_total += op.bin_need; nb++; total_blocks += op.sblocks; }
+  BatchInfo* infos = (BatchInfo*)c->batch_info + (size_t)c->flush_parity * wrcu_ctx::QMAX;
+  BatchInfo* infos_next = (BatchInfo*)c->batch_info + (size_t)(c->flush_parity ^ 1) * wrcu_ctx::QMAX;
+  int* ctr = c->pool_ctr + c->flush_parity * 2;
+  int* ctr_next = c->pool_ctr + (c->flush_parity ^ 1) * 2;
+  size_t jobs_off = 0, map_off = 0;
+  if (nb) {
+    int rc;
+    if ((rc = ensure_cmd_capacity(c, total_n)) != WRCU_OK) return rc;
+    if (bin_total > c->bin_cap_words) {
+      WRCU_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (c->bin_mask) cudaFree(c->bin_mask);
+      c->bin_mask = nullptr;
+      c->bin_cap_words = 0;
+      WRCU_CUDA(c, cudaMalloc((void**)&c->bin_mask, bin_total * 4 * 2));
+      c->bin_cap_words = bin_total * 2;
+    }
+    // the job table lives in the arena too; reserving it may still move the arena (pointers are resolved below)
+    if ((rc = arena_reserve(c, (size_t)nb * sizeof(SetupJob), &jobs_off)) != WRCU_OK) return rc;
+    if ((rc = arena_reserve(c, (size_t)total_blocks * sizeof(int), &map_off)) != WRCU_OK) return rc;
+    Arena* a = &c->arena[c->cur_arena];
+    SetupJob* jobs = (SetupJob*)(a->host + jobs_off);
+    int* block_job = (int*)(a->host + map_off);
+    size_t off = 0, boff = 0;
+    int bi = 0, blk = 0;
+    for (PendingOp& op : q) {
+      if (op.type != 1) continue;
+      SetupArgs& sa = op.sa;
+      RasterArgs& ra = op.ra;
+      sa.tabs = c->tables;
+      sa.instances = a->dev + op.inst_off;
+      sa.tex_list = op.views_off != (size_t)-1 ? (const TexView*)(a->dev + op.views_off) : nullptr;
+      sa.hot = (CmdHot*)c->cmd_hot + off;
+      sa.cold = (CmdCold*)c->cmd_cold + off;
+      sa.info = infos + bi;
+      sa.info_next = nullptr;
+      sa.pool_ctr = ctr;
+      sa.row_tab = c->row_tab;
+      sa.row_cap = c->row_cap;
+      if (op.bin_need) {
+        const size_t words = (size_t)sa.bin_words, tiles = (op.bin_need - (size_t)sa.any_words - 1) / words - 1;
+        sa.tile_mask = c->bin_mask + boff;
+        sa.wide_mask = sa.tile_mask + tiles * words;
+        sa.tile_any = sa.wide_mask + words;
+        boff += op.bin_need;
+      }
+      ra.hot = sa.hot;
+      ra.cold = sa.cold;
+      ra.info = sa.info;
+      ra.tile_mask = sa.tile_mask;
+      ra.wide_mask = sa.wide_mask;
+      ra.tile_any = sa.tile_any;
+      ra.row_tab = c->row_tab;
+      ra.gbuf_f = c->tables.gpu_buffer_f;
+      ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
+      ra.gpu_cache = c->tables.gpu_cache;
+      ra.n_gpu_cache = c->tables.n_gpu_cache;
+      memset(&jobs[bi], 0, sizeof(SetupJob));
+      jobs[bi].a = sa;
+      jobs[bi].kind = op.kind;
+      jobs[bi].features = op.features;
+      jobs[bi].first_block = blk;
+      for (int k = 0; k < op.sblocks; k++) block_job[blk + k] = bi;
+      blk += op.sblocks;
+      off += (size_t)op.n;
+      bi++;
+    }
+    mark_dirty(c, jobs_off, jobs_off + (size_t)nb * sizeof(SetupJob));
+    mark_dirty(c, map_off, map_off + (size_t)total_blocks * sizeof(int));
+    c->stats.h2d_bytes += (size_t)nb * sizeof(SetupJob) + (size_t)total_blocks * sizeof(int);
+  }
+  if (c->dirty_hi > c->dirty_lo) {
+    Arena* a = &c->arena[c->cur_arena];
+    WRCU_CUDA(c, cudaMemcpyAsync(a->dev + c->dirty_lo, a->host + c->dirty_lo, c->dirty_hi - c->dirty_lo, cudaMemcpyHostToDevice,
+                                 c->stream));
+    c->dirty_lo = c->dirty_hi = 0;
+  }
+  if (nb) {
+    Arena* a = &c->arena[c->cur_arena];
+    if (bin_total) WRCU_CUDA(c, cudaMemsetAsync(c->bin_mask, 0, bin_total * 4, c->stream));
+#ifndef WRCU_HOSTEMU
+    wr_setup_multi<<<total_blocks, 128, 0, c->stream>>>((const SetupJob*)(a->dev + jobs_off), (const int*)(a->dev + map_off), infos_next,
+                                                        wrcu_ctx::QMAX, ctr_next);
+    c->stats.kernel_launches++;
+    WRCU_CUDA(c, cudaGetLastError());
+#else
+    for (int i = 0; i < wrcu_ctx::QMAX; i++) wr_reset_batch_info(infos_next + i);
+    ctr_next[0] = ctr_next[1] = 0;
+    for (PendingOp& op : q)
+      if (op.type == 1) setup_host(op.kind, op.features, op.sa);
+#endif
+  }
+  for (PendingOp& op : q) {
+    int rc = op.type == 0 ? launch_clear(c, op) : launch_raster(c, op);
+    if (rc != WRCU_OK) return rc;
+  }
+  if (nb) c->flush_parity ^= 1;
   return WRCU_OK;
 }
 
@@ -1775,6 +2063,7 @@ extern "C" int wrcu_program_from_name(const char* key, int* kind, uint32_t* feat
 
 // ---- stats / timing ---------------------------------------------------------------------
 extern "C" int wrcu_get_stats(wrcu_ctx* c, wrcu_stats* out) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   *out = c->stats;
   return WRCU_OK;
 }
@@ -1788,16 +2077,19 @@ extern "C" int wrcu_profile_enable(wrcu_ctx* c, int on) {
   return WRCU_OK;
 }
 extern "C" int wrcu_last_raster_ms(wrcu_ctx* c, float* ms) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   if (!ms || !c->profile_valid) return wrcu_fail(c, WRCU_ERR_INVALID, "last_raster_ms: no profiled draw");
   WRCU_CUDA(c, cudaEventSynchronize(c->p1));
   WRCU_CUDA(c, cudaEventElapsedTime(ms, c->p0, c->p1));
   return WRCU_OK;
 }
 extern "C" int wrcu_timer_begin(wrcu_ctx* c) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WRCU_CUDA(c, cudaEventRecord(c->t0, c->stream));
   return WRCU_OK;
 }
 extern "C" int wrcu_timer_end(wrcu_ctx* c, float* ms) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
   WRCU_CUDA(c, cudaEventRecord(c->t1, c->stream));
   WRCU_CUDA(c, cudaEventSynchronize(c->t1));
   WRCU_CUDA(c, cudaEventElapsedTime(ms, c->t0, c->t1));

@@ -18,11 +18,17 @@
 #define WRD static inline
 #define WRD_MEMBER static inline
 #define WRD_METHOD inline
+#define WRD_SHARED static inline
 #else
 #include <cuda_runtime.h>
 #define WRD __device__ __forceinline__
 #define WRD_MEMBER __device__ static __forceinline__
 #define WRD_METHOD __device__ __forceinline__
+// Large helpers every kernel uses (exact running sums, the blend stage, span partitions, sampling).  Measured
+// both ways (profiles/README_r02.md): as real functions (__noinline__, pixel loop rolled) the kernels are a third
+// of the size and 3-instance batches run ~25 % faster, but the 4K text / image / video passes lose 25-40 % to
+// call overhead and spilled row state — so they stay inlined.
+#define WRD_SHARED __device__ __forceinline__
 #endif
 #include <stdint.h>
 #include <utility>
@@ -148,6 +154,17 @@ struct wrcu_ctx {
   int n_flags = 0;
   struct PeerFlags { uint32_t* ptr; int count; bool ipc; };
   std::vector<PeerFlags> peers;
+  // deferred submission (wrcu_api.cu: PendingOp, flush_pending): clears and batches queue up; one H2D copy, ONE
+  // set-up launch for all queued batches, then the clears / raster launches in order
+  static const int QMAX = 1024;
+  void* pending_ops = nullptr;   // std::vector<PendingOp>*
+  size_t pend_instances = 0;
+  bool in_flush = false;
+  bool immediate = false;        // WRCU_IMMEDIATE=1: flush after every call (A/B measurements)
+  int flush_parity = 0;          // which half of batch_info / pool_ctr the current submission uses
+  int* pool_ctr = nullptr;       // 2 x {row-table floats, depth-run words} handed out (device)
+  size_t dirty_lo = 0, dirty_hi = 0;  // arena range staged on the host but not yet copied to the device
+  int n_wait_kernel = 0, n_wait_event = 0;  // wrcu_peer_wait: polling kernels / event waits queued (diagnostics)
   uint32_t* fail_pool = nullptr;  // depth-run bitmaps of the current batch (CmdCold::fail_off)
   int fail_cap = 0;               // words
   void* tmaps_dev = nullptr;
