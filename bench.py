@@ -116,7 +116,7 @@ def run_reference(args):
         return
     from oracle.backends import have_swgl
     kind = "reference" if have_swgl() else "port"
-    cores = usable_cores()
+    cores = min(usable_cores(), args.ref_cores) if args.ref_cores > 0 else usable_cores()
     n_rects = args.ref_rects
     band_h = max(8, H // cores)
     times = []
@@ -541,6 +541,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="wrcu", choices=["wrcu", "reference"])
     ap.add_argument("--ref-rects", type=int, default=400, help="layers per step for --impl reference")
+    ap.add_argument("--ref-cores", type=int, default=0, help="--impl reference: use this many cores (default: all usable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config-e", action="store_true", help="also run the sharded 8K frame (always on for --gpus > 1)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the layer-depth roofline sweep")

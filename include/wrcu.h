@@ -20,6 +20,13 @@
  *    device/gl.rs:3552-3600).
  *  - Work is queued on a CUDA stream; wrcu_read_pixels / wrcu_finish
  *    synchronise (the SWGL equivalents are synchronous, gl.cc:2802).
+ *    wrcu_clear and wrcu_draw_batch / wrcu_draw_composite_tiles are further
+ *    queued inside the library and submitted together — one host-to-device
+ *    copy and one set-up launch for every queued batch — by the next call of
+ *    any other kind (wrcu_frame_end at the latest), so their execution order
+ *    relative to every other call is exactly the call order.  Asynchronous
+ *    errors of a draw (an instance the backend cannot rasterise) surface at
+ *    the next synchronising call, as GL errors do.
  *  - One context per host thread, like `MakeCurrent` (gl.cc:2808).
  *  - Colour targets are "RGBA8" with B,G,R,A byte order in memory exactly as
  *    SWGL stores them (swgl/src/texture.h:85-90); alpha targets are R8.

@@ -99,7 +99,8 @@ def test_direct_sharded_contexts_share_one_framebuffer(world):
     for r in rs:
         r.connect(blobs)
     for _ in range(2):
-        rs[0].begin()
+        for r in rs:          # rank 0 first: it clears and signals; the others only advance their frame counter
+            r.begin()
         for r in rs[1:]:
             r.draw()
         rs[0].draw()

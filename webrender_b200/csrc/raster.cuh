@@ -57,9 +57,22 @@ struct RasterArgs {
   const void* tmaps;     // device table of CUtensorMap records, indexed by TexView::tmap_id
   int copy_eligible;     // composite: a copy-class batch (BatchInfo::all_copy) is drawn by wr_composite_copy
   int tmap_acquire;      // tensor-map table slots have been reused: acquire each map before use (tma.cuh)
+  int pdl_early;         // programmatic dependent launch: this kernel may read its commands (written by the set-up
+                         // launch, which finished earlier) before the kernel ahead of it in the stream has completed
 };
 
 #define CHUNK_CMDS 256
+// Programmatic dependent launch (griddepcontrol): raster kernels of a submission are launched with
+// programmaticStreamSerialization, each lets its successor start at once and itself waits for its predecessor
+// only where it first touches pixels — the command scan of batch k+1 overlaps the pixels of batch k.  Both
+// instructions do nothing in a kernel launched the ordinary way.
+#ifdef WRCU_HOSTEMU
+static inline void wr_pdl_launch_dependents() {}
+static inline void wr_pdl_wait() {}
+#else
+__device__ __forceinline__ void wr_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void wr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // AA weight of pixel x for the current command (DO_AA, blend.h:433-445, with
 // the span set-up of aa_span, rasterize.h:546-557).  Chunks of 4 start at the
@@ -935,6 +948,7 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
       if (!loaded) {
         // lazy tile load: first command that touches this row
         loaded = true;
+        wr_pdl_wait();  // the kernel ahead of this one in the stream may still be writing these pixels
         if (FMT == WRCU_FMT_RGBA8) {
           uint4 v = *(const uint4*)(rowp + (size_t)x * 4);
           px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
@@ -1050,6 +1064,8 @@ __global__ void __launch_bounds__(WRCU_THREADS, WrMinCtas<S>::v)
 wr_raster(RasterArgs a) {
   __shared__ CmdHot sh[CHUNK_CMDS];
   __shared__ int wsum[WRCU_THREADS / 32 + 1];  // per-warp survivor counts + the last covering command
+  wr_pdl_launch_dependents();
+  if (!a.pdl_early) wr_pdl_wait();
   const BatchInfo bi = *a.info;
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
   const bool skip_copy = a.copy_eligible && bi.all_copy;  // CMD_COPY commands are drawn by wr_composite_copy
@@ -1115,15 +1131,25 @@ __global__ void __launch_bounds__(256) wr_depth_fail_rows(RasterArgs a, uint32_t
   __shared__ short4 crect[WR_FAIL_CAND];
   __shared__ unsigned char cgen[WR_FAIL_CAND];
   __shared__ int ncand;
+  wr_pdl_launch_dependents();
+  wr_pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int G = (int)gridDim.x;
   RasterArgs ar = a;
   GenRow g;
   // Work items = groups of `nwarps` rows of the commands that carry bitmaps (CMD_RUNS), dealt round-robin to
   // the persistent CTAs: a tall command spreads over the grid, thousands of glyph-sized ones cost a CTA each.
+  // The hot records are staged through shared memory 256 at a time: every CTA walks the whole list, and one
+  // dependent global load per command (x 60 glyphs) was most of this kernel's time on small batches.
+  __shared__ CmdHot hot_sh[256];
   int gbase = 0;
   for (int ci = 0; ci < a.n; ci++) {
-    const CmdHot c0 = a.hot[ci];
+    if ((ci & 255) == 0) {
+      __syncthreads();
+      if (ci + (int)threadIdx.x < a.n) hot_sh[threadIdx.x] = a.hot[ci + threadIdx.x];
+      __syncthreads();
+    }
+    const CmdHot c0 = hot_sh[ci & 255];
     if (!(c0.flags & CMD_RUNS) || c0.x1 <= c0.x0) continue;  // CTA-uniform
     const int rows = (int)c0.y1 - (int)c0.y0, ngroups = (rows + nwarps - 1) / nwarps;
     const int first = ((int)blockIdx.x - gbase % G + G) % G;
@@ -1374,6 +1400,8 @@ WRD void wr_fast_tile(const RasterArgs& a, int tx0, int ty0, uint4* fa, int4* fb
 __global__ void __launch_bounds__(FLAT_THREADS) wr_raster_solid_flat(RasterArgs a) {
   __shared__ int4 rect[FLAT_MAX];
   __shared__ uint4 col[FLAT_MAX];
+  wr_pdl_launch_dependents();
+  wr_pdl_wait();
   const BatchInfo bi = *a.info;
   if (!bi.simple) return;  // mixed batch → generic kernel
   if (threadIdx.x < a.n) {
@@ -1423,6 +1451,8 @@ wr_raster_solid_premult(RasterArgs a) {
   __shared__ uint4 fa[FAST_CHUNK];
   __shared__ int4 fb[FAST_CHUNK];
   __shared__ int wsum[FAST_THREADS / 32];
+  wr_pdl_launch_dependents();
+  wr_pdl_wait();
   const BatchInfo bi = *a.info;
   if (!bi.simple) return;  // mixed batch → generic kernel
   // tiles of the batch's bounding box (clamped to the target)

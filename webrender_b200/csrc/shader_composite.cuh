@@ -267,31 +267,42 @@ WRD uint32_t wr_over_px(uint32_t d, uint32_t s) {  // premultiplied-alpha over, 
   return rb | (ga << 8);
 }
 
+// one row of a box by plain accesses, `t` of `nt` threads: scalar pixels up to the destination's 16-byte
+// boundary, then 16-byte stores (the source as one vector load when it is in phase, four scalar loads otherwise)
+template <bool BLEND>
+__device__ __forceinline__ void wr_copy_row(const uint32_t* sp, uint32_t* dp, int bw, int t, int nt) {
+  int head = (int)(((16u - (unsigned)((uintptr_t)dp & 15u)) & 15u) >> 2);
+  if (head > bw) head = bw;
+  for (int q = t; q < head; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
+  sp += head; dp += head; bw -= head;
+  const int nv = bw >> 2;
+  const bool in_phase = ((uintptr_t)sp & 15) == 0;
+  for (int q = t; q < nv; q += nt) {
+    uint4 sv;
+    if (in_phase) sv = __ldg((const uint4*)sp + q);
+    else sv = make_uint4(__ldg(sp + 4 * q), __ldg(sp + 4 * q + 1), __ldg(sp + 4 * q + 2), __ldg(sp + 4 * q + 3));
+    if (BLEND) {
+      const uint4 dv = ((const uint4*)dp)[q];
+      sv = make_uint4(wr_over_px(dv.x, sv.x), wr_over_px(dv.y, sv.y), wr_over_px(dv.z, sv.z), wr_over_px(dv.w, sv.w));
+    }
+    ((uint4*)dp)[q] = sv;
+  }
+  for (int q = (nv << 2) + t; q < bw; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
+}
 // ragged-edge boxes by plain accesses: `t` of `nt` threads share the rows of each box
 template <bool BLEND>
 __device__ void wr_copy_ragged(const RasterArgs& a, const WrCopyCmd* cl, int n, int t, int nt) {
   WrBoxIter it;
   int bx, by;
+  const int lane = t & 31, w = t >> 5, nw = nt >> 5;
   while (it.next(cl, n, false, bx, by)) {
     const WrCopyCmd& c = cl[it.i];
     const int bw = min(WR_TMA_BOX_W, c.w - bx), bh = min(WR_TMA_BOX_H, c.h - by);
-    for (int r = 0; r < bh; r++) {
+    // a warp per row: 32 lanes x 16 bytes cover half a box row per step
+    for (int r = w; r < bh; r += nw) {
       const uint32_t* sp = (const uint32_t*)(c.sptr + (size_t)(c.sy + by + r) * c.spitch) + c.sx + bx;
       uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)c.y0 + by + r) * a.tgt.color_pitch) + (int)c.x0 + bx;
-      if ((((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
-        const int nv = bw >> 2;
-        for (int q = t; q < nv; q += nt) {
-          uint4 sv = __ldg((const uint4*)sp + q);
-          if (BLEND) {
-            const uint4 dv = ((const uint4*)dp)[q];
-            sv = make_uint4(wr_over_px(dv.x, sv.x), wr_over_px(dv.y, sv.y), wr_over_px(dv.z, sv.z), wr_over_px(dv.w, sv.w));
-          }
-          ((uint4*)dp)[q] = sv;
-        }
-        for (int q = (nv << 2) + t; q < bw; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
-      } else {
-        for (int q = t; q < bw; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
-      }
+      wr_copy_row<BLEND>(sp, dp, bw, lane, 32);
     }
   }
 }
@@ -302,19 +313,27 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
   extern __shared__ __align__(128) uint8_t wr_copy_smem[];
   __shared__ __align__(8) uint64_t full[WR_TMA_STAGES];
   __shared__ WrCopyCmd cl[WR_COPY_MAX_CMDS];
+  wr_pdl_launch_dependents();
+  wr_pdl_wait();
   const BatchInfo bi = *a.info;
   if (!bi.all_copy) return;  // the ordered tile kernel draws this batch
   const CUtensorMap* maps = (const CUtensorMap*)a.tmaps;
   const CUtensorMap* dst_map = maps + a.tgt.tmap_id;
-  const int n = min(a.n, WR_COPY_MAX_CMDS);
+  const int n0 = min(a.n, WR_COPY_MAX_CMDS);
+  // A tile whose clip starts off a 16-byte boundary (a dirty rect cut anywhere) is split: a strip of 1-3 pixel
+  // columns up to the boundary, copied by threads, and the rest — source and destination in phase for a 1:1
+  // tile — through the copy engine.  Entry i = the body (or all) of command i, entry n0 + i = its strip.
+  const bool split = 2 * n0 <= WR_COPY_MAX_CMDS;
+  const int n = split ? 2 * n0 : n0;
   // Start-up, spread over the CTA's threads (one thread walking the list pays two dependent DRAM
   // round trips per command): thread t stages command t.
-  for (int i = threadIdx.x; i < n; i += WR_TMA_THREADS) {
+  for (int i = threadIdx.x; i < n0; i += WR_TMA_THREADS) {
     const CmdHot c = a.hot[i];
-    WrCopyCmd cc;
+    WrCopyCmd cc, cs;
     cc.x0 = c.x0; cc.y0 = c.y0;
     cc.w = cc.h = 0;
     cc.sx = cc.sy = cc.tmap = cc.aligned = 0; cc.sptr = nullptr; cc.spitch = 0;
+    cs = cc;
     if (c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY)) {
       const CmdCold& k = a.cold[c.cold];
       const TexView& tv = wr_composite_tex(k);
@@ -325,11 +344,21 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
       cc.aligned = (((int)c.x0 | k.i[0]) & 3) == 0;
       cc.sptr = tv.ptr;
       cc.spitch = tv.pitch;
+      const int head = (4 - ((int)c.x0 & 3)) & 3;
+      if (split && !cc.aligned && (((int)c.x0 ^ k.i[0]) & 3) == 0 && cc.w > head) {
+        cs = cc;
+        cs.w = head;          // the strip: never a full box
+        cc.x0 = (short)((int)c.x0 + head);
+        cc.sx += head;
+        cc.w -= head;
+        cc.aligned = 1;
+      }
       // a table slot that held another texture's map before (RasterArgs::tmap_acquire, see wrcu_api.cu
       // make_tensor_map) must be re-read through the tensormap proxy
       if (a.tmap_acquire) wr_tma_acquire_map(maps + tv.tmap_id);
     }
     cl[i] = cc;
+    if (split) cl[n0 + i] = cs;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < WR_TMA_STAGES; s++) wr_mbar_init(&full[s], 1);

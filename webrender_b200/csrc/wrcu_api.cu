@@ -58,6 +58,7 @@ struct PendingOp {
   uint32_t features = 0;
   unsigned grid_x = 0, grid_y = 0;
   size_t bin_need = 0, inst_off = 0, views_off = (size_t)-1;
+  std::vector<const uint8_t*> tex_reads;  // wrcu_draw_composite_tiles: the instances' textures (stream scheduling)
   SetupArgs sa;
   RasterArgs ra;
 };
@@ -87,6 +88,11 @@ static int fmt_bpp(int fmt) {
 #else
 #define WR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
 #define WR_GLOBAL __global__
+#endif
+#ifdef WRCU_HOSTEMU
+#define WR_LAUNCH_CHAIN(kernel, grid, block, ra) kernel(ra)
+#else
+#define WR_LAUNCH_CHAIN(kernel, grid, block, ra) wr_launch_chain(c, kernel, (unsigned)(grid), (unsigned)(block), 0, ra)
 #endif
 
 // ---- small kernels ---------------------------------------------------------------
@@ -247,6 +253,12 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
   {
     const char* e = getenv("WRCU_IMMEDIATE");
     c->immediate = e && atoi(e) != 0;
+    e = getenv("WRCU_PDL");
+    c->pdl = e ? atoi(e) != 0 : true;
+    e = getenv("WRCU_STREAMS");
+    c->n_streams = e ? atoi(e) : 8;
+    if (c->n_streams < 1) c->n_streams = 1;
+    if (c->n_streams > 32) c->n_streams = 32;
   }
 #ifndef WRCU_HOSTEMU
   {  // TMA tensor maps: encoder entry point from the driver (no libcuda link), device table of records
@@ -311,6 +323,10 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   if (c->cmd_cold) cudaFree(c->cmd_cold);
   if (c->batch_info) cudaFree(c->batch_info);
   if (c->pool_ctr) cudaFree(c->pool_ctr);
+  for (cudaStream_t st : c->side) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (cudaEvent_t e : c->op_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->join_ev) cudaEventDestroy(e);
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   delete (std::vector<PendingOp>*)c->pending_ops;
   if (c->row_tab) cudaFree(c->row_tab);
   if (c->tmaps_dev) cudaFree(c->tmaps_dev);
@@ -1283,13 +1299,13 @@ static int launch_clear(wrcu_ctx* c, const PendingOp& op) {
   if (grid.x > 8) grid.x = 8;
   if (op.c_ptr) {
     if (op.c_fmt == WRCU_FMT_RGBA8)
-      WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, op.c_ptr, op.c_pitch, op.cx0, op.cy0, op.cx1, op.cy1, op.c_val);
+      WR_LAUNCH(wr_clear_u32, grid, 256, c->launch_stream, op.c_ptr, op.c_pitch, op.cx0, op.cy0, op.cx1, op.cy1, op.c_val);
     else
-      WR_LAUNCH(wr_clear_u8, grid, 256, c->stream, op.c_ptr, op.c_pitch, op.cx0, op.cy0, op.cx1, op.cy1, (uint8_t)op.c_val);
+      WR_LAUNCH(wr_clear_u8, grid, 256, c->launch_stream, op.c_ptr, op.c_pitch, op.cx0, op.cy0, op.cx1, op.cy1, (uint8_t)op.c_val);
     c->stats.kernel_launches++;
   }
   if (op.d_ptr) {
-    WR_LAUNCH(wr_clear_u32, grid, 256, c->stream, op.d_ptr, op.d_pitch, op.cx0, op.cy0, op.cx1, op.cy1, op.d_val);
+    WR_LAUNCH(wr_clear_u32, grid, 256, c->launch_stream, op.d_ptr, op.d_pitch, op.cx0, op.cy0, op.cx1, op.cy1, op.d_val);
     c->stats.kernel_launches++;
   }
   WRCU_CUDA(c, cudaGetLastError());
@@ -1661,6 +1677,8 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   op.ra = ra;
   op.inst_off = inst_off;
   op.views_off = textures ? views_off : (size_t)-1;
+  if (textures)
+    for (int i = 0; i < n; i++) op.tex_reads.push_back(tex_view(c, textures[i]).ptr);
   op.grid_x = grid.x;
   op.grid_y = grid.y;
   pending(c).push_back(op);
@@ -1668,6 +1686,30 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   if (pending(c).size() >= (size_t)wrcu_ctx::QMAX || c->immediate) return flush_pending(c);
   return WRCU_OK;
 }
+
+#ifndef WRCU_HOSTEMU
+// A raster-class launch with programmatic stream serialization (see raster.cuh wr_pdl_wait); the ordinary
+// launch when the context has it switched off (WRCU_PDL=0).
+template <typename K>
+static void wr_launch_chain(wrcu_ctx* c, K kernel, unsigned grid, unsigned block, size_t smem, const RasterArgs& ra) {
+  if (!c->pdl) {
+    kernel<<<grid, block, smem, c->launch_stream>>>(ra);
+    return;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->launch_stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, ra);
+}
+#endif
 
 // The raster launches of one queued batch (its set-up has run): depth-run prepass, then the kernel(s) of its kind.
 static int launch_raster(wrcu_ctx* c, PendingOp& op) {
@@ -1683,11 +1725,11 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
   if (op.sa.depth_runs) {
     // depth runs: the failing-sample bitmaps of this batch, before any of its depth writes
     ra.fail_pool = c->fail_pool;
-    wr_depth_fail_rows<<<c->sm_count * 4, 256, 0, c->stream>>>(ra, c->fail_pool);
+    wr_depth_fail_rows<<<c->sm_count * 4, 256, 0, c->launch_stream>>>(ra, c->fail_pool);
     c->stats.kernel_launches++;
   }
 #endif
-  if (c->profile) WRCU_CUDA(c, cudaEventRecord(c->p0, c->stream));
+  if (c->profile) WRCU_CUDA(c, cudaEventRecord(c->p0, c->launch_stream));
   bool fast_ok = T.fmt == WRCU_FMT_RGBA8 && op.blend == WRCU_BLEND_PREMULTIPLIED_ALPHA &&
                  ra.depth_mode == WRCU_DEPTH_OFF &&
                  (kind == WRCU_KIND_QUAD_TEXTURED || kind == WRCU_KIND_BRUSH_SOLID);  // the only kinds that emit CMD_CONST_COLOR
@@ -1711,7 +1753,7 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
       long long blocks = (groups + FLAT_THREADS - 1) / FLAT_THREADS;
       const long long cap = (long long)c->sm_count * 64;
       if (blocks > cap) blocks = cap;
-      wr_raster_solid_flat<<<(unsigned)blocks, FLAT_THREADS, 0, c->stream>>>(ra);
+      wr_launch_chain(c, wr_raster_solid_flat, (unsigned)blocks, FLAT_THREADS, 0, ra);
     } else {
     const int n_tiles = (int)(grid.x * grid.y);
     const int sms = c->sm_count > 0 ? c->sm_count : 148;
@@ -1725,7 +1767,7 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
         if (eff > best_eff + 1e-9) { best_eff = eff; best_grid = slots; }
       }
     }
-    wr_raster_solid_premult<<<best_grid, FAST_THREADS, 0, c->stream>>>(ra);
+    wr_launch_chain(c, wr_raster_solid_premult, (unsigned)best_grid, FAST_THREADS, 0, ra);
     }
 #endif
     c->stats.kernel_launches++;
@@ -1739,9 +1781,9 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
     auto k_rgba = wr_raster<S, WRCU_FMT_RGBA8>;                                   \
     auto k_r8 = wr_raster<S, WRCU_FMT_R8>;                                        \
     if (T.fmt == WRCU_FMT_RGBA8)                                                 \
-      WR_LAUNCH(k_rgba, pgrid, WRCU_THREADS, c->stream, ra);                     \
+      WR_LAUNCH_CHAIN(k_rgba, pgrid, WRCU_THREADS, ra);                          \
     else                                                                         \
-      WR_LAUNCH(k_r8, pgrid, WRCU_THREADS, c->stream, ra);                       \
+      WR_LAUNCH_CHAIN(k_r8, pgrid, WRCU_THREADS, ra);                            \
   } while (0)
   // kinds drawn under depth test: the depth-run variant when this batch has failing-sample bitmaps
 #ifdef WRCU_HOSTEMU
@@ -1751,7 +1793,7 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
   do {                                                                           \
     if (op.sa.depth_runs && T.fmt == WRCU_FMT_RGBA8) {                              \
       auto k_runs = wr_raster<S, WRCU_FMT_RGBA8, true>;                           \
-      WR_LAUNCH(k_runs, pgrid, WRCU_THREADS, c->stream, ra);                     \
+      WR_LAUNCH_CHAIN(k_runs, pgrid, WRCU_THREADS, ra);                          \
     } else LAUNCH_RASTER(S);                                                     \
   } while (0)
 #endif
@@ -1780,8 +1822,8 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
           c->copy_attr_set = true;
         }
         ra.copy_eligible = 1;
-        if (op.blend == WRCU_BLEND_NONE) wr_composite_copy<false><<<c->sm_count * 3, WR_TMA_THREADS, smem0, c->stream>>>(ra);
-        else wr_composite_copy<true><<<c->sm_count * 2, WR_TMA_THREADS, smem1, c->stream>>>(ra);
+        if (op.blend == WRCU_BLEND_NONE) wr_launch_chain(c, wr_composite_copy<false>, (unsigned)c->sm_count * 3, WR_TMA_THREADS, smem0, ra);
+        else wr_launch_chain(c, wr_composite_copy<true>, (unsigned)c->sm_count * 2, WR_TMA_THREADS, smem1, ra);
         c->stats.kernel_launches++;
       }
 #endif
@@ -1807,7 +1849,7 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
 #undef LAUNCH_RASTER_RUNS
   c->stats.kernel_launches++;
   if (c->profile) {
-    WRCU_CUDA(c, cudaEventRecord(c->p1, c->stream));
+    WRCU_CUDA(c, cudaEventRecord(c->p1, c->launch_stream));
     c->profile_valid = true;
   }
   WRCU_CUDA(c, cudaGetLastError());
@@ -1904,6 +1946,109 @@ static void setup_host(int kind, uint32_t features, const SetupArgs& a) {
 
 static int launch_clear(wrcu_ctx* c, const PendingOp& op);
 static int launch_raster(wrcu_ctx* c, PendingOp& op);
+
+
+#ifndef WRCU_HOSTEMU
+// Render targets of one submission are mostly independent (picture-cache tiles never read each other,
+// frame_builder.rs:995-1057): their clears and raster launches go to a few side streams — one
+// stream per target, round robin — so the small kernels of different tiles overlap instead of queueing behind
+// one another (a page's tile pass is ~150 launches of 10-30 us each, nearly all latency).  Ordering that does
+// matter is kept with events: an op waits for the latest earlier op on ANOTHER stream that wrote something it
+// reads or writes, or read something it writes (colour target, depth target, sampled textures, clip mask).
+// The side streams fork after the set-up launch and join before flush_pending returns, so everything outside
+// the submission still sees one stream.
+struct OpUse { const uint8_t* w[2]; int nw; const uint8_t* r[4]; int nr; };
+static bool uses_conflict(const PendingOp& a, const OpUse& ua, const PendingOp& b, const OpUse& ub) {
+  // a earlier, b later: RAW / WAW (a writes what b touches), WAR (a reads what b writes)
+  for (int i = 0; i < ua.nw; i++) {
+    for (int j = 0; j < ub.nw; j++) if (ua.w[i] == ub.w[j]) return true;
+    for (int j = 0; j < ub.nr; j++) if (ua.w[i] == ub.r[j]) return true;
+    for (const uint8_t* p : b.tex_reads) if (ua.w[i] == p) return true;
+  }
+  for (int j = 0; j < ub.nw; j++) {
+    for (int i = 0; i < ua.nr; i++) if (ua.r[i] == ub.w[j]) return true;
+    for (const uint8_t* p : a.tex_reads) if (p == ub.w[j]) return true;
+  }
+  return false;
+}
+static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
+  const int NS = c->n_streams;
+  if (c->side.empty()) {
+    c->side.resize((size_t)NS);
+    for (int i = 0; i < NS; i++) WRCU_CUDA(c, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    WRCU_CUDA(c, cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    c->join_ev.resize((size_t)NS);
+    for (int i = 0; i < NS; i++) WRCU_CUDA(c, cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+  }
+  const size_t n = q.size();
+  while (c->op_events.size() < n) {
+    cudaEvent_t e;
+    WRCU_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->op_events.push_back(e);
+  }
+  std::vector<OpUse> use(n);
+  std::vector<int> strm(n);
+  std::vector<const uint8_t*> targets;
+  for (size_t i = 0; i < n; i++) {
+    const PendingOp& op = q[i];
+    OpUse u;
+    memset(&u, 0, sizeof u);
+    const uint8_t* tgt = nullptr;
+    if (op.type == 0) {
+      if (op.c_ptr) u.w[u.nw++] = op.c_ptr;
+      if (op.d_ptr) u.w[u.nw++] = op.d_ptr;
+      tgt = op.c_ptr ? op.c_ptr : op.d_ptr;
+    } else {
+      u.w[u.nw++] = op.ra.tgt.color;
+      if (op.ra.tgt.depth) u.w[u.nw++] = (const uint8_t*)op.ra.tgt.depth;
+      const uint8_t* rs[4] = {op.sa.color0.ptr, op.sa.color1.ptr, op.sa.color2.ptr, op.sa.clip_mask.ptr};
+      for (int k = 0; k < 4; k++) if (rs[k]) u.r[u.nr++] = rs[k];
+      tgt = op.ra.tgt.color;
+    }
+    use[i] = u;
+    size_t t = 0;
+    while (t < targets.size() && targets[t] != tgt) t++;
+    if (t == targets.size()) targets.push_back(tgt);
+    strm[i] = (int)(t % (size_t)NS);
+  }
+  // fork
+  WRCU_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
+  std::vector<char> used((size_t)NS, 0), need_ev(n, 0);
+  std::vector<std::vector<int>> deps(n);
+  for (size_t i = 0; i < n; i++) {
+    // latest conflicting earlier op on each other stream
+    std::vector<int> last((size_t)NS, -1);
+    for (size_t j = 0; j < i; j++) {
+      if (strm[j] == strm[i]) continue;
+      if (uses_conflict(q[j], use[j], q[i], use[i])) last[(size_t)strm[j]] = (int)j;
+    }
+    for (int sidx = 0; sidx < NS; sidx++)
+      if (last[(size_t)sidx] >= 0) { deps[i].push_back(last[(size_t)sidx]); need_ev[(size_t)last[(size_t)sidx]] = 1; }
+  }
+  for (size_t i = 0; i < n; i++) {
+    PendingOp& op = q[i];
+    cudaStream_t st = c->side[(size_t)strm[i]];
+    if (!used[(size_t)strm[i]]) {
+      used[(size_t)strm[i]] = 1;
+      WRCU_CUDA(c, cudaStreamWaitEvent(st, c->fork_ev, 0));
+    }
+    for (int j : deps[i]) WRCU_CUDA(c, cudaStreamWaitEvent(st, c->op_events[(size_t)j], 0));
+    c->launch_stream = st;
+    if (op.type == 1) op.ra.pdl_early = c->pdl ? 1 : 0;  // the set-up launch finished before the fork event
+    int rc = op.type == 0 ? launch_clear(c, op) : launch_raster(c, op);
+    if (rc != WRCU_OK) { c->launch_stream = c->stream; return rc; }
+    if (need_ev[i]) WRCU_CUDA(c, cudaEventRecord(c->op_events[i], st));
+  }
+  c->launch_stream = c->stream;
+  // join
+  for (int sidx = 0; sidx < NS; sidx++) {
+    if (!used[(size_t)sidx]) continue;
+    WRCU_CUDA(c, cudaEventRecord(c->join_ev[(size_t)sidx], c->side[(size_t)sidx]));
+    WRCU_CUDA(c, cudaStreamWaitEvent(c->stream, c->join_ev[(size_t)sidx], 0));
+  }
+  return WRCU_OK;
+}
+#endif
 
 static int flush_pending(wrcu_ctx* c) {
   if (c->in_flush) return WRCU_OK;
@@ -2007,7 +2152,21 @@ static int flush_pending(wrcu_ctx* c) {
       if (op.type == 1) setup_host(op.kind, op.features, op.sa);
 #endif
   }
+  c->launch_stream = c->stream;
+#ifndef WRCU_HOSTEMU
+  if (c->n_streams > 1 && q.size() > 2) {
+    int rcs = flush_multi_stream(c, q);
+    if (rcs != WRCU_OK) return rcs;
+    if (nb) c->flush_parity ^= 1;
+    return WRCU_OK;
+  }
+#endif
+  bool after_setup = nb > 0;  // the first raster launch follows the set-up launch: it must wait before reading commands
   for (PendingOp& op : q) {
+    if (op.type == 1) {
+      op.ra.pdl_early = (c->pdl && !after_setup) ? 1 : 0;
+      after_setup = false;
+    }
     int rc = op.type == 0 ? launch_clear(c, op) : launch_raster(c, op);
     if (rc != WRCU_OK) return rc;
   }

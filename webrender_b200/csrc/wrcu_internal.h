@@ -160,6 +160,13 @@ struct wrcu_ctx {
   void* pending_ops = nullptr;   // std::vector<PendingOp>*
   size_t pend_instances = 0;
   bool in_flush = false;
+  // side streams of a submission (flush_multi_stream): one per render target, round robin (WRCU_STREAMS, 1 = off)
+  int n_streams = 8;
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> op_events, join_ev;
+  cudaEvent_t fork_ev = nullptr;
+  cudaStream_t launch_stream = nullptr;  // where launch_clear / launch_raster queue (the context's stream, or a side stream)
+  bool pdl = true;               // raster launches chained with programmatic stream serialization (WRCU_PDL=0: off)
   bool immediate = false;        // WRCU_IMMEDIATE=1: flush after every call (A/B measurements)
   int flush_parity = 0;          // which half of batch_info / pool_ctr the current submission uses
   int* pool_ctr = nullptr;       // 2 x {row-table floats, depth-run words} handed out (device)
