@@ -1141,20 +1141,32 @@ __global__ void __launch_bounds__(256) wr_depth_fail_rows(RasterArgs a, uint32_t
   // the persistent CTAs: a tall command spreads over the grid, thousands of glyph-sized ones cost a CTA each.
   // The hot records are staged through shared memory 256 at a time: every CTA walks the whole list, and one
   // dependent global load per command (x 60 glyphs) was most of this kernel's time on small batches.
+  // Many small commands (a text run: 60 glyphs of 12 rows) are dealt a CTA each instead (command-major): no CTA
+  // walks the list at all.
   __shared__ CmdHot hot_sh[256];
+  const bool cmd_major = a.n >= 48;
   int gbase = 0;
-  for (int ci = 0; ci < a.n; ci++) {
-    if ((ci & 255) == 0) {
-      __syncthreads();
-      if (ci + (int)threadIdx.x < a.n) hot_sh[threadIdx.x] = a.hot[ci + threadIdx.x];
-      __syncthreads();
+  for (int ci = cmd_major ? (int)blockIdx.x : 0; ci < a.n; ci += cmd_major ? G : 1) {
+    CmdHot c0;
+    if (cmd_major) {
+      c0 = a.hot[ci];
+    } else {
+      if ((ci & 255) == 0) {
+        __syncthreads();
+        if (ci + (int)threadIdx.x < a.n) hot_sh[threadIdx.x] = a.hot[ci + threadIdx.x];
+        __syncthreads();
+      }
+      c0 = hot_sh[ci & 255];
     }
-    const CmdHot c0 = hot_sh[ci & 255];
     if (!(c0.flags & CMD_RUNS) || c0.x1 <= c0.x0) continue;  // CTA-uniform
     const int rows = (int)c0.y1 - (int)c0.y0, ngroups = (rows + nwarps - 1) / nwarps;
-    const int first = ((int)blockIdx.x - gbase % G + G) % G;
-    gbase += ngroups;
-    if (first >= ngroups) continue;  // none of this command's row groups is ours
+    int first = 0, gstride = 1;
+    if (!cmd_major) {
+      first = ((int)blockIdx.x - gbase % G + G) % G;
+      gstride = G;
+      gbase += ngroups;
+      if (first >= ngroups) continue;  // none of this command's row groups is ours
+    }
     const CmdCold& k = a.cold[c0.cold];
     int nc = 0;
     if (a.depth_mode == WRCU_DEPTH_TEST_WRITE) {
@@ -1176,7 +1188,7 @@ __global__ void __launch_bounds__(256) wr_depth_fail_rows(RasterArgs a, uint32_t
       nc = ncand;
     }
     const int W = k.fail_w;
-    for (int grp = first; grp < ngroups; grp += G) {
+    for (int grp = first; grp < ngroups; grp += gstride) {
       const int r = grp * nwarps + warp;
       if (r >= rows) continue;
       const int y = (int)c0.y0 + r;
