@@ -545,6 +545,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config-e", action="store_true", help="also run the sharded 8K frame (always on for --gpus > 1)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the layer-depth roofline sweep")
+    ap.add_argument("--sweep-only", action="store_true", help="only the layer-depth sweep (for an ncu pass over its kernels)")
     ap.add_argument("--workload", default="config_b",
                     help="config_b (the contract's bench line) or one of the other §8 rows: see other_workloads(), update_path")
     args = ap.parse_args()
@@ -555,6 +556,15 @@ def main():
         return
     if args.workload != "config_b":
         run_other_workload(args)
+        return
+    if args.sweep_only:
+        import torch
+        from webrender_b200.device import CudaDevice
+        dev = CudaDevice(0)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        peak, _ = load_peaks()
+        print(json.dumps({"roofline_sweep": roofline_sweep(dev, flush, max(2, min(args.steps, 10)), peak)}))
+        dev.close()
         return
 
     import numpy as np

@@ -80,6 +80,10 @@ CASES = [
     ("split_composite", "split_composite_frame", dict(seed=1), False),
     ("split_composite_near_plane", "split_composite_frame", dict(seed=2, d=220.0, ry=65.0, rx=20.0, perspective_interpolate=1),
      False),
+    ("reftest_inset_no_blur_radius", "reftest_box_shadow_frame", dict(which="inset-no-blur-radius")),
+    ("reftest_box_shadow_spread", "reftest_box_shadow_frame", dict(which="box-shadow-spread")),
+    ("reftest_boxshadow_spread_only", "reftest_box_shadow_frame", dict(which="boxshadow-spread-only")),
+    ("reftest_filter_small_blur_radius", "reftest_filter_blur_frame", dict()),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

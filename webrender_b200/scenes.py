@@ -276,6 +276,12 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
         mprim_f = t.add_quad_prim(rect, rect, (1.0, 1.0, 1.0, 1.0))
         mqi = quad_instance(prim_i, mprim_f, QF_APPLY_DEVICE_CLIP | QF_IS_MASK, 0, PART_ALL, INVALID_SEGMENT_INDEX, task)
         (masks_fast if uniform else masks_slow).append(mask_instance(mqi, 0, clip_addr, 0))
+        # further clips of the same primitive (spec[i][4] = [(clip rect, uniform radius, mode), ...]): one more
+        # ps_quad_mask instance each, multiplied into the same task (build_mask_tasks, render_target.rs:1192-1442)
+        for crect, cradius, cmode in (spec[i][4] if spec is not None and len(spec[i]) > 4 else []):
+            r = float(cradius)
+            caddr = t.push_gpu_buffer_f([tuple(float(v) for v in crect), (r, r, r, r), (float(cmode), 0, 0, 0)])
+            masks_fast.append(mask_instance(mqi, 0, caddr, 0))
         # composite: textured quad, uv rect = the task rect in the off-screen surface
         cprim_f = t.add_quad_prim(rect, rect, (1.0, 1.0, 1.0, 1.0),
                                   uv_rect=(float(tx), float(ty), float(tx + w), float(ty + h)))
@@ -1751,6 +1757,69 @@ def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=F
     return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
 
 
+FILTER_REFTESTS = {
+    # wrench/reftests/filters/<name>.yaml == <name>-ref.yaml (filters/reftest.list:11-41): a rect under a CSS filter must
+    # equal a plain rect of the colour the reference's authors computed.  (page background, [(rect, source colour
+    # 0-255 + alpha, filter, amount, expected colour 0-255 + alpha)], allowed (max diff, pixels))
+    "filter-grayscale": ((255, 255, 255), [((10, 10, 210, 210), (0, 255, 0, 1.0), FILTER_GRAYSCALE, 1.0, (182, 182, 182, 1.0))], (0, 0)),
+    "filter-brightness": ((0, 0, 0), [((10, 10, 110, 110), (255, 255, 255, 0.25), FILTER_BRIGHTNESS, 2.0, (64, 64, 64, 1.0))], (0, 0)),
+    "filter-brightness-2": ((255, 255, 255), [((10, 10, 110, 110), (255, 0, 0, 1.0), FILTER_BRIGHTNESS, 0.0, (0, 0, 0, 1.0))], (0, 0)),
+    "filter-invert": ((255, 255, 255), [((10, 10, 110, 110), (255, 255, 255, 0.25), FILTER_INVERT, 1.0, (0, 0, 0, 0.25))], (0, 0)),
+    "filter-saturate-red-2": ((0, 0, 0), [((10, 10, 110, 110), (255, 0, 0, 1.0), FILTER_SATURATE, 0.5, (155, 27, 27, 1.0))], (0, 0)),
+    "filter-contrast-gray-alpha-1": ((255, 255, 255), [((10, 10, 110, 110), (128, 128, 128, 0.25), FILTER_CONTRAST, 0.0,
+                                                        (223, 223, 223, 1.0))], (0, 0)),
+    "filter-hue-rotate-1": ((0, 0, 0), [((10, 10, 60, 60), (255, 0, 0, 1.0), FILTER_HUE_ROTATE, 90.0, (0, 91, 0, 1.0)),
+                                        ((10, 60, 60, 110), (0, 255, 0, 1.0), FILTER_HUE_ROTATE, 90.0, (0, 218, 255, 1.0)),
+                                        ((60, 10, 110, 60), (0, 0, 255, 1.0), FILTER_HUE_ROTATE, 90.0, (255, 0, 37, 1.0)),
+                                        ((60, 60, 110, 110), (128, 128, 128, 1.0), FILTER_HUE_ROTATE, 90.0, (128, 128, 128, 1.0))],
+                            (1, 14)),   # fuzzy(1,14)
+}
+
+
+def filter_reftest_frames(name, size=(220, 220)):
+    """(test frame, reference frame) of one of FILTER_REFTESTS: the filtered rects as Brush(Blend) instances reading
+    uniform picture surfaces (premultiplied 8-bit, as the picture pass leaves them), the reference rects as alpha
+    Brush(Solid) instances, both premultiplied-over the page colour."""
+    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    bg, cases, _ = FILTER_REFTESTS[name]
+    w, h = size
+    out = []
+    for ref in (False, True):
+        t = FrameTables()
+        pic = t.add_render_task((0.0, 0.0, float(w), float(h)), 1.0, (0.0, 0.0))
+        inst = []
+        textures = {"target": TextureDesc(abi.FMT_RGBA8, w, h)}
+        sw, sh = 64 * len(cases), 64
+        surf = np.zeros((sh, sw, 4), dtype=np.uint8)
+        for i, (r, src, op, amount, exp) in enumerate(cases):
+            rect = tuple(float(v) for v in r)
+            if ref:
+                a = float(exp[3])
+                c = tuple(float(v) / 255.0 * a for v in exp[:3]) + (a,)
+                addr = t.push_gpu_cache([c])
+                hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), i + 1, addr, 0, pic, (65535, 0, 0, 0))
+                inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+                continue
+            a = float(src[3])
+            px = [int(np.float32(v / 255.0 * a) * np.float32(255.0) + np.float32(0.5)) for v in src[:3]] + [int(a * 255.0 + 0.5)]
+            surf[:, 64 * i: 64 * i + 64] = (px[2], px[1], px[0], px[3])   # BGRA
+            res = t.push_gpu_cache([(64.0 * i + 8, 8.0, 64.0 * i + 56, 56.0), (0.0, 0.0, 0.0, 0.0),
+                                    (0.0, 0.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)])
+            user = int(0.01745329251 * amount * 65536.0) if op == FILTER_HUE_ROTATE else int(amount * 65536.0)
+            spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
+            hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (res, op, user, 0))
+            inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+        clear = Clear(color=tuple(v / 255.0 for v in bg) + (1.0,))
+        if ref:
+            ops = [clear, Batch(abi.KIND_BRUSH_SOLID, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS)]
+        else:
+            textures["surface"] = TextureDesc(abi.FMT_RGBA8, sw, sh, data=surf.reshape(sh, sw * 4), filter=abi.LINEAR)
+            ops = [clear, Batch(abi.KIND_BRUSH_BLEND, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                features=abi.FEAT_ALPHA_PASS, color=("surface", "", ""))]
+        out.append(Frame(t.arrays(), textures, [[Target("target", ops=ops)]]))
+    return out[0], out[1]
+
+
 def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
     """Brush(MixBlend) batch (batch.rs:1931-2001): one picture per non-separable /
     separable mix-blend-mode handled in the shader (multiply, overlay, darken,
@@ -1900,6 +1969,75 @@ def reftest_clip_frame(which="clip-mode"):
             spec.append(((130, y0, 230, y0 + 100), green, rad, 1))
         size = (250, 470)
     return rounded_rects_frame(width=size[0], height=size[1], spec=spec, surface=(512, 512))
+
+
+def reftest_box_shadow_frame(which="inset-no-blur-radius"):
+    """wrench/reftests/boxshadow/inset-no-blur-radius.yaml: an INSET box shadow with blur radius 0 takes the frame
+    builder's no-blur path (box_shadow.rs:341-401): a Rectangle primitive = the box (10,10)-(90,90) in the shadow
+    colour under two rounded clips — Clip to the box (radius 10) and ClipOut of the shadow rect = the box moved by the
+    offset (10,10), same radius (spread 0).  A clipped rect of this size is drawn the Indirect way (quad.rs:722-792):
+    off-screen task, one ps_quad_mask per clip multiplied in, textured composite.  Reference image 106x112."""
+    if which == "box-shadow-spread":
+        # boxshadow/box-shadow-spread.yaml: nine inset shadows, spread 10, no blur, no offset, border radii 20..4: the
+        # shadow rect is the box shrunk by the spread, its radius max(r - 10, 0) (adjust_radius_for_box_shadow,
+        # box_shadow.rs:577-583).  Reference image 917x125.
+        blue = (0.0, 0.0, 1.0, 1.0)
+        spec = []
+        for k, r in enumerate([20, 25, 10, 9, 8, 7, 6, 5, 4]):
+            x = 20 + 100 * k
+            spec.append(((x, 20, x + 80, 100), blue, float(r), 0,
+                         [((x + 10.0, 30.0, x + 70.0, 90.0), float(max(r - 10, 0)), 1)]))
+        return rounded_rects_frame(width=917, height=125, spec=spec, surface=(512, 512))
+    if which == "boxshadow-spread-only":
+        # boxshadow/boxshadow-spread-only.yaml: OUTSET, spread 20, no blur, radius 200 on a 400x400 box: the primitive
+        # is the shadow rect (box inflated by the spread, radius 220) clipped OUT of the box (box_shadow.rs:351-367).
+        # Reference image 562x497.  (The reference splits a quad this large into tiles; the per-pixel coverage is the
+        # same whichever tile computes it.)
+        spec = [((20, 20, 460, 460), (0.0, 0.0, 0.0, 1.0), 220.0, 0, [((40.0, 40.0, 440.0, 440.0), 200.0, 1)])]
+        return rounded_rects_frame(width=562, height=497, spec=spec, surface=(512, 512))
+    assert which == "inset-no-blur-radius"
+    red = (1.0, 0.0, 0.0, 1.0)
+    spec = [((10, 10, 90, 90), red, 10.0, 0, [((20.0, 20.0, 100.0, 100.0), 10.0, 1)])]
+    return rounded_rects_frame(width=106, height=112, spec=spec, surface=(256, 256))
+
+
+def reftest_filter_blur_frame():
+    """wrench/reftests/filters/filter-small-blur-radius.yaml: a 512x512 red rect at (100,100) in a stacking context with
+    filter blur(2,2), on the 700x700 page of its reference image.  Draw list (picture.rs:5873-5938, render_task.rs
+    new_blur): the picture surface = the rect inflated by ceil(2) * BLUR_SAMPLE_SCALE = 6 px (524x524 task, content
+    origin (94,94)) drawn with an opaque Quad; std deviation 2 <= MAX_BLUR_STD_DEVIATION so no downscale: one vertical
+    and one horizontal cs_blur COLOR_TARGET pass (blur region = the picture size); the result composited 1:1 by
+    Brush(Image) with premultiplied blending."""
+    from .gpu_types import blur_instance, brush_instance, CLIP_TASK_EMPTY
+    t = FrameTables()
+    W = H = 700
+    inflate, std = 6.0, 2.0
+    x0, y0, x1, y1 = 100.0 - inflate, 100.0 - inflate, 612.0 + inflate, 612.0 + inflate
+    pw, ph = int(x1 - x0), int(y1 - y0)
+    tile_task = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    pic_task = t.add_render_task((0.0, 0.0, float(pw), float(ph)), 1.0, (x0, y0))
+    mid_task = t.add_render_task((0.0, 0.0, float(pw), float(ph)), 1.0, (0.0, 0.0))
+    out_task = t.add_render_task((0.0, 0.0, float(pw), float(ph)), 1.0, (0.0, 0.0))
+    rect = (100.0, 100.0, 612.0, 612.0)
+    prim_f = t.add_quad_prim(rect, rect, (1.0, 0.0, 0.0, 1.0))
+    prim_i = t.add_quad_header(0, 1)
+    qi = quad_instance(prim_i, prim_f, QF_APPLY_DEVICE_CLIP, 0, PART_ALL, INVALID_SEGMENT_INDEX, pic_task)
+    vert = blur_instance(mid_task, pic_task, 1, std, (float(pw), float(ph)))
+    hori = blur_instance(out_task, mid_task, 0, std, (float(pw), float(ph)))
+    addr = t.push_gpu_cache([(1.0, 1.0, 1.0, 1.0), (0.0, 0.0, 0.0, 0.0), (-1.0, -1.0, 0.0, 0.0)])
+    res = t.push_gpu_cache([(0.0, 0.0, float(pw), float(ph)), (0.0, 0.0, 0.0, 0.0)])
+    hdr = t.add_prim_header((x0, y0, x1, y1), (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, tile_task, (4 | (1 << 16), 0, 65535, 0))
+    comp = brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, res)
+    textures = {"pic": TextureDesc(abi.FMT_RGBA8, pw, ph), "mid": TextureDesc(abi.FMT_RGBA8, pw, ph),
+                "blurred": TextureDesc(abi.FMT_RGBA8, pw, ph), "target": TextureDesc(abi.FMT_RGBA8, W, H)}
+    zero = (0.0, 0.0, 0.0, 0.0)
+    return Frame(t.arrays(), textures, [
+        [Target("pic", ops=[Clear(color=zero), Batch(abi.KIND_QUAD_TEXTURED, qi[None, :], blend=abi.BLEND_NONE)])],
+        [Target("mid", ops=[Clear(color=zero), Batch(abi.KIND_BLUR, vert[None, :], features=abi.FEAT_COLOR_TARGET, color=("pic", "", ""))])],
+        [Target("blurred", ops=[Clear(color=zero), Batch(abi.KIND_BLUR, hori[None, :], features=abi.FEAT_COLOR_TARGET, color=("mid", "", ""))])],
+        [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                               Batch(abi.KIND_BRUSH_IMAGE, comp[None, :], blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                     features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("blurred", "", ""))])]])
 
 
 def reftest_gradient_frame(which="linear"):
