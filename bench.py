@@ -305,6 +305,40 @@ def run_other_workload(args):
     dev.close()
 
 
+def workloads_summary(local, flush, steps=5):
+    """The other §8 rows in the default bench line (device-timed, L2 flushed, C++ host mirror per step): what a
+    compositor's frame is made of besides the 1000-layer stress — many small batches (page), the tile composite,
+    clip masks, a text page, a scaled video surface.  ms per frame and launches per frame."""
+    from webrender_b200.device import CudaDevice
+    from webrender_b200.host import HostRenderer
+    out = {}
+    makes = other_workloads()
+    for name in ("page", "composite", "clip_rects", "text", "video_nv12", "images", "gradients"):
+        dev = CudaDevice(local)
+        try:
+            hr = HostRenderer(dev)
+            nf = hr.build(makes[name]())
+            for _ in range(3):
+                hr.render_native(nf)
+            dev.finish()
+            dev.reset_stats()
+            ms = []
+            for _ in range(steps):
+                l2_flush(flush)
+                dev.timer_begin()
+                hr.render_native(nf)
+                ms.append(dev.timer_end())
+            ms.sort()
+            out[name] = {"ms_per_frame": ms[len(ms) // 2], "launches": int(dev.stats()["kernel_launches"] // steps)}
+            nf.destroy()
+            hr.close()
+        except Exception as e:   # informational: never lose the headline line
+            out[name] = {"error": repr(e)[:160]}
+        finally:
+            dev.close()
+    return out
+
+
 def run_update_path(dev, flush, args):
     """§8f rank 3: a 2048^2 R8 glyph atlas arriving as 1024 tile uploads out of one staging blob, and a
     64K-block GPU cache arriving as ~5K Copy records; host memory in, device memory out, per step."""
@@ -780,6 +814,8 @@ def main():
             line["roofline_sweep"] = roofline_sweep(dev, flush, max(5, min(args.steps, 10)), peak)
         if config_e is not None:
             line["config_e"] = config_e
+        if world == 1 and not args.no_sweep:
+            line["workloads"] = workloads_summary(local, flush)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))

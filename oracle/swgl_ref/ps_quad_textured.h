@@ -88,6 +88,26 @@ struct ps_quad_textured_frag : FragmentShaderImpl, ps_quad_textured_vert {
     float chunks = steps * 0.25f;
     v_uv0 += interp_step.v_uv0 * chunks;
   }
+  struct InterpPerspective {
+    vec2 v_uv0;
+  };
+  InterpPerspective interp_perspective;
+  static void read_perspective_inputs(FragmentShaderImpl* impl, const void* init_, const void* step_) {
+    Self* self = (Self*)impl;
+    const InterpInputs* init = (const InterpInputs*)init_;
+    const InterpInputs* step = (const InterpInputs*)step_;
+    Float w = 1.0f / self->gl_FragCoord.w;
+    self->interp_perspective.v_uv0 = init_interp(init->v_uv0, step->v_uv0);
+    self->v_uv0 = self->interp_perspective.v_uv0 * w;
+    self->interp_step.v_uv0 = step->v_uv0 * 4.0f;
+  }
+  ALWAYS_INLINE void step_perspective_inputs(int steps = 4) {
+    this->step_perspective(steps);
+    float chunks = steps * 0.25f;
+    Float w = 1.0f / this->gl_FragCoord.w;
+    interp_perspective.v_uv0 += interp_step.v_uv0 * chunks;
+    v_uv0 = w * interp_perspective.v_uv0;
+  }
 
   // sample_color0.glsl:25-31
   vec4 fs_sample_color0() {
@@ -129,7 +149,7 @@ struct ps_quad_textured_frag : FragmentShaderImpl, ps_quad_textured_vert {
     DISPATCH_DRAW_SPAN(self, RGBA8);
   }
 
-  WR_FRAGMENT_ABI()
+  WR_FRAGMENT_ABI_W()
 
   ps_quad_textured_frag() {
     init_fragment_abi();

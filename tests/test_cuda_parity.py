@@ -533,12 +533,14 @@ def _swgl():
 
 
 @pytest.mark.parametrize("cam", PERSP_CAMERAS)
-@pytest.mark.parametrize("kind", ["solid", "solid_aa", "image", "image_nearest"])
+@pytest.mark.parametrize("kind", ["solid", "solid_aa", "image", "image_nearest", "quad"])
 def test_perspective_brushes(kind, cam):
     """draw_perspective (rasterize.h:1422-1545): near-plane clipping, polygon edge walk, per-sample z and
     1/w-corrected varyings — byte-exact against SWGL."""
     d, ry, rx = cam
-    if kind.startswith("image"):
+    if kind == "quad":
+        f = scenes.perspective_frame("quad", height=400, d=d, ry=ry, rx=rx, seed=2)
+    elif kind.startswith("image"):
         f = scenes.perspective_frame("image", d=d, ry=ry, rx=rx, seed=2,
                                      filter=abi.NEAREST if kind == "image_nearest" else abi.LINEAR)
     else:
@@ -570,3 +572,10 @@ def test_page_of_many_small_batches(seed):
     names = ["mask", "tile0", "tile1", "tile2", "tile3", "fb"]
     assert_same(render(CudaDevice, f, names), render(OracleDevice, f, names))
     assert_same(render(CudaDevice, f, ["fb"], tile_lists=True), render(OracleDevice, f, ["fb"]))
+
+
+@pytest.mark.parametrize("rot", [17.0, -33.5])
+def test_rotated_textured_quads(rot):
+    """ps_quad_textured under a rotated spatial node (the Indirect path's composite quads): edge walk + textured spans."""
+    f = scenes.rounded_rects_frame(seed=2, rotate=rot)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), f"rot {rot}")

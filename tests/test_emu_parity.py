@@ -408,7 +408,7 @@ def _swgl():
 
 
 @pytest.mark.parametrize("cam", PERSP_CAMERAS)
-@pytest.mark.parametrize("kind", ["solid", "solid_aa", "image"])
+@pytest.mark.parametrize("kind", ["solid", "solid_aa", "image", "quad"])
 def test_perspective_brushes(kind, cam):
     """draw_perspective (rasterize.h:1422-1545): w differs between the vertices — near-plane clipping (the d=220
     cameras put part of the page behind the eye), the polygon edge walk, per-sample z and 1/w-corrected varyings."""
@@ -416,8 +416,11 @@ def test_perspective_brushes(kind, cam):
     kw = dict(seed=3, n_opaque=6, n_alpha=12)
     if kind == "solid_aa":
         kw.update(seed=4, force_aa=True)
-    f = scenes.perspective_frame("image" if kind == "image" else "solid", d=d, ry=ry, rx=rx,
-                                 **({"seed": 2} if kind == "image" else kw))
+    if kind == "quad":   # ps_quad_textured: the textured composite quads of the Indirect path under the 3-D node
+        f = scenes.perspective_frame("quad", height=400, d=d, ry=ry, rx=rx, seed=2)
+    else:
+        f = scenes.perspective_frame("image" if kind == "image" else "solid", d=d, ry=ry, rx=rx,
+                                     **({"seed": 2} if kind == "image" else kw))
     assert_same(render(EmuDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
 
 

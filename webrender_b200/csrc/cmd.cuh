@@ -121,4 +121,4 @@ struct BatchInfo {
   int fail_alloc;          // words of the depth-run bitmap pool handed out to this batch's commands
   int n_noncopy;           // composite: drawn commands that are not CMD_COPY (0: the tile kernel has nothing to do)
 };
-#define WR_ROW_TAB_MIN 16
+#define WR_ROW_TAB_MIN 4   // glyph rows (~12) too: the per-(command,row,tile) walk was a third of the text kernel

@@ -614,7 +614,7 @@ struct QuadShader {
     const CmdCold& k = a.cold[c.cold];
     wr_row_interp<2>(a, k, c, y, r.o, r.step);
     int len = c.x1 - c.x0;
-    int body_len = (rgba && len >= 4 && !(c.flags & CMD_OUT_RRRR)) ? (len & ~3) : 0;
+    int body_len = (rgba && len >= 4 && !(c.flags & CMD_OUT_RRRR) && !a.persp) ? (len & ~3) : 0;  // (no span shaders under perspective)
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
@@ -633,7 +633,7 @@ struct QuadShader {
       // only the fragment-shader tail applies .rrrr.  R8 targets have no span
       // shader: always the fragment path.
       if (c.flags & CMD_OUT_RRRR) {
-        int body_len0 = (rgba && len >= 4) ? (len & ~3) : 0;
+        int body_len0 = (rgba && len >= 4 && !a.persp) ? (len & ~3) : 0;
         if (rel >= body_len0) col.b = col.g = col.a = col.r;
       }
       return col;

@@ -255,6 +255,9 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
     c->immediate = e && atoi(e) != 0;
     e = getenv("WRCU_PDL");
     c->pdl = e ? atoi(e) != 0 : true;
+    e = getenv("WRCU_SIDE_CTAS");
+    c->side_ctas_per_sm = e ? atoi(e) : 1;
+    if (c->side_ctas_per_sm < 1 || c->side_ctas_per_sm > 3) c->side_ctas_per_sm = 1;
     e = getenv("WRCU_STREAMS");
     c->n_streams = e ? atoi(e) : 8;
     if (c->n_streams < 1) c->n_streams = 1;
@@ -1458,7 +1461,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
 #endif
   // draw_perspective (w differs between an instance's vertices): the kinds whose fragment stage carries the
   // per-sample 1/w path; the solid colour case of ps_quad_textured shares brush_solid's shader
-  sa.persp_ok = kind == WRCU_KIND_BRUSH_SOLID || kind == WRCU_KIND_SPLIT_COMPOSITE ||
+  sa.persp_ok = kind == WRCU_KIND_BRUSH_SOLID || kind == WRCU_KIND_SPLIT_COMPOSITE || kind == WRCU_KIND_QUAD_TEXTURED ||
                 (kind == WRCU_KIND_BRUSH_IMAGE && !(features & WRCU_FEAT_REPETITION));
   sa.copy_ok = !T.depth && (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA);
   if (kind == WRCU_KIND_COMPOSITE && sa.copy_ok && !(features & WRCU_FEAT_YUV)) {
@@ -1725,7 +1728,12 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
   if (op.sa.depth_runs) {
     // depth runs: the failing-sample bitmaps of this batch, before any of its depth writes
     ra.fail_pool = c->fail_pool;
-    wr_depth_fail_rows<<<c->sm_count * 4, 256, 0, c->launch_stream>>>(ra, c->fail_pool);
+    // grid: a CTA per command in the command-major mode (n >= 48, see the kernel), else row groups over the chip —
+    // a quarter of it when other render targets' kernels share the GPU (side streams)
+    int fgrid = c->sm_count * 4;
+    if (n >= 48) fgrid = n < fgrid ? n : fgrid;
+    else if (c->side_reduce) fgrid = c->sm_count * c->side_ctas_per_sm;
+    wr_depth_fail_rows<<<fgrid, 256, 0, c->launch_stream>>>(ra, c->fail_pool);
     c->stats.kernel_launches++;
   }
 #endif
@@ -1775,7 +1783,11 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
   // generic kernels: persistent CTAs over the batch's tiles; 3 CTAs of 256 threads per SM
   // cover every shader's register budget (<= 128 regs/thread would allow 2; most use 80)
   const int total_tiles = (int)(grid.x * grid.y);
-  const int pgrid = total_tiles < c->sm_count * 3 ? total_tiles : c->sm_count * 3;
+  // On a side stream (several render targets in flight) a small batch takes one persistent CTA per SM instead of
+  // three: its CTAs each walk more tiles, but the start-up wave of a 444-CTA launch no longer holds every CTA slot
+  // of the chip while most of its CTAs find no tile.
+  const int max_ctas = (c->side_reduce && n <= 256) ? c->sm_count * c->side_ctas_per_sm : c->sm_count * 3;
+  const int pgrid = total_tiles < max_ctas ? total_tiles : max_ctas;
 #define LAUNCH_RASTER(S)                                                         \
   do {                                                                           \
     auto k_rgba = wr_raster<S, WRCU_FMT_RGBA8>;                                   \
@@ -2011,6 +2023,7 @@ static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
     if (t == targets.size()) targets.push_back(tgt);
     strm[i] = (int)(t % (size_t)NS);
   }
+  c->side_reduce = targets.size() >= 4;  // enough independent targets in flight to fill the chip between them
   // fork
   WRCU_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
   std::vector<char> used((size_t)NS, 0), need_ev(n, 0);
@@ -2036,10 +2049,11 @@ static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
     c->launch_stream = st;
     if (op.type == 1) op.ra.pdl_early = c->pdl ? 1 : 0;  // the set-up launch finished before the fork event
     int rc = op.type == 0 ? launch_clear(c, op) : launch_raster(c, op);
-    if (rc != WRCU_OK) { c->launch_stream = c->stream; return rc; }
+    if (rc != WRCU_OK) { c->launch_stream = c->stream; c->side_reduce = false; return rc; }
     if (need_ev[i]) WRCU_CUDA(c, cudaEventRecord(c->op_events[i], st));
   }
   c->launch_stream = c->stream;
+  c->side_reduce = false;
   // join
   for (int sidx = 0; sidx < NS; sidx++) {
     if (!used[(size_t)sidx]) continue;

@@ -162,6 +162,8 @@ struct wrcu_ctx {
   bool in_flush = false;
   // side streams of a submission (flush_multi_stream): one per render target, round robin (WRCU_STREAMS, 1 = off)
   int n_streams = 8;
+  bool side_reduce = false;      // set while a submission with >= 4 render targets is being launched
+  int side_ctas_per_sm = 1;      // persistent CTAs per SM of a small batch's raster kernel on a side stream (WRCU_SIDE_CTAS)
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> op_events, join_ev;
   cudaEvent_t fork_ev = nullptr;

@@ -208,7 +208,7 @@ def scale_matrix(s):
 
 
 def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=False, device_pixel_scale=1.0,
-                        filter=abi.LINEAR, spec=None, surface=(512, 512)):
+                        filter=abi.LINEAR, spec=None, surface=(512, 512), rotate=None):
     """Config A flavour (wrench/reftests/aa/rounded-rects.yaml): solid rects with
     rounded-rect clips drawn the Indirect way (quad.rs:722-792, 239-264):
       pass 0, off-screen colour target: each rect as an untextured Quad with
@@ -222,6 +222,9 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
     sw, sh = surface
     tile_task = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
     prims, masks_fast, masks_slow, composites = [], [], [], []
+    # `rotate`: the textured quads that composite the off-screen tasks into the tile sit under a transformed spatial
+    # node (a rotation, or via with_transform any 4x4 — a perspective one sends them through draw_perspective)
+    cxf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0), axis_aligned=False) if rotate is not None else 0
     cursor_x, cursor_y, row_h = 0, 0, 0
     s = device_pixel_scale
     if spec is not None:
@@ -285,7 +288,7 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
         # composite: textured quad, uv rect = the task rect in the off-screen surface
         cprim_f = t.add_quad_prim(rect, rect, (1.0, 1.0, 1.0, 1.0),
                                   uv_rect=(float(tx), float(ty), float(tx + w), float(ty + h)))
-        cprim_i = t.add_quad_header(0, 100 + i)
+        cprim_i = t.add_quad_header(cxf, 100 + i)
         composites.append(quad_instance(cprim_i, cprim_f, QF_APPLY_DEVICE_CLIP, 0, PART_ALL, INVALID_SEGMENT_INDEX,
                                         tile_task))
     textures = {"surface": TextureDesc(abi.FMT_RGBA8, sw, sh, filter=filter),
@@ -581,7 +584,7 @@ def perspective_frame(kind="solid", width=640, height=360, d=800.0, ry=35.0, rx=
     rasterize.h:1422-1545): kind = "solid" (brush_solid_frame: opaque + alpha with masks / AA) or "image"
     (image_frame: opaque + alpha pass sampling an atlas)."""
     m = perspective_matrix(width, height, d, ry, rx)
-    make = {"solid": brush_solid_frame, "image": image_frame}[kind]
+    make = {"solid": brush_solid_frame, "image": image_frame, "quad": rounded_rects_frame}[kind]
     return with_transform(make, m, width=width, height=height, **kw)
 
 
