@@ -159,7 +159,8 @@ _REF = {}
 def _ref_init(kind, w, h, n):
     sys.path.insert(0, ROOT)
     from oracle.backends import OracleDevice, SwglDevice
-    from webrender_b200 import scenes, draw_frame
+    from webrender_b200 import draw_frame
+    from workloads import scenes
     _REF["frame"] = scenes.alpha_rects_frame(w, h, n)
     _REF["dev"] = (SwglDevice if kind == "reference" else OracleDevice)()
     _REF["handles"] = draw_frame(_REF["dev"], _REF["frame"])
@@ -176,7 +177,8 @@ def cpu_baseline_sample():
     """1-core SWGL (or port) on a bounded sample of config B: timed beside the
     GPU number; reported, not a target."""
     from oracle.backends import OracleDevice, SwglDevice, have_swgl
-    from webrender_b200 import scenes, draw_frame
+    from webrender_b200 import draw_frame
+    from workloads import scenes
     kind = "reference" if have_swgl() else "port"
     w, h, n = W, 270, 200  # 1/8 of the frame height, 200 layers
     f = scenes.alpha_rects_frame(w, h, n)
@@ -201,7 +203,8 @@ def cpu_baseline_sample():
 # device-timed with the reference's CPU implementation beside it.  Not the contract's bench line
 # (that is config B, the default); run with --workload NAME.
 def other_workloads():
-    from webrender_b200 import abi, scenes
+    from webrender_b200 import abi
+    from workloads import scenes
     return {
         "b_prime": lambda: scenes.alpha_rects_frame(W, H, 1000, random_rects=True, seed=1, color=None),
         "text": lambda: scenes.text_frame(width=W, height=H, n_runs=68, glyphs_per_run=89, seed=2, atlas_size=2048),
@@ -434,7 +437,8 @@ def roofline_sweep(dev, flush, steps, peak):
     kernel actually moves (target once in, once out = 2 x 33.2 MB; ncu-measured figures per L are in
     profiles/) with its fraction of the measured HBM peak."""
     import torch
-    from webrender_b200 import abi, scenes
+    from webrender_b200 import abi
+    from workloads import scenes
     from webrender_b200.frame import Batch, Clear
     from webrender_b200.gpu_types import ortho
     tgt = dev.texture_create(abi.FMT_RGBA8, W, H)
@@ -616,7 +620,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from webrender_b200 import abi, scenes
+    from webrender_b200 import abi
+    from workloads import scenes
     from webrender_b200.device import CudaDevice
     from webrender_b200.frame import Batch, Clear
     from webrender_b200.gpu_types import ortho

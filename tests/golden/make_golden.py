@@ -93,7 +93,7 @@ CASES = [
 def main():
     from common import render
     from oracle.backends import SwglDevice
-    from webrender_b200 import scenes
+    from workloads import scenes
     index = {}
     regenerate_all = "--all" in sys.argv   # default: only cases whose fixture is missing
     for case in CASES:

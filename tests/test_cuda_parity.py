@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle.backends import OracleDevice
-from webrender_b200 import abi, scenes
+from webrender_b200 import abi
+from workloads import scenes
 from webrender_b200.device import CudaDevice
 
 from common import assert_same, render

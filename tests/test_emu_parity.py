@@ -4,7 +4,8 @@ aid for a box without a GPU; the parity tests proper are test_cuda_parity.py."""
 import pytest
 
 from oracle.backends import OracleDevice
-from webrender_b200 import abi, scenes
+from webrender_b200 import abi
+from workloads import scenes
 
 from common import assert_same, render
 from emu import EmuDevice

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.backends import OracleDevice
-from webrender_b200 import scenes
+from workloads import scenes
 
 from common import render
 

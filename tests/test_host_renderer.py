@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 from oracle.backends import OracleDevice
-from webrender_b200 import abi, scenes
+from webrender_b200 import abi
+from workloads import scenes
 
 from common import render
 

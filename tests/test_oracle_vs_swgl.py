@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 from oracle.backends import OracleDevice, SwglDevice, have_swgl
-from webrender_b200 import abi, scenes
+from webrender_b200 import abi
+from workloads import scenes
 
 from common import assert_same, render
 

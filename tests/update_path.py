@@ -11,7 +11,8 @@ scratch texture (texture-cache defragmentation), and the frame is drawn again.
 """
 import numpy as np
 
-from webrender_b200 import abi, scenes
+from webrender_b200 import abi
+from workloads import scenes
 from webrender_b200.frame import draw_frame
 
 

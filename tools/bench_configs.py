@@ -18,7 +18,8 @@ def main():
     ap.add_argument("--only", default="", help="substring of the config name to run alone")
     args = ap.parse_args()
     import torch
-    from webrender_b200 import abi, multi_gpu, scenes
+    from webrender_b200 import abi, multi_gpu
+    from workloads import scenes
     from webrender_b200.device import CudaDevice
     from webrender_b200.frame import draw_frame
 

@@ -6,9 +6,9 @@ scene; deterministic (seeded numpy RNG), no file or network input.
 """
 import numpy as np
 
-from . import abi
-from .frame import Batch, Clear, Frame, Target, TextureDesc
-from .gpu_types import (FrameTables, INVALID_SEGMENT_INDEX, PART_ALL, QF_APPLY_DEVICE_CLIP, quad_instance)
+from webrender_b200 import abi
+from webrender_b200.frame import Batch, Clear, Frame, Target, TextureDesc
+from webrender_b200.gpu_types import (FrameTables, INVALID_SEGMENT_INDEX, PART_ALL, QF_APPLY_DEVICE_CLIP, quad_instance)
 
 
 def alpha_rects_frame(width=3840, height=2160, n_rects=1000, random_rects=False, seed=1,
@@ -92,7 +92,7 @@ def brush_solid_frame(width=640, height=360, n_opaque=12, n_alpha=24, seed=1, wi
     (renderer/mod.rs:2804-2969): an opaque batch front-to-back with depth
     LEQUAL + write, then an alpha batch with premultiplied blending, depth test
     only, and per-instance clip masks sampled from an R8 alpha target."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
@@ -167,7 +167,7 @@ def clip_mask_frame(width=512, height=384, n_clips=10, seed=1, fractional=False,
     blending off, then secondary clips multiplied in (ZERO, SRC_COLOR).  Mixes
     the FAST_PATH (uniform radius) and general (per-corner elliptical radii)
     programs and both clip modes."""
-    from .gpu_types import clip_rect_instance
+    from webrender_b200.gpu_types import clip_rect_instance
     rng = np.random.RandomState(seed)
     t = FrameTables()
     xf = t.add_transform(scale_matrix(scale)) if scale != 1.0 else 0
@@ -216,7 +216,7 @@ def rounded_rects_frame(width=640, height=400, n_rects=6, seed=1, fractional=Fal
         ps_quad_mask (FAST_PATH for a uniform radius) (handle_clips, mod.rs:2278);
       pass 1, picture-cache tile: one textured Quad per rect sampling the
         off-screen task, premultiplied-alpha blended."""
-    from .gpu_types import mask_instance, QF_IS_MASK
+    from webrender_b200.gpu_types import mask_instance, QF_IS_MASK
     rng = np.random.RandomState(seed)
     t = FrameTables()
     sw, sh = surface
@@ -310,7 +310,7 @@ def image_frame(width=640, height=360, n_opaque=8, n_alpha=20, seed=1, filter=ab
     alpha batch (premultiplied over, depth test) sampling one RGBA8 atlas, with
     colour modes Image / ColorBitmap / Alpha(drop-shadow override), 1:1 and
     scaled mappings, plus segment-relative texel-rect (nine-patch style) instances."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -387,7 +387,7 @@ def page_frame(width=3840, height=2160, tile_w=1024, tile_h=512, seed=1, clips=1
     target: clear, opaque solids and images front to back with depth write, then alpha batches in order — masked /
     anti-aliased solids, images, a linear gradient, two text runs; (3) the tile list composited into the framebuffer.
     ~7 batches per tile x 20 tiles + masks + composite = ~150 draws of 2-60 instances each."""
-    from .gpu_types import (brush_instance, glyph_instance, clip_rect_instance, composite_instance,
+    from webrender_b200.gpu_types import (brush_instance, glyph_instance, clip_rect_instance, composite_instance,
                             build_gradient_table, CLIP_TASK_EMPTY)
     rng = np.random.RandomState(seed)
     t = FrameTables()
@@ -595,7 +595,7 @@ def split_composite_frame(width=640, height=360, n_polys=10, seed=1, d=600.0, ry
     depth test, behind a few opaque Brush(Solid) prims.  Polygon points are in the picture's local space; the
     prim header carries the picture rect and its (perspective) transform, user_data = [ImageSource address,
     perspective_interpolate, 0, clip task]; the ImageSource has the UvRectKind::Quad corner block."""
-    from .gpu_types import brush_instance, split_composite_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, split_composite_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -656,7 +656,7 @@ def image_repeat_frame(width=640, height=360, n_opaque=6, n_alpha=14, seed=1, fi
     (shade.rs:985-1000 "ANTIALIASING,REPETITION"): stretch sizes smaller than the primitive
     (background-repeat), segment-relative REPEAT_X / REPEAT_Y with ROUND and CENTERED flags and
     texel-rect nine-patch middles (border-image-repeat), small (few-texel) tiles and 1:1 tiles."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
@@ -745,7 +745,7 @@ def text_frame(width=960, height=540, n_runs=12, glyphs_per_run=40, seed=2, atla
     BatchFeatures::GLYPH_TRANSFORM (glyphs rasterised in the transformed space, quads trimmed to the
     glyph rect by gl_ClipDistance); clip_runs gives every other run a local clip rect that cuts
     through its glyphs (the non-"inside" branch of ps_text_run.glsl:160-167)."""
-    from .gpu_types import glyph_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import glyph_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
@@ -837,7 +837,7 @@ def gradient_frame(width=640, height=360, n_grad=6, seed=1, fractional=False, fu
     Brush(LinearGradient) instances; under is_software non-tiled linear gradients
     stay uncached brushes (scene_building.rs:3392-3396).  Each has its own
     130-entry two-colour LUT in gpu_buffer_f."""
-    from .gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -897,7 +897,7 @@ def cached_gradient_frame(kind, width=1024, height=512, n_tasks=6, seed=1, repea
     in a texture-cache RGBA8 target.  kind = KIND_{FAST_LINEAR,LINEAR,RADIAL,CONIC}_GRADIENT.
     Parameters follow the task builders in prim_store/gradient/{linear,radial,conic}.rs:
     points/radii in task-local device pixels, `scale` = prim size / task size."""
-    from . import gpu_types as G
+    from webrender_b200 import gpu_types as G
     rng = np.random.RandomState(seed)
     t = FrameTables()
     inst = []
@@ -973,7 +973,7 @@ def line_decoration_frame(width=512, height=256, n_tasks=24, seed=1):
     blending on, one LineDecorationJob per cached tile: solid / dotted / dashed /
     wavy, horizontal and vertical, at device scales 1, 1.5 and 2 (the task rect is
     the local size times the device scale, so the AA range varies)."""
-    from . import gpu_types as G
+    from webrender_b200 import gpu_types as G
     rng = np.random.RandomState(seed)
     pack = _ShelfPacker(width, height)
     inst = []
@@ -1020,7 +1020,7 @@ def border_frame(kind, width=1024, height=512, n_borders=6, seed=1, scale=1.0):
     KIND_BORDER_SEGMENT (double/dotted/dashed/groove/ridge/inset/outset).
     Dash and dot positions along a corner use uniform ellipse angles where the
     reference solves for arc length (the frame builder is outside this path)."""
-    from . import gpu_types as G
+    from webrender_b200 import gpu_types as G
     rng = np.random.RandomState(seed)
     pack = _ShelfPacker(width, height)
     inst = []
@@ -1182,7 +1182,7 @@ def quad_gradient_frame(kind, width=640, height=360, n_quads=8, seed=1, fraction
     """Quad(RadialGradient) / Quad(ConicGradient) primitives through the quad path
     (prim_store/gradient/{radial,conic}.rs `write_prim_gpu_blocks` → ps_quad_*_gradient):
     pattern_input = (gradient parameter blocks, stops LUT) in gpu_buffer_f."""
-    from . import gpu_types as G
+    from webrender_b200 import gpu_types as G
     rng = np.random.RandomState(seed)
     t = FrameTables()
     task = t.add_render_task((0.0, 0.0, float(width), float(height)), device_pixel_scale, (0.0, 0.0))
@@ -1226,8 +1226,8 @@ def reftest_cached_gradient_frame(which="premultiplied-radial"):
     cs_conic_gradient, task size = stretch size, scale 1) into a texture-cache target; pass 1
     composites the task 1:1 with Brush(Image) (premultiplied-alpha blend, white colour) onto
     the white 300x300 page at (50,50)."""
-    from . import gpu_types as G
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200 import gpu_types as G
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     W = H = 300
     red, green, blue, black = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0), (0.0, 0.0, 0.0, 1.0)
     clear = (0.0, 0.0, 0.0, 0.0)
@@ -1285,7 +1285,7 @@ def box_shadow_frame(width=512, height=384, n_clips=8, seed=1, fractional=False,
     with blending off for first clips, then one multiplied in.  Each instance
     nine-patches (Stretch) or scales (Simple) a blurred R8 mask into its task
     rect; every other one is ClipOut."""
-    from .gpu_types import box_shadow_instance
+    from webrender_b200.gpu_types import box_shadow_instance
     rng = np.random.RandomState(seed)
     t = FrameTables()
     xf = t.add_transform(scale_matrix(scale)) if scale != 1.0 else 0
@@ -1347,7 +1347,7 @@ def composite_frame(width=640, height=384, tile_w=256, tile_h=128, seed=1, exter
     tiles punch holes with premultiplied dest-out, alpha tiles and solid-colour
     tiles (1x1 dummy texture) go over back to front.  `external` adds RGB
     external surfaces: unnormalised uv sub-rects, linear filter, scaling, flips."""
-    from .gpu_types import composite_instance
+    from webrender_b200.gpu_types import composite_instance
     rng = np.random.RandomState(seed)
     textures = {"fb": TextureDesc(abi.FMT_RGBA8, width, height),
                 "dummy": TextureDesc(abi.FMT_RGBA8, 1, 1, data=np.full((1, 4), 255, dtype=np.uint8),
@@ -1437,7 +1437,7 @@ def yuv_composite_frame(fmt="planar", color_space=2, seed=1, width=512, height=3
     CompositeSurfaceFormat::Yuv): 8-bit PLANAR (three R8 planes), NV12 (R8 + RG8) or INTERLEAVED
     (one BGRA plane); 1:1, up- and down-scaled, flipped and clipped surfaces with texel-space uv
     sub-rects, chroma at half resolution."""
-    from .gpu_types import (composite_yuv_instance, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED)
+    from webrender_b200.gpu_types import (composite_yuv_instance, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED)
     rng = np.random.RandomState(seed * 31 + color_space)
     vw, vh = 192, 128
     planes = yuv_planes(vw, vh, seed + 5, fmt)
@@ -1484,7 +1484,7 @@ def yuv_image_frame(fmt="planar", color_space=2, seed=1, width=512, height=320, 
     [channel_bit_depth, colour space, format, 0], user data = the gpu-cache addresses of the planes'
     ImageSource entries.  Opaque pass (blend off) or alpha pass (premultiplied blend; AA edges, clip
     masks, optionally a rotated spatial node)."""
-    from .gpu_types import (brush_instance, CLIP_TASK_EMPTY, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12,
+    from webrender_b200.gpu_types import (brush_instance, CLIP_TASK_EMPTY, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12,
                             YUV_FORMAT_INTERLEAVED)
     rng = np.random.RandomState(seed * 17 + color_space)
     t = FrameTables()
@@ -1548,7 +1548,7 @@ def reftest_yuv_frame(ref_dir="/root/reference/wrench/reftests/image"):
     swgl_ext.h:1069-1075) — Color8, Rec709, limited range (yaml_frame_reader.rs:1203-1206), as opaque
     Brush(YuvImage) primitives on the white 1323x658 page.  Reads the reference's own plane PNGs."""
     from PIL import Image
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED
     import os
 
     def load(name):
@@ -1558,7 +1558,7 @@ def reftest_yuv_frame(ref_dir="/root/reference/wrench/reftests/image"):
         rgb = np.array(im.convert("RGB"), dtype=np.uint8)
         bgra = np.concatenate([rgb[..., ::-1], np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
         return abi.FMT_RGBA8, bgra.reshape(rgb.shape[0], rgb.shape[1] * 4)
-    from .gpu_types import composite_instance
+    from webrender_b200.gpu_types import composite_instance
     W, H = 1323, 658
     t = FrameTables()
     textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H)}
@@ -1599,7 +1599,7 @@ def reftest_yuv_frame(ref_dir="/root/reference/wrench/reftests/image"):
 def video_frame(width=3840, height=2160, vw=1920, vh=1080, fmt="nv12", color_space=2, seed=1):
     """One full-screen video surface: a vw x vh 8-bit YUV frame (NV12 by default, Rec.709 narrow
     range) scaled to the whole framebuffer by `composite` YUV — the compositor's video case."""
-    from .gpu_types import (composite_yuv_instance, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED)
+    from webrender_b200.gpu_types import (composite_yuv_instance, YUV_FORMAT_PLANAR, YUV_FORMAT_NV12, YUV_FORMAT_INTERLEAVED)
     planes = yuv_planes(vw, vh, seed, fmt)
     names = {"planar": ("vy", "vu", "vv"), "nv12": ("vy", "vuv", ""), "interleaved": ("vyuv", "", "")}[fmt]
     fmts = {"planar": (abi.FMT_R8,) * 3, "nv12": (abi.FMT_R8, abi.FMT_RG8), "interleaved": (abi.FMT_RGBA8,)}[fmt]
@@ -1637,7 +1637,7 @@ def opacity_frame(width=640, height=360, n_prims=14, seed=1, fractional=False, o
     """Brush(Opacity) batch (batch.rs:1671-1712): pictures with a filter:
     opacity() drawn from their off-screen surface, premultiplied-alpha blended;
     prim user data = [uv_rect_address, amount * 65536, 0, 0]."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -1663,7 +1663,7 @@ def clear_frame(width=512, height=320, seed=1, r8=False):
     3971-3994): rects cleared by ClearInstance quads with depth forced to the
     far plane (so a depth-writing clear also resets depth), between batches of
     opaque depth-tested solid brushes."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -1710,7 +1710,7 @@ def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=F
     contrast, grayscale, hue-rotate, invert, saturate, sepia, brightness, colour
     matrix, sRGB<->linear, flood and a component transfer (table / discrete /
     linear / gamma) — each reading its off-screen surface through sColor0."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -1783,7 +1783,7 @@ def filter_reftest_frames(name, size=(220, 220)):
     """(test frame, reference frame) of one of FILTER_REFTESTS: the filtered rects as Brush(Blend) instances reading
     uniform picture surfaces (premultiplied 8-bit, as the picture pass leaves them), the reference rects as alpha
     Brush(Solid) instances, both premultiplied-over the page colour."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     bg, cases, _ = FILTER_REFTESTS[name]
     w, h = size
     out = []
@@ -1829,7 +1829,7 @@ def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
     lighten, colour-dodge, colour-burn, hard-light, soft-light, difference, hue,
     saturation, colour, luminosity): sColor0 = backdrop readback, sColor1 = the
     picture's own surface; user data = [mode, backdrop uv, source uv, 0]."""
-    from .gpu_types import brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
     rng = np.random.RandomState(seed)
     t = FrameTables()
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
@@ -1876,7 +1876,7 @@ def blur_frame(width=384, height=256, seed=1, color=False, sigmas=(1.0, 2.5, 6.0
     the final target — ALPHA_TARGET (R8 box-shadow masks) or COLOR_TARGET (RGBA8
     filter blurs).  Regions sit at different offsets so the clamped sampling at
     the region edges is exercised."""
-    from .gpu_types import blur_instance
+    from webrender_b200.gpu_types import blur_instance
     rng = np.random.RandomState(seed)
     t = FrameTables()
     fmt = abi.FMT_RGBA8 if color else abi.FMT_R8
@@ -2011,7 +2011,7 @@ def reftest_filter_blur_frame():
     origin (94,94)) drawn with an opaque Quad; std deviation 2 <= MAX_BLUR_STD_DEVIATION so no downscale: one vertical
     and one horizontal cs_blur COLOR_TARGET pass (blur region = the picture size); the result composited 1:1 by
     Brush(Image) with premultiplied blending."""
-    from .gpu_types import blur_instance, brush_instance, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import blur_instance, brush_instance, CLIP_TASK_EMPTY
     t = FrameTables()
     W = H = 700
     inflate, std = 6.0, 2.0
@@ -2047,7 +2047,7 @@ def reftest_gradient_frame(which="linear"):
     """wrench/reftests/gradient/linear.yaml (four hard-stop bands), linear-reverse.yaml
     and linear-hard-stop.yaml as ONE Brush(LinearGradient) each on a 300x300 white
     page — the uncached brush path an `is_software` frame builder keeps."""
-    from .gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
+    from webrender_b200.gpu_types import brush_instance, build_gradient_table, CLIP_TASK_EMPTY
     W = H = 300
     red, green, blue, black = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0), (0.0, 0.0, 0.0, 1.0)
     clear = (0.0, 0.0, 0.0, 0.0)
