@@ -80,6 +80,10 @@ CASES = [
     ("split_composite", "split_composite_frame", dict(seed=1), False),
     ("split_composite_near_plane", "split_composite_frame", dict(seed=2, d=220.0, ry=65.0, rx=20.0, perspective_interpolate=1),
      False),
+    ("reftest_border_overlapping", "reftest_border_overlapping_frame", dict()),
+    ("reftest_border_no_bogus_line", "reftest_border_no_bogus_line_frame", dict()),
+    # wrench/reftests/split/near-plane.yaml (also checked against the reference's own PNG: 0 pixels differ)
+    ("reftest_split_near_plane", "reftest_split_near_plane_frame", dict(), False),
     ("reftest_inset_no_blur_radius", "reftest_box_shadow_frame", dict(which="inset-no-blur-radius")),
     ("reftest_box_shadow_spread", "reftest_box_shadow_frame", dict(which="box-shadow-spread")),
     ("reftest_boxshadow_spread_only", "reftest_box_shadow_frame", dict(which="boxshadow-spread-only")),

@@ -117,6 +117,55 @@ def test_box_shadow_reftests_against_reference_png(which, png, max_diff, max_px)
     assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))
 
 
+def test_border_overlapping_reftest_against_reference_png():
+    """wrench/reftests/border/overlapping.yaml == overlapping.png under fuzzy-if(platform(swgl),1,20): overlapping
+    corner ellipses of a complex clip.  Measured: 0 pixels differ."""
+    path = "/root/reference/wrench/reftests/border/overlapping.png"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_border_overlapping_frame()
+    out = render(OracleDevice, f, ["target"])["target"].reshape(240, 233, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref).max(axis=2)
+    assert d.max() <= 1 and int((d > 0).sum()) <= 20, (int(d.max()), int((d > 0).sum()))
+
+
+def test_border_no_bogus_line_reftest_against_reference_png():
+    """wrench/reftests/border/border-no-bogus-line.yaml == border-no-bogus-line-ref.png under
+    fuzzy-if(platform(swgl),1,8): a rounded solid border whose radii are scaled to fit (corner tasks by cs_border_solid,
+    segments by Brush(Image) from the texture cache).  Measured: 0 pixels differ."""
+    path = "/root/reference/wrench/reftests/border/border-no-bogus-line-ref.png"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_border_no_bogus_line_frame()
+    out = render(OracleDevice, f, ["target"])["target"].reshape(108, 116, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref).max(axis=2)
+    assert d.max() <= 1 and int((d > 0).sum()) <= 8, (int(d.max()), int((d > 0).sum()))
+
+
+def test_split_near_plane_reftest_against_reference_png():
+    """wrench/reftests/split/near-plane.yaml == near-plane.png (fuzzy(1,20); fuzzy-if(platform(swgl),128,39)): one
+    plane-split polygon crossing the near plane, drawn by ps_split_composite from the picture's surface — the
+    perspective path (draw_perspective with frustum clipping, rasterize.h:1064-1545) against an image the reference's
+    authors checked in.  Drawn by the reference build (the plain-C port does not restate perspective); the same
+    bytes are a golden the emulated and the CUDA kernels must reproduce.  Measured: 0 pixels differ."""
+    path = "/root/reference/wrench/reftests/split/near-plane.png"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    from oracle.backends import SwglDevice
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_split_near_plane_frame()
+    out = render(SwglDevice, f, ["target"])["target"].reshape(600, 600, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref).max(axis=2)
+    assert d.max() <= 128 and int((d > 0).sum()) <= 39, (int(d.max()), int((d > 0).sum()))
+    want = np.load(os.path.join(HERE, "reftest_split_near_plane.npz"))["target"]
+    assert np.array_equal(render(SwglDevice, f, ["target"])["target"], want)
+
+
 def _filter_reftest(device_cls, name):
     _, cases, (max_diff, max_px) = scenes.FILTER_REFTESTS[name]
     ft, fr = scenes.filter_reftest_frames(name)

@@ -2004,6 +2004,106 @@ def reftest_box_shadow_frame(which="inset-no-blur-radius"):
     return rounded_rects_frame(width=106, height=112, spec=spec, surface=(256, 256))
 
 
+def reftest_border_overlapping_frame():
+    """wrench/reftests/border/overlapping.yaml (== overlapping.png, fuzzy-if(platform(swgl),1,20)): a blue 200x200 rect
+    under a complex clip whose top-left and bottom-right radii are 180 — the two corner ellipses overlap, and every
+    pixel must still take exactly one corner's distance (ps_quad_mask.glsl:55-60 per-corner radii, the slow path).
+    Drawn the Indirect way like config A; reference image 233x240."""
+    spec = [((0, 0, 200, 200), (0.0, 0.0, 1.0, 1.0), ((180.0, 180.0), (0.0, 0.0), (0.0, 0.0), (180.0, 180.0)), 0)]
+    return rounded_rects_frame(width=233, height=240, spec=spec, surface=(256, 256))
+
+
+def reftest_border_no_bogus_line_frame():
+    """wrench/reftests/border/border-no-bogus-line.yaml (== border-no-bogus-line-ref.png, fuzzy-if(platform(swgl),1,8)):
+    a solid black border, width 3, radius 40.5, on the box (10,10)-(100,90).  The radii do not fit the 80-pixel height:
+    ensure_no_corner_overlap (border.rs:168-215, called by add_normal_border) scales them by 80/81 — exactly 40.0 in
+    fp32 — so the corners are 40x40, the left and right edges have no length (no "bogus line" between the corners)
+    and the top and bottom edges are 10 long.  Draw list as the frame builder makes it (border.rs:654-898, 904-1042,
+    1245-1297): each corner a cs_border_solid task of 40x40 in the texture cache (widths 3, radius 40, AA, the adjacent
+    corners' clips collapsed onto the task's own corners since their radii do not reach it), each edge an 8x3 task;
+    then one Brush(Image) instance per segment — SEGMENT_RELATIVE | SEGMENT_TEXEL_RECT corners, SEGMENT_RELATIVE |
+    SEGMENT_REPEAT_X edges — with premultiplied blending over the white page.  Reference image 116x108."""
+    from webrender_b200 import gpu_types as G
+    W, H = 116, 108
+    black = (0.0, 0.0, 0.0, 1.0)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    r, bw, bh = 40.0, 90.0, 80.0
+    # (segment, task origin in the cache, segment rect relative to the border rect, adjacent-corner clip points)
+    corners = [(G.SEGMENT_TOP_LEFT, (0, 0), (0.0, 0.0, r, r), (r, 0.0, 0.0, r)),
+               (G.SEGMENT_TOP_RIGHT, (40, 0), (bw - r, 0.0, bw, r), (0.0, 0.0, r, r)),
+               (G.SEGMENT_BOTTOM_RIGHT, (0, 40), (bw - r, bh - r, bw, bh), (0.0, r, r, 0.0)),
+               (G.SEGMENT_BOTTOM_LEFT, (40, 40), (0.0, bh - r, r, bh), (r, r, 0.0, 0.0))]
+    edges = [(G.SEGMENT_TOP, (80, 0), (r, 0.0, bw - r, 3.0)), (G.SEGMENT_BOTTOM, (80, 8), (r, bh - 3.0, bw - r, bh))]
+    inst, segs = [], []
+    for seg, org, srect, adj in corners:
+        inst.append(G.border_instance(task_origin=(float(org[0]), float(org[1])), local_rect=(0.0, 0.0, r, r), color0=black,
+                                      color1=black, segment=seg, style0=G.BORDER_STYLE_SOLID, style1=G.BORDER_STYLE_SOLID,
+                                      do_aa=True, widths=(3.0, 3.0), radius=(r, r),
+                                      clip_params=(adj[0], adj[1], 0.0, 0.0, adj[2], adj[3], 0.0, 0.0)))
+        segs.append((srect, (0.0, 0.0, 1.0, 1.0), 2 | 512, (float(org[0]), float(org[1]), org[0] + r, org[1] + r)))
+    for seg, org, srect in edges:
+        inst.append(G.border_instance(task_origin=(float(org[0]), float(org[1])), local_rect=(0.0, 0.0, 8.0, 3.0), color0=black,
+                                      color1=black, segment=seg, style0=G.BORDER_STYLE_SOLID, style1=G.BORDER_STYLE_SOLID,
+                                      do_aa=True, widths=(8.0, 3.0), radius=(0.0, 0.0)))
+        segs.append((srect, (0.0, 0.0, 8.0, 3.0), 2 | 4, (float(org[0]), float(org[1]), org[0] + 8.0, org[1] + 3.0)))
+    # the border primitive: brush data (colour, background, stretch size = the border's size) + two blocks per segment
+    blocks = [(1.0, 1.0, 1.0, 1.0), (0.0, 0.0, 0.0, 0.0), (bw, bh, 0.0, 0.0)]
+    for srect, texel, _, _ in segs:
+        blocks += [srect, texel]
+    addr = t.push_gpu_cache(blocks)
+    hdr = t.add_prim_header((10.0, 10.0, 10.0 + bw, 10.0 + bh), (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, pic,
+                            (4 | (1 << 16), 0, 65535, 0))
+    draws = []
+    for i, (_, _, flags, uv) in enumerate(segs):
+        res = t.push_gpu_cache([uv, (0.0, 0.0, 0.0, 0.0)])
+        draws.append(G.brush_instance(hdr, G.CLIP_TASK_EMPTY, i, 0, flags, res))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H),
+                "cache": TextureDesc(abi.FMT_RGBA8, 128, 128, filter=abi.LINEAR)}
+    p0 = [Target("cache", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)),
+                               Batch(abi.KIND_BORDER_SOLID, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA)])]
+    p1 = [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                                Batch(abi.KIND_BRUSH_IMAGE, np.stack(draws), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                      features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("cache", "", ""))])]
+    return Frame(t.arrays(), textures, [p0, p1])
+
+
+def reftest_split_near_plane_frame():
+    """wrench/reftests/split/near-plane.yaml (== near-plane.png, fuzzy(1,20); fuzzy-if(platform(swgl),128,39)): a
+    600x600 rect of (255,0,0,0.5) in a stacking context rotated by rotate-x(-60) about its centre, inside a
+    preserve-3d context with perspective 200 — "a single polygon intersecting the near plane".  Draw list
+    (picture.rs Picture3DContext::In, batch.rs:2040-2080): the child picture is rasterised in its local space into a
+    600x600 surface (one premultiplied Brush(Solid) = 128,0,0,128), the plane splitter hands back ONE polygon — the
+    picture rect cut where it comes too close to the eye (w -> 0 at y = 300 + 200/sin(60) = 530.9; cut here at
+    y = 500, which projects far below the 600-pixel viewport, so where exactly the cut lies cannot be seen) — and
+    ps_split_composite draws it over the white page with premultiplied blending."""
+    from webrender_b200.gpu_types import brush_instance, split_composite_instance, CLIP_TASK_EMPTY
+    W = H = 600
+    t = FrameTables()
+    surf_task = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    # the wrench rotation sign: the bottom half comes towards the eye (it fills the width of the reference image)
+    xf = t.add_transform(perspective_matrix(W, H, d=200.0, ry=0.0, rx=60.0), axis_aligned=False)
+    color = (0.5, 0.0, 0.0, 0.5)
+    addr = t.push_gpu_cache([color])
+    hdr0 = t.add_prim_header((0.0, 0.0, float(W), float(H)), (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, surf_task, (65535, 0, 0, 0))
+    solid = brush_instance(hdr0, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)
+    yc = 500.0
+    poly_addr = t.push_gpu_cache([(0.0, 0.0, float(W), 0.0), (float(W), yc, 0.0, yc)])
+    res = t.push_gpu_cache([(0.0, 0.0, float(W), float(H)), (0.0, 0.0, 0.0, 0.0),
+                            (0.0, 0.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)])
+    hdr = t.add_prim_header((0.0, 0.0, float(W), float(H)), (-1e9, -1e9, 1e9, 1e9), 1, 0, xf, pic, (res, 1, 0, CLIP_TASK_EMPTY))
+    poly = split_composite_instance(hdr, poly_addr, 1, pic)
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H),
+                "surface": TextureDesc(abi.FMT_RGBA8, W, H, filter=abi.LINEAR)}
+    p0 = [Target("surface", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)),
+                                 Batch(abi.KIND_BRUSH_SOLID, solid[None, :], blend=abi.BLEND_PREMULTIPLIED_ALPHA)])]
+    p1 = [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                                Batch(abi.KIND_SPLIT_COMPOSITE, poly[None, :], blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                      color=("surface", "", ""))])]
+    return Frame(t.arrays(), textures, [p0, p1])
+
+
 def reftest_filter_blur_frame():
     """wrench/reftests/filters/filter-small-blur-radius.yaml: a 512x512 red rect at (100,100) in a stacking context with
     filter blur(2,2), on the 700x700 page of its reference image.  Draw list (picture.rs:5873-5938, render_task.rs
