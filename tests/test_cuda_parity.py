@@ -191,6 +191,22 @@ def test_text_run_config_c_size():
     assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
 
 
+@pytest.mark.parametrize("variant", ["r8_alpha", "r8_fractional", "rgba_modes", "r8_shadow_masks"])
+@pytest.mark.parametrize("n_runs,glyphs", [(40, 40), (12, 40)])
+def test_text_run_dense_overlapping(n_runs, glyphs, variant):
+    """Runs crossing one another on a small page: many glyphs overlap EARLIER glyphs of the batch, so the glyph-major
+    kernel must leave them (and only them) to the ordered tile kernel — binned (1600 glyphs) and unbinned (480)."""
+    f = _text_frame(3, variant, width=640, height=200, n_runs=n_runs, glyphs_per_run=glyphs)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]), variant)
+
+
+def test_text_run_tile_kernel_only(monkeypatch):
+    """WRCU_GLYPH_MAJOR=0: the ordered tile kernel alone draws the batch (the path glyph-major falls back to)."""
+    monkeypatch.setenv("WRCU_GLYPH_MAJOR", "0")
+    f = _text_frame(2, "r8_fractional", width=640, height=200, n_runs=40, glyphs_per_run=40)
+    assert_same(render(CudaDevice, f, ["target"]), render(OracleDevice, f, ["target"]))
+
+
 GRADIENT_VARIANTS = ["opaque", "alpha", "fractional", "repeat", "full_frame"]
 
 

@@ -24,6 +24,9 @@ enum : uint32_t {
                             // the batch allows it (BatchInfo::all_copy)
   CMD_RUNS = 1u << 12,      // has failing-sample bitmaps (CmdCold::fail_off): its depth runs are reproduced
   CMD_SPAN_SOLID = 1u << 5, // span body is drawn by swgl_commitSolid* (mask folded into colour before AA)
+  CMD_ORDERED = 1u << 14,   // text: set by wr_raster_glyphs on a command it leaves to the ordered tile kernel (one it cannot draw, or
+                            // that overlaps an earlier such command); the tile kernel then draws only these
+  CMD_DONE = 1u << 15,      // text: drawn by wr_raster_glyphs (set after its pixels, release semantics)
   CMD_PERSP = 1u << 13,     // w differs between the vertices: draw_perspective (rasterize.h:1064-1545) — a clipped convex
                             // polygon (PerspPoly in the row-table pool, CmdCold::row_off), per-row spans from its edge walk,
                             // z/w and the interpolants (scaled by 1/w) stepped per sample; always set together with CMD_GENERAL
@@ -116,9 +119,9 @@ struct BatchInfo {
   int simple;              // 1 while every command is a plain solid quad (no mask/AA/texture, lanes<=255)
   int premul_valid;        // 1 while every command's colour lanes are <= its alpha lane
   int tile_counter;        // dynamic tile scheduler of the generic raster kernel
-  int row_alloc;           // floats of the row-table pool handed out to this batch's commands
+  int n_ordered;           // text: commands wr_raster_glyphs left to the tile kernel (CMD_ORDERED)
   int all_copy;            // composite: 1 while no two commands of the batch overlap: CMD_COPY commands go to wr_composite_copy
-  int fail_alloc;          // words of the depth-run bitmap pool handed out to this batch's commands
+  int glyph_ticket;        // text: next glyph wr_raster_glyphs hands to a warp
   int n_noncopy;           // composite: drawn commands that are not CMD_COPY (0: the tile kernel has nothing to do)
 };
 #define WR_ROW_TAB_MIN 4   // glyph rows (~12) too: the per-(command,row,tile) walk was a third of the text kernel

@@ -45,6 +45,9 @@ struct RasterArgs {
   const uint32_t* wide_mask;
   const uint32_t* tile_any;  // see SetupArgs
   int any_words;
+  uint32_t* tile_ord;    // glyph-major text: bit t = an ordered command (CMD_ORDERED) touches tile t (binned batches)
+  int glyph_major;       // the batch went through wr_raster_glyphs first: the tile kernel draws only CMD_ORDERED commands
+  int lane_rows;         // the lanes of a warp hold different (command,row)s: no warp-cooperative walks in the row set-up
   int bin_words, bin_tiles_x;
   const float* row_tab;  // row tables written by the setup kernel (CmdCold::row_off)
   // Depth runs (rasterize.h:601-657): with depth testing on, the reference draws each maximal run of
@@ -379,7 +382,9 @@ WRD void wr_row_interp_raw(const RasterArgs& a, const CmdCold& k, const CmdHot& 
 #ifndef WRCU_HOSTEMU
   // The 2N edge sums are independent and the whole warp is here (row_setup is
   // warp-uniform): lane l < 2N walks one of them, the results are broadcast.
-  // One walk's worth of instructions instead of 2N.
+  // One walk's worth of instructions instead of 2N.  (Not where lanes hold different rows:
+  // RasterArgs::lane_rows, the glyph-major kernel.)
+  if (!a.lane_rows) {
   const int wlane = threadIdx.x & 31;
   float walked = 0.0f;
   if (wlane < 2 * N) {
@@ -398,7 +403,9 @@ WRD void wr_row_interp_raw(const RasterArgs& a, const CmdCold& k, const CmdHot& 
     step[i] = st;
     o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
   }
-#else
+  return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < N; i++) {
     float sl = __fmul_rn(__fsub_rn(k.i_lb[i], k.i_lt[i]), k.yscale);
@@ -412,7 +419,6 @@ WRD void wr_row_interp_raw(const RasterArgs& a, const CmdCold& k, const CmdHot& 
     step[i] = st;
     o[i] = __fadd_rn(li, __fmul_rn(st, x0f));
   }
-#endif
 }
 
 template <int N>
@@ -898,7 +904,8 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
     if (candidate) {
       mine = a.hot[cidx];
       keep = mine.x1 > tx0 && mine.x0 < tx0 + WRCU_TILE_W && mine.y1 > ty0 && mine.y0 < ty0 + WRCU_TILE_H &&
-             mine.x1 > mine.x0 && !(skip_copy && (mine.flags & CMD_COPY));
+             mine.x1 > mine.x0 && !(skip_copy && (mine.flags & CMD_COPY)) &&
+             (!a.glyph_major || (mine.flags & CMD_ORDERED));
       // Hidden-surface removal inside a batch: with blending and depth off a command that
       // overwrites every writable pixel of this tile makes all earlier commands of the batch
       // invisible here, so the pixel loop can start at the last such command.
@@ -1070,6 +1077,9 @@ wr_raster(RasterArgs a) {
   if (a.fast_eligible && bi.simple) return;  // handled by wr_raster_solid_premult
   const bool skip_copy = a.copy_eligible && bi.all_copy;  // CMD_COPY commands are drawn by wr_composite_copy
   if (skip_copy && bi.n_noncopy == 0) return;
+  if (a.glyph_major && bi.n_ordered == 0) return;  // wr_raster_glyphs drew the whole batch
+  const uint32_t* any_map = a.glyph_major ? a.tile_ord : a.tile_any;
+  const bool any_all = !a.glyph_major && a.tile_any && a.tile_any[a.any_words];
   const int bx0 = max(bi.bx0, 0) / WRCU_TILE_W, by0 = max(bi.by0, 0) / WRCU_TILE_H;
   const int bx1 = (min(bi.bx1, a.tgt.w) + WRCU_TILE_W - 1) / WRCU_TILE_W;
   const int by1 = (min(bi.by1, a.tgt.h) + WRCU_TILE_H - 1) / WRCU_TILE_H;
@@ -1084,9 +1094,9 @@ wr_raster(RasterArgs a) {
       int tn;
       for (;;) {
         tn = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
-        if (tn >= n_tiles || !a.tile_any || !a.tile_mask) break;
+        if (tn >= n_tiles || !any_map || !a.tile_mask) break;
         const int tid = (by0 + tn / nx) * a.bin_tiles_x + bx0 + tn % nx;
-        if (a.tile_any[a.any_words] || ((a.tile_any[tid >> 5] >> (tid & 31)) & 1u)) break;
+        if (any_all || ((any_map[tid >> 5] >> (tid & 31)) & 1u)) break;
       }
       s_tile = tn;
     }

@@ -62,9 +62,9 @@ WRD void wr_reset_batch_info(BatchInfo* info) {
   info->simple = 1;
   info->premul_valid = 1;
   info->tile_counter = 0;
-  info->row_alloc = 0;
+  info->n_ordered = 0;
   info->all_copy = 1;
-  info->fail_alloc = 0;
+  info->glyph_ticket = 0;
   info->n_noncopy = 0;
 }
 // Each setup kernel also re-arms the per-batch record the NEXT draw will use

@@ -122,7 +122,7 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
     const CmdHot h = a.hot[idx];
     const int tiw = tex0.w, tih = tex0.h;
     k->i[2] = 0;
-    if (a.copy_ok && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 &&
+    if (a.copy_ok == 1 && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 &&
         tex0.tmap_id && is_white && !(h.flags & (CMD_GENERAL | CMD_AA | CMD_MASK | CMD_CLIP_DIST)) &&
         (tiw & (tiw - 1)) == 0 && (tih & (tih - 1)) == 0 &&
         k->i_lt[0] == k->i_lb[0] && k->i_rt[0] == k->i_rb[0] && k->i_lt[1] == k->i_rt[1] && k->i_lb[1] == k->i_rb[1]) {
@@ -143,6 +143,16 @@ WRD void wr_setup_composite_one(const SetupArgs& a, int idx) {
         else if (k->row_off >= 0 && k->row_n == 2) { k->i[2] = 1; copyc = true; }  // rows checked against the table
       }
     }
+    // Fill class: a solid-colour or clear tile samples the 1x1 white dummy texture (renderer/mod.rs:3197-3230), so its
+    // fragments are the instance colour on every pixel — body chunks (applyColor: muldiv255(c, 255) = c) and tail
+    // pixels (round(color * 1.0 * 255)) alike — and the tile is a constant store / over / dest-out of its rect.
+    if (!copyc && a.copy_ok && a.tgt.fmt == WRCU_FMT_RGBA8 && a.tgt.tmap_id && tex0.fmt == WRCU_FMT_RGBA8 && tiw == 1 && tih == 1 &&
+        !(h.flags & (CMD_GENERAL | CMD_AA | CMD_MASK | CMD_CLIP_DIST)) && *(const uint32_t*)tex0.ptr == 0xFFFFFFFFu &&
+        h.col[0] <= 255 && h.col[1] <= 255 && h.col[2] <= 255 && h.col[3] <= 255) {
+      k->i[2] = 2;
+      copyc = true;
+    }
+    if (a.copy_ok == 2 && k->i[2] != 2) copyc = false;  // dest-out: fills only
     if (copyc) a.hot[idx].flags |= CMD_COPY;
     else atomicAdd(&a.info->n_noncopy, 1);
   }
@@ -229,6 +239,7 @@ struct WrCopyCmd {
   int tmap, aligned;
   const uint8_t* sptr;
   int spitch;
+  uint32_t fill;   // fill class (sptr == nullptr): the constant source pixel
 };
 struct WrBoxIter {
   int i = -1, b = 0, nb = 0, nbx = 1, g = 0;
@@ -254,7 +265,7 @@ struct WrBoxIter {
       by = (b / nbx) * WR_TMA_BOX_H;
       // the copy engine takes whole boxes whose source and destination start on 16-byte boundaries
       // (box origins off them fault: tools/probe/tma_probe.cu); everything else is moved by threads
-      const bool full = c.aligned && bx + WR_TMA_BOX_W <= c.w && by + WR_TMA_BOX_H <= c.h;
+      const bool full = c.aligned && c.sptr && bx + WR_TMA_BOX_W <= c.w && by + WR_TMA_BOX_H <= c.h;
       if (full == want_full) return true;
     }
   }
@@ -267,30 +278,30 @@ WRD uint32_t wr_over_px(uint32_t d, uint32_t s) {  // premultiplied-alpha over, 
   return rb | (ga << 8);
 }
 
-// one row of a box by plain accesses, `t` of `nt` threads: scalar pixels up to the destination's 16-byte
-// boundary, then 16-byte stores (the source as one vector load when it is in phase, four scalar loads otherwise)
-template <bool BLEND>
-__device__ __forceinline__ void wr_copy_row(const uint32_t* sp, uint32_t* dp, int bw, int t, int nt) {
-  int head = (int)(((16u - (unsigned)((uintptr_t)dp & 15u)) & 15u) >> 2);
-  if (head > bw) head = bw;
-  for (int q = t; q < head; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
-  sp += head; dp += head; bw -= head;
-  const int nv = bw >> 2;
-  const bool in_phase = ((uintptr_t)sp & 15) == 0;
-  for (int q = t; q < nv; q += nt) {
-    uint4 sv;
-    if (in_phase) sv = __ldg((const uint4*)sp + q);
-    else sv = make_uint4(__ldg(sp + 4 * q), __ldg(sp + 4 * q + 1), __ldg(sp + 4 * q + 2), __ldg(sp + 4 * q + 3));
-    if (BLEND) {
-      const uint4 dv = ((const uint4*)dp)[q];
-      sv = make_uint4(wr_over_px(dv.x, sv.x), wr_over_px(dv.y, sv.y), wr_over_px(dv.z, sv.z), wr_over_px(dv.w, sv.w));
-    }
-    ((uint4*)dp)[q] = sv;
+// BLEND: 0 store, 1 premultiplied-alpha over (blend.h:473-474), 2 premultiplied dest-out (d - muldiv255(d, src.a))
+template <int BLEND>
+WRD uint32_t wr_copy_px(uint32_t d, uint32_t s) {
+  if (BLEND == 1) return wr_over_px(d, s);
+  if (BLEND == 2) {
+    const uint32_t sa = s >> 24;
+    const uint32_t rb = d & 0x00FF00FFu, ga = (d >> 8) & 0x00FF00FFu;
+    // per 16-bit lane: d - ((d * sa + d) >> 8), d <= 255 so the lanes never borrow or carry
+    const uint32_t mrb = ((rb * sa + rb) >> 8) & 0x00FF00FFu, mga = ((ga * sa + ga) >> 8) & 0x00FF00FFu;
+    return (rb - mrb) | ((ga - mga) << 8);
   }
-  for (int q = (nv << 2) + t; q < bw; q += nt) dp[q] = BLEND ? wr_over_px(dp[q], __ldg(sp + q)) : __ldg(sp + q);
+  return s;
 }
-// ragged-edge boxes by plain accesses: `t` of `nt` threads share the rows of each box
-template <bool BLEND>
+template <int BLEND>
+WRD uint4 wr_copy_px4(uint4 d, uint4 s) {
+  return make_uint4(wr_copy_px<BLEND>(d.x, s.x), wr_copy_px<BLEND>(d.y, s.y), wr_copy_px<BLEND>(d.z, s.z), wr_copy_px<BLEND>(d.w, s.w));
+}
+// Ragged-edge boxes and fills by plain accesses: `t` of `nt` threads (whole warps) share the rows of each box.
+// A warp takes WR_RAG_ROWS rows at a time and issues every load of a step — source and, when blending,
+// destination, of all its rows — before the first store, so a box costs two or three memory round trips
+// instead of one per row.  The destination's pitch is a multiple of 16 bytes (it has a tensor map), so all rows of
+// a box share the split into scalar head pixels up to the 16-byte boundary, 16-byte stores, scalar tail.
+#define WR_RAG_ROWS 4
+template <int BLEND>
 __device__ void wr_copy_ragged(const RasterArgs& a, const WrCopyCmd* cl, int n, int t, int nt) {
   WrBoxIter it;
   int bx, by;
@@ -298,17 +309,50 @@ __device__ void wr_copy_ragged(const RasterArgs& a, const WrCopyCmd* cl, int n, 
   while (it.next(cl, n, false, bx, by)) {
     const WrCopyCmd& c = cl[it.i];
     const int bw = min(WR_TMA_BOX_W, c.w - bx), bh = min(WR_TMA_BOX_H, c.h - by);
-    // a warp per row: 32 lanes x 16 bytes cover half a box row per step
-    for (int r = w; r < bh; r += nw) {
-      const uint32_t* sp = (const uint32_t*)(c.sptr + (size_t)(c.sy + by + r) * c.spitch) + c.sx + bx;
-      uint32_t* dp = (uint32_t*)(a.tgt.color + (size_t)((int)c.y0 + by + r) * a.tgt.color_pitch) + (int)c.x0 + bx;
-      wr_copy_row<BLEND>(sp, dp, bw, lane, 32);
+    const bool fill = c.sptr == nullptr;
+    uint32_t* d0 = (uint32_t*)(a.tgt.color + (size_t)((int)c.y0 + by) * a.tgt.color_pitch) + (int)c.x0 + bx;
+    const size_t dstride = (size_t)a.tgt.color_pitch >> 2;
+    const uint32_t* s0 = fill ? nullptr : (const uint32_t*)(c.sptr + (size_t)(c.sy + by) * c.spitch) + c.sx + bx;
+    const size_t sstride = (size_t)c.spitch >> 2;  // (RGBA8 sources: the pitch is a whole number of pixels)
+    int head = (int)(((16u - (unsigned)((uintptr_t)d0 & 15u)) & 15u) >> 2);
+    if (head > bw) head = bw;
+    const int nv = (bw - head) >> 2, tail0 = head + (nv << 2);
+    const bool in_phase = !fill && (((uintptr_t)(s0 + head) | (uintptr_t)c.spitch) & 15) == 0;
+    for (int r0 = w * WR_RAG_ROWS; r0 < bh; r0 += nw * WR_RAG_ROWS) {
+      const int nr = min(WR_RAG_ROWS, bh - r0);
+      for (int q = lane; q < nv; q += 32) {
+        uint4 sv[WR_RAG_ROWS], dv[WR_RAG_ROWS];
+#pragma unroll
+        for (int k = 0; k < WR_RAG_ROWS; k++) {
+          if (k >= nr) break;
+          if (fill) sv[k] = make_uint4(c.fill, c.fill, c.fill, c.fill);
+          else {
+            const uint32_t* sp = s0 + (size_t)(r0 + k) * sstride + head;
+            if (in_phase) sv[k] = __ldg((const uint4*)sp + q);
+            else sv[k] = make_uint4(__ldg(sp + 4 * q), __ldg(sp + 4 * q + 1), __ldg(sp + 4 * q + 2), __ldg(sp + 4 * q + 3));
+          }
+          if (BLEND) dv[k] = ((const uint4*)(d0 + (size_t)(r0 + k) * dstride + head))[q];
+        }
+#pragma unroll
+        for (int k = 0; k < WR_RAG_ROWS; k++) {
+          if (k >= nr) break;
+          ((uint4*)(d0 + (size_t)(r0 + k) * dstride + head))[q] = BLEND ? wr_copy_px4<BLEND>(dv[k], sv[k]) : sv[k];
+        }
+      }
+      // scalar pixels: the head and the tail of each row (at most 3 + 3), one (row, pixel) per lane
+      const int ns = head + (bw - tail0);
+      for (int e = lane; e < nr * ns; e += 32) {
+        const int k = e / ns, j = e % ns, xq = j < head ? j : tail0 + (j - head);
+        uint32_t* dp = d0 + (size_t)(r0 + k) * dstride + xq;
+        const uint32_t sv = fill ? c.fill : __ldg(s0 + (size_t)(r0 + k) * sstride + xq);
+        *dp = BLEND ? wr_copy_px<BLEND>(*dp, sv) : sv;
+      }
     }
   }
 }
 
 #define WR_TMA_BLEND_STAGES 3
-template <bool BLEND>
+template <int BLEND>
 __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a) {
   extern __shared__ __align__(128) uint8_t wr_copy_smem[];
   __shared__ __align__(8) uint64_t full[WR_TMA_STAGES];
@@ -332,9 +376,14 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
     WrCopyCmd cc, cs;
     cc.x0 = c.x0; cc.y0 = c.y0;
     cc.w = cc.h = 0;
-    cc.sx = cc.sy = cc.tmap = cc.aligned = 0; cc.sptr = nullptr; cc.spitch = 0;
+    cc.sx = cc.sy = cc.tmap = cc.aligned = 0; cc.sptr = nullptr; cc.spitch = 0; cc.fill = 0;
     cs = cc;
-    if (c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY)) {
+    if (c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY) && a.cold[c.cold].i[2] == 2) {
+      // fill class: the command's colour (BGRA lanes of the hot record) on every pixel
+      cc.w = (int)c.x1 - (int)c.x0;
+      cc.h = (int)c.y1 - (int)c.y0;
+      cc.fill = (uint32_t)c.col[0] | ((uint32_t)c.col[1] << 8) | ((uint32_t)c.col[2] << 16) | ((uint32_t)c.col[3] << 24);
+    } else if (BLEND != 2 && c.x1 > c.x0 && c.y1 > c.y0 && (c.flags & CMD_COPY)) {
       const CmdCold& k = a.cold[c.cold];
       const TexView& tv = wr_composite_tex(k);
       cc.w = (int)c.x1 - (int)c.x0;
@@ -367,6 +416,10 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
   }
   __syncthreads();
   int bx, by;
+  if (BLEND == 2) {  // dest-out: fills only (no box is "full")
+    wr_copy_ragged<2>(a, cl, n, threadIdx.x, WR_TMA_THREADS);
+    return;
+  }
   if (!BLEND) {
     if (threadIdx.x == 0) {
       // ---- the copy engine's driver: every full box of this CTA, loads DEPTH boxes ahead of stores ----
@@ -395,7 +448,7 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
       while (stored < issued) store_one();
       wr_tma_wait_all<0>();  // stores complete before the CTA's shared memory is released
     } else if (threadIdx.x >= 32) {
-      wr_copy_ragged<false>(a, cl, n, threadIdx.x - 32, WR_TMA_THREADS - 32);
+      wr_copy_ragged<0>(a, cl, n, threadIdx.x - 32, WR_TMA_THREADS - 32);
     }
     return;
   }
@@ -446,7 +499,7 @@ __global__ void __launch_bounds__(WR_TMA_THREADS) wr_composite_copy(RasterArgs a
   }
   if (threadIdx.x == 0) wr_tma_wait_all<0>();
   __syncthreads();
-  wr_copy_ragged<true>(a, cl, n, threadIdx.x, WR_TMA_THREADS);
+  wr_copy_ragged<1>(a, cl, n, threadIdx.x, WR_TMA_THREADS);
 }
 #endif
 

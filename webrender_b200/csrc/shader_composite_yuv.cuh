@@ -560,3 +560,15 @@ template <> struct WrRun<CompositeYuvShader> {  // brush_yuv_image draws under d
   enum { n = 6 };
   WRD_MEMBER int drawn(const CompositeYuvShader::Row& r) { return r.body_len; }
 };
+
+#ifndef WRCU_HOSTEMU
+// The same shader compiled for ONE resident CTA per SM (255 registers): the row state of three planes no longer
+// spills (608 bytes of stack at 128 registers).  WRCU_YUV_WIDE=1 launches it; measured against the default in
+// profiles/README_r02.md.
+struct CompositeYuvShaderWide : CompositeYuvShader {};
+template <> struct WrMinCtas<CompositeYuvShaderWide> { enum { v = 1 }; };
+template <> struct WrRun<CompositeYuvShaderWide> {
+  enum { n = 6 };
+  WRD_MEMBER int drawn(const CompositeYuvShader::Row& r) { return r.body_len; }
+};
+#endif

@@ -255,6 +255,12 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
     c->immediate = e && atoi(e) != 0;
     e = getenv("WRCU_PDL");
     c->pdl = e ? atoi(e) != 0 : true;
+    e = getenv("WRCU_YUV_WIDE");
+    c->yuv_wide = e && atoi(e) != 0;
+    e = getenv("WRCU_EARLY_CLEAR");
+    c->early_clear = e ? atoi(e) != 0 : true;
+    e = getenv("WRCU_GLYPH_MAJOR");
+    c->glyph_major = e ? atoi(e) != 0 : true;
     e = getenv("WRCU_SIDE_CTAS");
     c->side_ctas_per_sm = e ? atoi(e) : 1;
     if (c->side_ctas_per_sm < 1 || c->side_ctas_per_sm > 3) c->side_ctas_per_sm = 1;
@@ -330,6 +336,7 @@ extern "C" void wrcu_ctx_destroy(wrcu_ctx* c) {
   for (cudaEvent_t e : c->op_events) cudaEventDestroy(e);
   for (cudaEvent_t e : c->join_ev) cudaEventDestroy(e);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  if (c->fork0_ev) cudaEventDestroy(c->fork0_ev);
   delete (std::vector<PendingOp>*)c->pending_ops;
   if (c->row_tab) cudaFree(c->row_tab);
   if (c->tmaps_dev) cudaFree(c->tmaps_dev);
@@ -1463,7 +1470,9 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   // per-sample 1/w path; the solid colour case of ps_quad_textured shares brush_solid's shader
   sa.persp_ok = kind == WRCU_KIND_BRUSH_SOLID || kind == WRCU_KIND_SPLIT_COMPOSITE || kind == WRCU_KIND_QUAD_TEXTURED ||
                 (kind == WRCU_KIND_BRUSH_IMAGE && !(features & WRCU_FEAT_REPETITION));
-  sa.copy_ok = !T.depth && (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA);
+  // copy class (shader_composite.cuh): 1 = 1:1 tile copies and solid fills, 2 = fills only (the clear tile's dest-out)
+  sa.copy_ok = T.depth ? 0 : (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA) ? 1
+                             : st->blend == WRCU_BLEND_PREMULTIPLIED_DEST_OUT ? 2 : 0;
   if (kind == WRCU_KIND_COMPOSITE && sa.copy_ok && !(features & WRCU_FEAT_YUV)) {
     // The copy kernel moves boxes of different instances concurrently: a batch whose instances overlap keeps
     // the ordered tile kernel.  Picture-cache tiles never overlap; checked here on the host copies of the
@@ -1496,7 +1505,8 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
     const int tiles_x = (T.w + WRCU_TILE_W - 1) / WRCU_TILE_W, tiles_y = (T.h + WRCU_TILE_H - 1) / WRCU_TILE_H;
     const size_t words = ((size_t)n + 31) / 32;
     const size_t any_words = ((size_t)tiles_x * tiles_y + 31) / 32;
-    const size_t need = ((size_t)tiles_x * tiles_y + 1) * words + any_words + 1;  // + the wide mask + the tile-any bitmap
+    const size_t need = ((size_t)tiles_x * tiles_y + 1) * words + 2 * any_words + 1;  // + the wide mask + the tile-any bitmap
+                                                                                         // + the ordered-tile bitmap (text)
     if (n >= 512 && need * 4 <= (size_t)96 << 20) {
       // pointers into the submission's bin area are assigned at flush (PendingOp::bin_need)
       bin_need = need;
@@ -1695,7 +1705,10 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
 // launch when the context has it switched off (WRCU_PDL=0).
 template <typename K>
 static void wr_launch_chain(wrcu_ctx* c, K kernel, unsigned grid, unsigned block, size_t smem, const RasterArgs& ra) {
-  if (!c->pdl) {
+  // (a launch that directly follows an event wait in its stream is an ordinary one: the programmatic edge is
+  // between two kernels, and nothing is gained by leaving it to the driver what an event wait in between means)
+  if (!c->pdl || c->plain_next) {
+    c->plain_next = false;
     kernel<<<grid, block, smem, c->launch_stream>>>(ra);
     return;
   }
@@ -1816,26 +1829,49 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
       if (features & WRCU_FEAT_REPETITION) LAUNCH_RASTER_RUNS(ImageRepeatShader);
       else LAUNCH_RASTER_RUNS(ImageShader);
       break;
-    case WRCU_KIND_TEXT_RUN: LAUNCH_RASTER_RUNS(TextShader); break;
+    case WRCU_KIND_TEXT_RUN:
+#ifndef WRCU_HOSTEMU
+      // glyph-major first (a warp per glyph, shader_text.cuh); the tile kernel then draws what it flagged CMD_ORDERED
+      if (c->glyph_major && T.fmt == WRCU_FMT_RGBA8 && n >= 8 &&
+          (ra.depth_mode == WRCU_DEPTH_OFF || (ra.depth_mode == WRCU_DEPTH_TEST && op.sa.depth_runs))) {
+        ra.glyph_major = 1;
+        auto k_glyphs = wr_raster_glyphs<WRCU_FMT_RGBA8>;
+        const int per_cta = WR_GLYPH_THREADS / 32;
+        int ggrid = (n + per_cta - 1) / per_cta;           // persistent warps taking glyphs by ticket
+        if (ggrid > c->sm_count * 4) ggrid = c->sm_count * 4;
+        wr_launch_chain(c, k_glyphs, (unsigned)ggrid, WR_GLYPH_THREADS, 0, ra);
+        c->stats.kernel_launches++;
+        ra.pdl_early = 0;  // the tile kernel reads what the glyph kernel wrote (flags, BatchInfo::n_ordered)
+      }
+#endif
+      LAUNCH_RASTER_RUNS(TextShader);
+      break;
     case WRCU_KIND_BRUSH_LINEAR_GRADIENT: LAUNCH_RASTER_RUNS(GradientShader); break;
     case WRCU_KIND_CLIP_BOX_SHADOW: LAUNCH_RASTER(BoxShadowShader); break;
     case WRCU_KIND_BRUSH_YUV_IMAGE: LAUNCH_RASTER_RUNS(CompositeYuvShader); break;
     case WRCU_KIND_SPLIT_COMPOSITE: LAUNCH_RASTER_RUNS(ImageShader); break;
     case WRCU_KIND_COMPOSITE:
-      if (features & WRCU_FEAT_YUV) { LAUNCH_RASTER(CompositeYuvShader); break; }
+      if (features & WRCU_FEAT_YUV) {
+#ifndef WRCU_HOSTEMU
+        if (c->yuv_wide && T.fmt == WRCU_FMT_RGBA8) { auto k_w = wr_raster<CompositeYuvShaderWide, WRCU_FMT_RGBA8>; WR_LAUNCH_CHAIN(k_w, pgrid, WRCU_THREADS, ra); break; }
+#endif
+        LAUNCH_RASTER(CompositeYuvShader);
+        break;
+      }
 #ifndef WRCU_HOSTEMU
       if (c->tmaps_dev && T.tmap_id && op.sa.copy_ok) {
         // copy-class tile lists (decided on the device, BatchInfo::all_copy) go through the copy engine;
         // whichever of the two kernels is not in charge returns at once
         const size_t smem0 = (size_t)WR_TMA_STAGES * WR_TMA_BOX_BYTES, smem1 = (size_t)WR_TMA_BLEND_STAGES * 2 * WR_TMA_BOX_BYTES;
         if (!c->copy_attr_set) {
-          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+          WRCU_CUDA(c, cudaFuncSetAttribute(wr_composite_copy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
           c->copy_attr_set = true;
         }
         ra.copy_eligible = 1;
-        if (op.blend == WRCU_BLEND_NONE) wr_launch_chain(c, wr_composite_copy<false>, (unsigned)c->sm_count * 3, WR_TMA_THREADS, smem0, ra);
-        else wr_launch_chain(c, wr_composite_copy<true>, (unsigned)c->sm_count * 2, WR_TMA_THREADS, smem1, ra);
+        if (op.blend == WRCU_BLEND_NONE) wr_launch_chain(c, wr_composite_copy<0>, (unsigned)c->sm_count * 3, WR_TMA_THREADS, smem0, ra);
+        else if (op.blend == WRCU_BLEND_PREMULTIPLIED_ALPHA) wr_launch_chain(c, wr_composite_copy<1>, (unsigned)c->sm_count * 2, WR_TMA_THREADS, smem1, ra);
+        else wr_launch_chain(c, wr_composite_copy<2>, (unsigned)c->sm_count * 2, WR_TMA_THREADS, 0, ra);
         c->stats.kernel_launches++;
       }
 #endif
@@ -1983,15 +2019,23 @@ static bool uses_conflict(const PendingOp& a, const OpUse& ua, const PendingOp& 
   }
   return false;
 }
-static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
+static int ensure_side_streams(wrcu_ctx* c) {
   const int NS = c->n_streams;
   if (c->side.empty()) {
     c->side.resize((size_t)NS);
     for (int i = 0; i < NS; i++) WRCU_CUDA(c, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
     WRCU_CUDA(c, cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    WRCU_CUDA(c, cudaEventCreateWithFlags(&c->fork0_ev, cudaEventDisableTiming));
     c->join_ev.resize((size_t)NS);
     for (int i = 0; i < NS; i++) WRCU_CUDA(c, cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
   }
+  return WRCU_OK;
+}
+// Two fork points: `fork0_ev` was recorded before the submission's H2D copy and set-up launch — a stream that
+// starts with clears (they read nothing the set-up writes) waits only for that and overlaps them — and
+// `fork_ev` after the set-up launch, which every raster launch is behind.
+static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
+  const int NS = c->n_streams;
   const size_t n = q.size();
   while (c->op_events.size() < n) {
     cudaEvent_t e;
@@ -2026,7 +2070,7 @@ static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
   c->side_reduce = targets.size() >= 4;  // enough independent targets in flight to fill the chip between them
   // fork
   WRCU_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
-  std::vector<char> used((size_t)NS, 0), need_ev(n, 0);
+  std::vector<char> used((size_t)NS, 0), need_ev(n, 0), behind_setup((size_t)NS, 0);
   std::vector<std::vector<int>> deps(n);
   for (size_t i = 0; i < n; i++) {
     // latest conflicting earlier op on each other stream
@@ -2041,11 +2085,19 @@ static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
   for (size_t i = 0; i < n; i++) {
     PendingOp& op = q[i];
     cudaStream_t st = c->side[(size_t)strm[i]];
-    if (!used[(size_t)strm[i]]) {
-      used[(size_t)strm[i]] = 1;
+    c->plain_next = false;
+    if (op.type == 0 && c->early_clear) {
+      if (!used[(size_t)strm[i]]) WRCU_CUDA(c, cudaStreamWaitEvent(st, c->fork0_ev, 0));
+    } else if (!behind_setup[(size_t)strm[i]]) {
+      behind_setup[(size_t)strm[i]] = 1;
       WRCU_CUDA(c, cudaStreamWaitEvent(st, c->fork_ev, 0));
+      c->plain_next = true;
     }
-    for (int j : deps[i]) WRCU_CUDA(c, cudaStreamWaitEvent(st, c->op_events[(size_t)j], 0));
+    used[(size_t)strm[i]] = 1;
+    for (int j : deps[i]) {
+      WRCU_CUDA(c, cudaStreamWaitEvent(st, c->op_events[(size_t)j], 0));
+      c->plain_next = true;
+    }
     c->launch_stream = st;
     if (op.type == 1) op.ra.pdl_early = c->pdl ? 1 : 0;  // the set-up launch finished before the fork event
     int rc = op.type == 0 ? launch_clear(c, op) : launch_raster(c, op);
@@ -2054,6 +2106,7 @@ static int flush_multi_stream(wrcu_ctx* c, std::vector<PendingOp>& q) {
   }
   c->launch_stream = c->stream;
   c->side_reduce = false;
+  c->plain_next = false;
   // join
   for (int sidx = 0; sidx < NS; sidx++) {
     if (!used[(size_t)sidx]) continue;
@@ -2114,7 +2167,7 @@ static int flush_pending(wrcu_ctx* c) {
       sa.row_tab = c->row_tab;
       sa.row_cap = c->row_cap;
       if (op.bin_need) {
-        const size_t words = (size_t)sa.bin_words, tiles = (op.bin_need - (size_t)sa.any_words - 1) / words - 1;
+        const size_t words = (size_t)sa.bin_words, tiles = (op.bin_need - 2 * (size_t)sa.any_words - 1) / words - 1;
         sa.tile_mask = c->bin_mask + boff;
         sa.wide_mask = sa.tile_mask + tiles * words;
         sa.tile_any = sa.wide_mask + words;
@@ -2126,6 +2179,7 @@ static int flush_pending(wrcu_ctx* c) {
       ra.tile_mask = sa.tile_mask;
       ra.wide_mask = sa.wide_mask;
       ra.tile_any = sa.tile_any;
+      ra.tile_ord = sa.tile_any ? sa.tile_any + sa.any_words + 1 : nullptr;
       ra.row_tab = c->row_tab;
       ra.gbuf_f = c->tables.gpu_buffer_f;
       ra.n_gbuf_f = c->tables.n_gpu_buffer_f;
@@ -2145,6 +2199,15 @@ static int flush_pending(wrcu_ctx* c) {
     mark_dirty(c, map_off, map_off + (size_t)total_blocks * sizeof(int));
     c->stats.h2d_bytes += (size_t)nb * sizeof(SetupJob) + (size_t)total_blocks * sizeof(int);
   }
+#ifndef WRCU_HOSTEMU
+  // several launches, or a clear ahead of a draw: side streams (the clear overlaps the copy and the set-up launch)
+  const bool multi = c->n_streams > 1 && (q.size() > 2 || (c->early_clear && q.size() == 2 && q[0].type == 0 && q[1].type == 1));
+  if (multi) {
+    int rce = ensure_side_streams(c);
+    if (rce != WRCU_OK) return rce;
+    WRCU_CUDA(c, cudaEventRecord(c->fork0_ev, c->stream));
+  }
+#endif
   if (c->dirty_hi > c->dirty_lo) {
     Arena* a = &c->arena[c->cur_arena];
     WRCU_CUDA(c, cudaMemcpyAsync(a->dev + c->dirty_lo, a->host + c->dirty_lo, c->dirty_hi - c->dirty_lo, cudaMemcpyHostToDevice,
@@ -2168,7 +2231,7 @@ static int flush_pending(wrcu_ctx* c) {
   }
   c->launch_stream = c->stream;
 #ifndef WRCU_HOSTEMU
-  if (c->n_streams > 1 && q.size() > 2) {
+  if (multi) {
     int rcs = flush_multi_stream(c, q);
     if (rcs != WRCU_OK) return rcs;
     if (nb) c->flush_parity ^= 1;

@@ -166,7 +166,12 @@ struct wrcu_ctx {
   int side_ctas_per_sm = 1;      // persistent CTAs per SM of a small batch's raster kernel on a side stream (WRCU_SIDE_CTAS)
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> op_events, join_ev;
+  bool plain_next = false;         // the next chained launch follows an event wait: launch it the ordinary way
+  bool early_clear = true;         // clears wait for the fork point BEFORE the set-up launch (WRCU_EARLY_CLEAR=0: after it)
+  bool yuv_wide = false;           // composite YUV through the one-CTA-per-SM variant (WRCU_YUV_WIDE=1)
+  bool glyph_major = true;         // text batches go through wr_raster_glyphs first (WRCU_GLYPH_MAJOR=0: tile kernel only)
   cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t fork0_ev = nullptr;  // recorded before the submission's H2D copy: leading clears wait only for this
   cudaStream_t launch_stream = nullptr;  // where launch_clear / launch_raster queue (the context's stream, or a side stream)
   bool pdl = true;               // raster launches chained with programmatic stream serialization (WRCU_PDL=0: off)
   bool immediate = false;        // WRCU_IMMEDIATE=1: flush after every call (A/B measurements)
