@@ -341,6 +341,18 @@ int wrcu_composite_blit(wrcu_ctx* ctx, wrcu_tex dst, wrcu_tex src,
                         int opaque, int flip_x, int flip_y, int filter_linear,
                         const int32_t clip_rect[4]);
 
+/* `CompositeYUV` of the SWGL surface (swgl/src/composite.h:1335-1384; compositor/sw_compositor.rs composites video
+ * surfaces with it): three 8-bit planes (R8 textures; the two chroma planes of one size, full or half resolution)
+ * converted to BGRA with the 6/7-bit fixed-point matrix of `color_space` (YUVRangedColorSpace, composite.h:1210-1218:
+ * 0 BT601 narrow, 1 BT601 full, 2 BT709 narrow, 3 BT709 full, 4 BT2020 narrow, 5 BT2020 full, 6 GBR identity) while the
+ * `src_rect` of the luma plane is scaled into `dst_rect` with the reference's row walker (linear_row_yuv: integer
+ * coordinates, the half-resolution-chroma upscale path included), clipped to `clip_rect`; opaque.  Bit-exact.
+ * `color_depth` must be 8 (R16 planes: WRCU_ERR_UNSUPPORTED, as are planes under 2 texels wide). */
+int wrcu_composite_blit_yuv(wrcu_ctx* ctx, wrcu_tex dst, wrcu_tex y_plane, wrcu_tex u_plane, wrcu_tex v_plane,
+                            int color_space, uint32_t color_depth,
+                            const int32_t src_rect[4], const int32_t dst_rect[4],
+                            int flip_x, int flip_y, const int32_t clip_rect[4]);
+
 /* ---- multi-GPU: the tiles of ONE frame sharded over GPUs ----------------------
  * Picture-cache tiles are independent render targets (frame_builder.rs:995-1057): each GPU draws its
  * share with no data-path communication.  The one exchange step — finished tiles into the

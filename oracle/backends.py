@@ -263,6 +263,19 @@ class SwglDevice:
         g.UnlockResource(ls)
         g.UnlockResource(ld)
 
+    def sw_composite_yuv(self, dst, y, u, v, color_space, src_rect, dst_rect, flip_x, flip_y, clip_rect, color_depth=8):
+        """CompositeYUV (swgl/src/composite.h:1335-1384) between locked textures, as SwCompositor calls it."""
+        g = self.gl
+        g.LockTexture.restype = C.c_void_p
+        g.LockTexture.argtypes = [C.c_uint]
+        g.UnlockResource.argtypes = [C.c_void_p]
+        g.CompositeYUV.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_uint] + [C.c_int] * 8 + [C.c_ubyte] * 2 + [C.c_int] * 4
+        locks = [g.LockTexture(t) for t in (dst, y, u, v)]
+        g.CompositeYUV(*locks, int(color_space), int(color_depth), *src_rect, *dst_rect, 1 if flip_x else 0,
+                       1 if flip_y else 0, *clip_rect)
+        for l in locks[::-1]:
+            g.UnlockResource(l)
+
     def locked_pixels(self, tex):
         """GetResourceBuffer on a locked texture → a copy of what the compositor would read"""
         g = self.gl

@@ -1,6 +1,7 @@
 """CPU tier: the CUDA sources' per-instance / per-pixel device functions,
 executed on the host (tests/emu.py), against the oracle.  This is a development
 aid for a box without a GPU; the parity tests proper are test_cuda_parity.py."""
+import numpy as np
 import pytest
 
 from oracle.backends import OracleDevice
@@ -395,6 +396,36 @@ def test_sw_compositor_blit_math_against_swgl():
         got = e.read_pixels(ed, 0, 0, 640, 360, 4)
         e.close()
         assert (got == ref).all(), name
+
+
+def test_sw_compositor_yuv_blit_math_against_swgl():
+    """wrcu_composite_blit_yuv's arithmetic (the device functions of csrc/blit_yuv.cuh, run on the host) against the
+    unmodified reference's CompositeYUV (swgl/src/composite.h:1335-1384) — bytes equal.  (The GPU tier repeats this
+    through libwrcu_gl.so.)"""
+    import ctypes as C
+    from oracle.backends import SwglDevice, have_swgl
+    import test_gl_shim as T
+    if not have_swgl():
+        pytest.skip("oracle/_ref not built")
+    I4 = C.c_int32 * 4
+
+    def via(e, td, ty, tu, tv, cs, sr, dr, fx, fy, cr):
+        f = e.lib.wremu_composite_blit_yuv
+        f.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_int, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                     C.c_int, C.c_int, C.POINTER(C.c_int32)]
+        assert f(e.ctx, td, ty, tu, tv, int(cs), 8, I4(*sr), I4(*dr), int(fx), int(fy), I4(*cr)) == 0
+
+    for case in T.SW_COMPOSITE_YUV_CASES:
+        planes = T.sw_yuv_planes(case)
+        d = SwglDevice()
+        ref = T.run_sw_composite_yuv(d, case, planes)
+        d.close()
+        e = EmuDevice()
+        got = T.run_sw_composite_yuv(e, case, planes, via=via)
+        e.close()
+        diff = got != ref
+        assert not diff.any(), (case[0], int(diff.sum()), np.argwhere(diff)[:4].tolist())
+        assert (got != planes[3]).any(), case[0]
 
 
 # ---- perspective quads / plane-split polygons: against the reference build itself -------------------------

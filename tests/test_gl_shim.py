@@ -115,6 +115,66 @@ SW_COMPOSITE_CASES = [
 ]
 
 
+SW_COMPOSITE_YUV_CASES = [
+    # (name, luma size, chroma size, colour space, src rect, dst rect, flip_x, flip_y, clip rect)
+    ("420_upscale_bt709", (320, 180), (160, 90), 2, (0, 0, 320, 180), (10, 6, 600, 338), False, False, (0, 0, 640, 360)),
+    ("420_1to1_bt601", (320, 180), (160, 90), 0, (0, 0, 320, 180), (100, 50, 320, 180), False, False, (0, 0, 640, 360)),
+    ("420_upscale_clipped_full_range", (322, 182), (161, 91), 3, (3, 5, 300, 170), (21, 11, 577, 333), False, False, (60, 40, 400, 200)),
+    ("420_partly_outside", (200, 120), (100, 60), 4, (-12, -8, 230, 140), (30, 20, 500, 300), False, False, (0, 0, 640, 360)),
+    ("420_downscale", (640, 360), (320, 180), 1, (0, 0, 640, 360), (40, 30, 233, 131), False, False, (0, 0, 640, 360)),
+    ("420_flip_xy", (320, 180), (160, 90), 5, (0, 0, 320, 180), (50, 20, 480, 270), True, True, (0, 0, 640, 360)),
+    ("444_upscale", (160, 90), (160, 90), 2, (0, 0, 160, 90), (0, 0, 640, 360), False, False, (0, 0, 640, 360)),
+    ("444_gbr_identity", (200, 100), (200, 100), 6, (10, 10, 180, 80), (33, 44, 359, 161), False, True, (50, 50, 300, 140)),
+    ("422_wide_chroma", (320, 180), (160, 180), 2, (0, 0, 320, 180), (5, 5, 630, 350), False, False, (0, 0, 640, 360)),
+    ("420_big_zoom", (64, 48), (32, 24), 0, (8, 8, 40, 30), (0, 0, 640, 360), False, False, (0, 0, 640, 360)),
+    ("420_three_pixels_wide", (320, 180), (160, 90), 2, (0, 0, 320, 180), (100, 100, 3, 50), False, False, (0, 0, 640, 360)),
+    ("420_odd_planes_flipx", (321, 181), (161, 91), 2, (1, 1, 319, 179), (7, 3, 611, 347), True, False, (0, 0, 640, 360)),
+    ("420_dst_partly_off_target", (320, 180), (160, 90), 4, (0, 0, 320, 180), (-50, -40, 800, 450), False, False, (-50, -40, 800, 450)),
+]
+
+
+def sw_yuv_planes(case):
+    _, (yw, yh), (cw, ch), _, _, _, _, _, _ = case
+    rng = np.random.RandomState(7)
+    return (rng.randint(0, 256, (yh, yw)).astype(np.uint8), rng.randint(0, 256, (ch, cw)).astype(np.uint8),
+            rng.randint(0, 256, (ch, cw)).astype(np.uint8), rng.randint(0, 256, (360, 640 * 4)).astype(np.uint8))
+
+
+def run_sw_composite_yuv(dev, case, planes, via=None):
+    """Uploads the planes, runs CompositeYUV (through `via(dev, handles...)` when given), returns the destination."""
+    _, (yw, yh), (cw, ch), cs, sr, dr, fx, fy, cr = case
+    yp, up, vp, dst = planes
+    ty, tu, tv = (dev.texture_create(abi.FMT_R8, yw, yh), dev.texture_create(abi.FMT_R8, cw, ch),
+                  dev.texture_create(abi.FMT_R8, cw, ch))
+    td = dev.texture_create(abi.FMT_RGBA8, 640, 360)
+    dev.texture_upload(ty, 0, 0, yw, yh, yp)
+    dev.texture_upload(tu, 0, 0, cw, ch, up)
+    dev.texture_upload(tv, 0, 0, cw, ch, vp)
+    dev.texture_upload(td, 0, 0, 640, 360, dst)
+    if via is None:
+        dev.sw_composite_yuv(td, ty, tu, tv, cs, sr, dr, fx, fy, cr)
+        return dev.locked_pixels(td)
+    via(dev, td, ty, tu, tv, cs, sr, dr, fx, fy, cr)
+    return dev.read_pixels(td, 0, 0, 640, 360, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SW_COMPOSITE_YUV_CASES, ids=[c[0] for c in SW_COMPOSITE_YUV_CASES])
+def test_sw_compositor_composite_yuv(case):
+    """CompositeYUV (swgl/src/composite.h:1335-1384: linear_convert_yuv / linear_row_yuv / upscaleYUV42R8) through
+    libwrcu_gl.so on the CUDA backend against the unmodified reference: 4:2:0, 4:2:2 and 4:4:4 planes, up- and
+    downscaling, flips, clips, sources partly outside the planes, every colour space — bytes equal."""
+    planes = sw_yuv_planes(case)
+    outs = []
+    for D in (GlShimDevice, SwglDevice):
+        d = D()
+        outs.append(run_sw_composite_yuv(d, case, planes))
+        d.close()
+    diff = outs[0] != outs[1]
+    assert not diff.any(), f"{int(diff.sum())} bytes differ, first at {np.argwhere(diff)[0]}"
+    assert (outs[0] != planes[3]).any()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", SW_COMPOSITE_CASES, ids=[c[0] for c in SW_COMPOSITE_CASES])
 def test_sw_compositor_composite(case):

@@ -159,7 +159,7 @@ SYMBOLS = [
     "wrcu_read_pixels_async", "wrcu_fence_wait", "wrcu_fence_insert",
     "wrcu_profile_enable", "wrcu_last_raster_ms",
     "wrcu_texture_export", "wrcu_texture_import", "wrcu_peer_flags_create", "wrcu_peer_flags_open",
-    "wrcu_peer_signal", "wrcu_peer_wait", "wrcu_composite_blit",
+    "wrcu_peer_signal", "wrcu_peer_wait", "wrcu_composite_blit", "wrcu_composite_blit_yuv",
     "wrcu_texture_upload_batch", "wrcu_texture_copy", "wrcu_gpu_cache_update",
 ]
 

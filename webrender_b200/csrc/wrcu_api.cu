@@ -15,6 +15,7 @@
 #include "shader_box_shadow.cuh"
 #include "shader_composite.cuh"
 #include "shader_composite_yuv.cuh"
+#include "blit_yuv.cuh"
 #include "shader_opacity.cuh"
 #include "shader_blend.cuh"
 #include "shader_mix_blend.cuh"
@@ -937,6 +938,86 @@ extern "C" int wrcu_composite_blit(wrcu_ctx* c, wrcu_tex dst_id, wrcu_tex src_id
 #else
   dim3 block(64, 4), grid((unsigned)((db.x1 - db.x0 + 63) / 64), (unsigned)((db.y1 - db.y0 + 3) / 4));
   wr_sw_composite_blit<<<grid, block, 0, c->stream>>>(a);
+  WRCU_CUDA(c, cudaGetLastError());
+#endif
+  c->stats.kernel_launches++;
+  return WRCU_OK;
+}
+
+// ---- SwCompositor YUV blit (swgl/src/composite.h:1146-1205, 1335-1384) --------------------------
+extern "C" int wrcu_composite_blit_yuv(wrcu_ctx* c, wrcu_tex dst_id, wrcu_tex y_id, wrcu_tex u_id, wrcu_tex v_id,
+                                       int color_space, uint32_t color_depth, const int32_t sr[4], const int32_t dr[4],
+                                       int flip_x, int flip_y, const int32_t cr[4]) {
+  { int rcf_ = flush_pending(c); if (rcf_ != WRCU_OK) return rcf_; }
+  WrTexture *d = get_tex(c, dst_id), *ty = get_tex(c, y_id), *tu = get_tex(c, u_id), *tv = get_tex(c, v_id);
+  if (!d || !ty || !tu || !tv || !sr || !dr || !cr || d->fmt != WRCU_FMT_RGBA8 || color_space < 0 || color_space > 6)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "composite_blit_yuv: needs an RGBA8 destination, three planes, three rects, a colour space 0..6");
+  if (ty->fmt != WRCU_FMT_R8 || tu->fmt != WRCU_FMT_R8 || tv->fmt != WRCU_FMT_R8 || color_depth != 8)
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "composite_blit_yuv: 8-bit R8 planes only (R16 planes: DESIGN.md section 8)");
+  if (tu->w != tv->w || tu->h != tv->h || tu->pitch != tv->pitch)
+    return wrcu_fail(c, WRCU_ERR_INVALID, "composite_blit_yuv: the chroma planes must have one size");
+  if (ty->w < 2 || tu->w < 2)
+    return wrcu_fail(c, WRCU_ERR_UNSUPPORTED, "composite_blit_yuv: planes under 2 texels wide (the reference's single-texel fill)");
+  cudaSetDevice(c->device);
+  { int rcw = wait_pending_read(c, d); if (rcw != WRCU_OK) return rcw; }
+  const IRect srcReq{sr[0], sr[1], sr[0] + sr[2], sr[1] + sr[3]}, dstReq{dr[0], dr[1], dr[0] + dr[2], dr[1] + dr[3]};
+  if (srcReq.x1 <= srcReq.x0 || srcReq.y1 <= srcReq.y0 || dstReq.x1 <= dstReq.x0 || dstReq.y1 <= dstReq.y0) return WRCU_OK;
+  const IRect clip{cr[0] - dr[0], cr[1] - dr[1], cr[0] - dr[0] + cr[2], cr[1] - dr[1] + cr[3]};  // relative to dstReq
+  IRect db = irect_intersect(IRect{0, 0, d->w, d->h}, dstReq);  // dsttex.sample_bounds(dstReq)
+  db = IRect{db.x0 - dstReq.x0, db.y0 - dstReq.y0, db.x1 - dstReq.x0, db.y1 - dstReq.y0};
+  db = irect_intersect(db, clip);
+  if (db.x1 <= db.x0 || db.y1 <= db.y0) return WRCU_OK;
+  YuvBlitArgs a;
+  memset(&a, 0, sizeof a);
+  // linear_convert_yuv's float set-up, step for step (fp32, no contraction)
+  volatile float su = (float)srcReq.x0, sv = (float)srcReq.y0;
+  volatile float du = (float)sr[2] / (float)dr[2], dv = (float)sr[3] / (float)dr[3];
+  if (flip_x) { su = su + (float)sr[2]; du = -du; }
+  if (flip_y) { sv = sv + (float)sr[3]; dv = -dv; }
+  { volatile float t = du * ((float)db.x0 + 0.5f); su = su + t; }
+  { volatile float t = dv * ((float)db.y0 + 0.5f); sv = sv + t; }
+  volatile float csx = (float)tu->w / (float)ty->w, csy = (float)tu->h / (float)ty->h;
+  volatile float cu = su * csx, cv = sv * csy, cdu = du * csx, cdv = dv * csy;
+  const float qoff = 0.5f - 0.5f * 128.0f;  // linearQuantize(P, 128) = P * 128 + (0.5 - 0.5 * 128)
+  { volatile float t = su * 128.0f; su = t + qoff; } { volatile float t = sv * 128.0f; sv = t + qoff; }
+  du = du * 128.0f; dv = dv * 128.0f;
+  { volatile float t = cu * 128.0f; cu = t + qoff; } { volatile float t = cv * 128.0f; cv = t + qoff; }
+  cdu = cdu * 128.0f; cdv = cdv * 128.0f;
+  // linear_row_yuv's row-invariant lanes: cast(init_interp(uv.x, du) * (1 << STEP_BITS)), the per-chunk steps
+  volatile float yl = su, cl = cu;
+  for (int j = 0; j < 4; j++) {
+    { volatile float t = yl * (float)(1 << WR_YUV_STEP_BITS); a.yU0[j] = (int)t; }
+    { volatile float t = cl * (float)(1 << WR_YUV_STEP_BITS); a.cU0[j] = (int)t; }
+    yl = yl + du;
+    cl = cl + cdu;
+  }
+  { volatile float t = (float)(4 << WR_YUV_STEP_BITS) * du; a.yDU = (int)t; }
+  { volatile float t = (float)(4 << WR_YUV_STEP_BITS) * cdu; a.cDU = (int)t; }
+  a.v0 = sv; a.dv = dv; a.cv0 = cv; a.cdv = cdv;
+  a.span = db.x1 - db.x0;
+  a.rows = db.y1 - db.y0;
+  // the half-resolution fast path (composite.h:1089-1123): chunks before it, pixels inside it
+  a.fast = a.yDU >= a.cDU && a.cDU > 0 && a.yDU <= (4 << (WR_YUV_STEP_BITS + 7)) && a.cDU <= (2 << (WR_YUV_STEP_BITS + 7));
+  if (a.fast) {
+    int span = a.span, yx = a.yU0[0], cx = a.cU0[0];
+    while ((yx < 0 || cx < 0) && span >= 4) { span -= 4; yx += a.yDU; cx += a.cDU; a.pre++; }
+    const int in_y = (((ty->w - 4) << (WR_YUV_STEP_BITS + 7)) - yx) / a.yDU, in_c = (((tu->w - 4) << (WR_YUV_STEP_BITS + 7)) - cx) / a.cDU;
+    int inside = (in_y < in_c ? in_y : in_c) * 4;
+    if (inside > (span & ~3)) inside = span & ~3;
+    a.inside = inside > 0 ? inside : 0;
+  }
+  a.dst = d->dptr; a.dst_pitch = (int)d->pitch;
+  a.dx = dstReq.x0 + db.x0; a.dy = dstReq.y0 + db.y0;
+  a.yp = ty->dptr; a.up = tu->dptr; a.vp = tv->dptr;
+  a.y_pitch = (int)ty->pitch; a.c_pitch = (int)tu->pitch;
+  a.yw = ty->w; a.yh = ty->h; a.cw = tu->w; a.ch = tu->h;
+  a.color_space = color_space;
+#ifdef WRCU_HOSTEMU
+  wr_sw_composite_blit_yuv(a);
+#else
+  const int chunks = (a.span + 3) / 4;
+  dim3 block(32, 4), grid((unsigned)((chunks + 31) / 32), (unsigned)((a.rows + 3) / 4));
+  wr_sw_composite_blit_yuv<<<grid, block, 0, c->stream>>>(a);
   WRCU_CUDA(c, cudaGetLastError());
 #endif
   c->stats.kernel_launches++;

@@ -8,10 +8,10 @@
 // DrawElementsInstanced / Clear / ReadPixels / TexSubImage2D into calls on include/wrcu.h.
 // A host linked against it instead of SWGL needs no source change (option 1).
 //
-// Scope: the calls `Device` issues on the frame-draw path and its update path.  The calls that
-// hand raw CPU pointers into SWGL's own memory to the software compositor
-// (LockTexture/LockFramebuffer/Composite*/GetResourceBuffer, SetTextureBuffer) have no
-// counterpart for device memory: they set GL_INVALID_OPERATION and return null.
+// Scope: the calls `Device` issues on the frame-draw path and its update path, and the software
+// compositor's hooks (LockTexture / LockFramebuffer / Composite / CompositeYUV / GetResourceBuffer) as
+// device-side blits.  SetTextureBuffer (a caller-owned CPU buffer as texture storage) has no
+// counterpart for device memory: it sets GL_INVALID_OPERATION.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -885,7 +885,15 @@ void Composite(void* dst, void* src, GLint sx, GLint sy, GLsizei sw, GLsizei sh,
   check(wrcu_composite_blit(ctx->dev, d->dev, s->dev, sr, dr, opaque ? 1 : 0, flipX ? 1 : 0, flipY ? 1 : 0,
                             filter == GL_LINEAR ? 1 : 0, cr));
 }
-void CompositeYUV(void*, void*, void*, void*, int, GLuint, GLint, GLint, GLsizei, GLsizei, GLint, GLint, GLsizei, GLsizei, GLboolean,
-                  GLboolean, GLint, GLint, GLsizei, GLsizei) { set_error(GL_INVALID_OPERATION); }
+void CompositeYUV(void* dst, void* y, void* u, void* v, int colorSpace, GLuint colorDepth, GLint sx, GLint sy, GLsizei sw, GLsizei sh,
+                  GLint dx, GLint dy, GLsizei dw, GLsizei dh, GLboolean flipX, GLboolean flipY, GLint cx, GLint cy, GLsizei cw,
+                  GLsizei ch) {
+  if (!dst || !y || !u || !v) return;  // (composite.h:1342-1344)
+  Tex *d = tex_of(((Locked*)dst)->tex), *ty = tex_of(((Locked*)y)->tex), *tu = tex_of(((Locked*)u)->tex), *tv = tex_of(((Locked*)v)->tex);
+  if (!d || !ty || !tu || !tv || !d->dev || !ty->dev || !tu->dev || !tv->dev || bytes_per_pixel(d->ifmt) != 4) { set_error(GL_INVALID_OPERATION); return; }
+  const int32_t sr[4] = {sx, sy, sw, sh}, dr[4] = {dx, dy, dw, dh}, cr[4] = {cx, cy, cw, ch};
+  check(wrcu_composite_blit_yuv(ctx->dev, d->dev, ty->dev, tu->dev, tv->dev, colorSpace, colorDepth, sr, dr, flipX ? 1 : 0,
+                                flipY ? 1 : 0, cr));
+}
 
 }  // extern "C"
