@@ -187,6 +187,34 @@ struct brush_mix_blend_frag_t : FragmentShaderImpl, brush_mix_blend_vert_t<VARIA
     v_src_uv += interp_step.v_src_uv * chunks;
     v_backdrop_uv += interp_step.v_backdrop_uv * chunks;
   }
+  // draw_perspective: the varyings arrive divided by w and are interpolated linearly in screen space; each chunk
+  // multiplies them back by w = 1 / gl_FragCoord.w (what glsl-to-cxx generates next to the plain pair)
+  struct InterpPerspective {
+    vec2 v_src_uv;
+    vec2 v_backdrop_uv;
+  };
+  InterpPerspective interp_perspective;
+  static void read_perspective_inputs(FragmentShaderImpl* impl, const void* init_, const void* step_) {
+    Self* self = (Self*)impl;
+    const InterpInputs* init = (const InterpInputs*)init_;
+    const InterpInputs* step = (const InterpInputs*)step_;
+    Float w = 1.0f / self->gl_FragCoord.w;
+    self->interp_perspective.v_src_uv = init_interp(init->v_src_uv, step->v_src_uv);
+    self->v_src_uv = self->interp_perspective.v_src_uv * w;
+    self->interp_step.v_src_uv = step->v_src_uv * 4.0f;
+    self->interp_perspective.v_backdrop_uv = init_interp(init->v_backdrop_uv, step->v_backdrop_uv);
+    self->v_backdrop_uv = self->interp_perspective.v_backdrop_uv * w;
+    self->interp_step.v_backdrop_uv = step->v_backdrop_uv * 4.0f;
+  }
+  ALWAYS_INLINE void step_perspective_inputs(int steps = 4) {
+    this->step_perspective(steps);
+    float chunks = steps * 0.25f;
+    Float w = 1.0f / this->gl_FragCoord.w;
+    interp_perspective.v_src_uv += interp_step.v_src_uv * chunks;
+    v_src_uv = w * interp_perspective.v_src_uv;
+    interp_perspective.v_backdrop_uv += interp_step.v_backdrop_uv * chunks;
+    v_backdrop_uv = w * interp_perspective.v_backdrop_uv;
+  }
 
   void main() {
     Float perspective_divisor = mix(this->gl_FragCoord.w, Float(1.0f), Float(this->v_perspective.x));
@@ -207,7 +235,7 @@ struct brush_mix_blend_frag_t : FragmentShaderImpl, brush_mix_blend_vert_t<VARIA
     if (VARIANT == 1) result *= Float(1.0f);  // do_clip()
     this->gl_FragColor = result;
   }
-  WR_FRAGMENT_ABI()
+  WR_FRAGMENT_ABI_W()
   brush_mix_blend_frag_t() { this->init_fragment_abi(); }
 };
 

@@ -79,6 +79,28 @@ struct brush_opacity_frag_t : FragmentShaderImpl, brush_opacity_vert_t<VARIANT> 
     float chunks = steps * 0.25f;
     v_uv += interp_step.v_uv * chunks;
   }
+  // draw_perspective: the varyings arrive divided by w and are interpolated linearly in screen space; each chunk
+  // multiplies them back by w = 1 / gl_FragCoord.w (what glsl-to-cxx generates next to the plain pair)
+  struct InterpPerspective {
+    vec2 v_uv;
+  };
+  InterpPerspective interp_perspective;
+  static void read_perspective_inputs(FragmentShaderImpl* impl, const void* init_, const void* step_) {
+    Self* self = (Self*)impl;
+    const InterpInputs* init = (const InterpInputs*)init_;
+    const InterpInputs* step = (const InterpInputs*)step_;
+    Float w = 1.0f / self->gl_FragCoord.w;
+    self->interp_perspective.v_uv = init_interp(init->v_uv, step->v_uv);
+    self->v_uv = self->interp_perspective.v_uv * w;
+    self->interp_step.v_uv = step->v_uv * 4.0f;
+  }
+  ALWAYS_INLINE void step_perspective_inputs(int steps = 4) {
+    this->step_perspective(steps);
+    float chunks = steps * 0.25f;
+    Float w = 1.0f / this->gl_FragCoord.w;
+    interp_perspective.v_uv += interp_step.v_uv * chunks;
+    v_uv = w * interp_perspective.v_uv;
+  }
 
   // brush_opacity.glsl:56-74 + brush.glsl main
   void main() {
@@ -103,7 +125,7 @@ struct brush_opacity_frag_t : FragmentShaderImpl, brush_opacity_vert_t<VARIANT> 
     Self* self = (Self*)impl;
     DISPATCH_DRAW_SPAN(self, RGBA8);
   }
-  WR_FRAGMENT_ABI()
+  WR_FRAGMENT_ABI_W()
   brush_opacity_frag_t() {
     this->init_fragment_abi();
     this->draw_span_RGBA8_func = &draw_span_RGBA8;

@@ -77,6 +77,8 @@ CASES = [
     ("perspective_brush_solid_aa", "perspective_frame", dict(kind="solid", d=800.0, ry=35.0, rx=10.0, seed=4, force_aa=True,
                                                               n_opaque=6, n_alpha=12), False),
     ("perspective_brush_image_clipped", "perspective_frame", dict(kind="image", d=220.0, ry=60.0, rx=-30.0, seed=2), False),
+    ("perspective_brush_opacity", "perspective_frame", dict(kind="opacity", d=220.0, ry=60.0, rx=-30.0, seed=2, brush_flags=1), False),
+    ("perspective_brush_mix_blend", "perspective_frame", dict(kind="mix_blend", height=400, d=800.0, ry=-20.0, rx=15.0, seed=2), False),
     ("split_composite", "split_composite_frame", dict(seed=1), False),
     ("split_composite_near_plane", "split_composite_frame", dict(seed=2, d=220.0, ry=65.0, rx=20.0, perspective_interpolate=1),
      False),

@@ -566,6 +566,24 @@ def test_perspective_brushes(kind, cam):
     assert_same(render(CudaDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
 
 
+@pytest.mark.parametrize("cam", PERSP_CAMERAS[:4])
+@pytest.mark.parametrize("kind", ["opacity", "blend", "mix_blend"])
+def test_perspective_picture_brushes(kind, cam):
+    """brush_opacity / brush_blend / brush_mix_blend drawing a picture's surface under a perspective node —
+    byte-exact against SWGL (hue-rotate's cosf/sinf aside: <= 1 LSB)."""
+    d, ry, rx = cam
+    kw = dict(seed=2)
+    if kind == "opacity":
+        kw.update(brush_flags=1)
+    f = scenes.perspective_frame(kind, height=400 if kind != "opacity" else 360, d=d, ry=ry, rx=rx, **kw)
+    got, want = render(CudaDevice, f, ["target"]), render(_swgl(), f, ["target"])
+    if kind == "blend":
+        dd = np.abs(got["target"].astype(int) - want["target"].astype(int))
+        assert dd.max() <= 1 and (dd != 0).mean() < 2e-3, (int(dd.max()), float((dd != 0).mean()))
+    else:
+        assert_same(got, want, f"{kind} {cam}")
+
+
 def test_perspective_full_size():
     """4K: long polygon edges (rows up to 2160) and spans up to 3840 samples of stepped z/w."""
     f = scenes.perspective_frame("solid", width=3840, height=2160, d=3000.0, ry=50.0, rx=-20.0, seed=5, n_opaque=4,

@@ -456,6 +456,20 @@ def test_perspective_brushes(kind, cam):
     assert_same(render(EmuDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
 
 
+@pytest.mark.parametrize("cam", PERSP_CAMERAS[1:3])
+@pytest.mark.parametrize("kind", ["opacity", "blend", "mix_blend"])
+def test_perspective_picture_brushes(kind, cam):
+    """brush_opacity / brush_blend / brush_mix_blend drawing a picture's surface under a perspective node: fragment
+    path only, varyings times w, mix(gl_FragCoord.w, 1, v_perspective) per sample (with and without
+    BrushFlags::PERSPECTIVE_INTERPOLATION for opacity)."""
+    d, ry, rx = cam
+    kw = dict(seed=2)
+    if kind == "opacity":
+        kw.update(brush_flags=1)
+    f = scenes.perspective_frame(kind, height=400 if kind != "opacity" else 360, d=d, ry=ry, rx=rx, **kw)
+    assert_same(render(EmuDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(d=220.0, ry=65.0, rx=20.0), dict(perspective_interpolate=1, seed=3),
                                 dict(d=1e9, ry=0.0, rx=0.0, seed=4), dict(seed=5, filter=abi.NEAREST)])
 def test_split_composite(kw):

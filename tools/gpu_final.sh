@@ -22,7 +22,7 @@ for l in open("gpurun_out/z_workloads.jsonl"):
     d=json.loads(l); cb=d.get("cpu_baseline",{})
     print("%-12s %.3f ms  (warm %.3f, pipelined %.3f) launches %d | SWGL 1 core %.2f ms"%(d["config"]["workload"], d["ms_per_step"], d["ms_warm_l2"], d["ms_pipelined"], d["gpu_launches"], 1e3/cb["value"] if cb else -1))
 PY
-for w in composite page; do
+for w in composite page text; do
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/z_launches_$w.csv python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/z_ncu_$w.log 2>&1
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/z_launches_configB.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sweep > gpurun_out/z_ncu_configB.log 2>&1
@@ -33,5 +33,7 @@ timeout 300 ncu --set full --clock-control none -k regex:wr_composite_copy -s 3 
 ncu -i /tmp/z_prof_copy.ncu-rep --page raw --csv > gpurun_out/ncu_full_composite_copy_r02.raw.csv 2>/dev/null
 timeout 300 ncu --set full --clock-control none -k regex:wr_raster_solid_flat -s 2 -c 1 -o /tmp/z_prof_flat python bench.py --sweep-only --steps 2 > gpurun_out/z_ncu_flat.log 2>&1
 ncu -i /tmp/z_prof_flat.ncu-rep --page raw --csv > gpurun_out/ncu_full_solid_flat_r02.raw.csv 2>/dev/null
+timeout 300 ncu --set full --clock-control none -k regex:wr_raster_glyphs -s 1 -c 1 -o /tmp/z_prof_glyphs python bench.py --workload text --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/z_ncu_glyphs.log 2>&1
+ncu -i /tmp/z_prof_glyphs.ncu-rep --page raw --csv > gpurun_out/ncu_full_text_glyphs_r02.raw.csv 2>/dev/null
 du -sh gpurun_out
 echo done

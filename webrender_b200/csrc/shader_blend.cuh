@@ -117,7 +117,12 @@ struct BlendShader {
     float uv[2];
     wr_chunk_lane<2>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, uv);
     float Cs[4];
-    wr_tex_fragment(a.color0, wr_clamp(uv[0] * r.pd, k.f[0], k.f[2]), wr_clamp(uv[1] * r.pd, k.f[1], k.f[3]), Cs);
+    float pd = r.pd;
+    if (a.persp) {  // gl_FragCoord.w varies per sample
+      const float fw = wr_persp_zw(*a.persp, 1, rel);
+      pd = (1.0f - fw) * k.f[4] + fw;
+    }
+    wr_tex_fragment(a.color0, wr_clamp(uv[0] * pd, k.f[0], k.f[2]), wr_clamp(uv[1] * pd, k.f[1], k.f[3]), Cs);
     float alpha = Cs[3];
     float color[3];
     for (int i = 0; i < 3; i++) color[i] = alpha != 0.0f ? Cs[i] / alpha : Cs[i];

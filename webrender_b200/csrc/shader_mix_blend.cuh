@@ -91,7 +91,12 @@ struct MixBlendShader {
     wr_chunk_lane<4>(a, r.base, r.step, r.kb, rel >> 2, rel & 3, L);
     float Cb[4], Cs[4], t[3], result[4];
     wr_tex_fragment(a.color0, wr_clamp(L[2], k.f[4], k.f[6]), wr_clamp(L[3], k.f[5], k.f[7]), Cb);
-    wr_tex_fragment(a.color1, wr_clamp(L[0] * r.pd, k.f[0], k.f[2]), wr_clamp(L[1] * r.pd, k.f[1], k.f[3]), Cs);
+    float pd = r.pd;
+    if (a.persp) {  // gl_FragCoord.w varies per sample
+      const float fw = wr_persp_zw(*a.persp, 1, rel);
+      pd = (1.0f - fw) * k.g[0] + fw;
+    }
+    wr_tex_fragment(a.color1, wr_clamp(L[0] * pd, k.f[0], k.f[2]), wr_clamp(L[1] * pd, k.f[1], k.f[3]), Cs);
     if (Cb[3] != 0.0f) for (int i = 0; i < 3; i++) Cb[i] /= Cb[3];
     if (Cs[3] != 0.0f) for (int i = 0; i < 3; i++) Cs[i] /= Cs[3];
     result[0] = 1.0f; result[1] = 1.0f; result[2] = 0.0f; result[3] = 1.0f;

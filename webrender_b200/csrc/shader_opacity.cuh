@@ -17,7 +17,7 @@ struct OpacityShader {
     wr_row_interp<2>(a, k, c, y, r.o, r.step);
     r.pd = (1.0f - k.f[6]) * k.f[5] + k.f[6];
     int len = c.x1 - c.x0;
-    int body_len = (rgba && len >= 4) ? (len & ~3) : 0;
+    int body_len = (rgba && len >= 4 && !a.persp) ? (len & ~3) : 0;  // (perspective rows have no span body)
     float u[4], v[4];
     for (int j = 0; j < 4; j++) {
       float uv[2];
@@ -38,7 +38,12 @@ struct OpacityShader {
     float uv[2];
     wr_interp_at<2>(a, r.o, r.step, rel, uv);
     float texel[4];
-    wr_tex_fragment(t, wr_clamp(uv[0] * r.pd, k.f[0], k.f[2]), wr_clamp(uv[1] * r.pd, k.f[1], k.f[3]), texel);
+    float pd = r.pd;
+    if (a.persp) {  // gl_FragCoord.w varies per sample
+      const float fw = wr_persp_zw(*a.persp, 1, rel);
+      pd = (1.0f - fw) * k.f[5] + fw;
+    }
+    wr_tex_fragment(t, wr_clamp(uv[0] * pd, k.f[0], k.f[2]), wr_clamp(uv[1] * pd, k.f[1], k.f[3]), texel);
     Px o;
     o.r = wr_round_pixel(k.f[4] * texel[0], 255.0f) & 0xFFFF;
     o.g = wr_round_pixel(k.f[4] * texel[1], 255.0f) & 0xFFFF;

@@ -1550,6 +1550,7 @@ static int draw_batch_impl(wrcu_ctx* c, int kind, uint32_t features, const wrcu_
   // draw_perspective (w differs between an instance's vertices): the kinds whose fragment stage carries the
   // per-sample 1/w path; the solid colour case of ps_quad_textured shares brush_solid's shader
   sa.persp_ok = kind == WRCU_KIND_BRUSH_SOLID || kind == WRCU_KIND_SPLIT_COMPOSITE || kind == WRCU_KIND_QUAD_TEXTURED ||
+                kind == WRCU_KIND_BRUSH_OPACITY || kind == WRCU_KIND_BRUSH_BLEND || kind == WRCU_KIND_BRUSH_MIX_BLEND ||
                 (kind == WRCU_KIND_BRUSH_IMAGE && !(features & WRCU_FEAT_REPETITION));
   // copy class (shader_composite.cuh): 1 = 1:1 tile copies and solid fills, 2 = fills only (the clear tile's dest-out)
   sa.copy_ok = T.depth ? 0 : (st->blend == WRCU_BLEND_NONE || st->blend == WRCU_BLEND_PREMULTIPLIED_ALPHA) ? 1

@@ -584,7 +584,8 @@ def perspective_frame(kind="solid", width=640, height=360, d=800.0, ry=35.0, rx=
     rasterize.h:1422-1545): kind = "solid" (brush_solid_frame: opaque + alpha with masks / AA) or "image"
     (image_frame: opaque + alpha pass sampling an atlas)."""
     m = perspective_matrix(width, height, d, ry, rx)
-    make = {"solid": brush_solid_frame, "image": image_frame, "quad": rounded_rects_frame}[kind]
+    make = {"solid": brush_solid_frame, "image": image_frame, "quad": rounded_rects_frame, "opacity": opacity_frame,
+            "blend": blend_frame, "mix_blend": mix_blend_frame}[kind]
     return with_transform(make, m, width=width, height=height, **kw)
 
 
@@ -1633,7 +1634,8 @@ def _picture_source(t, rng, aw, ah, w, h, one_to_one):
                              (0.0, 0.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)])
 
 
-def opacity_frame(width=640, height=360, n_prims=14, seed=1, fractional=False, one_to_one=False, filter=abi.LINEAR):
+def opacity_frame(width=640, height=360, n_prims=14, seed=1, fractional=False, one_to_one=False, filter=abi.LINEAR,
+                  rotate=None, brush_flags=0):
     """Brush(Opacity) batch (batch.rs:1671-1712): pictures with a filter:
     opacity() drawn from their off-screen surface, premultiplied-alpha blended;
     prim user data = [uv_rect_address, amount * 65536, 0, 0]."""
@@ -1643,13 +1645,15 @@ def opacity_frame(width=640, height=360, n_prims=14, seed=1, fractional=False, o
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
     aw, ah = 320, 200
     inst = []
+    # `rotate`: the pictures sit under a transformed spatial node (with_transform: any 4x4, e.g. a perspective one)
+    xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0), axis_aligned=False) if rotate is not None else 0
     for i in range(n_prims):
         r = _rand_rect(rng, width, height, 24, 220, integer=not fractional)
         src = _picture_source(t, rng, aw, ah, r[2] - r[0], r[3] - r[1], one_to_one)
         spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
         amount = 1.0 if i % 5 == 0 else float(rng.uniform(0.05, 1.0))
-        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (src, int(amount * 65536.0), 0, 0))
-        inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, xf, pic, (src, int(amount * 65536.0), 0, 0))
+        inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, brush_flags if i % 2 else 0, 0))
     textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
                 "surface": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 31, opaque=False), filter=filter)}
     ops = [Clear(color=(0.9, 0.9, 0.9, 1.0)),
@@ -1705,7 +1709,7 @@ def clear_frame(width=512, height=320, seed=1, r8=False):
  FILTER_COMPONENT_TRANSFER) = range(12)
 
 
-def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=False):
+def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=False, rotate=None):
     """Brush(Blend) batch (batch.rs:1715-1890): one picture per CSS filter op —
     contrast, grayscale, hue-rotate, invert, saturate, sepia, brightness, colour
     matrix, sRGB<->linear, flood and a component transfer (table / discrete /
@@ -1716,6 +1720,7 @@ def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=F
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
     aw, ah = 320, 200
     inst = []
+    xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0), axis_aligned=False) if rotate is not None else 0
     filters = [(FILTER_CONTRAST, 1.6), (FILTER_GRAYSCALE, 0.7), (FILTER_HUE_ROTATE, 110.0), (FILTER_INVERT, 0.85),
                (FILTER_SATURATE, 2.2), (FILTER_SEPIA, 0.6), (FILTER_BRIGHTNESS, 1.4), (FILTER_COLOR_MATRIX, None),
                (FILTER_SRGB_TO_LINEAR, None), (FILTER_LINEAR_TO_SRGB, None), (FILTER_FLOOD, None),
@@ -1748,7 +1753,7 @@ def blend_frame(width=640, height=400, seed=1, fractional=False, opaque_source=F
         else:
             user = 0
         spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
-        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (src, mode, user, 0))
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, xf, pic, (src, mode, user, 0))
         inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
     textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
                 "surface": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 51, opaque=opaque_source),
@@ -1823,7 +1828,7 @@ def filter_reftest_frames(name, size=(220, 220)):
     return out[0], out[1]
 
 
-def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
+def mix_blend_frame(width=640, height=400, seed=1, fractional=False, rotate=None):
     """Brush(MixBlend) batch (batch.rs:1931-2001): one picture per non-separable /
     separable mix-blend-mode handled in the shader (multiply, overlay, darken,
     lighten, colour-dodge, colour-burn, hard-light, soft-light, difference, hue,
@@ -1835,6 +1840,7 @@ def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
     pic = t.add_render_task((0.0, 0.0, float(width), float(height)), 1.0, (0.0, 0.0))
     aw, ah = 320, 200
     inst = []
+    xf = t.add_transform(rotation_matrix(rotate, width / 2.0, height / 2.0), axis_aligned=False) if rotate is not None else 0
     modes = [1, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 14, 15, 9, 6]
     for i, mode in enumerate(modes):
         col, row = i % 5, i // 5
@@ -1845,7 +1851,7 @@ def mix_blend_frame(width=640, height=400, seed=1, fractional=False):
         back = _picture_source(t, rng, aw, ah, 118, 122, True)
         src = _picture_source(t, rng, aw, ah, 118, 122, i % 3 != 2)
         spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
-        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, 0, pic, (mode, back, src, 0))
+        hdr = t.add_prim_header(r, (-1e9, -1e9, 1e9, 1e9), i + 1, spec, xf, pic, (mode, back, src, 0))
         inst.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
     textures = {"target": TextureDesc(abi.FMT_RGBA8, width, height),
                 "backdrop": TextureDesc(abi.FMT_RGBA8, aw, ah, data=tile_texture(aw, ah, seed + 61, opaque=seed % 2 == 0),
