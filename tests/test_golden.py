@@ -188,6 +188,31 @@ def test_filter_reftests_known_answers(name):
     _filter_reftest(OracleDevice, name)
 
 
+def _picture_reftest(device_cls, name):
+    _, r, _, _, _, _, exp, (max_diff, max_px) = scenes.PICTURE_REFTESTS[name]
+    f = scenes.picture_reftest_frame(name)
+    out = render(device_cls, f, ["target"])["target"].reshape(140, 140, 4)[..., [2, 1, 0, 3]].astype(int)
+    inside = out[r[1]:r[3], r[0]:r[2], :3]
+    d = np.abs(inside - np.array(exp)).max(axis=2)
+    assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (name, int(d.max()), int((d > 0).sum()), inside[0, 0])
+    assert (out[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("name", sorted(scenes.PICTURE_REFTESTS))
+def test_picture_reftests_known_answers(name):
+    """filters/opacity.yaml, blend/{multiply,difference,darken,lighten}.yaml == their -ref.yaml: brush_opacity and
+    brush_mix_blend must produce the colour the reference's authors wrote down (255,255,209 for yellow at alpha 0.2 under
+    opacity(0.9) over white; green x green = green; green - green = black; per-channel min / max)."""
+    _picture_reftest(OracleDevice, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(scenes.PICTURE_REFTESTS))
+def test_cuda_picture_reftests_known_answers(name):
+    from webrender_b200.device import CudaDevice
+    _picture_reftest(CudaDevice, name)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(scenes.FILTER_REFTESTS))
 def test_cuda_filter_reftests_known_answers(name):

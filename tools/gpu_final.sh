@@ -12,6 +12,8 @@ timeout 400 python bench.py --impl reference --ref-cores 1 --steps 2 --warmup 1 
 for w in page composite clip_rects text video_nv12 gradients box_shadow images blur b_prime; do
   timeout 200 python bench.py --workload $w --steps 10 >> gpurun_out/z_workloads.jsonl 2>> gpurun_out/z_workloads.err
 done
+for g in 4 6 8; do WRCU_GLYPH_CTAS=$g timeout 200 python bench.py --workload text --steps 10 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('text glyph_ctas=$g', round(d['ms_per_step'],3))"; done
+for w in video_nv12 gradients; do WRCU_STRIP=0 timeout 200 python bench.py --workload $w --steps 10 --no-cpu-baseline >> gpurun_out/z_workloads_strip0.jsonl 2>/dev/null; done
 python - <<PY
 import json
 for f in ("z_ref_all","z_ref_8","z_ref_1"):

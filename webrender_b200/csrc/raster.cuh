@@ -48,6 +48,7 @@ struct RasterArgs {
   uint32_t* tile_ord;    // glyph-major text: bit t = an ordered command (CMD_ORDERED) touches tile t (binned batches)
   int glyph_major;       // the batch went through wr_raster_glyphs first: the tile kernel draws only CMD_ORDERED commands
   int lane_rows;         // the lanes of a warp hold different (command,row)s: no warp-cooperative walks in the row set-up
+  int strip_seg;         // > 0: strip mode of the tile kernel — work items are runs of this many adjacent tiles of a tile row
   int bin_words, bin_tiles_x;
   const float* row_tab;  // row tables written by the setup kernel (CmdCold::row_off)
   // Depth runs (rasterize.h:601-657): with depth testing on, the reference draws each maximal run of
@@ -827,13 +828,27 @@ WRD int wr_bits_next(const uint32_t* w, int from, int to, bool want) {
   return to;
 }
 
+// Row state across the tiles of a row.  A full-width surface (a video frame, a page-wide gradient) crosses 30 tiles
+// of a 4K row and S::row_setup — edge interpolants, quantised start lanes, filter selection — is the same work in each
+// of them.  In STRIP mode (RasterArgs::strip_seg) a CTA takes a run of horizontally adjacent tiles and walks it left
+// to right; its warps stay on their rows, so a shader that says its Row can serve a later tile of the same
+// (command,row) (WrRowReuse<S>::ok) has it kept instead of rebuilt.
+template <class S> struct WrRowReuse {
+  enum { v = 0 };
+  WRD_MEMBER bool ok(const typename S::Row&) { return false; }
+};
+template <class S> struct WrRowCache {
+  typename S::Row row;
+  int cold, y;  // the (command,row) `row` was built for; cold < 0: none
+};
+
 // ---- the generic tile kernel (any command kind via the shader policy S, any
 // blend key).  S::row_setup computes per-(command,row) constants once per warp
 // (all 32 lanes of a warp share the row, so the work is warp-uniform);
 // S::source returns the fragment stage's output for one pixel as 16-bit lanes.
 template <class S, int FMT, bool RUNS>
 WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh, int* wsum, unsigned short* list,
-                        const bool skip_copy) {
+                        const bool skip_copy, WrRowCache<S>& cache) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = tx0 + lane * 4, y = ty0 + warp;
   const bool row_ok = y < a.tgt.h;
@@ -968,7 +983,10 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
           zb[0] = v.x; zb[1] = v.y; zb[2] = v.z; zb[3] = v.w;
         }
       }
-      typename S::Row row;
+      // (strip mode: the Row of the tile to the left, when this is still its command and the shader allows it)
+      typename S::Row row_local;
+      const bool cacheable = WrRowReuse<S>::v && a.strip_seg > 0 && !(c.flags & (CMD_GENERAL | CMD_PERSP | CMD_CLIP_DIST));
+      typename S::Row& row = cacheable ? cache.row : row_local;
       // With depth testing on, each maximal run of passing samples of the row's span is drawn as a span of
       // its own (draw_depth_span, rasterize.h:612-657).  The runs are walked in order up to this tile
       // (warp-uniform; the failing-sample bitmap was written by wr_depth_fail_rows before this kernel
@@ -997,7 +1015,12 @@ WRD void wr_raster_tile(RasterArgs& a, const int tx0, const int ty0, CmdHot* sh,
           walk.begin(a, kc, cr, y);
         }
         // (for a run left of the tile only its span-shader pixel count is needed)
-        S::row_setup(a, cr, y, here ? tx0 : ((int)cr.x0 & ~(WRCU_TILE_W - 1)), FMT == WRCU_FMT_RGBA8, row);
+        if (cacheable && !runs && cache.cold == (int)c.cold && cache.y == y && WrRowReuse<S>::ok(cache.row)) {
+          // kept from the tile to the left
+        } else {
+          S::row_setup(a, cr, y, here ? tx0 : ((int)cr.x0 & ~(WRCU_TILE_W - 1)), FMT == WRCU_FMT_RGBA8, row);
+          if (cacheable) { cache.cold = runs ? -1 : (int)c.cold; cache.y = y; }
+        }
         if (here) {
           const CmdHot& c = cr;
       const int nxs = max((int)c.x0, tx0), nw = min((int)c.x1, tx0 + WRCU_TILE_W) - nxs;
@@ -1088,6 +1111,26 @@ wr_raster(RasterArgs a) {
   // tiles are handed out dynamically: their cost varies with what lands on them
   __shared__ int s_tile;
   __shared__ unsigned short list[WRCU_THREADS * 32];  // command indices of the tile's set mask bits, in order
+  WrRowCache<S> cache;
+  cache.cold = -1;
+  cache.y = -1;
+  if (WrRowReuse<S>::v && a.strip_seg > 0) {
+    // strip mode: the work items are runs of strip_seg horizontally adjacent tiles, walked left to right
+    const int segs = (nx + a.strip_seg - 1) / a.strip_seg, n_items = segs * (by1 - by0);
+    for (;;) {
+      if (threadIdx.x == 0) s_tile = atomicAdd(const_cast<int*>(&a.info->tile_counter), 1);
+      __syncthreads();
+      const int t = s_tile;
+      if (t >= n_items) break;
+      const int ty = by0 + t / segs, txa = bx0 + (t % segs) * a.strip_seg, txb = min(txa + a.strip_seg, bx1);
+      cache.cold = -1;
+      for (int tx = txa; tx < txb; tx++) {
+        wr_raster_tile<S, FMT, RUNS>(a, tx * WRCU_TILE_W, ty * WRCU_TILE_H, sh, wsum, list, skip_copy, cache);
+        __syncthreads();
+      }
+    }
+    return;
+  }
   for (;;) {
     if (threadIdx.x == 0) {
       // binned batches: pass over tiles no command touches (text: ~7 of 8 tiles of a 4K page) with one load each
@@ -1103,7 +1146,7 @@ wr_raster(RasterArgs a) {
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) break;
-    wr_raster_tile<S, FMT, RUNS>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list, skip_copy);
+    wr_raster_tile<S, FMT, RUNS>(a, (bx0 + t % nx) * WRCU_TILE_W, (by0 + t / nx) * WRCU_TILE_H, sh, wsum, list, skip_copy, cache);
     __syncthreads();
   }
 }

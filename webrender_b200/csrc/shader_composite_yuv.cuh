@@ -562,6 +562,15 @@ template <> struct WrRun<CompositeYuvShader> {  // brush_yuv_image draws under d
 };
 
 #ifndef WRCU_HOSTEMU
+// Strip mode: with the chain table the Row holds nothing that depends on the tile (the u sums come from the
+// table, v does not move along a row, the tail pixels interpolate from the span start).
+template <> struct WrRowReuse<CompositeYuvShader> {
+  enum { v = 1 };
+  WRD_MEMBER bool ok(const CompositeYuvShader::Row& r) { return r.chain != nullptr; }
+};
+#endif
+
+#ifndef WRCU_HOSTEMU
 // The same shader compiled for ONE resident CTA per SM (255 registers): the row state of three planes no longer
 // spills (608 bytes of stack at 128 registers).  WRCU_YUV_WIDE=1 launches it; measured against the default in
 // profiles/README_r02.md.

@@ -322,3 +322,13 @@ template <> struct WrRun<GradientShader> {
   enum { n = 2 };
   WRD_MEMBER int drawn(const GradientShader::Row& r) { return r.body_len; }
 };
+
+#ifndef WRCU_HOSTEMU
+// Strip mode: the Row is the state of the reference's walk along the span (position, current run); a pixel further
+// right continues that walk (source() walks forward from it), exactly as the reference does — so the Row of the tile
+// to the left serves, and the walk from the span start to this tile is not repeated.
+template <> struct WrRowReuse<GradientShader> {
+  enum { v = 1 };
+  WRD_MEMBER bool ok(const GradientShader::Row&) { return true; }
+};
+#endif

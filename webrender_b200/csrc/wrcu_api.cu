@@ -256,6 +256,11 @@ extern "C" int wrcu_ctx_create(int device_ordinal, wrcu_ctx** out) {
     c->immediate = e && atoi(e) != 0;
     e = getenv("WRCU_PDL");
     c->pdl = e ? atoi(e) != 0 : true;
+    e = getenv("WRCU_GLYPH_CTAS");
+    c->glyph_ctas = e ? atoi(e) : 6;
+    if (c->glyph_ctas < 1 || c->glyph_ctas > 16) c->glyph_ctas = 6;
+    e = getenv("WRCU_STRIP");
+    c->strip = e ? atoi(e) != 0 : true;
     e = getenv("WRCU_YUV_WIDE");
     c->yuv_wide = e && atoi(e) != 0;
     e = getenv("WRCU_EARLY_CLEAR");
@@ -1883,6 +1888,14 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
   // of the chip while most of its CTAs find no tile.
   const int max_ctas = (c->side_reduce && n <= 256) ? c->sm_count * c->side_ctas_per_sm : c->sm_count * 3;
   const int pgrid = total_tiles < max_ctas ? total_tiles : max_ctas;
+  // strip mode (raster.cuh WrRowReuse): few commands on a wide target — work items become runs of adjacent tiles,
+  // as long as there are still about two items per resident CTA
+  ra.strip_seg = 0;
+  if (c->strip && n <= 16 && (kind == WRCU_KIND_COMPOSITE || kind == WRCU_KIND_BRUSH_YUV_IMAGE || kind == WRCU_KIND_BRUSH_LINEAR_GRADIENT)) {
+    int seg = 10;
+    while (seg > 1 && (((int)grid.x + seg - 1) / seg) * (int)grid.y < 2 * max_ctas) seg--;
+    if (seg > 1) ra.strip_seg = seg;
+  }
 #define LAUNCH_RASTER(S)                                                         \
   do {                                                                           \
     auto k_rgba = wr_raster<S, WRCU_FMT_RGBA8>;                                   \
@@ -1920,7 +1933,7 @@ static int launch_raster(wrcu_ctx* c, PendingOp& op) {
         auto k_glyphs = wr_raster_glyphs<WRCU_FMT_RGBA8>;
         const int per_cta = WR_GLYPH_THREADS / 32;
         int ggrid = (n + per_cta - 1) / per_cta;           // persistent warps taking glyphs by ticket
-        if (ggrid > c->sm_count * 4) ggrid = c->sm_count * 4;
+        if (ggrid > c->sm_count * c->glyph_ctas) ggrid = c->sm_count * c->glyph_ctas;
         wr_launch_chain(c, k_glyphs, (unsigned)ggrid, WR_GLYPH_THREADS, 0, ra);
         c->stats.kernel_launches++;
         ra.pdl_early = 0;  // the tile kernel reads what the glyph kernel wrote (flags, BatchInfo::n_ordered)

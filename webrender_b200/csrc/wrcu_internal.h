@@ -168,6 +168,8 @@ struct wrcu_ctx {
   std::vector<cudaEvent_t> op_events, join_ev;
   bool plain_next = false;         // the next chained launch follows an event wait: launch it the ordinary way
   bool early_clear = true;         // clears wait for the fork point BEFORE the set-up launch (WRCU_EARLY_CLEAR=0: after it)
+  int glyph_ctas = 6;              // persistent CTAs per SM of the glyph-major kernel (WRCU_GLYPH_CTAS)
+  bool strip = true;               // strip mode of the tile kernel for wide single-surface batches (WRCU_STRIP=0: off)
   bool yuv_wide = false;           // composite YUV through the one-CTA-per-SM variant (WRCU_YUV_WIDE=1)
   bool glyph_major = true;         // text batches go through wr_raster_glyphs first (WRCU_GLYPH_MAJOR=0: tile kernel only)
   cudaEvent_t fork_ev = nullptr;

@@ -1828,6 +1828,63 @@ def filter_reftest_frames(name, size=(220, 220)):
     return out[0], out[1]
 
 
+PICTURE_REFTESTS = {
+    # Known answers the reference's authors wrote down for picture compositing (a yaml that must equal a plain rect of
+    # the stated colour): (page background, rect, kind, source colour 0-255 + alpha, parameter, backdrop colour or None,
+    # expected colour 0-255, allowed (max diff, pixels)).
+    # filters/opacity.yaml == opacity-ref.yaml, fuzzy-if(platform(swgl),1,10000): "opacity pre-multiplied color"
+    "opacity": ((255, 255, 255), (20, 20, 120, 120), "opacity", (255, 255, 0, 0.2), 0.9, None, (255, 255, 209), (1, 10000)),
+    # blend/multiply.yaml == multiply-ref.yaml: green x green = green
+    "multiply": ((255, 255, 255), (25, 25, 75, 75), "mix", (0, 255, 0, 1.0), 1, (0, 255, 0), (0, 255, 0), (0, 0)),
+    # blend/difference.yaml == difference-ref.yaml: green - green = black
+    "difference": ((255, 255, 255), (0, 0, 100, 100), "mix", (0, 255, 0, 1.0), 10, (0, 255, 0), (0, 0, 0), (0, 0)),
+    # blend/darken.yaml, lighten.yaml (fuzzy-if(platform(swgl),1,10000)): per-channel min / max
+    "darken": ((255, 255, 255), (0, 0, 100, 100), "mix", (30, 20, 10, 1.0), 4, (10, 20, 30), (10, 20, 10), (1, 10000)),
+    "lighten": ((255, 255, 255), (0, 0, 100, 100), "mix", (30, 20, 10, 1.0), 5, (10, 20, 30), (30, 20, 30), (1, 10000)),
+}
+
+
+def picture_reftest_frame(name, size=(140, 140)):
+    """One of PICTURE_REFTESTS: a uniform picture surface (premultiplied 8-bit, as the picture pass leaves it) drawn by
+    Brush(Opacity) or Brush(MixBlend) — backdrop readback in sColor0, the picture's surface in sColor1 — over the page
+    (for mix-blend: over the backdrop rect drawn first), premultiplied blending."""
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
+    bg, r, kind, src, param, backdrop, _, _ = PICTURE_REFTESTS[name]
+    w, h = size
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(w), float(h)), 1.0, (0.0, 0.0))
+    rect = tuple(float(v) for v in r)
+
+    def uniform(col, alpha):
+        px = [int(np.float32(v / 255.0 * alpha) * np.float32(255.0) + np.float32(0.5)) for v in col] + [int(alpha * 255.0 + 0.5)]
+        img = np.zeros((64, 64, 4), dtype=np.uint8)
+        img[:, :] = (px[2], px[1], px[0], px[3])   # BGRA
+        return img.reshape(64, 256)
+
+    def source():
+        return t.push_gpu_cache([(8.0, 8.0, 56.0, 56.0), (0.0, 0.0, 0.0, 0.0),
+                                 (0.0, 0.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)])
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, w, h),
+                "surface": TextureDesc(abi.FMT_RGBA8, 64, 64, data=uniform(src[:3], float(src[3])), filter=abi.LINEAR)}
+    ops = [Clear(color=tuple(v / 255.0 for v in bg) + (1.0,))]
+    spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
+    if kind == "opacity":
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 1, spec, 0, pic, (source(), int(param * 65536.0), 0, 0))
+        ops.append(Batch(abi.KIND_BRUSH_OPACITY, brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
+                         blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS, color=("surface", "", "")))
+    else:
+        # the backdrop content (an opaque rect of the blend container), then the mix-blend picture over it
+        baddr = t.push_gpu_cache([tuple(float(v) / 255.0 for v in backdrop) + (1.0,)])
+        bh = t.add_prim_header((0.0, 0.0, 100.0, 100.0), (-1e9, -1e9, 1e9, 1e9), 1, baddr, 0, pic, (65535, 0, 0, 0))
+        ops.append(Batch(abi.KIND_BRUSH_SOLID, brush_instance(bh, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
+                         blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS))
+        textures["backdrop"] = TextureDesc(abi.FMT_RGBA8, 64, 64, data=uniform(backdrop, 1.0), filter=abi.LINEAR)
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 2, spec, 0, pic, (int(param), source(), source(), 0))
+        ops.append(Batch(abi.KIND_BRUSH_MIX_BLEND, brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
+                         blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS, color=("backdrop", "surface", "")))
+    return Frame(t.arrays(), textures, [[Target("target", ops=ops)]])
+
+
 def mix_blend_frame(width=640, height=400, seed=1, fractional=False, rotate=None):
     """Brush(MixBlend) batch (batch.rs:1931-2001): one picture per non-separable /
     separable mix-blend-mode handled in the shader (multiply, overlay, darken,
