@@ -84,6 +84,9 @@ CASES = [
      False),
     ("reftest_border_overlapping", "reftest_border_overlapping_frame", dict()),
     ("reftest_border_no_bogus_line", "reftest_border_no_bogus_line_frame", dict()),
+    ("reftest_border_radii", "reftest_border_frame", dict(name="border-radii")),
+    ("reftest_border_clamp_corner_radius", "reftest_border_frame", dict(name="border-clamp-corner-radius")),
+    ("reftest_clip_inverted_ellipse", "reftest_clip_inverted_ellipse_frame", dict()),
     # wrench/reftests/split/near-plane.yaml (also checked against the reference's own PNG: 0 pixels differ)
     ("reftest_split_near_plane", "reftest_split_near_plane_frame", dict(), False),
     ("reftest_inset_no_blur_radius", "reftest_box_shadow_frame", dict(which="inset-no-blur-radius")),

@@ -146,6 +146,38 @@ def test_border_no_bogus_line_reftest_against_reference_png():
     assert d.max() <= 1 and int((d > 0).sum()) <= 8, (int(d.max()), int((d > 0).sum()))
 
 
+@pytest.mark.parametrize("name,png", [("border-radii", "border/border-radii.png"),
+                                      ("border-clamp-corner-radius", "border/border-clamp-corner-radius.png")])
+def test_border_reftests_against_reference_png(name, png):
+    """wrench/reftests/border/{border-radii,border-clamp-corner-radius}.yaml against the reference's images: solid
+    rounded borders through the frame builder's segment decomposition (cs_border_solid corner and edge tasks in the
+    texture cache, Brush(Image) per segment), per-corner radii and radii scaled to fit.  Measured: 0 pixels differ."""
+    path = "/root/reference/wrench/reftests/" + png
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    (w, h), _, (max_diff, max_px) = scenes.BORDER_REFTESTS[name]
+    assert ref.shape[:2] == (h, w)
+    f = scenes.reftest_border_frame(name)
+    out = render(OracleDevice, f, ["target"])["target"].reshape(h, w, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref).max(axis=2)
+    assert d.max() <= max_diff and int((d > 0).sum()) <= max_px, (int(d.max()), int((d > 0).sum()))
+
+
+def test_clip_inverted_ellipse_reftest_against_reference_png():
+    """wrench/reftests/clip/inverted-ellipse.yaml == inverted-ellipse.png (exact): an elliptical complex clip whose
+    corner-size ratio is the inverse of the primitive's.  Measured: 0 pixels differ."""
+    path = "/root/reference/wrench/reftests/clip/inverted-ellipse.png"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_clip_inverted_ellipse_frame()
+    out = render(OracleDevice, f, ["target"])["target"].reshape(236, 319, 4)[..., [2, 1, 0, 3]].astype(int)
+    assert np.array_equal(out, ref), int((np.abs(out - ref).max(axis=2) > 0).sum())
+
+
 def test_split_near_plane_reftest_against_reference_png():
     """wrench/reftests/split/near-plane.yaml == near-plane.png (fuzzy(1,20); fuzzy-if(platform(swgl),128,39)): one
     plane-split polygon crossing the near plane, drawn by ps_split_composite from the picture's surface — the

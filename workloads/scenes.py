@@ -2131,6 +2131,122 @@ def reftest_border_no_bogus_line_frame():
     return Frame(t.arrays(), textures, [p0, p1])
 
 
+def solid_border_frame(size, borders, cache=(512, 512)):
+    """Solid one-colour CSS borders as the frame builder draws them (border.rs:168-215 ensure_no_corner_overlap,
+    654-898 create_border_segments, 1044-1241 corner / edge segments and their cache keys in app units, 1245-1297
+    build_border_instances): per border four corner tasks (cs_border_solid, the adjacent corners' clips kept only
+    where their radii reach into the task) and up to four 8-pixel edge tasks in the texture cache, then one Brush(Image)
+    instance per segment (SEGMENT_RELATIVE | SEGMENT_TEXEL_RECT corners, SEGMENT_RELATIVE | SEGMENT_REPEAT_X/Y edges),
+    premultiplied over the white page.  borders = [(rect, width, (tl, tr, br, bl) radii as (rx, ry), rgba)]."""
+    from webrender_b200 import gpu_types as G
+    f32 = np.float32
+    W, H = size
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    pack = _ShelfPacker(cache[0], cache[1])
+    inst, draws = [], []
+    au = lambda v: float(f32(round(float(v) * 60.0) / 60.0))  # noqa: E731  (LayoutSizeAu round trip)
+    for bi, (rect, width, radii, rgba) in enumerate(borders):
+        bw, bh = f32(rect[2] - rect[0]), f32(rect[3] - rect[1])
+        r = [[f32(v[0]), f32(v[1])] for v in radii]  # tl, tr, br, bl
+        ratio = f32(1.0)
+        for a_, b_, ext, k in ((0, 1, bw, 0), (3, 2, bw, 0), (0, 3, bh, 1), (1, 2, bh, 1)):
+            sm = f32(r[a_][k] + r[b_][k])
+            if ext > 0 and ext < sm:
+                ratio = min(ratio, f32(ext / sm))
+        if ratio < 1.0:
+            r = [[f32(v[0] * ratio), f32(v[1] * ratio)] for v in r]
+        r = [(au(v[0]), au(v[1])) for v in r]
+        w = float(width)
+        bw, bh = float(bw), float(bh)
+        sz = [(max(v[0], w), max(v[1], w)) for v in r]  # local sizes tl, tr, br, bl
+        tl, tr, br, bl = sz
+        col = tuple(float(f32(c * rgba[3])) for c in rgba[:3]) + (float(rgba[3]),)
+        segs = []  # (segment rect rel. to the border, texel rect, brush flags, task rect in the cache)
+
+        def corner(seg, img, h_out, h_rad, h_keep, h_dflt, v_out, v_rad, v_keep, v_dflt, radius):
+            cw, ch = img[2] - img[0], img[3] - img[1]
+            tw, th = int(np.ceil(cw)), int(np.ceil(ch))
+            at = pack.place(tw, th)
+            ho, hr = (h_out, h_rad) if h_keep else (h_dflt, (0.0, 0.0))
+            vo, vr = (v_out, v_rad) if v_keep else (v_dflt, (0.0, 0.0))
+            cp = (round(ho[0] - img[0]), round(ho[1] - img[1]), float(np.ceil(hr[0])), float(np.ceil(hr[1])),
+                  round(vo[0] - img[0]), round(vo[1] - img[1]), float(np.ceil(vr[0])), float(np.ceil(vr[1])))
+            inst.append(G.border_instance(task_origin=(float(at[0]), float(at[1])), local_rect=(0.0, 0.0, float(tw), float(th)),
+                                          color0=col, color1=col, segment=seg, style0=G.BORDER_STYLE_SOLID,
+                                          style1=G.BORDER_STYLE_SOLID, do_aa=True, widths=(float(np.ceil(w)), float(np.ceil(w))),
+                                          radius=(float(np.ceil(radius[0])), float(np.ceil(radius[1]))),
+                                          clip_params=tuple(float(v) for v in cp)))
+            segs.append((img, (0.0, 0.0, 1.0, 1.0), 2 | 512, (float(at[0]), float(at[1]), float(at[0] + tw), float(at[1] + th))))
+
+        def edge(seg, img, vertical):
+            if img[2] - img[0] <= 0.0 or img[3] - img[1] <= 0.0:
+                return
+            size = (w, 8.0) if vertical else (8.0, w)
+            tw, th = int(np.ceil(size[0])), int(np.ceil(size[1]))
+            at = pack.place(tw, th)
+            inst.append(G.border_instance(task_origin=(float(at[0]), float(at[1])), local_rect=(0.0, 0.0, float(tw), float(th)),
+                                          color0=col, color1=col, segment=seg, style0=G.BORDER_STYLE_SOLID,
+                                          style1=G.BORDER_STYLE_SOLID, do_aa=True, widths=(float(tw), float(th)), radius=(0.0, 0.0)))
+            segs.append((img, (0.0, 0.0, size[0], size[1]), 2 | (8 if vertical else 4),
+                         (float(at[0]), float(at[1]), float(at[0] + tw), float(at[1] + th))))
+        edge(G.SEGMENT_LEFT, (0.0, tl[1], w, bh - bl[1]), True)
+        edge(G.SEGMENT_TOP, (tl[0], 0.0, bw - tr[0], w), False)
+        edge(G.SEGMENT_RIGHT, (bw - w, tr[1], bw, bh - br[1]), True)
+        edge(G.SEGMENT_BOTTOM, (bl[0], bh - w, bw - br[0], bh), False)
+        i_tl, i_tr = (0.0, 0.0, tl[0], tl[1]), (bw - tr[0], 0.0, bw, tr[1])
+        i_br, i_bl = (bw - br[0], bh - br[1], bw, bh), (0.0, bh - bl[1], bl[0], bh)
+        corner(G.SEGMENT_TOP_LEFT, i_tl, (bw, 0.0), r[1], bw - r[1][0] < i_tl[2], (i_tl[2], i_tl[1]),
+               (0.0, bh), r[3], bh - r[3][1] < i_tl[3], (i_tl[0], i_tl[3]), r[0])
+        corner(G.SEGMENT_TOP_RIGHT, i_tr, (0.0, 0.0), r[0], 0.0 + r[0][0] > i_tr[0], (i_tr[0], i_tr[1]),
+               (bw, bh), r[2], bh - r[2][1] < i_tr[3], (i_tr[2], i_tr[3]), r[1])
+        corner(G.SEGMENT_BOTTOM_RIGHT, i_br, (0.0, bh), r[3], 0.0 + r[3][0] > i_br[0], (i_br[0], i_br[3]),
+               (bw, 0.0), r[1], 0.0 + r[1][1] > i_br[1], (i_br[2], i_br[1]), r[2])
+        corner(G.SEGMENT_BOTTOM_LEFT, i_bl, (bw, bh), r[2], bw - r[2][0] < i_bl[2], (i_bl[2], i_bl[3]),
+               (0.0, 0.0), r[0], 0.0 + r[0][1] > i_bl[1], (i_bl[0], i_bl[1]), r[3])
+        blocks = [(1.0, 1.0, 1.0, 1.0), (0.0, 0.0, 0.0, 0.0), (bw, bh, 0.0, 0.0)]
+        for srect, texel, _, _ in segs:
+            blocks += [tuple(float(v) for v in srect), texel]
+        addr = t.push_gpu_cache(blocks)
+        hdr = t.add_prim_header(tuple(float(v) for v in rect), (-1e9, -1e9, 1e9, 1e9), bi + 1, addr, 0, pic,
+                                (4 | (1 << 16), 0, 65535, 0))
+        for i, (_, _, flags, uv) in enumerate(segs):
+            res = t.push_gpu_cache([uv, (0.0, 0.0, 0.0, 0.0)])
+            draws.append(G.brush_instance(hdr, G.CLIP_TASK_EMPTY, i, 0, flags, res))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H),
+                "cache": TextureDesc(abi.FMT_RGBA8, cache[0], cache[1], filter=abi.LINEAR)}
+    p0 = [Target("cache", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)),
+                               Batch(abi.KIND_BORDER_SOLID, np.stack(inst), blend=abi.BLEND_PREMULTIPLIED_ALPHA)])]
+    p1 = [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                                Batch(abi.KIND_BRUSH_IMAGE, np.stack(draws), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                      features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D, color=("cache", "", ""))])]
+    return Frame(t.arrays(), textures, [p0, p1])
+
+
+BORDER_REFTESTS = {
+    # wrench/reftests/border/<name>.yaml against its reference image: (image size, borders, allowed (max diff, pixels))
+    # border-radii.yaml == border-radii.png, fuzzy(1,10): per-corner radii 16 / 8 on a width-10 border
+    "border-radii": ((113, 119), [((10, 10, 100, 100), 10.0, ((16, 16), (8, 8), (16, 16), (8, 8)), (0.0, 0.0, 1.0, 1.0))], (1, 10)),
+    # border-clamp-corner-radius.yaml == border-clamp-corner-radius.png: radii of 180 on 200-pixel boxes are scaled to fit
+    "border-clamp-corner-radius": ((430, 230), [((0, 0, 200, 200), 10.0, ((180, 180),) * 4, (0.0, 0.0, 1.0, 1.0)),
+                                                ((200, 0, 400, 200), 10.0, ((180, 180), (0, 0), (180, 180), (0, 0)),
+                                                 (0.0, 0.0, 1.0, 1.0))], (0, 0)),
+}
+
+
+def reftest_clip_inverted_ellipse_frame():
+    """wrench/reftests/clip/inverted-ellipse.yaml (== inverted-ellipse.png): a 225x150 red rect under a complex clip
+    whose corner radii (112.5, 75) make it an ellipse "where the ratio of the corner size is inverted from the ratio of
+    the primitive size".  Indirect path like config A; reference image 319x236."""
+    spec = [((50, 50, 275, 200), (1.0, 0.0, 0.0, 1.0), ((112.5, 75.0),) * 4, 0)]
+    return rounded_rects_frame(width=319, height=236, spec=spec, surface=(256, 256))
+
+
+def reftest_border_frame(name):
+    size, borders, _ = BORDER_REFTESTS[name]
+    return solid_border_frame(size, borders)
+
+
 def reftest_split_near_plane_frame():
     """wrench/reftests/split/near-plane.yaml (== near-plane.png, fuzzy(1,20); fuzzy-if(platform(swgl),128,39)): a
     600x600 rect of (255,0,0,0.5) in a stacking context rotated by rotate-x(-60) about its centre, inside a
