@@ -92,6 +92,7 @@ CASES = [
     ("reftest_inset_no_blur_radius", "reftest_box_shadow_frame", dict(which="inset-no-blur-radius")),
     ("reftest_box_shadow_spread", "reftest_box_shadow_frame", dict(which="box-shadow-spread")),
     ("reftest_boxshadow_spread_only", "reftest_box_shadow_frame", dict(which="boxshadow-spread-only")),
+    ("reftest_box_shadow_suite_no_blur", "reftest_box_shadow_frame", dict(which="suite-no-blur")),
     ("reftest_filter_small_blur_radius", "reftest_filter_blur_frame", dict()),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),

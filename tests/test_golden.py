@@ -98,6 +98,8 @@ def test_clip_reftests_against_reference_png(which, png, max_diff, max_px):
     ("box-shadow-spread", "boxshadow/box-shadow-spread.png", 9, 34),           # fuzzy-if(platform(swgl),9,34); measured 0
     ("boxshadow-spread-only", "boxshadow/boxshadow-spread-only-ref.png", 1, 10),  # GL-rendered, exact on linux/mac GL;
                                                                                  # SWGL rounding: 1 LSB on 10 px
+    ("suite-no-blur", "boxshadow/box-shadow-suite-no-blur.png", 1, 8),  # 16 shadows (outset / inset, radius 0 / 32, offsets,
+                                                                       # spread); GL-rendered: 1 LSB on 8 px of 705 366
 ])
 def test_box_shadow_reftests_against_reference_png(which, png, max_diff, max_px):
     """wrench/reftests/boxshadow/*: box shadows WITHOUT blur take the frame builder's rectangle path

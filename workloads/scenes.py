@@ -2038,6 +2038,12 @@ def reftest_clip_frame(which="clip-mode"):
 
 
 def reftest_box_shadow_frame(which="inset-no-blur-radius"):
+    if which == "suite-no-blur":
+        return reftest_box_shadow_suite_no_blur_frame()
+    return _reftest_box_shadow_frame(which)
+
+
+def _reftest_box_shadow_frame(which="inset-no-blur-radius"):
     """wrench/reftests/boxshadow/inset-no-blur-radius.yaml: an INSET box shadow with blur radius 0 takes the frame
     builder's no-blur path (box_shadow.rs:341-401): a Rectangle primitive = the box (10,10)-(90,90) in the shadow
     colour under two rounded clips — Clip to the box (radius 10) and ClipOut of the shadow rect = the box moved by the
@@ -2281,6 +2287,32 @@ def reftest_split_near_plane_frame():
                                 Batch(abi.KIND_SPLIT_COMPOSITE, poly[None, :], blend=abi.BLEND_PREMULTIPLIED_ALPHA,
                                       color=("surface", "", ""))])]
     return Frame(t.arrays(), textures, [p0, p1])
+
+
+def reftest_box_shadow_suite_no_blur_frame():
+    """wrench/reftests/boxshadow/box-shadow-suite-no-blur.yaml (== box-shadow-suite-no-blur.png): four rows of five box
+    shadows without blur — outset, outset with border-radius 32, inset, inset with radius 32 — each with offsets (20,0),
+    (0,-40), spread 30, and spread 30 + offset (50,-10); the first of a row (no offset, no spread) is rejected as
+    invisible.  The frame builder's no-blur path (box_shadow.rs:331-401): outset = the shadow rect (box moved by the
+    offset, inflated by the spread, radius r + spread when r > 0) under ClipOut of the box; inset = the box under
+    ClipOut of the shadow rect (box moved, shrunk by the spread, radius max(r - spread, 0)).  Reference image 894x789."""
+    red, green = (1.0, 0.0, 0.0, 1.0), (0.0, 1.0, 0.0, 1.0)
+    spec = []
+    cols = [(0, 0, 0), (20, 0, 0), (0, -40, 0), (0, 0, 30), (50, -10, 30)]
+    for y, inset, r, col in ((50, False, 0, red), (250, False, 32, green), (450, True, 0, red), (650, True, 32, red)):
+        for i, (ox, oy, sp) in enumerate(cols):
+            if ox == 0 and oy == 0 and sp == 0:
+                continue
+            x = 50 + 150 * i
+            box = (x, y, x + 100, y + 100)
+            if not inset:
+                sh = (box[0] + ox - sp, box[1] + oy - sp, box[2] + ox + sp, box[3] + oy + sp)
+                spec.append((sh, col, float(r + sp if r > 0 else 0), 0, [(tuple(float(v) for v in box), float(r), 1)]))
+            else:
+                sh = (box[0] + ox + sp, box[1] + oy + sp, box[2] + ox - sp, box[3] + oy - sp)
+                extra = [(tuple(float(v) for v in sh), float(max(r - sp, 0) if r > 0 else 0), 1)] if sh[2] > sh[0] and sh[3] > sh[1] else []
+                spec.append((box, col, float(r), 0, extra))
+    return rounded_rects_frame(width=894, height=789, spec=spec, surface=(1024, 1024))
 
 
 def reftest_filter_blur_frame():
