@@ -26,7 +26,7 @@ done
 prof() {  # name workload kernel-regex skip
   timeout 300 ncu --set full --import-source on --clock-control none -k regex:$3 -s $4 -c 1 -o /tmp/q_prof_$1 python bench.py --workload $2 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/q_ncu_$1.log 2>&1
   ncu -i /tmp/q_prof_$1.ncu-rep --page raw --csv > gpurun_out/q_prof_$1.raw.csv 2>/dev/null
-  ncu -i /tmp/q_prof_$1.ncu-rep --page source --print-source cuda --csv 2>/dev/null | python tools/src_hot.py > gpurun_out/q_prof_$1.lines.txt
+  ncu -i /tmp/q_prof_$1.ncu-rep --page source --print-source cuda --csv 2>/dev/null | gzip -9 > gpurun_out/q_prof_$1.source.csv.gz
 }
 prof glyphs text wr_raster_glyphs 1
 prof setup_text text wr_setup_multi 1
