@@ -65,6 +65,9 @@ CASES = [
                                                      glyph_transform=(-33.0, 1.3, 0.9), clip_runs=True)),
     ("reftest_premultiplied_radial", "reftest_cached_gradient_frame", dict(which="premultiplied-radial")),
     ("reftest_conic_center", "reftest_cached_gradient_frame", dict(which="conic-center")),
+    ("reftest_radial_circle", "reftest_cached_gradient_frame2", dict(name="radial-circle")),
+    ("reftest_radial_ellipse", "reftest_cached_gradient_frame2", dict(name="radial-ellipse")),
+    ("reftest_conic_simple", "reftest_cached_gradient_frame2", dict(name="conic-simple")),
     ("composite_yuv_planar_rec709", "yuv_composite_frame", dict(fmt="planar", color_space=2, seed=1)),
     ("composite_yuv_nv12_rec601_full", "yuv_composite_frame", dict(fmt="nv12", color_space=1, seed=2, fractional=True)),
     ("composite_yuv_interleaved_rec2020", "yuv_composite_frame", dict(fmt="interleaved", color_space=4, seed=3)),

@@ -1265,6 +1265,53 @@ def reftest_cached_gradient_frame(which="premultiplied-radial"):
     return Frame(t.arrays(), textures, [[p0], [p1]])
 
 
+CACHED_GRADIENT_REFTESTS = {
+    # wrench/reftests/gradient/<name>.yaml against its reference image, drawn as a cached gradient task + Brush(Image)
+    # like reftest_cached_gradient_frame: (image size, bounds x y w h, kind, centre, radius (rx, ry) | angle, stops with
+    # 0-255 colours + alpha, allowed (max diff, pixels))
+    "radial-circle": ((400, 400), (50, 50, 300, 300), "radial", (150, 150), (200, 200),
+                      [(0.0, (255, 0, 0, 1.0)), (1.0, (0, 0, 255, 1.0))], (1, 80000)),
+    "radial-ellipse": ((400, 400), (50, 50, 300, 300), "radial", (150, 150), (100, 200),
+                       [(0.0, (255, 0, 0, 1.0)), (1.0, (0, 0, 255, 1.0))], (1, 80000)),
+    "conic-simple": ((400, 400), (50, 50, 300, 300), "conic", (150, 150), 0.0,
+                     [(0.0, (255, 0, 0, 1.0)), (1.0, (255, 255, 0, 1.0))], (1, 300)),
+}
+
+
+def reftest_cached_gradient_frame2(name):
+    """One of CACHED_GRADIENT_REFTESTS: the gradient as a cached render task of its own size (cs_radial_gradient /
+    cs_conic_gradient; prim_store/gradient/{radial,conic}.rs: start radius 0, end radius rx, ratio_xy = rx / ry), then
+    Brush(Image) 1:1 onto the white page, premultiplied blending."""
+    from webrender_b200 import gpu_types as G
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
+    (W, H), (bx, by, bw, bh), kind, center, param, stops, _ = CACHED_GRADIENT_REFTESTS[name]
+    t = FrameTables()
+    task_rect = (0.0, 0.0, float(bw), float(bh))
+    pm = [(o, (c[0] / 255.0 * c[3], c[1] / 255.0 * c[3], c[2] / 255.0 * c[3], c[3])) for o, c in stops]
+    lut = t.push_gpu_buffer_f(list(G.build_gradient_table(pm)))
+    if kind == "radial":
+        rx, ry = param
+        inst = G.radial_gradient_instance(task_rect, (float(center[0]), float(center[1])), (1.0, 1.0), 0.0, float(rx),
+                                          float(rx) / float(ry), 0, lut)
+        k = abi.KIND_RADIAL_GRADIENT
+    else:
+        inst = G.conic_gradient_instance(task_rect, (float(center[0]), float(center[1])), (1.0, 1.0), 0.0, 1.0, float(param), 0, lut)
+        k = abi.KIND_CONIC_GRADIENT
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    addr = t.push_gpu_cache([(1.0, 1.0, 1.0, 1.0), (1.0, 1.0, 1.0, 1.0), (float(bw), float(bh), 0.0, 0.0)])
+    res = t.push_gpu_cache([task_rect, (0.0, 0.0, 0.0, 0.0)])
+    hdr = t.add_prim_header((float(bx), float(by), float(bx + bw), float(by + bh)), (-1e9, -1e9, 1e9, 1e9), 1, addr, 0, pic,
+                            (4 | (1 << 16), 0, 65535, 0))
+    img = np.stack([brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, res)])
+    textures = {"cache": TextureDesc(abi.FMT_RGBA8, 512, 512, filter=abi.LINEAR),
+                "target": TextureDesc(abi.FMT_RGBA8, W, H)}
+    p0 = Target("cache", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)), Batch(k, np.stack([inst]), blend=abi.BLEND_NONE)])
+    p1 = Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                               Batch(abi.KIND_BRUSH_IMAGE, img, blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                     features=abi.FEAT_TEXTURE_2D | abi.FEAT_ALPHA_PASS, color=("cache", "", ""))])
+    return Frame(t.arrays(), textures, [[p0], [p1]])
+
+
 def shadow_mask_texture(size=256, seed=5):
     """A seeded stand-in for the blurred box-shadow masks cs_blur produces
     (render_task.rs BlurTask): soft-edged blobs plus a little noise, R8."""
