@@ -19,9 +19,9 @@ INDEX = json.load(open(os.path.join(HERE, "index.json")))
 # cases whose CUDA result may differ from the reference by <= 1 LSB on a few
 # pixels for a documented reason: hue-rotate's cosf/sinf; conic gradient: atan2f
 CUDA_LSB_TOLERANT = {"brush_blend_filters", "cs_conic_gradient",  # conic: atan2f
-                     # the three gradient reftest goldens were added after the round's last GPU call; conic-simple for
+                     # three gradient reftest goldens and the line decorations were added after the round's last GPU call; conic-simple for
                      # atan2f, the radial pair until a GPU run has confirmed them exact like cs_radial_gradient
-                     "reftest_conic_simple", "reftest_radial_circle", "reftest_radial_ellipse"}
+                     "reftest_conic_simple", "reftest_radial_circle", "reftest_radial_ellipse", "reftest_line_decorations"}
 
 
 def _check(device_cls, name, tolerant=False):
@@ -338,6 +338,22 @@ def test_more_cached_gradient_reftests_against_reference_png(name, png):
     out = render(OracleDevice, f, ["target"])["target"].reshape(h, w, 4)[..., [2, 1, 0, 3]].astype(int)
     d = np.abs(out - ref).max(axis=2)
     assert d.max() <= max_diff and int((d > 0).sum()) <= min(max_px, 20), (int(d.max()), int((d > 0).sum()))
+
+
+def test_line_decorations_reftest_against_reference_png():
+    """The first eight items of wrench/reftests/text/decorations-suite.yaml against the matching region (rows 0-99,
+    columns 0-217) of decorations-suite.png: solid, dashed, dotted and wavy lines at two thicknesses — cs_line_decoration
+    tasks repeated along the line by Brush(Image) REPETITION.  The reftest allows SWGL 3 on 13 540 pixels over the whole
+    suite; measured on this region: 0 pixels differ (2 001 of its 21 800 pixels are drawn)."""
+    path = "/root/reference/wrench/reftests/text/decorations-suite.png"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_line_decorations_frame()
+    out = render(OracleDevice, f, ["target"])["target"].reshape(439, 495, 4)[..., [2, 1, 0, 3]].astype(int)
+    assert np.array_equal(out[:100, :218], ref[:100, :218])
+    assert int((ref[:100, :218, :3] != 255).any(axis=2).sum()) == 2001
 
 
 def test_yuv_reftest_against_reference_png():

@@ -1008,6 +1008,62 @@ def line_decoration_frame(width=512, height=256, n_tasks=24, seed=1):
     return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
 
 
+def reftest_line_decorations_frame():
+    """The first eight items of wrench/reftests/text/decorations-suite.yaml (rows 0-99 of decorations-suite.png; the
+    reftest allows SWGL 3 on 13 540 pixels over the whole suite): horizontal lines 200 long, 1 / 2 / 3 / 6 thick —
+    solid (black), dashed (blue), dotted (green), wavy (red).  Draw list (scene_building.rs add_line, prim_store/
+    line_dec.rs:195-241 get_line_decoration_size, prepare.rs:345-425, batch.rs:1338-1420): a solid line is a
+    Brush(Solid) rect; the others are a cs_line_decoration task of ceil(size) — dashed (2 * min(3h, 64), 4), dotted
+    (2h, h), wavy (2 * (h - t + max(2(t - 1), 1)), h) — in the texture cache, repeated along the line by Brush(Image)
+    REPETITION with the stretch size = the task's local size and the line colour, premultiplied blending."""
+    from webrender_b200 import gpu_types as G
+    from webrender_b200.gpu_types import brush_instance, CLIP_TASK_EMPTY
+    W, H = 495, 439
+    black, blue, green, red = (0.0, 0.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0), (0.0, 1.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0)
+    lines = [(10, 10, 210, 1, 0, black, 0.0), (20, 10, 210, 1, 2, blue, 0.0), (30, 10, 210, 1, 1, green, 0.0),
+             (40, 10, 210, 3, 3, red, 1.0), (50, 10, 210, 2, 0, black, 0.0), (65, 10, 210, 2, 2, blue, 0.0),
+             (80, 10, 207, 2, 1, green, 0.0), (95, 10, 210, 6, 3, red, 2.0)]   # style: 0 solid, 1 dotted, 2 dashed, 3 wavy
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    pack = _ShelfPacker(256, 64)
+    tasks, solids, images = [], [], []
+    for i, (base, x0, x1, h, style, col, thick) in enumerate(lines):
+        rect = (float(x0), float(base), float(x1), float(base + h))
+        if style == 0:
+            addr = t.push_gpu_cache([col])
+            hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), i + 1, addr, 0, pic, (65535, 0, 0, 0))
+            solids.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+            continue
+        hf = float(h)
+        if style == 2:
+            size = (2.0 * max(min(3.0 * hf, 64.0), 1.0), 4.0)
+        elif style == 1:
+            d = max(min(hf, 64.0), 1.0)
+            size = (2.0 * d, d)
+        else:
+            lt = max(thick, 1.0)
+            size = (2.0 * ((hf - lt) + max((lt - 1.0) * 2.0, 1.0)), hf)
+        tw, th = int(np.ceil(size[0])), int(np.ceil(size[1]))
+        at = pack.place(tw, th)
+        trect = (float(at[0]), float(at[1]), float(at[0] + tw), float(at[1] + th))
+        tasks.append(G.line_decoration_instance(trect, size, thick, style, 0.0))
+        addr = t.push_gpu_cache([col, (1.0, 1.0, 1.0, 1.0), (size[0], size[1], 0.0, 0.0)])
+        res = t.push_gpu_cache([trect, (0.0, 0.0, 0.0, 0.0)])
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), i + 1, addr, 0, pic, (4 | (1 << 16), 0, 65535, 0))
+        images.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, res))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H),
+                "cache": TextureDesc(abi.FMT_RGBA8, 256, 64, filter=abi.LINEAR)}
+    p0 = [Target("cache", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)),
+                               Batch(abi.KIND_LINE_DECORATION, np.stack(tasks), blend=abi.BLEND_PREMULTIPLIED_ALPHA)])]
+    p1 = [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                                Batch(abi.KIND_BRUSH_SOLID, np.stack(solids), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                      features=abi.FEAT_ALPHA_PASS),
+                                Batch(abi.KIND_BRUSH_IMAGE, np.stack(images), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                      features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D | abi.FEAT_REPETITION | abi.FEAT_ANTIALIASING,
+                                      color=("cache", "", ""))])]
+    return Frame(t.arrays(), textures, [p0, p1])
+
+
 def _ellipse_point_tangent(rx, ry, theta):
     c, s = float(np.cos(theta)), float(np.sin(theta))
     return (rx * c, ry * s), (-rx * s, ry * c)
