@@ -1008,6 +1008,56 @@ def line_decoration_frame(width=512, height=256, n_tasks=24, seed=1):
     return Frame(FrameTables().arrays(), textures, [[Target("target", ops=ops)]])
 
 
+def wrench_checkerboard(border, tile, count):
+    """wrench's `checkerboard(border, tile size, tile count)` image (yaml_frame_reader.rs:195-240, BlackGrey kind):
+    BGRA bytes, a `border`-pixel frame of (0, 0, 255, 255) around 0xff / 0x7f squares."""
+    n = 2 * border + tile * count
+    yy, xx = np.mgrid[0:n, 0:n]
+    inner = (xx >= border) & (xx < n - border) & (yy >= border) & (yy < n - border)
+    xon = ((xx - border) % (2 * tile)) < tile
+    yon = ((yy - border) % (2 * tile)) < tile
+    v = np.where(xon ^ yon, 0xFF, 0x7F).astype(np.uint8)
+    img = np.zeros((n, n, 4), dtype=np.uint8)
+    img[..., 0] = np.where(inner, v, 0)
+    img[..., 1] = np.where(inner, v, 0)
+    img[..., 2] = np.where(inner, v, 0xFF)
+    img[..., 3] = 0xFF
+    return img.reshape(n, n * 4)
+
+
+def reftest_image_segments_frame():
+    """wrench/reftests/image/segments.yaml (== segments.png, fuzzy-if(platform(swgl),1,20)): a 260x260 checkerboard image
+    drawn 1:1 twice — at (10,10) under a rounded clip of radius 32, at (10,290) unclipped.  The frame builder segments
+    the clipped image and masks only its corners; the pixels are those of the whole image under the clip's coverage
+    mask, which is how it is drawn here: cs_clip_rectangle into an R8 mask task, then Brush(Image) alpha pass with the
+    mask; the second image is an opaque Brush(Image).  Reference image 290x583."""
+    from webrender_b200.gpu_types import brush_instance, clip_rect_instance, CLIP_TASK_EMPTY
+    W, H = 290, 583
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    rect = (10.0, 10.0, 270.0, 270.0)
+    mask_task = t.add_render_task((0.0, 0.0, 260.0, 260.0), 1.0, (10.0, 10.0))
+    clip = clip_rect_instance((0.0, 0.0, 260.0, 260.0), (0.0, 0.0), (10.0, 10.0), 1.0, 0, 0, (rect[0], rect[1]), rect, 0.0,
+                              ((32.0, 32.0),) * 4)
+    uv = t.push_gpu_cache([(0.0, 0.0, 260.0, 260.0), (0.0, 0.0, 0.0, 0.0)])
+    blocks = [(1.0, 1.0, 1.0, 1.0), (0.0, 0.0, 0.0, 0.0), (-1.0, -1.0, 0.0, 0.0)]
+    h1 = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 2, t.push_gpu_cache(blocks), 0, pic, (4 | (1 << 16), 0, 65535, 0))
+    h2 = t.add_prim_header((10.0, 290.0, 270.0, 550.0), (-1e9, -1e9, 1e9, 1e9), 1, t.push_gpu_cache(blocks), 0, pic,
+                           (4 | (1 << 16), 0, 65535, 0))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H),
+                "mask": TextureDesc(abi.FMT_R8, 512, 512),
+                "image": TextureDesc(abi.FMT_RGBA8, 260, 260, data=wrench_checkerboard(2, 16, 16), filter=abi.LINEAR)}
+    p0 = [Target("mask", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                              Batch(abi.KIND_CLIP_RECTANGLE, clip[None, :], blend=abi.BLEND_NONE, features=abi.FEAT_FAST_PATH)])]
+    p1 = [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                                Batch(abi.KIND_BRUSH_IMAGE, brush_instance(h2, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, uv)[None, :],
+                                      blend=abi.BLEND_NONE, features=abi.FEAT_TEXTURE_2D, color=("image", "", "")),
+                                Batch(abi.KIND_BRUSH_IMAGE, brush_instance(h1, mask_task, 0xFFFF, 0, 0, uv)[None, :],
+                                      blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS | abi.FEAT_TEXTURE_2D,
+                                      color=("image", "", ""), clip_mask="mask")])]
+    return Frame(t.arrays(), textures, [p0, p1])
+
+
 def reftest_line_decorations_frame():
     """The first eight items of wrench/reftests/text/decorations-suite.yaml (rows 0-99 of decorations-suite.png; the
     reftest allows SWGL 3 on 13 540 pixels over the whole suite): horizontal lines 200 long, 1 / 2 / 3 / 6 thick —
