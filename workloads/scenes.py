@@ -1994,6 +1994,12 @@ PICTURE_REFTESTS = {
     # blend/darken.yaml, lighten.yaml (fuzzy-if(platform(swgl),1,10000)): per-channel min / max
     "darken": ((255, 255, 255), (0, 0, 100, 100), "mix", (30, 20, 10, 1.0), 4, (10, 20, 30), (10, 20, 10), (1, 10000)),
     "lighten": ((255, 255, 255), (0, 0, 100, 100), "mix", (30, 20, 10, 1.0), 5, (10, 20, 30), (30, 20, 30), (1, 10000)),
+    # the same four the way SWGL itself draws them: KHR_blend_equation_advanced on the picture's draw (blend.h advanced
+    # equations; parameter = wrcu_blend key)
+    "adv-multiply": ((255, 255, 255), (25, 25, 75, 75), "adv", (0, 255, 0, 1.0), abi.BLEND_ADV_MULTIPLY, (0, 255, 0), (0, 255, 0), (0, 0)),
+    "adv-difference": ((255, 255, 255), (0, 0, 100, 100), "adv", (0, 255, 0, 1.0), abi.BLEND_ADV_DIFFERENCE, (0, 255, 0), (0, 0, 0), (0, 0)),
+    "adv-darken": ((255, 255, 255), (0, 0, 100, 100), "adv", (30, 20, 10, 1.0), abi.BLEND_ADV_DARKEN, (10, 20, 30), (10, 20, 10), (1, 10000)),
+    "adv-lighten": ((255, 255, 255), (0, 0, 100, 100), "adv", (30, 20, 10, 1.0), abi.BLEND_ADV_LIGHTEN, (10, 20, 30), (30, 20, 30), (1, 10000)),
 }
 
 
@@ -2025,6 +2031,17 @@ def picture_reftest_frame(name, size=(140, 140)):
         hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 1, spec, 0, pic, (source(), int(param * 65536.0), 0, 0))
         ops.append(Batch(abi.KIND_BRUSH_OPACITY, brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
                          blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS, color=("surface", "", "")))
+    elif kind == "adv":
+        # the backdrop rect, then the picture's content drawn with the advanced blend equation
+        baddr = t.push_gpu_cache([tuple(float(v) / 255.0 for v in backdrop) + (1.0,)])
+        bh = t.add_prim_header((0.0, 0.0, 100.0, 100.0), (-1e9, -1e9, 1e9, 1e9), 1, baddr, 0, pic, (65535, 0, 0, 0))
+        ops.append(Batch(abi.KIND_BRUSH_SOLID, brush_instance(bh, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
+                         blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS))
+        a = float(src[3])
+        saddr = t.push_gpu_cache([tuple(float(v) / 255.0 * a for v in src[:3]) + (a,)])
+        sh = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 2, saddr, 0, pic, (65535, 0, 0, 0))
+        ops.append(Batch(abi.KIND_BRUSH_SOLID, brush_instance(sh, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
+                         blend=int(param), features=abi.FEAT_ALPHA_PASS))
     else:
         # the backdrop content (an opaque rect of the blend container), then the mix-blend picture over it
         baddr = t.push_gpu_cache([tuple(float(v) / 255.0 for v in backdrop) + (1.0,)])
