@@ -99,6 +99,7 @@ CASES = [
     ("reftest_filter_small_blur_radius", "reftest_filter_blur_frame", dict()),
     ("reftest_line_decorations", "reftest_line_decorations_frame", dict()),
     ("reftest_image_segments", "reftest_image_segments_frame", dict()),
+    ("reftest_linear_aligned_border_radius", "reftest_gradient_border_radius_frame", dict()),
     ("cs_line_decoration", "line_decoration_frame", dict(seed=2)),
     ("cs_border_solid", "border_frame", dict(kind=21, width=512, height=512, n_borders=3, seed=2)),
     ("cs_border_segment", "border_frame", dict(kind=22, width=768, height=512, n_borders=5, seed=3, scale=1.5)),

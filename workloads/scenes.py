@@ -1058,6 +1058,45 @@ def reftest_image_segments_frame():
     return Frame(t.arrays(), textures, [p0, p1])
 
 
+def reftest_gradient_border_radius_frame(repeat=False):
+    """wrench/reftests/gradient/linear-aligned-border-radius.yaml (== linear-aligned-border-radius.png on GL; `repeat`
+    sets the extend mode of repeat-border-radius.yaml's first row): three 100x100 vertical red -> yellow gradients under a rounded
+    clip of radius 32 — on the white page, on a blue and on a black 120x120 rect.  Brush(LinearGradient) in the alpha
+    pass with a cs_clip_rectangle mask each (the uncached brush path an `is_software` frame builder keeps).
+    Reference images 395x151."""
+    from webrender_b200.gpu_types import brush_instance, build_gradient_table, clip_rect_instance, CLIP_TASK_EMPTY
+    W, H = 395, 151
+    red, yellow = (1.0, 0.0, 0.0, 1.0), (1.0, 1.0, 0.0, 1.0)
+    t = FrameTables()
+    pic = t.add_render_task((0.0, 0.0, float(W), float(H)), 1.0, (0.0, 0.0))
+    lut = t.push_gpu_buffer_f(list(build_gradient_table([(0.0, red), (1.0, yellow)])))
+    solids, grads, clips = [], [], []
+    z = 1
+    for i, (x, bg) in enumerate(((20, None), (140, (0.0, 0.0, 1.0, 1.0)), (270, (0.0, 0.0, 0.0, 1.0)))):
+        if bg is not None:
+            addr = t.push_gpu_cache([bg])
+            hdr = t.add_prim_header((float(x - 10), 10.0, float(x + 110), 130.0), (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic, (65535, 0, 0, 0))
+            z += 1
+            solids.append(brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0))
+        rect = (float(x), 20.0, float(x + 100), 120.0)
+        mask_task = t.add_render_task((float(128 * i), 0.0, float(128 * i + 100), 100.0), 1.0, (rect[0], rect[1]))
+        clips.append(clip_rect_instance((0.0, 0.0, 100.0, 100.0), (float(128 * i), 0.0), (rect[0], rect[1]), 1.0, 0, 0,
+                                        (rect[0], rect[1]), rect, 0.0, ((32.0, 32.0),) * 4))
+        # gradient brush data: start / end points relative to the prim, extend mode, stretch size
+        addr = t.push_gpu_cache([(50.0, 0.0, 50.0, 100.0), (1.0 if repeat else 0.0, 100.0, 100.0, 0.0)])
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), z, addr, 0, pic, (lut, 0, 0, 0))
+        z += 1
+        grads.append(brush_instance(hdr, mask_task, 0xFFFF, 0, 0, 0))
+    textures = {"target": TextureDesc(abi.FMT_RGBA8, W, H), "mask": TextureDesc(abi.FMT_R8, 512, 128)}
+    p0 = [Target("mask", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                              Batch(abi.KIND_CLIP_RECTANGLE, np.stack(clips), blend=abi.BLEND_NONE, features=abi.FEAT_FAST_PATH)])]
+    p1 = [Target("target", ops=[Clear(color=(1.0, 1.0, 1.0, 1.0)),
+                                Batch(abi.KIND_BRUSH_SOLID, np.stack(solids), blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS),
+                                Batch(abi.KIND_BRUSH_LINEAR_GRADIENT, np.stack(grads), blend=abi.BLEND_PREMULTIPLIED_ALPHA,
+                                      features=abi.FEAT_ALPHA_PASS, clip_mask="mask")])]
+    return Frame(t.arrays(), textures, [p0, p1])
+
+
 def reftest_line_decorations_frame():
     """The first eight items of wrench/reftests/text/decorations-suite.yaml (rows 0-99 of decorations-suite.png; the
     reftest allows SWGL 3 on 13 540 pixels over the whole suite): horizontal lines 200 long, 1 / 2 / 3 / 6 thick —
