@@ -96,6 +96,7 @@ CASES = [
     ("reftest_box_shadow_spread", "reftest_box_shadow_frame", dict(which="box-shadow-spread")),
     ("reftest_boxshadow_spread_only", "reftest_box_shadow_frame", dict(which="boxshadow-spread-only")),
     ("reftest_box_shadow_suite_no_blur", "reftest_box_shadow_frame", dict(which="suite-no-blur")),
+    ("reftest_box_shadow_suite_composited", "reftest_box_shadow_suite_composited_frame", dict()),
     ("reftest_filter_small_blur_radius", "reftest_filter_blur_frame", dict()),
     ("reftest_line_decorations", "reftest_line_decorations_frame", dict()),
     ("reftest_image_segments", "reftest_image_segments_frame", dict()),

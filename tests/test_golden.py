@@ -23,6 +23,7 @@ CUDA_LSB_TOLERANT = {"brush_blend_filters", "cs_conic_gradient",  # conic: atan2
                      # atan2f, the radial pair until a GPU run has confirmed them exact like cs_radial_gradient
                      "reftest_conic_simple", "reftest_radial_circle", "reftest_radial_ellipse", "reftest_line_decorations",
                      "reftest_image_segments", "reftest_linear_aligned_border_radius"}
+# (reftest_box_shadow_suite_composited, also added late, is integer copies of an exact frame: not in the tolerant set)
 
 
 def _check(device_cls, name, tolerant=False):
@@ -355,6 +356,21 @@ def test_linear_aligned_border_radius_reftest_against_reference_png():
     out = render(OracleDevice, f, ["target"])["target"].reshape(151, 395, 4)[..., [2, 1, 0, 3]].astype(int)
     d = np.abs(out - ref).max(axis=2)
     assert d.max() <= 1 and int((d > 0).sum()) <= 240, (int(d.max()), int((d > 0).sum()))
+
+
+def test_box_shadow_suite_through_the_compositor_against_reference_png():
+    """The box-shadow suite drawn the way a page reaches the screen: into a picture-cache tile, then the tile list
+    composited into the framebuffer (composite FAST_PATH, the copy class on the GPU) — the framebuffer against
+    boxshadow/box-shadow-suite-no-blur.png: the same 1 LSB on 8 pixels as the direct draw."""
+    path = "/root/reference/wrench/reftests/boxshadow/box-shadow-suite-no-blur.png"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    Image = pytest.importorskip("PIL.Image")
+    ref = np.array(Image.open(path).convert("RGBA")).astype(int)
+    f = scenes.reftest_box_shadow_suite_composited_frame()
+    out = render(OracleDevice, f, ["fb"])["fb"].reshape(789, 894, 4)[..., [2, 1, 0, 3]].astype(int)
+    d = np.abs(out - ref).max(axis=2)
+    assert d.max() <= 1 and int((d > 0).sum()) <= 8, (int(d.max()), int((d > 0).sum()))
 
 
 def test_image_segments_reftest_against_reference_png():

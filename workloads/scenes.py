@@ -1097,6 +1097,29 @@ def reftest_gradient_border_radius_frame(repeat=False):
     return Frame(t.arrays(), textures, [p0, p1])
 
 
+def composited_through_tile(frame, tile=(1024, 1024)):
+    """A single-target frame drawn the way the compositor path draws a page: "target" becomes a picture-cache tile (a
+    power-of-two texture, same content, same render task) and an extra pass composites it into the framebuffer "fb" of
+    the page's size — clear, one opaque FAST_PATH tile instance clipped to the page (composite_simple / draw_tile_list,
+    renderer/mod.rs:3126-3484).  The tile maps 1:1, so it takes the copy class on the GPU (§4.7 of DESIGN.md)."""
+    from webrender_b200.gpu_types import composite_instance
+    d = frame.textures["target"]
+    W, H = d.width, d.height
+    textures = dict(frame.textures)
+    textures["target"] = TextureDesc(d.fmt, tile[0], tile[1], filter=abi.NEAREST)
+    textures["fb"] = TextureDesc(abi.FMT_RGBA8, W, H)
+    inst = composite_instance((0.0, 0.0, float(tile[0]), float(tile[1])), (0.0, 0.0, float(W), float(H)))
+    fb = Target("fb", ops=[Clear(color=(0.0, 0.0, 0.0, 0.0)),
+                           Batch(abi.KIND_COMPOSITE, inst[None, :], blend=abi.BLEND_NONE,
+                                 features=abi.FEAT_FAST_PATH | abi.FEAT_TEXTURE_2D, color=("target", "", ""))])
+    return Frame(frame.tables, textures, list(frame.passes) + [[fb]])
+
+
+def reftest_box_shadow_suite_composited_frame():
+    """reftest_box_shadow_suite_no_blur_frame through a picture-cache tile and the composite pass."""
+    return composited_through_tile(reftest_box_shadow_suite_no_blur_frame())
+
+
 def reftest_line_decorations_frame():
     """The first eight items of wrench/reftests/text/decorations-suite.yaml (rows 0-99 of decorations-suite.png; the
     reftest allows SWGL 3 on 13 540 pixels over the whole suite): horizontal lines 200 long, 1 / 2 / 3 / 6 thick —
