@@ -398,6 +398,53 @@ def test_sw_compositor_blit_math_against_swgl():
         assert (got == ref).all(), name
 
 
+def test_sw_compositor_blit_random_cases_against_swgl():
+    """Sixty seeded Composite calls (source / destination rects also partly outside, integer and fractional scale
+    ratios, opaque and over, flips, both filters, clips) — device functions on the host against the unmodified
+    reference: bytes equal."""
+    import ctypes as C
+    from oracle.backends import SwglDevice, have_swgl
+    if not have_swgl():
+        pytest.skip("oracle/_ref not built")
+    I4 = C.c_int32 * 4
+    rng = np.random.RandomState(77)
+    for i in range(60):
+        sw, sh = int(rng.randint(2, 300)), int(rng.randint(2, 200))
+        src = rng.randint(0, 256, (sh, sw, 4)).astype(np.uint8)
+        al = src[..., 3:4].astype(np.uint16)
+        src[..., :3] = (src[..., :3].astype(np.uint16) * al // 255).astype(np.uint8)
+        dst = rng.randint(0, 256, (360, 640, 4)).astype(np.uint8)
+        rw, rh = int(rng.randint(1, sw + 1)), int(rng.randint(1, sh + 1))
+        sr = (int(rng.randint(-5, sw - rw + 6)), int(rng.randint(-5, sh - rh + 6)), rw, rh)
+        if i % 4 == 0:
+            dr = (int(rng.randint(-20, 500)), int(rng.randint(-20, 300)), rw, rh)           # 1:1
+        elif i % 4 == 1:
+            k = int(rng.randint(2, 4))
+            dr = (int(rng.randint(-20, 300)), int(rng.randint(-20, 150)), rw * k, rh * k)   # integer upscale
+        else:
+            dr = (int(rng.randint(-20, 400)), int(rng.randint(-20, 250)), int(rng.randint(1, 500)), int(rng.randint(1, 300)))
+        cr = (0, 0, 640, 360) if i % 3 else (int(rng.randint(0, 300)), int(rng.randint(0, 150)), int(rng.randint(1, 400)), int(rng.randint(1, 250)))
+        opaque, fx, fy, lin = bool(rng.randint(0, 2)), bool(rng.randint(0, 2)), bool(rng.randint(0, 2)), bool(rng.randint(0, 2))
+        d = SwglDevice()
+        ts, td = d.texture_create(abi.FMT_RGBA8, sw, sh), d.texture_create(abi.FMT_RGBA8, 640, 360)
+        d.texture_upload(ts, 0, 0, sw, sh, src.reshape(sh, sw * 4))
+        d.texture_upload(td, 0, 0, 640, 360, dst.reshape(360, 2560))
+        d.sw_composite(td, ts, sr, dr, opaque, fx, fy, lin, cr)
+        ref = d.locked_pixels(td)
+        d.close()
+        e = EmuDevice()
+        es, ed = e.texture_create(abi.FMT_RGBA8, sw, sh), e.texture_create(abi.FMT_RGBA8, 640, 360)
+        e.texture_upload(es, 0, 0, sw, sh, src.reshape(sh, sw * 4))
+        e.texture_upload(ed, 0, 0, 640, 360, dst.reshape(360, 2560))
+        f = e.lib.wremu_composite_blit
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                      C.c_int, C.c_int, C.POINTER(C.c_int32)]
+        assert f(e.ctx, ed, es, I4(*sr), I4(*dr), int(opaque), int(fx), int(fy), int(lin), I4(*cr)) == 0
+        got = e.read_pixels(ed, 0, 0, 640, 360, 4)
+        e.close()
+        assert (got == ref).all(), (i, sr, dr, cr, opaque, fx, fy, lin, int((got != ref).sum()))
+
+
 def test_sw_compositor_yuv_blit_math_against_swgl():
     """wrcu_composite_blit_yuv's arithmetic (the device functions of csrc/blit_yuv.cuh, run on the host) against the
     unmodified reference's CompositeYUV (swgl/src/composite.h:1335-1384) — bytes equal.  (The GPU tier repeats this
@@ -426,6 +473,46 @@ def test_sw_compositor_yuv_blit_math_against_swgl():
         diff = got != ref
         assert not diff.any(), (case[0], int(diff.sum()), np.argwhere(diff)[:4].tolist())
         assert (got != planes[3]).any(), case[0]
+
+
+def test_sw_compositor_yuv_blit_random_cases_against_swgl():
+    """Eighty seeded CompositeYUV calls — plane sizes, chroma subsampling, source and destination rects (also partly
+    outside the planes / the target), flips, clips, colour spaces drawn at random — device functions on the host
+    against the unmodified reference: bytes equal."""
+    import ctypes as C
+    from oracle.backends import SwglDevice, have_swgl
+    import test_gl_shim as T
+    if not have_swgl():
+        pytest.skip("oracle/_ref not built")
+    I4 = C.c_int32 * 4
+
+    def via(e, td, ty, tu, tv, cs, sr, dr, fx, fy, cr):
+        f = e.lib.wremu_composite_blit_yuv
+        f.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_int, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                     C.c_int, C.c_int, C.POINTER(C.c_int32)]
+        assert f(e.ctx, td, ty, tu, tv, int(cs), 8, I4(*sr), I4(*dr), int(fx), int(fy), I4(*cr)) == 0
+
+    rng = np.random.RandomState(2024)
+    for i in range(80):
+        yw, yh = int(rng.randint(2 if i % 10 == 9 else 8, 400)), int(rng.randint(2, 300))
+        sub = [(1, 1), (2, 2), (2, 1)][int(rng.randint(0, 3))]
+        cw, ch = max(2, (yw + sub[0] - 1) // sub[0]), max(2, (yh + sub[1] - 1) // sub[1])
+        sx, sy = int(rng.randint(-10, yw // 2)), int(rng.randint(-8, yh // 2))
+        sw, sh = int(rng.randint(1, yw + 1)), int(rng.randint(1, yh + 1))
+        dx, dy = int(rng.randint(-40, 400)), int(rng.randint(-30, 250))
+        dw, dh = int(rng.randint(1, 700)), int(rng.randint(1, 400))
+        clip = (0, 0, 640, 360) if i % 3 else (int(rng.randint(0, 300)), int(rng.randint(0, 150)), int(rng.randint(1, 400)), int(rng.randint(1, 250)))
+        case = ("rand%d" % i, (yw, yh), (cw, ch), int(rng.randint(0, 7)), (sx, sy, sw, sh), (dx, dy, dw, dh),
+                bool(rng.randint(0, 2)), bool(rng.randint(0, 2)), clip)
+        planes = T.sw_yuv_planes(case)
+        d = SwglDevice()
+        ref = T.run_sw_composite_yuv(d, case, planes)
+        d.close()
+        e = EmuDevice()
+        got = T.run_sw_composite_yuv(e, case, planes, via=via)
+        e.close()
+        diff = got != ref
+        assert not diff.any(), (case, int(diff.sum()), np.argwhere(diff)[:4].tolist())
 
 
 # ---- perspective quads / plane-split polygons: against the reference build itself -------------------------
