@@ -2049,6 +2049,9 @@ PICTURE_REFTESTS = {
     # expected colour 0-255, allowed (max diff, pixels)).
     # filters/opacity.yaml == opacity-ref.yaml, fuzzy-if(platform(swgl),1,10000): "opacity pre-multiplied color"
     "opacity": ((255, 255, 255), (20, 20, 120, 120), "opacity", (255, 255, 0, 0.2), 0.9, None, (255, 255, 209), (1, 10000)),
+    # filters/opacity-overlap.yaml == opacity-overlap-ref.yaml, fuzzy-if(platform(swgl),1,10000): (0,0,128) at opacity 0.75
+    # over an opaque (128,0,0) rect
+    "opacity-overlap": ((255, 255, 255), (20, 20, 120, 120), "opacity", (0, 0, 128, 1.0), 0.75, (128, 0, 0), (32, 0, 96), (1, 10000)),
     # blend/multiply.yaml == multiply-ref.yaml: green x green = green
     "multiply": ((255, 255, 255), (25, 25, 75, 75), "mix", (0, 255, 0, 1.0), 1, (0, 255, 0), (0, 255, 0), (0, 0)),
     # blend/difference.yaml == difference-ref.yaml: green - green = black
@@ -2090,7 +2093,12 @@ def picture_reftest_frame(name, size=(140, 140)):
     ops = [Clear(color=tuple(v / 255.0 for v in bg) + (1.0,))]
     spec = t.push_gpu_cache([(0.0, 0.0, 0.0, 0.0)] * 3)
     if kind == "opacity":
-        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 1, spec, 0, pic, (source(), int(param * 65536.0), 0, 0))
+        if backdrop is not None:   # an opaque rect under the picture
+            baddr = t.push_gpu_cache([tuple(float(v) / 255.0 for v in backdrop) + (1.0,)])
+            bh = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 1, baddr, 0, pic, (65535, 0, 0, 0))
+            ops.append(Batch(abi.KIND_BRUSH_SOLID, brush_instance(bh, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
+                             blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS))
+        hdr = t.add_prim_header(rect, (-1e9, -1e9, 1e9, 1e9), 2, spec, 0, pic, (source(), int(param * 65536.0), 0, 0))
         ops.append(Batch(abi.KIND_BRUSH_OPACITY, brush_instance(hdr, CLIP_TASK_EMPTY, 0xFFFF, 0, 0, 0)[None, :],
                          blend=abi.BLEND_PREMULTIPLIED_ALPHA, features=abi.FEAT_ALPHA_PASS, color=("surface", "", "")))
     elif kind == "adv":
