@@ -543,7 +543,7 @@ def test_perspective_brushes(kind, cam):
     assert_same(render(EmuDevice, f, ["target"]), render(_swgl(), f, ["target"]), f"{kind} {cam}")
 
 
-@pytest.mark.parametrize("cam", PERSP_CAMERAS[1:3])
+@pytest.mark.parametrize("cam", PERSP_CAMERAS)
 @pytest.mark.parametrize("kind", ["opacity", "blend", "mix_blend"])
 def test_perspective_picture_brushes(kind, cam):
     """brush_opacity / brush_blend / brush_mix_blend drawing a picture's surface under a perspective node: fragment
